@@ -1,0 +1,96 @@
+"""ctypes binding of libfeaturecraft_b200.so (the C ABI declared in include/featurecraft_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+Build it with ``python exvision_featurecraft_b200/csrc/build.py`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfeaturecraft_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "featurecraft_b200.h")
+
+FC_OK = 0
+FC_F32, FC_F64 = 0, 1
+FC_FILTER_APP, FC_FILTER_SCRIPT = 0, 1
+
+
+class FeatureCraftError(RuntimeError):
+    pass
+
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_d = C.c_double
+
+#: name -> (restype, argtypes); must list every function the header declares
+SIGNATURES = {
+    "fc_version": (_i, []),
+    "fc_status_string": (C.c_char_p, [_i]),
+    "fc_last_cuda_error": (_i, []),
+    "fc_launch_count": (C.c_ulonglong, []),
+    "fc_rgb_to_gray_u8": (_i, [_p, _i, _i, _i, _p, _p]),
+    "fc_correlate_zero_pad_f64": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
+    "fc_harris_response": (_i, [_p, _i, _i, _i, _i, _d, _d, _p, _p, _p]),
+    "fc_notebook_harris_response": (_i, [_p, _i, _i, _i, _i, _d, _p, _p]),
+    "fc_lambda_minus_response": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "fc_threshold_mask_abs": (_i, [_p, _i, _i, _i, _d, _i, _p, _p]),
+    "fc_threshold_mask_rel": (_i, [_p, _i, _i, _i, _d, _p, _p, _p]),
+    "fc_scan_scratch_elems": (_i64, [_i64]),
+    "fc_mask_scan": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "fc_mask_emit": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "fc_gauss_octave": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _d, _d, _p, _p, _p]),
+    "fc_downsample2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "fc_convert_f64": (_i, [_p, _i64, _i, _p, _p]),
+    "fc_gradient_field": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fc_orientation_bins": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p]),
+    "fc_orientation_scan": (_i, [_p, _i, _p, _p, _p]),
+    "fc_orientation_emit": (_i, [_p, _p, _p, _i, _p, _p]),
+    "fc_descriptors": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
+    "fc_match_workspace_bytes": (_i64, [_i, _i]),
+    "fc_match_knn2": (_i, [_p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),
+    "fc_match_knn2_exact": (_i, [_p, _i, _p, _i, _d, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; raise (never fall back) if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FeatureCraftError(
+            "libfeaturecraft_b200.so is not built (%s). Run `python exvision_featurecraft_b200/csrc/build.py`; "
+            "this package has no CPU or PyTorch fallback." % LIB_PATH
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != FC_OK:
+        lib = load()
+        msg = lib.fc_status_string(status).decode()
+        extra = ""
+        if status == -3:
+            extra = " (cudaError %d)" % lib.fc_last_cuda_error()
+        raise FeatureCraftError("%s failed: %s%s" % (what, msg, extra))
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise on a non-zero status."""
+    check(getattr(load(), name)(*args), name)
+
+
+def launch_count() -> int:
+    return int(load().fc_launch_count())

@@ -1,0 +1,138 @@
+"""Batched, device-resident corner detectors (Harris / lambda-minus) over the C ABI.
+
+These are the drivers the reference-shaped functions in ``backend.py`` sit on, and what the
+benchmarks call: inputs and outputs are CUDA tensors, nothing synchronises except the one read of
+the corner count that sizes the output list.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from .device import ptr, require_cuda, scan_scratch, stream_ptr, to_device
+
+
+@dataclass
+class CornerResult:
+    """response: [B,H,W] float64; mask: [B,H,ceil(W/32)] int32 bit mask of response > threshold;
+    coords: [N,2] int32 (row, col) in np.argwhere order, images concatenated; values: [N] float64;
+    image_offsets: [B+1] int64 -- corners of image b are coords[image_offsets[b]:image_offsets[b+1]];
+    image_max: [B] float64 (lambda-minus only)."""
+
+    response: torch.Tensor
+    mask: torch.Tensor | None = None
+    coords: torch.Tensor | None = None
+    values: torch.Tensor | None = None
+    image_offsets: torch.Tensor | None = None
+    image_max: torch.Tensor | None = None
+
+
+def _as_gray_batch(gray) -> torch.Tensor:
+    g = to_device(gray)
+    if g.dtype != torch.uint8:
+        raise TypeError("gray images must be uint8 (convert_to_gray output)")
+    if g.dim() == 2:
+        g = g.unsqueeze(0)
+    if g.dim() != 3:
+        raise ValueError("expected [H,W] or [B,H,W] gray images")
+    return g.contiguous()
+
+
+def rgb_to_gray(rgb) -> torch.Tensor:
+    """convert_to_gray on the device: [B,H,W,3] or [H,W,3] uint8 -> uint8 gray."""
+    t = to_device(rgb)
+    single = t.dim() == 3
+    if single:
+        t = t.unsqueeze(0)
+    if t.dim() != 4 or t.shape[-1] < 3 or t.dtype != torch.uint8:
+        raise ValueError("expected uint8 [..., H, W, >=3]")
+    t = t[..., :3].contiguous()
+    b, h, w, _ = t.shape
+    out = torch.empty((b, h, w), dtype=torch.uint8, device=t.device)
+    _lib.call("fc_rgb_to_gray_u8", ptr(t), b, h, w, ptr(out), stream_ptr())
+    return out[0] if single else out
+
+
+def compact_mask(mask: torch.Tensor, width: int, response: torch.Tensor | None = None):
+    """np.argwhere order compaction of a [B,H,pitch] bit mask -> (coords, values, image_offsets)."""
+    b, h, _ = mask.shape
+    rows = b * h
+    row_offsets = torch.empty(rows + 1, dtype=torch.int32, device=mask.device)
+    scratch = scan_scratch(rows)
+    _lib.call("fc_mask_scan", ptr(mask), b, h, width, ptr(row_offsets), ptr(scratch), stream_ptr())
+    image_offsets = row_offsets[::h].to(torch.int64)  # B+1 entries, still on the device
+    total = int(row_offsets[-1].item())  # the one host sync: sizes the output
+    coords = torch.empty((total, 2), dtype=torch.int32, device=mask.device)
+    values = torch.empty(total, dtype=torch.float64, device=mask.device) if response is not None else None
+    if total:
+        _lib.call("fc_mask_emit", ptr(mask), ptr(row_offsets), b, h, width, ptr(response), ptr(coords), ptr(values),
+                  stream_ptr())
+    return coords, values, image_offsets
+
+
+def _new_mask(b, h, w, device):
+    return torch.empty((b, h, (w + 31) // 32), dtype=torch.int32, device=device)
+
+
+def harris(gray, window_size: int = 5, k: float = 0.04, threshold: float | None = 10000, compact: bool = True,
+           out: torch.Tensor | None = None) -> CornerResult:
+    """Harris response (reference arithmetic, bit-exact) + optional threshold / compaction."""
+    if window_size % 2 == 0:
+        raise ValueError("cannot reshape array: window_size must be odd (reference fails the same way)")
+    g = _as_gray_batch(gray)
+    b, h, w = g.shape
+    if h < 2 or w < 2:
+        raise ValueError(
+            "Shape of array too small to calculate a numerical gradient, at least (edge_order + 1) elements are required."
+        )
+    resp = out if out is not None else torch.empty((b, h, w), dtype=torch.float64, device=g.device)
+    mask = _new_mask(b, h, w, g.device) if threshold is not None else None
+    _lib.call("fc_harris_response", ptr(g), b, h, w, int(window_size), float(k),
+              float(threshold if threshold is not None else 0.0), ptr(resp), ptr(mask), stream_ptr())
+    res = CornerResult(resp, mask)
+    if mask is not None and compact:
+        res.coords, res.values, res.image_offsets = compact_mask(mask, w, resp)
+    return res
+
+
+def notebook_harris(gray, window_size: int, k: float, threshold: float, compact: bool = True) -> CornerResult:
+    """harris.ipynb variant: K_X gradient, corners only for offset <= y < H-offset."""
+    g = _as_gray_batch(gray)
+    b, h, w = g.shape
+    resp = torch.empty((b, h, w), dtype=torch.float64, device=g.device)
+    _lib.call("fc_notebook_harris_response", ptr(g), b, h, w, int(window_size), float(k), ptr(resp), stream_ptr())
+    mask = _new_mask(b, h, w, g.device)
+    _lib.call("fc_threshold_mask_abs", ptr(resp), b, h, w, float(threshold), int(window_size / 2), ptr(mask), stream_ptr())
+    res = CornerResult(resp, mask)
+    if compact:
+        res.coords, res.values, res.image_offsets = compact_mask(mask, w, resp)
+    return res
+
+
+def lambda_minus(gray, threshold_percentage: float | None = 0.01, compact: bool = True) -> CornerResult:
+    """lambda-minus (min eigenvalue) map, per-image max, and map > pct * max."""
+    g = _as_gray_batch(gray)
+    b, h, w = g.shape
+    eig = torch.empty((b, h, w), dtype=torch.float64, device=g.device)
+    image_max = torch.empty(b, dtype=torch.float64, device=g.device)
+    _lib.call("fc_lambda_minus_response", ptr(g), b, h, w, ptr(eig), ptr(image_max), stream_ptr())
+    res = CornerResult(eig, image_max=image_max)
+    if threshold_percentage is not None:
+        res.mask = _new_mask(b, h, w, g.device)
+        _lib.call("fc_threshold_mask_rel", ptr(eig), b, h, w, float(threshold_percentage), ptr(image_max), ptr(res.mask),
+                  stream_ptr())
+        if compact:
+            res.coords, res.values, res.image_offsets = compact_mask(res.mask, w, eig)
+    return res
+
+
+def rethreshold(response: torch.Tensor, threshold: float, border: int = 0):
+    """on_changing_threshold (APP/FeatureCraft_Backend.py:261-292): re-threshold a resident map with
+    an ABSOLUTE value (the reference compares eigenvalues to slider/10000, not to a percentage)."""
+    r = response if response.dim() == 3 else response.unsqueeze(0)
+    b, h, w = r.shape
+    mask = _new_mask(b, h, w, r.device)
+    _lib.call("fc_threshold_mask_abs", ptr(r), b, h, w, float(threshold), int(border), ptr(mask), stream_ptr())
+    return compact_mask(mask, w, r)

@@ -1,0 +1,594 @@
+// Harris / lambda-minus corner response kernels (sm_100a).
+//
+//   harris5_strip_kernel   app Harris, 5x5 window (the reference default and the benchmarked config):
+//                          register-resident sliding-window kernel, no shared memory, one warp per
+//                          128-column strip, 4 pixels per thread, exact integer arithmetic in fp32.
+//   corner_tiled_kernel    every other combination (any odd window <= 31, K_X gradient, lambda-minus):
+//                          shared-memory tiled, exact integer sums.
+//
+// Reference arithmetic: APP/FeatureCraft_Backend.py:336-355 (Harris), :402-437 (lambda-minus),
+// implementation_without_ui/Corner Detection/harris.ipynb:150-190 (notebook Harris).
+// HBM traffic per pixel: 1 B gray in + 8 B float64 response out (+ 1 bit mask).
+#include "fc_common.cuh"
+
+namespace fc {
+
+enum { GRAD_CENTRAL = 0, GRAD_KX = 1 };
+enum { RESP_HARRIS = 0, RESP_LAMBDA_MINUS = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: Harris, np.gradient, 5x5 window
+// ------------------------------------------------------------------------------------------------
+//
+// All quantities are kept in units that make them integers: g2 = 2*gradient (|g2| <= 510), products
+// p = g2*g2 (<= 260100), 5-tap row sums (<= 1.3e6), 5x5 sums A, B, C (<= 6.6e6 < 2^24) -- so every
+// fp32 operation below is exact and FFMA contraction cannot change a bit.  With Sxx = A/4, Sxy = B/4,
+// Syy = C/4 the reference's R = (Sxx*Syy - Sxy^2) - k*(Sxx+Syy)^2 equals
+//   R = ( (A*C - B*B) - rn(k * (A+C)^2) ) / 16
+// because A*C, B*B, (A+C)^2 < 2^53 are exact in float64, det and trace^2 are therefore exact in the
+// reference too, scaling by 2^-4 commutes with rounding, and exactly two roundings remain (k*tr^2 and
+// the final subtraction), performed here with __dmul_rn / __dsub_rn.
+
+struct Row3 {
+  uint32_t w[3];  // bytes of columns c0-4 .. c0+7 of one image row
+};
+
+__device__ __forceinline__ Row3 load_row3(const uint8_t* __restrict__ img, int row, int H, int W, int c0) {
+  row = min(max(row, 0), H - 1);
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (size_t)row * W);
+  const int wi = c0 >> 2;
+  const int nw = W >> 2;
+  Row3 r;
+  r.w[0] = (wi - 1 >= 0 && wi - 1 < nw) ? __ldg(p + wi - 1) : 0u;
+  r.w[1] = (wi < nw) ? __ldg(p + wi) : 0u;
+  r.w[2] = (wi + 1 < nw) ? __ldg(p + wi + 1) : 0u;
+  return r;
+}
+
+// float value of column c0 - 4 + k (k = 0..11) of a packed row
+__device__ __forceinline__ float col_f(const Row3& r, int k) {
+  return (float)((r.w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+}
+
+// Horizontal 5-tap sums of the three products for output columns c0..c0+3 of image row `row`.
+// h[0..3] = xx, h[4..7] = xy, h[8..11] = yy.   INTERIOR: no image border within reach.
+template <bool INTERIOR>
+__device__ __forceinline__ void harris_row_sums(const Row3& up, const Row3& mid, const Row3& dn, int row, int H, int W,
+                                                int c0, float (&h)[12]) {
+  float gx[8], gy[8];  // product columns c0-2 .. c0+5  <->  k = 2 .. 9
+  if (INTERIOR) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      gx[i] = col_f(dn, i + 2) - col_f(up, i + 2);
+      gy[i] = col_f(mid, i + 3) - col_f(mid, i + 1);
+    }
+  } else {
+    // rows were clamped when loaded, so dn - up is the one-sided difference on the first / last row
+    const float sy = (row == 0 || row == H - 1) ? 2.0f : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 - 2 + i;
+      const bool inside = (c >= 0) && (c < W);
+      float vx = sy * (col_f(dn, i + 2) - col_f(up, i + 2));
+      float vy;
+      if (c == 0) vy = 2.0f * (col_f(mid, i + 3) - col_f(mid, i + 2));
+      else if (c == W - 1) vy = 2.0f * (col_f(mid, i + 2) - col_f(mid, i + 1));
+      else vy = col_f(mid, i + 3) - col_f(mid, i + 1);
+      gx[i] = inside ? vx : 0.0f;
+      gy[i] = inside ? vy : 0.0f;
+    }
+  }
+  // sliding 5-tap sums; products are folded into FFMAs (exact, see header comment)
+  float xx = gx[0] * gx[0], xy = gx[0] * gy[0], yy = gy[0] * gy[0];
+#pragma unroll
+  for (int i = 1; i < 5; ++i) {
+    xx = fmaf(gx[i], gx[i], xx);
+    xy = fmaf(gx[i], gy[i], xy);
+    yy = fmaf(gy[i], gy[i], yy);
+  }
+  h[0] = xx; h[4] = xy; h[8] = yy;
+#pragma unroll
+  for (int j = 1; j < 4; ++j) {
+    xx = fmaf(gx[j + 4], gx[j + 4], fmaf(-gx[j - 1], gx[j - 1], xx));
+    xy = fmaf(gx[j + 4], gy[j + 4], fmaf(-gx[j - 1], gy[j - 1], xy));
+    yy = fmaf(gy[j + 4], gy[j + 4], fmaf(-gy[j - 1], gy[j - 1], yy));
+    h[j] = xx; h[4 + j] = xy; h[8 + j] = yy;
+  }
+}
+
+__device__ __forceinline__ double harris_from_quarter_sums(float a, float b, float c, double k) {
+  const double da = (double)a, db = (double)b, dc = (double)c;
+  const double det16 = fma(-db, db, da * dc);  // exact
+  const double tr = (double)(a + c);           // a + c < 2^24: exact in fp32
+  const double t = __dmul_rn(k, tr * tr);      // tr*tr exact
+  return __dsub_rn(det16, t) * 0.0625;
+}
+
+static constexpr int kStripWarps = 4;
+static constexpr int kStripCols = 128;  // per warp
+
+__global__ void __launch_bounds__(kStripWarps * 32)
+harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double k, double thr,
+                     double* __restrict__ out, uint32_t* __restrict__ mask, int mask_pitch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * kStripWarps + warp;
+  const int strip_c0 = strip * kStripCols;
+  if (strip_c0 >= W) return;  // warp-uniform
+  const int c0 = strip_c0 + lane * 4;
+  const bool active = c0 < W;
+  const size_t img_off = (size_t)blockIdx.z * H * W;
+  const uint8_t* img = gray + img_off;
+  double* o = out + img_off;
+  uint32_t* m = mask ? mask + (size_t)blockIdx.z * H * mask_pitch : nullptr;
+  const int y0 = blockIdx.y * rows_per_band;
+  const int y1 = min(y0 + rows_per_band, H);
+  // product columns of the whole strip are c in [strip_c0 - 2, strip_c0 + 129]; they all need
+  // 1 <= c <= W-2 for the border-free code path
+  const bool cols_interior = (strip_c0 - 2 >= 1) && (strip_c0 + kStripCols + 1 <= W - 2);
+
+  float ring[5][12];
+  float S[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    S[i] = 0.0f;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) ring[s][i] = 0.0f;
+  }
+  Row3 up = load_row3(img, y0 - 3, H, W, c0);
+  Row3 mid = load_row3(img, y0 - 2, H, W, c0);
+  Row3 dn = load_row3(img, y0 - 1, H, W, c0);
+
+  for (int base = y0 - 2; base <= y1 + 1; base += 5) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const int hr = base + s;  // image row whose horizontal sums are produced now
+      if (hr > y1 + 1) break;
+      const Row3 nxt = load_row3(img, hr + 2, H, W, c0);  // prefetch for the next iteration
+      float h[12];
+      if (hr < 0 || hr >= H) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) h[i] = 0.0f;
+      } else if (cols_interior && hr >= 1 && hr <= H - 2) {
+        harris_row_sums<true>(up, mid, dn, hr, H, W, c0, h);
+      } else {
+        harris_row_sums<false>(up, mid, dn, hr, H, W, c0, h);
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        S[i] += h[i] - ring[s][i];
+        ring[s][i] = h[i];
+      }
+      const int r = hr - 2;  // rows r-2 .. r+2 are now summed
+      if (r >= y0) {
+        double res[4];
+        uint32_t nib = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          res[j] = harris_from_quarter_sums(S[j], S[4 + j], S[8 + j], k);
+          nib |= (res[j] > thr) ? (1u << j) : 0u;
+        }
+        if (active) {
+          double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
+          __stcs(dst, make_double2(res[0], res[1]));
+          __stcs(dst + 1, make_double2(res[2], res[3]));
+        }
+        if (m) {
+          uint32_t v = active ? (nib << (4 * (lane & 7))) : 0u;
+          v |= __shfl_xor_sync(0xffffffffu, v, 1);
+          v |= __shfl_xor_sync(0xffffffffu, v, 2);
+          v |= __shfl_xor_sync(0xffffffffu, v, 4);
+          if ((lane & 7) == 0 && active) m[(size_t)r * mask_pitch + (c0 >> 5)] = v;
+        }
+      }
+      up = mid;
+      mid = dn;
+      dn = nxt;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// General path: shared-memory tiled, any odd window <= 31, both gradients, both responses
+// ------------------------------------------------------------------------------------------------
+static constexpr int kTileX = 32;
+static constexpr int kTileY = 16;
+static constexpr int kTiledThreads = 256;
+
+__device__ __forceinline__ int kx_a(int d) { return d == 2 ? 3 : (d == 1 || d == 3) ? 2 : 1; }  // 1 2 3 2 1
+__device__ __forceinline__ int kx_b(int d) { return d == 2 ? 5 : (d == 1 || d == 3) ? 3 : 2; }  // 2 3 5 3 2
+
+template <int GRAD>
+__global__ void __launch_bounds__(kTiledThreads)
+corner_tiled_kernel(const uint8_t* __restrict__ gray, int H, int W, int R, int resp, double k,
+                    double* __restrict__ out, unsigned long long* __restrict__ img_max_bits) {
+  constexpr int G = (GRAD == GRAD_KX) ? 2 : 1;  // gradient reach
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int gw = kTileX + 2 * R, gh = kTileY + 2 * R;  // gradient tile
+  const int iw = gw + 2 * G, ih = gh + 2 * G;          // intensity tile
+  int* sI = reinterpret_cast<int*>(smem_raw);          // ih * iw
+  int* sGx = sI + ih * iw;                             // gh * gw
+  int* sGy = sGx + gh * gw;                            // gh * gw
+  int* sH = sGy + gh * gw;                             // 3 * gh * kTileX
+  const size_t img_off = (size_t)blockIdx.z * H * W;
+  const uint8_t* img = gray + img_off;
+  const int x0 = blockIdx.x * kTileX, y0 = blockIdx.y * kTileY;
+
+  // 1. intensities.  CENTRAL: clamped coordinates (np.gradient's one-sided edges fall out of the
+  //    clamp + a factor 2); KX: zeros outside the image (padding_matrix).
+  for (int t = threadIdx.x; t < ih * iw; t += kTiledThreads) {
+    const int ly = t / iw, lx = t - ly * iw;
+    int y = y0 - R - G + ly, x = x0 - R - G + lx;
+    int v;
+    if (GRAD == GRAD_CENTRAL) {
+      y = min(max(y, 0), H - 1);
+      x = min(max(x, 0), W - 1);
+      v = img[(size_t)y * W + x];
+    } else {
+      v = (y >= 0 && y < H && x >= 0 && x < W) ? (int)img[(size_t)y * W + x] : 0;
+    }
+    sI[t] = v;
+  }
+  __syncthreads();
+  // 2. gradients on the (gh x gw) tile; zero outside the image (the window sum is zero padded)
+  for (int t = threadIdx.x; t < gh * gw; t += kTiledThreads) {
+    const int ly = t / gw, lx = t - ly * gw;
+    const int y = y0 - R + ly, x = x0 - R + lx;
+    int gx = 0, gy = 0;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const int* c = sI + (ly + G) * iw + (lx + G);
+      if (GRAD == GRAD_CENTRAL) {
+        // 2 * np.gradient: axis 0 first (named Ix in the reference), then axis 1
+        gx = (c[iw] - c[-iw]) * ((y == 0 || y == H - 1) ? 2 : 1);
+        gy = (c[1] - c[-1]) * ((x == 0 || x == W - 1) ? 2 : 1);
+      } else {
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+          const int* rr = c + (d - 2) * iw;
+          gx += kx_a(d) * (rr[2] - rr[-2]) + kx_b(d) * (rr[1] - rr[-1]);          // K_X
+          gy += kx_a(d) * (c[2 * iw + d - 2] - c[-2 * iw + d - 2]) +
+                kx_b(d) * (c[iw + d - 2] - c[-iw + d - 2]);                        // K_X^T
+        }
+      }
+    }
+    sGx[t] = gx;
+    sGy[t] = gy;
+  }
+  __syncthreads();
+  // 3. horizontal window sums of the products (int32: (2R+1) * 6120^2 < 2^31 for R <= 15)
+  for (int t = threadIdx.x; t < gh * kTileX; t += kTiledThreads) {
+    const int ly = t / kTileX, lx = t - ly * kTileX;
+    const int* px = sGx + ly * gw + lx;
+    const int* py = sGy + ly * gw + lx;
+    int xx = 0, xy = 0, yy = 0;
+    for (int d = 0; d <= 2 * R; ++d) {
+      const int a = px[d], b = py[d];
+      xx += a * a;
+      xy += a * b;
+      yy += b * b;
+    }
+    sH[t] = xx;
+    sH[gh * kTileX + t] = xy;
+    sH[2 * gh * kTileX + t] = yy;
+  }
+  __syncthreads();
+  // 4. vertical sums (int64) + response
+  double local_max = -INFINITY;
+  for (int t = threadIdx.x; t < kTileY * kTileX; t += kTiledThreads) {
+    const int ly = t / kTileX, lx = t - ly * kTileX;
+    const int y = y0 + ly, x = x0 + lx;
+    if (y >= H || x >= W) continue;
+    long long a = 0, b = 0, c = 0;
+    for (int d = 0; d <= 2 * R; ++d) {
+      const int idx = (ly + d) * kTileX + lx;
+      a += sH[idx];
+      b += sH[gh * kTileX + idx];
+      c += sH[2 * gh * kTileX + idx];
+    }
+    // CENTRAL sums are in quarter units (exact scaling); KX sums are the reference's integers
+    const double scale = (GRAD == GRAD_CENTRAL) ? 0.25 : 1.0;
+    double sxx = (double)a * scale, sxy = (double)b * scale, syy = (double)c * scale;
+    double r;
+    if (resp == RESP_HARRIS) {
+      r = harris_from_sums(sxx, sxy, syy, k);
+    } else {
+      r = dsterf_2x2_min(__ddiv_rn(sxx, 25.0), __ddiv_rn(sxy, 25.0), __ddiv_rn(syy, 25.0));
+      local_max = fmax(local_max, r);
+    }
+    out[img_off + (size_t)y * W + x] = r;
+  }
+  if (resp == RESP_LAMBDA_MINUS && img_max_bits) {
+    local_max = warp_max(local_max);
+    if ((threadIdx.x & 31) == 0 && local_max > -INFINITY)
+      atomicMax(img_max_bits + blockIdx.z, ordered_bits(local_max));
+  }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, int n, unsigned long long v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void decode_max_kernel(unsigned long long* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) reinterpret_cast<double*>(p)[i] = from_ordered_bits(p[i]);
+}
+
+static size_t tiled_smem_bytes(int R, int G) {
+  const int gw = kTileX + 2 * R, gh = kTileY + 2 * R;
+  const int iw = gw + 2 * G, ih = gh + 2 * G;
+  return sizeof(int) * ((size_t)ih * iw + 2 * (size_t)gh * gw + 3 * (size_t)gh * kTileX);
+}
+
+template <int GRAD>
+static int launch_tiled(const uint8_t* gray, int B, int H, int W, int R, int resp, double k, double* out,
+                        unsigned long long* max_bits, cudaStream_t st) {
+  const size_t smem = tiled_smem_bytes(R, GRAD == GRAD_KX ? 2 : 1);
+  FC_CUDA_TRY(cudaFuncSetAttribute(corner_tiled_kernel<GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(div_up(W, kTileX), div_up(H, kTileY), B);
+  corner_tiled_kernel<GRAD><<<grid, kTiledThreads, smem, st>>>(gray, H, W, R, resp, k, out, max_bits);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gray conversion, thresholds, compaction
+// ------------------------------------------------------------------------------------------------
+__global__ void rgb_to_gray_kernel(const uint8_t* __restrict__ rgb, int64_t n, uint8_t* __restrict__ gray) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+  // np.dot over the 3 channels, left to right, then the truncating astype(uint8)
+  const double v = __dadd_rn(__dadd_rn(__dmul_rn(r, 0.2989), __dmul_rn(g, 0.5870)), __dmul_rn(b, 0.1140));
+  gray[i] = (uint8_t)(int)v;
+}
+
+// one warp per (image row, 32-column word)
+__global__ void threshold_mask_kernel(const double* __restrict__ map, int B, int H, int W, double thr_abs,
+                                      double fraction, const double* __restrict__ image_max, int border,
+                                      uint32_t* __restrict__ mask, int pitch) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)B * H * pitch;
+  if (warp >= total) return;
+  const int word = (int)(warp % pitch);
+  const int64_t row_g = warp / pitch;
+  const int y = (int)(row_g % H);
+  const int b = (int)(row_g / H);
+  const double thr = image_max ? __dmul_rn(fraction, image_max[b]) : thr_abs;
+  const int x = word * 32 + lane;
+  bool hit = false;
+  if (x < W && y >= border && y < H - border && x >= border && x < W - border) hit = map[row_g * W + x] > thr;
+  const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) mask[warp] = bits;
+}
+
+// one thread per mask row: popcount of the row
+__global__ void mask_row_count_kernel(const uint32_t* __restrict__ mask, int64_t rows, int pitch,
+                                      int32_t* __restrict__ counts) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  int c = 0;
+  for (int w = lane; w < pitch; w += 32) c += __popc(mask[warp * pitch + w]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) counts[warp] = c;
+}
+
+// one warp per mask row: ordered emission of (row, col) and the gathered map values
+__global__ void mask_emit_kernel(const uint32_t* __restrict__ mask, const int32_t* __restrict__ row_offsets,
+                                 int64_t rows, int H, int W, int pitch, const double* __restrict__ map,
+                                 int32_t* __restrict__ coords, double* __restrict__ values) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  int base = row_offsets[warp];
+  if (row_offsets[warp + 1] == base) return;
+  const int y = (int)(warp % H);
+  for (int w0 = 0; w0 < pitch; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t bits = (w < pitch) ? mask[warp * pitch + w] : 0u;
+    const int cnt = __popc(bits);
+    const int inc = warp_inclusive_scan(cnt);
+    int pos = base + inc - cnt;
+    while (bits) {
+      const int bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int x = w * 32 + bit;
+      coords[2 * (size_t)pos] = y;
+      coords[2 * (size_t)pos + 1] = x;
+      if (values) values[pos] = map[warp * W + x];
+      ++pos;
+    }
+    base += __shfl_sync(0xffffffffu, inc, 31);
+  }
+}
+
+}  // namespace fc
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace fc;
+
+static bool bad_image_args(const void* p, int B, int H, int W) { return !p || B <= 0 || H <= 0 || W <= 0; }
+
+extern "C" int fc_rgb_to_gray_u8(const uint8_t* rgb, int batch, int height, int width, uint8_t* gray, void* stream) {
+  if (bad_image_args(rgb, batch, height, width) || !gray) return FC_ERR_BAD_ARG;
+  const int64_t n = (int64_t)batch * height * width;
+  rgb_to_gray_kernel<<<(unsigned)div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(rgb, n, gray);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_harris_response(const uint8_t* gray, int batch, int height, int width, int window_size, double k,
+                                  double threshold, double* response, uint32_t* mask, void* stream) {
+  if (bad_image_args(gray, batch, height, width) || !response) return FC_ERR_BAD_ARG;
+  if (window_size < 1 || window_size > 31 || (window_size & 1) == 0) return FC_ERR_BAD_ARG;
+  if (height < 2 || width < 2) return FC_ERR_BAD_ARG;  // np.gradient needs two samples per axis
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pitch = div_up(width, 32);
+  const bool aligned = (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(gray) & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(response) & 15) == 0);
+  if (window_size == 5 && aligned) {
+    // band height: amortise the 6 halo rows, but keep enough warps in flight on small inputs
+    const int strips = div_up(width, kStripCols);
+    int rows = 64;
+    while (rows > 8 && (int64_t)strips * div_up(height, rows) * batch < 148 * 16) rows >>= 1;
+    dim3 grid(div_up(strips, kStripWarps), div_up(height, rows), batch);
+    harris5_strip_kernel<<<grid, kStripWarps * 32, 0, st>>>(gray, height, width, rows, k, threshold, response, mask,
+                                                           pitch);
+    note_launch();
+    FC_RETURN_IF_LAUNCH_FAILED();
+    return FC_OK;
+  }
+  int rc = launch_tiled<GRAD_CENTRAL>(gray, batch, height, width, window_size / 2, RESP_HARRIS, k, response, nullptr, st);
+  if (rc != FC_OK) return rc;
+  if (mask) return fc_threshold_mask_abs(response, batch, height, width, threshold, 0, mask, stream);
+  return FC_OK;
+}
+
+extern "C" int fc_notebook_harris_response(const uint8_t* gray, int batch, int height, int width, int window_size,
+                                           double k, double* response, void* stream) {
+  if (bad_image_args(gray, batch, height, width) || !response) return FC_ERR_BAD_ARG;
+  if (window_size < 1 || window_size > 31 || (window_size & 1) == 0) return FC_ERR_BAD_ARG;
+  return launch_tiled<GRAD_KX>(gray, batch, height, width, window_size / 2, RESP_HARRIS, k, response, nullptr,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int height, int width, double* eig,
+                                        double* image_max, void* stream) {
+  if (bad_image_args(gray, batch, height, width) || !eig) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* bits = reinterpret_cast<unsigned long long*>(image_max);
+  if (bits) {
+    fill_u64_kernel<<<div_up(batch, 256), 256, 0, st>>>(bits, batch, 0ull);
+    note_launch();
+    FC_RETURN_IF_LAUNCH_FAILED();
+  }
+  int rc = launch_tiled<GRAD_KX>(gray, batch, height, width, 2, RESP_LAMBDA_MINUS, 0.0, eig, bits, st);
+  if (rc != FC_OK) return rc;
+  if (bits) {
+    decode_max_kernel<<<div_up(batch, 256), 256, 0, st>>>(bits, batch);
+    note_launch();
+    FC_RETURN_IF_LAUNCH_FAILED();
+  }
+  return FC_OK;
+}
+
+static int launch_threshold(const double* map, int B, int H, int W, double thr, double frac, const double* image_max,
+                            int border, uint32_t* mask, cudaStream_t st) {
+  if (bad_image_args(map, B, H, W) || !mask || border < 0) return FC_ERR_BAD_ARG;
+  const int pitch = div_up(W, 32);
+  const int64_t warps = (int64_t)B * H * pitch;
+  threshold_mask_kernel<<<(unsigned)div_up64(warps * 32, 256), 256, 0, st>>>(map, B, H, W, thr, frac, image_max, border,
+                                                                           mask, pitch);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_threshold_mask_abs(const double* map, int batch, int height, int width, double threshold, int border,
+                                     uint32_t* mask, void* stream) {
+  return launch_threshold(map, batch, height, width, threshold, 0.0, nullptr, border, mask, (cudaStream_t)stream);
+}
+
+extern "C" int fc_threshold_mask_rel(const double* map, int batch, int height, int width, double fraction,
+                                     const double* image_max, uint32_t* mask, void* stream) {
+  if (!image_max) return FC_ERR_BAD_ARG;
+  return launch_threshold(map, batch, height, width, 0.0, fraction, image_max, 0, mask, (cudaStream_t)stream);
+}
+
+extern "C" int64_t fc_scan_scratch_elems(int64_t n) { return n + scan_scratch_elems(n); }
+
+extern "C" int fc_mask_scan(const uint32_t* mask, int batch, int height, int width, int32_t* row_offsets,
+                            int32_t* scratch, void* stream) {
+  if (bad_image_args(mask, batch, height, width) || !row_offsets || !scratch) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)batch * height;
+  const int pitch = div_up(width, 32);
+  mask_row_count_kernel<<<(unsigned)div_up64(rows * 32, 256), 256, 0, st>>>(mask, rows, pitch, scratch);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return exclusive_scan_i32(scratch, rows, row_offsets, scratch + rows, st);
+}
+
+extern "C" int fc_mask_emit(const uint32_t* mask, const int32_t* row_offsets, int batch, int height, int width,
+                            const double* map, int32_t* coords, double* values, void* stream) {
+  if (bad_image_args(mask, batch, height, width) || !row_offsets || !coords) return FC_ERR_BAD_ARG;
+  if (values && !map) return FC_ERR_BAD_ARG;
+  const int64_t rows = (int64_t)batch * height;
+  mask_emit_kernel<<<(unsigned)div_up64(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      mask, row_offsets, rows, height, width, div_up(width, 32), map, coords, values);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// convolve2d_optimized (APP/utils/harris_utils.py:33-80) for arbitrary float64 data
+// ------------------------------------------------------------------------------------------------
+namespace fc {
+
+struct WindowProducts {
+  const double* img;
+  const double* ker;
+  int H, W, ks, pad, y, x;
+  __device__ __forceinline__ double operator()(int i) const {
+    const int dy = i / ks, dx = i - dy * ks;
+    const int yy = y + dy - pad, xx = x + dx - pad;
+    const double v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[(size_t)yy * W + xx] : 0.0;
+    return __dmul_rn(v, ker[i]);
+  }
+};
+
+// numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src, pairwise_sum_DOUBLE) -- the
+// reduction np.sum(..., axis=(2, 3)) performs over the k*k contiguous products of one output pixel.
+__device__ double numpy_pairwise_sum(const WindowProducts& a, int lo, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, a(lo + i));
+    return res;
+  }
+  if (n <= 128) {
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a(lo + j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a(lo + i + j));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a(lo + i));
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __dadd_rn(numpy_pairwise_sum(a, lo, n2), numpy_pairwise_sum(a, lo + n2, n - n2));
+}
+
+__global__ void correlate_zero_pad_f64_kernel(const double* __restrict__ img, int H, int W,
+                                              const double* __restrict__ ker, int ks, double* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t off = (size_t)blockIdx.z * H * W;
+  WindowProducts a{img + off, ker, H, W, ks, ks / 2, y, x};
+  out[off + (size_t)y * W + x] = numpy_pairwise_sum(a, 0, ks * ks);
+}
+
+}  // namespace fc
+
+extern "C" int fc_correlate_zero_pad_f64(const double* image, int batch, int height, int width, const double* kernel,
+                                         int kernel_size, double* out, void* stream) {
+  if (bad_image_args(image, batch, height, width) || !kernel || !out) return FC_ERR_BAD_ARG;
+  if (kernel_size < 1 || kernel_size > 63 || (kernel_size & 1) == 0) return FC_ERR_BAD_ARG;
+  dim3 block(32, 8), grid(div_up(width, 32), div_up(height, 8), batch);
+  correlate_zero_pad_f64_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(image, height, width, kernel, kernel_size, out);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}

@@ -1,0 +1,190 @@
+/*
+ * featurecraft_b200.h -- C ABI of libfeaturecraft_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the feature-extraction hot path of exVision-FeatureCraft.  The reference is
+ * pure Python (no FFI of its own), so each entry point below names the reference function whose
+ * arithmetic it replaces (file:line relative to the reference root; APP = FeatureCraft-PyQt-App).
+ * The host-side mirror of the reference's Python signatures lives in exvision_featurecraft_b200/
+ * and binds these symbols with ctypes (INTEGRATION.md shows the stub a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library never allocates result buffers and never synchronises: the caller owns all memory
+ *     and the stream (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - images are dense row-major, batched as [batch][height][width] with identical shapes;
+ *   - return value: FC_OK or a negative fc_status; fc_last_cuda_error() gives the CUDA code behind
+ *     FC_ERR_CUDA;
+ *   - there is no CPU fallback: without a CUDA device every compute call returns FC_ERR_CUDA.
+ */
+#ifndef FEATURECRAFT_B200_H
+#define FEATURECRAFT_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define FC_API __attribute__((visibility("default")))
+#else
+#define FC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum fc_status {
+  FC_OK = 0,
+  FC_ERR_BAD_ARG = -1,   /* null pointer, non-positive size, unsupported parameter            */
+  FC_ERR_CAPACITY = -2,  /* an output buffer is too small; the required count is written back */
+  FC_ERR_CUDA = -3,      /* a CUDA runtime call or launch failed                              */
+  FC_ERR_UNSUPPORTED = -4
+} fc_status;
+
+/* element type of the SIFT scale space (FC_F32 = production layout, FC_F64 = exact-parity mode) */
+typedef enum fc_dtype { FC_F32 = 0, FC_F64 = 1 } fc_dtype;
+
+/* keypoint filter: FC_FILTER_APP keeps every extremum (APP/utils/SIFT_scale_space.py:89-105),
+ * FC_FILTER_SCRIPT applies the contrast + edge-ratio tests of
+ * implementation_without_ui/SIFT/SIFT.py:202-215. */
+typedef enum fc_filter { FC_FILTER_APP = 0, FC_FILTER_SCRIPT = 1 } fc_filter;
+
+FC_API int fc_version(void);
+FC_API const char* fc_status_string(int status);
+FC_API int fc_last_cuda_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+FC_API unsigned long long fc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Corner detectors
+ * ------------------------------------------------------------------------------------------- */
+
+/* convert_to_gray, APP/utils/harris_utils.py:4-9: (0.2989 r + 0.5870 g + 0.1140 b) truncated to u8.
+ * rgb is [batch][h][w][3] uint8. */
+FC_API int fc_rgb_to_gray_u8(const uint8_t* rgb, int batch, int height, int width, uint8_t* gray, void* stream);
+
+/* convolve2d_optimized, APP/utils/harris_utils.py:33-80: zero-padded CORRELATION of float64 images
+ * with a square odd kernel (device pointer, kernel_size^2 float64); the k*k products of each pixel
+ * are reduced in numpy's pairwise order so float data reproduce np.sum(..., axis=(2, 3)). */
+FC_API int fc_correlate_zero_pad_f64(const double* image, int batch, int height, int width, const double* kernel,
+                              int kernel_size, double* out, void* stream);
+
+/* apply_harris_detector_vectorized, APP/FeatureCraft_Backend.py:336-358: np.gradient central
+ * differences, window_size x window_size ones window (zero padded), R = det - k*trace^2, bit-exact.
+ * response: [batch][h][w] float64.  mask (optional, may be NULL): bit (x & 31) of word
+ * [b][y][x >> 5] is set iff R > threshold; row pitch = (width + 31) / 32 words. */
+FC_API int fc_harris_response(const uint8_t* gray, int batch, int height, int width, int window_size, double k,
+                       double threshold, double* response, uint32_t* mask, void* stream);
+
+/* harris_detection, implementation_without_ui/Corner Detection/harris.ipynb:150-201: same response
+ * with the 5x5 K_X gradient (zero padded).  The notebook only visits window_size/2 <= y < H - ...;
+ * pass that as `border` to fc_threshold_mask_abs. */
+FC_API int fc_notebook_harris_response(const uint8_t* gray, int batch, int height, int width, int window_size, double k,
+                                double* response, void* stream);
+
+/* apply_lambda_minus_vectorized, APP/FeatureCraft_Backend.py:402-437: K_X gradients, 5x5 ones
+ * window / 25, smallest eigenvalue with LAPACK's dsterf/dlae2 rounding sequence, bit-exact.
+ * eig: [batch][h][w] float64; image_max: [batch] float64 (max over each image, for
+ * threshold = pct * max, :440). */
+FC_API int fc_lambda_minus_response(const uint8_t* gray, int batch, int height, int width, double* eig,
+                             double* image_max, void* stream);
+
+/* np.argwhere(map > thr) as a bit mask (APP/FeatureCraft_Backend.py:358, :268).  Pixels closer than
+ * `border` to any image edge are never set. */
+FC_API int fc_threshold_mask_abs(const double* map, int batch, int height, int width, double threshold, int border,
+                          uint32_t* mask, void* stream);
+/* map > fraction * image_max[b] (APP/FeatureCraft_Backend.py:440-441); the product is rounded once. */
+FC_API int fc_threshold_mask_rel(const double* map, int batch, int height, int width, double fraction,
+                          const double* image_max, uint32_t* mask, void* stream);
+
+/* Row-major compaction of a bit mask (the order np.argwhere / np.where produce).
+ * fc_mask_scan: row_offsets[i] = number of set bits in rows [0, i) of the whole batch, i in
+ * [0, batch*height]; so row_offsets[batch*height] is the total and row_offsets[b*height] the start
+ * of image b.  scratch must hold fc_scan_scratch_elems(batch*height) int32. */
+FC_API int64_t fc_scan_scratch_elems(int64_t n);
+FC_API int fc_mask_scan(const uint32_t* mask, int batch, int height, int width, int32_t* row_offsets, int32_t* scratch,
+                 void* stream);
+/* coords: [total][2] int32 (row, col); values (optional): map gathered at those pixels. */
+FC_API int fc_mask_emit(const uint32_t* mask, const int32_t* row_offsets, int batch, int height, int width,
+                 const double* map, int32_t* coords, double* values, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SIFT scale space (APP/utils/SIFT_scale_space.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* One octave of generate_gaussian_images_in_octave (:109-160) for a batch of equally sized bases:
+ * G_i = base (*) K_i for the n_levels unnormalised, truncated Gaussians whose separable taps are
+ * given in taps_host (concatenated, lengths in tap_len_host; 'same' / 'symm' border), except that
+ * for first_is_identity != 0 level 0 is the base itself (octaves > 0, :136-137).
+ * gauss: [batch][n_levels][h][w] of `dtype`.  The 3x3x3 extremum rule of get_keypoints (:78-88) is
+ * evaluated on DoG_k = G_{k+1} - G_k for k = 1 .. n_levels-3 and written as bit masks
+ * extrema: [batch][n_levels-3][h][(w+31)/32]; with filter == FC_FILTER_SCRIPT the contrast and
+ * edge-ratio tests are applied too.  base has element type `dtype`. */
+FC_API int fc_gauss_octave(const void* base, int dtype, int batch, int height, int width, int n_levels,
+                    const double* taps_host, const int* tap_len_host, int first_is_identity, int filter,
+                    double contrast_th, double ratio_th, void* gauss, uint32_t* extrema, void* stream);
+
+/* img[::2, ::2] (APP/utils/SIFT_scale_space.py:209) of level `level` of a [batch][n_levels][h][w]
+ * stack into a dense [batch][(h+1)/2][(w+1)/2] array. */
+FC_API int fc_downsample2(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
+                   void* out, void* stream);
+
+/* float64 image -> scale-space dtype (identity copy for FC_F64) */
+FC_API int fc_convert_f64(const double* src, int64_t n, int dtype, void* dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SIFT orientation + descriptor (APP/utils/keypoint_descriptor.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* sift_gradient (:72-79) of level `level` of a [batch][n_levels][h][w] stack: magnitude and
+ * direction (degrees, wrapped with Python's % 360), stored in `dtype`, each [batch][h][w]. */
+FC_API int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
+                      void* magnitude, void* direction, void* stream);
+
+/* dog_keypoints_orientations (:116-172) for one (octave, scale): keypoints are (image, row, col)
+ * int32 triples in reference order; weights_host is gaussian_filter_kernel(sigma) as a dense
+ * (2r+1)^2 float64 table that the caller uploaded to `weights` (device).  For keypoint n the 36-bin
+ * float32 histogram is built and bin_mask[n] receives bit b for every bin with
+ * hist[b] >= float32(0.8) * max (:165-167). */
+FC_API int fc_orientation_bins(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
+                        const int32_t* keypoints, int n_keypoints, const double* weights, int radius,
+                        uint64_t* bin_mask, void* stream);
+
+/* Expand bin masks into oriented keypoints in reference order: offsets[n] = popcount prefix
+ * (exclusive, offsets[n_keypoints] = total; scratch as for fc_mask_scan), then
+ * oriented[m] = (image, row, col, bin). */
+FC_API int fc_orientation_scan(const uint64_t* bin_mask, int n_keypoints, int32_t* offsets, int32_t* scratch, void* stream);
+FC_API int fc_orientation_emit(const int32_t* keypoints, const uint64_t* bin_mask, const int32_t* offsets, int n_keypoints,
+                        int32_t* oriented, void* stream);
+
+/* extract_sift_descriptors (:230-289) for one (octave, scale): 16x16 nearest-neighbour rotated
+ * window (cv2.warpAffine fixed-point rule, :175-212), Gaussian mask `gmask` (16x16 float64, device,
+ * from get_gaussian_mask :215-227), 4x4x8 float32 cell histograms, normalise / clip / normalise.
+ * trig: device table [36][2 + 32] float64 per orientation bin: cos, sin of theta*3.14159/180 and
+ * the rint(cos*x*1024), rint(sin*x*1024) columns for x = 0..15 (computed on the host with the
+ * reference's own libm calls).  descriptors: [n_oriented][128] float32 (out_dtype FC_F32) or
+ * float64. */
+FC_API int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
+                   const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
+                   void* descriptors, int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Matching (APP/utils/keypoint_descriptor.py:330-349)
+ * ------------------------------------------------------------------------------------------- */
+
+/* cv2.BFMatcher().knnMatch(query, train, k=2) + the ratio test: for each of n_query float32
+ * descriptors the two nearest of n_train in L2, ties to the lower train index.
+ * Candidate search: fp16 tcgen05 GEMM (|a-b|^2 = |a|^2 + |b|^2 - 2ab) with a fused running top-2;
+ * the two winners are then re-evaluated in exact float32 so distances and the ratio test match an
+ * fp32 brute-force matcher.  knn_idx: [n_query][2] int32, knn_dist: [n_query][2] float32,
+ * good: [n_query] uint8 = dist0 < ratio * dist1 (evaluated in double, strict).  workspace must hold
+ * fc_match_workspace_bytes(n_query, n_train) bytes. */
+FC_API int64_t fc_match_workspace_bytes(int n_query, int n_train);
+FC_API int fc_match_knn2(const float* query, int n_query, const float* train, int n_train, double ratio,
+                  int32_t* knn_idx, float* knn_dist, uint8_t* good, void* workspace, void* stream);
+/* exact float32 brute force on CUDA cores (same outputs); the verification twin of fc_match_knn2 */
+FC_API int fc_match_knn2_exact(const float* query, int n_query, const float* train, int n_train, double ratio,
+                        int32_t* knn_idx, float* knn_dist, uint8_t* good, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEATURECRAFT_B200_H */
