@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 feature-extraction hot path (contract: see DESIGN.md, "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sift|harris|match] [--impl reference]
+
+One rank per GPU (torchrun for N > 1).  A "step" is one pass of the hot path over one batch of synthetic
+images that is already resident in HBM (`value`) or starts in pinned host memory and ends with the
+results back on the host (`e2e`).  Images are independent, so ranks never exchange data: weak scaling,
+value = images of all ranks / max-over-ranks device time.
+
+`--impl reference` times the CPU oracle (oracle/featurecraft_oracle.py, the restatement of the reference's
+NumPy path -- the reference itself is Python and cannot travel to the GPU box) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # "under load" = samples in the upper half of the observed power range
+        if sm:
+            cut = (max(power) + min(power)) / 2 if len(power) > 2 else -1
+            loaded = [s for s, p in zip(sm, power) if p >= cut] or sm
+            return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                    "samples": len(sm), "power_w_max": max(power)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(reasons), "samples": 0}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arms (oracle) -- run in worker processes, one image per task
+# ----------------------------------------------------------------------------------------------
+def _cpu_harris_task(args):
+    h, w, seed = args
+    from exvision_featurecraft_b200 import synthetic
+    from oracle import featurecraft_oracle as O
+
+    gray = synthetic.corner_image(h, w, seed)
+    t0 = time.perf_counter()
+    r = O.harris_response(gray, 5, 0.04)
+    idx, vals = O.threshold_corners(r, 10000)
+    lam = O.lambda_minus_response(gray)
+    rows, cols = np.where(lam > 0.01 * lam.max())
+    return time.perf_counter() - t0, int(idx.shape[0]) + int(rows.shape[0])
+
+
+def _cpu_sift_task(args):
+    h, w, seed = args
+    from exvision_featurecraft_b200 import synthetic
+    from oracle import featurecraft_oracle as O
+
+    img = synthetic.sift_image(h, w, seed)
+    t0 = time.perf_counter()
+    base = upsample2_host(img)
+    pts, desc = O.compute_keypoints_and_descriptors_from_base(base, 4, 2, 1.6, 0.03, 10, "app", "separable")
+    return time.perf_counter() - t0, len(desc)
+
+
+def upsample2_host(img):
+    """The x2 bilinear up-sample in front of the parity boundary (rescale, KD:296) -- same array on both arms."""
+    from scipy import ndimage
+
+    return ndimage.zoom(np.asarray(img, dtype=np.float64), 2, order=1, mode="mirror", grid_mode=True)
+
+
+def cpu_pool_run(task, items, cores):
+    """Run `task` over `items` on `cores` processes; returns (wall seconds, results)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    if cores <= 1:
+        res = [task(it) for it in items]
+    else:
+        with ctx.Pool(cores) as pool:
+            res = pool.map(task, items, chunksize=1)
+    return time.perf_counter() - t0, res
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------
+class HarrisWorkload:
+    """BASELINE config 4: batched Harris + lambda-minus over 2048x2048 uint8 images, sharded by image."""
+
+    name = "harris"
+    metric = "harris_lambda_minus_megapixels_per_sec"
+    unit = "MP/s"
+    dtype = "u8->int32 sums->f64 response"
+    H = W = 2048
+
+    def __init__(self, args):
+        self.batch = args.batch or 64
+
+    def describe(self, world):
+        return {"workload": "config[3]: batched Harris (k=0.04, 5x5, thr 1e4) + lambda-minus (1%% of max) over %d synthetic "
+                            "2048x2048 u8 images per step per GPU (1024-image job = 16 steps/GPU at 1 GPU)" % self.batch,
+                "images_per_step_per_gpu": self.batch, "image": [self.H, self.W], "sharding": "images, no collective",
+                "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (self.batch * self.H * self.W * 17 / 1e9)}
+
+    def units_per_step(self):
+        return self.batch * self.H * self.W / 1e6  # megapixels
+
+    def setup(self, rank, torch):
+        from exvision_featurecraft_b200 import corners, synthetic
+
+        self.torch, self.corners = torch, corners
+        # 8 distinct seeded images tiled to the batch (generation cost), distinct per rank
+        base = np.stack([synthetic.corner_image(self.H, self.W, seed=rank * 8 + i) for i in range(8)])
+        host = np.concatenate([base] * ((self.batch + 7) // 8))[: self.batch]
+        self.host_in = torch.from_numpy(host).pin_memory()
+        self.dev_in = self.host_in.cuda(non_blocking=True)
+        self.resp = torch.empty((self.batch, self.H, self.W), dtype=torch.float64, device="cuda")
+        self.eig = torch.empty((self.batch, self.H, self.W), dtype=torch.float64, device="cuda")
+        self.kernel_ms = []
+        self.ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(64)]
+        self.ev_i = 0
+
+    def step_device(self, record=False):
+        c, torch = self.corners, self.torch
+        if record and self.ev_i < len(self.ev):
+            a, b = self.ev[self.ev_i]
+            a.record()
+            res = c.harris(self.dev_in, 5, 0.04, 10000, compact=False, out=self.resp)
+            b.record()
+            self.ev_i += 1
+        else:
+            res = c.harris(self.dev_in, 5, 0.04, 10000, compact=False, out=self.resp)
+        coords, values, offs = c.compact_mask(res.mask, self.W, res.response)
+        lam = c.lambda_minus(self.dev_in, 0.01, compact=True, out=self.eig)
+        return coords, values, lam.coords
+
+    def step_e2e(self):
+        torch = self.torch
+        d = self.host_in.cuda(non_blocking=True)
+        keep = self.dev_in
+        self.dev_in = d
+        coords, values, lcoords = self.step_device()
+        self.dev_in = keep
+        out = (coords.cpu(), values.cpu(), lcoords.cpu())
+        h2d = self.host_in.numel()
+        d2h = sum(t.numel() * t.element_size() for t in out)
+        return h2d, d2h
+
+    def dominant_kernel(self):
+        n = self.ev_i
+        ms = [a.elapsed_time(b) for a, b in self.ev[:n]]
+        t = float(np.mean(ms)) if ms else None
+        alg = 9.0 * self.batch * self.H * self.W  # 1 B in + 8 B out per pixel
+        return "harris5_strip_kernel", alg, t, "hbm"
+
+    cpu_task = staticmethod(_cpu_harris_task)
+
+    def cpu_items(self, n):
+        return [(self.H, self.W, s) for s in range(n)]
+
+    def cpu_units(self, n):
+        return n * self.H * self.W / 1e6
+
+
+WORKLOADS = {"harris": HarrisWorkload}
+
+
+def pick_workload(name):
+    try:
+        from bench_sift import SiftWorkload, MatchWorkload  # noqa: F401  (added when the SIFT path lands)
+
+        WORKLOADS["sift"] = SiftWorkload
+        WORKLOADS["match"] = MatchWorkload
+    except ImportError:
+        pass
+    if name is None:
+        name = "sift" if "sift" in WORKLOADS else "harris"
+    return WORKLOADS[name]
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_items = max(cores, 1) * max(1, args.ref_items_per_core)
+    items = wl.cpu_items(n_items)
+    times = []
+    for s in range(args.warmup + args.steps):
+        wall, _ = cpu_pool_run(wl.cpu_task, items, cores)
+        if s >= args.warmup:
+            times.append(wall)
+    t = float(np.mean(times))
+    v = wl.cpu_units(n_items) / t
+    line = {"impl": "reference", "metric": wl.metric, "value": v, "unit": wl.unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": wl.describe(1),
+            "cpu_baseline": {"value": v, "unit": wl.unit, "cores": cores, "kind": "port",
+                             "sample": "%d images per step on %d processes (oracle = NumPy restatement of the reference)" % (n_items, cores)},
+            "e2e": {"value": v, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--batch", type=int, default=None, help="images per step per GPU")
+    ap.add_argument("--ref-items-per-core", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl_cls = pick_workload(args.workload)
+    wl = wl_cls(args)
+    if args.impl == "reference":
+        args.steps = args.steps or 1
+        args.warmup = 0 if args.warmup is None else min(args.warmup, 1)
+        run_reference(args, wl)
+        return
+    args.steps = args.steps or 10
+    args.warmup = 3 if args.warmup is None else max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from exvision_featurecraft_b200 import _lib
+
+    _lib.load()
+    wl.setup(rank, torch)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        wl.step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        wl.step_device(record=True)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    # end to end: pinned host -> device -> hot path -> results on the host
+    wl.step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        h2d, d2h = wl.step_e2e()
+    g1.record()
+    barrier()
+    e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    if rank == 0:
+        units = wl.units_per_step() * args.steps * world
+        kname, alg, kms, bound = wl.dominant_kernel()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        if bound == "hbm":
+            peak, punit, src = peaks.get("hbm_gbs", 6650.0), "GB/s", ("measured" if peaks else "fallback")
+            ach = alg / (kms * 1e-3) / 1e9 if kms else None
+        else:
+            peak, punit, src = peaks.get("bf16_tflops", 1590.0), "TFLOP/s", ("measured burst" if peaks else "fallback")
+            ach = alg / (kms * 1e-3) / 1e12 if kms else None
+        line = {"metric": wl.metric, "value": units / (ms * 1e-3), "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.describe(world),
+                "e2e": {"value": units / (e2e_ms * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": kname, "bound": bound, "achieved": ach, "peak": peak, "unit": punit,
+                             "frac": (ach / peak) if ach else None, "traffic": getattr(wl, "ncu_traffic", None),
+                             "peak_source": src, "kernel_ms": kms, "algorithmic_per_launch": alg},
+                "clocks": clocks}
+        extra = getattr(wl, "extra", None)
+        if extra:
+            line["stages"] = extra() if callable(extra) else extra
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_items = getattr(wl, "cpu_sample_items", cores)
+            wall, res = cpu_pool_run(wl.cpu_task, wl.cpu_items(n_items), min(cores, n_items))
+            line["cpu_baseline"] = {"value": wl.cpu_units(n_items) / wall, "unit": wl.unit, "cores": min(cores, n_items),
+                                    "kind": "port", "sample": "%d image(s) of the workload shape through the oracle, %.1f s wall" % (n_items, wall)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -111,11 +111,12 @@ def notebook_harris(gray, window_size: int, k: float, threshold: float, compact:
     return res
 
 
-def lambda_minus(gray, threshold_percentage: float | None = 0.01, compact: bool = True) -> CornerResult:
+def lambda_minus(gray, threshold_percentage: float | None = 0.01, compact: bool = True,
+                 out: torch.Tensor | None = None) -> CornerResult:
     """lambda-minus (min eigenvalue) map, per-image max, and map > pct * max."""
     g = _as_gray_batch(gray)
     b, h, w = g.shape
-    eig = torch.empty((b, h, w), dtype=torch.float64, device=g.device)
+    eig = out if out is not None else torch.empty((b, h, w), dtype=torch.float64, device=g.device)
     image_max = torch.empty(b, dtype=torch.float64, device=g.device)
     _lib.call("fc_lambda_minus_response", ptr(g), b, h, w, ptr(eig), ptr(image_max), stream_ptr())
     res = CornerResult(eig, image_max=image_max)
