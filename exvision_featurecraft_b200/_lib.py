@@ -42,10 +42,11 @@ SIGNATURES = {
     "fc_scan_scratch_elems": (_i64, [_i64]),
     "fc_mask_scan": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "fc_mask_emit": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "fc_mask_emit_keypoints": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "fc_gauss_octave": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _d, _d, _p, _p, _p]),
     "fc_downsample2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fc_convert_f64": (_i, [_p, _i64, _i, _p, _p]),
-    "fc_gradient_field": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fc_gradient_field": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fc_orientation_bins": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p]),
     "fc_orientation_scan": (_i, [_p, _i, _p, _p, _p]),
     "fc_orientation_emit": (_i, [_p, _p, _p, _i, _p, _p]),

@@ -378,7 +378,7 @@ __global__ void mask_row_count_kernel(const uint32_t* __restrict__ mask, int64_t
 // one warp per mask row: ordered emission of (row, col) and the gathered map values
 __global__ void mask_emit_kernel(const uint32_t* __restrict__ mask, const int32_t* __restrict__ row_offsets,
                                  int64_t rows, int H, int W, int pitch, const double* __restrict__ map,
-                                 int32_t* __restrict__ coords, double* __restrict__ values) {
+                                 int32_t* __restrict__ coords, double* __restrict__ values, int triples) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -395,8 +395,14 @@ __global__ void mask_emit_kernel(const uint32_t* __restrict__ mask, const int32_
       const int bit = __ffs(bits) - 1;
       bits &= bits - 1;
       const int x = w * 32 + bit;
-      coords[2 * (size_t)pos] = y;
-      coords[2 * (size_t)pos + 1] = x;
+      if (triples) {  // (image, row, col) keypoint records
+        coords[3 * (size_t)pos] = (int)(warp / H);
+        coords[3 * (size_t)pos + 1] = y;
+        coords[3 * (size_t)pos + 2] = x;
+      } else {
+        coords[2 * (size_t)pos] = y;
+        coords[2 * (size_t)pos + 1] = x;
+      }
       if (values) values[pos] = map[warp * W + x];
       ++pos;
     }
@@ -520,7 +526,18 @@ extern "C" int fc_mask_emit(const uint32_t* mask, const int32_t* row_offsets, in
   if (values && !map) return FC_ERR_BAD_ARG;
   const int64_t rows = (int64_t)batch * height;
   mask_emit_kernel<<<(unsigned)div_up64(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      mask, row_offsets, rows, height, width, div_up(width, 32), map, coords, values);
+      mask, row_offsets, rows, height, width, div_up(width, 32), map, coords, values, 0);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_mask_emit_keypoints(const uint32_t* mask, const int32_t* row_offsets, int batch, int height, int width,
+                                      int32_t* keypoints, void* stream) {
+  if (bad_image_args(mask, batch, height, width) || !row_offsets || !keypoints) return FC_ERR_BAD_ARG;
+  const int64_t rows = (int64_t)batch * height;
+  mask_emit_kernel<<<(unsigned)div_up64(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      mask, row_offsets, rows, height, width, div_up(width, 32), nullptr, keypoints, nullptr, 1);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;

@@ -1,0 +1,321 @@
+// SIFT orientation assignment and descriptors (sm_100a).
+//
+//   gradient_field_kernel<T>   sift_gradient (APP/utils/keypoint_descriptor.py:72-79) of one pyramid level:
+//                              magnitude, direction (degrees, Python % 360) and the 36-bin index
+//                              np.round(direction * 36 / 360) (:140-142) as one byte per pixel.
+//   orientation_kernel<T>      one warp per keypoint: zero-padded (2r+1)^2 window, weight = magnitude x
+//                              unnormalised Gaussian table, 36-bin histogram (:144-163).  Every lane owns a
+//                              private copy of the histogram in shared memory ([bin][lane], conflict free,
+//                              no atomics, deterministic float64 sums); bins are reduced by shuffles, rounded
+//                              to float32 and compared with float32(0.8) * max (:165-167).
+//   descriptor_kernel<T>       one warp per oriented keypoint: 16x16 nearest-neighbour rotated window with
+//                              OpenCV's 10-bit fixed-point coordinates (:175-212), 4x4 cells x 8 bins with
+//                              float32 cell histograms, normalise / clip [2^-10, 0.2] / normalise (:259-287).
+//                              Two lanes per cell, 8 samples per lane, 8 private bins in registers.
+#include "fc_common.cuh"
+
+namespace fc {
+
+template <typename T> struct Math;
+template <> struct Math<float> {
+  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+  static __device__ __forceinline__ float fmod_(float a, float b) { return fmodf(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+};
+template <> struct Math<double> {
+  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+  static __device__ __forceinline__ double fmod_(double a, double b) { return fmod(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+};
+
+// Python's float % 360 (numpy remainder): fmod, then shift negatives up; can return exactly 360.0
+template <typename T>
+__device__ __forceinline__ T py_mod360(T a) {
+  T r = Math<T>::fmod_(a, T(360));
+  if (r < T(0)) r = Math<T>::add(r, T(360));
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int W, T* __restrict__ mag,
+                      T* __restrict__ dir, uint8_t* __restrict__ obin) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= W) return;
+  const T* g = gauss + ((size_t)b * L + level) * H * W;
+  // true convolution with [-1, 0, 1], 'symm' border: gx = I[., x-1] - I[., x+1] with the edge sample repeated
+  const int xl = x > 0 ? x - 1 : 0, xr = x < W - 1 ? x + 1 : W - 1;
+  const int yu = y > 0 ? y - 1 : 0, yd = y < H - 1 ? y + 1 : H - 1;
+  const T gx = g[(size_t)y * W + xl] - g[(size_t)y * W + xr];
+  const T gy = g[(size_t)yu * W + x] - g[(size_t)yd * W + x];
+  const T m = Math<T>::sqrt_(Math<T>::add(Math<T>::mul(gx, gx), Math<T>::mul(gy, gy)));
+  // np.rad2deg(arctan2(gy, gx)) % 360
+  const T deg = Math<T>::mul(Math<T>::atan2_(gy, gx), T(57.29577951308232087680));
+  const T d = py_mod360<T>(deg);
+  const size_t o = ((size_t)b * H + y) * W + x;
+  mag[o] = m;
+  dir[o] = d;
+  // np.round(direction * 36 / 360): half to even, evaluated in double on the stored direction
+  obin[o] = (uint8_t)(int)rint(__ddiv_rn(__dmul_rn((double)d, 36.0), 360.0));
+}
+
+// ------------------------------------------------------------------------------------------------
+static constexpr int kOriWarps = 4;
+static constexpr int kOriBins = 36;
+static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the final column sums are conflict free
+
+template <typename T>
+__global__ void __launch_bounds__(kOriWarps * 32)
+orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, int H, int W,
+                   const int32_t* __restrict__ keypoints, int n_keypoints, const double* __restrict__ weights,
+                   int radius, unsigned long long* __restrict__ bin_mask) {
+  __shared__ double hist[kOriWarps][(kOriBins + 1) * kOriPitch];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kOriWarps + warp;
+  if (n >= n_keypoints) return;  // warp-uniform; no block-wide barriers below
+  double* h = hist[warp];
+  for (int t = lane; t < (kOriBins + 1) * kOriPitch; t += 32) h[t] = 0.0;
+  __syncwarp();
+  const int b = keypoints[3 * n], ki = keypoints[3 * n + 1], kj = keypoints[3 * n + 2];
+  const T* m = mag + (size_t)b * H * W;
+  const uint8_t* ob = obin + (size_t)b * H * W;
+  const int side = 2 * radius + 1;
+  // clip the window to the image (outside is zero padding = no contribution)
+  const int r0 = max(ki - radius, 0), r1 = min(ki + radius, H - 1);
+  const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
+  const int nc = c1 - c0 + 1;
+  const int total = (r1 - r0 + 1) * nc;
+  for (int t = lane; t < total; t += 32) {
+    const int rr = t / nc;
+    const int y = r0 + rr, x = c0 + (t - rr * nc);
+    const size_t o = (size_t)y * W + x;
+    const int bin = ob[o];
+    const double w = __dmul_rn((double)m[o], weights[(y - ki + radius) * side + (x - kj + radius)]);
+    h[bin * kOriPitch + lane] += w;  // bin 36 (= 360 degrees after rounding) is accumulated but never read
+  }
+  __syncwarp();
+  // column sums: lane l reduces bins l and l + 32
+  float f0, f1 = 0.0f;
+  {
+    double s = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) s += h[lane * kOriPitch + k];
+    f0 = (float)s;
+    if (lane < kOriBins - 32) {
+      double s2 = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) s2 += h[(lane + 32) * kOriPitch + k];
+      f1 = (float)s2;
+    }
+  }
+  float mx = fmaxf(f0, f1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float cut = __fmul_rn(0.8f, mx);  // NEP 50: python float * float32 scalar stays float32
+  const uint32_t lo = __ballot_sync(0xffffffffu, f0 >= cut);
+  const uint32_t hi = __ballot_sync(0xffffffffu, (lane < kOriBins - 32) && (f1 >= cut));
+  if (lane == 0) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+__global__ void popcount64_kernel(const unsigned long long* __restrict__ m, int n, int32_t* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) counts[i] = __popcll(m[i]);
+}
+
+__global__ void orientation_emit_kernel(const int32_t* __restrict__ keypoints, const unsigned long long* __restrict__ m,
+                                        const int32_t* __restrict__ offsets, int n, int32_t* __restrict__ oriented) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long bits = m[i];
+  int pos = offsets[i];
+  const int b = keypoints[3 * i], r = keypoints[3 * i + 1], c = keypoints[3 * i + 2];
+  while (bits) {
+    const int bin = __ffsll((long long)bits) - 1;
+    bits &= bits - 1;
+    reinterpret_cast<int4*>(oriented)[pos++] = make_int4(b, r, c, bin);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static constexpr int kDescWarps = 4;
+static constexpr int kTrigStride = 2 + 32;
+
+template <typename T, typename OUT>
+__global__ void __launch_bounds__(kDescWarps * 32)
+descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, int W, const int32_t* __restrict__ oriented,
+                  int n_oriented, const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc) {
+  __shared__ int sXY[kDescWarps][32];  // x0[0..15], y0[0..15] per warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kDescWarps + warp;
+  if (n >= n_oriented) return;
+  const int4 kp = reinterpret_cast<const int4*>(oriented)[n];
+  const int b = kp.x, ki = kp.y, kj = kp.z, bin = kp.w;
+  const double theta = (double)(10 * bin + 5);  // (bin + 0.5) * 10 % 360, exact
+  const double* tg = trig + bin * kTrigStride;
+  const double cs = tg[0], sn = tg[1];
+  // rotated_subimage: v_x = (c, s), v_y = (-s, c); s_x = j - c*7.5 - (-s)*7.5; s_y = i - s*7.5 - c*7.5
+  const double sx = __dsub_rn(__dsub_rn((double)kj, __dmul_rn(cs, 7.5)), __dmul_rn(-sn, 7.5));
+  const double sy = __dsub_rn(__dsub_rn((double)ki, __dmul_rn(sn, 7.5)), __dmul_rn(cs, 7.5));
+  {
+    const int yy = lane & 15;
+    // X0[y] = rint((M01*y + M02) * 1024) + 512 ; Y0[y] = rint((M11*y + M12) * 1024) + 512
+    const double a = (lane < 16) ? __dadd_rn(__dmul_rn(-sn, (double)yy), sx) : __dadd_rn(__dmul_rn(cs, (double)yy), sy);
+    sXY[warp][lane] = __double2int_rn(__dmul_rn(a, 1024.0)) + 512;
+  }
+  __syncwarp();
+  const T* m = mag + (size_t)b * H * W;
+  const T* d = dir + (size_t)b * H * W;
+  const int cell = lane >> 1, half = lane & 1;
+  const int cy = (cell >> 2) * 4 + half * 2, cx = (cell & 3) * 4;
+  double hist[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) hist[k] = 0.0;
+#pragma unroll
+  for (int ry = 0; ry < 2; ++ry) {
+    const int wy = cy + ry;
+    const int X0 = sXY[warp][wy], Y0 = sXY[warp][16 + wy];
+#pragma unroll
+    for (int rx = 0; rx < 4; ++rx) {
+      const int wx = cx + rx;
+      const int X = (X0 + (int)tg[2 + wx]) >> 10;
+      const int Y = (Y0 + (int)tg[2 + 16 + wx]) >> 10;
+      double wv = 0.0, dv = 0.0;
+      if (X >= 0 && X < W && Y >= 0 && Y < H) {
+        const size_t o = (size_t)Y * W + X;
+        wv = (double)m[o];
+        dv = (double)d[o];
+      }
+      wv = __dmul_rn(wv, gmask[wy * 16 + wx]);
+      // bin = int(((dir - theta) % 360) * 8 / 360.0); 8 (dir - theta a hair below 0) is dropped
+      const double rel = py_mod360<double>(__dsub_rn(dv, theta));
+      const int hb = (int)__ddiv_rn(__dmul_rn(rel, 8.0), 360.0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hist[k] += (hb == k) ? wv : 0.0;
+    }
+  }
+  // merge the two halves of the cell (rows 0-1 then rows 2-3), round to float32 like the reference's cell hist
+  double f[4];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double other = __shfl_xor_sync(0xffffffffu, hist[k], 1);
+    const double s = half ? __dadd_rn(other, hist[k]) : __dadd_rn(hist[k], other);
+    hist[k] = (double)(float)s;
+  }
+  // even lane keeps bins 0..3, odd lane bins 4..7 of the cell -> feature index cell*8 + half*4 + k
+#pragma unroll
+  for (int k = 0; k < 4; ++k) f[k] = half ? hist[4 + k] : hist[k];
+  double ss = f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const double nrm = sqrt(ss);
+  const double lo = 0.0009765625, hi = 0.2;  // np.finfo(np.float16).eps, 0.2
+  double s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = __ddiv_rn(f[k], nrm);
+    if (v == v) v = v < lo ? lo : (v > hi ? hi : v);  // np.clip keeps NaN
+    f[k] = v;
+    s2 += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  const double nrm2 = sqrt(s2);
+  OUT* dst = desc + (size_t)n * 128 + lane * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dst[k] = (OUT)__ddiv_rn(f[k], nrm2);
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
+                                 void* magnitude, void* direction, uint8_t* orientation_bin, void* stream) {
+  if (!gauss || !magnitude || !direction || !orientation_bin || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (level < 0 || level >= n_levels) return FC_ERR_BAD_ARG;
+  dim3 grid(div_up(width, 256), height, batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FC_F32)
+    gradient_field_kernel<float><<<grid, 256, 0, st>>>((const float*)gauss, n_levels, level, height, width,
+                                                       (float*)magnitude, (float*)direction, orientation_bin);
+  else if (dtype == FC_F64)
+    gradient_field_kernel<double><<<grid, 256, 0, st>>>((const double*)gauss, n_levels, level, height, width,
+                                                        (double*)magnitude, (double*)direction, orientation_bin);
+  else
+    return FC_ERR_BAD_ARG;
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
+                                   int width, const int32_t* keypoints, int n_keypoints, const double* weights, int radius,
+                                   uint64_t* bin_mask, void* stream) {
+  if (!magnitude || !orientation_bin || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0) return FC_ERR_BAD_ARG;
+  if (n_keypoints == 0) return FC_OK;
+  if (!keypoints || !bin_mask || n_keypoints < 0) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = div_up(n_keypoints, kOriWarps);
+  if (dtype == FC_F32)
+    orientation_kernel<float><<<blocks, kOriWarps * 32, 0, st>>>((const float*)magnitude, orientation_bin, height, width,
+                                                                 keypoints, n_keypoints, weights, radius,
+                                                                 (unsigned long long*)bin_mask);
+  else if (dtype == FC_F64)
+    orientation_kernel<double><<<blocks, kOriWarps * 32, 0, st>>>((const double*)magnitude, orientation_bin, height, width,
+                                                                  keypoints, n_keypoints, weights, radius,
+                                                                  (unsigned long long*)bin_mask);
+  else
+    return FC_ERR_BAD_ARG;
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_orientation_scan(const uint64_t* bin_mask, int n_keypoints, int32_t* offsets, int32_t* scratch, void* stream) {
+  if (!bin_mask || !offsets || !scratch || n_keypoints <= 0) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  popcount64_kernel<<<div_up(n_keypoints, 256), 256, 0, st>>>((const unsigned long long*)bin_mask, n_keypoints, scratch);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return exclusive_scan_i32(scratch, n_keypoints, offsets, scratch + n_keypoints, st);
+}
+
+extern "C" int fc_orientation_emit(const int32_t* keypoints, const uint64_t* bin_mask, const int32_t* offsets, int n_keypoints,
+                                   int32_t* oriented, void* stream) {
+  if (!keypoints || !bin_mask || !offsets || !oriented || n_keypoints <= 0) return FC_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(oriented) & 15) return FC_ERR_BAD_ARG;
+  orientation_emit_kernel<<<div_up(n_keypoints, 256), 256, 0, (cudaStream_t)stream>>>(
+      keypoints, (const unsigned long long*)bin_mask, offsets, n_keypoints, oriented);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
+                              const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
+                              void* descriptors, int out_dtype, void* stream) {
+  if (!magnitude || !direction || !gmask || !trig || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (n_oriented == 0) return FC_OK;
+  if (!oriented || !descriptors || n_oriented < 0) return FC_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(oriented) & 15) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = div_up(n_oriented, kDescWarps);
+#define FC_LAUNCH(T, OUT)                                                                                         \
+  descriptor_kernel<T, OUT><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
+                                                               width, oriented, n_oriented, gmask, trig, (OUT*)descriptors)
+  if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float);
+  else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double);
+  else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float);
+  else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double);
+  else return FC_ERR_BAD_ARG;
+#undef FC_LAUNCH
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}

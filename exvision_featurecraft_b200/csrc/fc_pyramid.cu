@@ -1,0 +1,372 @@
+// SIFT scale space (sm_100a): one fused kernel per octave builds every Gaussian level from the octave
+// base (the reference blurs the BASE with each kernel, APP/utils/SIFT_scale_space.py:132,144 -- not
+// incrementally), a second kernel evaluates the 3x3x3 extremum rule on DoG values formed on the fly.
+//
+//   gauss_octave_kernel<T, TX, TY>  base tile + halo -> shared memory ('symm' reflection), then per level:
+//                                   vertical pass (8 rows per thread, taps and the sliding window in
+//                                   registers) -> shared -> horizontal pass (4 columns per thread,
+//                                   float4 shared loads) -> coalesced vector stores.
+//   extrema_kernel<T>               DoG_k = G_{k+1} - G_k in shared memory, argmax==13 || argmin==13 rule
+//                                   (:78-88), optional script filter (SIFT.py:202-215), ballot -> bit mask.
+//
+// HBM traffic per octave pixel (T = float): 4 B base read + 4 B x n_levels written; the extrema kernel
+// re-reads the levels once (+ 4 B x n_levels) -- DESIGN.md states the algorithmic figure (24 B).
+#include "fc_common.cuh"
+
+namespace fc {
+
+static constexpr int kMaxLevels = 8;
+static constexpr int kMaxRadius = 32;
+static constexpr int kMaxTapsTotal = 320;
+
+template <typename T>
+struct TapTable {
+  int n_levels;
+  int first_is_identity;
+  int radius[kMaxLevels];
+  int offset[kMaxLevels];  // start of the level's 2R+1 taps inside taps[]
+  T taps[kMaxTapsTotal];
+};
+
+// scipy 'symm' / ndimage 'reflect': ... b a | a b c | c b ...
+__device__ __forceinline__ int reflect_symm(int x, int n) {
+  if (x >= 0 && x < n) return x;
+  const int p = 2 * n;
+  int m = x % p;
+  if (m < 0) m += p;
+  return m < n ? m : p - 1 - m;
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+template <typename T>
+__device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// Vertical pass for one level: out rows [0, TY) of the tile, columns [c_lo, c_hi) of the input tile.
+// sIn row r <-> image row y0 - RMAX + r.  sTmp[y][c] with pitch tp.
+template <typename T, int R, int TY>
+__device__ __forceinline__ void vertical_pass(const T* __restrict__ sIn, int ip, int rmax, T* __restrict__ sTmp, int tp,
+                                              int c_lo, int n_cols, int tmp_c0, const T* __restrict__ taps) {
+  T tap[2 * R + 1];
+#pragma unroll
+  for (int k = 0; k <= 2 * R; ++k) tap[k] = taps[k];
+  constexpr int G = TY / 8;
+  for (int item = threadIdx.x; item < n_cols * G; item += blockDim.x) {
+    const int g = item / n_cols;
+    const int c = item - g * n_cols;
+    const T* src = sIn + (size_t)(rmax - R + g * 8) * ip + (c_lo + c);
+    T v[8 + 2 * R];
+#pragma unroll
+    for (int k = 0; k < 8 + 2 * R; ++k) v[k] = src[k * ip];
+    T* dst = sTmp + (size_t)(g * 8) * tp + tmp_c0 + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      T acc = tap[0] * v[j];
+#pragma unroll
+      for (int k = 1; k <= 2 * R; ++k) acc = fma_t<T>(tap[k], v[j + k], acc);
+      dst[j * tp] = acc;
+    }
+  }
+}
+
+// Horizontal pass: sTmp column index c <-> image column x0 - RP + c (RP = R rounded up to 4).
+template <typename T, int R, int TX, int TY>
+__device__ __forceinline__ void horizontal_pass(const T* __restrict__ sTmp, int tp, const T* __restrict__ taps,
+                                                T* __restrict__ out, int x0, int y0, int H, int W, bool vec_ok) {
+  constexpr int RP = (R + 3) & ~3;
+  constexpr int NV = (4 + 2 * RP) / 4;
+  using V4 = typename Vec4<T>::type;
+  T tap[2 * R + 1];
+#pragma unroll
+  for (int k = 0; k <= 2 * R; ++k) tap[k] = taps[k];
+  constexpr int G = TX / 4;
+  for (int item = threadIdx.x; item < TY * G; item += blockDim.x) {
+    const int y = item / G;
+    const int g = item - y * G;
+    const V4* src = reinterpret_cast<const V4*>(sTmp + (size_t)y * tp + g * 4);
+    T v[4 * NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const V4 t = src[q];
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    T r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      T acc = tap[0] * v[j + RP - R];
+#pragma unroll
+      for (int k = 1; k <= 2 * R; ++k) acc = fma_t<T>(tap[k], v[j + RP - R + k], acc);
+      r[j] = acc;
+    }
+    const int yy = y0 + y, xx = x0 + g * 4;
+    if (yy < H && xx < W) {
+      T* dst = out + (size_t)yy * W + xx;
+      if (vec_ok && xx + 3 < W) {
+        V4 o; o.x = r[0]; o.y = r[1]; o.z = r[2]; o.w = r[3];
+        *reinterpret_cast<V4*>(dst) = o;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (xx + j < W) dst[j] = r[j];
+      }
+    }
+  }
+}
+
+template <typename T, int R, int TX, int TY>
+__device__ __forceinline__ void blur_level(const T* sIn, int ip, int rmax, T* sTmp, int tp, const T* taps, T* out,
+                                           int x0, int y0, int H, int W, bool vec_ok) {
+  constexpr int RP = (R + 3) & ~3;
+  // vertical results are needed for image columns [x0 - R, x0 + TX + R)
+  vertical_pass<T, R, TY>(sIn, ip, rmax, sTmp, tp, rmax - R, TX + 2 * R, RP - R, taps);
+  __syncthreads();
+  horizontal_pass<T, R, TX, TY>(sTmp, tp, taps, out, x0, y0, H, W, vec_ok);
+  __syncthreads();
+}
+
+template <typename T, int TX, int TY>
+__global__ void __launch_bounds__(256)
+gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, int rmax, T* __restrict__ gauss) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ip = TX + 2 * rmax + 1;            // input tile pitch (odd-ish: column reads are conflict free anyway)
+  const int ih = TY + 2 * rmax;
+  const int rp_max = (rmax + 3) & ~3;
+  const int tp = TX + 2 * rp_max + 4;          // tmp pitch, multiple of 4
+  T* sIn = reinterpret_cast<T*>(smem_raw);
+  size_t in_elems = ((size_t)ih * ip + 3) & ~(size_t)3;
+  T* sTmp = sIn + in_elems;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int b = blockIdx.z;
+  const T* img = base + (size_t)b * H * W;
+  const int L = tab.n_levels;
+  T* gout = gauss + (size_t)b * L * H * W;
+
+  for (int t = threadIdx.x; t < ih * (TX + 2 * rmax); t += blockDim.x) {
+    const int r = t / (TX + 2 * rmax), c = t - r * (TX + 2 * rmax);
+    const int y = reflect_symm(y0 - rmax + r, H);
+    const int x = reflect_symm(x0 - rmax + c, W);
+    sIn[(size_t)r * ip + c] = img[(size_t)y * W + x];
+  }
+  __syncthreads();
+  const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gauss) & (4 * sizeof(T) - 1)) == 0);
+
+  for (int l = 0; l < L; ++l) {
+    T* out = gout + (size_t)l * H * W;
+    if (l == 0 && tab.first_is_identity) {
+      for (int t = threadIdx.x; t < TX * TY; t += blockDim.x) {
+        const int r = t / TX, c = t - r * TX;
+        if (y0 + r < H && x0 + c < W) out[(size_t)(y0 + r) * W + x0 + c] = sIn[(size_t)(r + rmax) * ip + c + rmax];
+      }
+      continue;
+    }
+    const T* taps = tab.taps + tab.offset[l];
+    switch (tab.radius[l]) {
+#define FC_CASE(RR) case RR: blur_level<T, RR, TX, TY>(sIn, ip, rmax, sTmp, tp, taps, out, x0, y0, H, W, vec_ok); break;
+      FC_CASE(1) FC_CASE(2) FC_CASE(3) FC_CASE(4) FC_CASE(5) FC_CASE(6) FC_CASE(7) FC_CASE(8)
+      FC_CASE(9) FC_CASE(10) FC_CASE(11) FC_CASE(12) FC_CASE(13) FC_CASE(14) FC_CASE(15) FC_CASE(16)
+      FC_CASE(17) FC_CASE(18) FC_CASE(19) FC_CASE(20) FC_CASE(21) FC_CASE(22) FC_CASE(23) FC_CASE(24)
+#undef FC_CASE
+      default: break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3x3 extrema on DoG (+ optional script filter)
+// ------------------------------------------------------------------------------------------------
+static constexpr int kExTX = 32, kExTY = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kExTX * kExTY)
+extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int L, int filter, double contrast_th, double ratio_th,
+               uint32_t* __restrict__ extrema, int pitch) {
+  // DoG tile: (L-1) levels x (TY+2) x (TX+2)
+  __shared__ T sD[(kMaxLevels - 1) * (kExTY + 2) * (kExTX + 2)];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * kExTX, y0 = blockIdx.y * kExTY;
+  const int nd = L - 1;
+  const T* g = gauss + (size_t)b * L * H * W;
+  constexpr int TW = kExTX + 2, TH = kExTY + 2;
+  const int tid = threadIdx.y * kExTX + threadIdx.x;
+  for (int t = tid; t < TH * TW; t += kExTX * kExTY) {
+    const int r = t / TW, c = t - r * TW;
+    const int y = y0 - 1 + r, x = x0 - 1 + c;
+    const bool in = (y >= 0 && y < H && x >= 0 && x < W);
+    T prev = in ? g[(size_t)y * W + x] : T(0);
+    for (int l = 0; l < nd; ++l) {
+      T cur = in ? g[((size_t)(l + 1) * H + y) * W + x] : T(0);
+      sD[(l * TH + r) * TW + c] = cur - prev;
+      prev = cur;
+    }
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  const bool center_ok = (y >= 1 && y <= H - 3 && x >= 1 && x <= W - 3);
+  const int nk = L - 3;
+  for (int k = 1; k <= nk; ++k) {
+    bool hit = false;
+    if (center_ok) {
+      const T* d0 = sD + ((k - 1) * TH + threadIdx.y) * TW + threadIdx.x;  // top-left of the 3x3 window
+      const T* d1 = d0 + TH * TW;
+      const T* d2 = d1 + TH * TW;
+      const T c = d1[TW + 1];
+      bool is_max = true, is_min = true;
+#pragma unroll
+      for (int di = 0; di < 3; ++di) {
+#pragma unroll
+        for (int dj = 0; dj < 3; ++dj) {
+          const int o = di * TW + dj;
+          const int flat = di * 9 + dj * 3;
+          const T a0 = d0[o], a1 = d1[o], a2 = d2[o];
+          // entries before the centre (flat index < 13): strict; after: non-strict (first extremum wins)
+          if (flat + 0 < 13) { is_max &= c > a0; is_min &= c < a0; } else { is_max &= c >= a0; is_min &= c <= a0; }
+          if (flat + 1 < 13) { is_max &= c > a1; is_min &= c < a1; }
+          else if (flat + 1 > 13) { is_max &= c >= a1; is_min &= c <= a1; }
+          if (flat + 2 < 13) { is_max &= c > a2; is_min &= c < a2; } else { is_max &= c >= a2; is_min &= c <= a2; }
+        }
+      }
+      hit = is_max || is_min;
+      if (hit && filter == FC_FILTER_SCRIPT) {
+        // SIFT.py:202-215: contrast from DoG[2k-1], Hessian on DoG[k]
+        const int ci = 2 * k - 1;
+        const double contrast = (ci < nd) ? (double)sD[(ci * TH + threadIdx.y + 1) * TW + threadIdx.x + 1] : 0.0;
+        const T* d = d1 + TW + 1;
+        const double c0 = (double)d[0];
+        const double dxx = __dadd_rn(__dsub_rn((double)d[1], __dmul_rn(2.0, c0)), (double)d[-1]);
+        const double dyy = __dadd_rn(__dsub_rn((double)d[TW], __dmul_rn(2.0, c0)), (double)d[-TW]);
+        const double dxy = __ddiv_rn(__dsub_rn(__dsub_rn((double)d[TW + 1], (double)d[TW - 1]),
+                                               __dsub_rn((double)d[-TW + 1], (double)d[-TW - 1])), 4.0);
+        const double tr = __dadd_rn(dxx, dyy);
+        const double det = __dsub_rn(__dmul_rn(dxx, dyy), __dmul_rn(dxy, dxy));
+        const double r = __ddiv_rn(__dmul_rn(tr, tr), det);
+        if (fabs(contrast) < contrast_th) hit = false;
+        if (r > ratio_th) hit = false;
+      }
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+    if (threadIdx.x == 0 && y < H && (x0 >> 5) < pitch)
+      extrema[(((size_t)(k - 1) * B + b) * H + y) * pitch + (x0 >> 5)] = bits;
+  }
+}
+
+template <typename T>
+__global__ void downsample2_kernel(const T* __restrict__ gauss, int L, int level, int H, int W, T* __restrict__ out,
+                                   int H2, int W2) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= W2) return;
+  out[((size_t)b * H2 + y) * W2 + x] = gauss[(((size_t)b * L + level) * H + 2 * y) * W + 2 * x];
+}
+
+template <typename T>
+__global__ void convert_f64_kernel(const double* __restrict__ src, int64_t n, T* __restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = (T)src[i];
+}
+
+template <typename T, int TX, int TY>
+static int launch_octave(const void* base, int B, int H, int W, int L, const double* taps_host, const int* tap_len_host,
+                         int first_is_identity, void* gauss, cudaStream_t st) {
+  TapTable<T> tab;
+  tab.n_levels = L;
+  tab.first_is_identity = first_is_identity;
+  int off = 0, rmax = 0;
+  const double* tp = taps_host;
+  for (int l = 0; l < L; ++l) {
+    const int n = tap_len_host[l];
+    if (n < 1 || (n & 1) == 0) return FC_ERR_BAD_ARG;
+    const int r = n / 2;
+    const bool used = !(l == 0 && first_is_identity);
+    if (used && (r < 1 || r > 24)) return FC_ERR_UNSUPPORTED;
+    if (off + n > kMaxTapsTotal) return FC_ERR_UNSUPPORTED;
+    tab.radius[l] = r;
+    tab.offset[l] = off;
+    for (int k = 0; k < n; ++k) tab.taps[off + k] = (T)tp[k];
+    if (used && r > rmax) rmax = r;
+    off += n;
+    tp += n;
+  }
+  for (int l = L; l < kMaxLevels; ++l) tab.radius[l] = tab.offset[l] = 0;
+  const int ip = TX + 2 * rmax + 1, ih = TY + 2 * rmax;
+  const int rp_max = (rmax + 3) & ~3;
+  const int tpitch = TX + 2 * rp_max + 4;
+  const size_t in_elems = ((size_t)ih * ip + 3) & ~(size_t)3;
+  const size_t smem = sizeof(T) * (in_elems + (size_t)TY * tpitch);
+  if (smem > 227 * 1024) return FC_ERR_UNSUPPORTED;
+  FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_kernel<T, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(div_up(W, TX), div_up(H, TY), B);
+  gauss_octave_kernel<T, TX, TY><<<grid, 256, smem, st>>>((const T*)base, H, W, tab, rmax, (T*)gauss);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+template <typename T>
+static int launch_extrema(const void* gauss, int B, int H, int W, int L, int filter, double cth, double rth,
+                          uint32_t* extrema, cudaStream_t st) {
+  const int pitch = div_up(W, 32);
+  dim3 grid(pitch, div_up(H, kExTY), B), block(kExTX, kExTY);
+  extrema_kernel<T><<<grid, block, 0, st>>>((const T*)gauss, B, H, W, L, filter, cth, rth, extrema, pitch);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_gauss_octave(const void* base, int dtype, int batch, int height, int width, int n_levels,
+                               const double* taps_host, const int* tap_len_host, int first_is_identity, int filter,
+                               double contrast_th, double ratio_th, void* gauss, uint32_t* extrema, void* stream) {
+  if (!base || !gauss || !taps_host || !tap_len_host || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (n_levels < 2 || n_levels > kMaxLevels) return FC_ERR_BAD_ARG;
+  if (dtype != FC_F32 && dtype != FC_F64) return FC_ERR_BAD_ARG;
+  if (filter != FC_FILTER_APP && filter != FC_FILTER_SCRIPT) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = dtype == FC_F32
+               ? launch_octave<float, 64, 64>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st)
+               : launch_octave<double, 32, 32>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st);
+  if (rc != FC_OK) return rc;
+  if (extrema && n_levels >= 4) {
+    rc = dtype == FC_F32 ? launch_extrema<float>(gauss, batch, height, width, n_levels, filter, contrast_th, ratio_th, extrema, st)
+                         : launch_extrema<double>(gauss, batch, height, width, n_levels, filter, contrast_th, ratio_th, extrema, st);
+  }
+  return rc;
+}
+
+extern "C" int fc_downsample2(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
+                              void* out, void* stream) {
+  if (!gauss || !out || batch <= 0 || height <= 0 || width <= 0 || level < 0 || level >= n_levels) return FC_ERR_BAD_ARG;
+  const int H2 = (height + 1) / 2, W2 = (width + 1) / 2;
+  dim3 grid(div_up(W2, 256), H2, batch);
+  if (dtype == FC_F32)
+    downsample2_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)gauss, n_levels, level, height, width, (float*)out, H2, W2);
+  else if (dtype == FC_F64)
+    downsample2_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)gauss, n_levels, level, height, width, (double*)out, H2, W2);
+  else
+    return FC_ERR_BAD_ARG;
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_convert_f64(const double* src, int64_t n, int dtype, void* dst, void* stream) {
+  if (!src || !dst || n <= 0) return FC_ERR_BAD_ARG;
+  const unsigned blocks = (unsigned)(div_up64(n, 256) < 148 * 32 ? div_up64(n, 256) : 148 * 32);
+  if (dtype == FC_F32)
+    convert_f64_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, (float*)dst);
+  else if (dtype == FC_F64)
+    convert_f64_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, (double*)dst);
+  else
+    return FC_ERR_BAD_ARG;
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}

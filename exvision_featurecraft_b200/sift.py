@@ -1,0 +1,345 @@
+"""Batched, device-resident SIFT: scale space -> extrema -> orientation -> descriptors over the C ABI.
+
+This is the driver the reference-shaped functions in ``utils/SIFT_scale_space.py`` and
+``utils/keypoint_descriptor.py`` sit on, and what the benchmarks call.  All images of a batch have the
+same shape; every stage is one (or a few) kernel launches over the whole batch.  The only host work is
+the parameter tables the reference also builds on the host (Gaussian taps, window tables: a few KB).
+
+Reference structure followed (APP = FeatureCraft-PyQt-App):
+  generate_octaves_pyramid            APP/utils/SIFT_scale_space.py:163-210
+  generate_gaussian_images_in_octave  APP/utils/SIFT_scale_space.py:109-160
+  represent_keypoints                 APP/utils/keypoint_descriptor.py:42-69   (scale range quirk)
+  dog_keypoints_orientations          APP/utils/keypoint_descriptor.py:116-172
+  extract_sift_descriptors            APP/utils/keypoint_descriptor.py:230-289
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from math import cos, sin
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import ptr, require_cuda, scan_scratch, stream_ptr, to_device
+
+
+@dataclass(frozen=True)
+class SiftParams:
+    """Defaults = the app's (APP/FeatureCraft_Backend.py:58-63)."""
+
+    n_octaves: int = 4
+    s_value: int = 2
+    sigma_base: float = 1.6
+    contrast_th: float = 0.03
+    ratio_th: float = 10
+    variant: str = "app"  # "app": keep every extremum; "script": SIFT.py contrast + edge tests
+    dtype: str = "f32"  # storage / arithmetic type of the scale space: "f32" (production) or "f64" (exact mode)
+
+    @property
+    def torch_dtype(self):
+        return torch.float32 if self.dtype == "f32" else torch.float64
+
+    @property
+    def fc_dtype(self):
+        return _lib.FC_F32 if self.dtype == "f32" else _lib.FC_F64
+
+    @property
+    def n_levels(self):
+        return self.s_value + 3
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side parameter tables (the reference builds the same tables on the host; a7 in SURVEY 8(a))
+# ---------------------------------------------------------------------------------------------
+def sigma_levels(sigma, s):
+    """generateGaussianKernels' sigma sequence: repeated multiplication by 2**(1/s) (SS:46-56)."""
+    out = [sigma]
+    lvl = sigma
+    k = 2 ** (1 / s)
+    for _ in range(1, s + 3):
+        lvl *= k
+        out.append(lvl)
+    return out
+
+
+def kernel_radius(sigma):
+    """gaussian_filter_kernel's half width: ((4*sigma)+1)//2 in float arithmetic (SS:18-20)."""
+    return int(((4 * sigma) + 1) // 2)
+
+
+def separable_taps(sigma):
+    """g(x) = exp(-x^2/2s^2)/sqrt(2*pi*s^2): outer(g, g) is the reference's (unnormalised, truncated)
+    2-D kernel exp(-r^2/2s^2)/(2*pi*s^2) to 1 ulp."""
+    r = kernel_radius(sigma)
+    x = np.arange(-r, r + 1, dtype=np.float64)
+    return np.exp(-(x ** 2) / (2 * sigma ** 2)) / np.sqrt(2 * np.pi * (sigma ** 2))
+
+
+def gaussian_window_table(sigma):
+    """gaussian_filter_kernel(sigma) as the dense 2-D table the orientation stage multiplies by (SS:22-28)."""
+    r = kernel_radius(sigma)
+    x = np.arange(-r, r + 1)[:, np.newaxis]
+    y = np.arange(-r, r + 1)
+    k = np.exp(-(x ** 2 + y ** 2) / (2 * sigma ** 2))
+    k /= 2 * np.pi * (sigma ** 2)
+    return k
+
+
+def gaussian_mask16(sigma, n=16):
+    """get_gaussian_mask (KD:215-227): sum-normalised Gaussian centred at (n-1)/2."""
+    if not sigma > 0:
+        raise ValueError("Invalid value of Sigma")
+    k = np.fromfunction(
+        lambda x, y: (1 / (2 * np.pi * sigma ** 2)) * np.exp(-((x - (n - 1) / 2) ** 2 + (y - (n - 1) / 2) ** 2) / (2 * sigma ** 2)),
+        (n, n),
+    )
+    return k / np.sum(k)
+
+
+def keypoint_sigma(sigma_base, octave_idx, scale_idx, s):
+    """KD:127-134 / :244-251 with the reference's operation order."""
+    return 1.5 * sigma_base * (2 ** octave_idx) * ((2 ** (1 / s)) ** (scale_idx))
+
+
+def trig_table():
+    """Per orientation bin: cos, sin of theta*3.14159/180 (KD:182) and the fixed-point column deltas
+    rint(cos*x*1024), rint(sin*x*1024), x = 0..15, of cv2.warpAffine's nearest-neighbour path."""
+    t = np.zeros((36, 34), dtype=np.float64)
+    xs = np.arange(16)
+    for b in range(36):
+        theta = ((b + 0.5) * (360.0 / 36) % 360) * (3.14159 / 180)
+        c, s = cos(theta), sin(theta)
+        t[b, 0], t[b, 1] = c, s
+        t[b, 2:18] = np.rint(c * xs * 1024)
+        t[b, 18:34] = np.rint(s * xs * 1024)
+    return t
+
+
+_TABLE_CACHE: dict = {}
+
+
+def _cached(key, builder):
+    dev = torch.cuda.current_device()
+    k = (dev,) + key
+    t = _TABLE_CACHE.get(k)
+    if t is None:
+        t = to_device(np.ascontiguousarray(builder(), dtype=np.float64))
+        _TABLE_CACHE[k] = t
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Octave:
+    gauss: torch.Tensor  # [B, L, h, w]
+    extrema: torch.Tensor | None  # [L-3, B, h, ceil(w/32)] int32 bit masks, index k-1
+    height: int
+    width: int
+
+
+@dataclass
+class ScaleBlock:
+    """Everything for one (octave, scale): keypoints (image,row,col), oriented (image,row,col,bin), descriptors."""
+
+    octave: int
+    scale: int
+    keypoints: torch.Tensor
+    oriented: torch.Tensor | None = None
+    descriptors: torch.Tensor | None = None
+
+
+@dataclass
+class SiftResult:
+    params: SiftParams
+    octaves: list
+    blocks: list = field(default_factory=list)
+
+    def assemble(self, batch: int):
+        """Per-image (points [m,5] float64 = (i, j, octave, scale, angle), descriptors [m,128]) in the
+        reference's emission order (octave, scale, row-major, bin)."""
+        pts, desc = [], []
+        for blk in self.blocks:
+            if blk.oriented is None or blk.oriented.shape[0] == 0:
+                continue
+            o = blk.oriented
+            p = torch.empty((o.shape[0], 6), dtype=torch.float64, device=o.device)
+            p[:, 0] = o[:, 0]
+            p[:, 1] = o[:, 1]
+            p[:, 2] = o[:, 2]
+            p[:, 3] = blk.octave
+            p[:, 4] = blk.scale
+            p[:, 5] = o[:, 3].to(torch.float64) * 10.0 + 5.0
+            pts.append(p)
+            desc.append(blk.descriptors)
+        if not pts:
+            e = np.zeros((0, 5))
+            return [(e, np.zeros((0, 128), dtype=np.float32)) for _ in range(batch)]
+        p = torch.cat(pts)
+        d = torch.cat(desc)
+        order = torch.sort(p[:, 0], stable=True).indices
+        p = p[order]
+        d = d[order]
+        counts = torch.bincount(p[:, 0].to(torch.int64), minlength=batch).cpu().numpy()
+        p = p[:, 1:].cpu().numpy()
+        d = d.cpu().numpy()
+        out, lo = [], 0
+        for b in range(batch):
+            out.append((p[lo:lo + counts[b]], d[lo:lo + counts[b]]))
+            lo += counts[b]
+        return out
+
+
+def _as_base_batch(base, params: SiftParams) -> torch.Tensor:
+    t = to_device(base)
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3:
+        raise ValueError("expected [H,W] or [B,H,W] grayscale base images")
+    if t.dtype == torch.float64 and params.dtype == "f32":
+        out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+        _lib.call("fc_convert_f64", ptr(t.contiguous()), C.c_int64(t.numel()), _lib.FC_F32, ptr(out), stream_ptr())
+        return out
+    return t.to(params.torch_dtype).contiguous()
+
+
+def gauss_octave(base: torch.Tensor, params: SiftParams, octave_index: int, with_extrema: bool = True) -> Octave:
+    """generate_gaussian_images_in_octave for a [B,h,w] batch (SS:109-160)."""
+    b, h, w = base.shape
+    L = params.n_levels
+    sig = sigma_levels(params.sigma_base, params.s_value)
+    taps = [separable_taps(s) for s in sig]
+    lens = (C.c_int * L)(*[len(t) for t in taps])
+    flat = np.ascontiguousarray(np.concatenate(taps))
+    gauss = torch.empty((b, L, h, w), dtype=params.torch_dtype, device=base.device)
+    extrema = None
+    if with_extrema and L >= 4:
+        extrema = torch.empty((L - 3, b, h, (w + 31) // 32), dtype=torch.int32, device=base.device)
+    filt = _lib.FC_FILTER_SCRIPT if params.variant == "script" else _lib.FC_FILTER_APP
+    if params.variant == "script" and L - 3 >= 3:
+        # SIFT.py:206 indexes a 3-deep stack with the global k: k >= 3 raises in the reference
+        raise IndexError("index 3 is out of bounds for axis 2 with size 3")
+    _lib.call("fc_gauss_octave", ptr(base), params.fc_dtype, b, h, w, L, flat.ctypes.data_as(C.c_void_p),
+              C.cast(lens, C.c_void_p), 1 if octave_index > 0 else 0, filt, float(params.contrast_th),
+              float(params.ratio_th), ptr(gauss), ptr(extrema), stream_ptr())
+    return Octave(gauss, extrema, h, w)
+
+
+def downsample(octv: Octave, params: SiftParams) -> torch.Tensor:
+    """next base = G[-3][::2, ::2] (SS:209)."""
+    b, L, h, w = octv.gauss.shape
+    out = torch.empty((b, (h + 1) // 2, (w + 1) // 2), dtype=octv.gauss.dtype, device=octv.gauss.device)
+    _lib.call("fc_downsample2", ptr(octv.gauss), params.fc_dtype, b, L, L - 3, h, w, ptr(out), stream_ptr())
+    return out
+
+
+def scale_space(base, params: SiftParams, with_extrema: bool = True) -> list:
+    """generate_octaves_pyramid (SS:163-210) for a batch of base images."""
+    img = _as_base_batch(base, params)
+    octaves = []
+    for o in range(params.n_octaves):
+        octv = gauss_octave(img, params, o, with_extrema)
+        octaves.append(octv)
+        if o + 1 < params.n_octaves:
+            img = downsample(octv, params)
+    return octaves
+
+
+def keypoints_from_mask(mask: torch.Tensor, width: int) -> torch.Tensor:
+    """np.argwhere order (image, row, col) int32 triples of a [B,h,pitch] bit mask."""
+    b, h, _ = mask.shape
+    rows = b * h
+    row_offsets = torch.empty(rows + 1, dtype=torch.int32, device=mask.device)
+    scratch = scan_scratch(rows)
+    _lib.call("fc_mask_scan", ptr(mask), b, h, width, ptr(row_offsets), ptr(scratch), stream_ptr())
+    total = int(row_offsets[-1].item())
+    kps = torch.empty((total, 3), dtype=torch.int32, device=mask.device)
+    if total:
+        _lib.call("fc_mask_emit_keypoints", ptr(mask), ptr(row_offsets), b, h, width, ptr(kps), stream_ptr())
+    return kps
+
+
+def gradient_field(octv: Octave, level: int, params: SiftParams):
+    b, L, h, w = octv.gauss.shape
+    mag = torch.empty((b, h, w), dtype=octv.gauss.dtype, device=octv.gauss.device)
+    direction = torch.empty_like(mag)
+    obin = torch.empty((b, h, w), dtype=torch.uint8, device=mag.device)
+    _lib.call("fc_gradient_field", ptr(octv.gauss), params.fc_dtype, b, L, level, h, w, ptr(mag), ptr(direction), ptr(obin),
+              stream_ptr())
+    return mag, direction, obin
+
+
+def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
+    """dog_keypoints_orientations for one (octave, scale): -> oriented [m,4] int32 (image,row,col,bin)."""
+    n = keypoints.shape[0]
+    dev = mag.device
+    if n == 0:
+        return torch.empty((0, 4), dtype=torch.int32, device=dev)
+    radius = int(round(sigma * 2))
+    if 2 * kernel_radius(sigma) + 1 != 2 * radius + 1:
+        # the reference multiplies a (2r+1)^2 window by the kernel: shapes must agree or numpy raises
+        raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,%d)"
+                         % (2 * radius + 1, 2 * radius + 1, 2 * kernel_radius(sigma) + 1, 2 * kernel_radius(sigma) + 1))
+    weights = _cached(("ori", float(sigma)), lambda: gaussian_window_table(sigma))
+    b, h, w = mag.shape
+    bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), params.fc_dtype, b, h, w, ptr(keypoints), n, ptr(weights), radius,
+              ptr(bin_mask), stream_ptr())
+    offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    scratch = scan_scratch(n)
+    _lib.call("fc_orientation_scan", ptr(bin_mask), n, ptr(offsets), ptr(scratch), stream_ptr())
+    total = int(offsets[-1].item())
+    oriented = torch.empty((total, 4), dtype=torch.int32, device=dev)
+    if total:
+        _lib.call("fc_orientation_emit", ptr(keypoints), ptr(bin_mask), ptr(offsets), n, ptr(oriented), stream_ptr())
+    return oriented
+
+
+def describe(mag, direction, oriented, sigma, params: SiftParams, out_dtype=torch.float32) -> torch.Tensor:
+    """extract_sift_descriptors for one (octave, scale): -> [m,128]."""
+    m = oriented.shape[0]
+    desc = torch.empty((m, 128), dtype=out_dtype, device=mag.device)
+    if m == 0:
+        return desc
+    gmask = _cached(("gmask", float(sigma)), lambda: gaussian_mask16(sigma))
+    trig = _cached(("trig",), trig_table)
+    b, h, w = mag.shape
+    _lib.call("fc_descriptors", ptr(mag), ptr(direction), params.fc_dtype, b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig),
+              ptr(desc), _lib.FC_F32 if out_dtype == torch.float32 else _lib.FC_F64, stream_ptr())
+    return desc
+
+
+def active_scales(params: SiftParams):
+    """represent_keypoints builds masks for dog_idx in range(1, n_octaves-1) (KD:60: len(DoG) is the
+    number of OCTAVES); get_keypoints only ever emits k in 1..s.  dog_keypoints_orientations then reads
+    img_gaussians[o][dog_idx] for every mask, raising IndexError when dog_idx >= s+3."""
+    ks = list(range(1, params.n_octaves - 1))
+    if ks and ks[-1] >= params.n_levels:
+        raise IndexError("list index out of range")
+    return [k for k in ks if k <= params.s_value]
+
+
+def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch.float32, keep_octaves: bool = False) -> SiftResult:
+    """The whole hot path after the x2 up-sample: computeKeypointsAndDescriptors (KD:297-311) for a
+    [B,H,W] batch of base images."""
+    require_cuda()
+    scales = active_scales(params)
+    img = _as_base_batch(base, params)
+    res = SiftResult(params, [])
+    for o in range(params.n_octaves):
+        octv = gauss_octave(img, params, o, True)
+        if o + 1 < params.n_octaves:
+            img = downsample(octv, params)
+        for k in scales:
+            kps = keypoints_from_mask(octv.extrema[k - 1], octv.width)
+            blk = ScaleBlock(o, k, kps)
+            if kps.shape[0]:
+                sigma = keypoint_sigma(params.sigma_base, o, k, params.s_value)
+                mag, direction, obin = gradient_field(octv, k, params)
+                blk.oriented = orient(mag, obin, kps, sigma, params)
+                blk.descriptors = describe(mag, direction, blk.oriented, sigma, params, out_dtype)
+            res.blocks.append(blk)
+        if keep_octaves:
+            res.octaves.append(octv)
+    return res

@@ -105,6 +105,10 @@ FC_API int fc_mask_scan(const uint32_t* mask, int batch, int height, int width, 
 /* coords: [total][2] int32 (row, col); values (optional): map gathered at those pixels. */
 FC_API int fc_mask_emit(const uint32_t* mask, const int32_t* row_offsets, int batch, int height, int width,
                  const double* map, int32_t* coords, double* values, void* stream);
+/* same order, but (image, row, col) int32 triples: the keypoint records the SIFT stages consume
+ * (np.argwhere(mask) of represent_keypoints' bool images, APP/utils/keypoint_descriptor.py:42-69, :144). */
+FC_API int fc_mask_emit_keypoints(const uint32_t* mask, const int32_t* row_offsets, int batch, int height, int width,
+                           int32_t* keypoints, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SIFT scale space (APP/utils/SIFT_scale_space.py)
@@ -116,7 +120,7 @@ FC_API int fc_mask_emit(const uint32_t* mask, const int32_t* row_offsets, int ba
  * for first_is_identity != 0 level 0 is the base itself (octaves > 0, :136-137).
  * gauss: [batch][n_levels][h][w] of `dtype`.  The 3x3x3 extremum rule of get_keypoints (:78-88) is
  * evaluated on DoG_k = G_{k+1} - G_k for k = 1 .. n_levels-3 and written as bit masks
- * extrema: [batch][n_levels-3][h][(w+31)/32]; with filter == FC_FILTER_SCRIPT the contrast and
+ * extrema: [n_levels-3][batch][h][(w+31)/32] (one batch of masks per k, ready for fc_mask_scan); with filter == FC_FILTER_SCRIPT the contrast and
  * edge-ratio tests are applied too.  base has element type `dtype`. */
 FC_API int fc_gauss_octave(const void* base, int dtype, int batch, int height, int width, int n_levels,
                     const double* taps_host, const int* tap_len_host, int first_is_identity, int filter,
@@ -135,17 +139,18 @@ FC_API int fc_convert_f64(const double* src, int64_t n, int dtype, void* dst, vo
  * ------------------------------------------------------------------------------------------- */
 
 /* sift_gradient (:72-79) of level `level` of a [batch][n_levels][h][w] stack: magnitude and
- * direction (degrees, wrapped with Python's % 360), stored in `dtype`, each [batch][h][w]. */
+ * direction (degrees, wrapped with Python's % 360), stored in `dtype`, each [batch][h][w], plus
+ * orientation_bin = np.round(direction * 36 / 360) (:140-142; 0..36, half to even) as uint8. */
 FC_API int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
-                      void* magnitude, void* direction, void* stream);
+                      void* magnitude, void* direction, uint8_t* orientation_bin, void* stream);
 
 /* dog_keypoints_orientations (:116-172) for one (octave, scale): keypoints are (image, row, col)
  * int32 triples in reference order; weights_host is gaussian_filter_kernel(sigma) as a dense
  * (2r+1)^2 float64 table that the caller uploaded to `weights` (device).  For keypoint n the 36-bin
  * float32 histogram is built and bin_mask[n] receives bit b for every bin with
  * hist[b] >= float32(0.8) * max (:165-167). */
-FC_API int fc_orientation_bins(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
-                        const int32_t* keypoints, int n_keypoints, const double* weights, int radius,
+FC_API int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
+                        int width, const int32_t* keypoints, int n_keypoints, const double* weights, int radius,
                         uint64_t* bin_mask, void* stream);
 
 /* Expand bin masks into oriented keypoints in reference order: offsets[n] = popcount prefix
