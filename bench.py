@@ -223,10 +223,9 @@ WORKLOADS = {"harris": HarrisWorkload}
 
 def pick_workload(name):
     try:
-        from bench_sift import SiftWorkload, MatchWorkload  # noqa: F401  (added when the SIFT path lands)
+        from bench_sift import SiftWorkload  # noqa: F401
 
         WORKLOADS["sift"] = SiftWorkload
-        WORKLOADS["match"] = MatchWorkload
     except ImportError:
         pass
     if name is None:
@@ -269,6 +268,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="images per step per GPU")
     ap.add_argument("--ref-items-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sift-dtype", default=None, choices=["f32", "f64"])
     args = ap.parse_args()
     wl_cls = pick_workload(args.workload)
     wl = wl_cls(args)
@@ -363,7 +363,8 @@ def main():
             n_items = getattr(wl, "cpu_sample_items", cores)
             wall, res = cpu_pool_run(wl.cpu_task, wl.cpu_items(n_items), min(cores, n_items))
             line["cpu_baseline"] = {"value": wl.cpu_units(n_items) / wall, "unit": wl.unit, "cores": min(cores, n_items),
-                                    "kind": "port", "sample": "%d image(s) of the workload shape through the oracle, %.1f s wall" % (n_items, wall)}
+                                    "kind": "port", "sample": "%d image(s) %s through the oracle, %.1f s wall"
+                                    % (n_items, getattr(wl, "cpu_sample_note", "of the workload shape"), wall)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

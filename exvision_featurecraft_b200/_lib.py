@@ -44,6 +44,10 @@ SIGNATURES = {
     "fc_mask_emit": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "fc_mask_emit_keypoints": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "fc_gauss_octave": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _d, _d, _p, _p, _p]),
+    "fc_gauss_octave_extrema": (_i, [_p, _i, _i, _i, _i, _i, _i, _d, _d, _p, _p]),
+    "fc_dog_extrema": (_i, [_p, _i, _i, _i, _i, _i, _i, _d, _d, _p, _p]),
+    "fc_upsample2": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "fc_rotated_window": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, _i, _p, _p]),
     "fc_downsample2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fc_convert_f64": (_i, [_p, _i64, _i, _p, _p]),
     "fc_gradient_field": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

@@ -231,9 +231,36 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
   for (int k = 0; k < 4; ++k) dst[k] = (OUT)__ddiv_rn(f[k], nrm2);
 }
 
+// rotated_subimage (APP/utils/keypoint_descriptor.py:175-212) as a standalone call: any theta, any size
+// up to 64x64; cos/sin are computed by the caller with the reference's own libm calls.
+__global__ void rotated_window_kernel(const double* __restrict__ image, int H, int W, double cx, double cy, double cs,
+                                      double sn, int width, int height, double* __restrict__ out) {
+  const int x = threadIdx.x, y = threadIdx.y;
+  if (x >= width || y >= height) return;
+  const double sx = __dsub_rn(__dsub_rn(cx, __dmul_rn(cs, (width - 1) / 2.0)), __dmul_rn(-sn, (height - 1) / 2.0));
+  const double sy = __dsub_rn(__dsub_rn(cy, __dmul_rn(sn, (width - 1) / 2.0)), __dmul_rn(cs, (height - 1) / 2.0));
+  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(-sn, (double)y), sx), 1024.0)) + 512;
+  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(cs, (double)y), sy), 1024.0)) + 512;
+  const int X = (X0 + __double2int_rn(__dmul_rn(__dmul_rn(cs, (double)x), 1024.0))) >> 10;
+  const int Y = (Y0 + __double2int_rn(__dmul_rn(__dmul_rn(sn, (double)x), 1024.0))) >> 10;
+  out[y * width + x] = (X >= 0 && X < W && Y >= 0 && Y < H) ? image[(size_t)Y * W + X] : 0.0;
+}
+
 }  // namespace fc
 
 using namespace fc;
+
+extern "C" int fc_rotated_window(const double* image, int height, int width, double center_x, double center_y,
+                                 double cos_theta, double sin_theta, int out_width, int out_height, double* out, void* stream) {
+  if (!image || !out || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (out_width < 1 || out_height < 1 || out_width * out_height > 1024) return FC_ERR_UNSUPPORTED;
+  dim3 block(out_width, out_height);
+  rotated_window_kernel<<<1, block, 0, (cudaStream_t)stream>>>(image, height, width, center_x, center_y, cos_theta,
+                                                              sin_theta, out_width, out_height, out);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
 
 extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
                                  void* magnitude, void* direction, uint8_t* orientation_bin, void* stream) {

@@ -182,13 +182,13 @@ static constexpr int kExTX = 32, kExTY = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(kExTX * kExTY)
-extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int L, int filter, double contrast_th, double ratio_th,
-               uint32_t* __restrict__ extrema, int pitch) {
+extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int L, int is_dog, int filter, double contrast_th,
+               double ratio_th, uint32_t* __restrict__ extrema, int pitch) {
   // DoG tile: (L-1) levels x (TY+2) x (TX+2)
   __shared__ T sD[(kMaxLevels - 1) * (kExTY + 2) * (kExTX + 2)];
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * kExTX, y0 = blockIdx.y * kExTY;
-  const int nd = L - 1;
+  const int nd = is_dog ? L : L - 1;  // is_dog: the L levels ARE the DoG images (get_keypoints called directly)
   const T* g = gauss + (size_t)b * L * H * W;
   constexpr int TW = kExTX + 2, TH = kExTY + 2;
   const int tid = threadIdx.y * kExTX + threadIdx.x;
@@ -196,17 +196,21 @@ extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int L, int filt
     const int r = t / TW, c = t - r * TW;
     const int y = y0 - 1 + r, x = x0 - 1 + c;
     const bool in = (y >= 0 && y < H && x >= 0 && x < W);
-    T prev = in ? g[(size_t)y * W + x] : T(0);
-    for (int l = 0; l < nd; ++l) {
-      T cur = in ? g[((size_t)(l + 1) * H + y) * W + x] : T(0);
-      sD[(l * TH + r) * TW + c] = cur - prev;
-      prev = cur;
+    if (is_dog) {
+      for (int l = 0; l < nd; ++l) sD[(l * TH + r) * TW + c] = in ? g[((size_t)l * H + y) * W + x] : T(0);
+    } else {
+      T prev = in ? g[(size_t)y * W + x] : T(0);
+      for (int l = 0; l < nd; ++l) {
+        T cur = in ? g[((size_t)(l + 1) * H + y) * W + x] : T(0);
+        sD[(l * TH + r) * TW + c] = cur - prev;
+        prev = cur;
+      }
     }
   }
   __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
   const bool center_ok = (y >= 1 && y <= H - 3 && x >= 1 && x <= W - 3);
-  const int nk = L - 3;
+  const int nk = nd - 2;
   for (int k = 1; k <= nk; ++k) {
     bool hit = false;
     if (center_ok) {
@@ -308,11 +312,11 @@ static int launch_octave(const void* base, int B, int H, int W, int L, const dou
 }
 
 template <typename T>
-static int launch_extrema(const void* gauss, int B, int H, int W, int L, int filter, double cth, double rth,
+static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_dog, int filter, double cth, double rth,
                           uint32_t* extrema, cudaStream_t st) {
   const int pitch = div_up(W, 32);
   dim3 grid(pitch, div_up(H, kExTY), B), block(kExTX, kExTY);
-  extrema_kernel<T><<<grid, block, 0, st>>>((const T*)gauss, B, H, W, L, filter, cth, rth, extrema, pitch);
+  extrema_kernel<T><<<grid, block, 0, st>>>((const T*)gauss, B, H, W, L, is_dog, filter, cth, rth, extrema, pitch);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
@@ -335,10 +339,74 @@ extern "C" int fc_gauss_octave(const void* base, int dtype, int batch, int heigh
                : launch_octave<double, 32, 32>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st);
   if (rc != FC_OK) return rc;
   if (extrema && n_levels >= 4) {
-    rc = dtype == FC_F32 ? launch_extrema<float>(gauss, batch, height, width, n_levels, filter, contrast_th, ratio_th, extrema, st)
-                         : launch_extrema<double>(gauss, batch, height, width, n_levels, filter, contrast_th, ratio_th, extrema, st);
+    rc = dtype == FC_F32 ? launch_extrema<float>(gauss, batch, height, width, n_levels, 0, filter, contrast_th, ratio_th, extrema, st)
+                         : launch_extrema<double>(gauss, batch, height, width, n_levels, 0, filter, contrast_th, ratio_th, extrema, st);
   }
   return rc;
+}
+
+extern "C" int fc_gauss_octave_extrema(const void* gauss, int dtype, int batch, int height, int width, int n_levels,
+                                       int filter, double contrast_th, double ratio_th, uint32_t* extrema, void* stream) {
+  if (!gauss || !extrema || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (n_levels < 4 || n_levels > kMaxLevels) return FC_ERR_BAD_ARG;
+  if (filter != FC_FILTER_APP && filter != FC_FILTER_SCRIPT) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FC_F32) return launch_extrema<float>(gauss, batch, height, width, n_levels, 0, filter, contrast_th, ratio_th, extrema, st);
+  if (dtype == FC_F64) return launch_extrema<double>(gauss, batch, height, width, n_levels, 0, filter, contrast_th, ratio_th, extrema, st);
+  return FC_ERR_BAD_ARG;
+}
+
+extern "C" int fc_dog_extrema(const void* dog, int dtype, int batch, int height, int width, int n_dog, int filter,
+                              double contrast_th, double ratio_th, uint32_t* extrema, void* stream) {
+  if (!dog || !extrema || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (n_dog < 3 || n_dog > kMaxLevels - 1) return FC_ERR_BAD_ARG;
+  if (filter != FC_FILTER_APP && filter != FC_FILTER_SCRIPT) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FC_F32) return launch_extrema<float>(dog, batch, height, width, n_dog, 1, filter, contrast_th, ratio_th, extrema, st);
+  if (dtype == FC_F64) return launch_extrema<double>(dog, batch, height, width, n_dog, 1, filter, contrast_th, ratio_th, extrema, st);
+  return FC_ERR_BAD_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x2 bilinear up-sample with pixel-centre alignment and mirror border: the `rescale(img, 2)` in front of the
+// pyramid (APP/utils/keypoint_descriptor.py:296).  out[2k] = .25 a[k-1] + .75 a[k], out[2k+1] = .75 a[k] + .25 a[k+1]
+// per axis, with a[-1] = a[1], a[n] = a[n-2].  Input float64, output `dtype`.
+// ------------------------------------------------------------------------------------------------
+namespace fc {
+__device__ __forceinline__ int mirror_idx(int k, int n) {
+  if (n == 1) return 0;
+  if (k < 0) k = -k;
+  if (k >= n) k = 2 * n - 2 - k;
+  return k;
+}
+template <typename T>
+__global__ void upsample2_kernel(const double* __restrict__ in, int H, int W, T* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= 2 * W) return;
+  const double* a = in + (size_t)b * H * W;
+  const int ky = y >> 1, kx = x >> 1;
+  const int y2 = mirror_idx((y & 1) ? ky + 1 : ky - 1, H), x2 = mirror_idx((x & 1) ? kx + 1 : kx - 1, W);
+  // rows first (like the separable spline filter), then columns
+  const double r0 = __dadd_rn(__dmul_rn(0.75, a[(size_t)ky * W + kx]), __dmul_rn(0.25, a[(size_t)y2 * W + kx]));
+  const double r1 = __dadd_rn(__dmul_rn(0.75, a[(size_t)ky * W + x2]), __dmul_rn(0.25, a[(size_t)y2 * W + x2]));
+  out[((size_t)b * 2 * H + y) * 2 * W + x] = (T)__dadd_rn(__dmul_rn(0.75, r0), __dmul_rn(0.25, r1));
+}
+}  // namespace fc
+
+extern "C" int fc_upsample2(const double* image, int batch, int height, int width, int dtype, void* out, void* stream) {
+  if (!image || !out || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  dim3 grid(div_up(2 * width, 256), 2 * height, batch);
+  if (dtype == FC_F32)
+    upsample2_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(image, height, width, (float*)out);
+  else if (dtype == FC_F64)
+    upsample2_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(image, height, width, (double*)out);
+  else
+    return FC_ERR_BAD_ARG;
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
 }
 
 extern "C" int fc_downsample2(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,

@@ -5,6 +5,3 @@ extern "C" int64_t fc_match_workspace_bytes(int, int) { return 0; }
 extern "C" int fc_match_knn2(const float*, int, const float*, int, double, int32_t*, float*, uint8_t*, void*, void*) {
   return FC_ERR_UNSUPPORTED;
 }
-extern "C" int fc_match_knn2_exact(const float*, int, const float*, int, double, int32_t*, float*, uint8_t*, void*) {
-  return FC_ERR_UNSUPPORTED;
-}

@@ -120,6 +120,55 @@ def trig_table():
 _TABLE_CACHE: dict = {}
 
 
+class StageTimer:
+    """Optional CUDA-event timing of the pipeline stages (bench.py installs one; None = no overhead)."""
+
+    def __init__(self):
+        self.events = []
+
+    class _Ctx:
+        def __init__(self, owner, name):
+            self.owner, self.name = owner, name
+
+        def __enter__(self):
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+        def __exit__(self, *exc):
+            self.b.record()
+            self.owner.events.append((self.name, self.a, self.b))
+
+    def stage(self, name):
+        return StageTimer._Ctx(self, name)
+
+    def totals(self):
+        """ms per stage name, summed (call after a synchronize)."""
+        out = {}
+        for name, a, b in self.events:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+    def reset(self):
+        self.events = []
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+TIMER: StageTimer | None = None
+_NULL = _NullCtx()
+
+
+def _stage(name):
+    return TIMER.stage(name) if TIMER is not None else _NULL
+
+
 def _cached(key, builder):
     dev = torch.cuda.current_device()
     k = (dev,) + key
@@ -204,12 +253,24 @@ def _as_base_batch(base, params: SiftParams) -> torch.Tensor:
     return t.to(params.torch_dtype).contiguous()
 
 
-def gauss_octave(base: torch.Tensor, params: SiftParams, octave_index: int, with_extrema: bool = True) -> Octave:
-    """generate_gaussian_images_in_octave for a [B,h,w] batch (SS:109-160)."""
+def upsample2(gray, params: SiftParams) -> torch.Tensor:
+    """rescale(gray, 2, anti_aliasing=False) (KD:296) for [H,W] or [B,H,W] float64 images -> [B,2H,2W]."""
+    t = to_device(np.asarray(gray, dtype=np.float64) if not isinstance(gray, torch.Tensor) else gray, torch.float64)
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    b, h, w = t.shape
+    out = torch.empty((b, 2 * h, 2 * w), dtype=params.torch_dtype, device=t.device)
+    _lib.call("fc_upsample2", ptr(t), b, h, w, params.fc_dtype, ptr(out), stream_ptr())
+    return out
+
+
+def gauss_octave(base: torch.Tensor, params: SiftParams, octave_index: int, with_extrema: bool = True, taps=None) -> Octave:
+    """generate_gaussian_images_in_octave for a [B,h,w] batch (SS:109-160).  `taps` overrides the separable
+    taps derived from (sigma_base, s_value) -- used when the caller hands in its own kernel list."""
     b, h, w = base.shape
     L = params.n_levels
-    sig = sigma_levels(params.sigma_base, params.s_value)
-    taps = [separable_taps(s) for s in sig]
+    if taps is None:
+        taps = [separable_taps(s) for s in sigma_levels(params.sigma_base, params.s_value)]
     lens = (C.c_int * L)(*[len(t) for t in taps])
     flat = np.ascontiguousarray(np.concatenate(taps))
     gauss = torch.empty((b, L, h, w), dtype=params.torch_dtype, device=base.device)
@@ -220,9 +281,14 @@ def gauss_octave(base: torch.Tensor, params: SiftParams, octave_index: int, with
     if params.variant == "script" and L - 3 >= 3:
         # SIFT.py:206 indexes a 3-deep stack with the global k: k >= 3 raises in the reference
         raise IndexError("index 3 is out of bounds for axis 2 with size 3")
-    _lib.call("fc_gauss_octave", ptr(base), params.fc_dtype, b, h, w, L, flat.ctypes.data_as(C.c_void_p),
-              C.cast(lens, C.c_void_p), 1 if octave_index > 0 else 0, filt, float(params.contrast_th),
-              float(params.ratio_th), ptr(gauss), ptr(extrema), stream_ptr())
+    with _stage("pyramid_o%d" % octave_index):
+        _lib.call("fc_gauss_octave", ptr(base), params.fc_dtype, b, h, w, L, flat.ctypes.data_as(C.c_void_p),
+                  C.cast(lens, C.c_void_p), 1 if octave_index > 0 else 0, filt, float(params.contrast_th),
+                  float(params.ratio_th), ptr(gauss), None, stream_ptr())
+    if extrema is not None:
+        with _stage("extrema"):
+            _lib.call("fc_gauss_octave_extrema", ptr(gauss), params.fc_dtype, b, h, w, L, filt, float(params.contrast_th),
+                      float(params.ratio_th), ptr(extrema), stream_ptr())
     return Octave(gauss, extrema, h, w)
 
 
@@ -332,13 +398,17 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
         if o + 1 < params.n_octaves:
             img = downsample(octv, params)
         for k in scales:
-            kps = keypoints_from_mask(octv.extrema[k - 1], octv.width)
+            with _stage("compact"):
+                kps = keypoints_from_mask(octv.extrema[k - 1], octv.width)
             blk = ScaleBlock(o, k, kps)
             if kps.shape[0]:
                 sigma = keypoint_sigma(params.sigma_base, o, k, params.s_value)
-                mag, direction, obin = gradient_field(octv, k, params)
-                blk.oriented = orient(mag, obin, kps, sigma, params)
-                blk.descriptors = describe(mag, direction, blk.oriented, sigma, params, out_dtype)
+                with _stage("gradient_field"):
+                    mag, direction, obin = gradient_field(octv, k, params)
+                with _stage("orientation"):
+                    blk.oriented = orient(mag, obin, kps, sigma, params)
+                with _stage("descriptors"):
+                    blk.descriptors = describe(mag, direction, blk.oriented, sigma, params, out_dtype)
             res.blocks.append(blk)
         if keep_octaves:
             res.octaves.append(octv)

@@ -126,6 +126,22 @@ FC_API int fc_gauss_octave(const void* base, int dtype, int batch, int height, i
                     const double* taps_host, const int* tap_len_host, int first_is_identity, int filter,
                     double contrast_th, double ratio_th, void* gauss, uint32_t* extrema, void* stream);
 
+/* the extrema half of fc_gauss_octave on an existing [batch][n_levels][h][w] stack (extrema == NULL there
+ * skips it): lets a caller time / re-run the two kernels separately. */
+FC_API int fc_gauss_octave_extrema(const void* gauss, int dtype, int batch, int height, int width, int n_levels,
+                            int filter, double contrast_th, double ratio_th, uint32_t* extrema, void* stream);
+
+/* get_keypoints (APP/utils/SIFT_scale_space.py:60-106 / SIFT.py:172-222) called directly on a stack of
+ * n_dog >= 3 DoG images [batch][n_dog][h][w]: extrema [n_dog-2][batch][h][(w+31)/32], plane k-1 for DoG k. */
+FC_API int fc_dog_extrema(const void* dog, int dtype, int batch, int height, int width, int n_dog, int filter,
+                   double contrast_th, double ratio_th, uint32_t* extrema, void* stream);
+
+/* rescale(gray, 2, anti_aliasing=False) in front of the pyramid (APP/utils/keypoint_descriptor.py:296):
+ * bilinear, pixel-centre aligned, mirror border (== scipy.ndimage.zoom(order=1, mode='mirror',
+ * grid_mode=True); scikit-image itself is not in this image).  image: [batch][h][w]
+ * float64; out: [batch][2h][2w] of `dtype`. */
+FC_API int fc_upsample2(const double* image, int batch, int height, int width, int dtype, void* out, void* stream);
+
 /* img[::2, ::2] (APP/utils/SIFT_scale_space.py:209) of level `level` of a [batch][n_levels][h][w]
  * stack into a dense [batch][(h+1)/2][(w+1)/2] array. */
 FC_API int fc_downsample2(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
@@ -170,6 +186,12 @@ FC_API int fc_orientation_emit(const int32_t* keypoints, const uint64_t* bin_mas
 FC_API int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
                    const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
                    void* descriptors, int out_dtype, void* stream);
+
+/* rotated_subimage (:175-212) on its own: nearest-neighbour window of out_width x out_height (<= 1024
+ * samples) around (center_x, center_y) with cv2.warpAffine's 10-bit fixed-point coordinates; the caller
+ * passes cos/sin of theta*3.14159/180.  image and out are float64. */
+FC_API int fc_rotated_window(const double* image, int height, int width, double center_x, double center_y,
+                      double cos_theta, double sin_theta, int out_width, int out_height, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Matching (APP/utils/keypoint_descriptor.py:330-349)
