@@ -56,6 +56,7 @@ SIGNATURES = {
     "fc_orientation_emit": (_i, [_p, _p, _p, _i, _p, _p]),
     "fc_descriptors": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
     "fc_match_workspace_bytes": (_i64, [_i, _i]),
+    "fc_match_workspace_stats_offset": (_i64, [_i, _i]),
     "fc_match_knn2": (_i, [_p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),
     "fc_match_knn2_exact": (_i, [_p, _i, _p, _i, _d, _p, _p, _p, _p]),
 }

@@ -23,8 +23,24 @@ def _as_desc(d) -> torch.Tensor:
     return t.contiguous()
 
 
+#: diagnostics of the last tensor-engine call: {"rechecked_rows": int tensor (device), "overflow": ...}; read lazily
+LAST_STATS = None
+
+
+def last_stats() -> dict:
+    """Rows the last tensor-engine call re-checked with the exact kernel, and the fp16 overflow flag (syncs)."""
+    if LAST_STATS is None:
+        return {}
+    v = LAST_STATS.cpu().numpy()
+    return {"overflow": int(v[1]), "rechecked_rows": int(v[2])}
+
+
 def knn2(query, train, ratio: float = 0.3, engine: str = "tensor"):
-    """-> (knn_idx [nq,2] int32, knn_dist [nq,2] float32, good [nq] bool), all CUDA tensors."""
+    """-> (knn_idx [nq,2] int32, knn_dist [nq,2] float32, good [nq] bool), all CUDA tensors.
+
+    engine="tensor": good[], and for rows with good=1 knn_idx[:,0] / knn_dist[:,0], are exactly the brute-force
+    float32 results (proved per row by the candidate bounds, otherwise the row is re-done exactly); the second
+    neighbour of rows that clearly fail the ratio test is the best candidate found.  engine="exact": everything."""
     dev = require_cuda()
     q, t = _as_desc(query), _as_desc(train)
     nq, nt = q.shape[0], t.shape[0]
@@ -42,6 +58,9 @@ def knn2(query, train, ratio: float = 0.3, engine: str = "tensor"):
         nbytes = int(_lib.load().fc_match_workspace_bytes(nq, nt))
         ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
         _lib.call("fc_match_knn2", ptr(q), nq, ptr(t), nt, float(ratio), ptr(idx), ptr(dist), ptr(good), ptr(ws), stream_ptr())
+        global LAST_STATS
+        off = int(_lib.load().fc_match_workspace_stats_offset(nq, nt))
+        LAST_STATS = ws[off:off + 16].view(torch.int32)
     else:
         raise ValueError("engine must be 'tensor' or 'exact'")
     return idx, dist, good.bool()

@@ -205,6 +205,9 @@ FC_API int fc_rotated_window(const double* image, int height, int width, double 
  * good: [n_query] uint8 = dist0 < ratio * dist1 (evaluated in double, strict).  workspace must hold
  * fc_match_workspace_bytes(n_query, n_train) bytes. */
 FC_API int64_t fc_match_workspace_bytes(int n_query, int n_train);
+/* byte offset inside the workspace of four uint32 diagnostics written by fc_match_knn2: bits of max |t|^2,
+ * fp16-overflow flag (1 = whole call re-done exactly), number of rows re-checked exactly, reserved. */
+FC_API int64_t fc_match_workspace_stats_offset(int n_query, int n_train);
 FC_API int fc_match_knn2(const float* query, int n_query, const float* train, int n_train, double ratio,
                   int32_t* knn_idx, float* knn_dist, uint8_t* good, void* workspace, void* stream);
 /* exact float32 brute force on CUDA cores (same outputs); the verification twin of fc_match_knn2 */

@@ -161,3 +161,39 @@ def test_matching_random_vs_oracle(engine):
         if engine == "exact":
             assert np.array_equal(idx, ref_idx)
             assert np.array_equal(dist, ref_dist)
+
+
+def test_tensor_matcher_rarely_needs_the_exact_recheck():
+    """The tcgen05 candidates + bounds must decide almost every row on their own (otherwise the test above
+    would pass on the exact fallback alone), and agree with the exact engine at a size that spans many tiles,
+    several splits and a ragged tail."""
+    import torch
+
+    from exvision_featurecraft_b200 import matching
+
+    rng = np.random.default_rng(11)
+    nq, nt = 5000, 7777
+    b = np.abs(rng.normal(0, 1, (nt, 128))).astype(np.float32)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    a = np.abs(rng.normal(0, 1, (nq, 128))).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    pick = rng.integers(0, nt, nq // 2)
+    a[: nq // 2] = b[pick] + rng.normal(0, 0.01, (nq // 2, 128)).astype(np.float32)
+    for ratio in (0.3, 0.8):
+        ei, ed, eg = matching.knn2(a, b, ratio, "exact")
+        ti, td, tg = matching.knn2(a, b, ratio, "tensor")
+        st = matching.last_stats()
+        assert st["overflow"] == 0
+        assert st["rechecked_rows"] <= 0.05 * nq, st
+        assert torch.equal(eg, tg)
+        g = eg.nonzero().flatten()
+        assert g.numel() > nq // 4
+        assert torch.equal(ei[g, 0], ti[g, 0]) and torch.equal(ed[g, 0], td[g, 0])
+        # the nearest neighbour itself is almost always identical even for rows that fail the ratio test
+        assert (ei[:, 0] == ti[:, 0]).float().mean() > 0.99
+    # fp16 overflow -> the call falls back to the exact kernel for every row
+    big = a * 1e5
+    ei, ed, eg = matching.knn2(big, b, 0.8, "exact")
+    ti, td, tg = matching.knn2(big, b, 0.8, "tensor")
+    assert matching.last_stats()["overflow"] == 1
+    assert torch.equal(ei, ti) and torch.equal(eg, tg)
