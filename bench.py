@@ -223,9 +223,10 @@ WORKLOADS = {"harris": HarrisWorkload}
 
 def pick_workload(name):
     try:
-        from bench_sift import SiftWorkload  # noqa: F401
+        from bench_sift import MatchWorkload, SiftWorkload  # noqa: F401
 
         WORKLOADS["sift"] = SiftWorkload
+        WORKLOADS["match"] = MatchWorkload
     except ImportError:
         pass
     if name is None:

@@ -91,5 +91,96 @@ class SiftWorkload:
         return n * 256 * 256 / 1e6
 
 
+def _cpu_match_task(args):
+    nq, nt, seed = args
+    import time
+
+    from oracle import featurecraft_oracle as O
+
+    a, b = match_sets(nq, nt, seed)
+    t0 = time.perf_counter()
+    O.match_indices(a, b, 0.3)
+    return time.perf_counter() - t0, nq
+
+
+def match_sets(nq, nt, seed):
+    """Unit-norm non-negative descriptor sets; half of the queries are noisy copies of train rows."""
+    rng = np.random.default_rng(seed)
+    b = np.abs(rng.standard_normal((nt, 128), dtype=np.float32))
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    a = np.abs(rng.standard_normal((nq, 128), dtype=np.float32))
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    h = nq // 2
+    a[:h] = b[rng.integers(0, nt, h)] + rng.normal(0, 0.01, (h, 128)).astype(np.float32)
+    return a, b
+
+
 class MatchWorkload:
-    pass
+    """Brute-force 2-NN + ratio test between two descriptor sets of the size one 1024x1024 image yields
+    (BASELINE configs[2]/[4] matching leg): value = descriptor pairs compared per second."""
+
+    name = "match"
+    metric = "match_descriptor_pairs_per_sec"
+    unit = "Gpairs/s"
+    dtype = "fp16 tcgen05 candidates, fp32 exact re-rank"
+    cpu_sample_items = 16
+    cpu_sample_note = "(2048 x 8192 descriptor sets per task: float32 brute force of the oracle)"
+
+    def __init__(self, args):
+        self.nq = self.nt = (args.batch or 128) * 1024
+
+    def describe(self, world):
+        return {"workload": "2-NN ratio-test matching of %d query x %d train 128-d float32 descriptors per step per GPU "
+                            "(synthetic unit vectors, half of the queries have a true match)" % (self.nq, self.nt),
+                "sharding": "independent pairs of descriptor sets, no collective",
+                "l2": "operands per step (%.0f MB fp32 + %.0f MB fp16) vs 126 MB L2: train tiles are re-read from L2 by design"
+                      % ((self.nq + self.nt) * 512 / 1e6, (self.nq + self.nt) * 288 / 1e6)}
+
+    def units_per_step(self):
+        return self.nq * self.nt / 1e9
+
+    def setup(self, rank, torch):
+        from exvision_featurecraft_b200 import matching
+
+        self.torch, self.matching = torch, matching
+        a, b = match_sets(self.nq, self.nt, rank)
+        self.host_a = torch.from_numpy(a).pin_memory()
+        self.host_b = torch.from_numpy(b).pin_memory()
+        self.a = self.host_a.cuda()
+        self.b = self.host_b.cuda()
+        self.ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(64)]
+        self.ev_i = 0
+
+    def step_device(self, record=False):
+        if record and self.ev_i < len(self.ev):
+            e0, e1 = self.ev[self.ev_i]
+            self.ev_i += 1
+            e0.record()
+            out = self.matching.knn2(self.a, self.b, 0.3, "tensor")
+            e1.record()
+            return out
+        return self.matching.knn2(self.a, self.b, 0.3, "tensor")
+
+    def step_e2e(self):
+        a = self.host_a.cuda(non_blocking=True)
+        b = self.host_b.cuda(non_blocking=True)
+        idx, dist, good = self.matching.knn2(a, b, 0.3, "tensor")
+        q = self.torch.nonzero(good).flatten()
+        out = (q.cpu(), idx[q, 0].cpu(), dist[q, 0].cpu())
+        return (self.nq + self.nt) * 512, sum(t.numel() * t.element_size() for t in out)
+
+    def dominant_kernel(self):
+        ms = [a.elapsed_time(b) for a, b in self.ev[: self.ev_i]]
+        # whole knn2 call (prep + GEMM + re-rank + re-check); algorithmic FLOPs = 2 * nq * nt * 128
+        return "match_tc_kernel (+prep, re-rank, re-check)", 2.0 * self.nq * self.nt * 128, float(np.mean(ms)) if ms else None, "tensor"
+
+    def extra(self):
+        return self.matching.last_stats()
+
+    cpu_task = staticmethod(_cpu_match_task)
+
+    def cpu_items(self, n):
+        return [(2048, 8192, s) for s in range(n)]
+
+    def cpu_units(self, n):
+        return n * 2048 * 8192 / 1e9

@@ -1,6 +1,6 @@
 // Tensor-core 2-NN descriptor matching for sm_100a: tcgen05.mma (fp16 in, fp32 accumulate in TMEM), operand
-// tiles staged by bulk async copies (TMA unit, 1-D mode), fused per-row running top-4 in the epilogue, exact
-// float32 re-rank of the candidates and an exact CUDA-core re-check of the rows the bounds cannot decide.
+// tiles staged by bulk async copies (TMA unit, 1-D mode), fused per-row running top-4 of 16-row GROUP minima in
+// the epilogue, exact float32 re-rank of the members of the kept groups and an exact CUDA-core re-check of the rows the bounds cannot decide.
 //
 // Reference: cv2.BFMatcher().knnMatch(query, train, k=2) + ratio test (APP/utils/keypoint_descriptor.py:338-349).
 //
@@ -15,7 +15,7 @@
 //                        128-row train tiles), warp 1: MMA issuer (2 x 9 tcgen05.mma 128x128x16 per tile, two
 //                        accumulator stages = all 512 TMEM columns), warps 2-5: epilogue (tcgen05.ld, min-tree
 //                        fast path, sorted top-4 insert on the rare slow path).
-//   match_rerank_kernel  one warp per query: exact float32 distances of the <= 32 candidates (same operation order
+//   match_rerank_kernel  one warp per query: exact float32 distances of the members of the kept groups (same operation order
 //                        as the exact kernel), top-2, ratio test, and the bound test that proves the answer equals
 //                        the brute-force one; undecidable rows are appended to a list ...
 //   match_exact_kernel   ... and re-done exactly (fc_match_exact.cu).
@@ -38,9 +38,10 @@ constexpr int kTileRows = 128;
 constexpr int kTileBytes = kTileRows / 8 * kRowGroupBytes;  // 36864
 constexpr int kStages = 3;
 constexpr int kQueriesPerCta = 256;
-constexpr int kCand = 4;
-constexpr int kMaxSplits = 8;
-constexpr int kThreads = 192;
+constexpr int kCand = 4;   // kept groups per (query row, split)
+constexpr int kGroup = 16;  // train rows per group
+constexpr int kMaxSplits = 4;
+constexpr int kThreads = 320;  // producer warp, MMA warp, 8 epilogue warps
 constexpr float kPadNorm = 60000.0f;
 constexpr size_t kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 256;
 
@@ -81,8 +82,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -92,9 +92,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return r;
 }
 
 struct TopK {
@@ -119,13 +122,24 @@ struct TopK {
   }
 };
 
-__device__ __forceinline__ void scan_chunk(const float (&v)[32], int base, TopK& best) {
-  float m = v[0];
-#pragma unroll
-  for (int j = 1; j < 32; ++j) m = fminf(m, v[j]);
-  if (m < best.s[3]) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) best.insert(v[j], base + j);
+__device__ __forceinline__ float min16(const uint32_t* r) {
+  const float a = min3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+  const float b = min3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
+  const float c = min3(__uint_as_float(r[6]), __uint_as_float(r[7]), __uint_as_float(r[8]));
+  const float d = min3(__uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
+  const float e = min3(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]));
+  return min3(min3(a, b, c), min3(d, e, __uint_as_float(r[15])), INFINITY);
+}
+
+// 32 accumulator columns of one row = two groups of 16 consecutive train rows.  Only the MINIMUM of each group
+// is tracked (FMNMX3 trees, no per-element branches): the running top-4 GROUPS per query row are kept, and the
+// re-rank kernel evaluates all 16 members of the kept groups exactly.  The k-th best row always lies in one of
+// the k best groups, and every row outside the kept groups scores >= the 4th kept group minimum.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], int group0, TopK& best) {
+  const float lo = min16(r), hi = min16(r + 16);
+  if (fminf(lo, hi) < best.s[3]) {
+    best.insert(lo, group0);
+    best.insert(hi, group0 + 1);
   }
 }
 
@@ -199,7 +213,7 @@ match_tc_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, in
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(a_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -251,37 +265,42 @@ match_tc_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, in
       }
     }
   } else {
-    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = query rows of both 128-row halves
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 only; warps 2-5 take the first 128 queries (h = 0),
+    // warps 6-9 the second 128 (h = 1).  Loads are software pipelined: chunk c+1 is in flight while c is scanned.
     const int lg = warp & 3;
+    const int h = (warp - 2) >> 2;
     const int row = lg * 32 + lane;
-    TopK best[2];
-    best[0].init();
-    best[1].init();
+    TopK best;
+    best.init();
     for (int it = 0; it < n_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(t_full + acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int n0 = (tile0 + it) * kTileRows;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 256 + h * 128 + c * 32, v);
-          scan_chunk(v, n0 + c * 32, best[h]);
-        }
-      }
+      const int n0 = (tile0 + it) * (kTileRows / kGroup);  // first 16-row group of this tile
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 256 + h * 128;
+      uint32_t ra[32], rb[32];
+      tmem_ld32_issue(taddr, ra);
+      tmem_ld_wait();
+      tmem_ld32_issue(taddr + 32, rb);
+      scan_chunk(ra, n0, best);
+      tmem_ld_wait();
+      tmem_ld32_issue(taddr + 64, ra);
+      scan_chunk(rb, n0 + 2, best);
+      tmem_ld_wait();
+      tmem_ld32_issue(taddr + 96, rb);
+      scan_chunk(ra, n0 + 4, best);
+      tmem_ld_wait();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + acc);
+      if (lane == 0) mbar_arrive(t_empty + acc);  // TMEM stage is free as soon as the registers hold it
+      scan_chunk(rb, n0 + 6, best);
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    {
       const size_t q = (size_t)qtile * kQueriesPerCta + h * 128 + row;
       const size_t o = ((size_t)split * n_query_padded + q) * kCand;
-      *reinterpret_cast<float4*>(cand_score + o) = make_float4(best[h].s[0], best[h].s[1], best[h].s[2], best[h].s[3]);
-      *reinterpret_cast<int4*>(cand_idx + o) = make_int4(best[h].i[0], best[h].i[1], best[h].i[2], best[h].i[3]);
+      *reinterpret_cast<float4*>(cand_score + o) = make_float4(best.s[0], best.s[1], best.s[2], best.s[3]);
+      *reinterpret_cast<int4*>(cand_idx + o) = make_int4(best.i[0], best.i[1], best.i[2], best.i[3]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -296,6 +315,16 @@ match_tc_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, in
 // exact re-rank of the candidates + decision bounds (see DESIGN.md "Matching: why the tensor path is exact")
 // ------------------------------------------------------------------------------------------------
 static constexpr int kRerankWarps = 4;
+
+struct Best2 {
+  float d0, d1;
+  int i0, i1;
+  __device__ __forceinline__ void init() { d0 = d1 = INFINITY; i0 = i1 = 0x7fffffff; }
+  __device__ __forceinline__ void push(float d, int i) {
+    if (d < d0 || (d == d0 && i < i0)) { d1 = d0; i1 = i0; d0 = d; i0 = i; }
+    else if (d < d1 || (d == d1 && i < i1)) { d1 = d; i1 = i; }
+  }
+};
 
 __global__ void __launch_bounds__(kRerankWarps * 32)
 match_rerank_kernel(const float* __restrict__ query, int n_query, int n_query_padded, const float* __restrict__ train,
@@ -313,51 +342,59 @@ match_rerank_kernel(const float* __restrict__ query, int n_query, int n_query_pa
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
   __syncwarp();
-  int idx = -1;
-  float approx = INFINITY;
+  // kept groups: lane l < n_splits*kCand holds (group id, group minimum)
+  int grp = -1;
+  float gmin = INFINITY;
   if (lane < n_splits * kCand) {
     const size_t o = ((size_t)(lane / kCand) * n_query_padded + q) * kCand + (lane % kCand);
-    idx = cand_idx[o];
-    approx = cand_score[o];
-    if (idx >= n_train) idx = -1;
+    grp = cand_idx[o];
+    gmin = cand_score[o];
   }
-  // smallest approximate score any NON-candidate can have: min over splits of the split's 4th kept score
-  float s4 = (lane < n_splits * kCand && (lane % kCand) == kCand - 1 && idx >= 0) ? approx : INFINITY;
+  // smallest approximate score any row OUTSIDE the kept groups can have: min over splits of the 4th kept minimum
+  float s4 = (lane < n_splits * kCand && (lane % kCand) == kCand - 1) ? gmin : INFINITY;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s4 = fminf(s4, __shfl_xor_sync(0xffffffffu, s4, o));
-  float d = INFINITY;
-  if (idx >= 0) {
-    const float* t = train + (size_t)idx * kDim;
-    float acc = 0.0f;
-#pragma unroll 8
-    for (int k = 0; k < kDim; ++k) {
-      const float df = __fsub_rn(sQ[warp][k], __ldg(t + k));
-      acc = __fadd_rn(acc, __fmul_rn(df, df));
+  // exact float32 distances (same operation order as match_exact_kernel) of every member of the kept groups
+  Best2 b;
+  b.init();
+  const int n_cand = n_splits * kCand * kGroup;
+  for (int c = lane; c < n_cand; c += 32) {
+    const int g = __shfl_sync(0xffffffffu, grp, c / kGroup);
+    const int row = g * kGroup + (c % kGroup);
+    if (g >= 0 && row < n_train) {
+      const float4* t = reinterpret_cast<const float4*>(train + (size_t)row * kDim);
+      float acc = 0.0f;
+#pragma unroll 4
+      for (int k4 = 0; k4 < kDim / 4; ++k4) {
+        const float4 tv = __ldg(t + k4);
+        float df = __fsub_rn(sQ[warp][4 * k4], tv.x);
+        acc = __fadd_rn(acc, __fmul_rn(df, df));
+        df = __fsub_rn(sQ[warp][4 * k4 + 1], tv.y);
+        acc = __fadd_rn(acc, __fmul_rn(df, df));
+        df = __fsub_rn(sQ[warp][4 * k4 + 2], tv.z);
+        acc = __fadd_rn(acc, __fmul_rn(df, df));
+        df = __fsub_rn(sQ[warp][4 * k4 + 3], tv.w);
+        acc = __fadd_rn(acc, __fmul_rn(df, df));
+      }
+      const float d = sqrtf(acc);
+      if (d == d) b.push(d, row);
     }
-    d = sqrtf(acc);
-    if (!(d == d)) { d = INFINITY; idx = -1; }
   }
-  // two rounds of lexicographic (d, idx) arg-min
+  // warp merge of the lane-local best-2 lists: two rounds of lexicographic arg-min; the winning lane pops
   float d0, d1;
   int i0, i1;
-  {
-    float bd = d; int bi = idx < 0 ? 0x7fffffff : idx;
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    float bd = b.d0;
+    int bi = b.i0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float od = __shfl_xor_sync(0xffffffffu, bd, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
     }
-    d0 = bd; i0 = bi;
-    float cd = (idx >= 0 && idx == i0) ? INFINITY : d;
-    int ci = (idx < 0 || idx == i0) ? 0x7fffffff : idx;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, cd, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-      if (od < cd || (od == cd && oi < ci)) { cd = od; ci = oi; }
-    }
-    d1 = cd; i1 = ci;
+    if (round == 0) { d0 = bd; i0 = bi; } else { d1 = bd; i1 = bi; }
+    if (b.i0 == bi && bi != 0x7fffffff) { b.d0 = b.d1; b.i0 = b.i1; b.d1 = INFINITY; b.i1 = 0x7fffffff; }
   }
   if (i0 == 0x7fffffff) i0 = -1;
   if (i1 == 0x7fffffff) i1 = -1;
@@ -368,20 +405,20 @@ match_rerank_kernel(const float* __restrict__ query, int n_query, int n_query_pa
     // the two-term fp16 split of |t|^2 and fp32 accumulation
     const float qn = sqrtf(q2), tn = sqrtf(tmax);
     const float delta = 2.0f * (0.0009775f * qn * tn + 6.8e-7f * (qn + tn)) + 2e-6f * (1.0f + q2 + tmax);
-    const float lb2 = s4 + q2 - delta;  // lower bound on the true squared distance of every non-candidate
+    const float lb2 = s4 + q2 - delta;  // lower bound on the true squared distance of every row outside the kept groups
     const float lb = lb2 > 0.f ? sqrtf(lb2) : 0.f;
-    const bool all_seen = !(s4 < INFINITY);  // fewer than 4 train rows per split: every row was a candidate
     const double r = ratio;
     const bool is_good = i1 >= 0 && (double)d0 < r * (double)d1;
     bool decided;
-    if (all_seen || lb > d1) {
-      decided = true;  // the candidates contain the true two nearest neighbours
+    if (lb > d1) {
+      decided = true;  // the kept groups contain the true two nearest neighbours
     } else if (is_good) {
       decided = (d0 < lb) && ((double)d0 < r * (double)fminf(lb, d1));
     } else {
       decided = ((double)lb >= r * (double)d0);
     }
-    if (overflow || i0 < 0) decided = overflow ? false : true;
+    if (overflow) decided = false;
+    else if (i0 < 0) decided = true;  // NaN query row: no match (the reference would raise)
     knn_idx[2 * (size_t)q] = i0;
     knn_idx[2 * (size_t)q + 1] = i1;
     knn_dist[2 * (size_t)q] = d0;
@@ -407,10 +444,15 @@ static Plan make_plan(int nq, int nt) {
   p.nt_pad = div_up(nt, kTileRows) * kTileRows;
   p.n_qtiles = p.nq_pad / kQueriesPerCta;
   p.n_tiles = p.nt_pad / kTileRows;
-  int want = div_up(2 * 148, p.n_qtiles);
-  if (want > kMaxSplits) want = kMaxSplits;
-  if (want > p.n_tiles) want = p.n_tiles;
-  if (want < 1) want = 1;
+  // number of train splits: fill the 148 SMs (1 CTA each) in whole waves, keep >= 16 tiles per CTA when possible
+  int want = 1;
+  double best_eff = -1.0;
+  for (int s = 1; s <= kMaxSplits && s <= p.n_tiles; ++s) {
+    if (s > 1 && p.n_tiles / s < 16) break;
+    const int ctas = p.n_qtiles * s;
+    const double eff = (double)ctas / ((double)div_up(ctas, 148) * 148.0);
+    if (eff > best_eff + 0.02) { best_eff = eff; want = s; }
+  }
   p.tiles_per_split = div_up(p.n_tiles, want);
   p.splits = div_up(p.n_tiles, p.tiles_per_split);
   auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
