@@ -317,16 +317,22 @@ def main():
     launches = _lib.launch_count() - n0
     ms = e0.elapsed_time(e1)
     # end to end: pinned host -> device -> hot path -> results on the host
+    # (workloads with a pipelined driver overlap the D2H of step i with the kernels of step i+1; the timed
+    # region still contains every step's H2D, kernels and D2H, closed by e2e_end() + synchronize)
+    begin, end = getattr(wl, "e2e_begin", None), getattr(wl, "e2e_end", None)
+    if begin:
+        begin()
     wl.step_e2e()
+    if end:
+        end()
     barrier()
     t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
     for _ in range(args.steps):
         h2d, d2h = wl.step_e2e()
-    g1.record()
+    if end:
+        h2d, d2h = end()
     barrier()
-    e2e_ms = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    e2e_ms = (time.perf_counter() - t0) * 1e3  # host clock around synchronised ends: includes every copy and sync
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -205,6 +205,35 @@ class SiftResult:
     octaves: list
     blocks: list = field(default_factory=list)
 
+    def assemble_device(self, batch: int):
+        """Device tensors (points [M,5] float64, descriptors [M,128], per-image counts [B] int64), images
+        concatenated, each image in the reference's emission order (octave, scale, row-major, bin)."""
+        pts, desc = [], []
+        for blk in self.blocks:
+            if blk.oriented is None or blk.oriented.shape[0] == 0:
+                continue
+            o = blk.oriented
+            p = torch.empty((o.shape[0], 6), dtype=torch.float64, device=o.device)
+            p[:, :3] = o[:, :3]
+            p[:, 3] = blk.octave
+            p[:, 4] = blk.scale
+            p[:, 5] = o[:, 3].to(torch.float64) * 10.0 + 5.0
+            pts.append(p)
+            desc.append(blk.descriptors)
+        if not pts:
+            dev = require_cuda()
+            return (torch.zeros((0, 5), dtype=torch.float64, device=dev), torch.zeros((0, 128), dtype=torch.float32, device=dev),
+                    torch.zeros(batch, dtype=torch.int64, device=dev))
+        p = torch.cat(pts)
+        d = torch.cat(desc)
+        img = p[:, 0].to(torch.int64)
+        counts = torch.bincount(img, minlength=batch)
+        if batch > 1:
+            order = torch.sort(img, stable=True).indices
+            p = p[order]
+            d = d[order]
+        return p[:, 1:].contiguous(), d, counts
+
     def assemble(self, batch: int):
         """Per-image (points [m,5] float64 = (i, j, octave, scale, angle), descriptors [m,128]) in the
         reference's emission order (octave, scale, row-major, bin)."""
@@ -413,3 +442,85 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
         if keep_octaves:
             res.octaves.append(octv)
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# host <-> device pipeline for streams of image batches
+# ---------------------------------------------------------------------------------------------
+class BatchExtractor:
+    """computeKeypointsAndDescriptors for a stream of equally shaped image batches that live on the HOST.
+
+    Three CUDA streams: pinned input -> device (copy-in), the kernels (compute, = the caller's current stream),
+    results -> pinned output (copy-out).  `submit` returns as soon as the work of a batch is queued; `collect`
+    waits for its copy-out only, so the D2H of batch i overlaps the kernels of batch i+1 (descriptors are
+    ~80 MB per 1024x1024 image: PCIe, not the kernels, bounds the end-to-end rate)."""
+
+    def __init__(self, params: SiftParams, batch: int, height: int, width: int, max_descriptors: int, depth: int = 2,
+                 upsample: bool = True):
+        dev = require_cuda()
+        self.params, self.batch, self.h, self.w, self.depth, self.upsample = params, batch, height, width, depth, upsample
+        self.cap = int(max_descriptors)
+        self.copy_in = torch.cuda.Stream(device=dev)
+        self.copy_out = torch.cuda.Stream(device=dev)
+        self.host_in = [torch.empty((batch, height, width), dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.dev_in = [torch.empty((batch, height, width), dtype=torch.float64, device=dev) for _ in range(depth)]
+        self.host_desc = [torch.empty((self.cap, 128), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.host_pts = [torch.empty((self.cap, 5), dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.host_cnt = [torch.empty(batch, dtype=torch.int64).pin_memory() for _ in range(depth)]
+        self.slots = [None] * depth
+        self.n_submitted = 0
+
+    def submit(self, images) -> int:
+        """images: [B,H,W] float64 numpy array / CPU tensor (copied into the pinned staging buffer) or None to
+        reuse what the staging buffer of this slot already holds.  Returns a ticket for collect()."""
+        ticket = self.n_submitted
+        slot = ticket % self.depth
+        if self.slots[slot] is not None:
+            raise RuntimeError("collect() the batch submitted %d calls ago before reusing its buffers" % self.depth)
+        if images is not None:
+            src = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+            self.host_in[slot].copy_(src)
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_in):
+            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(self.copy_in)
+        compute.wait_event(ev_in)
+        base = upsample2(self.dev_in[slot], self.params) if self.upsample else _as_base_batch(self.dev_in[slot], self.params)
+        res = detect_and_describe(base, self.params, out_dtype=torch.float32)
+        pts, desc, counts = res.assemble_device(self.batch)
+        m = int(pts.shape[0])
+        if m > self.cap:
+            raise _lib.FeatureCraftError("batch produced %d descriptors, more than max_descriptors=%d" % (m, self.cap))
+        ev_done = torch.cuda.Event()
+        ev_done.record(compute)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(ev_done)
+            self.host_desc[slot][:m].copy_(desc, non_blocking=True)
+            self.host_pts[slot][:m].copy_(pts, non_blocking=True)
+            self.host_cnt[slot].copy_(counts, non_blocking=True)
+            ev_out = torch.cuda.Event()
+            ev_out.record(self.copy_out)
+        self.slots[slot] = (ev_out, m, (pts, desc, counts))  # keep the device tensors alive until the copy is done
+        self.n_submitted += 1
+        return ticket
+
+    def collect(self, ticket: int, copy: bool = False):
+        """-> list of (points [m,5] float64, descriptors [m,128] float32) per image; views into the pinned
+        buffers (valid until the slot is reused) unless copy=True."""
+        slot = ticket % self.depth
+        ev_out, m, _keep = self.slots[slot]
+        ev_out.synchronize()
+        self.slots[slot] = None
+        cnt = self.host_cnt[slot].numpy()
+        pts = self.host_pts[slot][:m].numpy()
+        desc = self.host_desc[slot][:m].numpy()
+        out, lo = [], 0
+        for b in range(self.batch):
+            hi = lo + int(cnt[b])
+            out.append((pts[lo:hi].copy(), desc[lo:hi].copy()) if copy else (pts[lo:hi], desc[lo:hi]))
+            lo = hi
+        return out
+
+    def bytes_per_batch(self, ticket_result):
+        return self.batch * self.h * self.w * 8, sum(p.nbytes + d.nbytes for p, d in ticket_result) + self.batch * 8
