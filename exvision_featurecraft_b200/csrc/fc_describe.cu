@@ -91,9 +91,11 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
   const int nc = c1 - c0 + 1;
   const int total = (r1 - r0 + 1) * nc;
+  int rr = lane / nc, cc = lane - rr * nc;
   for (int t = lane; t < total; t += 32) {
-    const int rr = t / nc;
-    const int y = r0 + rr, x = c0 + (t - rr * nc);
+    const int y = r0 + rr, x = c0 + cc;
+    cc += 32;
+    while (cc >= nc) { cc -= nc; ++rr; }
     const size_t o = (size_t)y * W + x;
     const int bin = ob[o];
     const double w = __dmul_rn((double)m[o], weights[(y - ki + radius) * side + (x - kj + radius)]);
@@ -193,7 +195,10 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
       }
       wv = __dmul_rn(wv, gmask[wy * 16 + wx]);
       // bin = int(((dir - theta) % 360) * 8 / 360.0); 8 (dir - theta a hair below 0) is dropped
-      const double rel = py_mod360<double>(__dsub_rn(dv, theta));
+      // (dir - theta) % 360 with dir in [0, 360], theta in [5, 355]: |dir - theta| < 360, so Python's % is the
+      // identity for non-negative values and one rounded +360 otherwise (can give exactly 360.0 -> bin 8, dropped)
+      double rel = __dsub_rn(dv, theta);
+      if (rel < 0.0) rel = __dadd_rn(rel, 360.0);
       const int hb = (int)__ddiv_rn(__dmul_rn(rel, 8.0), 360.0);
 #pragma unroll
       for (int k = 0; k < 8; ++k) hist[k] += (hb == k) ? wv : 0.0;

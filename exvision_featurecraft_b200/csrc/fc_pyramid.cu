@@ -46,28 +46,33 @@ __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 
-// Vertical pass for one level: out rows [0, TY) of the tile, columns [c_lo, c_hi) of the input tile.
-// sIn row r <-> image row y0 - RMAX + r.  sTmp[y][c] with pitch tp.
-template <typename T, int R, int TY>
+// Taps are symmetric (g(-x) = g(x)): only the centre and one side are kept in registers and every output is
+// evaluated as c*v[0] + sum_k t_k (v[-k] + v[+k]).
+//
+// Vertical pass for one level: out rows [0, TY) of the tile, image columns [x0 - R, x0 + TX + R).
+// sIn row r <-> image row y0 - rmax + r.  sTmp[y][c] with pitch tp.
+template <typename T, int R, int TX, int TY>
 __device__ __forceinline__ void vertical_pass(const T* __restrict__ sIn, int ip, int rmax, T* __restrict__ sTmp, int tp,
-                                              int c_lo, int n_cols, int tmp_c0, const T* __restrict__ taps) {
-  T tap[2 * R + 1];
-#pragma unroll
-  for (int k = 0; k <= 2 * R; ++k) tap[k] = taps[k];
+                                              const T* __restrict__ taps) {
+  constexpr int RP = (R + 3) & ~3;
+  constexpr int NC = TX + 2 * R;
   constexpr int G = TY / 8;
-  for (int item = threadIdx.x; item < n_cols * G; item += blockDim.x) {
-    const int g = item / n_cols;
-    const int c = item - g * n_cols;
-    const T* src = sIn + (size_t)(rmax - R + g * 8) * ip + (c_lo + c);
+  T tap[R + 1];
+#pragma unroll
+  for (int k = 0; k <= R; ++k) tap[k] = taps[R + k];
+  for (int item = threadIdx.x; item < NC * G; item += blockDim.x) {
+    const int g = item / NC;
+    const int c = item - g * NC;
+    const T* src = sIn + (size_t)(rmax - R + g * 8) * ip + (rmax - R + c);
     T v[8 + 2 * R];
 #pragma unroll
     for (int k = 0; k < 8 + 2 * R; ++k) v[k] = src[k * ip];
-    T* dst = sTmp + (size_t)(g * 8) * tp + tmp_c0 + c;
+    T* dst = sTmp + (size_t)(g * 8) * tp + (RP - R) + c;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      T acc = tap[0] * v[j];
+      T acc = tap[0] * v[j + R];
 #pragma unroll
-      for (int k = 1; k <= 2 * R; ++k) acc = fma_t<T>(tap[k], v[j + k], acc);
+      for (int k = 1; k <= R; ++k) acc = fma_t<T>(tap[k], v[j + R - k] + v[j + R + k], acc);
       dst[j * tp] = acc;
     }
   }
@@ -80,9 +85,9 @@ __device__ __forceinline__ void horizontal_pass(const T* __restrict__ sTmp, int 
   constexpr int RP = (R + 3) & ~3;
   constexpr int NV = (4 + 2 * RP) / 4;
   using V4 = typename Vec4<T>::type;
-  T tap[2 * R + 1];
+  T tap[R + 1];
 #pragma unroll
-  for (int k = 0; k <= 2 * R; ++k) tap[k] = taps[k];
+  for (int k = 0; k <= R; ++k) tap[k] = taps[R + k];
   constexpr int G = TX / 4;
   for (int item = threadIdx.x; item < TY * G; item += blockDim.x) {
     const int y = item / G;
@@ -97,9 +102,9 @@ __device__ __forceinline__ void horizontal_pass(const T* __restrict__ sTmp, int 
     T r[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      T acc = tap[0] * v[j + RP - R];
+      T acc = tap[0] * v[j + RP];
 #pragma unroll
-      for (int k = 1; k <= 2 * R; ++k) acc = fma_t<T>(tap[k], v[j + RP - R + k], acc);
+      for (int k = 1; k <= R; ++k) acc = fma_t<T>(tap[k], v[j + RP - k] + v[j + RP + k], acc);
       r[j] = acc;
     }
     const int yy = y0 + y, xx = x0 + g * 4;
@@ -120,19 +125,19 @@ __device__ __forceinline__ void horizontal_pass(const T* __restrict__ sTmp, int 
 template <typename T, int R, int TX, int TY>
 __device__ __forceinline__ void blur_level(const T* sIn, int ip, int rmax, T* sTmp, int tp, const T* taps, T* out,
                                            int x0, int y0, int H, int W, bool vec_ok) {
-  constexpr int RP = (R + 3) & ~3;
-  // vertical results are needed for image columns [x0 - R, x0 + TX + R)
-  vertical_pass<T, R, TY>(sIn, ip, rmax, sTmp, tp, rmax - R, TX + 2 * R, RP - R, taps);
+  vertical_pass<T, R, TX, TY>(sIn, ip, rmax, sTmp, tp, taps);
   __syncthreads();
   horizontal_pass<T, R, TX, TY>(sTmp, tp, taps, out, x0, y0, H, W, vec_ok);
   __syncthreads();
 }
 
-template <typename T, int TX, int TY>
-__global__ void __launch_bounds__(256)
+// RCLASS = largest radius this instantiation can run (registers are sized by the largest unrolled case)
+template <typename T, int TX, int TY, int RCLASS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, int rmax, T* __restrict__ gauss) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int ip = TX + 2 * rmax + 1;            // input tile pitch (odd-ish: column reads are conflict free anyway)
+  const int iw = TX + 2 * rmax;
+  const int ip = iw + 1;                       // input tile pitch
   const int ih = TY + 2 * rmax;
   const int rp_max = (rmax + 3) & ~3;
   const int tp = TX + 2 * rp_max + 4;          // tmp pitch, multiple of 4
@@ -144,12 +149,21 @@ gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, i
   const T* img = base + (size_t)b * H * W;
   const int L = tab.n_levels;
   T* gout = gauss + (size_t)b * L * H * W;
-
-  for (int t = threadIdx.x; t < ih * (TX + 2 * rmax); t += blockDim.x) {
-    const int r = t / (TX + 2 * rmax), c = t - r * (TX + 2 * rmax);
-    const int y = reflect_symm(y0 - rmax + r, H);
-    const int x = reflect_symm(x0 - rmax + c, W);
-    sIn[(size_t)r * ip + c] = img[(size_t)y * W + x];
+  {
+    // one warp per tile row, lanes along the row: coalesced, reflection only where the tile leaves the image
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool interior_x = (x0 - rmax >= 0) && (x0 - rmax + iw <= W);
+    for (int r = warp; r < ih; r += 8) {
+      const int y = reflect_symm(y0 - rmax + r, H);
+      const T* row = img + (size_t)y * W;
+      T* dst = sIn + (size_t)r * ip;
+      if (interior_x) {
+        const T* src = row + (x0 - rmax);
+        for (int c = lane; c < iw; c += 32) dst[c] = src[c];
+      } else {
+        for (int c = lane; c < iw; c += 32) dst[c] = row[reflect_symm(x0 - rmax + c, W)];
+      }
+    }
   }
   __syncthreads();
   const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gauss) & (4 * sizeof(T) - 1)) == 0);
@@ -164,96 +178,153 @@ gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, i
       continue;
     }
     const T* taps = tab.taps + tab.offset[l];
-    switch (tab.radius[l]) {
-#define FC_CASE(RR) case RR: blur_level<T, RR, TX, TY>(sIn, ip, rmax, sTmp, tp, taps, out, x0, y0, H, W, vec_ok); break;
+    const int R = tab.radius[l];
+#define FC_CASE(RR) \
+  case RR:          \
+    if constexpr (RR <= RCLASS) blur_level<T, RR, TX, TY>(sIn, ip, rmax, sTmp, tp, taps, out, x0, y0, H, W, vec_ok); \
+    break;
+    switch (R) {
       FC_CASE(1) FC_CASE(2) FC_CASE(3) FC_CASE(4) FC_CASE(5) FC_CASE(6) FC_CASE(7) FC_CASE(8)
       FC_CASE(9) FC_CASE(10) FC_CASE(11) FC_CASE(12) FC_CASE(13) FC_CASE(14) FC_CASE(15) FC_CASE(16)
       FC_CASE(17) FC_CASE(18) FC_CASE(19) FC_CASE(20) FC_CASE(21) FC_CASE(22) FC_CASE(23) FC_CASE(24)
-#undef FC_CASE
       default: break;
     }
+#undef FC_CASE
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // 3x3x3 extrema on DoG (+ optional script filter)
 // ------------------------------------------------------------------------------------------------
-static constexpr int kExTX = 32, kExTY = 8;
+// Tile = 32 columns x 64 rows per block; warp w owns rows 8w .. 8w+7, lane = column, so one ballot is one mask word.
+// Fast path per pixel and DoG level: 3x3 max / min by a separable max3 (3 shared loads + 4 FMNMX3), sliding down
+// the column in registers.  A pixel can only be an extremum if centre >= max (or <= min) of the 3 planes' 3x3
+// blocks; only those (~1 %) run the exact 26-neighbour test with the reference's strict / non-strict tie rule.
+static constexpr int kExTX = 32, kExTY = 64, kExPitch = 36;
 
+template <typename T> __device__ __forceinline__ T max3_t(T a, T b, T c) { return fmax(fmax(a, b), c); }
+template <typename T> __device__ __forceinline__ T min3_t(T a, T b, T c) { return fmin(fmin(a, b), c); }
+template <> __device__ __forceinline__ float max3_t<float>(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+template <> __device__ __forceinline__ float min3_t<float>(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// exact rule of get_keypoints (:78-88) on the 3x3x3 block whose top-left corners are d0/d1/d2 (pitch TW)
 template <typename T>
-__global__ void __launch_bounds__(kExTX * kExTY)
-extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int L, int is_dog, int filter, double contrast_th,
+__device__ __forceinline__ bool exact_extremum(const T* d0, const T* d1, const T* d2, int TW) {
+  const T c = d1[TW + 1];
+  bool is_max = true, is_min = true;
+#pragma unroll
+  for (int di = 0; di < 3; ++di) {
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj) {
+      const int o = di * TW + dj;
+      const int flat = di * 9 + dj * 3;
+      const T a0 = d0[o], a1 = d1[o], a2 = d2[o];
+      // entries before the centre (flat index < 13): strict; after: non-strict (the first extremum wins)
+      if (flat + 0 < 13) { is_max &= c > a0; is_min &= c < a0; } else { is_max &= c >= a0; is_min &= c <= a0; }
+      if (flat + 1 < 13) { is_max &= c > a1; is_min &= c < a1; }
+      else if (flat + 1 > 13) { is_max &= c >= a1; is_min &= c <= a1; }
+      if (flat + 2 < 13) { is_max &= c > a2; is_min &= c < a2; } else { is_max &= c >= a2; is_min &= c <= a2; }
+    }
+  }
+  return is_max || is_min;
+}
+
+template <typename T, int ND>
+__global__ void __launch_bounds__(256)
+extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int is_dog, int filter, double contrast_th,
                double ratio_th, uint32_t* __restrict__ extrema, int pitch) {
-  // DoG tile: (L-1) levels x (TY+2) x (TX+2)
-  __shared__ T sD[(kMaxLevels - 1) * (kExTY + 2) * (kExTX + 2)];
+  extern __shared__ __align__(16) unsigned char ex_smem[];
+  T* sD = reinterpret_cast<T*>(ex_smem);  // [ND][TH][kExPitch]
+  constexpr int TW = kExPitch, TH = kExTY + 2;
+  const int L = is_dog ? ND : ND + 1;
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * kExTX, y0 = blockIdx.y * kExTY;
-  const int nd = is_dog ? L : L - 1;  // is_dog: the L levels ARE the DoG images (get_keypoints called directly)
   const T* g = gauss + (size_t)b * L * H * W;
-  constexpr int TW = kExTX + 2, TH = kExTY + 2;
-  const int tid = threadIdx.y * kExTX + threadIdx.x;
-  for (int t = tid; t < TH * TW; t += kExTX * kExTY) {
-    const int r = t / TW, c = t - r * TW;
-    const int y = y0 - 1 + r, x = x0 - 1 + c;
-    const bool in = (y >= 0 && y < H && x >= 0 && x < W);
-    if (is_dog) {
-      for (int l = 0; l < nd; ++l) sD[(l * TH + r) * TW + c] = in ? g[((size_t)l * H + y) * W + x] : T(0);
-    } else {
-      T prev = in ? g[(size_t)y * W + x] : T(0);
-      for (int l = 0; l < nd; ++l) {
-        T cur = in ? g[((size_t)(l + 1) * H + y) * W + x] : T(0);
-        sD[(l * TH + r) * TW + c] = cur - prev;
-        prev = cur;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < TH; r += 8) {
+    const int y = y0 - 1 + r;
+    for (int c = lane; c < kExTX + 2; c += 32) {
+      const int x = x0 - 1 + c;
+      const bool in = (y >= 0 && y < H && x >= 0 && x < W);
+      const size_t o = (size_t)y * W + x;
+      if (is_dog) {
+#pragma unroll
+        for (int l = 0; l < ND; ++l) sD[(l * TH + r) * TW + c] = in ? g[(size_t)l * H * W + o] : T(0);
+      } else {
+        T prev = in ? g[o] : T(0);
+#pragma unroll
+        for (int l = 0; l < ND; ++l) {
+          const T cur = in ? g[(size_t)(l + 1) * H * W + o] : T(0);
+          sD[(l * TH + r) * TW + c] = cur - prev;
+          prev = cur;
+        }
       }
     }
   }
   __syncthreads();
-  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  const bool center_ok = (y >= 1 && y <= H - 3 && x >= 1 && x <= W - 3);
-  const int nk = nd - 2;
-  for (int k = 1; k <= nk; ++k) {
-    bool hit = false;
-    if (center_ok) {
-      const T* d0 = sD + ((k - 1) * TH + threadIdx.y) * TW + threadIdx.x;  // top-left of the 3x3 window
-      const T* d1 = d0 + TH * TW;
-      const T* d2 = d1 + TH * TW;
-      const T c = d1[TW + 1];
-      bool is_max = true, is_min = true;
+  const int x = x0 + lane;
+  const int t0 = warp * 8;  // tile rows t0+1 .. t0+8 are this warp's output rows (tile row t <-> image row y0-1+t)
+  T hM[ND][3], hm[ND][3];
+  const T* col = sD + lane;  // columns lane, lane+1, lane+2 = x-1, x, x+1
 #pragma unroll
-      for (int di = 0; di < 3; ++di) {
+  for (int l = 0; l < ND; ++l) {
 #pragma unroll
-        for (int dj = 0; dj < 3; ++dj) {
-          const int o = di * TW + dj;
-          const int flat = di * 9 + dj * 3;
-          const T a0 = d0[o], a1 = d1[o], a2 = d2[o];
-          // entries before the centre (flat index < 13): strict; after: non-strict (first extremum wins)
-          if (flat + 0 < 13) { is_max &= c > a0; is_min &= c < a0; } else { is_max &= c >= a0; is_min &= c <= a0; }
-          if (flat + 1 < 13) { is_max &= c > a1; is_min &= c < a1; }
-          else if (flat + 1 > 13) { is_max &= c >= a1; is_min &= c <= a1; }
-          if (flat + 2 < 13) { is_max &= c > a2; is_min &= c < a2; } else { is_max &= c >= a2; is_min &= c <= a2; }
+    for (int q = 0; q < 2; ++q) {
+      const T* p = col + (l * TH + t0 + q) * TW;
+      hM[l][q + 1] = max3_t<T>(p[0], p[1], p[2]);
+      hm[l][q + 1] = min3_t<T>(p[0], p[1], p[2]);
+    }
+  }
+  for (int rr = 0; rr < 8; ++rr) {
+    const int t = t0 + 1 + rr;  // centre tile row
+    const int y = y0 - 1 + t;
+    T M[ND], m[ND];
+#pragma unroll
+    for (int l = 0; l < ND; ++l) {
+      hM[l][0] = hM[l][1]; hM[l][1] = hM[l][2];
+      hm[l][0] = hm[l][1]; hm[l][1] = hm[l][2];
+      const T* p = col + (l * TH + t + 1) * TW;
+      hM[l][2] = max3_t<T>(p[0], p[1], p[2]);
+      hm[l][2] = min3_t<T>(p[0], p[1], p[2]);
+      M[l] = max3_t<T>(hM[l][0], hM[l][1], hM[l][2]);
+      m[l] = min3_t<T>(hm[l][0], hm[l][1], hm[l][2]);
+    }
+    const bool center_ok = (y >= 1 && y <= H - 3 && x >= 1 && x <= W - 3);
+#pragma unroll
+    for (int k = 1; k <= ND - 2; ++k) {
+      bool hit = false;
+      const T c = col[(k * TH + t) * TW + 1];
+      if (center_ok && (c >= max3_t<T>(M[k - 1], M[k], M[k + 1]) || c <= min3_t<T>(m[k - 1], m[k], m[k + 1]))) {
+        const T* d1 = col + (k * TH + t - 1) * TW;
+        hit = exact_extremum<T>(d1 - TH * TW, d1, d1 + TH * TW, TW);
+        if (hit && filter == FC_FILTER_SCRIPT) {
+          // SIFT.py:202-215: contrast from DoG[2k-1] (local 3-stack indexed with the global k), Hessian on DoG[k]
+          const int ci = 2 * k - 1;
+          const double contrast = (ci < ND) ? (double)col[(ci * TH + t) * TW + 1] : 0.0;
+          const T* d = d1 + TW + 1;
+          const double c0 = (double)d[0];
+          const double dxx = __dadd_rn(__dsub_rn((double)d[1], __dmul_rn(2.0, c0)), (double)d[-1]);
+          const double dyy = __dadd_rn(__dsub_rn((double)d[TW], __dmul_rn(2.0, c0)), (double)d[-TW]);
+          const double dxy = __ddiv_rn(__dsub_rn(__dsub_rn((double)d[TW + 1], (double)d[TW - 1]),
+                                                 __dsub_rn((double)d[-TW + 1], (double)d[-TW - 1])), 4.0);
+          const double tr = __dadd_rn(dxx, dyy);
+          const double det = __dsub_rn(__dmul_rn(dxx, dyy), __dmul_rn(dxy, dxy));
+          const double r = __ddiv_rn(__dmul_rn(tr, tr), det);
+          if (fabs(contrast) < contrast_th) hit = false;
+          if (r > ratio_th) hit = false;
         }
       }
-      hit = is_max || is_min;
-      if (hit && filter == FC_FILTER_SCRIPT) {
-        // SIFT.py:202-215: contrast from DoG[2k-1], Hessian on DoG[k]
-        const int ci = 2 * k - 1;
-        const double contrast = (ci < nd) ? (double)sD[(ci * TH + threadIdx.y + 1) * TW + threadIdx.x + 1] : 0.0;
-        const T* d = d1 + TW + 1;
-        const double c0 = (double)d[0];
-        const double dxx = __dadd_rn(__dsub_rn((double)d[1], __dmul_rn(2.0, c0)), (double)d[-1]);
-        const double dyy = __dadd_rn(__dsub_rn((double)d[TW], __dmul_rn(2.0, c0)), (double)d[-TW]);
-        const double dxy = __ddiv_rn(__dsub_rn(__dsub_rn((double)d[TW + 1], (double)d[TW - 1]),
-                                               __dsub_rn((double)d[-TW + 1], (double)d[-TW - 1])), 4.0);
-        const double tr = __dadd_rn(dxx, dyy);
-        const double det = __dsub_rn(__dmul_rn(dxx, dyy), __dmul_rn(dxy, dxy));
-        const double r = __ddiv_rn(__dmul_rn(tr, tr), det);
-        if (fabs(contrast) < contrast_th) hit = false;
-        if (r > ratio_th) hit = false;
-      }
+      const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0 && y < H) extrema[(((size_t)(k - 1) * B + b) * H + y) * pitch + (x0 >> 5)] = bits;
     }
-    const uint32_t bits = __ballot_sync(0xffffffffu, hit);
-    if (threadIdx.x == 0 && y < H && (x0 >> 5) < pitch)
-      extrema[(((size_t)(k - 1) * B + b) * H + y) * pitch + (x0 >> 5)] = bits;
   }
 }
 
@@ -274,7 +345,25 @@ __global__ void convert_f64_kernel(const double* __restrict__ src, int64_t n, T*
   for (; i < n; i += stride) dst[i] = (T)src[i];
 }
 
-template <typename T, int TX, int TY>
+template <typename T, int TX, int TY, int RCLASS, int MINB>
+static int launch_octave_cfg(const void* base, int B, int H, int W, const TapTable<T>& tab, int rmax, void* gauss,
+                             cudaStream_t st) {
+  const int ip = TX + 2 * rmax + 1, ih = TY + 2 * rmax;
+  const int rp_max = (rmax + 3) & ~3;
+  const int tpitch = TX + 2 * rp_max + 4;
+  const size_t in_elems = ((size_t)ih * ip + 3) & ~(size_t)3;
+  const size_t smem = sizeof(T) * (in_elems + (size_t)TY * tpitch);
+  if (smem > 227 * 1024) return FC_ERR_UNSUPPORTED;
+  auto kern = gauss_octave_kernel<T, TX, TY, RCLASS, MINB>;
+  FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(div_up(W, TX), div_up(H, TY), B);
+  kern<<<grid, 256, smem, st>>>((const T*)base, H, W, tab, rmax, (T*)gauss);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+template <typename T>
 static int launch_octave(const void* base, int B, int H, int W, int L, const double* taps_host, const int* tap_len_host,
                          int first_is_identity, void* gauss, cudaStream_t st) {
   TapTable<T> tab;
@@ -291,21 +380,33 @@ static int launch_octave(const void* base, int B, int H, int W, int L, const dou
     if (off + n > kMaxTapsTotal) return FC_ERR_UNSUPPORTED;
     tab.radius[l] = r;
     tab.offset[l] = off;
-    for (int k = 0; k < n; ++k) tab.taps[off + k] = (T)tp[k];
+    for (int k = 0; k < n; ++k) {
+      if (tp[k] != tp[n - 1 - k]) return FC_ERR_UNSUPPORTED;  // the kernels assume symmetric taps (Gaussians are)
+      tab.taps[off + k] = (T)tp[k];
+    }
     if (used && r > rmax) rmax = r;
     off += n;
     tp += n;
   }
   for (int l = L; l < kMaxLevels; ++l) tab.radius[l] = tab.offset[l] = 0;
-  const int ip = TX + 2 * rmax + 1, ih = TY + 2 * rmax;
-  const int rp_max = (rmax + 3) & ~3;
-  const int tpitch = TX + 2 * rp_max + 4;
-  const size_t in_elems = ((size_t)ih * ip + 3) & ~(size_t)3;
-  const size_t smem = sizeof(T) * (in_elems + (size_t)TY * tpitch);
-  if (smem > 227 * 1024) return FC_ERR_UNSUPPORTED;
-  FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_kernel<T, TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(div_up(W, TX), div_up(H, TY), B);
-  gauss_octave_kernel<T, TX, TY><<<grid, 256, smem, st>>>((const T*)base, H, W, tab, rmax, (T*)gauss);
+  if constexpr (sizeof(T) == 4) {
+    if (rmax <= 16) return launch_octave_cfg<T, 64, 64, 16, 2>(base, B, H, W, tab, rmax, gauss, st);
+    return launch_octave_cfg<T, 64, 64, 24, 1>(base, B, H, W, tab, rmax, gauss, st);
+  } else {
+    if (rmax <= 16) return launch_octave_cfg<T, 32, 32, 16, 1>(base, B, H, W, tab, rmax, gauss, st);
+    return launch_octave_cfg<T, 32, 32, 24, 1>(base, B, H, W, tab, rmax, gauss, st);
+  }
+}
+
+template <typename T, int ND>
+static int launch_extrema_nd(const void* gauss, int B, int H, int W, int is_dog, int filter, double cth, double rth,
+                             uint32_t* extrema, cudaStream_t st) {
+  const int pitch = div_up(W, 32);
+  const size_t smem = sizeof(T) * (size_t)ND * (kExTY + 2) * kExPitch;
+  auto kern = extrema_kernel<T, ND>;
+  FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(pitch, div_up(H, kExTY), B);
+  kern<<<grid, 256, smem, st>>>((const T*)gauss, B, H, W, is_dog, filter, cth, rth, extrema, pitch);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
@@ -314,12 +415,15 @@ static int launch_octave(const void* base, int B, int H, int W, int L, const dou
 template <typename T>
 static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_dog, int filter, double cth, double rth,
                           uint32_t* extrema, cudaStream_t st) {
-  const int pitch = div_up(W, 32);
-  dim3 grid(pitch, div_up(H, kExTY), B), block(kExTX, kExTY);
-  extrema_kernel<T><<<grid, block, 0, st>>>((const T*)gauss, B, H, W, L, is_dog, filter, cth, rth, extrema, pitch);
-  note_launch();
-  FC_RETURN_IF_LAUNCH_FAILED();
-  return FC_OK;
+  const int nd = is_dog ? L : L - 1;
+  switch (nd) {
+    case 3: return launch_extrema_nd<T, 3>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
+    case 4: return launch_extrema_nd<T, 4>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
+    case 5: return launch_extrema_nd<T, 5>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
+    case 6: return launch_extrema_nd<T, 6>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
+    case 7: return launch_extrema_nd<T, 7>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
+    default: return FC_ERR_UNSUPPORTED;
+  }
 }
 
 }  // namespace fc
@@ -335,8 +439,8 @@ extern "C" int fc_gauss_octave(const void* base, int dtype, int batch, int heigh
   if (filter != FC_FILTER_APP && filter != FC_FILTER_SCRIPT) return FC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = dtype == FC_F32
-               ? launch_octave<float, 64, 64>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st)
-               : launch_octave<double, 32, 32>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st);
+               ? launch_octave<float>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st)
+               : launch_octave<double>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st);
   if (rc != FC_OK) return rc;
   if (extrema && n_levels >= 4) {
     rc = dtype == FC_F32 ? launch_extrema<float>(gauss, batch, height, width, n_levels, 0, filter, contrast_th, ratio_th, extrema, st)
