@@ -1,8 +1,8 @@
 // Harris / lambda-minus corner response kernels (sm_100a).
 //
 //   harris5_strip_kernel   app Harris, 5x5 window (the reference default and the benchmarked config):
-//                          register-resident sliding-window kernel, no shared memory, one warp per
-//                          128-column strip, 4 pixels per thread, exact integer arithmetic in fp32.
+//                          sliding-window kernel, one warp per 128-column strip, 4 pixels per thread,
+//                          exact int32 / int64 arithmetic (bytes unpacked by PRMT, no conversion-unit ops).
 //   corner_tiled_kernel    every other combination (any odd window <= 31, K_X gradient, lambda-minus):
 //                          shared-memory tiled, exact integer sums.
 //
@@ -21,13 +21,14 @@ enum { RESP_HARRIS = 0, RESP_LAMBDA_MINUS = 1 };
 // ------------------------------------------------------------------------------------------------
 //
 // All quantities are kept in units that make them integers: g2 = 2*gradient (|g2| <= 510), products
-// p = g2*g2 (<= 260100), 5-tap row sums (<= 1.3e6), 5x5 sums A, B, C (<= 6.6e6 < 2^24) -- so every
-// fp32 operation below is exact and FFMA contraction cannot change a bit.  With Sxx = A/4, Sxy = B/4,
-// Syy = C/4 the reference's R = (Sxx*Syy - Sxy^2) - k*(Sxx+Syy)^2 equals
+// p = g2*g2 (<= 260100), 5-tap row sums (<= 1.3e6), 5x5 sums A, B, C (<= 6.6e6): int32 arithmetic, exact.
+// With Sxx = A/4, Sxy = B/4, Syy = C/4 the reference's R = (Sxx*Syy - Sxy^2) - k*(Sxx+Syy)^2 equals
 //   R = ( (A*C - B*B) - rn(k * (A+C)^2) ) / 16
 // because A*C, B*B, (A+C)^2 < 2^53 are exact in float64, det and trace^2 are therefore exact in the
 // reference too, scaling by 2^-4 commutes with rounding, and exactly two roundings remain (k*tr^2 and
-// the final subtraction), performed here with __dmul_rn / __dsub_rn.
+// the final subtraction), performed here with __dmul_rn / __dsub_rn.  A*C - B*B and (A+C)^2 are formed in
+// int64 and moved to float64 with the 2^52 exponent trick (no I2F / F2F: the conversion unit runs at a
+// quarter of the ALU rate and was the bottleneck of the float version of this kernel).
 
 struct Row3 {
   uint32_t w[3];  // bytes of columns c0-4 .. c0+7 of one image row
@@ -45,75 +46,83 @@ __device__ __forceinline__ Row3 load_row3(const uint8_t* __restrict__ img, int r
   return r;
 }
 
-// float value of column c0 - 4 + k (k = 0..11) of a packed row
-__device__ __forceinline__ float col_f(const Row3& r, int k) {
-  return (float)((r.w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+// value of column c0 - 4 + k (k = 0..11) of a packed row: one PRMT
+__device__ __forceinline__ int col_i(const Row3& r, int k) {
+  return (int)__byte_perm(r.w[k >> 2], 0u, 0x4440u + (unsigned)(k & 3));
 }
 
 // Horizontal 5-tap sums of the three products for output columns c0..c0+3 of image row `row`.
 // h[0..3] = xx, h[4..7] = xy, h[8..11] = yy.   INTERIOR: no image border within reach.
 template <bool INTERIOR>
 __device__ __forceinline__ void harris_row_sums(const Row3& up, const Row3& mid, const Row3& dn, int row, int H, int W,
-                                                int c0, float (&h)[12]) {
-  float gx[8], gy[8];  // product columns c0-2 .. c0+5  <->  k = 2 .. 9
+                                                int c0, int (&h)[12]) {
+  int gx[8], gy[8];  // product columns c0-2 .. c0+5  <->  k = 2 .. 9
   if (INTERIOR) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      gx[i] = col_f(dn, i + 2) - col_f(up, i + 2);
-      gy[i] = col_f(mid, i + 3) - col_f(mid, i + 1);
+      gx[i] = col_i(dn, i + 2) - col_i(up, i + 2);
+      gy[i] = col_i(mid, i + 3) - col_i(mid, i + 1);
     }
   } else {
     // rows were clamped when loaded, so dn - up is the one-sided difference on the first / last row
-    const float sy = (row == 0 || row == H - 1) ? 2.0f : 1.0f;
+    const int sy = (row == 0 || row == H - 1) ? 2 : 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = c0 - 2 + i;
       const bool inside = (c >= 0) && (c < W);
-      float vx = sy * (col_f(dn, i + 2) - col_f(up, i + 2));
-      float vy;
-      if (c == 0) vy = 2.0f * (col_f(mid, i + 3) - col_f(mid, i + 2));
-      else if (c == W - 1) vy = 2.0f * (col_f(mid, i + 2) - col_f(mid, i + 1));
-      else vy = col_f(mid, i + 3) - col_f(mid, i + 1);
-      gx[i] = inside ? vx : 0.0f;
-      gy[i] = inside ? vy : 0.0f;
+      const int vx = sy * (col_i(dn, i + 2) - col_i(up, i + 2));
+      int vy;
+      if (c == 0) vy = 2 * (col_i(mid, i + 3) - col_i(mid, i + 2));
+      else if (c == W - 1) vy = 2 * (col_i(mid, i + 2) - col_i(mid, i + 1));
+      else vy = col_i(mid, i + 3) - col_i(mid, i + 1);
+      gx[i] = inside ? vx : 0;
+      gy[i] = inside ? vy : 0;
     }
   }
-  // sliding 5-tap sums; products are folded into FFMAs (exact, see header comment)
-  float xx = gx[0] * gx[0], xy = gx[0] * gy[0], yy = gy[0] * gy[0];
+  int xx = gx[0] * gx[0], xy = gx[0] * gy[0], yy = gy[0] * gy[0];
 #pragma unroll
   for (int i = 1; i < 5; ++i) {
-    xx = fmaf(gx[i], gx[i], xx);
-    xy = fmaf(gx[i], gy[i], xy);
-    yy = fmaf(gy[i], gy[i], yy);
+    xx += gx[i] * gx[i];
+    xy += gx[i] * gy[i];
+    yy += gy[i] * gy[i];
   }
   h[0] = xx; h[4] = xy; h[8] = yy;
 #pragma unroll
   for (int j = 1; j < 4; ++j) {
-    xx = fmaf(gx[j + 4], gx[j + 4], fmaf(-gx[j - 1], gx[j - 1], xx));
-    xy = fmaf(gx[j + 4], gy[j + 4], fmaf(-gx[j - 1], gy[j - 1], xy));
-    yy = fmaf(gy[j + 4], gy[j + 4], fmaf(-gy[j - 1], gy[j - 1], yy));
+    xx += gx[j + 4] * gx[j + 4] - gx[j - 1] * gx[j - 1];
+    xy += gx[j + 4] * gy[j + 4] - gx[j - 1] * gy[j - 1];
+    yy += gy[j + 4] * gy[j + 4] - gy[j - 1] * gy[j - 1];
     h[j] = xx; h[4 + j] = xy; h[8 + j] = yy;
   }
 }
 
-__device__ __forceinline__ double harris_from_quarter_sums(float a, float b, float c, double k) {
-  const double da = (double)a, db = (double)b, dc = (double)c;
-  const double det16 = fma(-db, db, da * dc);  // exact
-  const double tr = (double)(a + c);           // a + c < 2^24: exact in fp32
-  const double t = __dmul_rn(k, tr * tr);      // tr*tr exact
-  return __dsub_rn(det16, t) * 0.0625;
+// exact int64 -> float64 for |n| < 2^51: build 2^52 + (n + 2^51) from bits, subtract 2^52 + 2^51
+__device__ __forceinline__ double exact_i64_to_f64(long long n) {
+  const unsigned long long u = (unsigned long long)(n + (1ll << 51));
+  const double biased = __hiloint2double((int)(0x43300000u | (unsigned)(u >> 32)), (int)(unsigned)u);
+  return __dsub_rn(biased, 6755399441055744.0);  // 2^52 + 2^51
+}
+
+__device__ __forceinline__ double harris_from_quarter_sums(int a, int b, int c, double k) {
+  const long long det16 = (long long)a * c - (long long)b * b;  // |.| < 2^46
+  const long long tr = (long long)a + c;
+  const double t = __dmul_rn(k, exact_i64_to_f64(tr * tr));     // tr^2 < 2^48
+  return __dmul_rn(__dsub_rn(exact_i64_to_f64(det16), t), 0.0625);
 }
 
 static constexpr int kStripWarps = 4;
 static constexpr int kStripCols = 128;  // per warp
+static constexpr int kStripThreads = kStripWarps * 32;
 
-__global__ void __launch_bounds__(kStripWarps * 32)
+__global__ void __launch_bounds__(kStripThreads, 5)
 harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double k, double thr,
                      double* __restrict__ out, uint32_t* __restrict__ mask, int mask_pitch) {
+  // ring of the last 5 rows of horizontal sums, private to each thread: [slot][quantity][thread] (conflict free)
+  __shared__ int sRing[5 * 12 * kStripThreads];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x * kStripWarps + warp;
   const int strip_c0 = strip * kStripCols;
-  if (strip_c0 >= W) return;  // warp-uniform
+  if (strip_c0 >= W) return;  // warp-uniform, and the kernel has no block-wide barrier
   const int c0 = strip_c0 + lane * 4;
   const bool active = c0 < W;
   const size_t img_off = (size_t)blockIdx.z * H * W;
@@ -125,14 +134,13 @@ harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_pe
   // product columns of the whole strip are c in [strip_c0 - 2, strip_c0 + 129]; they all need
   // 1 <= c <= W-2 for the border-free code path
   const bool cols_interior = (strip_c0 - 2 >= 1) && (strip_c0 + kStripCols + 1 <= W - 2);
-
-  float ring[5][12];
-  float S[12];
+  int* ring = sRing + threadIdx.x;
+  int S[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
-    S[i] = 0.0f;
+    S[i] = 0;
 #pragma unroll
-    for (int s = 0; s < 5; ++s) ring[s][i] = 0.0f;
+    for (int s = 0; s < 5; ++s) ring[(s * 12 + i) * kStripThreads] = 0;
   }
   Row3 up = load_row3(img, y0 - 3, H, W, c0);
   Row3 mid = load_row3(img, y0 - 2, H, W, c0);
@@ -144,10 +152,10 @@ harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_pe
       const int hr = base + s;  // image row whose horizontal sums are produced now
       if (hr > y1 + 1) break;
       const Row3 nxt = load_row3(img, hr + 2, H, W, c0);  // prefetch for the next iteration
-      float h[12];
+      int h[12];
       if (hr < 0 || hr >= H) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) h[i] = 0.0f;
+        for (int i = 0; i < 12; ++i) h[i] = 0;
       } else if (cols_interior && hr >= 1 && hr <= H - 2) {
         harris_row_sums<true>(up, mid, dn, hr, H, W, c0, h);
       } else {
@@ -155,8 +163,9 @@ harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_pe
       }
 #pragma unroll
       for (int i = 0; i < 12; ++i) {
-        S[i] += h[i] - ring[s][i];
-        ring[s][i] = h[i];
+        int* slot = ring + (s * 12 + i) * kStripThreads;
+        S[i] += h[i] - *slot;
+        *slot = h[i];
       }
       const int r = hr - 2;  // rows r-2 .. r+2 are now summed
       if (r >= y0) {

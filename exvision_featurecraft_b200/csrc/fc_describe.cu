@@ -91,15 +91,29 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
   const int nc = c1 - c0 + 1;
   const int total = (r1 - r0 + 1) * nc;
-  int rr = lane / nc, cc = lane - rr * nc;
-  for (int t = lane; t < total; t += 32) {
-    const int y = r0 + rr, x = c0 + cc;
-    cc += 32;
-    while (cc >= nc) { cc -= nc; ++rr; }
-    const size_t o = (size_t)y * W + x;
-    const int bin = ob[o];
-    const double w = __dmul_rn((double)m[o], weights[(y - ki + radius) * side + (x - kj + radius)]);
-    h[bin * kOriPitch + lane] += w;  // bin 36 (= 360 degrees after rounding) is accumulated but never read
+  const float inv_nc = 1.0f / (float)nc;
+  const double* wrow = weights + (r0 - ki + radius) * side + (c0 - kj + radius);
+  // 4 samples per lane and trip: all 12 loads are issued before the first dependent shared-memory update
+  for (int tb = 0; tb < total; tb += 128) {
+    int bins[4];
+    double ws[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = tb + u * 32 + lane;
+      int rr = __float2int_rd(__fmul_rn((float)t, inv_nc));  // t / nc up to +-1, fixed below
+      int cc = t - rr * nc;
+      if (cc < 0) { cc += nc; --rr; }
+      if (cc >= nc) { cc -= nc; ++rr; }
+      bins[u] = kOriBins;  // the dropped bin
+      ws[u] = 0.0;
+      if (t < total) {
+        const size_t o = (size_t)(r0 + rr) * W + (c0 + cc);
+        bins[u] = ob[o];
+        ws[u] = __dmul_rn((double)m[o], wrow[rr * side + cc]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h[bins[u] * kOriPitch + lane] += ws[u];  // bin 36 is accumulated but never read
   }
   __syncwarp();
   // column sums: lane l reduces bins l and l + 32
@@ -152,10 +166,16 @@ template <typename T, typename OUT>
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, int W, const int32_t* __restrict__ oriented,
                   int n_oriented, const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc) {
-  __shared__ int sXY[kDescWarps][32];  // x0[0..15], y0[0..15] per warp
+  __shared__ int sXY[kDescWarps][32];          // x0[0..15], y0[0..15] per warp
+  __shared__ double sHist[kDescWarps][9][32];  // per-lane private bins 0..8 (8 = dropped), [bin][lane]: conflict free
+  __shared__ double sThr[8];                   // smallest rel with int(rel * 8 / 360.0) >= j + 1 (host computed, exact)
+  __shared__ double sMask[256];
+  if (threadIdx.x < 8) sThr[threadIdx.x] = trig[36 * kTrigStride + threadIdx.x];
+  for (int t = threadIdx.x; t < 256; t += kDescWarps * 32) sMask[t] = gmask[t];
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * kDescWarps + warp;
-  if (n >= n_oriented) return;
+  if (n >= n_oriented) return;  // warp-uniform; no block-wide barrier below
   const int4 kp = reinterpret_cast<const int4*>(oriented)[n];
   const int b = kp.x, ki = kp.y, kj = kp.z, bin = kp.w;
   const double theta = (double)(10 * bin + 5);  // (bin + 0.5) * 10 % 360, exact
@@ -170,46 +190,58 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     const double a = (lane < 16) ? __dadd_rn(__dmul_rn(-sn, (double)yy), sx) : __dadd_rn(__dmul_rn(cs, (double)yy), sy);
     sXY[warp][lane] = __double2int_rn(__dmul_rn(a, 1024.0)) + 512;
   }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) sHist[warp][k][lane] = 0.0;
   __syncwarp();
   const T* m = mag + (size_t)b * H * W;
   const T* d = dir + (size_t)b * H * W;
   const int cell = lane >> 1, half = lane & 1;
   const int cy = (cell >> 2) * 4 + half * 2, cx = (cell & 3) * 4;
-  double hist[8];
+  int ad[4], bd[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) hist[k] = 0.0;
+  for (int rx = 0; rx < 4; ++rx) {
+    ad[rx] = (int)tg[2 + cx + rx];
+    bd[rx] = (int)tg[2 + 16 + cx + rx];
+  }
+  double* myh = &sHist[warp][0][lane];
 #pragma unroll
   for (int ry = 0; ry < 2; ++ry) {
     const int wy = cy + ry;
     const int X0 = sXY[warp][wy], Y0 = sXY[warp][16 + wy];
+    // the 4 gathers of this row are issued before any of them is consumed
+    T mv[4], dv4[4];
 #pragma unroll
     for (int rx = 0; rx < 4; ++rx) {
-      const int wx = cx + rx;
-      const int X = (X0 + (int)tg[2 + wx]) >> 10;
-      const int Y = (Y0 + (int)tg[2 + 16 + wx]) >> 10;
-      double wv = 0.0, dv = 0.0;
-      if (X >= 0 && X < W && Y >= 0 && Y < H) {
-        const size_t o = (size_t)Y * W + X;
-        wv = (double)m[o];
-        dv = (double)d[o];
-      }
-      wv = __dmul_rn(wv, gmask[wy * 16 + wx]);
-      // bin = int(((dir - theta) % 360) * 8 / 360.0); 8 (dir - theta a hair below 0) is dropped
+      const int X = (X0 + ad[rx]) >> 10;
+      const int Y = (Y0 + bd[rx]) >> 10;
+      const bool in = (X >= 0 && X < W && Y >= 0 && Y < H);
+      const size_t o = in ? (size_t)Y * W + X : 0;
+      mv[rx] = in ? m[o] : T(0);
+      dv4[rx] = in ? d[o] : T(0);
+    }
+#pragma unroll
+    for (int rx = 0; rx < 4; ++rx) {
+      const double wv = __dmul_rn((double)mv[rx], sMask[wy * 16 + cx + rx]);
       // (dir - theta) % 360 with dir in [0, 360], theta in [5, 355]: |dir - theta| < 360, so Python's % is the
       // identity for non-negative values and one rounded +360 otherwise (can give exactly 360.0 -> bin 8, dropped)
-      double rel = __dsub_rn(dv, theta);
+      double rel = __dsub_rn((double)dv4[rx], theta);
       if (rel < 0.0) rel = __dadd_rn(rel, 360.0);
-      const int hb = (int)__ddiv_rn(__dmul_rn(rel, 8.0), 360.0);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) hist[k] += (hb == k) ? wv : 0.0;
+      // bin = int(rel * 8 / 360.0): count of thresholds <= rel (binary search over the exact host table)
+      int hb = (rel >= sThr[3]) ? 4 : 0;
+      hb += (rel >= sThr[hb + 1]) ? 2 : 0;
+      hb += (rel >= sThr[hb]) ? 1 : 0;
+      hb = (rel >= sThr[7]) ? 8 : hb;
+      myh[hb * 32] += wv;
     }
   }
+  __syncwarp();
   // merge the two halves of the cell (rows 0-1 then rows 2-3), round to float32 like the reference's cell hist
-  double f[4];
+  double hist[8], f[4];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const double other = __shfl_xor_sync(0xffffffffu, hist[k], 1);
-    const double s = half ? __dadd_rn(other, hist[k]) : __dadd_rn(hist[k], other);
+    const double mine = myh[k * 32];
+    const double other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    const double s = half ? __dadd_rn(other, mine) : __dadd_rn(mine, other);
     hist[k] = (double)(float)s;
   }
   // even lane keeps bins 0..3, odd lane bins 4..7 of the cell -> feature index cell*8 + half*4 + k
@@ -232,8 +264,15 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
   for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   const double nrm2 = sqrt(s2);
   OUT* dst = desc + (size_t)n * 128 + lane * 4;
+  if (sizeof(OUT) == 4) {
+    float4 o4;
+    o4.x = (float)__ddiv_rn(f[0], nrm2); o4.y = (float)__ddiv_rn(f[1], nrm2);
+    o4.z = (float)__ddiv_rn(f[2], nrm2); o4.w = (float)__ddiv_rn(f[3], nrm2);
+    *reinterpret_cast<float4*>(dst) = o4;
+  } else {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) dst[k] = (OUT)__ddiv_rn(f[k], nrm2);
+    for (int k = 0; k < 4; ++k) dst[k] = (OUT)__ddiv_rn(f[k], nrm2);
+  }
 }
 
 // rotated_subimage (APP/utils/keypoint_descriptor.py:175-212) as a standalone call: any theta, any size

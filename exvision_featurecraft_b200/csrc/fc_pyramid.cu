@@ -51,8 +51,8 @@ template <> __device__ __forceinline__ double fma_t<double>(double a, double b, 
 //
 // Vertical pass for one level: out rows [0, TY) of the tile, image columns [x0 - R, x0 + TX + R).
 // sIn row r <-> image row y0 - rmax + r.  sTmp[y][c] with pitch tp.
-template <typename T, int R, int TX, int TY>
-__device__ __forceinline__ void vertical_pass(const T* __restrict__ sIn, int ip, int rmax, T* __restrict__ sTmp, int tp,
+template <typename T, int R, int TX, int TY, int ip, int tp>
+__device__ __forceinline__ void vertical_pass(const T* __restrict__ sIn, int rmax, T* __restrict__ sTmp,
                                               const T* __restrict__ taps) {
   constexpr int RP = (R + 3) & ~3;
   constexpr int NC = TX + 2 * R;
@@ -79,8 +79,8 @@ __device__ __forceinline__ void vertical_pass(const T* __restrict__ sIn, int ip,
 }
 
 // Horizontal pass: sTmp column index c <-> image column x0 - RP + c (RP = R rounded up to 4).
-template <typename T, int R, int TX, int TY>
-__device__ __forceinline__ void horizontal_pass(const T* __restrict__ sTmp, int tp, const T* __restrict__ taps,
+template <typename T, int R, int TX, int TY, int tp>
+__device__ __forceinline__ void horizontal_pass(const T* __restrict__ sTmp, const T* __restrict__ taps,
                                                 T* __restrict__ out, int x0, int y0, int H, int W, bool vec_ok) {
   constexpr int RP = (R + 3) & ~3;
   constexpr int NV = (4 + 2 * RP) / 4;
@@ -122,12 +122,12 @@ __device__ __forceinline__ void horizontal_pass(const T* __restrict__ sTmp, int 
   }
 }
 
-template <typename T, int R, int TX, int TY>
-__device__ __forceinline__ void blur_level(const T* sIn, int ip, int rmax, T* sTmp, int tp, const T* taps, T* out,
+template <typename T, int R, int TX, int TY, int ip, int tp>
+__device__ __forceinline__ void blur_level(const T* sIn, int rmax, T* sTmp, const T* taps, T* out,
                                            int x0, int y0, int H, int W, bool vec_ok) {
-  vertical_pass<T, R, TX, TY>(sIn, ip, rmax, sTmp, tp, taps);
+  vertical_pass<T, R, TX, TY, ip, tp>(sIn, rmax, sTmp, taps);
   __syncthreads();
-  horizontal_pass<T, R, TX, TY>(sTmp, tp, taps, out, x0, y0, H, W, vec_ok);
+  horizontal_pass<T, R, TX, TY, tp>(sTmp, taps, out, x0, y0, H, W, vec_ok);
   __syncthreads();
 }
 
@@ -136,11 +136,11 @@ template <typename T, int TX, int TY, int RCLASS, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, int rmax, T* __restrict__ gauss) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // pitches are compile-time (sized for RCLASS) so that every shared-memory offset is an immediate
+  constexpr int ip = TX + 2 * RCLASS + 1;                   // input tile pitch
+  constexpr int tp = TX + 2 * ((RCLASS + 3) & ~3) + 4;      // tmp pitch, multiple of 4
   const int iw = TX + 2 * rmax;
-  const int ip = iw + 1;                       // input tile pitch
   const int ih = TY + 2 * rmax;
-  const int rp_max = (rmax + 3) & ~3;
-  const int tp = TX + 2 * rp_max + 4;          // tmp pitch, multiple of 4
   T* sIn = reinterpret_cast<T*>(smem_raw);
   size_t in_elems = ((size_t)ih * ip + 3) & ~(size_t)3;
   T* sTmp = sIn + in_elems;
@@ -181,7 +181,7 @@ gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, i
     const int R = tab.radius[l];
 #define FC_CASE(RR) \
   case RR:          \
-    if constexpr (RR <= RCLASS) blur_level<T, RR, TX, TY>(sIn, ip, rmax, sTmp, tp, taps, out, x0, y0, H, W, vec_ok); \
+    if constexpr (RR <= RCLASS) blur_level<T, RR, TX, TY, ip, tp>(sIn, rmax, sTmp, taps, out, x0, y0, H, W, vec_ok); \
     break;
     switch (R) {
       FC_CASE(1) FC_CASE(2) FC_CASE(3) FC_CASE(4) FC_CASE(5) FC_CASE(6) FC_CASE(7) FC_CASE(8)
@@ -348,9 +348,9 @@ __global__ void convert_f64_kernel(const double* __restrict__ src, int64_t n, T*
 template <typename T, int TX, int TY, int RCLASS, int MINB>
 static int launch_octave_cfg(const void* base, int B, int H, int W, const TapTable<T>& tab, int rmax, void* gauss,
                              cudaStream_t st) {
-  const int ip = TX + 2 * rmax + 1, ih = TY + 2 * rmax;
-  const int rp_max = (rmax + 3) & ~3;
-  const int tpitch = TX + 2 * rp_max + 4;
+  constexpr int ip = TX + 2 * RCLASS + 1;
+  constexpr int tpitch = TX + 2 * ((RCLASS + 3) & ~3) + 4;
+  const int ih = TY + 2 * rmax;
   const size_t in_elems = ((size_t)ih * ip + 3) & ~(size_t)3;
   const size_t smem = sizeof(T) * (in_elems + (size_t)TY * tpitch);
   if (smem > 227 * 1024) return FC_ERR_UNSUPPORTED;

@@ -105,8 +105,9 @@ def keypoint_sigma(sigma_base, octave_idx, scale_idx, s):
 
 def trig_table():
     """Per orientation bin: cos, sin of theta*3.14159/180 (KD:182) and the fixed-point column deltas
-    rint(cos*x*1024), rint(sin*x*1024), x = 0..15, of cv2.warpAffine's nearest-neighbour path."""
-    t = np.zeros((36, 34), dtype=np.float64)
+    rint(cos*x*1024), rint(sin*x*1024), x = 0..15, of cv2.warpAffine's nearest-neighbour path; last row: the
+    8 bin edges of int(rel * 8 / 360.0) (KD:263-268)."""
+    t = np.zeros((37, 34), dtype=np.float64)
     xs = np.arange(16)
     for b in range(36):
         theta = ((b + 0.5) * (360.0 / 36) % 360) * (3.14159 / 180)
@@ -114,6 +115,15 @@ def trig_table():
         t[b, 0], t[b, 1] = c, s
         t[b, 2:18] = np.rint(c * xs * 1024)
         t[b, 18:34] = np.rint(s * xs * 1024)
+    # row 36: descriptor bin edges.  int(rel * 8 / 360.0) >= j  <=>  rel >= edge[j-1]; the smallest such double is
+    # found by stepping from 45*j so that the device's comparisons reproduce the reference's two roundings exactly
+    for j in range(1, 9):
+        r = np.float64(45.0 * j)
+        while (r * 8) / 360.0 >= j:
+            r = np.nextafter(r, -np.inf)
+        while (r * 8) / 360.0 < j:
+            r = np.nextafter(r, np.inf)
+        t[36, j - 1] = r
     return t
 
 

@@ -179,9 +179,9 @@ FC_API int fc_orientation_emit(const int32_t* keypoints, const uint64_t* bin_mas
 /* extract_sift_descriptors (:230-289) for one (octave, scale): 16x16 nearest-neighbour rotated
  * window (cv2.warpAffine fixed-point rule, :175-212), Gaussian mask `gmask` (16x16 float64, device,
  * from get_gaussian_mask :215-227), 4x4x8 float32 cell histograms, normalise / clip / normalise.
- * trig: device table [36][2 + 32] float64 per orientation bin: cos, sin of theta*3.14159/180 and
+ * trig: device table [37][2 + 32] float64; rows 0..35 per orientation bin: cos, sin of theta*3.14159/180 and
  * the rint(cos*x*1024), rint(sin*x*1024) columns for x = 0..15 (computed on the host with the
- * reference's own libm calls).  descriptors: [n_oriented][128] float32 (out_dtype FC_F32) or
+ * reference's own libm calls); row 36, entries 0..7: smallest float64 rel with int(rel*8/360.0) >= j+1.  descriptors: [n_oriented][128] float32 (out_dtype FC_F32) or
  * float64. */
 FC_API int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
                    const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
