@@ -85,3 +85,23 @@ def harris_detection(img, window_size, k, threshold):
             xx = np.clip(rc[:, 1] + dx, 0, w - 1)
             out[yy, xx] = (0, 0, 255)
     return [[int(x), int(y), r] for (y, x), r in zip(rc.tolist(), vals.tolist())], out
+
+
+def apply_sift(main_image, template, n_octaves=4, s_value=2, sigma_base=1.6, contrast_th=0.03, r_ratio=10,
+               tuning_factor=0.3, resize=None):
+    """BackendClass.apply_sift (FeatureCraft_Backend.py:480-523) / SIFT.py:683-707 without the Qt calls:
+    keypoints + descriptors of both images, 2-NN ratio-test matching.
+
+    `resize` is the reference's ``sift_resize`` (scikit-image, the step before the hot path): pass it to get the
+    reference's ~1 MP working size, or None to use the images as given.  Returns
+    (good [(queryIdx, trainIdx, distance)], (points_main, desc_main), (points_template, desc_template));
+    the reference draws `good` with cv2.drawMatches (utils/keypoint_descriptor.py:351-364)."""
+    from .utils import keypoint_descriptor as KD
+
+    if resize is not None:
+        main_image, ratio = resize(main_image)
+        template, _ = resize(template, ratio)
+    kp_a, des_a = KD.computeKeypointsAndDescriptors(main_image, n_octaves, s_value, sigma_base, contrast_th, r_ratio)
+    kp_b, des_b = KD.computeKeypointsAndDescriptors(template, n_octaves, s_value, sigma_base, contrast_th, r_ratio)
+    good = KD.match(main_image, kp_a, des_a, template, kp_b, des_b, tuning_factor)
+    return good, (kp_a, des_a), (kp_b, des_b)

@@ -1,0 +1,108 @@
+"""BASELINE.json's full-size shapes through size-independent properties (the oracle needs minutes to hours per
+image at these sizes): config[2] template matching, config[4] 4K SIFT, large matching problems."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import featurecraft_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(lib):
+    from exvision_featurecraft_b200 import backend, matching, sift, synthetic
+    from exvision_featurecraft_b200.utils import SIFT_scale_space
+
+    SIFT_scale_space.set_dtype("f64")
+    SIFT_scale_space.set_variant("app")
+    return backend, matching, sift, synthetic
+
+
+def test_template_matching_is_geometrically_consistent(mods):
+    """apply_sift on a main image and a crop of it: the good matches must map template keypoints onto the crop's
+    position (same octave, displacement = 2 * crop origin in base-image pixels scaled by the octave)."""
+    backend, matching, sift, synthetic = mods
+    main = synthetic.sift_image(360, 480, seed=21)
+    y0, x0, size = 96, 160, 128
+    tmpl = np.ascontiguousarray(main[y0:y0 + size, x0:x0 + size])
+    good, (kp_a, des_a), (kp_b, des_b) = backend.apply_sift(main, tmpl, 4, 2, 1.6, 0.03, 10, 0.5)
+    assert len(good) > 200
+    ok = 0
+    for q, t, dist in good:
+        ia, ja, oa, sa, tha = kp_a[q]
+        ib, jb, ob, sb, thb = kp_b[t]
+        scale = 2 ** oa
+        # keypoint (i, j) of octave o sits at (i, j) * 2^o in the up-sampled (x2) frame
+        dy = ia * scale - (ib * 2 ** ob + 2 * y0)
+        dx = ja * scale - (jb * 2 ** ob + 2 * x0)
+        ok += (oa == ob) and abs(dy) <= 2 * scale and abs(dx) <= 2 * scale
+    assert ok >= 0.85 * len(good)  # the rest are chance matches among ~1e5 unfiltered keypoints
+    # the descriptor lists going into match() are what the oracle computes from the same up-sampled base
+    rp, rd = O.compute_keypoints_and_descriptors_from_base(sift.upsample2(tmpl, sift.SiftParams(dtype="f64"))[0].cpu().numpy(),
+                                                           4, 2, 1.6, 0.03, 10, "app", "separable")
+    assert len(rp) == len(kp_b)
+    assert sum(tuple(a) == tuple(b) for a, b in zip(rp, kp_b)) >= 0.995 * len(rp)  # separable-vs-direct oracle only
+
+
+def test_config2_shapes_run(mods):
+    """1920x1080 main image (working size 768x1365 after the reference's resize) vs a 182x182 template crop."""
+    backend, matching, sift, synthetic = mods
+    main = synthetic.sift_image(768, 1365, seed=3, max_blobs=800)
+    tmpl = np.ascontiguousarray(main[300:482, 600:782])
+    p = sift.SiftParams(dtype="f32")
+    ra = sift.detect_and_describe(sift.upsample2(main, p), p).assemble(1)[0]
+    rb = sift.detect_and_describe(sift.upsample2(tmpl, p), p).assemble(1)[0]
+    assert ra[0].shape[0] > 50000 and rb[0].shape[0] > 1000
+    for pts, desc in (ra, rb):
+        ok = ~np.isnan(desc).any(1)
+        assert np.abs(np.linalg.norm(desc[ok], axis=1) - 1).max() < 1e-5  # descriptors are unit vectors
+        assert desc[ok].min() >= 0
+        assert set(np.unique(pts[:, 2])) <= {0, 1, 2, 3} and set(np.unique(pts[:, 3])) <= {1, 2}
+        assert np.all((pts[:, 4] - 5) % 10 == 0)
+    pairs_t, _ = matching.match_indices(ra[1], rb[1], 0.6, "tensor")
+    pairs_e, _ = matching.match_indices(ra[1], rb[1], 0.6, "exact")
+    assert np.array_equal(pairs_t, pairs_e) and len(pairs_e) > 100
+
+
+def test_4k_image_scale_space_properties(mods):
+    """config[4] shape: 3840x2160 -> base 7680x4320, float32 scale space."""
+    backend, matching, sift, synthetic = mods
+    img = synthetic.sift_image(2160, 3840, seed=1, max_blobs=600)
+    p = sift.SiftParams(dtype="f32")
+    base = sift.upsample2(img, p)
+    assert tuple(base.shape) == (1, 4320, 7680)
+    octs = sift.scale_space(base, p)
+    assert [tuple(o.gauss.shape[2:]) for o in octs] == [(4320, 7680), (2160, 3840), (1080, 1920), (540, 960)]
+    kern = O.generateGaussianKernels(1.6, 2)
+    band = base[0, 2000:2200, 3000:3400].double().cpu().numpy()
+    for lvl in (1, 3):
+        ref = O.blur(band, kern[lvl], "separable")[40:-40, 40:-40]
+        got = octs[0].gauss[0, lvl, 2040:2160, 3040:3360].cpu().numpy()
+        assert np.abs(got - ref).max() < 1e-6
+    for o in range(3):
+        assert torch.equal(octs[o + 1].gauss[0, 0], octs[o].gauss[0, 2, ::2, ::2])
+    # extrema masks never touch the two-pixel frame the reference's loop bounds exclude
+    m = octs[0].extrema[0, 0]
+    assert int(m[0].ne(0).sum()) == 0 and int(m[-2:].ne(0).sum()) == 0
+    n_ext = sum(int(sift.keypoints_from_mask(o.extrema[k], o.width).shape[0]) for o in octs for k in range(2))
+    assert n_ext > 100000
+
+
+def test_large_matching_tensor_equals_exact(mods):
+    backend, matching, sift, synthetic = mods
+    rng = np.random.default_rng(3)
+    nq, nt = 40000, 50021
+    b = np.abs(rng.standard_normal((nt, 128), dtype=np.float32))
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    a = np.abs(rng.standard_normal((nq, 128), dtype=np.float32))
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    a[: nq // 3] = b[rng.integers(0, nt, nq // 3)] + rng.normal(0, 0.02, (nq // 3, 128)).astype(np.float32)
+    ei, ed, eg = matching.knn2(a, b, 0.7, "exact")
+    ti, td, tg = matching.knn2(a, b, 0.7, "tensor")
+    st = matching.last_stats()
+    assert st["overflow"] == 0 and st["rechecked_rows"] < 0.02 * nq
+    assert torch.equal(eg, tg)
+    g = eg.nonzero().flatten()
+    assert g.numel() > nq // 4
+    assert torch.equal(ei[g, 0], ti[g, 0]) and torch.equal(ed[g, 0], td[g, 0])
