@@ -137,3 +137,77 @@ def rethreshold(response: torch.Tensor, threshold: float, border: int = 0):
     mask = _new_mask(b, h, w, r.device)
     _lib.call("fc_threshold_mask_abs", ptr(r), b, h, w, float(threshold), int(border), ptr(mask), stream_ptr())
     return compact_mask(mask, w, r)
+
+
+class BatchCornerDetector:
+    """Harris + lambda-minus for a stream of equally shaped uint8 image batches that live on the HOST.
+
+    Same three-stream structure as sift.BatchExtractor: pinned input -> device, kernels on the caller's stream,
+    corner lists -> pinned output, the D2H of batch i overlapping the kernels of batch i+1.  The response maps stay
+    on the device (the reference caches them for its threshold slider, APP/FeatureCraft_Backend.py:355, :437);
+    what travels back is what the reference returns: Harris (row, col, R) and lambda-minus (row, col) lists."""
+
+    def __init__(self, batch: int, height: int, width: int, max_corners: int, window_size: int = 5, k: float = 0.04,
+                 threshold: float = 10000, threshold_percentage: float = 0.01, depth: int = 2):
+        dev = require_cuda()
+        self.batch, self.h, self.w, self.depth = batch, height, width, depth
+        self.args = (window_size, k, threshold, threshold_percentage)
+        self.cap = int(max_corners)
+        self.copy_in = torch.cuda.Stream(device=dev)
+        self.copy_out = torch.cuda.Stream(device=dev)
+        self.host_in = [torch.empty((batch, height, width), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.dev_in = [torch.empty((batch, height, width), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.resp = torch.empty((batch, height, width), dtype=torch.float64, device=dev)
+        self.eig = torch.empty((batch, height, width), dtype=torch.float64, device=dev)
+        self.h_coords = [torch.empty((self.cap, 2), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.h_values = [torch.empty(self.cap, dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.h_lcoords = [torch.empty((self.cap, 2), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.h_offs = [torch.empty((2, batch + 1), dtype=torch.int64).pin_memory() for _ in range(depth)]
+        self.slots = [None] * depth
+        self.n_submitted = 0
+
+    def submit(self, images) -> int:
+        ticket = self.n_submitted
+        slot = ticket % self.depth
+        if self.slots[slot] is not None:
+            raise RuntimeError("collect() the batch submitted %d calls ago before reusing its buffers" % self.depth)
+        if images is not None:
+            src = images if isinstance(images, torch.Tensor) else torch.from_numpy(images)
+            self.host_in[slot].copy_(src)
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_in):
+            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(self.copy_in)
+        compute.wait_event(ev_in)
+        ws, k, thr, pct = self.args
+        hr = harris(self.dev_in[slot], ws, k, thr, compact=True, out=self.resp)
+        lm = lambda_minus(self.dev_in[slot], pct, compact=True, out=self.eig)
+        n1, n2 = int(hr.coords.shape[0]), int(lm.coords.shape[0])
+        if max(n1, n2) > self.cap:
+            raise _lib.FeatureCraftError("batch produced %d corners, more than max_corners=%d" % (max(n1, n2), self.cap))
+        offs = torch.stack([hr.image_offsets, lm.image_offsets])
+        ev_done = torch.cuda.Event()
+        ev_done.record(compute)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(ev_done)
+            self.h_coords[slot][:n1].copy_(hr.coords, non_blocking=True)
+            self.h_values[slot][:n1].copy_(hr.values, non_blocking=True)
+            self.h_lcoords[slot][:n2].copy_(lm.coords, non_blocking=True)
+            self.h_offs[slot].copy_(offs, non_blocking=True)
+            ev_out = torch.cuda.Event()
+            ev_out.record(self.copy_out)
+        self.slots[slot] = (ev_out, n1, n2, (hr, lm, offs))
+        self.n_submitted += 1
+        return ticket
+
+    def collect(self, ticket: int):
+        """-> (harris_coords [n,2], harris_values [n], harris_image_offsets [B+1], lm_coords [m,2], lm_image_offsets)
+        as numpy views into the pinned buffers (valid until the slot is reused)."""
+        slot = ticket % self.depth
+        ev_out, n1, n2, _keep = self.slots[slot]
+        ev_out.synchronize()
+        self.slots[slot] = None
+        offs = self.h_offs[slot].numpy()
+        return (self.h_coords[slot][:n1].numpy(), self.h_values[slot][:n1].numpy(), offs[0],
+                self.h_lcoords[slot][:n2].numpy(), offs[1])

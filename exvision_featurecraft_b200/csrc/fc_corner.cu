@@ -197,6 +197,192 @@ harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_pe
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast path: lambda-minus (K_X gradients, 5x5 window / 25, smallest eigenvalue), same strip structure
+// ------------------------------------------------------------------------------------------------
+// K_X = a (x) [-1 0 0 0 1] + b (x) [0 -1 0 1 0] with a = (1,2,3,2,1), b = (2,3,5,3,2) down the rows
+// (APP/FeatureCraft_Backend.py:405-413), applied as zero-padded correlation.  |g| <= 12240, products <= 1.5e8,
+// 5-tap row sums <= 7.5e8 (int32); 5x5 sums <= 3.75e9: Sxx, Syy in uint32 (modular updates are exact below 2^32),
+// Sxy in int64.  One IEEE division by 25 per sum and LAPACK's dlae2 sequence give numpy's eigvalsh bit for bit.
+struct Row5 {
+  Row3 r[5];  // circular: slot (row + 2) % 5 when the band starts at a multiple of 5 of the unrolled loop
+};
+
+__device__ __forceinline__ Row3 load_row3_zero(const uint8_t* __restrict__ img, int row, int H, int W, int c0) {
+  Row3 r;
+  r.w[0] = r.w[1] = r.w[2] = 0u;
+  if (row < 0 || row >= H) return r;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (size_t)row * W);
+  const int wi = c0 >> 2;
+  const int nw = W >> 2;
+  if (wi - 1 >= 0 && wi - 1 < nw) r.w[0] = __ldg(p + wi - 1);
+  if (wi < nw) r.w[1] = __ldg(p + wi);
+  if (wi + 1 < nw) r.w[2] = __ldg(p + wi + 1);
+  return r;
+}
+
+// S = slot of the NEWEST row (hr+2); rows hr-2 .. hr+2 sit in slots S+1, S+2, S+3, S+4, S (mod 5): with the row
+// loop unrolled by 5 every index is static and no register is ever moved when the window slides.
+template <int S>
+__device__ __forceinline__ void lambda_row_sums(const Row5& R, int W, int c0, bool cols_interior, int (&h)[12]) {
+  int A[12], B[12], D1[12], D2[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const int v0 = col_i(R.r[(S + 1) % 5], k), v1 = col_i(R.r[(S + 2) % 5], k), v2 = col_i(R.r[(S + 3) % 5], k),
+              v3 = col_i(R.r[(S + 4) % 5], k), v4 = col_i(R.r[S], k);
+    const int s04 = v0 + v4, s13 = v1 + v3;
+    A[k] = s04 + 2 * s13 + 3 * v2;
+    B[k] = 2 * s04 + 3 * s13 + 5 * v2;
+    D2[k] = v4 - v0;
+    D1[k] = v3 - v1;
+  }
+  int gx[8], gy[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = i + 2;
+    gx[i] = (A[k + 2] - A[k - 2]) + (B[k + 1] - B[k - 1]);
+    gy[i] = (D2[k - 2] + D2[k + 2]) + 2 * (D2[k - 1] + D2[k + 1]) + 3 * D2[k] + 2 * (D1[k - 2] + D1[k + 2]) +
+            3 * (D1[k - 1] + D1[k + 1]) + 5 * D1[k];
+  }
+  if (!cols_interior) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 - 2 + i;
+      if (c < 0 || c >= W) { gx[i] = 0; gy[i] = 0; }  // the window sum is zero padded
+    }
+  }
+  int xx = gx[0] * gx[0], xy = gx[0] * gy[0], yy = gy[0] * gy[0];
+#pragma unroll
+  for (int i = 1; i < 5; ++i) {
+    xx += gx[i] * gx[i];
+    xy += gx[i] * gy[i];
+    yy += gy[i] * gy[i];
+  }
+  h[0] = xx; h[4] = xy; h[8] = yy;
+#pragma unroll
+  for (int j = 1; j < 4; ++j) {
+    xx += gx[j + 4] * gx[j + 4] - gx[j - 1] * gx[j - 1];
+    xy += gx[j + 4] * gy[j + 4] - gx[j - 1] * gy[j - 1];
+    yy += gy[j + 4] * gy[j + 4] - gy[j - 1] * gy[j - 1];
+    h[j] = xx; h[4 + j] = xy; h[8 + j] = yy;
+  }
+}
+
+// exact uint32 -> float64: bits of 2^52 + n, minus 2^52
+__device__ __forceinline__ double exact_u32_to_f64(uint32_t n) {
+  return __dsub_rn(__hiloint2double(0x43300000, (int)n), 4503599627370496.0);
+}
+
+// n / 25 correctly rounded for every integer |n| < 2^33 (what `sum / 25` gives in numpy): reciprocal multiply +
+// one Markstein correction (two FMAs).  fc_selftest_div25 checks all 2^33 + 1 magnitudes against __ddiv_rn on the
+// device (tests/test_corners_gpu.py runs it), so this is a proven identity, not an approximation.
+__device__ __forceinline__ double div25_exact(double n) {
+  const double y = 0.04;  // rn(1/25)
+  const double q = __dmul_rn(n, y);
+  const double r = __fma_rn(-q, 25.0, n);
+  return __fma_rn(r, y, q);
+}
+
+__global__ void selftest_div25_kernel(unsigned long long* __restrict__ mismatches) {
+  unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (; n <= (1ull << 33); n += stride) {
+    const double d = (double)n;
+    bad += (div25_exact(d) != __ddiv_rn(d, 25.0)) + (div25_exact(-d) != __ddiv_rn(-d, 25.0));
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+struct LambdaState {
+  Row5 R;
+  uint32_t Sxx[4], Syy[4];
+  long long Sxy[4];
+  double local_max;
+};
+
+// one image row of the band; S = hr mod-5 slot (static), see lambda_row_sums
+template <int S>
+__device__ __forceinline__ void lambda_step(LambdaState& st, const uint8_t* __restrict__ img, int hr, int H, int W, int c0,
+                                            bool cols_interior, bool active, int y0, int* __restrict__ ring,
+                                            double* __restrict__ o) {
+  st.R.r[S] = load_row3_zero(img, hr + 2, H, W, c0);  // replaces row hr-3
+  int h[12];
+  if (hr < 0 || hr >= H) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) h[i] = 0;
+  } else {
+    lambda_row_sums<S>(st.R, W, c0, cols_interior, h);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int* s0 = ring + (S * 12 + j) * kStripThreads;
+    int* s1 = ring + (S * 12 + 4 + j) * kStripThreads;
+    int* s2 = ring + (S * 12 + 8 + j) * kStripThreads;
+    st.Sxx[j] += (uint32_t)(h[j] - *s0);
+    st.Sxy[j] += (long long)(h[4 + j] - *s1);
+    st.Syy[j] += (uint32_t)(h[8 + j] - *s2);
+    *s0 = h[j]; *s1 = h[4 + j]; *s2 = h[8 + j];
+  }
+  const int r = hr - 2;  // rows r-2 .. r+2 are now summed
+  if (r >= y0) {
+    double res[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double a = div25_exact(exact_u32_to_f64(st.Sxx[j]));
+      const double b = div25_exact(exact_i64_to_f64(st.Sxy[j]));
+      const double c = div25_exact(exact_u32_to_f64(st.Syy[j]));
+      res[j] = dsterf_2x2_min(a, b, c);
+      if (active) st.local_max = fmax(st.local_max, res[j]);
+    }
+    if (active) {
+      double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
+      __stcs(dst, make_double2(res[0], res[1]));
+      __stcs(dst + 1, make_double2(res[2], res[3]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kStripThreads, 4)
+lambda5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double* __restrict__ out,
+                     unsigned long long* __restrict__ img_max_bits) {
+  __shared__ int sRing[5 * 12 * kStripThreads];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * kStripWarps + warp;
+  const int strip_c0 = strip * kStripCols;
+  if (strip_c0 >= W) return;  // warp-uniform, no block-wide barrier in this kernel
+  const int c0 = strip_c0 + lane * 4;
+  const bool active = c0 < W;
+  const size_t img_off = (size_t)blockIdx.z * H * W;
+  const uint8_t* img = gray + img_off;
+  double* o = out + img_off;
+  const int y0 = blockIdx.y * rows_per_band;
+  const int y1 = min(y0 + rows_per_band, H);
+  const bool cols_interior = (strip_c0 - 2 >= 0) && (strip_c0 + kStripCols + 1 <= W - 1);
+  int* ring = sRing + threadIdx.x;
+  LambdaState st;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { st.Sxx[j] = 0u; st.Syy[j] = 0u; st.Sxy[j] = 0; }
+#pragma unroll
+  for (int i = 0; i < 12; ++i)
+#pragma unroll
+    for (int s = 0; s < 5; ++s) ring[(s * 12 + i) * kStripThreads] = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) st.R.r[q + 1] = load_row3_zero(img, y0 - 4 + q, H, W, c0);  // rows hr-2 .. hr+1 of hr = y0-2
+  st.local_max = -INFINITY;
+
+  for (int base = y0 - 2; base <= y1 + 1; base += 5) {
+#define FC_LSTEP(S) \
+  if (base + S <= y1 + 1) lambda_step<S>(st, img, base + S, H, W, c0, cols_interior, active, y0, ring, o);
+    FC_LSTEP(0) FC_LSTEP(1) FC_LSTEP(2) FC_LSTEP(3) FC_LSTEP(4)
+#undef FC_LSTEP
+  }
+  if (img_max_bits) {
+    const double m = warp_max(st.local_max);
+    if (lane == 0 && m > -INFINITY) atomicMax(img_max_bits + blockIdx.z, ordered_bits(m));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // General path: shared-memory tiled, any odd window <= 31, both gradients, both responses
 // ------------------------------------------------------------------------------------------------
 static constexpr int kTileX = 32;
@@ -472,6 +658,15 @@ extern "C" int fc_notebook_harris_response(const uint8_t* gray, int batch, int h
                                (cudaStream_t)stream);
 }
 
+extern "C" int fc_selftest_div25(unsigned long long* mismatches, void* stream) {
+  if (!mismatches) return FC_ERR_BAD_ARG;
+  FC_CUDA_TRY(cudaMemsetAsync(mismatches, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  selftest_div25_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(mismatches);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
 extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int height, int width, double* eig,
                                         double* image_max, void* stream) {
   if (bad_image_args(gray, batch, height, width) || !eig) return FC_ERR_BAD_ARG;
@@ -482,8 +677,20 @@ extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int heig
     note_launch();
     FC_RETURN_IF_LAUNCH_FAILED();
   }
-  int rc = launch_tiled<GRAD_KX>(gray, batch, height, width, 2, RESP_LAMBDA_MINUS, 0.0, eig, bits, st);
-  if (rc != FC_OK) return rc;
+  const bool aligned = (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(gray) & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(eig) & 15) == 0);
+  if (aligned) {
+    const int strips = div_up(width, kStripCols);
+    int rows = 64;
+    while (rows > 8 && (int64_t)strips * div_up(height, rows) * batch < 148 * 16) rows >>= 1;
+    dim3 grid(div_up(strips, kStripWarps), div_up(height, rows), batch);
+    lambda5_strip_kernel<<<grid, kStripThreads, 0, st>>>(gray, height, width, rows, eig, bits);
+    note_launch();
+    FC_RETURN_IF_LAUNCH_FAILED();
+  } else {
+    int rc = launch_tiled<GRAD_KX>(gray, batch, height, width, 2, RESP_LAMBDA_MINUS, 0.0, eig, bits, st);
+    if (rc != FC_OK) return rc;
+  }
   if (bits) {
     decode_max_kernel<<<div_up(batch, 256), 256, 0, st>>>(bits, batch);
     note_launch();

@@ -87,6 +87,10 @@ FC_API int fc_notebook_harris_response(const uint8_t* gray, int batch, int heigh
 FC_API int fc_lambda_minus_response(const uint8_t* gray, int batch, int height, int width, double* eig,
                              double* image_max, void* stream);
 
+/* Device self-test: counts the integers |n| <= 2^33 for which the division-free n/25 used by the lambda-minus
+ * kernel differs from IEEE division (must be 0).  mismatches: one device uint64. */
+FC_API int fc_selftest_div25(unsigned long long* mismatches, void* stream);
+
 /* np.argwhere(map > thr) as a bit mask (APP/FeatureCraft_Backend.py:358, :268).  Pixels closer than
  * `border` to any image edge are never set. */
 FC_API int fc_threshold_mask_abs(const double* map, int batch, int height, int width, double threshold, int border,

@@ -172,3 +172,13 @@ def test_full_size_properties(fc):
     # transposing the image transposes the response (Sxx <-> Syy symmetry of det and trace)
     res_t = fc.corners.harris(np.ascontiguousarray(gray.T), 5, 0.04, None)
     assert np.array_equal(res_t.response[0].cpu().numpy().T, resp)
+
+
+def test_div25_identity_is_exhaustively_exact(fc, lib):
+    """The lambda-minus kernel divides the window sums by 25 with a reciprocal + Markstein step; the device checks
+    every possible magnitude (|n| <= 2^33) against IEEE division."""
+    import ctypes
+
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert lib.fc_selftest_div25(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    assert int(out.item()) == 0
