@@ -57,12 +57,16 @@ gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int 
   const T m = Math<T>::sqrt_(Math<T>::add(Math<T>::mul(gx, gx), Math<T>::mul(gy, gy)));
   // np.rad2deg(arctan2(gy, gx)) % 360
   const T deg = Math<T>::mul(Math<T>::atan2_(gy, gx), T(57.29577951308232087680));
-  const T d = py_mod360<T>(deg);
+  // |deg| <= 180, so Python's % 360 is the identity for deg >= 0 and one rounded + 360 otherwise
+  const T d = deg < T(0) ? Math<T>::add(deg, T(360)) : deg;
   const size_t o = ((size_t)b * H + y) * W + x;
   mag[o] = m;
   dir[o] = d;
-  // np.round(direction * 36 / 360): half to even, evaluated in double on the stored direction
-  obin[o] = (uint8_t)(int)rint(__ddiv_rn(__dmul_rn((double)d, 36.0), 360.0));
+  // np.round(direction * 36 / 360): half to even, evaluated in the scale-space type on the stored direction
+  if constexpr (sizeof(T) == 4)
+    obin[o] = (uint8_t)(int)rintf(__fdiv_rn(__fmul_rn(d, 36.0f), 360.0f));
+  else
+    obin[o] = (uint8_t)(int)rint(__ddiv_rn(__dmul_rn((double)d, 36.0), 360.0));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -70,17 +74,20 @@ static constexpr int kOriWarps = 4;
 static constexpr int kOriBins = 36;
 static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the final column sums are conflict free
 
+// ACC = double in exact (f64) mode; float in f32 mode (whose parity bar is a tolerance: every per-sample operation
+// then stays on the fp32 pipes and the histograms need half the shared memory)
 template <typename T>
 __global__ void __launch_bounds__(kOriWarps * 32)
 orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, int H, int W,
-                   const int32_t* __restrict__ keypoints, int n_keypoints, const double* __restrict__ weights,
+                   const int32_t* __restrict__ keypoints, int n_keypoints, const T* __restrict__ weights,
                    int radius, unsigned long long* __restrict__ bin_mask) {
-  __shared__ double hist[kOriWarps][(kOriBins + 1) * kOriPitch];
+  using ACC = T;
+  __shared__ ACC hist[kOriWarps][(kOriBins + 1) * kOriPitch];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * kOriWarps + warp;
   if (n >= n_keypoints) return;  // warp-uniform; no block-wide barriers below
-  double* h = hist[warp];
-  for (int t = lane; t < (kOriBins + 1) * kOriPitch; t += 32) h[t] = 0.0;
+  ACC* h = hist[warp];
+  for (int t = lane; t < (kOriBins + 1) * kOriPitch; t += 32) h[t] = ACC(0);
   __syncwarp();
   const int b = keypoints[3 * n], ki = keypoints[3 * n + 1], kj = keypoints[3 * n + 2];
   const T* m = mag + (size_t)b * H * W;
@@ -92,11 +99,11 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const int nc = c1 - c0 + 1;
   const int total = (r1 - r0 + 1) * nc;
   const float inv_nc = 1.0f / (float)nc;
-  const double* wrow = weights + (r0 - ki + radius) * side + (c0 - kj + radius);
+  const int woff = (r0 - ki + radius) * side + (c0 - kj + radius);
   // 4 samples per lane and trip: all 12 loads are issued before the first dependent shared-memory update
   for (int tb = 0; tb < total; tb += 128) {
     int bins[4];
-    double ws[4];
+    ACC ws[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int t = tb + u * 32 + lane;
@@ -105,11 +112,11 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
       if (cc < 0) { cc += nc; --rr; }
       if (cc >= nc) { cc -= nc; ++rr; }
       bins[u] = kOriBins;  // the dropped bin
-      ws[u] = 0.0;
+      ws[u] = ACC(0);
       if (t < total) {
         const size_t o = (size_t)(r0 + rr) * W + (c0 + cc);
         bins[u] = ob[o];
-        ws[u] = __dmul_rn((double)m[o], wrow[rr * side + cc]);
+        ws[u] = Math<T>::mul(m[o], weights[woff + rr * side + cc]);
       }
     }
 #pragma unroll
@@ -119,12 +126,12 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   // column sums: lane l reduces bins l and l + 32
   float f0, f1 = 0.0f;
   {
-    double s = 0.0;
+    ACC s = ACC(0);
 #pragma unroll 8
     for (int k = 0; k < 32; ++k) s += h[lane * kOriPitch + k];
     f0 = (float)s;
     if (lane < kOriBins - 32) {
-      double s2 = 0.0;
+      ACC s2 = ACC(0);
 #pragma unroll 8
       for (int k = 0; k < 32; ++k) s2 += h[(lane + 32) * kOriPitch + k];
       f1 = (float)s2;
@@ -167,11 +174,12 @@ __global__ void __launch_bounds__(kDescWarps * 32)
 descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, int W, const int32_t* __restrict__ oriented,
                   int n_oriented, const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc) {
   __shared__ int sXY[kDescWarps][32];          // x0[0..15], y0[0..15] per warp
-  __shared__ double sHist[kDescWarps][9][32];  // per-lane private bins 0..8 (8 = dropped), [bin][lane]: conflict free
-  __shared__ double sThr[8];                   // smallest rel with int(rel * 8 / 360.0) >= j + 1 (host computed, exact)
-  __shared__ double sMask[256];
-  if (threadIdx.x < 8) sThr[threadIdx.x] = trig[36 * kTrigStride + threadIdx.x];
-  for (int t = threadIdx.x; t < 256; t += kDescWarps * 32) sMask[t] = gmask[t];
+  using ACC = T;  // per-sample arithmetic: double in exact mode, float in f32 mode (tolerance-based parity)
+  __shared__ ACC sHist[kDescWarps][9][32];  // per-lane private bins 0..8 (8 = dropped), [bin][lane]: conflict free
+  __shared__ ACC sThr[8];                   // smallest rel with int(rel * 8 / 360.0) >= j + 1 (host computed, exact)
+  __shared__ ACC sMask[256];
+  if (threadIdx.x < 8) sThr[threadIdx.x] = (ACC)trig[36 * kTrigStride + threadIdx.x];
+  for (int t = threadIdx.x; t < 256; t += kDescWarps * 32) sMask[t] = (ACC)gmask[t];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * kDescWarps + warp;
@@ -191,7 +199,7 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     sXY[warp][lane] = __double2int_rn(__dmul_rn(a, 1024.0)) + 512;
   }
 #pragma unroll
-  for (int k = 0; k < 9; ++k) sHist[warp][k][lane] = 0.0;
+  for (int k = 0; k < 9; ++k) sHist[warp][k][lane] = ACC(0);
   __syncwarp();
   const T* m = mag + (size_t)b * H * W;
   const T* d = dir + (size_t)b * H * W;
@@ -203,7 +211,8 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     ad[rx] = (int)tg[2 + cx + rx];
     bd[rx] = (int)tg[2 + 16 + cx + rx];
   }
-  double* myh = &sHist[warp][0][lane];
+  ACC* myh = &sHist[warp][0][lane];
+  const ACC theta_a = (ACC)theta;
 #pragma unroll
   for (int ry = 0; ry < 2; ++ry) {
     const int wy = cy + ry;
@@ -221,11 +230,11 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     }
 #pragma unroll
     for (int rx = 0; rx < 4; ++rx) {
-      const double wv = __dmul_rn((double)mv[rx], sMask[wy * 16 + cx + rx]);
+      const ACC wv = Math<ACC>::mul((ACC)mv[rx], sMask[wy * 16 + cx + rx]);
       // (dir - theta) % 360 with dir in [0, 360], theta in [5, 355]: |dir - theta| < 360, so Python's % is the
       // identity for non-negative values and one rounded +360 otherwise (can give exactly 360.0 -> bin 8, dropped)
-      double rel = __dsub_rn((double)dv4[rx], theta);
-      if (rel < 0.0) rel = __dadd_rn(rel, 360.0);
+      ACC rel = Math<ACC>::add((ACC)dv4[rx], -theta_a);
+      if (rel < ACC(0)) rel = Math<ACC>::add(rel, ACC(360));
       // bin = int(rel * 8 / 360.0): count of thresholds <= rel (binary search over the exact host table)
       int hb = (rel >= sThr[3]) ? 4 : 0;
       hb += (rel >= sThr[hb + 1]) ? 2 : 0;
@@ -239,9 +248,9 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
   double hist[8], f[4];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const double mine = myh[k * 32];
-    const double other = __shfl_xor_sync(0xffffffffu, mine, 1);
-    const double s = half ? __dadd_rn(other, mine) : __dadd_rn(mine, other);
+    const ACC mine = myh[k * 32];
+    const ACC other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    const ACC s = half ? Math<ACC>::add(other, mine) : Math<ACC>::add(mine, other);
     hist[k] = (double)(float)s;
   }
   // even lane keeps bins 0..3, odd lane bins 4..7 of the cell -> feature index cell*8 + half*4 + k
@@ -255,7 +264,7 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
   double s2 = 0.0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    double v = __ddiv_rn(f[k], nrm);
+    double v = __ddiv_rn(f[k], nrm);  // 0 / 0 = NaN for an all-zero window, like the reference
     if (v == v) v = v < lo ? lo : (v > hi ? hi : v);  // np.clip keeps NaN
     f[k] = v;
     s2 += v * v;
@@ -326,7 +335,7 @@ extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_
 }
 
 extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
-                                   int width, const int32_t* keypoints, int n_keypoints, const double* weights, int radius,
+                                   int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
                                    uint64_t* bin_mask, void* stream) {
   if (!magnitude || !orientation_bin || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0) return FC_ERR_BAD_ARG;
   if (n_keypoints == 0) return FC_OK;
@@ -335,11 +344,11 @@ extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orienta
   const int blocks = div_up(n_keypoints, kOriWarps);
   if (dtype == FC_F32)
     orientation_kernel<float><<<blocks, kOriWarps * 32, 0, st>>>((const float*)magnitude, orientation_bin, height, width,
-                                                                 keypoints, n_keypoints, weights, radius,
+                                                                 keypoints, n_keypoints, (const float*)weights, radius,
                                                                  (unsigned long long*)bin_mask);
   else if (dtype == FC_F64)
     orientation_kernel<double><<<blocks, kOriWarps * 32, 0, st>>>((const double*)magnitude, orientation_bin, height, width,
-                                                                  keypoints, n_keypoints, weights, radius,
+                                                                  keypoints, n_keypoints, (const double*)weights, radius,
                                                                   (unsigned long long*)bin_mask);
   else
     return FC_ERR_BAD_ARG;

@@ -179,12 +179,12 @@ def _stage(name):
     return TIMER.stage(name) if TIMER is not None else _NULL
 
 
-def _cached(key, builder):
+def _cached(key, builder, dtype=torch.float64):
     dev = torch.cuda.current_device()
     k = (dev,) + key
     t = _TABLE_CACHE.get(k)
     if t is None:
-        t = to_device(np.ascontiguousarray(builder(), dtype=np.float64))
+        t = to_device(np.ascontiguousarray(builder(), dtype=np.float64)).to(dtype).contiguous()
         _TABLE_CACHE[k] = t
     return t
 
@@ -386,7 +386,7 @@ def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
         # the reference multiplies a (2r+1)^2 window by the kernel: shapes must agree or numpy raises
         raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,%d)"
                          % (2 * radius + 1, 2 * radius + 1, 2 * kernel_radius(sigma) + 1, 2 * kernel_radius(sigma) + 1))
-    weights = _cached(("ori", float(sigma)), lambda: gaussian_window_table(sigma))
+    weights = _cached(("ori", float(sigma), params.dtype), lambda: gaussian_window_table(sigma), params.torch_dtype)
     b, h, w = mag.shape
     bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
     _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), params.fc_dtype, b, h, w, ptr(keypoints), n, ptr(weights), radius,

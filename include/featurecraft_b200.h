@@ -165,12 +165,11 @@ FC_API int fc_gradient_field(const void* gauss, int dtype, int batch, int n_leve
                       void* magnitude, void* direction, uint8_t* orientation_bin, void* stream);
 
 /* dog_keypoints_orientations (:116-172) for one (octave, scale): keypoints are (image, row, col)
- * int32 triples in reference order; weights_host is gaussian_filter_kernel(sigma) as a dense
- * (2r+1)^2 float64 table that the caller uploaded to `weights` (device).  For keypoint n the 36-bin
- * float32 histogram is built and bin_mask[n] receives bit b for every bin with
- * hist[b] >= float32(0.8) * max (:165-167). */
+ * int32 triples in reference order; `weights` is gaussian_filter_kernel(sigma) as a dense (2r+1)^2 device
+ * table of element type `dtype`.  For keypoint n the 36-bin float32 histogram is built (sums in `dtype`)
+ * and bin_mask[n] receives bit b for every bin with hist[b] >= float32(0.8) * max (:165-167). */
 FC_API int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
-                        int width, const int32_t* keypoints, int n_keypoints, const double* weights, int radius,
+                        int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
                         uint64_t* bin_mask, void* stream);
 
 /* Expand bin masks into oriented keypoints in reference order: offsets[n] = popcount prefix
