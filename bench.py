@@ -203,7 +203,7 @@ class HarrisWorkload:
         return self.host_in.numel(), sum(a.nbytes for a in out)
 
     def step_e2e(self):
-        t = self.det.submit(None)
+        t = self.det.submit(None, prefetch_next=True)
         if self.pending is not None:
             self.io_bytes = self._account(self.det.collect(self.pending))
         self.pending = t
@@ -346,6 +346,21 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3  # host clock around synchronised ends: includes every copy and sync
     clocks = sampler.stop() if rank == 0 else None
+    pcie = None
+    if rank == 0:
+        # context for the end-to-end number: what one pinned 256 MB copy achieves on this box, each direction
+        hp = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dp = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        pcie = {}
+        for name, (dst, src) in (("h2d_gbs", (dp, hp)), ("d2h_gbs", (hp, dp))):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            tp = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            pcie[name] = round(3 * hp.numel() / (time.perf_counter() - tp) / 1e9, 1)
+        del hp, dp
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -373,7 +388,7 @@ def main():
                 "roofline": {"kernel": kname, "bound": bound, "achieved": ach, "peak": peak, "unit": punit,
                              "frac": (ach / peak) if ach else None, "traffic": getattr(wl, "ncu_traffic", None),
                              "peak_source": src, "kernel_ms": kms, "algorithmic_per_launch": alg},
-                "clocks": clocks}
+                "clocks": clocks, "pcie": pcie}
         extra = getattr(wl, "extra", None)
         if extra:
             line["stages"] = extra() if callable(extra) else extra

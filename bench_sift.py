@@ -72,7 +72,7 @@ class SiftWorkload:
         self.io_bytes = (0, 0)
 
     def step_e2e(self):
-        t = self.extractor.submit(None)  # the pinned staging buffer already holds this step's images
+        t = self.extractor.submit(None, prefetch_next=True)  # the pinned staging buffers already hold the images
         if self.pending is not None:
             out = self.extractor.collect(self.pending)
             self.io_bytes = self.extractor.bytes_per_batch(out)

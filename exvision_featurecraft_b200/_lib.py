@@ -42,6 +42,7 @@ SIGNATURES = {
     "fc_threshold_mask_rel": (_i, [_p, _i, _i, _i, _d, _p, _p, _p]),
     "fc_scan_scratch_elems": (_i64, [_i64]),
     "fc_mask_scan": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "fc_publish_i32": (_i, [_p, _p, _i, _p]),
     "fc_mask_emit": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "fc_mask_emit_keypoints": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "fc_gauss_octave": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _d, _d, _p, _p, _p]),

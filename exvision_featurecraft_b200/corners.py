@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from .device import ptr, require_cuda, scan_scratch, stream_ptr, to_device
+from .device import ptr, read_int, require_cuda, scan_scratch, stream_ptr, to_device
 
 
 @dataclass
@@ -63,7 +63,7 @@ def compact_mask(mask: torch.Tensor, width: int, response: torch.Tensor | None =
     scratch = scan_scratch(rows)
     _lib.call("fc_mask_scan", ptr(mask), b, h, width, ptr(row_offsets), ptr(scratch), stream_ptr())
     image_offsets = row_offsets[::h].to(torch.int64)  # B+1 entries, still on the device
-    total = int(row_offsets[-1].item())  # the one host sync: sizes the output
+    total = read_int(row_offsets)  # the one host sync: sizes the output
     coords = torch.empty((total, 2), dtype=torch.int32, device=mask.device)
     values = torch.empty(total, dtype=torch.float64, device=mask.device) if response is not None else None
     if total:
@@ -164,25 +164,42 @@ class BatchCornerDetector:
         self.h_lcoords = [torch.empty((self.cap, 2), dtype=torch.int32).pin_memory() for _ in range(depth)]
         self.h_offs = [torch.empty((2, batch + 1), dtype=torch.int64).pin_memory() for _ in range(depth)]
         self.slots = [None] * depth
+        self.staged = [None] * depth
+        self.consumed = [None] * depth
         self.n_submitted = 0
 
-    def submit(self, images) -> int:
+    def stage(self, images, ticket: int | None = None):
+        """Start the H2D copy of the batch a later submit() will process (overlaps the previous batch's kernels)."""
+        ticket = self.n_submitted if ticket is None else ticket
+        slot = ticket % self.depth
+        if images is not None:
+            src = images if isinstance(images, torch.Tensor) else torch.from_numpy(images)
+            self.host_in[slot].copy_(src)
+        with torch.cuda.stream(self.copy_in):
+            if self.consumed[slot] is not None:
+                self.copy_in.wait_event(self.consumed[slot])
+            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(self.copy_in)
+        self.staged[slot] = ev_in
+
+    def submit(self, images, prefetch_next: bool = False) -> int:
         ticket = self.n_submitted
         slot = ticket % self.depth
         if self.slots[slot] is not None:
             raise RuntimeError("collect() the batch submitted %d calls ago before reusing its buffers" % self.depth)
-        if images is not None:
-            src = images if isinstance(images, torch.Tensor) else torch.from_numpy(images)
-            self.host_in[slot].copy_(src)
+        if images is not None or self.staged[slot] is None:
+            self.stage(images, ticket)
+        ev_in, self.staged[slot] = self.staged[slot], None
+        if prefetch_next and self.depth > 1:
+            self.stage(None, ticket + 1)
         compute = torch.cuda.current_stream()
-        with torch.cuda.stream(self.copy_in):
-            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
-            ev_in = torch.cuda.Event()
-            ev_in.record(self.copy_in)
         compute.wait_event(ev_in)
         ws, k, thr, pct = self.args
         hr = harris(self.dev_in[slot], ws, k, thr, compact=True, out=self.resp)
         lm = lambda_minus(self.dev_in[slot], pct, compact=True, out=self.eig)
+        self.consumed[slot] = torch.cuda.Event()
+        self.consumed[slot].record(compute)
         n1, n2 = int(hr.coords.shape[0]), int(lm.coords.shape[0])
         if max(n1, n2) > self.cap:
             raise _lib.FeatureCraftError("batch produced %d corners, more than max_corners=%d" % (max(n1, n2), self.cap))

@@ -244,43 +244,45 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     }
   }
   __syncwarp();
-  // merge the two halves of the cell (rows 0-1 then rows 2-3), round to float32 like the reference's cell hist
-  double hist[8], f[4];
+  // merge the two halves of the cell (rows 0-1 then rows 2-3), round to float32 like the reference's cell hist;
+  // normalise / clip [2^-10, 0.2] / normalise (:281-287) in NT = double (exact mode) or float (f32 mode)
+  using NT = T;
+  NT hist[8], f[4];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const ACC mine = myh[k * 32];
     const ACC other = __shfl_xor_sync(0xffffffffu, mine, 1);
     const ACC s = half ? Math<ACC>::add(other, mine) : Math<ACC>::add(mine, other);
-    hist[k] = (double)(float)s;
+    hist[k] = (NT)(float)s;
   }
   // even lane keeps bins 0..3, odd lane bins 4..7 of the cell -> feature index cell*8 + half*4 + k
 #pragma unroll
   for (int k = 0; k < 4; ++k) f[k] = half ? hist[4 + k] : hist[k];
-  double ss = f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
+  NT ss = f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const double nrm = sqrt(ss);
-  const double lo = 0.0009765625, hi = 0.2;  // np.finfo(np.float16).eps, 0.2
-  double s2 = 0.0;
+  const NT nrm = Math<NT>::sqrt_(ss);
+  const NT lo = NT(0.0009765625), hi = NT(0.2);  // np.finfo(np.float16).eps, 0.2
+  NT s2 = NT(0);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    double v = __ddiv_rn(f[k], nrm);  // 0 / 0 = NaN for an all-zero window, like the reference
+    NT v = f[k] / nrm;  // IEEE division; 0 / 0 = NaN for an all-zero window, like the reference
     if (v == v) v = v < lo ? lo : (v > hi ? hi : v);  // np.clip keeps NaN
     f[k] = v;
     s2 += v * v;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  const double nrm2 = sqrt(s2);
+  const NT nrm2 = Math<NT>::sqrt_(s2);
   OUT* dst = desc + (size_t)n * 128 + lane * 4;
   if (sizeof(OUT) == 4) {
     float4 o4;
-    o4.x = (float)__ddiv_rn(f[0], nrm2); o4.y = (float)__ddiv_rn(f[1], nrm2);
-    o4.z = (float)__ddiv_rn(f[2], nrm2); o4.w = (float)__ddiv_rn(f[3], nrm2);
+    o4.x = (float)(f[0] / nrm2); o4.y = (float)(f[1] / nrm2);
+    o4.z = (float)(f[2] / nrm2); o4.w = (float)(f[3] / nrm2);
     *reinterpret_cast<float4*>(dst) = o4;
   } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = (OUT)__ddiv_rn(f[k], nrm2);
+    for (int k = 0; k < 4; ++k) dst[k] = (OUT)(f[k] / nrm2);
   }
 }
 

@@ -89,3 +89,23 @@ int exclusive_scan_i32(const int32_t* in, int64_t n, int32_t* out, int32_t* scra
 }
 
 }  // namespace fc
+
+
+// Publish a few int32 values to PINNED host memory straight from a kernel (the pointer of cudaHostAlloc'ed memory
+// is valid on the device under UVA).  Unlike a 4-byte cudaMemcpy D2H this does not queue behind bulk transfers on
+// the device-to-host copy engine, so the host can learn an output size while a large result copy is in flight.
+namespace fc {
+__global__ void publish_i32_kernel(const int32_t* __restrict__ src, volatile int32_t* __restrict__ dst_host, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst_host[i] = src[i];
+  __threadfence_system();
+}
+}  // namespace fc
+
+extern "C" int fc_publish_i32(const int32_t* src, int32_t* dst_host_pinned, int n, void* stream) {
+  if (!src || !dst_host_pinned || n <= 0) return FC_ERR_BAD_ARG;
+  fc::publish_i32_kernel<<<fc::div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(src, dst_host_pinned, n);
+  fc::note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}

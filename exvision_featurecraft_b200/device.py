@@ -44,3 +44,24 @@ def to_device(a, dtype=None) -> torch.Tensor:
 def scan_scratch(n: int) -> torch.Tensor:
     elems = int(_lib.load().fc_scan_scratch_elems(int(n)))
     return torch.empty(max(elems, 1), dtype=torch.int32, device=require_cuda())
+
+
+_PINNED_SLOTS: dict = {}
+
+
+def read_int(t: torch.Tensor, index: int = -1) -> int:
+    """int(t[index]) for an int32 CUDA tensor WITHOUT a D2H memcpy: a kernel stores the value into pinned host
+    memory and the host waits on an event.  A 4-byte cudaMemcpy would queue behind any bulk device-to-host
+    transfer in flight on the copy engine and serialise the pipelined drivers (BatchExtractor etc.)."""
+    assert t.is_cuda and t.dtype == torch.int32
+    key = (t.device.index, torch.cuda.current_stream().cuda_stream)
+    slot = _PINNED_SLOTS.get(key)
+    if slot is None:
+        slot = (torch.zeros(16, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        _PINNED_SLOTS[key] = slot
+    host, ev = slot
+    src = t.reshape(-1)[index:] if index != -1 else t.reshape(-1)[-1:]
+    _lib.call("fc_publish_i32", C.c_void_p(src.data_ptr()), C.c_void_p(host.data_ptr()), 1, stream_ptr())
+    ev.record()
+    ev.synchronize()
+    return int(host[0])

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import ptr, require_cuda, scan_scratch, stream_ptr, to_device
+from .device import ptr, read_int, require_cuda, scan_scratch, stream_ptr, to_device
 
 
 @dataclass(frozen=True)
@@ -237,11 +237,13 @@ class SiftResult:
         p = torch.cat(pts)
         d = torch.cat(desc)
         img = p[:, 0].to(torch.int64)
-        counts = torch.bincount(img, minlength=batch)
         if batch > 1:
-            order = torch.sort(img, stable=True).indices
+            img, order = torch.sort(img, stable=True)
             p = p[order]
             d = d[order]
+        # per-image counts without torch.bincount (which reads the maximum back to the host)
+        edges = torch.searchsorted(img, torch.arange(batch + 1, device=img.device, dtype=torch.int64))
+        counts = edges[1:] - edges[:-1]
         return p[:, 1:].contiguous(), d, counts
 
     def assemble(self, batch: int):
@@ -358,7 +360,7 @@ def keypoints_from_mask(mask: torch.Tensor, width: int) -> torch.Tensor:
     row_offsets = torch.empty(rows + 1, dtype=torch.int32, device=mask.device)
     scratch = scan_scratch(rows)
     _lib.call("fc_mask_scan", ptr(mask), b, h, width, ptr(row_offsets), ptr(scratch), stream_ptr())
-    total = int(row_offsets[-1].item())
+    total = read_int(row_offsets)
     kps = torch.empty((total, 3), dtype=torch.int32, device=mask.device)
     if total:
         _lib.call("fc_mask_emit_keypoints", ptr(mask), ptr(row_offsets), b, h, width, ptr(kps), stream_ptr())
@@ -394,7 +396,7 @@ def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
     offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
     scratch = scan_scratch(n)
     _lib.call("fc_orientation_scan", ptr(bin_mask), n, ptr(offsets), ptr(scratch), stream_ptr())
-    total = int(offsets[-1].item())
+    total = read_int(offsets)
     oriented = torch.empty((total, 4), dtype=torch.int32, device=dev)
     if total:
         _lib.call("fc_orientation_emit", ptr(keypoints), ptr(bin_mask), ptr(offsets), n, ptr(oriented), stream_ptr())
@@ -478,25 +480,45 @@ class BatchExtractor:
         self.host_pts = [torch.empty((self.cap, 5), dtype=torch.float64).pin_memory() for _ in range(depth)]
         self.host_cnt = [torch.empty(batch, dtype=torch.int64).pin_memory() for _ in range(depth)]
         self.slots = [None] * depth
+        self.staged = [None] * depth   # H2D-done event of an input already on its way to the device
+        self.consumed = [None] * depth  # event after the last kernel that read dev_in[slot]
         self.n_submitted = 0
 
-    def submit(self, images) -> int:
+    def stage(self, images, ticket: int | None = None):
+        """Start the H2D copy of the batch that a later submit() (ticket = the next one by default) will process, so
+        that it overlaps the kernels of the batch before it.  images=None: the pinned staging buffer is already filled."""
+        ticket = self.n_submitted if ticket is None else ticket
+        slot = ticket % self.depth
+        if images is not None:
+            src = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
+            self.host_in[slot].copy_(src)
+        with torch.cuda.stream(self.copy_in):
+            if self.consumed[slot] is not None:
+                self.copy_in.wait_event(self.consumed[slot])
+            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(self.copy_in)
+        self.staged[slot] = ev_in
+
+    def submit(self, images, prefetch_next: bool = False) -> int:
         """images: [B,H,W] float64 numpy array / CPU tensor (copied into the pinned staging buffer) or None to
-        reuse what the staging buffer of this slot already holds.  Returns a ticket for collect()."""
+        reuse what the staging buffer of this slot already holds (or what stage() already sent).  prefetch_next:
+        also start the H2D of the following ticket from ITS staging buffer before this batch's kernels are queued.
+        Returns a ticket for collect()."""
         ticket = self.n_submitted
         slot = ticket % self.depth
         if self.slots[slot] is not None:
             raise RuntimeError("collect() the batch submitted %d calls ago before reusing its buffers" % self.depth)
-        if images is not None:
-            src = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(images))
-            self.host_in[slot].copy_(src)
+        if images is not None or self.staged[slot] is None:
+            self.stage(images, ticket)
+        ev_in, self.staged[slot] = self.staged[slot], None
+        if prefetch_next and self.depth > 1:
+            self.stage(None, ticket + 1)
         compute = torch.cuda.current_stream()
-        with torch.cuda.stream(self.copy_in):
-            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
-            ev_in = torch.cuda.Event()
-            ev_in.record(self.copy_in)
         compute.wait_event(ev_in)
         base = upsample2(self.dev_in[slot], self.params) if self.upsample else _as_base_batch(self.dev_in[slot], self.params)
+        self.consumed[slot] = torch.cuda.Event()
+        self.consumed[slot].record(compute)
         res = detect_and_describe(base, self.params, out_dtype=torch.float32)
         pts, desc, counts = res.assemble_device(self.batch)
         m = int(pts.shape[0])

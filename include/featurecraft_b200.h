@@ -106,6 +106,10 @@ FC_API int fc_threshold_mask_rel(const double* map, int batch, int height, int w
 FC_API int64_t fc_scan_scratch_elems(int64_t n);
 FC_API int fc_mask_scan(const uint32_t* mask, int batch, int height, int width, int32_t* row_offsets, int32_t* scratch,
                  void* stream);
+/* Copy n int32 from device memory to PINNED host memory by a kernel store (UVA pointer), not by the D2H copy
+ * engine: the way the host mirrors read output sizes without queueing behind bulk result transfers. */
+FC_API int fc_publish_i32(const int32_t* src, int32_t* dst_host_pinned, int n, void* stream);
+
 /* coords: [total][2] int32 (row, col); values (optional): map gathered at those pixels. */
 FC_API int fc_mask_emit(const uint32_t* mask, const int32_t* row_offsets, int batch, int height, int width,
                  const double* map, int32_t* coords, double* values, void* stream);
