@@ -331,7 +331,7 @@ __device__ __forceinline__ void lambda_step(LambdaState& st, const uint8_t* __re
       const double a = div25_exact(exact_u32_to_f64(st.Sxx[j]));
       const double b = div25_exact(exact_i64_to_f64(st.Sxy[j]));
       const double c = div25_exact(exact_u32_to_f64(st.Syy[j]));
-      res[j] = dsterf_2x2_min(a, b, c);
+      res[j] = lambda_min_psd(a, b, c);
       if (active) st.local_max = fmax(st.local_max, res[j]);
     }
     if (active) {
@@ -537,24 +537,46 @@ __global__ void rgb_to_gray_kernel(const uint8_t* __restrict__ rgb, int64_t n, u
   gray[i] = (uint8_t)(int)v;
 }
 
-// one warp per (image row, 32-column word)
-__global__ void threshold_mask_kernel(const double* __restrict__ map, int B, int H, int W, double thr_abs,
-                                      double fraction, const double* __restrict__ image_max, int border,
-                                      uint32_t* __restrict__ mask, int pitch) {
+// one warp per (image row, 128 columns): 4 pixels per lane (two 16-byte loads in flight), nibbles merged by shuffles
+__global__ void __launch_bounds__(256)
+threshold_mask_kernel(const double* __restrict__ map, int B, int H, int W, double thr_abs, double fraction,
+                      const double* __restrict__ image_max, int border, uint32_t* __restrict__ mask, int pitch) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t total = (int64_t)B * H * pitch;
+  const int groups = (pitch + 3) >> 2;  // 128-column groups per row
+  const int64_t total = (int64_t)B * H * groups;
   if (warp >= total) return;
-  const int word = (int)(warp % pitch);
-  const int64_t row_g = warp / pitch;
+  const int grp = (int)(warp % groups);
+  const int64_t row_g = warp / groups;
   const int y = (int)(row_g % H);
   const int b = (int)(row_g / H);
   const double thr = image_max ? __dmul_rn(fraction, image_max[b]) : thr_abs;
-  const int x = word * 32 + lane;
-  bool hit = false;
-  if (x < W && y >= border && y < H - border && x >= border && x < W - border) hit = map[row_g * W + x] > thr;
-  const uint32_t bits = __ballot_sync(0xffffffffu, hit);
-  if (lane == 0) mask[warp] = bits;
+  const int x0 = grp * 128 + lane * 4;
+  const double* src = map + row_g * W;
+  const bool row_ok = (y >= border && y < H - border);
+  uint32_t nib = 0;
+  if (row_ok && x0 < W) {
+    double v[4];
+    if (((W & 1) == 0) && x0 + 3 < W && ((reinterpret_cast<uintptr_t>(src + x0) & 15) == 0)) {
+      const double2 p = __ldcs(reinterpret_cast<const double2*>(src + x0));
+      const double2 q = __ldcs(reinterpret_cast<const double2*>(src + x0) + 1);
+      v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (x0 + j < W) ? src[x0 + j] : -INFINITY;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + j;
+      if (x < W && x >= border && x < W - border && v[j] > thr) nib |= 1u << j;
+    }
+  }
+  uint32_t v32 = nib << (4 * (lane & 7));
+  v32 |= __shfl_xor_sync(0xffffffffu, v32, 1);
+  v32 |= __shfl_xor_sync(0xffffffffu, v32, 2);
+  v32 |= __shfl_xor_sync(0xffffffffu, v32, 4);
+  const int word = grp * 4 + (lane >> 3);
+  if ((lane & 7) == 0 && word < pitch) mask[row_g * pitch + word] = v32;
 }
 
 // one thread per mask row: popcount of the row
@@ -703,7 +725,7 @@ static int launch_threshold(const double* map, int B, int H, int W, double thr, 
                             int border, uint32_t* mask, cudaStream_t st) {
   if (bad_image_args(map, B, H, W) || !mask || border < 0) return FC_ERR_BAD_ARG;
   const int pitch = div_up(W, 32);
-  const int64_t warps = (int64_t)B * H * pitch;
+  const int64_t warps = (int64_t)B * H * div_up(pitch, 4);
   threshold_mask_kernel<<<(unsigned)div_up64(warps * 32, 256), 256, 0, st>>>(map, B, H, W, thr, frac, image_max, border,
                                                                            mask, pitch);
   note_launch();
