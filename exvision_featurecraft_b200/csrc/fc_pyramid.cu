@@ -46,6 +46,15 @@ __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  if constexpr (sizeof(T) == 4)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 // Taps are symmetric (g(-x) = g(x)): only the centre and one side are kept in registers and every output is
 // evaluated as c*v[0] + sum_k t_k (v[-k] + v[+k]).
 //
@@ -150,7 +159,9 @@ gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, i
   const int L = tab.n_levels;
   T* gout = gauss + (size_t)b * L * H * W;
   {
-    // one warp per tile row, lanes along the row: coalesced, reflection only where the tile leaves the image
+    // one warp per tile row, lanes along the row (coalesced); reflection only where the tile leaves the image.
+    // Every element goes global -> shared with its own cp.async (LDGSTS): all ~32 copies of a thread are in flight
+    // at once, so the tile costs one memory latency instead of one per row.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool interior_x = (x0 - rmax >= 0) && (x0 - rmax + iw <= W);
     for (int r = warp; r < ih; r += 8) {
@@ -159,11 +170,12 @@ gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, i
       T* dst = sIn + (size_t)r * ip;
       if (interior_x) {
         const T* src = row + (x0 - rmax);
-        for (int c = lane; c < iw; c += 32) dst[c] = src[c];
+        for (int c = lane; c < iw; c += 32) cp_async_elem<T>(dst + c, src + c);
       } else {
-        for (int c = lane; c < iw; c += 32) dst[c] = row[reflect_symm(x0 - rmax + c, W)];
+        for (int c = lane; c < iw; c += 32) cp_async_elem<T>(dst + c, row + reflect_symm(x0 - rmax + c, W));
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
   const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gauss) & (4 * sizeof(T) - 1)) == 0);
@@ -390,7 +402,7 @@ static int launch_octave(const void* base, int B, int H, int W, int L, const dou
   }
   for (int l = L; l < kMaxLevels; ++l) tab.radius[l] = tab.offset[l] = 0;
   if constexpr (sizeof(T) == 4) {
-    if (rmax <= 16) return launch_octave_cfg<T, 64, 64, 16, 2>(base, B, H, W, tab, rmax, gauss, st);
+    if (rmax <= 16) return launch_octave_cfg<T, 64, 64, 16, 3>(base, B, H, W, tab, rmax, gauss, st);
     return launch_octave_cfg<T, 64, 64, 24, 1>(base, B, H, W, tab, rmax, gauss, st);
   } else {
     if (rmax <= 16) return launch_octave_cfg<T, 32, 32, 16, 1>(base, B, H, W, tab, rmax, gauss, st);
