@@ -235,10 +235,11 @@ WORKLOADS = {"harris": HarrisWorkload}
 
 def pick_workload(name):
     try:
-        from bench_sift import MatchWorkload, SiftWorkload  # noqa: F401
+        from bench_sift import AllPairsWorkload, MatchWorkload, SiftWorkload  # noqa: F401
 
         WORKLOADS["sift"] = SiftWorkload
         WORKLOADS["match"] = MatchWorkload
+        WORKLOADS["allpairs"] = AllPairsWorkload
     except ImportError:
         pass
     if name is None:

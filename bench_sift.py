@@ -201,3 +201,62 @@ class MatchWorkload:
 
     def cpu_units(self, n):
         return n * 2048 * 8192 / 1e9
+
+
+class AllPairsWorkload(MatchWorkload):
+    """BASELINE configs[4] matching leg, scaled: every rank keeps its block of descriptors resident and matches it
+    against the block of every rank; the blocks travel around a ring of NCCL send/recv (sharding.all_pairs_match).
+    The one workload with a real exchange step; value = descriptor pairs compared per second over all ranks."""
+
+    name = "allpairs"
+    metric = "allpairs_match_descriptor_pairs_per_sec"
+
+    def __init__(self, args):
+        self.nq = self.nt = (args.batch or 64) * 1024
+        self.world = 1
+
+    def describe(self, world):
+        return {"workload": "all-pairs 2-NN ratio-test matching: %d descriptors per GPU against the blocks of all %d GPUs per step "
+                            "(ring of NCCL send/recv, %d-row blocks)" % (self.nq, world, self.nq),
+                "sharding": "descriptor blocks per rank; exchange = (world-1)-step ring, overlapped by nothing yet",
+                "l2": "blocks (%.0f MB fp32 each) exceed L2 together with the fp16 operands" % (self.nq * 512 / 1e6)}
+
+    def units_per_step(self):
+        return self.nq * self.nt * self.world / 1e9
+
+    def setup(self, rank, torch):
+        super().setup(rank, torch)
+        from exvision_featurecraft_b200 import sharding
+
+        self.sharding = sharding
+        self.world = sharding.world_info()[1]
+
+    def _run(self):
+        return self.sharding.all_pairs_match(self.a, lambda q, t: self.matching.knn2(q, t, 0.3, "tensor"), max_rows=self.nq)
+
+    def step_device(self, record=False):
+        if record and self.ev_i < len(self.ev):
+            e0, e1 = self.ev[self.ev_i]
+            self.ev_i += 1
+            e0.record()
+            out = self._run()
+            e1.record()
+            return out
+        return self._run()
+
+    def step_e2e(self):
+        a = self.host_a.cuda(non_blocking=True)
+        keep, self.a = self.a, a
+        res = self._run()
+        self.a = keep
+        d2h = 0
+        for _, (idx, dist, good) in res:
+            q = self.torch.nonzero(good).flatten()
+            out = (q.cpu(), idx[q, 0].cpu(), dist[q, 0].cpu())
+            d2h += sum(t.numel() * t.element_size() for t in out)
+        return self.nq * 512, d2h
+
+    def dominant_kernel(self):
+        ms = [a.elapsed_time(b) for a, b in self.ev[: self.ev_i]]
+        return ("match_tc_kernel (+prep, re-rank, ring exchange)", 2.0 * self.nq * self.nt * self.world * 128,
+                float(np.mean(ms)) if ms else None, "tensor")
