@@ -39,7 +39,7 @@ constexpr int kTileBytes = kTileRows / 8 * kRowGroupBytes;  // 36864
 constexpr int kStages = 3;
 constexpr int kQueriesPerCta = 256;
 constexpr int kCand = 4;   // kept groups per (query row, split)
-constexpr int kGroup = 16;  // train rows per group
+constexpr int kGroup = 8;   // train rows per group
 constexpr int kMaxSplits = 4;
 constexpr int kThreads = 320;  // producer warp, MMA warp, 8 epilogue warps
 constexpr float kPadNorm = 60000.0f;
@@ -122,24 +122,23 @@ struct TopK {
   }
 };
 
-__device__ __forceinline__ float min16(const uint32_t* r) {
+__device__ __forceinline__ float min8(const uint32_t* r) {
   const float a = min3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
   const float b = min3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
-  const float c = min3(__uint_as_float(r[6]), __uint_as_float(r[7]), __uint_as_float(r[8]));
-  const float d = min3(__uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
-  const float e = min3(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]));
-  return min3(min3(a, b, c), min3(d, e, __uint_as_float(r[15])), INFINITY);
+  return min3(min3(a, b, __uint_as_float(r[6])), __uint_as_float(r[7]), INFINITY);
 }
 
-// 32 accumulator columns of one row = two groups of 16 consecutive train rows.  Only the MINIMUM of each group
+// 32 accumulator columns of one row = four groups of 8 consecutive train rows.  Only the MINIMUM of each group
 // is tracked (FMNMX3 trees, no per-element branches): the running top-4 GROUPS per query row are kept, and the
-// re-rank kernel evaluates all 16 members of the kept groups exactly.  The k-th best row always lies in one of
+// re-rank kernel evaluates all 8 members of the kept groups exactly.  The k-th best row always lies in one of
 // the k best groups, and every row outside the kept groups scores >= the 4th kept group minimum.
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], int group0, TopK& best) {
-  const float lo = min16(r), hi = min16(r + 16);
-  if (fminf(lo, hi) < best.s[3]) {
-    best.insert(lo, group0);
-    best.insert(hi, group0 + 1);
+  const float g0 = min8(r), g1 = min8(r + 8), g2 = min8(r + 16), g3 = min8(r + 24);
+  if (min3(fminf(g0, g1), g2, g3) < best.s[3]) {
+    best.insert(g0, group0);
+    best.insert(g1, group0 + 1);
+    best.insert(g2, group0 + 2);
+    best.insert(g3, group0 + 3);
   }
 }
 
@@ -277,7 +276,7 @@ match_tc_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, in
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(t_full + acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int n0 = (tile0 + it) * (kTileRows / kGroup);  // first 16-row group of this tile
+      const int n0 = (tile0 + it) * (kTileRows / kGroup);  // first 8-row group of this tile
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 256 + h * 128;
       uint32_t ra[32], rb[32];
       tmem_ld32_issue(taddr, ra);
@@ -286,15 +285,15 @@ match_tc_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, in
       scan_chunk(ra, n0, best);
       tmem_ld_wait();
       tmem_ld32_issue(taddr + 64, ra);
-      scan_chunk(rb, n0 + 2, best);
+      scan_chunk(rb, n0 + 4, best);
       tmem_ld_wait();
       tmem_ld32_issue(taddr + 96, rb);
-      scan_chunk(ra, n0 + 4, best);
+      scan_chunk(ra, n0 + 8, best);
       tmem_ld_wait();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + acc);  // TMEM stage is free as soon as the registers hold it
-      scan_chunk(rb, n0 + 6, best);
+      scan_chunk(rb, n0 + 12, best);
     }
     {
       const size_t q = (size_t)qtile * kQueriesPerCta + h * 128 + row;
@@ -364,7 +363,7 @@ match_rerank_kernel(const float* __restrict__ query, int n_query, int n_query_pa
     if (g >= 0 && row < n_train) {
       const float4* t = reinterpret_cast<const float4*>(train + (size_t)row * kDim);
       float acc = 0.0f;
-#pragma unroll 4
+#pragma unroll 16
       for (int k4 = 0; k4 < kDim / 4; ++k4) {
         const float4 tv = __ldg(t + k4);
         float df = __fsub_rn(sQ[warp][4 * k4], tv.x);
@@ -447,11 +446,12 @@ static Plan make_plan(int nq, int nt) {
   // number of train splits: fill the 148 SMs (1 CTA each) in whole waves, keep >= 16 tiles per CTA when possible
   int want = 1;
   double best_eff = -1.0;
+  // (every extra split costs a second set of candidates in the re-rank: only split when it buys >= 15 %)
   for (int s = 1; s <= kMaxSplits && s <= p.n_tiles; ++s) {
     if (s > 1 && p.n_tiles / s < 16) break;
     const int ctas = p.n_qtiles * s;
     const double eff = (double)ctas / ((double)div_up(ctas, 148) * 148.0);
-    if (eff > best_eff + 0.02) { best_eff = eff; want = s; }
+    if (eff > best_eff + 0.15) { best_eff = eff; want = s; }
   }
   p.tiles_per_split = div_up(p.n_tiles, want);
   p.splits = div_up(p.n_tiles, p.tiles_per_split);
