@@ -16,6 +16,8 @@ from .device import ptr, require_cuda, stream_ptr, to_device
 def _as_desc(d) -> torch.Tensor:
     if not isinstance(d, torch.Tensor):
         d = np.asarray(d, dtype=np.float32)  # match() casts both sides to float32 (KD:333-334)
+        if d.ndim == 2 and d.shape[1] != 128:
+            raise ValueError("descriptors must be [n, 128]")
         d = d.reshape(-1, 128) if d.size else np.zeros((0, 128), np.float32)
     t = to_device(d, torch.float32)
     if t.dim() != 2 or t.shape[1] != 128:
