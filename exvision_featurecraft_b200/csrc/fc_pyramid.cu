@@ -395,42 +395,42 @@ __device__ __forceinline__ void fused_vertical_level(const FusedTaps& taps, floa
   *dst = acc;
 }
 
+// 8 output columns per thread: TY * TX / 8 = 256 items = exactly one per thread, no loop
 template <int L>
 __device__ __forceinline__ void fused_horizontal_level(const FusedTaps& taps, const float* __restrict__ sTmp,
                                                        float* __restrict__ out, int x0, int y0, int H, int W, bool vec_ok) {
   constexpr int R = FusedRadius<L>::R;
   constexpr int RP = (R + 3) & ~3;
-  constexpr int NV = (4 + 2 * RP) / 4;
-  constexpr int G = kFTX / 4;
-  const float* lvl = sTmp + L * kFTY * kFTP + (kFRP - RP);
-  for (int item = threadIdx.x; item < kFTY * G; item += 256) {
-    const int y = item / G;
-    const int g = item - y * G;
-    const float4* src = reinterpret_cast<const float4*>(lvl + y * kFTP + g * 4);
-    float v[4 * NV];
+  constexpr int NV = (8 + 2 * RP) / 4;
+  constexpr int G = kFTX / 8;
+  static_assert(kFTY * G == 256, "one item per thread");
+  const int y = threadIdx.x / G;
+  const int g = threadIdx.x - y * G;
+  const float4* src = reinterpret_cast<const float4*>(sTmp + L * kFTY * kFTP + (kFRP - RP) + y * kFTP + g * 8);
+  float v[4 * NV];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      const float4 t = src[q];
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-    }
-    float r[4];
+  for (int q = 0; q < NV; ++q) {
+    const float4 t = src[q];
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+  float r[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float acc = taps.t[L][0] * v[j + RP];
+  for (int j = 0; j < 8; ++j) {
+    float acc = taps.t[L][0] * v[j + RP];
 #pragma unroll
-      for (int k = 1; k <= R; ++k) acc = fmaf(taps.t[L][k], v[j + RP - k] + v[j + RP + k], acc);
-      r[j] = acc;
-    }
-    const int yy = y0 + y, xx = x0 + g * 4;
-    if (yy < H && xx < W) {
-      float* dst = out + (size_t)yy * W + xx;
-      if (vec_ok && xx + 3 < W) {
-        *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
-      } else {
+    for (int k = 1; k <= R; ++k) acc = fmaf(taps.t[L][k], v[j + RP - k] + v[j + RP + k], acc);
+    r[j] = acc;
+  }
+  const int yy = y0 + y, xx = x0 + g * 8;
+  if (yy < H && xx < W) {
+    float* dst = out + (size_t)yy * W + xx;
+    if (vec_ok && xx + 7 < W) {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(r[0], r[1], r[2], r[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(r[4], r[5], r[6], r[7]);
+    } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (xx + j < W) dst[j] = r[j];
-      }
+      for (int j = 0; j < 8; ++j)
+        if (xx + j < W) dst[j] = r[j];
     }
   }
 }
