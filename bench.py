@@ -221,6 +221,10 @@ class HarrisWorkload:
         alg = 9.0 * self.batch * self.H * self.W  # 1 B in + 8 B out per pixel
         return "harris5_strip_kernel", alg, t, "hbm"
 
+    def traffic(self, tr):
+        """dram bytes per launch of the dominant kernel, from the committed ncu capture scaled to this launch"""
+        return tr["harris5_strip_kernel"]["bytes_per_pixel"] * self.batch * self.H * self.W
+
     cpu_task = staticmethod(_cpu_harris_task)
 
     def cpu_items(self, n):
@@ -385,6 +389,12 @@ def main():
         else:
             peak, punit, src = peaks.get("bf16_tflops", 1590.0), "TFLOP/s", ("measured burst" if peaks else "fallback")
             ach = alg / (kms * 1e-3) / 1e12 if kms else None
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = wl.traffic(tr)
+        except Exception:
+            traffic = None
         line = {"metric": wl.metric, "value": units / (ms * 1e-3), "unit": wl.unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": wl.describe(world),
@@ -392,7 +402,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": kname, "bound": bound, "achieved": ach, "peak": peak, "unit": punit,
-                             "frac": (ach / peak) if ach else None, "traffic": getattr(wl, "ncu_traffic", None),
+                             "frac": (ach / peak) if ach else None, "traffic": traffic,
                              "peak_source": src, "kernel_ms": kms, "algorithmic_per_launch": alg},
                 "clocks": clocks, "pcie": pcie}
         extra = getattr(wl, "extra", None)

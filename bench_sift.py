@@ -92,7 +92,10 @@ class SiftWorkload:
         alg = 24.0 * self.batch * (2 * self.H) * (2 * self.W)  # 4 B base read + 5 x 4 B levels written per octave pixel
         if self.mode == "f64":
             alg *= 2
-        return "gauss_octave_kernel (octave 0)", alg, ms, "hbm"
+        return "gauss_octave_fused_kernel (octave 0)" if self.mode == "f32" else "gauss_octave_kernel (octave 0)", alg, ms, "hbm"
+
+    def traffic(self, tr):
+        return tr["gauss_octave_fused_kernel"]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W) * (2 if self.mode == "f64" else 1)
 
     def extra(self):
         n = max(self.recorded_steps, 1)
@@ -190,6 +193,10 @@ class MatchWorkload:
         ms = [a.elapsed_time(b) for a, b in self.ev[: self.ev_i]]
         # whole knn2 call (prep + GEMM + re-rank + re-check); algorithmic FLOPs = 2 * nq * nt * 128
         return "match_tc_kernel (+prep, re-rank, re-check)", 2.0 * self.nq * self.nt * 128, float(np.mean(ms)) if ms else None, "tensor"
+
+    def traffic(self, tr):
+        t = tr["match_tc_kernel"]
+        return t["bytes_per_launch"] if (self.nq, self.nt) == (t["n_query"], t["n_train"]) else None
 
     def extra(self):
         return self.matching.last_stats()
