@@ -114,7 +114,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
       bins[u] = kOriBins;  // the dropped bin
       ws[u] = ACC(0);
       if (t < total) {
-        const size_t o = (size_t)(r0 + rr) * W + (c0 + cc);
+        const int o = (r0 + rr) * W + (c0 + cc);
         bins[u] = ob[o];
         ws[u] = Math<T>::mul(m[o], weights[woff + rr * side + cc]);
       }
@@ -223,8 +223,8 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     for (int rx = 0; rx < 4; ++rx) {
       const int X = (X0 + ad[rx]) >> 10;
       const int Y = (Y0 + bd[rx]) >> 10;
-      const bool in = (X >= 0 && X < W && Y >= 0 && Y < H);
-      const size_t o = in ? (size_t)Y * W + X : 0;
+      const bool in = ((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H);
+      const int o = in ? Y * W + X : 0;  // one image plane has fewer than 2^31 pixels (checked on the host)
       mv[rx] = in ? m[o] : T(0);
       dv4[rx] = in ? d[o] : T(0);
     }
@@ -235,11 +235,18 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
       // identity for non-negative values and one rounded +360 otherwise (can give exactly 360.0 -> bin 8, dropped)
       ACC rel = Math<ACC>::add((ACC)dv4[rx], -theta_a);
       if (rel < ACC(0)) rel = Math<ACC>::add(rel, ACC(360));
-      // bin = int(rel * 8 / 360.0): count of thresholds <= rel (binary search over the exact host table)
-      int hb = (rel >= sThr[3]) ? 4 : 0;
-      hb += (rel >= sThr[hb + 1]) ? 2 : 0;
-      hb += (rel >= sThr[hb]) ? 1 : 0;
-      hb = (rel >= sThr[7]) ? 8 : hb;
+      int hb;
+      if constexpr (sizeof(ACC) == 4) {
+        // f32 mode: truncate rel / 45 and repair the one-off at the bin edges with a single compare
+        hb = __float2int_rz(rel * 0.022222222f);
+        hb += (rel >= 45.0f * (float)(hb + 1)) ? 1 : 0;
+      } else {
+        // bin = int(rel * 8 / 360.0): count of thresholds <= rel (binary search over the exact host table)
+        hb = (rel >= sThr[3]) ? 4 : 0;
+        hb += (rel >= sThr[hb + 1]) ? 2 : 0;
+        hb += (rel >= sThr[hb]) ? 1 : 0;
+        hb = (rel >= sThr[7]) ? 8 : hb;
+      }
       myh[hb * 32] += wv;
     }
   }
@@ -342,6 +349,7 @@ extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orienta
   if (!magnitude || !orientation_bin || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0) return FC_ERR_BAD_ARG;
   if (n_keypoints == 0) return FC_OK;
   if (!keypoints || !bin_mask || n_keypoints < 0) return FC_ERR_BAD_ARG;
+  if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = div_up(n_keypoints, kOriWarps);
   if (dtype == FC_F32)
@@ -385,6 +393,7 @@ extern "C" int fc_descriptors(const void* magnitude, const void* direction, int 
   if (!magnitude || !direction || !gmask || !trig || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
   if (n_oriented == 0) return FC_OK;
   if (!oriented || !descriptors || n_oriented < 0) return FC_ERR_BAD_ARG;
+  if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
   if (reinterpret_cast<uintptr_t>(oriented) & 15) return FC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = div_up(n_oriented, kDescWarps);
