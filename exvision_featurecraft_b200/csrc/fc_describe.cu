@@ -3,7 +3,7 @@
 //   gradient_field_kernel<T>   sift_gradient (APP/utils/keypoint_descriptor.py:72-79) of one pyramid level:
 //                              magnitude, direction (degrees, Python % 360) and the 36-bin index
 //                              np.round(direction * 36 / 360) (:140-142) as one byte per pixel.
-//   orientation_kernel<T>      one warp per keypoint: zero-padded (2r+1)^2 window, weight = magnitude x
+//   orientation_kernel<T,LPK>  8 / 16 / 32 lanes per keypoint: zero-padded (2r+1)^2 window, weight = magnitude x
 //                              unnormalised Gaussian table, 36-bin histogram (:144-163).  Every lane owns a
 //                              private copy of the histogram in shared memory ([bin][lane], conflict free,
 //                              no atomics, deterministic float64 sums); bins are reduced by shuffles, rounded
@@ -74,22 +74,29 @@ static constexpr int kOriWarps = 4;
 static constexpr int kOriBins = 36;
 static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the final column sums are conflict free
 
-// ACC = double in exact (f64) mode; float in f32 mode (whose parity bar is a tolerance: every per-sample operation
-// then stays on the fp32 pipes and the histograms need half the shared memory)
-template <typename T>
+// LPK lanes share one keypoint (32 / LPK keypoints per warp): the per-lane fixed work (clearing and reducing the private
+// histograms) is the same for every LPK, so small windows -- most keypoints sit in octave 0 with 15x15 or 21x21
+// windows -- use 8 lanes and amortise it over four keypoints per warp.  Sums are in T: double in exact (f64) mode,
+// float in f32 mode (whose parity bar is a tolerance), always in a fixed order (deterministic).
+template <typename T, int LPK>
 __global__ void __launch_bounds__(kOriWarps * 32)
 orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, int H, int W,
                    const int32_t* __restrict__ keypoints, int n_keypoints, const T* __restrict__ weights,
                    int radius, unsigned long long* __restrict__ bin_mask) {
-  using ACC = T;
-  __shared__ ACC hist[kOriWarps][(kOriBins + 1) * kOriPitch];
+  constexpr int KPW = 32 / LPK;        // keypoints per warp
+  constexpr int PITCH = LPK + 1;       // [bin][lane] + one pad column: the final column sums are conflict free
+  constexpr int NB = (kOriBins + LPK - 1) / LPK;  // bins reduced by one lane
+  __shared__ T hist[kOriWarps][KPW][(kOriBins + 1) * PITCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * kOriWarps + warp;
-  if (n >= n_keypoints) return;  // warp-uniform; no block-wide barriers below
-  ACC* h = hist[warp];
-  for (int t = lane; t < (kOriBins + 1) * kOriPitch; t += 32) h[t] = ACC(0);
+  const int sub = lane % LPK, slot = lane / LPK;
+  const int n = (blockIdx.x * kOriWarps + warp) * KPW + slot;
+  const bool valid = n < n_keypoints;
+  if ((blockIdx.x * kOriWarps + warp) * KPW >= n_keypoints) return;  // warp-uniform; no block-wide barriers below
+  T* h = hist[warp][slot];
+  for (int t = sub; t < (kOriBins + 1) * PITCH; t += LPK) h[t] = T(0);
   __syncwarp();
-  const int b = keypoints[3 * n], ki = keypoints[3 * n + 1], kj = keypoints[3 * n + 2];
+  const int nn = valid ? n : 0;
+  const int b = keypoints[3 * nn], ki = keypoints[3 * nn + 1], kj = keypoints[3 * nn + 2];
   const T* m = mag + (size_t)b * H * W;
   const uint8_t* ob = obin + (size_t)b * H * W;
   const int side = 2 * radius + 1;
@@ -97,22 +104,22 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const int r0 = max(ki - radius, 0), r1 = min(ki + radius, H - 1);
   const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
   const int nc = c1 - c0 + 1;
-  const int total = (r1 - r0 + 1) * nc;
+  const int total = valid ? (r1 - r0 + 1) * nc : 0;
   const float inv_nc = 1.0f / (float)nc;
   const int woff = (r0 - ki + radius) * side + (c0 - kj + radius);
   // 4 samples per lane and trip: all 12 loads are issued before the first dependent shared-memory update
-  for (int tb = 0; tb < total; tb += 128) {
+  for (int tb = 0; __any_sync(0xffffffffu, tb < total); tb += 4 * LPK) {
     int bins[4];
-    ACC ws[4];
+    T ws[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int t = tb + u * 32 + lane;
+      const int t = tb + u * LPK + sub;
       int rr = __float2int_rd(__fmul_rn((float)t, inv_nc));  // t / nc up to +-1, fixed below
       int cc = t - rr * nc;
       if (cc < 0) { cc += nc; --rr; }
       if (cc >= nc) { cc -= nc; ++rr; }
       bins[u] = kOriBins;  // the dropped bin
-      ws[u] = ACC(0);
+      ws[u] = T(0);
       if (t < total) {
         const int o = (r0 + rr) * W + (c0 + cc);
         bins[u] = ob[o];
@@ -120,30 +127,41 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) h[bins[u] * kOriPitch + lane] += ws[u];  // bin 36 is accumulated but never read
+    for (int u = 0; u < 4; ++u) h[bins[u] * PITCH + sub] += ws[u];  // bin 36 is accumulated but never read
   }
   __syncwarp();
-  // column sums: lane l reduces bins l and l + 32
-  float f0, f1 = 0.0f;
-  {
-    ACC s = ACC(0);
+  // column sums: lane `sub` reduces bins sub, sub + LPK, ...; histogram entries are float32 in the reference (:158)
+  float f[NB];
+  float mx = 0.0f;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int bin = sub + q * LPK;
+    f[q] = -1.0f;
+    if (bin < kOriBins) {
+      T sacc = T(0);
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) s += h[lane * kOriPitch + k];
-    f0 = (float)s;
-    if (lane < kOriBins - 32) {
-      ACC s2 = ACC(0);
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) s2 += h[(lane + 32) * kOriPitch + k];
-      f1 = (float)s2;
+      for (int k = 0; k < LPK; ++k) sacc += h[bin * PITCH + k];
+      f[q] = (float)sacc;
+      mx = fmaxf(mx, f[q]);
     }
   }
-  float mx = fmaxf(f0, f1);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  for (int o = LPK / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   const float cut = __fmul_rn(0.8f, mx);  // NEP 50: python float * float32 scalar stays float32
-  const uint32_t lo = __ballot_sync(0xffffffffu, f0 >= cut);
-  const uint32_t hi = __ballot_sync(0xffffffffu, (lane < kOriBins - 32) && (f1 >= cut));
-  if (lane == 0) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+  uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int bin = sub + q * LPK;
+    if (bin < kOriBins && f[q] >= cut) {
+      if (bin < 32) lo |= 1u << bin; else hi |= 1u << (bin - 32);
+    }
+  }
+#pragma unroll
+  for (int o = LPK / 2; o > 0; o >>= 1) {
+    lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+    hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+  }
+  if (sub == 0 && valid) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
 
 __global__ void popcount64_kernel(const unsigned long long* __restrict__ m, int n, int32_t* __restrict__ counts) {
@@ -351,17 +369,19 @@ extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orienta
   if (!keypoints || !bin_mask || n_keypoints < 0) return FC_ERR_BAD_ARG;
   if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
   cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = div_up(n_keypoints, kOriWarps);
-  if (dtype == FC_F32)
-    orientation_kernel<float><<<blocks, kOriWarps * 32, 0, st>>>((const float*)magnitude, orientation_bin, height, width,
-                                                                 keypoints, n_keypoints, (const float*)weights, radius,
-                                                                 (unsigned long long*)bin_mask);
-  else if (dtype == FC_F64)
-    orientation_kernel<double><<<blocks, kOriWarps * 32, 0, st>>>((const double*)magnitude, orientation_bin, height, width,
-                                                                  keypoints, n_keypoints, (const double*)weights, radius,
-                                                                  (unsigned long long*)bin_mask);
-  else
-    return FC_ERR_BAD_ARG;
+  if (dtype != FC_F32 && dtype != FC_F64) return FC_ERR_BAD_ARG;
+  // lanes per keypoint by window size: (2r+1)^2 <= 441 samples -> 8, <= 961 -> 16, else a whole warp
+  const int lpk = radius <= 10 ? 8 : (radius <= 15 ? 16 : 32);
+#define FC_ORI(T, LPK)                                                                                              \
+  orientation_kernel<T, LPK><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(                \
+      (const T*)magnitude, orientation_bin, height, width, keypoints, n_keypoints, (const T*)weights, radius,      \
+      (unsigned long long*)bin_mask)
+  if (dtype == FC_F32) {
+    if (lpk == 8) FC_ORI(float, 8); else if (lpk == 16) FC_ORI(float, 16); else FC_ORI(float, 32);
+  } else {
+    if (lpk == 8) FC_ORI(double, 8); else if (lpk == 16) FC_ORI(double, 16); else FC_ORI(double, 32);
+  }
+#undef FC_ORI
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
