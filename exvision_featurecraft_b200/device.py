@@ -49,6 +49,25 @@ def scan_scratch(n: int) -> torch.Tensor:
 _PINNED_SLOTS: dict = {}
 
 
+def read_last_ints(tensors) -> list:
+    """[int(t[-1]) for t in tensors] (int32 CUDA tensors) with ONE host synchronisation: the last elements are
+    published to pinned host memory by kernels (see read_int) and a single event is waited for."""
+    if not tensors:
+        return []
+    key = (tensors[0].device.index, torch.cuda.current_stream().cuda_stream)
+    slot = _PINNED_SLOTS.get(key)
+    if slot is None or slot[0].numel() < len(tensors):
+        slot = (torch.zeros(max(16, len(tensors)), dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        _PINNED_SLOTS[key] = slot
+    host, ev = slot
+    for i, t in enumerate(tensors):
+        src = t.reshape(-1)[-1:]
+        _lib.call("fc_publish_i32", C.c_void_p(src.data_ptr()), C.c_void_p(host.data_ptr() + 4 * i), 1, stream_ptr())
+    ev.record()
+    ev.synchronize()
+    return [int(v) for v in host[: len(tensors)].tolist()]
+
+
 def read_int(t: torch.Tensor, index: int = -1) -> int:
     """int(t[index]) for an int32 CUDA tensor WITHOUT a D2H memcpy: a kernel stores the value into pinned host
     memory and the host waits on an event.  A 4-byte cudaMemcpy would queue behind any bulk device-to-host

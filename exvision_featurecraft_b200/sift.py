@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import ptr, read_int, require_cuda, scan_scratch, stream_ptr, to_device
+from .device import ptr, read_int, read_last_ints, require_cuda, scan_scratch, stream_ptr, to_device
 
 
 @dataclass(frozen=True)
@@ -383,12 +383,7 @@ def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
     dev = mag.device
     if n == 0:
         return torch.empty((0, 4), dtype=torch.int32, device=dev)
-    radius = int(round(sigma * 2))
-    if 2 * kernel_radius(sigma) + 1 != 2 * radius + 1:
-        # the reference multiplies a (2r+1)^2 window by the kernel: shapes must agree or numpy raises
-        raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,%d)"
-                         % (2 * radius + 1, 2 * radius + 1, 2 * kernel_radius(sigma) + 1, 2 * kernel_radius(sigma) + 1))
-    weights = _cached(("ori", float(sigma), params.dtype), lambda: gaussian_window_table(sigma), params.torch_dtype)
+    radius, weights = _orientation_weights(sigma, params)
     b, h, w = mag.shape
     bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
     _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), params.fc_dtype, b, h, w, ptr(keypoints), n, ptr(weights), radius,
@@ -427,32 +422,93 @@ def active_scales(params: SiftParams):
     return [k for k in ks if k <= params.s_value]
 
 
+def _mask_scan(mask: torch.Tensor, width: int):
+    b, h, _ = mask.shape
+    row_offsets = torch.empty(b * h + 1, dtype=torch.int32, device=mask.device)
+    scratch = scan_scratch(b * h)
+    _lib.call("fc_mask_scan", ptr(mask), b, h, width, ptr(row_offsets), ptr(scratch), stream_ptr())
+    return row_offsets
+
+
+def _orientation_weights(sigma, params: SiftParams):
+    radius = int(round(sigma * 2))
+    if 2 * kernel_radius(sigma) + 1 != 2 * radius + 1:
+        # the reference multiplies a (2r+1)^2 window by the kernel: shapes must agree or numpy raises
+        raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,%d)"
+                         % (2 * radius + 1, 2 * radius + 1, 2 * kernel_radius(sigma) + 1, 2 * kernel_radius(sigma) + 1))
+    return radius, _cached(("ori", float(sigma), params.dtype), lambda: gaussian_window_table(sigma), params.torch_dtype)
+
+
 def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch.float32, keep_octaves: bool = False) -> SiftResult:
     """The whole hot path after the x2 up-sample: computeKeypointsAndDescriptors (KD:297-311) for a
-    [B,H,W] batch of base images."""
+    [B,H,W] batch of base images.
+
+    The (octave, scale) blocks are independent once the pyramid exists, so the work is queued in four phases with
+    only TWO host synchronisations per batch (the two data-dependent output sizes): A pyramid + extrema of every
+    octave, B mask scans -> all keypoint counts, C keypoint lists + gradient fields + orientation histograms + bin
+    scans -> all oriented counts, D oriented lists + descriptors."""
     require_cuda()
     scales = active_scales(params)
     img = _as_base_batch(base, params)
+    dev = img.device
     res = SiftResult(params, [])
+    # A: scale space
+    octaves = []
     for o in range(params.n_octaves):
         octv = gauss_octave(img, params, o, True)
+        octaves.append(octv)
         if o + 1 < params.n_octaves:
             img = downsample(octv, params)
-        for k in scales:
-            with _stage("compact"):
-                kps = keypoints_from_mask(octv.extrema[k - 1], octv.width)
-            blk = ScaleBlock(o, k, kps)
-            if kps.shape[0]:
-                sigma = keypoint_sigma(params.sigma_base, o, k, params.s_value)
-                with _stage("gradient_field"):
-                    mag, direction, obin = gradient_field(octv, k, params)
-                with _stage("orientation"):
-                    blk.oriented = orient(mag, obin, kps, sigma, params)
-                with _stage("descriptors"):
-                    blk.descriptors = describe(mag, direction, blk.oriented, sigma, params, out_dtype)
-            res.blocks.append(blk)
-        if keep_octaves:
-            res.octaves.append(octv)
+    if keep_octaves:
+        res.octaves = octaves
+    work = [(o, k) for o in range(params.n_octaves) for k in scales]
+    if not work:
+        return res
+    # B: row-major compaction offsets of every extrema mask, then one sync for the counts
+    with _stage("compact"):
+        row_offs = [_mask_scan(octaves[o].extrema[k - 1], octaves[o].width) for o, k in work]
+        n_kps = read_last_ints(row_offs)
+    # C: keypoints, gradient fields, orientation histograms, scans of the per-keypoint orientation counts
+    state = []
+    for (o, k), ro, n in zip(work, row_offs, n_kps):
+        octv = octaves[o]
+        b, h = octv.gauss.shape[0], octv.height
+        kps = torch.empty((n, 3), dtype=torch.int32, device=dev)
+        blk = ScaleBlock(o, k, kps)
+        res.blocks.append(blk)
+        if n == 0:
+            state.append(None)
+            continue
+        with _stage("compact"):
+            _lib.call("fc_mask_emit_keypoints", ptr(octv.extrema[k - 1]), ptr(ro), b, h, octv.width, ptr(kps), stream_ptr())
+        sigma = keypoint_sigma(params.sigma_base, o, k, params.s_value)
+        with _stage("gradient_field"):
+            mag, direction, obin = gradient_field(octv, k, params)
+        with _stage("orientation"):
+            radius, weights = _orientation_weights(sigma, params)
+            bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
+            _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), params.fc_dtype, b, h, octv.width, ptr(kps), n, ptr(weights),
+                      radius, ptr(bin_mask), stream_ptr())
+            offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            scratch = scan_scratch(n)
+            _lib.call("fc_orientation_scan", ptr(bin_mask), n, ptr(offsets), ptr(scratch), stream_ptr())
+        state.append((mag, direction, bin_mask, offsets, sigma))
+    live = [st for st in state if st is not None]
+    with _stage("orientation"):
+        totals = iter(read_last_ints([st[3] for st in live]))
+    # D: oriented keypoint lists and descriptors
+    for blk, st in zip(res.blocks, state):
+        if st is None:
+            continue
+        mag, direction, bin_mask, offsets, sigma = st
+        total = next(totals)
+        n = blk.keypoints.shape[0]
+        blk.oriented = torch.empty((total, 4), dtype=torch.int32, device=dev)
+        if total:
+            with _stage("orientation"):
+                _lib.call("fc_orientation_emit", ptr(blk.keypoints), ptr(bin_mask), ptr(offsets), n, ptr(blk.oriented), stream_ptr())
+        with _stage("descriptors"):
+            blk.descriptors = describe(mag, direction, blk.oriented, sigma, params, out_dtype)
     return res
 
 
