@@ -20,6 +20,7 @@
 //                        the brute-force one; undecidable rows are appended to a list ...
 //   match_exact_kernel   ... and re-done exactly (fc_match_exact.cu).
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "fc_common.cuh"
 
@@ -311,6 +312,197 @@ match_tc_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2-SM variant: a cluster of two CTAs issues tcgen05.mma.cta_group::2 (M = 256 = 2 x 128 query rows, N = 256 train
+// rows per instruction).  Each CTA stages its own 128-row query tile and ITS HALF of every 256-row train tile, so per
+// SM and MMA only 4 KB (A) + 4 KB (half of B) are read from shared memory instead of 8 + 8 KB for the same FLOPs:
+// the 1-SM kernel above is bound by the 128 B/clk shared-memory port (ncu: tensor pipe 79 % active), this one is not.
+//   leader CTA (rank 0): MMA issue; waits for its own and the peer's operand halves, commits with multicast so the
+//                        smem-free and accumulator-ready barriers of BOTH CTAs are signalled;
+//   peer CTA (rank 1):   warp 1 relays "my half has landed" to the leader; epilogue warps arrive remotely on the
+//                        leader's accumulator-free barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStages2 = 4;
+constexpr int kTileRows2 = 256;                 // train rows per stage (128 per CTA)
+constexpr size_t kSmemBytes2 = (1 + kStages2) * kTileBytes + 512;
+constexpr uint32_t kIdesc2 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);  // M = 256, N = 256
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc2), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+match_tc2_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, int n_query_padded, int n_tiles_total,
+                 int tiles_per_split, float* __restrict__ cand_score, int32_t* __restrict__ cand_idx) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sA = smem;                         // my 128 query rows
+  unsigned char* sB = smem + kTileBytes;            // kStages2 x my half (128 rows) of a 256-row train tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + kStages2) * kTileBytes);
+  uint64_t* full = bars;                         // [kStages2] my half landed (tx)
+  uint64_t* peer_full = full + kStages2;         // [kStages2] leader only: the peer's half landed
+  uint64_t* empty = peer_full + kStages2;        // [kStages2] MMAs that read the stage are done (multicast commit)
+  uint64_t* a_full = empty + kStages2;           // my query tile landed (tx)
+  uint64_t* peer_a_full = a_full + 1;            // leader only
+  uint64_t* t_full = peer_a_full + 1;            // [2] accumulators ready (multicast commit)
+  uint64_t* t_empty = t_full + 2;                // [2] leader only: 8 local + 8 remote epilogue warps drained the stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cq = blockIdx.x >> 1, split = blockIdx.y;
+  const int tile0 = split * tiles_per_split;
+  const int n_tiles = min(tiles_per_split, n_tiles_total - tile0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages2; ++s) { mbar_init(full + s, 1); mbar_init(peer_full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(a_full, 1);
+    mbar_init(peer_a_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const char* a_src = reinterpret_cast<const char*>(Ah) + ((size_t)cq * 2 + rank) * kTileBytes;
+      mbar_expect_tx(a_full, kTileBytes);
+      bulk_g2s(sA, a_src, kTileBytes, a_full);
+      const char* b_src = reinterpret_cast<const char*>(Bh) + ((size_t)tile0 * 2 + rank) * kTileBytes;
+      for (int it = 0; it < n_tiles; ++it) {
+        const int st = it % kStages2;
+        const uint32_t ph = (it / kStages2) & 1;
+        mbar_wait(empty + st, ph ^ 1);
+        mbar_expect_tx(full + st, kTileBytes);
+        bulk_g2s(sB + (size_t)st * kTileBytes, b_src + (size_t)it * 2 * kTileBytes, kTileBytes, full + st);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (rank == 1) {
+        // relay: tell the leader when my operands are in my shared memory
+        mbar_wait(a_full, 0);
+        mbar_arrive_remote(peer_a_full, 0);
+        for (int it = 0; it < n_tiles; ++it) {
+          const int st = it % kStages2;
+          mbar_wait(full + st, (it / kStages2) & 1);
+          mbar_arrive_remote(peer_full + st, 0);
+        }
+      } else {
+        mbar_wait(a_full, 0);
+        mbar_wait_cluster(peer_a_full, 0);
+        const uint32_t a_addr = smem_u32(sA);
+        for (int it = 0; it < n_tiles; ++it) {
+          const int st = it % kStages2;
+          const uint32_t ph = (it / kStages2) & 1;
+          const int acc = it & 1;
+          const uint32_t aph = (it >> 1) & 1;
+          mbar_wait_cluster(t_empty + acc, aph ^ 1);
+          mbar_wait(full + st, ph);
+          mbar_wait_cluster(peer_full + st, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b_addr = smem_u32(sB + (size_t)st * kTileBytes);
+          const uint32_t d = tmem_base + acc * 256;
+#pragma unroll
+          for (int kk = 0; kk < KP / 16; ++kk) umma2_f16(d, umma_desc(a_addr + kk * 256), umma_desc(b_addr + kk * 256), kk > 0);
+          umma2_commit_both(empty + st);    // both CTAs may refill this stage
+          umma2_commit_both(t_full + acc);  // both CTAs' epilogues may read the accumulators
+        }
+      }
+    }
+  } else {
+    // epilogue (both CTAs): my 128 query rows x 256 train columns per tile; warps 2-5 scan columns 0..127, warps 6-9
+    // columns 128..255 of the same rows
+    const int lg = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int row = lg * 32 + lane;
+    TopK best;
+    best.init();
+    for (int it = 0; it < n_tiles; ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(t_full + acc, aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int n0 = ((tile0 + it) * kTileRows2 + h * 128) / kGroup;  // first 8-row group of my 128 columns
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 256 + h * 128;
+      uint32_t ra[32], rb[32];
+      tmem_ld32_issue(taddr, ra);
+      tmem_ld_wait();
+      tmem_ld32_issue(taddr + 32, rb);
+      scan_chunk(ra, n0, best);
+      tmem_ld_wait();
+      tmem_ld32_issue(taddr + 64, ra);
+      scan_chunk(rb, n0 + 4, best);
+      tmem_ld_wait();
+      tmem_ld32_issue(taddr + 96, rb);
+      scan_chunk(ra, n0 + 8, best);
+      tmem_ld_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(t_empty + acc); else mbar_arrive_remote(t_empty + acc, 0);
+      }
+      scan_chunk(rb, n0 + 12, best);
+    }
+    // merge the two column halves of every row through shared memory (all operand stages are idle by now)
+    float* mS = reinterpret_cast<float*>(sB);
+    int* mI = reinterpret_cast<int*>(sB) + 128 * kCand;
+    if (h == 1) {
+#pragma unroll
+      for (int c = 0; c < kCand; ++c) { mS[row * kCand + c] = best.s[c]; mI[row * kCand + c] = best.i[c]; }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (h == 0) {
+#pragma unroll
+      for (int c = 0; c < kCand; ++c) best.insert(mS[row * kCand + c], mI[row * kCand + c]);  // groups of h = 1 are larger ids: ties keep h = 0
+      const size_t q = ((size_t)cq * 2 + rank) * 128 + row;
+      const size_t o = ((size_t)split * n_query_padded + q) * kCand;
+      *reinterpret_cast<float4*>(cand_score + o) = make_float4(best.s[0], best.s[1], best.s[2], best.s[3]);
+      *reinterpret_cast<int4*>(cand_idx + o) = make_int4(best.i[0], best.i[1], best.i[2], best.i[3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves before everything is done
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // exact re-rank of the candidates + decision bounds (see DESIGN.md "Matching: why the tensor path is exact")
 // ------------------------------------------------------------------------------------------------
 static constexpr int kRerankWarps = 4;
@@ -433,23 +625,33 @@ __global__ void zero_u32_kernel(unsigned int* p, int n) {
 }
 
 struct Plan {
-  int nq_pad, nt_pad, n_qtiles, n_tiles, splits, tiles_per_split;
+  int nq_pad, nt_pad, n_qtiles, n_tiles, splits, tiles_per_split;  // tiles = kTileRows2-row tiles when two_sm
   size_t off_a, off_b, off_cs, off_ci, off_stats, off_rows, total;
 };
 
+static bool use_two_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FC_MATCH_1SM");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static Plan make_plan(int nq, int nt) {
   Plan p;
+  const int tile_rows = use_two_sm() ? kTileRows2 : kTileRows;
   p.nq_pad = div_up(nq, kQueriesPerCta) * kQueriesPerCta;
-  p.nt_pad = div_up(nt, kTileRows) * kTileRows;
-  p.n_qtiles = p.nq_pad / kQueriesPerCta;
-  p.n_tiles = p.nt_pad / kTileRows;
+  p.nt_pad = div_up(nt, tile_rows) * tile_rows;
+  p.n_qtiles = p.nq_pad / kQueriesPerCta;  // 256 queries: one CTA (1-SM kernel) or one CTA pair (2-SM kernel)
+  p.n_tiles = p.nt_pad / tile_rows;
   // number of train splits: fill the 148 SMs (1 CTA each) in whole waves, keep >= 16 tiles per CTA when possible
   int want = 1;
   double best_eff = -1.0;
   // (every extra split costs a second set of candidates in the re-rank: only split when it buys >= 15 %)
   for (int s = 1; s <= kMaxSplits && s <= p.n_tiles; ++s) {
     if (s > 1 && p.n_tiles / s < 16) break;
-    const int ctas = p.n_qtiles * s;
+    const int ctas = p.n_qtiles * s * (use_two_sm() ? 2 : 1);
     const double eff = (double)ctas / ((double)div_up(ctas, 148) * 148.0);
     if (eff > best_eff + 0.15) { best_eff = eff; want = s; }
   }
@@ -504,9 +706,15 @@ extern "C" int fc_match_knn2(const float* query, int n_query, const float* train
   tc::match_prep_kernel<<<div_up(p.nt_pad * 32, 256), 256, 0, st>>>(train, n_train, p.nt_pad, 0, Bh, stats);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
-  FC_CUDA_TRY(cudaFuncSetAttribute(tc::match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-  dim3 grid(p.n_qtiles, p.splits);
-  tc::match_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(Ah, Bh, p.nq_pad, p.n_tiles, p.tiles_per_split, cs, ci);
+  if (tc::use_two_sm()) {
+    FC_CUDA_TRY(cudaFuncSetAttribute(tc::match_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
+    dim3 grid(2 * p.n_qtiles, p.splits);
+    tc::match_tc2_kernel<<<grid, tc::kThreads, tc::kSmemBytes2, st>>>(Ah, Bh, p.nq_pad, p.n_tiles, p.tiles_per_split, cs, ci);
+  } else {
+    FC_CUDA_TRY(cudaFuncSetAttribute(tc::match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
+    dim3 grid(p.n_qtiles, p.splits);
+    tc::match_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(Ah, Bh, p.nq_pad, p.n_tiles, p.tiles_per_split, cs, ci);
+  }
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   tc::match_rerank_kernel<<<div_up(n_query, tc::kRerankWarps), tc::kRerankWarps * 32, 0, st>>>(
