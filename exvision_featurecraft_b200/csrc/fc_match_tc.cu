@@ -541,18 +541,23 @@ match_rerank_kernel(const float* __restrict__ query, int n_query, int n_query_pa
     grp = cand_idx[o];
     gmin = cand_score[o];
   }
-  // smallest approximate score any row OUTSIDE the kept groups can have: min over splits of the 4th kept minimum
-  float s4 = (lane < n_splits * kCand && (lane % kCand) == kCand - 1) ? gmin : INFINITY;
+  // Only the kEval = 2 best groups of every split are evaluated exactly: the best row of a split lies in its best
+  // group and its second best row in its two best groups.  Every row that is NOT evaluated (members of the 3rd / 4th
+  // kept group and everything outside) has an approximate score >= the 3rd kept minimum of its split.
+  constexpr int kEval = 2;
+  float s4 = (lane < n_splits * kCand && (lane % kCand) == kEval) ? gmin : INFINITY;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s4 = fminf(s4, __shfl_xor_sync(0xffffffffu, s4, o));
-  // exact float32 distances (same operation order as match_exact_kernel) of every member of the kept groups
+  // exact float32 distances (same operation order as match_exact_kernel) of every member of the evaluated groups
   Best2 b;
   b.init();
-  const int n_cand = n_splits * kCand * kGroup;
-  for (int c = lane; c < n_cand; c += 32) {
-    const int g = __shfl_sync(0xffffffffu, grp, c / kGroup);
+  const int n_cand = n_splits * kEval * kGroup;
+  for (int c0 = 0; c0 < n_cand; c0 += 32) {  // warp-uniform trip count: the shuffle below needs all 32 lanes
+    const int c = c0 + lane;
+    const int gi = (c / kGroup) % (kMaxSplits * kEval);  // evaluated group number: split gi / kEval, rank gi % kEval
+    const int g = __shfl_sync(0xffffffffu, grp, (gi / kEval) * kCand + (gi % kEval));
     const int row = g * kGroup + (c % kGroup);
-    if (g >= 0 && row < n_train) {
+    if (c < n_cand && g >= 0 && row < n_train) {
       const float4* t = reinterpret_cast<const float4*>(train + (size_t)row * kDim);
       float acc = 0.0f;
 #pragma unroll 16
@@ -596,7 +601,7 @@ match_rerank_kernel(const float* __restrict__ query, int n_query, int n_query_pa
     // the two-term fp16 split of |t|^2 and fp32 accumulation
     const float qn = sqrtf(q2), tn = sqrtf(tmax);
     const float delta = 2.0f * (0.0009775f * qn * tn + 6.8e-7f * (qn + tn)) + 2e-6f * (1.0f + q2 + tmax);
-    const float lb2 = s4 + q2 - delta;  // lower bound on the true squared distance of every row outside the kept groups
+    const float lb2 = s4 + q2 - delta;  // lower bound on the true squared distance of every row that was not evaluated
     const float lb = lb2 > 0.f ? sqrtf(lb2) : 0.f;
     const double r = ratio;
     const bool is_good = i1 >= 0 && (double)d0 < r * (double)d1;
