@@ -16,7 +16,7 @@ class SiftWorkload:
     dtype = "f32"
     H = W = 1024
     cpu_sample_items = 16
-    cpu_sample_note = "(256x256 crops of the same generator: a 1024x1024 image takes ~5 min per core)"
+    cpu_sample_note = "(256x256 crops of the same generator, oracle with separable blurs: the reference's direct 2-D convolution is ~5x slower and a 1024x1024 image takes ~5 min per core)"
 
     def __init__(self, args):
         self.batch = args.batch or 8
