@@ -225,7 +225,7 @@ class AllPairsWorkload(MatchWorkload):
     def describe(self, world):
         return {"workload": "all-pairs 2-NN ratio-test matching: %d descriptors per GPU against the blocks of all %d GPUs per step "
                             "(ring of NCCL send/recv, %d-row blocks)" % (self.nq, world, self.nq),
-                "sharding": "descriptor blocks per rank; exchange = (world-1)-step ring, overlapped by nothing yet",
+                "sharding": "descriptor blocks per rank; exchange = (world-1)-step ring, next block in flight while the current one is matched",
                 "l2": "blocks (%.0f MB fp32 each) exceed L2 together with the fp16 operands" % (self.nq * 512 / 1e6)}
 
     def units_per_step(self):

@@ -68,12 +68,13 @@ def ring_schedule(world: int):
     return [[(r, (r + s) % world) for r in range(world)] for s in range(world)]
 
 
-def ring_shift(block: torch.Tensor, max_rows: int):
-    """One ring step: send `block` ([n, d], n <= max_rows) to rank-1 and receive the block of rank+1, so that
-    after s steps a rank holds the block of rank (r + s) % world.  Returns the received [n', d] tensor."""
+def ring_shift_start(block: torch.Tensor, max_rows: int):
+    """Post one ring step: send `block` ([n, d], n <= max_rows) to rank-1 and receive the block of rank+1 (after s
+    steps a rank holds the block of rank (r + s) % world).  Returns a handle for ring_shift_finish; the transfers run
+    on the communication backend's own stream, so kernels queued in between overlap them."""
     rank, world = world_info()
     if world == 1:
-        return block
+        return ("local", block)
     d = block.shape[1]
     send = torch.zeros((max_rows + 1, d), dtype=block.dtype, device=block.device)
     send[0, 0] = block.shape[0]  # row count travels in the header row
@@ -81,20 +82,34 @@ def ring_shift(block: torch.Tensor, max_rows: int):
     recv = torch.empty_like(send)
     dst, src = (rank - 1) % world, (rank + 1) % world
     ops = [dist.P2POp(dist.isend, send, dst), dist.P2POp(dist.irecv, recv, src)]
-    for req in dist.batch_isend_irecv(ops):
+    return ("posted", dist.batch_isend_irecv(ops), send, recv)
+
+
+def ring_shift_finish(handle):
+    if handle[0] == "local":
+        return handle[1]
+    _, reqs, _send, recv = handle
+    for req in reqs:
         req.wait()
     n = int(recv[0, 0].item())
     return recv[1:1 + n].contiguous()
 
 
+def ring_shift(block: torch.Tensor, max_rows: int):
+    """One blocking ring step (see ring_shift_start)."""
+    return ring_shift_finish(ring_shift_start(block, max_rows))
+
+
 def all_pairs_match(local_desc: torch.Tensor, match_fn, max_rows: int):
-    """Match the local descriptor block (queries) against the block of every rank (train), ring order.
+    """Match the local descriptor block (queries) against the block of every rank (train), ring order.  The transfer
+    of the NEXT block is posted before the current block is matched, so NVLink traffic hides under the GEMM.
     match_fn(query, train) -> any result; returns [(train_rank, result)] with world entries."""
     rank, world = world_info()
     results = []
     visiting = local_desc
     for s in range(world):
+        handle = ring_shift_start(visiting, max_rows) if s + 1 < world else None
         results.append(((rank + s) % world, match_fn(local_desc, visiting)))
-        if s + 1 < world:
-            visiting = ring_shift(visiting, max_rows)
+        if handle is not None:
+            visiting = ring_shift_finish(handle)
     return results
