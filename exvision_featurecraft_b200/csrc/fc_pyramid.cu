@@ -11,6 +11,8 @@
 //
 // HBM traffic per octave pixel (T = float): 4 B base read + 4 B x n_levels written; the extrema kernel
 // re-reads the levels once (+ 4 B x n_levels) -- DESIGN.md states the algorithmic figure (24 B).
+#include <stdlib.h>
+
 #include "fc_common.cuh"
 
 namespace fc {
@@ -503,6 +505,204 @@ gauss_octave_fused_kernel(const float* __restrict__ base, int H, int W, FusedTap
   fused_horizontal_level<4>(taps, sTmp, gout + 4 * plane, x0, y0, H, W, vec_ok);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed (FFMA2) variant of the fused default-radii kernel
+// ------------------------------------------------------------------------------------------------
+// The fused kernel above is issue-bound: 9.4 warp instructions per octave pixel of which only 4.9 are FP32 math.
+// sm_100 has packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2: one issue slot, two lanes of the FP32 pipe), so this
+// version keeps every value as an aligned pair of horizontally adjacent pixels:
+//   * vertical pass: a thread owns a column PAIR and 8 output rows; the 34-row window, the 13 pair sums
+//     v[-k] + v[+k] (shared by all five levels) and the taps (t, t) are all float2 -> 13 FADD2 + 41 FFMA2 per output pair.
+//   * horizontal pass: a thread owns 12 consecutive output columns (6 pairs) of one row and walks the ALIGNED input
+//     pairs P_e = (h[o+e], h[o+e+1]), e even, of each output pair (o, o+1) with two accumulators:
+//         A += (t|e|, t|e|) * P_e            -> (out[o], out[o+1]) contributions of even distance
+//         B += (t|e-1|, t|e+1|) * P_e        -> (out[o+1], out[o]) contributions of odd distance (lanes crossed)
+//     out[o] = A.lo + B.hi, out[o+1] = A.hi + B.lo.  No register shuffles, no unaligned shared loads.
+// Tile = 96 x 32 outputs; input tile 128 columns (x0-16 .. x0+111, 16-byte cp.async) x 58 rows; the five
+// intermediate tiles use the same 128-column pitch.  Vertical items = 62 column pairs x 4 row groups = 248 of 256
+// threads, horizontal items = 8 x 32 = 256.
+struct PackedTaps {
+  float2 v[5][14];   // (t_k, t_k)
+  float2 ha[5][15];  // index (e + E) / 2: (t|e|, t|e|), zero outside the radius
+  float2 hb[5][15];  // index (e + E) / 2: (t|e-1|, t|e+1|), zero outside the radius
+};
+
+static constexpr int kPTX = 96, kPTY = 32, kPP = 128;  // tile and shared pitch (floats)
+static constexpr int kPIH = kPTY + 2 * kFR;            // 58 input rows
+static constexpr int kPPairs = (kPTX + 28) / 2;        // 62 column pairs: smem columns 2 .. 125
+static constexpr size_t kPackedSmem = sizeof(float) * (size_t)(kPIH * kPP + 5 * kPTY * kPP);
+
+template <int L>
+__device__ __forceinline__ void packed_vertical_level(const PackedTaps& taps, float2 centre, const float2 (&s)[kFR + 1],
+                                                      float2* __restrict__ dst) {
+  constexpr int R = FusedRadius<L>::R;
+  float2 acc = __fmul2_rn(taps.v[L][0], centre);
+#pragma unroll
+  for (int k = 1; k <= R; ++k) acc = __ffma2_rn(taps.v[L][k], s[k], acc);
+  *dst = acc;
+}
+
+template <int L>
+__device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, const float* __restrict__ sTmp,
+                                                        float* __restrict__ out, int x0, int y0, int H, int W, bool vec_ok) {
+  constexpr int R = FusedRadius<L>::R;
+  constexpr int E = (R & 1) ? R + 1 : R;    // input pairs at even offsets -E .. E of each output pair
+  constexpr int E4 = (E + 3) & ~3;
+  constexpr int N4 = (2 * E4 + 12) / 4;
+  const int y = threadIdx.x >> 3;
+  const int g = threadIdx.x & 7;
+  const float4* src = reinterpret_cast<const float4*>(sTmp + (L * kPTY + y) * kPP + 16 + 12 * g - E4);
+  float2 p[2 * N4];
+#pragma unroll
+  for (int q = 0; q < N4; ++q) {
+    const float4 t = src[q];
+    p[2 * q] = make_float2(t.x, t.y);
+    p[2 * q + 1] = make_float2(t.z, t.w);
+  }
+  float r[12];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int e = -E; e <= E; e += 2) {
+      const float2 in = p[E4 / 2 + q + e / 2];
+      const int i = (e + E) / 2;
+      if (e >= -R && e <= R) a = (e == -E || e - 2 < -R) ? __fmul2_rn(taps.ha[L][i], in) : __ffma2_rn(taps.ha[L][i], in, a);
+      b = (e == -E) ? __fmul2_rn(taps.hb[L][i], in) : __ffma2_rn(taps.hb[L][i], in, b);
+    }
+    r[2 * q] = a.x + b.y;
+    r[2 * q + 1] = a.y + b.x;
+  }
+  const int yy = y0 + y, xx = x0 + 12 * g;
+  if (yy < H && xx < W) {
+    float* dst = out + (size_t)yy * W + xx;
+    if (vec_ok && xx + 11 < W) {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(r[0], r[1], r[2], r[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(r[4], r[5], r[6], r[7]);
+      reinterpret_cast<float4*>(dst)[2] = make_float4(r[8], r[9], r[10], r[11]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 12; ++j)
+        if (xx + j < W) dst[j] = r[j];
+    }
+  }
+}
+
+template <bool IDENT0>
+__global__ void __launch_bounds__(256, 2)
+gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, const __grid_constant__ PackedTaps taps,
+                           float* __restrict__ gauss) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sIn = reinterpret_cast<float*>(smem_raw);
+  float* sTmp = sIn + kPIH * kPP;
+  const int x0 = blockIdx.x * kPTX, y0 = blockIdx.y * kPTY;
+  const int b = blockIdx.z;
+  const float* img = base + (size_t)b * H * W;
+  float* gout = gauss + (size_t)b * 5 * H * W;
+  const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gauss) & 15) == 0);
+  {
+    // smem column c <-> image column x0 - 16 + c; interior tiles copy 16 bytes per cp.async
+    const bool interior_x = (x0 - 16 >= 0) && (x0 - 16 + kPP <= W) && (W % 4 == 0) &&
+                            ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    if (interior_x) {
+      for (int t = threadIdx.x; t < kPIH * (kPP / 4); t += 256) {
+        const int r = t >> 5, c4 = t & 31;
+        const int y = reflect_symm(y0 - kFR + r, H);
+        const float* src = img + (size_t)y * W + (x0 - 16) + 4 * c4;
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(sIn + r * kPP + 4 * c4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+      }
+    } else {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int r = warp; r < kPIH; r += 8) {
+        const int y = reflect_symm(y0 - kFR + r, H);
+        const float* row = img + (size_t)y * W;
+        float* dst = sIn + r * kPP;
+        for (int c = lane; c < kPP; c += 32) cp_async_elem<float>(dst + c, row + reflect_symm(x0 - 16 + c, W));
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 * kPPairs) {
+    const int rg = threadIdx.x / kPPairs;
+    const int pc = threadIdx.x - rg * kPPairs + 1;  // pair index: smem columns 2pc, 2pc+1
+    const float2* src = reinterpret_cast<const float2*>(sIn + (rg * 8) * kPP) + pc;
+    float2 v[8 + 2 * kFR];
+#pragma unroll
+    for (int k = 0; k < 8 + 2 * kFR; ++k) v[k] = src[k * (kPP / 2)];
+    float2* dst = reinterpret_cast<float2*>(sTmp + (rg * 8) * kPP) + pc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 s[kFR + 1];
+#pragma unroll
+      for (int k = 1; k <= kFR; ++k) s[k] = __fadd2_rn(v[j + kFR - k], v[j + kFR + k]);
+      const float2 centre = v[j + kFR];
+      float2* d = dst + j * (kPP / 2);
+      if (!IDENT0) packed_vertical_level<0>(taps, centre, s, d);
+      packed_vertical_level<1>(taps, centre, s, d + 1 * kPTY * (kPP / 2));
+      packed_vertical_level<2>(taps, centre, s, d + 2 * kPTY * (kPP / 2));
+      packed_vertical_level<3>(taps, centre, s, d + 3 * kPTY * (kPP / 2));
+      packed_vertical_level<4>(taps, centre, s, d + 4 * kPTY * (kPP / 2));
+    }
+  }
+  if (IDENT0) {
+    // level 0 of octaves > 0 is the unblurred base (:136-137); reads sIn only, so it can run before the barrier
+    const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
+    const int yy = y0 + y, xx = x0 + 12 * g;
+    const float4* s4 = reinterpret_cast<const float4*>(sIn + (y + kFR) * kPP + 16 + 12 * g);
+    if (yy < H && xx < W) {
+      float* dst = gout + (size_t)yy * W + xx;
+      if (vec_ok && xx + 11 < W) {
+        reinterpret_cast<float4*>(dst)[0] = s4[0];
+        reinterpret_cast<float4*>(dst)[1] = s4[1];
+        reinterpret_cast<float4*>(dst)[2] = s4[2];
+      } else {
+        const float* s1 = reinterpret_cast<const float*>(s4);
+        for (int j = 0; j < 12; ++j)
+          if (xx + j < W) dst[j] = s1[j];
+      }
+    }
+  }
+  __syncthreads();
+  const size_t plane = (size_t)H * W;
+  if (!IDENT0) packed_horizontal_level<0>(taps, sTmp, gout, x0, y0, H, W, vec_ok);
+  packed_horizontal_level<1>(taps, sTmp, gout + plane, x0, y0, H, W, vec_ok);
+  packed_horizontal_level<2>(taps, sTmp, gout + 2 * plane, x0, y0, H, W, vec_ok);
+  packed_horizontal_level<3>(taps, sTmp, gout + 3 * plane, x0, y0, H, W, vec_ok);
+  packed_horizontal_level<4>(taps, sTmp, gout + 4 * plane, x0, y0, H, W, vec_ok);
+}
+
+static int launch_octave_packed(const void* base, int B, int H, int W, const double* taps_host, const int* tap_len_host,
+                                int first_is_identity, void* gauss, cudaStream_t st) {
+  static const int radius[5] = {3, 5, 6, 9, 13};
+  PackedTaps pt;
+  const double* tp = taps_host;
+  for (int l = 0; l < 5; ++l) {
+    const int R = radius[l];
+    const int E = (R & 1) ? R + 1 : R;
+    auto tap = [&](int d) -> float { d = d < 0 ? -d : d; return d <= R ? (float)tp[R + d] : 0.0f; };
+    for (int k = 0; k < 14; ++k) pt.v[l][k] = make_float2(tap(k <= R ? k : 99), tap(k <= R ? k : 99));
+    for (int i = 0; i < 15; ++i) {
+      const int e = 2 * i - E;
+      pt.ha[l][i] = (e <= E) ? make_float2(tap(e), tap(e)) : make_float2(0.f, 0.f);
+      pt.hb[l][i] = (e <= E) ? make_float2(tap(e - 1), tap(e + 1)) : make_float2(0.f, 0.f);
+    }
+    tp += tap_len_host[l];
+  }
+  dim3 grid(div_up(W, kPTX), div_up(H, kPTY), B);
+  if (first_is_identity) {
+    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmem));
+    gauss_octave_packed_kernel<true><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, pt, (float*)gauss);
+  } else {
+    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmem));
+    gauss_octave_packed_kernel<false><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, pt, (float*)gauss);
+  }
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
 static int launch_octave_fused(const void* base, int B, int H, int W, const double* taps_host, const int* tap_len_host,
                                int first_is_identity, void* gauss, cudaStream_t st) {
   FusedTaps ft;
@@ -633,9 +833,12 @@ extern "C" int fc_gauss_octave(const void* base, int dtype, int batch, int heigh
   if (filter != FC_FILTER_APP && filter != FC_FILTER_SCRIPT) return FC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (dtype == FC_F32 && fused_applicable(n_levels, taps_host, tap_len_host))
-    rc = launch_octave_fused(base, batch, height, width, taps_host, tap_len_host, first_is_identity, gauss, st);
-  else
+  if (dtype == FC_F32 && fused_applicable(n_levels, taps_host, tap_len_host)) {
+    static const bool scalar_variant = getenv("FC_PYRAMID_SCALAR") != nullptr;  // A/B switch for profiling
+    rc = scalar_variant
+             ? launch_octave_fused(base, batch, height, width, taps_host, tap_len_host, first_is_identity, gauss, st)
+             : launch_octave_packed(base, batch, height, width, taps_host, tap_len_host, first_is_identity, gauss, st);
+  } else
     rc = dtype == FC_F32
              ? launch_octave<float>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st)
              : launch_octave<double>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st);
