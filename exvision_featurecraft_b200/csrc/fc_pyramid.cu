@@ -543,15 +543,14 @@ __device__ __forceinline__ void packed_vertical_level(const PackedTaps& taps, fl
 }
 
 template <int L>
-__device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, const float* __restrict__ sTmp,
-                                                        float* __restrict__ out, int x0, int y0, int H, int W, bool vec_ok) {
+__device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, const float* __restrict__ sRow,
+                                                        float* __restrict__ dst, bool in_img, bool full, int n_valid) {
   constexpr int R = FusedRadius<L>::R;
   constexpr int E = (R & 1) ? R + 1 : R;    // input pairs at even offsets -E .. E of each output pair
   constexpr int E4 = (E + 3) & ~3;
   constexpr int N4 = (2 * E4 + 12) / 4;
-  const int y = threadIdx.x >> 3;
-  const int g = threadIdx.x & 7;
-  const float4* src = reinterpret_cast<const float4*>(sTmp + (L * kPTY + y) * kPP + 16 + 12 * g - E4);
+  // sRow = this thread's row of level 0 at smem column 16 + 12 g (its first output column)
+  const float4* src = reinterpret_cast<const float4*>(sRow + L * kPTY * kPP - E4);
   float2 p[2 * N4];
 #pragma unroll
   for (int q = 0; q < N4; ++q) {
@@ -573,104 +572,140 @@ __device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, 
     r[2 * q] = a.x + b.y;
     r[2 * q + 1] = a.y + b.x;
   }
-  const int yy = y0 + y, xx = x0 + 12 * g;
-  if (yy < H && xx < W) {
-    float* dst = out + (size_t)yy * W + xx;
-    if (vec_ok && xx + 11 < W) {
-      reinterpret_cast<float4*>(dst)[0] = make_float4(r[0], r[1], r[2], r[3]);
-      reinterpret_cast<float4*>(dst)[1] = make_float4(r[4], r[5], r[6], r[7]);
-      reinterpret_cast<float4*>(dst)[2] = make_float4(r[8], r[9], r[10], r[11]);
-    } else {
+  if (full) {
+    reinterpret_cast<float4*>(dst)[0] = make_float4(r[0], r[1], r[2], r[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(r[4], r[5], r[6], r[7]);
+    reinterpret_cast<float4*>(dst)[2] = make_float4(r[8], r[9], r[10], r[11]);
+  } else if (in_img) {
 #pragma unroll
-      for (int j = 0; j < 12; ++j)
-        if (xx + j < W) dst[j] = r[j];
-    }
+    for (int j = 0; j < 12; ++j)
+      if (j < n_valid) dst[j] = r[j];
   }
 }
 
+// Persistent: 2 CTAs per SM walk the tile list with stride gridDim.x.  The input tile is dead once the vertical pass
+// is done, so the NEXT tile's cp.async copies are issued right after the middle barrier and land while the horizontal
+// pass (55 % of the arithmetic, reads only the intermediate tiles) runs.
 template <bool IDENT0>
 __global__ void __launch_bounds__(256, 2)
-gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, const __grid_constant__ PackedTaps taps,
-                           float* __restrict__ gauss) {
+gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int tiles_x, int tiles_y, int n_tiles,
+                           const __grid_constant__ PackedTaps taps, float* __restrict__ gauss) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sIn = reinterpret_cast<float*>(smem_raw);
   float* sTmp = sIn + kPIH * kPP;
-  const int x0 = blockIdx.x * kPTX, y0 = blockIdx.y * kPTY;
-  const int b = blockIdx.z;
-  const float* img = base + (size_t)b * H * W;
-  float* gout = gauss + (size_t)b * 5 * H * W;
   const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gauss) & 15) == 0);
-  {
+  const bool in_vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  const size_t plane = (size_t)H * W;
+
+  auto issue_load = [&](int tile) {
+    const int tx = tile % tiles_x;
+    const int rest = tile / tiles_x;
+    const int ty = rest % tiles_y;
+    const int b = rest / tiles_y;
+    const int x0 = tx * kPTX, y0 = ty * kPTY;
+    const float* img = base + (size_t)b * plane;
     // smem column c <-> image column x0 - 16 + c; interior tiles copy 16 bytes per cp.async
-    const bool interior_x = (x0 - 16 >= 0) && (x0 - 16 + kPP <= W) && (W % 4 == 0) &&
-                            ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
-    if (interior_x) {
-      for (int t = threadIdx.x; t < kPIH * (kPP / 4); t += 256) {
-        const int r = t >> 5, c4 = t & 31;
-        const int y = reflect_symm(y0 - kFR + r, H);
-        const float* src = img + (size_t)y * W + (x0 - 16) + 4 * c4;
-        const uint32_t d = (uint32_t)__cvta_generic_to_shared(sIn + r * kPP + 4 * c4);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    if (in_vec_ok && x0 - 16 >= 0 && x0 - 16 + kPP <= W) {
+      // thread -> (row r0 + 8i, 16-byte column c4): one pointer increment per copy when no row is reflected
+      const int r0 = threadIdx.x >> 5, c4 = threadIdx.x & 31;
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(sIn + r0 * kPP + 4 * c4);
+      const float* col = img + (x0 - 16) + 4 * c4;
+      if (y0 - kFR >= 0 && y0 - kFR + kPIH <= H) {
+        const float* src = col + (size_t)(y0 - kFR + r0) * W;
+#pragma unroll
+        for (int i = 0; i < (kPIH + 7) / 8; ++i)
+          if (8 * i + 7 < kPIH || r0 + 8 * i < kPIH)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 8 * kPP * 4), "l"(src + (size_t)i * 8 * W) : "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < (kPIH + 7) / 8; ++i)
+          if (r0 + 8 * i < kPIH) {
+            const float* src = col + (size_t)reflect_symm(y0 - kFR + r0 + 8 * i, H) * W;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 8 * kPP * 4), "l"(src) : "memory");
+          }
       }
     } else {
-      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      for (int r = warp; r < kPIH; r += 8) {
-        const int y = reflect_symm(y0 - kFR + r, H);
-        const float* row = img + (size_t)y * W;
-        float* dst = sIn + r * kPP;
-        for (int c = lane; c < kPP; c += 32) cp_async_elem<float>(dst + c, row + reflect_symm(x0 - 16 + c, W));
+      // tiles that touch the left / right image border: 4-byte copies, the column reflection is computed once
+      const int r0 = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      int xr[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xr[k] = reflect_symm(x0 - 16 + lane + 32 * k, W);
+      for (int r = r0; r < kPIH; r += 8) {
+        const float* row = img + (size_t)reflect_symm(y0 - kFR + r, H) * W;
+        float* dst = sIn + r * kPP + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cp_async_elem<float>(dst + 32 * k, row + xr[k]);
       }
     }
+  };
+
+  int tile = blockIdx.x;
+  if (tile < n_tiles) issue_load(tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int rest = tile / tiles_x;
+    const int ty = rest % tiles_y;
+    const int b = rest / tiles_y;
+    const int x0 = tx * kPTX, y0 = ty * kPTY;
+    float* gout = gauss + (size_t)b * 5 * plane;
     asm volatile("cp.async.wait_all;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x < 4 * kPPairs) {
-    const int rg = threadIdx.x / kPPairs;
-    const int pc = threadIdx.x - rg * kPPairs + 1;  // pair index: smem columns 2pc, 2pc+1
-    const float2* src = reinterpret_cast<const float2*>(sIn + (rg * 8) * kPP) + pc;
-    float2 v[8 + 2 * kFR];
+    __syncthreads();  // input tile complete; every thread has left the previous tile's horizontal pass
+    if (threadIdx.x < 4 * kPPairs) {
+      const int rg = threadIdx.x / kPPairs;
+      const int pc = threadIdx.x - rg * kPPairs + 1;  // pair index: smem columns 2pc, 2pc+1
+      const float2* src = reinterpret_cast<const float2*>(sIn + (rg * 8) * kPP) + pc;
+      float2 v[8 + 2 * kFR];
 #pragma unroll
-    for (int k = 0; k < 8 + 2 * kFR; ++k) v[k] = src[k * (kPP / 2)];
-    float2* dst = reinterpret_cast<float2*>(sTmp + (rg * 8) * kPP) + pc;
+      for (int k = 0; k < 8 + 2 * kFR; ++k) v[k] = src[k * (kPP / 2)];
+      float2* dst = reinterpret_cast<float2*>(sTmp + (rg * 8) * kPP) + pc;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float2 s[kFR + 1];
+      for (int j = 0; j < 8; ++j) {
+        float2 s[kFR + 1];
 #pragma unroll
-      for (int k = 1; k <= kFR; ++k) s[k] = __fadd2_rn(v[j + kFR - k], v[j + kFR + k]);
-      const float2 centre = v[j + kFR];
-      float2* d = dst + j * (kPP / 2);
-      if (!IDENT0) packed_vertical_level<0>(taps, centre, s, d);
-      packed_vertical_level<1>(taps, centre, s, d + 1 * kPTY * (kPP / 2));
-      packed_vertical_level<2>(taps, centre, s, d + 2 * kPTY * (kPP / 2));
-      packed_vertical_level<3>(taps, centre, s, d + 3 * kPTY * (kPP / 2));
-      packed_vertical_level<4>(taps, centre, s, d + 4 * kPTY * (kPP / 2));
-    }
-  }
-  if (IDENT0) {
-    // level 0 of octaves > 0 is the unblurred base (:136-137); reads sIn only, so it can run before the barrier
-    const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
-    const int yy = y0 + y, xx = x0 + 12 * g;
-    const float4* s4 = reinterpret_cast<const float4*>(sIn + (y + kFR) * kPP + 16 + 12 * g);
-    if (yy < H && xx < W) {
-      float* dst = gout + (size_t)yy * W + xx;
-      if (vec_ok && xx + 11 < W) {
-        reinterpret_cast<float4*>(dst)[0] = s4[0];
-        reinterpret_cast<float4*>(dst)[1] = s4[1];
-        reinterpret_cast<float4*>(dst)[2] = s4[2];
-      } else {
-        const float* s1 = reinterpret_cast<const float*>(s4);
-        for (int j = 0; j < 12; ++j)
-          if (xx + j < W) dst[j] = s1[j];
+        for (int k = 1; k <= kFR; ++k) s[k] = __fadd2_rn(v[j + kFR - k], v[j + kFR + k]);
+        const float2 centre = v[j + kFR];
+        float2* d = dst + j * (kPP / 2);
+        if (!IDENT0) packed_vertical_level<0>(taps, centre, s, d);
+        packed_vertical_level<1>(taps, centre, s, d + 1 * kPTY * (kPP / 2));
+        packed_vertical_level<2>(taps, centre, s, d + 2 * kPTY * (kPP / 2));
+        packed_vertical_level<3>(taps, centre, s, d + 3 * kPTY * (kPP / 2));
+        packed_vertical_level<4>(taps, centre, s, d + 4 * kPTY * (kPP / 2));
       }
     }
+    if (IDENT0) {
+      // level 0 of octaves > 0 is the unblurred base (:136-137); reads the input tile, so it goes before the barrier
+      const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
+      const int yy = y0 + y, xx = x0 + 12 * g;
+      const float4* s4 = reinterpret_cast<const float4*>(sIn + (y + kFR) * kPP + 16 + 12 * g);
+      if (yy < H && xx < W) {
+        float* dst = gout + (size_t)yy * W + xx;
+        if (vec_ok && xx + 11 < W) {
+          reinterpret_cast<float4*>(dst)[0] = s4[0];
+          reinterpret_cast<float4*>(dst)[1] = s4[1];
+          reinterpret_cast<float4*>(dst)[2] = s4[2];
+        } else {
+          const float* s1 = reinterpret_cast<const float*>(s4);
+          for (int j = 0; j < 12; ++j)
+            if (xx + j < W) dst[j] = s1[j];
+        }
+      }
+    }
+    __syncthreads();  // intermediates complete, input tile free
+    if (tile + (int)gridDim.x < n_tiles) issue_load(tile + gridDim.x);
+    {
+      const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
+      const int yy = y0 + y, xx = x0 + 12 * g;
+      const bool in_img = yy < H && xx < W;
+      const bool full = in_img && vec_ok && xx + 11 < W;
+      const float* sRow = sTmp + y * kPP + 16 + 12 * g;
+      float* dst = gout + (size_t)yy * W + xx;
+      if (!IDENT0) packed_horizontal_level<0>(taps, sRow, dst, in_img, full, W - xx);
+      packed_horizontal_level<1>(taps, sRow, dst + plane, in_img, full, W - xx);
+      packed_horizontal_level<2>(taps, sRow, dst + 2 * plane, in_img, full, W - xx);
+      packed_horizontal_level<3>(taps, sRow, dst + 3 * plane, in_img, full, W - xx);
+      packed_horizontal_level<4>(taps, sRow, dst + 4 * plane, in_img, full, W - xx);
+    }
   }
-  __syncthreads();
-  const size_t plane = (size_t)H * W;
-  if (!IDENT0) packed_horizontal_level<0>(taps, sTmp, gout, x0, y0, H, W, vec_ok);
-  packed_horizontal_level<1>(taps, sTmp, gout + plane, x0, y0, H, W, vec_ok);
-  packed_horizontal_level<2>(taps, sTmp, gout + 2 * plane, x0, y0, H, W, vec_ok);
-  packed_horizontal_level<3>(taps, sTmp, gout + 3 * plane, x0, y0, H, W, vec_ok);
-  packed_horizontal_level<4>(taps, sTmp, gout + 4 * plane, x0, y0, H, W, vec_ok);
 }
 
 static int launch_octave_packed(const void* base, int B, int H, int W, const double* taps_host, const int* tap_len_host,
@@ -690,13 +725,23 @@ static int launch_octave_packed(const void* base, int B, int H, int W, const dou
     }
     tp += tap_len_host[l];
   }
-  dim3 grid(div_up(W, kPTX), div_up(H, kPTY), B);
+  const int tiles_x = div_up(W, kPTX), tiles_y = div_up(H, kPTY);
+  const long long n_tiles_ll = (long long)tiles_x * tiles_y * B;
+  if (n_tiles_ll > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;
+  const int n_tiles = (int)n_tiles_ll;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    FC_CUDA_TRY(cudaGetDevice(&dev));
+    FC_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
   if (first_is_identity) {
     FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmem));
-    gauss_octave_packed_kernel<true><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, pt, (float*)gauss);
+    gauss_octave_packed_kernel<true><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, pt, (float*)gauss);
   } else {
     FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmem));
-    gauss_octave_packed_kernel<false><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, pt, (float*)gauss);
+    gauss_octave_packed_kernel<false><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, pt, (float*)gauss);
   }
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
