@@ -9,6 +9,8 @@
 // Reference arithmetic: APP/FeatureCraft_Backend.py:336-355 (Harris), :402-437 (lambda-minus),
 // implementation_without_ui/Corner Detection/harris.ipynb:150-190 (notebook Harris).
 // HBM traffic per pixel: 1 B gray in + 8 B float64 response out (+ 1 bit mask).
+#include <stdlib.h>
+
 #include "fc_common.cuh"
 
 namespace fc {
@@ -193,6 +195,215 @@ harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_pe
       mid = dn;
       dn = nxt;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Harris fast path, packed-fp32 variant (the one fc_harris_response launches)
+// ------------------------------------------------------------------------------------------------
+// Every quantity before the response is a multiple of 1/4 below 2^22, i.e. exactly representable in float32:
+// gradients (multiples of 1/2, |g| <= 255), products (<= 65 025), 5-tap row sums (<= 325 125), 5x5 sums
+// (<= 1 625 625 -> 23 significant bits with the two fraction bits).  float32 adds / multiplies of such values are
+// exact, so the sums equal the reference's float64 sums bit for bit, and sm_100's packed FADD2 / FMUL2 do two of
+// them per issue slot.  Bytes are unpacked straight into "2^22 + byte/2" floats by one PRMT (0x4A800000 | byte:
+// the mantissa LSB of that binade is 1/2); the bias cancels in every difference, so the halved central difference
+// of np.gradient costs one subtraction.  Only the response itself (det, trace^2 up to 2^44) needs float64: three
+// exact float->double conversions and six float64 operations per pixel, two of which round -- the same two as in
+// the reference (k * trace^2 and the final subtraction, APP/FeatureCraft_Backend.py:351-355).
+// 36 instructions per pixel instead of the 81 of the integer kernel above (kept for reference / A-B runs).
+struct RowF {
+  float lo;      // column c0 - 3            (k = 1 in Row3 numbering)
+  float2 e[4];   // columns c0 - 2 .. c0 + 5 (k = 2 .. 9), register-pair aligned
+  float hi;      // column c0 + 6            (k = 10)
+  template <int K> __device__ __forceinline__ float get() const {
+    static_assert(K >= 1 && K <= 10, "column out of range");
+    if constexpr (K == 1) return lo;
+    else if constexpr (K == 10) return hi;
+    else if constexpr ((K & 1) == 0) return e[(K - 2) / 2].x;
+    else return e[(K - 2) / 2].y;
+  }
+};
+
+__device__ __forceinline__ float unpack_half_biased(uint32_t w, int byte) {
+  return __uint_as_float(__byte_perm(w, 0x4A800000u, 0x7640u + (unsigned)byte));
+}
+
+__device__ __forceinline__ RowF unpack_row(const Row3& r) {
+  RowF f;
+  f.lo = unpack_half_biased(r.w[0], 1);
+  f.e[0] = make_float2(unpack_half_biased(r.w[0], 2), unpack_half_biased(r.w[0], 3));
+  f.e[1] = make_float2(unpack_half_biased(r.w[1], 0), unpack_half_biased(r.w[1], 1));
+  f.e[2] = make_float2(unpack_half_biased(r.w[1], 2), unpack_half_biased(r.w[1], 3));
+  f.e[3] = make_float2(unpack_half_biased(r.w[2], 0), unpack_half_biased(r.w[2], 1));
+  f.hi = unpack_half_biased(r.w[2], 2);
+  return f;
+}
+
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+
+// 5-tap sums h[j] = p[j] + .. + p[j+4], j = 0..3, of eight consecutive values given as four pairs (9 additions)
+__device__ __forceinline__ float4 five_tap_sums(const float2 (&p)[4]) {
+  const float t1 = p[0].y + p[1].x, t2 = p[1].y + p[2].x, t3 = p[2].y + p[3].x;
+  const float c = t1 + t2, c2 = t2 + t3;
+  return make_float4(c + p[0].x, c + p[2].y, c2 + p[1].x, c2 + p[3].y);
+}
+
+template <int I> __device__ __forceinline__ void border_grad(const RowF& up, const RowF& mid, const RowF& dn, float sy,
+                                                             int c0, int W, float (&gx)[8], float (&gy)[8]) {
+  constexpr int K = I + 2;
+  const int c = c0 - 2 + I;
+  const bool inside = (c >= 0) && (c < W);
+  const float vx = sy * (dn.get<K>() - up.get<K>());
+  float vy;
+  if (c == 0) vy = 2.f * (mid.get<K + 1>() - mid.get<K>());
+  else if (c == W - 1) vy = 2.f * (mid.get<K>() - mid.get<K - 1>());
+  else vy = mid.get<K + 1>() - mid.get<K - 1>();
+  gx[I] = inside ? vx : 0.f;
+  gy[I] = inside ? vy : 0.f;
+}
+
+// h[0] = xx, h[1] = xy, h[2] = yy row sums for output columns c0 .. c0+3
+template <bool INTERIOR>
+__device__ __forceinline__ void harris_row_sums_f32(const RowF& up, const RowF& mid, const RowF& dn, int row, int H, int W,
+                                                    int c0, float4 (&h)[3]) {
+  float2 gx[4], gy[4];  // product columns c0-2 .. c0+5
+  if (INTERIOR) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gx[i] = sub2(dn.e[i], up.e[i]);
+    gy[0] = make_float2(mid.e[0].y - mid.lo, mid.e[1].x - mid.e[0].x);
+    gy[1] = make_float2(mid.e[1].y - mid.e[0].y, mid.e[2].x - mid.e[1].x);
+    gy[2] = make_float2(mid.e[2].y - mid.e[1].y, mid.e[3].x - mid.e[2].x);
+    gy[3] = make_float2(mid.e[3].y - mid.e[2].y, mid.hi - mid.e[3].x);
+  } else {
+    // rows were clamped when loaded, so dn - up is half the one-sided difference on the first / last row
+    const float sy = (row == 0 || row == H - 1) ? 2.f : 1.f;
+    float ax[8], ay[8];
+    border_grad<0>(up, mid, dn, sy, c0, W, ax, ay); border_grad<1>(up, mid, dn, sy, c0, W, ax, ay);
+    border_grad<2>(up, mid, dn, sy, c0, W, ax, ay); border_grad<3>(up, mid, dn, sy, c0, W, ax, ay);
+    border_grad<4>(up, mid, dn, sy, c0, W, ax, ay); border_grad<5>(up, mid, dn, sy, c0, W, ax, ay);
+    border_grad<6>(up, mid, dn, sy, c0, W, ax, ay); border_grad<7>(up, mid, dn, sy, c0, W, ax, ay);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      gx[i] = make_float2(ax[2 * i], ax[2 * i + 1]);
+      gy[i] = make_float2(ay[2 * i], ay[2 * i + 1]);
+    }
+  }
+  float2 xx[4], xy[4], yy[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xx[i] = __fmul2_rn(gx[i], gx[i]);
+    xy[i] = __fmul2_rn(gx[i], gy[i]);
+    yy[i] = __fmul2_rn(gy[i], gy[i]);
+  }
+  h[0] = five_tap_sums(xx);
+  h[1] = five_tap_sums(xy);
+  h[2] = five_tap_sums(yy);
+}
+
+// the reference's R from exact float32 window sums: det and trace^2 are exact in float64, two roundings remain
+__device__ __forceinline__ double harris_from_f32_sums(float sxx, float sxy, float syy, double k) {
+  const double a = (double)sxx, b = (double)sxy, c = (double)syy;
+  const double det = __fma_rn(-b, b, __dmul_rn(a, c));
+  const double tr = __dadd_rn(a, c);
+  return __dsub_rn(det, __dmul_rn(k, __dmul_rn(tr, tr)));
+}
+
+struct HarrisF32State {
+  float4 S[3];  // running 5x5 sums (xx, xy, yy) of the four output columns
+  int slot;     // ring slot of the row that leaves the window next
+};
+
+template <bool HAS_MASK>
+__device__ __forceinline__ void harris_f32_step(HarrisF32State& st, RowF& up, const RowF& mid, const RowF& dn,
+                                                const uint8_t* __restrict__ img, int hr, int H, int W, int c0,
+                                                bool cols_interior, bool active, int y0, float4* __restrict__ ring,
+                                                double k, double thr, double* __restrict__ o, uint32_t* __restrict__ m,
+                                                int mask_pitch, int lane) {
+  const Row3 nxt = load_row3(img, hr + 2, H, W, c0);  // in flight during the arithmetic below
+  float4 h[3];
+  if (hr < 0 || hr >= H) {
+    h[0] = h[1] = h[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (cols_interior && hr >= 1 && hr <= H - 2) {
+    harris_row_sums_f32<true>(up, mid, dn, hr, H, W, c0, h);
+  } else {
+    harris_row_sums_f32<false>(up, mid, dn, hr, H, W, c0, h);
+  }
+  float4* slot = ring + st.slot * (3 * kStripThreads);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float4 old = slot[q * kStripThreads];
+    slot[q * kStripThreads] = h[q];
+    const float2 d0 = sub2(make_float2(h[q].x, h[q].y), make_float2(old.x, old.y));
+    const float2 d1 = sub2(make_float2(h[q].z, h[q].w), make_float2(old.z, old.w));
+    const float2 s0 = __fadd2_rn(make_float2(st.S[q].x, st.S[q].y), d0);
+    const float2 s1 = __fadd2_rn(make_float2(st.S[q].z, st.S[q].w), d1);
+    st.S[q] = make_float4(s0.x, s0.y, s1.x, s1.y);
+  }
+  st.slot = (st.slot == 4) ? 0 : st.slot + 1;
+  const int r = hr - 2;  // rows r-2 .. r+2 are now summed
+  if (r >= y0) {
+    double res[4];
+    res[0] = harris_from_f32_sums(st.S[0].x, st.S[1].x, st.S[2].x, k);
+    res[1] = harris_from_f32_sums(st.S[0].y, st.S[1].y, st.S[2].y, k);
+    res[2] = harris_from_f32_sums(st.S[0].z, st.S[1].z, st.S[2].z, k);
+    res[3] = harris_from_f32_sums(st.S[0].w, st.S[1].w, st.S[2].w, k);
+    if (active) {
+      double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
+      __stcs(dst, make_double2(res[0], res[1]));
+      __stcs(dst + 1, make_double2(res[2], res[3]));
+    }
+    if (HAS_MASK) {
+      uint32_t nib = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nib |= (res[j] > thr) ? (1u << j) : 0u;
+      uint32_t v = active ? (nib << (4 * (lane & 7))) : 0u;
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      v |= __shfl_xor_sync(0xffffffffu, v, 2);
+      v |= __shfl_xor_sync(0xffffffffu, v, 4);
+      if ((lane & 7) == 0 && active) m[(size_t)r * mask_pitch + (c0 >> 5)] = v;
+    }
+  }
+  up = unpack_row(nxt);  // the buffer of row hr-1 becomes row hr+2
+}
+
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(kStripThreads, 5)
+harris5_f32_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double k, double thr,
+                   double* __restrict__ out, uint32_t* __restrict__ mask, int mask_pitch) {
+  // ring of the last 5 rows of horizontal sums, private to each thread: [slot][quantity][thread] float4 (conflict free)
+  __shared__ float4 sRing[5 * 3 * kStripThreads];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * kStripWarps + warp;
+  const int strip_c0 = strip * kStripCols;
+  if (strip_c0 >= W) return;  // warp-uniform, and the kernel has no block-wide barrier
+  const int c0 = strip_c0 + lane * 4;
+  const bool active = c0 < W;
+  const size_t img_off = (size_t)blockIdx.z * H * W;
+  const uint8_t* img = gray + img_off;
+  double* o = out + img_off;
+  uint32_t* m = HAS_MASK ? mask + (size_t)blockIdx.z * H * mask_pitch : nullptr;
+  const int y0 = blockIdx.y * rows_per_band;
+  const int y1 = min(y0 + rows_per_band, H);
+  const bool cols_interior = (strip_c0 - 2 >= 1) && (strip_c0 + kStripCols + 1 <= W - 2);
+  float4* ring = sRing + threadIdx.x;
+  HarrisF32State st;
+  st.slot = 0;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    st.S[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < 5; ++s) ring[(s * 3 + q) * kStripThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  RowF A = unpack_row(load_row3(img, y0 - 3, H, W, c0));
+  RowF B = unpack_row(load_row3(img, y0 - 2, H, W, c0));
+  RowF C = unpack_row(load_row3(img, y0 - 1, H, W, c0));
+  // three rows per trip: the roles up / mid / dn rotate through A, B, C without moving a register
+  for (int hr = y0 - 2; hr <= y1 + 1; hr += 3) {
+    harris_f32_step<HAS_MASK>(st, A, B, C, img, hr, H, W, c0, cols_interior, active, y0, ring, k, thr, o, m, mask_pitch, lane);
+    if (hr + 1 > y1 + 1) break;
+    harris_f32_step<HAS_MASK>(st, B, C, A, img, hr + 1, H, W, c0, cols_interior, active, y0, ring, k, thr, o, m, mask_pitch, lane);
+    if (hr + 2 > y1 + 1) break;
+    harris_f32_step<HAS_MASK>(st, C, A, B, img, hr + 2, H, W, c0, cols_interior, active, y0, ring, k, thr, o, m, mask_pitch, lane);
   }
 }
 
@@ -660,8 +871,13 @@ extern "C" int fc_harris_response(const uint8_t* gray, int batch, int height, in
     int rows = 64;
     while (rows > 8 && (int64_t)strips * div_up(height, rows) * batch < 148 * 16) rows >>= 1;
     dim3 grid(div_up(strips, kStripWarps), div_up(height, rows), batch);
-    harris5_strip_kernel<<<grid, kStripWarps * 32, 0, st>>>(gray, height, width, rows, k, threshold, response, mask,
-                                                           pitch);
+    static const bool int_variant = getenv("FC_HARRIS_INT") != nullptr;  // A/B switch: the integer kernel
+    if (int_variant)
+      harris5_strip_kernel<<<grid, kStripWarps * 32, 0, st>>>(gray, height, width, rows, k, threshold, response, mask, pitch);
+    else if (mask)
+      harris5_f32_kernel<true><<<grid, kStripWarps * 32, 0, st>>>(gray, height, width, rows, k, threshold, response, mask, pitch);
+    else
+      harris5_f32_kernel<false><<<grid, kStripWarps * 32, 0, st>>>(gray, height, width, rows, k, threshold, response, mask, pitch);
     note_launch();
     FC_RETURN_IF_LAUNCH_FAILED();
     return FC_OK;
