@@ -219,11 +219,11 @@ class HarrisWorkload:
         ms = [a.elapsed_time(b) for a, b in self.ev[:n]]
         t = float(np.mean(ms)) if ms else None
         alg = 9.0 * self.batch * self.H * self.W  # 1 B in + 8 B out per pixel
-        return "harris5_strip_kernel", alg, t, "hbm"
+        return "harris5_f32_kernel", alg, t, "hbm"
 
     def traffic(self, tr):
         """dram bytes per launch of the dominant kernel, from the committed ncu capture scaled to this launch"""
-        return tr["harris5_strip_kernel"]["bytes_per_pixel"] * self.batch * self.H * self.W
+        return tr["harris5_f32_kernel"]["bytes_per_pixel"] * self.batch * self.H * self.W
 
     cpu_task = staticmethod(_cpu_harris_task)
 

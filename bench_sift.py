@@ -92,10 +92,10 @@ class SiftWorkload:
         alg = 24.0 * self.batch * (2 * self.H) * (2 * self.W)  # 4 B base read + 5 x 4 B levels written per octave pixel
         if self.mode == "f64":
             alg *= 2
-        return "gauss_octave_fused_kernel (octave 0)" if self.mode == "f32" else "gauss_octave_kernel (octave 0)", alg, ms, "hbm"
+        return "gauss_octave_packed_kernel (octave 0)" if self.mode == "f32" else "gauss_octave_kernel (octave 0)", alg, ms, "hbm"
 
     def traffic(self, tr):
-        return tr["gauss_octave_fused_kernel"]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W) * (2 if self.mode == "f64" else 1)
+        return tr["gauss_octave_packed_kernel"]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W) * (2 if self.mode == "f64" else 1)
 
     def extra(self):
         n = max(self.recorded_steps, 1)

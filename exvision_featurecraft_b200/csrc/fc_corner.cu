@@ -210,7 +210,7 @@ harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_pe
 // of np.gradient costs one subtraction.  Only the response itself (det, trace^2 up to 2^44) needs float64: three
 // exact float->double conversions and six float64 operations per pixel, two of which round -- the same two as in
 // the reference (k * trace^2 and the final subtraction, APP/FeatureCraft_Backend.py:351-355).
-// 36 instructions per pixel instead of the 81 of the integer kernel above (kept for reference / A-B runs).
+// 56 instructions per pixel instead of the 81 of the integer kernel above (kept for A/B runs: FC_HARRIS_INT=1).
 struct RowF {
   float lo;      // column c0 - 3            (k = 1 in Row3 numbering)
   float2 e[4];   // columns c0 - 2 .. c0 + 5 (k = 2 .. 9), register-pair aligned
@@ -309,26 +309,55 @@ __device__ __forceinline__ double harris_from_f32_sums(float sxx, float sxy, flo
 }
 
 struct HarrisF32State {
-  float4 S[3];  // running 5x5 sums (xx, xy, yy) of the four output columns
-  int slot;     // ring slot of the row that leaves the window next
+  float4 S[3];           // running 5x5 sums (xx, xy, yy) of the four output columns
+  int slot;              // ring offset of the row that leaves the window next
+  const uint32_t* in_p;  // FAST: this lane's word (column c0) of the next row to stage
+  uint32_t* stage;       // FAST: this warp's staging rows in shared memory, [kHarrisStageRows][36] words
+  int stage_slot;        // FAST: staging row that holds image row hr+2
+  double* out_p;         // FAST: response address of (row hr-2, column c0)
+  uint32_t* mask_p;      // FAST: mask word of (row hr-2, column c0)
+  Row3 nxt;              // bytes of row hr+2, loaded at the end of the previous step
 };
 
-template <bool HAS_MASK>
+static constexpr int kHarrisStageRows = 4;  // image rows in flight per warp (three ahead of the one being unpacked)
+
+// FAST path input staging: one 4-byte cp.async per lane per image row (lanes 0 and 1 also fetch the two halo
+// words), landing in a small per-warp ring in shared memory.  Completion is tracked by cp.async groups, not by
+// register scoreboards, so three rows (about three steps of run time) are in flight without holding a register,
+// and every byte is fetched from L1/L2 once instead of three times.
+__device__ __forceinline__ void harris_stage_row(const uint32_t* __restrict__ own_word, uint32_t* stage_row, int lane) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(stage_row + 1 + lane);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(own_word) : "memory");
+  if (lane < 2) {
+    // lane 0: word left of the strip -> stage word 0; lane 1: word right of the strip -> stage word 33
+    const uint32_t dh = (uint32_t)__cvta_generic_to_shared(stage_row + lane * 33);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dh), "l"(own_word - 1 + lane * 32) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// One image row hr of the band: row sums of hr -> ring -> window sums -> response of row hr-2; then the bytes of
+// row hr+2 replace the buffer of row hr-1 (FAST: from the staging ring, and row hr+5 is requested; otherwise from
+// registers loaded at the end of the previous step).
+// FAST: the whole strip and rows hr-1 .. hr+3 are inside the image (no clamping, no border gradient, every lane
+// active, pointer increments instead of index arithmetic).
+template <bool HAS_MASK, bool FAST>
 __device__ __forceinline__ void harris_f32_step(HarrisF32State& st, RowF& up, const RowF& mid, const RowF& dn,
                                                 const uint8_t* __restrict__ img, int hr, int H, int W, int c0,
                                                 bool cols_interior, bool active, int y0, float4* __restrict__ ring,
                                                 double k, double thr, double* __restrict__ o, uint32_t* __restrict__ m,
                                                 int mask_pitch, int lane) {
-  const Row3 nxt = load_row3(img, hr + 2, H, W, c0);  // in flight during the arithmetic below
   float4 h[3];
-  if (hr < 0 || hr >= H) {
+  if (FAST) {
+    harris_row_sums_f32<true>(up, mid, dn, hr, H, W, c0, h);
+  } else if (hr < 0 || hr >= H) {
     h[0] = h[1] = h[2] = make_float4(0.f, 0.f, 0.f, 0.f);
   } else if (cols_interior && hr >= 1 && hr <= H - 2) {
     harris_row_sums_f32<true>(up, mid, dn, hr, H, W, c0, h);
   } else {
     harris_row_sums_f32<false>(up, mid, dn, hr, H, W, c0, h);
   }
-  float4* slot = ring + st.slot * (3 * kStripThreads);
+  float4* slot = ring + st.slot;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     const float4 old = slot[q * kStripThreads];
@@ -339,7 +368,7 @@ __device__ __forceinline__ void harris_f32_step(HarrisF32State& st, RowF& up, co
     const float2 s1 = __fadd2_rn(make_float2(st.S[q].z, st.S[q].w), d1);
     st.S[q] = make_float4(s0.x, s0.y, s1.x, s1.y);
   }
-  st.slot = (st.slot == 4) ? 0 : st.slot + 1;
+  st.slot = (st.slot == 4 * 3 * kStripThreads) ? 0 : st.slot + 3 * kStripThreads;
   const int r = hr - 2;  // rows r-2 .. r+2 are now summed
   if (r >= y0) {
     double res[4];
@@ -347,8 +376,8 @@ __device__ __forceinline__ void harris_f32_step(HarrisF32State& st, RowF& up, co
     res[1] = harris_from_f32_sums(st.S[0].y, st.S[1].y, st.S[2].y, k);
     res[2] = harris_from_f32_sums(st.S[0].z, st.S[1].z, st.S[2].z, k);
     res[3] = harris_from_f32_sums(st.S[0].w, st.S[1].w, st.S[2].w, k);
-    if (active) {
-      double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
+    if (FAST || active) {
+      double2* dst = reinterpret_cast<double2*>(FAST ? st.out_p : o + (size_t)r * W + c0);
       __stcs(dst, make_double2(res[0], res[1]));
       __stcs(dst + 1, make_double2(res[2], res[3]));
     }
@@ -356,22 +385,44 @@ __device__ __forceinline__ void harris_f32_step(HarrisF32State& st, RowF& up, co
       uint32_t nib = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) nib |= (res[j] > thr) ? (1u << j) : 0u;
-      uint32_t v = active ? (nib << (4 * (lane & 7))) : 0u;
-      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      uint32_t v = (FAST || active) ? (nib << (4 * (lane & 7))) : 0u;
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);  // (a REDUX with per-group member masks was measured 20 % slower)
       v |= __shfl_xor_sync(0xffffffffu, v, 2);
       v |= __shfl_xor_sync(0xffffffffu, v, 4);
-      if ((lane & 7) == 0 && active) m[(size_t)r * mask_pitch + (c0 >> 5)] = v;
+      if ((lane & 7) == 0 && (FAST || active)) *(FAST ? st.mask_p : m + (size_t)r * mask_pitch + (c0 >> 5)) = v;
+    }
+    if (FAST) {
+      st.out_p += W;
+      if (HAS_MASK) st.mask_p += mask_pitch;
     }
   }
-  up = unpack_row(nxt);  // the buffer of row hr-1 becomes row hr+2
+  if (FAST) {
+    // the copy of row hr+2 was committed three groups ago; the warp barrier makes every lane's words visible and
+    // also orders this step's reads after the previous step's, so the slot refilled below is no longer in use
+    asm volatile("cp.async.wait_group %0;" ::"n"(kHarrisStageRows - 2) : "memory");
+    __syncwarp();
+    const uint32_t* srow = st.stage + st.stage_slot * 36 + lane;
+    Row3 cur;
+    cur.w[0] = srow[0]; cur.w[1] = srow[1]; cur.w[2] = srow[2];
+    up = unpack_row(cur);  // the buffer of row hr-1 becomes row hr+2
+    const int refill = (st.stage_slot + kHarrisStageRows - 1) & (kHarrisStageRows - 1);  // slot of row hr+1
+    harris_stage_row(st.in_p, st.stage + refill * 36, lane);                              // <- row hr+5
+    st.in_p += W >> 2;
+    st.stage_slot = (st.stage_slot + 1) & (kHarrisStageRows - 1);
+  } else {
+    up = unpack_row(st.nxt);
+    st.nxt = load_row3(img, hr + 3, H, W, c0);
+  }
 }
 
+// 4 CTAs per SM (<= 128 registers): at 5 the step spills, and with the staged input 16 warps per SM are enough
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(kStripThreads, 5)
+__global__ void __launch_bounds__(kStripThreads, 4)
 harris5_f32_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double k, double thr,
                    double* __restrict__ out, uint32_t* __restrict__ mask, int mask_pitch) {
   // ring of the last 5 rows of horizontal sums, private to each thread: [slot][quantity][thread] float4 (conflict free)
   __shared__ float4 sRing[5 * 3 * kStripThreads];
+  __shared__ uint32_t sStage[kStripWarps * kHarrisStageRows * 36];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x * kStripWarps + warp;
   const int strip_c0 = strip * kStripCols;
@@ -397,14 +448,39 @@ harris5_f32_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_
   RowF A = unpack_row(load_row3(img, y0 - 3, H, W, c0));
   RowF B = unpack_row(load_row3(img, y0 - 2, H, W, c0));
   RowF C = unpack_row(load_row3(img, y0 - 1, H, W, c0));
-  // three rows per trip: the roles up / mid / dn rotate through A, B, C without moving a register
-  for (int hr = y0 - 2; hr <= y1 + 1; hr += 3) {
-    harris_f32_step<HAS_MASK>(st, A, B, C, img, hr, H, W, c0, cols_interior, active, y0, ring, k, thr, o, m, mask_pitch, lane);
-    if (hr + 1 > y1 + 1) break;
-    harris_f32_step<HAS_MASK>(st, B, C, A, img, hr + 1, H, W, c0, cols_interior, active, y0, ring, k, thr, o, m, mask_pitch, lane);
-    if (hr + 2 > y1 + 1) break;
-    harris_f32_step<HAS_MASK>(st, C, A, B, img, hr + 2, H, W, c0, cols_interior, active, y0, ring, k, thr, o, m, mask_pitch, lane);
+  const int last = y1 + 1;
+  int hr = y0 - 2;
+#define FC_STEP(FAST, U, M, D) \
+  harris_f32_step<HAS_MASK, FAST>(st, U, M, D, img, hr, H, W, c0, cols_interior, active, y0, ring, k, thr, o, m, mask_pitch, lane)
+  if (cols_interior && y0 - 3 >= 0 && y1 + 6 <= H - 1) {
+    // band and strip entirely inside the image.  The roles up / mid / dn rotate through A, B, C without moving a
+    // register: three rows per trip.  Rows y0 .. y0+2 are staged before the first step (hr = y0-2 consumes row y0).
+    st.stage = sStage + warp * (kHarrisStageRows * 36);
+    st.stage_slot = 0;
+    st.in_p = reinterpret_cast<const uint32_t*>(img + (size_t)y0 * W + c0);
+#pragma unroll
+    for (int i = 0; i < kHarrisStageRows - 1; ++i) {
+      harris_stage_row(st.in_p, st.stage + i * 36, lane);
+      st.in_p += W >> 2;
+    }
+    st.out_p = o + (size_t)y0 * W + c0;
+    st.mask_p = HAS_MASK ? m + (size_t)y0 * mask_pitch + (c0 >> 5) : nullptr;
+    for (;;) {
+      FC_STEP(true, A, B, C); if (++hr > last) break;
+      FC_STEP(true, B, C, A); if (++hr > last) break;
+      FC_STEP(true, C, A, B); if (++hr > last) break;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // the last three staged rows are never consumed
+  } else {
+    // bands / strips that touch the image border: same step with every check, rolled (registers are moved)
+    st.nxt = load_row3(img, y0, H, W, c0);
+#pragma unroll 1
+    for (; hr <= last; ++hr) {
+      FC_STEP(false, A, B, C);
+      const RowF t = A; A = B; B = C; C = t;
+    }
   }
+#undef FC_STEP
 }
 
 // ------------------------------------------------------------------------------------------------
