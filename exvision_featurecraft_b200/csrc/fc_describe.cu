@@ -78,7 +78,7 @@ static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the fi
 // histograms) is the same for every LPK, so small windows -- most keypoints sit in octave 0 with 15x15 or 21x21
 // windows -- use 8 lanes and amortise it over four keypoints per warp.  Sums are in T: double in exact (f64) mode,
 // float in f32 mode (whose parity bar is a tolerance), always in a fixed order (deterministic).
-template <typename T, int LPK>
+template <typename T, int LPK, int NR>
 __global__ void __launch_bounds__(kOriWarps * 32)
 orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, int H, int W,
                    const int32_t* __restrict__ keypoints, int n_keypoints, const T* __restrict__ weights,
@@ -101,33 +101,45 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const uint8_t* ob = obin + (size_t)b * H * W;
   const int side = 2 * radius + 1;
   // clip the window to the image (outside is zero padding = no contribution)
-  const int r0 = max(ki - radius, 0), r1 = min(ki + radius, H - 1);
+  const int r0 = max(ki - radius, 0), r1 = valid ? min(ki + radius, H - 1) : -1;
   const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
-  const int nc = c1 - c0 + 1;
-  const int total = valid ? (r1 - r0 + 1) * nc : 0;
-  const float inv_nc = 1.0f / (float)nc;
-  const int woff = (r0 - ki + radius) * side + (c0 - kj + radius);
-  // 4 samples per lane and trip: all 12 loads are issued before the first dependent shared-memory update
-  for (int tb = 0; __any_sync(0xffffffffu, tb < total); tb += 4 * LPK) {
-    int bins[4];
-    T ws[4];
+  // Row-wise walk: lane `sub` owns window columns c0+sub, c0+sub+LPK, ... of every row, so a sample costs two
+  // gathers, one table load and one private shared-memory update -- no index division.  Two rows (2*NR samples
+  // per lane) are loaded before the first dependent histogram update.
+  // NR = column rounds that cover the window (template parameter, chosen by the launcher from the radius)
+  const int woff = (radius - ki) * side + (radius - kj);  // weight of image pixel (r, c): weights[woff + r*side + c]
+  const int rounds = (c1 - c0 + LPK) / LPK;
+  T* hme = h + sub;
+  if (rounds <= NR) {
+    for (int rr = r0; rr <= r1; rr += 2) {
+      int bins[2][NR];
+      T ws[2][NR];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = tb + u * LPK + sub;
-      int rr = __float2int_rd(__fmul_rn((float)t, inv_nc));  // t / nc up to +-1, fixed below
-      int cc = t - rr * nc;
-      if (cc < 0) { cc += nc; --rr; }
-      if (cc >= nc) { cc -= nc; ++rr; }
-      bins[u] = kOriBins;  // the dropped bin
-      ws[u] = T(0);
-      if (t < total) {
-        const int o = (r0 + rr) * W + (c0 + cc);
-        bins[u] = ob[o];
-        ws[u] = Math<T>::mul(m[o], weights[woff + rr * side + cc]);
+      for (int v = 0; v < 2; ++v) {
+        const int r = rr + v;
+        const bool row_ok = r <= r1;
+        const int ro = r * W;
+        const int wo = woff + r * side;
+#pragma unroll
+        for (int u = 0; u < NR; ++u) {
+          const int c = c0 + sub + u * LPK;
+          bins[v][u] = kOriBins;  // the dropped bin
+          ws[v][u] = T(0);
+          if (row_ok && c <= c1) {
+            bins[v][u] = ob[ro + c];
+            ws[v][u] = Math<T>::mul(m[ro + c], weights[wo + c]);
+          }
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) h[bins[u] * PITCH + sub] += ws[u];  // bin 36 is accumulated but never read
+      for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int u = 0; u < NR; ++u) hme[bins[v][u] * PITCH] += ws[v][u];  // bin 36 is accumulated but never read
+    }
+  } else {
+    // window wider than the class was sized for (only reachable through the C ABI with a hand-picked radius)
+    for (int rr = r0; rr <= r1; ++rr)
+      for (int c = c0 + sub; c <= c1; c += LPK) hme[ob[rr * W + c] * PITCH] += Math<T>::mul(m[rr * W + c], weights[woff + rr * side + c]);
   }
   __syncwarp();
   // column sums: lane `sub` reduces bins sub, sub + LPK, ...; histogram entries are float32 in the reference (:158)
@@ -187,127 +199,164 @@ __global__ void orientation_emit_kernel(const int32_t* __restrict__ keypoints, c
 static constexpr int kDescWarps = 4;
 static constexpr int kTrigStride = 2 + 32;
 
+// Persistent: every CTA converts the host tables once (Gaussian mask, bin edges, the fixed-point column deltas as
+// int32, cos / sin) into shared memory, then its warps walk the oriented keypoints with stride = warps in the grid.
 template <typename T, typename OUT>
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, int W, const int32_t* __restrict__ oriented,
                   int n_oriented, const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc) {
-  __shared__ int sXY[kDescWarps][32];          // x0[0..15], y0[0..15] per warp
   using ACC = T;  // per-sample arithmetic: double in exact mode, float in f32 mode (tolerance-based parity)
+  __shared__ int sXY[kDescWarps][32];       // x0[0..15], y0[0..15] per warp
   __shared__ ACC sHist[kDescWarps][9][32];  // per-lane private bins 0..8 (8 = dropped), [bin][lane]: conflict free
   __shared__ ACC sThr[8];                   // smallest rel with int(rel * 8 / 360.0) >= j + 1 (host computed, exact)
   __shared__ ACC sMask[256];
+  __shared__ __align__(16) int sAd[36][16], sBd[36][16];  // rint(cos * x * 1024), rint(sin * x * 1024) per bin
+  __shared__ double sCS[36][2];
   if (threadIdx.x < 8) sThr[threadIdx.x] = (ACC)trig[36 * kTrigStride + threadIdx.x];
   for (int t = threadIdx.x; t < 256; t += kDescWarps * 32) sMask[t] = (ACC)gmask[t];
+  for (int t = threadIdx.x; t < 36 * 16; t += kDescWarps * 32) {
+    const int bn = t >> 4, x = t & 15;
+    sAd[bn][x] = (int)trig[bn * kTrigStride + 2 + x];
+    sBd[bn][x] = (int)trig[bn * kTrigStride + 18 + x];
+  }
+  if (threadIdx.x < 72) sCS[threadIdx.x >> 1][threadIdx.x & 1] = trig[(threadIdx.x >> 1) * kTrigStride + (threadIdx.x & 1)];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * kDescWarps + warp;
-  if (n >= n_oriented) return;  // warp-uniform; no block-wide barrier below
-  const int4 kp = reinterpret_cast<const int4*>(oriented)[n];
-  const int b = kp.x, ki = kp.y, kj = kp.z, bin = kp.w;
-  const double theta = (double)(10 * bin + 5);  // (bin + 0.5) * 10 % 360, exact
-  const double* tg = trig + bin * kTrigStride;
-  const double cs = tg[0], sn = tg[1];
-  // rotated_subimage: v_x = (c, s), v_y = (-s, c); s_x = j - c*7.5 - (-s)*7.5; s_y = i - s*7.5 - c*7.5
-  const double sx = __dsub_rn(__dsub_rn((double)kj, __dmul_rn(cs, 7.5)), __dmul_rn(-sn, 7.5));
-  const double sy = __dsub_rn(__dsub_rn((double)ki, __dmul_rn(sn, 7.5)), __dmul_rn(cs, 7.5));
-  {
-    const int yy = lane & 15;
-    // X0[y] = rint((M01*y + M02) * 1024) + 512 ; Y0[y] = rint((M11*y + M12) * 1024) + 512
-    const double a = (lane < 16) ? __dadd_rn(__dmul_rn(-sn, (double)yy), sx) : __dadd_rn(__dmul_rn(cs, (double)yy), sy);
-    sXY[warp][lane] = __double2int_rn(__dmul_rn(a, 1024.0)) + 512;
-  }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) sHist[warp][k][lane] = ACC(0);
-  __syncwarp();
-  const T* m = mag + (size_t)b * H * W;
-  const T* d = dir + (size_t)b * H * W;
   const int cell = lane >> 1, half = lane & 1;
   const int cy = (cell >> 2) * 4 + half * 2, cx = (cell & 3) * 4;
-  int ad[4], bd[4];
-#pragma unroll
-  for (int rx = 0; rx < 4; ++rx) {
-    ad[rx] = (int)tg[2 + cx + rx];
-    bd[rx] = (int)tg[2 + 16 + cx + rx];
-  }
   ACC* myh = &sHist[warp][0][lane];
-  const ACC theta_a = (ACC)theta;
+  ACC wmask[2][4];  // this lane's 8 Gaussian weights never change
 #pragma unroll
-  for (int ry = 0; ry < 2; ++ry) {
-    const int wy = cy + ry;
-    const int X0 = sXY[warp][wy], Y0 = sXY[warp][16 + wy];
-    // the 4 gathers of this row are issued before any of them is consumed
-    T mv[4], dv4[4];
+  for (int ry = 0; ry < 2; ++ry)
 #pragma unroll
-    for (int rx = 0; rx < 4; ++rx) {
-      const int X = (X0 + ad[rx]) >> 10;
-      const int Y = (Y0 + bd[rx]) >> 10;
-      const bool in = ((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H);
-      const int o = in ? Y * W + X : 0;  // one image plane has fewer than 2^31 pixels (checked on the host)
-      mv[rx] = in ? m[o] : T(0);
-      dv4[rx] = in ? d[o] : T(0);
+    for (int rx = 0; rx < 4; ++rx) wmask[ry][rx] = sMask[(cy + ry) * 16 + cx + rx];
+  const int warps_total = gridDim.x * kDescWarps;
+  for (int n = blockIdx.x * kDescWarps + warp; n < n_oriented; n += warps_total) {  // no block-wide barrier inside
+    const int4 kp = reinterpret_cast<const int4*>(oriented)[n];
+    const int b = kp.x, ki = kp.y, kj = kp.z, bin = kp.w;
+    const double theta = (double)(10 * bin + 5);  // (bin + 0.5) * 10 % 360, exact
+    const double cs = sCS[bin][0], sn = sCS[bin][1];
+    {
+      // rotated_subimage: v_x = (c, s), v_y = (-s, c); s_x = j - c*7.5 - (-s)*7.5; s_y = i - s*7.5 - c*7.5
+      // X0[y] = rint((M01*y + M02) * 1024) + 512 ; Y0[y] = rint((M11*y + M12) * 1024) + 512
+      const double yy = (double)(lane & 15);
+      double a;
+      if (lane < 16) a = __dadd_rn(__dmul_rn(-sn, yy), __dsub_rn(__dsub_rn((double)kj, __dmul_rn(cs, 7.5)), __dmul_rn(-sn, 7.5)));
+      else a = __dadd_rn(__dmul_rn(cs, yy), __dsub_rn(__dsub_rn((double)ki, __dmul_rn(sn, 7.5)), __dmul_rn(cs, 7.5)));
+      sXY[warp][lane] = __double2int_rn(__dmul_rn(a, 1024.0)) + 512;
     }
 #pragma unroll
-    for (int rx = 0; rx < 4; ++rx) {
-      const ACC wv = Math<ACC>::mul((ACC)mv[rx], sMask[wy * 16 + cx + rx]);
-      // (dir - theta) % 360 with dir in [0, 360], theta in [5, 355]: |dir - theta| < 360, so Python's % is the
-      // identity for non-negative values and one rounded +360 otherwise (can give exactly 360.0 -> bin 8, dropped)
-      ACC rel = Math<ACC>::add((ACC)dv4[rx], -theta_a);
-      if (rel < ACC(0)) rel = Math<ACC>::add(rel, ACC(360));
-      int hb;
-      if constexpr (sizeof(ACC) == 4) {
-        // f32 mode: truncate rel / 45 and repair the one-off at the bin edges with a single compare
-        hb = __float2int_rz(rel * 0.022222222f);
-        hb += (rel >= 45.0f * (float)(hb + 1)) ? 1 : 0;
-      } else {
-        // bin = int(rel * 8 / 360.0): count of thresholds <= rel (binary search over the exact host table)
-        hb = (rel >= sThr[3]) ? 4 : 0;
-        hb += (rel >= sThr[hb + 1]) ? 2 : 0;
-        hb += (rel >= sThr[hb]) ? 1 : 0;
-        hb = (rel >= sThr[7]) ? 8 : hb;
+    for (int k = 0; k < 9; ++k) myh[k * 32] = ACC(0);
+    __syncwarp();
+    const T* m = mag + (size_t)b * H * W;
+    const T* d = dir + (size_t)b * H * W;
+    const int4 ad4 = *reinterpret_cast<const int4*>(&sAd[bin][cx]);
+    const int4 bd4 = *reinterpret_cast<const int4*>(&sBd[bin][cx]);
+    const int ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w}, bd[4] = {bd4.x, bd4.y, bd4.z, bd4.w};
+    const ACC theta_a = (ACC)theta;
+    // the rotated 16x16 window reaches at most 7.5 * sqrt(2) + 1 < 12 pixels from the keypoint
+    const bool interior = (ki >= 12) && (ki < H - 12) && (kj >= 12) && (kj < W - 12);
+    // all 8 gathers of the lane are issued before the first dependent histogram update
+    T mv[2][4], dv[2][4];
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+      const int X0 = sXY[warp][cy + ry], Y0 = sXY[warp][16 + cy + ry];
+#pragma unroll
+      for (int rx = 0; rx < 4; ++rx) {
+        const int X = (X0 + ad[rx]) >> 10;
+        const int Y = (Y0 + bd[rx]) >> 10;
+        if (interior) {
+          const int o = Y * W + X;  // one image plane has fewer than 2^31 pixels (checked on the host)
+          mv[ry][rx] = m[o];
+          dv[ry][rx] = d[o];
+        } else {
+          const bool in = ((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H);
+          const int o = in ? Y * W + X : 0;
+          mv[ry][rx] = in ? m[o] : T(0);
+          dv[ry][rx] = in ? d[o] : T(0);
+        }
       }
-      myh[hb * 32] += wv;
     }
-  }
-  __syncwarp();
-  // merge the two halves of the cell (rows 0-1 then rows 2-3), round to float32 like the reference's cell hist;
-  // normalise / clip [2^-10, 0.2] / normalise (:281-287) in NT = double (exact mode) or float (f32 mode)
-  using NT = T;
-  NT hist[8], f[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const ACC mine = myh[k * 32];
-    const ACC other = __shfl_xor_sync(0xffffffffu, mine, 1);
-    const ACC s = half ? Math<ACC>::add(other, mine) : Math<ACC>::add(mine, other);
-    hist[k] = (NT)(float)s;
-  }
-  // even lane keeps bins 0..3, odd lane bins 4..7 of the cell -> feature index cell*8 + half*4 + k
+    for (int ry = 0; ry < 2; ++ry) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) f[k] = half ? hist[4 + k] : hist[k];
-  NT ss = f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
+      for (int rx = 0; rx < 4; ++rx) {
+        const ACC wv = Math<ACC>::mul((ACC)mv[ry][rx], wmask[ry][rx]);
+        // (dir - theta) % 360 with dir in [0, 360], theta in [5, 355]: |dir - theta| < 360, so Python's % is the
+        // identity for non-negative values and one rounded +360 otherwise (can give exactly 360.0 -> bin 8, dropped)
+        ACC rel = Math<ACC>::add((ACC)dv[ry][rx], -theta_a);
+        if (rel < ACC(0)) rel = Math<ACC>::add(rel, ACC(360));
+        int hb;
+        if constexpr (sizeof(ACC) == 4) {
+          // f32 mode: truncate rel / 45 and repair the one-off at the bin edges with a single compare
+          hb = __float2int_rz(rel * 0.022222222f);
+          hb += (rel >= 45.0f * (float)(hb + 1)) ? 1 : 0;
+        } else {
+          // bin = int(rel * 8 / 360.0): count of thresholds <= rel (binary search over the exact host table)
+          hb = (rel >= sThr[3]) ? 4 : 0;
+          hb += (rel >= sThr[hb + 1]) ? 2 : 0;
+          hb += (rel >= sThr[hb]) ? 1 : 0;
+          hb = (rel >= sThr[7]) ? 8 : hb;
+        }
+        myh[hb * 32] += wv;
+      }
+    }
+    __syncwarp();
+    // merge the two halves of the cell (rows 0-1 then rows 2-3), round to float32 like the reference's cell hist;
+    // normalise / clip [2^-10, 0.2] / normalise (:281-287) in NT = double (exact mode) or float (f32 mode)
+    using NT = T;
+    NT f[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const NT nrm = Math<NT>::sqrt_(ss);
-  const NT lo = NT(0.0009765625), hi = NT(0.2);  // np.finfo(np.float16).eps, 0.2
-  NT s2 = NT(0);
+    for (int k = 0; k < 8; ++k) {
+      const ACC mine = myh[k * 32];
+      const ACC other = __shfl_xor_sync(0xffffffffu, mine, 1);
+      const ACC sum = half ? Math<ACC>::add(other, mine) : Math<ACC>::add(mine, other);
+      // even lane keeps bins 0..3, odd lane bins 4..7 of the cell -> feature index cell*8 + half*4 + k
+      if ((k >> 2) == half) f[k & 3] = (NT)(float)sum;
+    }
+    NT ss = f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    NT v = f[k] / nrm;  // IEEE division; 0 / 0 = NaN for an all-zero window, like the reference
-    if (v == v) v = v < lo ? lo : (v > hi ? hi : v);  // np.clip keeps NaN
-    f[k] = v;
-    s2 += v * v;
-  }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const NT lo = NT(0.0009765625), hi = NT(0.2);  // np.finfo(np.float16).eps, 0.2
+    NT s2 = NT(0);
+    if constexpr (sizeof(NT) == 4) {
+      // f32 mode: one reciprocal square root instead of a square root and four IEEE divisions; 0 * inf = NaN for an
+      // all-zero window, like the reference's 0 / 0
+      const float inv = rsqrtf(ss);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  const NT nrm2 = Math<NT>::sqrt_(s2);
-  OUT* dst = desc + (size_t)n * 128 + lane * 4;
-  if (sizeof(OUT) == 4) {
-    float4 o4;
-    o4.x = (float)(f[0] / nrm2); o4.y = (float)(f[1] / nrm2);
-    o4.z = (float)(f[2] / nrm2); o4.w = (float)(f[3] / nrm2);
-    *reinterpret_cast<float4*>(dst) = o4;
-  } else {
+      for (int k = 0; k < 4; ++k) {
+        NT v = f[k] * inv;
+        if (v == v) v = v < lo ? lo : (v > hi ? hi : v);  // np.clip keeps NaN
+        f[k] = v;
+        s2 += v * v;
+      }
+    } else {
+      const NT nrm = Math<NT>::sqrt_(ss);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = (OUT)(f[k] / nrm2);
+      for (int k = 0; k < 4; ++k) {
+        NT v = f[k] / nrm;  // IEEE division; 0 / 0 = NaN for an all-zero window, like the reference
+        if (v == v) v = v < lo ? lo : (v > hi ? hi : v);
+        f[k] = v;
+        s2 += v * v;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    OUT* dst = desc + (size_t)n * 128 + lane * 4;
+    if constexpr (sizeof(NT) == 4) {
+      const float inv2 = rsqrtf(s2);
+      if (sizeof(OUT) == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(f[0] * inv2, f[1] * inv2, f[2] * inv2, f[3] * inv2);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = (OUT)(f[k] * inv2);
+      }
+    } else {
+      const NT nrm2 = Math<NT>::sqrt_(s2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[k] = (OUT)(f[k] / nrm2);
+    }
+    __syncwarp();  // the next keypoint rewrites sXY and the private bins
   }
 }
 
@@ -370,17 +419,26 @@ extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orienta
   if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype != FC_F32 && dtype != FC_F64) return FC_ERR_BAD_ARG;
-  // lanes per keypoint by window size: (2r+1)^2 <= 441 samples -> 8, <= 961 -> 16, else a whole warp
+  // lanes per keypoint by window size: (2r+1)^2 <= 441 samples -> 8, <= 961 -> 16, else a whole warp; the number
+  // of column rounds per row is a template parameter so that the row loop is fully unrolled and predicated
   const int lpk = radius <= 10 ? 8 : (radius <= 15 ? 16 : 32);
-#define FC_ORI(T, LPK)                                                                                              \
-  orientation_kernel<T, LPK><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(                \
+  const int nr = div_up(2 * radius + 1, lpk);
+#define FC_ORI(T, LPK, NR)                                                                                          \
+  orientation_kernel<T, LPK, NR><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(            \
       (const T*)magnitude, orientation_bin, height, width, keypoints, n_keypoints, (const T*)weights, radius,      \
       (unsigned long long*)bin_mask)
-  if (dtype == FC_F32) {
-    if (lpk == 8) FC_ORI(float, 8); else if (lpk == 16) FC_ORI(float, 16); else FC_ORI(float, 32);
-  } else {
-    if (lpk == 8) FC_ORI(double, 8); else if (lpk == 16) FC_ORI(double, 16); else FC_ORI(double, 32);
-  }
+#define FC_ORI_T(T)                                                  \
+  do {                                                               \
+    if (lpk == 8) {                                                  \
+      if (nr <= 1) FC_ORI(T, 8, 1); else if (nr == 2) FC_ORI(T, 8, 2); else FC_ORI(T, 8, 3); \
+    } else if (lpk == 16) {                                          \
+      FC_ORI(T, 16, 2);                                              \
+    } else {                                                         \
+      if (nr <= 2) FC_ORI(T, 32, 2); else if (nr == 3) FC_ORI(T, 32, 3); else if (nr == 4) FC_ORI(T, 32, 4); else FC_ORI(T, 32, 5); \
+    }                                                                \
+  } while (0)
+  if (dtype == FC_F32) FC_ORI_T(float); else FC_ORI_T(double);
+#undef FC_ORI_T
 #undef FC_ORI
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
@@ -416,10 +474,23 @@ extern "C" int fc_descriptors(const void* magnitude, const void* direction, int 
   if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
   if (reinterpret_cast<uintptr_t>(oriented) & 15) return FC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = div_up(n_oriented, kDescWarps);
+  // persistent grid: as many CTAs as are resident at once (occupancy query per instantiation), fewer when there is less work
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    FC_CUDA_TRY(cudaGetDevice(&dev));
+    FC_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
 #define FC_LAUNCH(T, OUT)                                                                                         \
-  descriptor_kernel<T, OUT><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
-                                                               width, oriented, n_oriented, gmask, trig, (OUT*)descriptors)
+  do {                                                                                                            \
+    static int per_sm = 0;                                                                                        \
+    if (per_sm == 0)                                                                                              \
+      FC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descriptor_kernel<T, OUT>, kDescWarps * 32, 0)); \
+    const int want = div_up(n_oriented, kDescWarps);                                                              \
+    const int blocks = want < n_sm * per_sm ? want : n_sm * per_sm;                                               \
+    descriptor_kernel<T, OUT><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
+                                                                 width, oriented, n_oriented, gmask, trig, (OUT*)descriptors); \
+  } while (0)
   if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float);
   else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double);
   else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float);
