@@ -5,7 +5,7 @@
 //                              np.round(direction * 36 / 360) (:140-142) as one byte per pixel.
 //   orientation_kernel<T,LPK>  8 / 16 / 32 lanes per keypoint: zero-padded (2r+1)^2 window, weight = magnitude x
 //                              unnormalised Gaussian table, 36-bin histogram (:144-163).  Every lane owns a
-//                              private copy of the histogram in shared memory ([bin][lane], conflict free,
+//                              private copy of the histogram in shared memory ([bin][lane],
 //                              no atomics, deterministic float64 sums); bins are reduced by shuffles, rounded
 //                              to float32 and compared with float32(0.8) * max (:165-167).
 //   descriptor_kernel<T>       one warp per oriented keypoint: 16x16 nearest-neighbour rotated window with
@@ -69,6 +69,19 @@ gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int 
     obin[o] = (uint8_t)(int)rint(__ddiv_rn(__dmul_rn((double)d, 36.0), 360.0));
 }
 
+// 16-byte shared-memory vectors of the histogram type
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  using type = float4;
+  static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ float add_in_order(float s, float4 v) { return (((s + v.x) + v.y) + v.z) + v.w; }
+};
+template <> struct Vec16<double> {
+  using type = double2;
+  static __device__ __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
+  static __device__ __forceinline__ double add_in_order(double s, double2 v) { return (s + v.x) + v.y; }
+};
+
 // ------------------------------------------------------------------------------------------------
 static constexpr int kOriWarps = 4;
 static constexpr int kOriBins = 36;
@@ -84,16 +97,22 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
                    const int32_t* __restrict__ keypoints, int n_keypoints, const T* __restrict__ weights,
                    int radius, unsigned long long* __restrict__ bin_mask) {
   constexpr int KPW = 32 / LPK;        // keypoints per warp
-  constexpr int PITCH = LPK + 1;       // [bin][lane] + one pad column: the final column sums are conflict free
+  constexpr int PITCH = LPK;           // [bin][lane]: rows of LPK values, so clearing and the final sums move 16 bytes at a time
   constexpr int NB = (kOriBins + LPK - 1) / LPK;  // bins reduced by one lane
-  __shared__ T hist[kOriWarps][KPW][(kOriBins + 1) * PITCH];
+  constexpr int VEC = 16 / sizeof(T);  // values per 16-byte shared access
+  constexpr int NROWS = (NR <= 2) ? 4 : 2;  // image rows whose samples are loaded before the first histogram update
+  __shared__ __align__(16) T hist[kOriWarps][KPW][(kOriBins + 1) * PITCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPK, slot = lane / LPK;
   const int n = (blockIdx.x * kOriWarps + warp) * KPW + slot;
   const bool valid = n < n_keypoints;
   if ((blockIdx.x * kOriWarps + warp) * KPW >= n_keypoints) return;  // warp-uniform; no block-wide barriers below
   T* h = hist[warp][slot];
-  for (int t = sub; t < (kOriBins + 1) * PITCH; t += LPK) h[t] = T(0);
+  {
+    using V = typename Vec16<T>::type;
+    V* hv = reinterpret_cast<V*>(h);
+    for (int t = sub; t < (kOriBins + 1) * PITCH / VEC; t += LPK) hv[t] = Vec16<T>::zero();
+  }
   __syncwarp();
   const int nn = valid ? n : 0;
   const int b = keypoints[3 * nn], ki = keypoints[3 * nn + 1], kj = keypoints[3 * nn + 2];
@@ -111,11 +130,11 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const int rounds = (c1 - c0 + LPK) / LPK;
   T* hme = h + sub;
   if (rounds <= NR) {
-    for (int rr = r0; rr <= r1; rr += 2) {
-      int bins[2][NR];
-      T ws[2][NR];
+    for (int rr = r0; rr <= r1; rr += NROWS) {
+      int bins[NROWS][NR];
+      T ws[NROWS][NR];
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
+      for (int v = 0; v < NROWS; ++v) {
         const int r = rr + v;
         const bool row_ok = r <= r1;
         const int ro = r * W;
@@ -132,7 +151,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
         }
       }
 #pragma unroll
-      for (int v = 0; v < 2; ++v)
+      for (int v = 0; v < NROWS; ++v)
 #pragma unroll
         for (int u = 0; u < NR; ++u) hme[bins[v][u] * PITCH] += ws[v][u];  // bin 36 is accumulated but never read
     }
@@ -150,9 +169,11 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
     const int bin = sub + q * LPK;
     f[q] = -1.0f;
     if (bin < kOriBins) {
+      using V = typename Vec16<T>::type;
+      const V* row = reinterpret_cast<const V*>(h + bin * PITCH);
       T sacc = T(0);
-#pragma unroll 8
-      for (int k = 0; k < LPK; ++k) sacc += h[bin * PITCH + k];
+#pragma unroll
+      for (int k = 0; k < LPK / VEC; ++k) sacc = Vec16<T>::add_in_order(sacc, row[k]);  // lane 0, 1, 2, ... of the keypoint
       f[q] = (float)sacc;
       mx = fmaxf(mx, f[q]);
     }
