@@ -43,7 +43,7 @@ __device__ __forceinline__ T py_mod360(T a) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int W, T* __restrict__ mag,
-                      T* __restrict__ dir, uint8_t* __restrict__ obin) {
+                      T* __restrict__ dir, uint8_t* __restrict__ obin, uint32_t* __restrict__ packed) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -63,10 +63,15 @@ gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int 
   mag[o] = m;
   dir[o] = d;
   // np.round(direction * 36 / 360): half to even, evaluated in the scale-space type on the stored direction
-  if constexpr (sizeof(T) == 4)
-    obin[o] = (uint8_t)(int)rintf(__fdiv_rn(__fmul_rn(d, 36.0f), 360.0f));
-  else
+  if constexpr (sizeof(T) == 4) {
+    const int ob = (int)rintf(__fdiv_rn(__fmul_rn(d, 36.0f), 360.0f));
+    if (obin) obin[o] = (uint8_t)ob;
+    // orientation operand of the f32 pipeline: magnitude rounded to 18 mantissa bits with the bin (0..36) in the low
+    // 6 bits, so that the orientation kernel gathers one 4-byte word per sample instead of a float and a byte
+    if (packed) packed[o] = ((__float_as_uint(m) + 32u) & ~63u) | (uint32_t)ob;
+  } else {
     obin[o] = (uint8_t)(int)rint(__ddiv_rn(__dmul_rn((double)d, 36.0), 360.0));
+  }
 }
 
 // 16-byte shared-memory vectors of the histogram type
@@ -91,7 +96,7 @@ static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the fi
 // histograms) is the same for every LPK, so small windows -- most keypoints sit in octave 0 with 15x15 or 21x21
 // windows -- use 8 lanes and amortise it over four keypoints per warp.  Sums are in T: double in exact (f64) mode,
 // float in f32 mode (whose parity bar is a tolerance), always in a fixed order (deterministic).
-template <typename T, int LPK, int NR>
+template <typename T, int LPK, int NR, bool PACKED>
 __global__ void __launch_bounds__(kOriWarps * 32)
 orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, int H, int W,
                    const int32_t* __restrict__ keypoints, int n_keypoints, const T* __restrict__ weights,
@@ -117,7 +122,9 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const int nn = valid ? n : 0;
   const int b = keypoints[3 * nn], ki = keypoints[3 * nn + 1], kj = keypoints[3 * nn + 2];
   const T* m = mag + (size_t)b * H * W;
-  const uint8_t* ob = obin + (size_t)b * H * W;
+  const uint8_t* ob = PACKED ? nullptr : obin + (size_t)b * H * W;
+  // PACKED (float only): `mag` holds fc_gradient_field_packed's words = magnitude | bin
+  const uint32_t* pk = reinterpret_cast<const uint32_t*>(m);
   const int side = 2 * radius + 1;
   // clip the window to the image (outside is zero padding = no contribution)
   const int r0 = max(ki - radius, 0), r1 = valid ? min(ki + radius, H - 1) : -1;
@@ -145,8 +152,14 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
           bins[v][u] = kOriBins;  // the dropped bin
           ws[v][u] = T(0);
           if (row_ok && c <= c1) {
-            bins[v][u] = ob[ro + c];
-            ws[v][u] = Math<T>::mul(m[ro + c], weights[wo + c]);
+            if constexpr (PACKED) {
+              const uint32_t p = pk[ro + c];
+              bins[v][u] = (int)(p & 63u);
+              ws[v][u] = (T)__fmul_rn(__uint_as_float(p & ~63u), (float)weights[wo + c]);
+            } else {
+              bins[v][u] = ob[ro + c];
+              ws[v][u] = Math<T>::mul(m[ro + c], weights[wo + c]);
+            }
           }
         }
       }
@@ -158,7 +171,14 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   } else {
     // window wider than the class was sized for (only reachable through the C ABI with a hand-picked radius)
     for (int rr = r0; rr <= r1; ++rr)
-      for (int c = c0 + sub; c <= c1; c += LPK) hme[ob[rr * W + c] * PITCH] += Math<T>::mul(m[rr * W + c], weights[woff + rr * side + c]);
+      for (int c = c0 + sub; c <= c1; c += LPK) {
+        if constexpr (PACKED) {
+          const uint32_t p = pk[rr * W + c];
+          hme[(p & 63u) * PITCH] += (T)__fmul_rn(__uint_as_float(p & ~63u), (float)weights[woff + rr * side + c]);
+        } else {
+          hme[ob[rr * W + c] * PITCH] += Math<T>::mul(m[rr * W + c], weights[woff + rr * side + c]);
+        }
+      }
   }
   __syncwarp();
   // column sums: lane `sub` reduces bins sub, sub + LPK, ...; histogram entries are float32 in the reference (:158)
@@ -412,18 +432,18 @@ extern "C" int fc_rotated_window(const double* image, int height, int width, dou
   return FC_OK;
 }
 
-extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
-                                 void* magnitude, void* direction, uint8_t* orientation_bin, void* stream) {
-  if (!gauss || !magnitude || !direction || !orientation_bin || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+static int launch_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
+                                 void* magnitude, void* direction, uint8_t* orientation_bin, uint32_t* packed, void* stream) {
+  if (!gauss || !magnitude || !direction || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
   if (level < 0 || level >= n_levels) return FC_ERR_BAD_ARG;
   dim3 grid(div_up(width, 256), height, batch);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FC_F32)
     gradient_field_kernel<float><<<grid, 256, 0, st>>>((const float*)gauss, n_levels, level, height, width,
-                                                       (float*)magnitude, (float*)direction, orientation_bin);
-  else if (dtype == FC_F64)
+                                                       (float*)magnitude, (float*)direction, orientation_bin, packed);
+  else if (dtype == FC_F64 && orientation_bin && !packed)
     gradient_field_kernel<double><<<grid, 256, 0, st>>>((const double*)gauss, n_levels, level, height, width,
-                                                        (double*)magnitude, (double*)direction, orientation_bin);
+                                                        (double*)magnitude, (double*)direction, orientation_bin, nullptr);
   else
     return FC_ERR_BAD_ARG;
   note_launch();
@@ -431,10 +451,25 @@ extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_
   return FC_OK;
 }
 
-extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
-                                   int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
-                                   uint64_t* bin_mask, void* stream) {
-  if (!magnitude || !orientation_bin || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0) return FC_ERR_BAD_ARG;
+extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
+                                 void* magnitude, void* direction, uint8_t* orientation_bin, void* stream) {
+  if (!orientation_bin) return FC_ERR_BAD_ARG;
+  return launch_gradient_field(gauss, dtype, batch, n_levels, level, height, width, magnitude, direction, orientation_bin,
+                               nullptr, stream);
+}
+
+extern "C" int fc_gradient_field_packed(const void* gauss, int batch, int n_levels, int level, int height, int width,
+                                        void* magnitude, void* direction, uint32_t* magnitude_bin, void* stream) {
+  if (!magnitude_bin) return FC_ERR_BAD_ARG;
+  return launch_gradient_field(gauss, FC_F32, batch, n_levels, level, height, width, magnitude, direction, nullptr,
+                               magnitude_bin, stream);
+}
+
+static int launch_orientation(const void* magnitude, const uint8_t* orientation_bin, int dtype, bool packed, int batch,
+                              int height, int width, const int32_t* keypoints, int n_keypoints, const void* weights,
+                              int radius, uint64_t* bin_mask, void* stream) {
+  if (!magnitude || (!packed && !orientation_bin) || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0)
+    return FC_ERR_BAD_ARG;
   if (n_keypoints == 0) return FC_OK;
   if (!keypoints || !bin_mask || n_keypoints < 0) return FC_ERR_BAD_ARG;
   if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
@@ -444,26 +479,40 @@ extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orienta
   // of column rounds per row is a template parameter so that the row loop is fully unrolled and predicated
   const int lpk = radius <= 10 ? 8 : (radius <= 15 ? 16 : 32);
   const int nr = div_up(2 * radius + 1, lpk);
-#define FC_ORI(T, LPK, NR)                                                                                          \
-  orientation_kernel<T, LPK, NR><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(            \
+#define FC_ORI(T, LPK, NR, PK)                                                                                      \
+  orientation_kernel<T, LPK, NR, PK><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(        \
       (const T*)magnitude, orientation_bin, height, width, keypoints, n_keypoints, (const T*)weights, radius,      \
       (unsigned long long*)bin_mask)
-#define FC_ORI_T(T)                                                  \
+#define FC_ORI_T(T, PK)                                              \
   do {                                                               \
     if (lpk == 8) {                                                  \
-      if (nr <= 1) FC_ORI(T, 8, 1); else if (nr == 2) FC_ORI(T, 8, 2); else FC_ORI(T, 8, 3); \
+      if (nr <= 1) FC_ORI(T, 8, 1, PK); else if (nr == 2) FC_ORI(T, 8, 2, PK); else FC_ORI(T, 8, 3, PK); \
     } else if (lpk == 16) {                                          \
-      FC_ORI(T, 16, 2);                                              \
+      FC_ORI(T, 16, 2, PK);                                          \
     } else {                                                         \
-      if (nr <= 2) FC_ORI(T, 32, 2); else if (nr == 3) FC_ORI(T, 32, 3); else if (nr == 4) FC_ORI(T, 32, 4); else FC_ORI(T, 32, 5); \
+      if (nr <= 2) FC_ORI(T, 32, 2, PK); else if (nr == 3) FC_ORI(T, 32, 3, PK); else if (nr == 4) FC_ORI(T, 32, 4, PK); else FC_ORI(T, 32, 5, PK); \
     }                                                                \
   } while (0)
-  if (dtype == FC_F32) FC_ORI_T(float); else FC_ORI_T(double);
+  if (packed) FC_ORI_T(float, true); else if (dtype == FC_F32) FC_ORI_T(float, false); else FC_ORI_T(double, false);
 #undef FC_ORI_T
 #undef FC_ORI
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
+}
+
+extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
+                                   int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
+                                   uint64_t* bin_mask, void* stream) {
+  return launch_orientation(magnitude, orientation_bin, dtype, false, batch, height, width, keypoints, n_keypoints, weights,
+                            radius, bin_mask, stream);
+}
+
+extern "C" int fc_orientation_bins_packed(const uint32_t* magnitude_bin, int batch, int height, int width,
+                                          const int32_t* keypoints, int n_keypoints, const float* weights, int radius,
+                                          uint64_t* bin_mask, void* stream) {
+  return launch_orientation(magnitude_bin, nullptr, FC_F32, true, batch, height, width, keypoints, n_keypoints, weights,
+                            radius, bin_mask, stream);
 }
 
 extern "C" int fc_orientation_scan(const uint64_t* bin_mask, int n_keypoints, int32_t* offsets, int32_t* scratch, void* stream) {

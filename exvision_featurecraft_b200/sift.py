@@ -368,13 +368,31 @@ def keypoints_from_mask(mask: torch.Tensor, width: int) -> torch.Tensor:
 
 
 def gradient_field(octv: Octave, level: int, params: SiftParams):
+    """sift_gradient of one level -> (magnitude, direction, orientation operand).  The orientation operand is the
+    uint8 bin plane in f64 mode and the packed magnitude|bin int32 plane in f32 mode (one gather per sample)."""
     b, L, h, w = octv.gauss.shape
     mag = torch.empty((b, h, w), dtype=octv.gauss.dtype, device=octv.gauss.device)
     direction = torch.empty_like(mag)
+    if params.fc_dtype == _lib.FC_F32:
+        packed = torch.empty((b, h, w), dtype=torch.int32, device=mag.device)
+        _lib.call("fc_gradient_field_packed", ptr(octv.gauss), b, L, level, h, w, ptr(mag), ptr(direction), ptr(packed),
+                  stream_ptr())
+        return mag, direction, packed
     obin = torch.empty((b, h, w), dtype=torch.uint8, device=mag.device)
     _lib.call("fc_gradient_field", ptr(octv.gauss), params.fc_dtype, b, L, level, h, w, ptr(mag), ptr(direction), ptr(obin),
               stream_ptr())
     return mag, direction, obin
+
+
+def orientation_bins(mag, obin, keypoints, n, weights, radius, bin_mask, params: SiftParams):
+    """Launch the 36-bin histogram kernel on whichever orientation operand gradient_field produced."""
+    b, h, w = mag.shape
+    if obin.dtype == torch.int32:
+        _lib.call("fc_orientation_bins_packed", ptr(obin), b, h, w, ptr(keypoints), n, ptr(weights), radius, ptr(bin_mask),
+                  stream_ptr())
+    else:
+        _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), params.fc_dtype, b, h, w, ptr(keypoints), n, ptr(weights),
+                  radius, ptr(bin_mask), stream_ptr())
 
 
 def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
@@ -386,8 +404,7 @@ def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
     radius, weights = _orientation_weights(sigma, params)
     b, h, w = mag.shape
     bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
-    _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), params.fc_dtype, b, h, w, ptr(keypoints), n, ptr(weights), radius,
-              ptr(bin_mask), stream_ptr())
+    orientation_bins(mag, obin, keypoints, n, weights, radius, bin_mask, params)
     offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
     scratch = scan_scratch(n)
     _lib.call("fc_orientation_scan", ptr(bin_mask), n, ptr(offsets), ptr(scratch), stream_ptr())
@@ -487,8 +504,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
         with _stage("orientation"):
             radius, weights = _orientation_weights(sigma, params)
             bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
-            _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), params.fc_dtype, b, h, octv.width, ptr(kps), n, ptr(weights),
-                      radius, ptr(bin_mask), stream_ptr())
+            orientation_bins(mag, obin, kps, n, weights, radius, bin_mask, params)
             offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
             scratch = scan_scratch(n)
             _lib.call("fc_orientation_scan", ptr(bin_mask), n, ptr(offsets), ptr(scratch), stream_ptr())

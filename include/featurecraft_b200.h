@@ -168,6 +168,12 @@ FC_API int fc_convert_f64(const double* src, int64_t n, int dtype, void* dst, vo
 FC_API int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
                       void* magnitude, void* direction, uint8_t* orientation_bin, void* stream);
 
+/* The same gradient field for the float32 pipeline, with the orientation operand packed for a single gather:
+ * magnitude_bin[b][y][x] = (bits of magnitude rounded to 18 mantissa bits) | orientation_bin (low 6 bits).
+ * magnitude and direction are written in full float32 as above (the descriptor stage reads those). */
+FC_API int fc_gradient_field_packed(const void* gauss, int batch, int n_levels, int level, int height, int width,
+                             void* magnitude, void* direction, uint32_t* magnitude_bin, void* stream);
+
 /* dog_keypoints_orientations (:116-172) for one (octave, scale): keypoints are (image, row, col)
  * int32 triples in reference order; `weights` is gaussian_filter_kernel(sigma) as a dense (2r+1)^2 device
  * table of element type `dtype`.  For keypoint n the 36-bin float32 histogram is built (sums in `dtype`)
@@ -175,6 +181,10 @@ FC_API int fc_gradient_field(const void* gauss, int dtype, int batch, int n_leve
 FC_API int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
                         int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
                         uint64_t* bin_mask, void* stream);
+/* float32 pipeline: the same histograms from fc_gradient_field_packed's words (weights float32). */
+FC_API int fc_orientation_bins_packed(const uint32_t* magnitude_bin, int batch, int height, int width,
+                               const int32_t* keypoints, int n_keypoints, const float* weights, int radius,
+                               uint64_t* bin_mask, void* stream);
 
 /* Expand bin masks into oriented keypoints in reference order: offsets[n] = popcount prefix
  * (exclusive, offsets[n_keypoints] = total; scratch as for fc_mask_scan), then

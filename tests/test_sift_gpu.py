@@ -105,6 +105,12 @@ def test_gradient_field(S):
             # angles of near-zero gradients are ill conditioned in float32; compare where |g| is resolvable
             ok = g["mag"] > 1e-3
             assert dd[ok].max() < 5e-3
+            # f32 mode returns the orientation operand packed: magnitude (18 mantissa bits) | 36-bin index (low 6 bits)
+            pk = obin[0].cpu().numpy().view(np.uint32)
+            ref_bin = np.round(g["direction"] * 36 / 360).astype(int)
+            assert ((pk & 63) != ref_bin)[ok].mean() < 1e-3
+            pm = (pk & ~np.uint32(63)).view(np.float32).astype(np.float64)
+            assert np.abs(pm - g["mag"]).max() <= 2.0 ** -18 * g["mag"].max() + 1e-6
 
 
 def _run_full(S, g, case, dtype):
