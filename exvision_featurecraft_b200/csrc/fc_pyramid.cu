@@ -342,6 +342,232 @@ extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int is_dog, int
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Strip variant of the extremum search (float32 Gaussian stack, width % 4 == 0): the kernel launched on the hot path
+// ------------------------------------------------------------------------------------------------
+// One warp owns a 128-column strip of a band of rows and walks down it; a lane owns 4 adjacent pixels.  Per row the
+// L Gaussian levels of the strip (+ one halo column each side) are staged with cp.async into a 4-row per-warp ring
+// (three rows in flight), read back as 6 values per level and lane, and reduced in registers:
+//   D_d   = G_{d+1} - G_d                                 (DoG on the fly, never stored)
+//   A_k   = max3 / min3 over the levels k-1, k, k+1       (per pixel)
+//   H_k   = max3 / min3 over x-1, x, x+1 of A_k           (per row)
+//   M_k   = max3 / min3 over the rows y-1, y, y+1 of H_k  (three rows of H kept in registers, roles rotate)
+// with the centre excluded from its own row's reduction, so that M / m are the extrema of the 26 NEIGHBOURS: a value
+// strictly above M (below m) is the unique maximum (minimum) = the reference's argmax == 13 || argmin == 13 (:78-88);
+// only exact ties re-read their neighbourhood from global memory and apply the reference's first-wins tie rule, as do
+// the hits of the script variant for its contrast / edge tests.
+static constexpr int kExsWarps = 4;
+static constexpr int kExsRows = 4;       // ring rows per warp
+static constexpr int kExsPitch = 136;    // floats per level and ring row: [3] = left halo, [4..131] = strip, [132] = right halo
+
+template <int ND>
+struct ExsRow {  // what a row contributes to the rows above and below it
+  float emax[ND - 2][4], emin[ND - 2][4];  // 3-max / 3-min over x-1..x+1 of max / min over the levels k-1, k, k+1
+};
+template <int ND>
+struct ExsMid {  // what a row needs when it is the centre row
+  float nmax[ND - 2][4], nmin[ND - 2][4];  // max / min over its own 3x3x3 slice WITHOUT the centre value
+  float c[ND - 2][4];                      // DoG_k at the lane's 4 pixels
+};
+
+template <int ND>
+__device__ __forceinline__ void exs_stage_row(const float* __restrict__ g, size_t plane, int H, int W, int yy, int x,
+                                              int strip_c0, float* __restrict__ slot, int lane) {
+  const int row = min(max(yy, 0), H - 1);
+  const float* src = g + (size_t)row * W;
+  if (x < W) {
+#pragma unroll
+    for (int l = 0; l <= ND; ++l) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(slot + l * kExsPitch + 4 + 4 * lane);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + l * plane + x) : "memory");
+    }
+  }
+  if (lane == 0 || lane == 31) {
+    // halo columns; clamped at the image border (border pixels are never centres, so the value is irrelevant there)
+    const int hc = lane == 0 ? max(strip_c0 - 1, 0) : min(strip_c0 + 128, W - 1);
+    const int di = lane == 0 ? 3 : 132;
+#pragma unroll
+    for (int l = 0; l <= ND; ++l) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(slot + l * kExsPitch + di);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + l * plane + hc) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// exact rule on the 3x3x3 block around (y, x, k), read from the Gaussian stack in global memory
+template <int ND>
+__device__ __noinline__ bool exs_exact(const float* __restrict__ g, size_t plane, int W, int y, int x, int k, int filter,
+                                       double contrast_th, double ratio_th) {
+  float dv[3][3][3];  // [di][dj][level k-1..k+1]
+#pragma unroll
+  for (int di = 0; di < 3; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj) {
+      const float* p = g + (size_t)(k - 1) * plane + (size_t)(y - 1 + di) * W + (x - 1 + dj);
+      const float g0 = p[0], g1 = p[plane], g2 = p[2 * plane], g3 = p[3 * plane];
+      dv[di][dj][0] = g1 - g0; dv[di][dj][1] = g2 - g1; dv[di][dj][2] = g3 - g2;
+    }
+  const float c = dv[1][1][1];
+  bool is_max = true, is_min = true;
+#pragma unroll
+  for (int di = 0; di < 3; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+      for (int dk = 0; dk < 3; ++dk) {
+        const int flat = di * 9 + dj * 3 + dk;
+        const float a = dv[di][dj][dk];
+        // entries before the centre (flat index < 13): strict; after: non-strict (the first extremum wins)
+        if (flat < 13) { is_max &= c > a; is_min &= c < a; }
+        else if (flat > 13) { is_max &= c >= a; is_min &= c <= a; }
+      }
+  bool hit = is_max || is_min;
+  if (hit && filter == FC_FILTER_SCRIPT) {
+    // SIFT.py:202-215: contrast from DoG[2k-1] (local 3-stack indexed with the global k), Hessian on DoG[k]
+    const int ci = 2 * k - 1;
+    double contrast = 0.0;
+    if (ci < ND) {
+      const float* p = g + (size_t)ci * plane + (size_t)y * W + x;
+      contrast = (double)(p[plane] - p[0]);
+    }
+    const double c0 = (double)c;
+    const double dxx = __dadd_rn(__dsub_rn((double)dv[1][2][1], __dmul_rn(2.0, c0)), (double)dv[1][0][1]);
+    const double dyy = __dadd_rn(__dsub_rn((double)dv[2][1][1], __dmul_rn(2.0, c0)), (double)dv[0][1][1]);
+    const double dxy = __ddiv_rn(__dsub_rn(__dsub_rn((double)dv[2][2][1], (double)dv[2][0][1]),
+                                           __dsub_rn((double)dv[0][2][1], (double)dv[0][0][1])), 4.0);
+    const double tr = __dadd_rn(dxx, dyy);
+    const double det = __dsub_rn(__dmul_rn(dxx, dyy), __dmul_rn(dxy, dxy));
+    const double r = __ddiv_rn(__dmul_rn(tr, tr), det);
+    if (fabs(contrast) < contrast_th) hit = false;
+    if (r > ratio_th) hit = false;
+  }
+  return hit;
+}
+
+// One row: `nw` receives the reductions of the newest staged row yy; the row above it is evaluated with its own
+// centre-excluded slice maxima (`mid`, computed one step earlier) and the full slice maxima of the rows around it
+// (`old`, `nw`).  M = max over the 26 neighbours: c > M is a unique maximum (argmax == 13), c < M is no maximum,
+// c == M is a tie whose outcome depends on the position of the equal neighbour -> exact path (rare; an all-equal
+// neighbourhood, c == M == m, is decided here: the first of 27 equal values wins, not the centre).
+template <int ND>
+__device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const ExsRow<ND>& old, bool emit,
+                                         const float* __restrict__ g, size_t plane, int B, int b, int H, int W, int yy,
+                                         int x, int strip_c0, float* __restrict__ ring, int& slot, int stage_row, int filter,
+                                         double contrast_th, double ratio_th, uint32_t* __restrict__ extrema, int pitch,
+                                         int lane) {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kExsRows - 2) : "memory");
+  __syncwarp();
+  const float* srow = ring + slot * ((ND + 1) * kExsPitch) + 4 * lane;
+  float D[ND][6];
+  {
+    float prev[6];
+#pragma unroll
+    for (int l = 0; l <= ND; ++l) {
+      const float4 v = *reinterpret_cast<const float4*>(srow + l * kExsPitch + 4);
+      const float cur[6] = {srow[l * kExsPitch + 3], v.x, v.y, v.z, v.w, srow[l * kExsPitch + 8]};
+      if (l > 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) D[l - 1][i] = cur[i] - prev[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) prev[i] = cur[i];
+    }
+  }
+  // refill the slot that held row yy-1 (every lane passed the barrier above after reading it) with row yy+3
+  exs_stage_row<ND>(g, plane, H, W, stage_row, x, strip_c0, ring + ((slot + kExsRows - 1) & (kExsRows - 1)) * ((ND + 1) * kExsPitch), lane);
+  slot = (slot + 1) & (kExsRows - 1);
+  ExsMid<ND> cur;  // the newest row's centre-row quantities, needed one step from now
+#pragma unroll
+  for (int k = 1; k <= ND - 2; ++k) {
+    float bmax[6], bmin[6], amax[6], amin[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      bmax[i] = fmaxf(D[k - 1][i], D[k + 1][i]);
+      bmin[i] = fminf(D[k - 1][i], D[k + 1][i]);
+      amax[i] = fmaxf(bmax[i], D[k][i]);
+      amin[i] = fminf(bmin[i], D[k][i]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      nw.emax[k - 1][j] = max3_t<float>(amax[j], amax[j + 1], amax[j + 2]);
+      nw.emin[k - 1][j] = min3_t<float>(amin[j], amin[j + 1], amin[j + 2]);
+      // own row without the centre: levels k-1 / k+1 at x-1, x, x+1 and level k at x-1, x+1
+      cur.nmax[k - 1][j] = fmaxf(max3_t<float>(bmax[j], bmax[j + 1], bmax[j + 2]), fmaxf(D[k][j], D[k][j + 2]));
+      cur.nmin[k - 1][j] = fminf(min3_t<float>(bmin[j], bmin[j + 1], bmin[j + 2]), fminf(D[k][j], D[k][j + 2]));
+      cur.c[k - 1][j] = D[k][j + 1];
+    }
+  }
+  if (emit) {
+    const int y = yy - 1;  // the row being evaluated
+    const bool row_ok = (y >= 1) && (y <= H - 3);
+#pragma unroll
+    for (int k = 1; k <= ND - 2; ++k) {
+      uint32_t nib = 0, slow = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float M = max3_t<float>(old.emax[k - 1][j], mid.nmax[k - 1][j], nw.emax[k - 1][j]);
+        const float m = min3_t<float>(old.emin[k - 1][j], mid.nmin[k - 1][j], nw.emin[k - 1][j]);
+        const float c = mid.c[k - 1][j];
+        const bool ok = row_ok && (x + j >= 1) && (x + j <= W - 3);
+        const bool hit = ok && (c > M || c < m);
+        const bool tie = ok && !hit && (c == M || c == m) && !(c == M && c == m);
+        nib |= hit ? (1u << j) : 0u;
+        slow |= tie ? (1u << j) : 0u;
+      }
+      if (filter == FC_FILTER_SCRIPT) { slow |= nib; nib = 0u; }  // the script variant's contrast / edge tests
+      if (__any_sync(0xffffffffu, slow != 0u)) {
+        while (slow) {
+          const int j = __ffs(slow) - 1;
+          slow &= slow - 1;
+          if (exs_exact<ND>(g, plane, W, y, x + j, k, filter, contrast_th, ratio_th)) nib |= 1u << j;
+        }
+        __syncwarp();
+      }
+      uint32_t v = nib << (4 * (lane & 7));
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      v |= __shfl_xor_sync(0xffffffffu, v, 2);
+      v |= __shfl_xor_sync(0xffffffffu, v, 4);
+      if ((lane & 7) == 0 && x < W && y < H) extrema[(((size_t)(k - 1) * B + b) * H + y) * pitch + (x >> 5)] = v;
+    }
+  }
+  mid = cur;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(kExsWarps * 32, 3)
+extrema_strip_kernel(const float* __restrict__ gauss, int B, int H, int W, int rows_per_band, int filter,
+                     double contrast_th, double ratio_th, uint32_t* __restrict__ extrema, int pitch) {
+  extern __shared__ __align__(16) float exs_ring[];  // [warp][kExsRows][ND + 1][kExsPitch]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip_c0 = (blockIdx.x * kExsWarps + warp) * 128;
+  if (strip_c0 >= W) return;  // warp-uniform; the kernel has no block-wide barrier
+  const int x = strip_c0 + 4 * lane;
+  const int b = blockIdx.z;
+  const size_t plane = (size_t)H * W;
+  const float* g = gauss + (size_t)b * (ND + 1) * plane;
+  const int y0 = blockIdx.y * rows_per_band;
+  const int y1 = min(y0 + rows_per_band, H);
+  float* ring = exs_ring + warp * (kExsRows * (ND + 1) * kExsPitch);
+  // rows y0-1 .. y1 are walked; row yy is staged three steps before it is consumed
+#pragma unroll
+  for (int i = 0; i < kExsRows - 1; ++i) exs_stage_row<ND>(g, plane, H, W, y0 - 1 + i, x, strip_c0, ring + i * ((ND + 1) * kExsPitch), lane);
+  int slot = 0;
+  ExsRow<ND> R0, R1, R2;
+  ExsMid<ND> mid;
+  int yy = y0 - 1;
+#define FC_EXS(NW, OLD) \
+  exs_step<ND>(NW, mid, OLD, yy >= y0 + 1, g, plane, B, b, H, W, yy, x, strip_c0, ring, slot, yy + kExsRows - 1, filter, contrast_th, ratio_th, extrema, pitch, lane)
+  // the full-slice maxima of three consecutive rows rotate through R0, R1, R2 without moving a register
+  for (;;) {
+    FC_EXS(R0, R1); if (++yy > y1) break;
+    FC_EXS(R1, R2); if (++yy > y1) break;
+    FC_EXS(R2, R0); if (++yy > y1) break;
+  }
+#undef FC_EXS
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 template <typename T>
 __global__ void downsample2_kernel(const T* __restrict__ gauss, int L, int level, int H, int W, T* __restrict__ out,
                                    int H2, int W2) {
@@ -851,10 +1077,35 @@ static int launch_extrema_nd(const void* gauss, int B, int H, int W, int is_dog,
   return FC_OK;
 }
 
+template <int ND>
+static int launch_extrema_strip(const void* gauss, int B, int H, int W, int filter, double cth, double rth, uint32_t* extrema,
+                                cudaStream_t st) {
+  const int pitch = div_up(W, 32);
+  const size_t smem = sizeof(float) * kExsWarps * kExsRows * (ND + 1) * kExsPitch;
+  auto kern = extrema_strip_kernel<ND>;
+  FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int strips = div_up(W, 128);
+  int rows = 64;  // band height: amortise the two halo rows, but keep enough warps in flight on small inputs
+  while (rows > 8 && (int64_t)strips * div_up(H, rows) * B < 148 * 12) rows >>= 1;
+  dim3 grid(div_up(strips, kExsWarps), div_up(H, rows), B);
+  kern<<<grid, kExsWarps * 32, smem, st>>>((const float*)gauss, B, H, W, rows, filter, cth, rth, extrema, pitch);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
 template <typename T>
 static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_dog, int filter, double cth, double rth,
                           uint32_t* extrema, cudaStream_t st) {
   const int nd = is_dog ? L : L - 1;
+  if constexpr (sizeof(T) == 4) {
+    static const bool tiled_variant = getenv("FC_EXTREMA_TILED") != nullptr;  // A/B switch for profiling
+    if (!is_dog && !tiled_variant && W % 4 == 0 && H >= 3 && (reinterpret_cast<uintptr_t>(gauss) & 15) == 0) {
+      if (nd == 4) return launch_extrema_strip<4>(gauss, B, H, W, filter, cth, rth, extrema, st);
+      if (nd == 3) return launch_extrema_strip<3>(gauss, B, H, W, filter, cth, rth, extrema, st);
+      if (nd == 5) return launch_extrema_strip<5>(gauss, B, H, W, filter, cth, rth, extrema, st);
+    }
+  }
   switch (nd) {
     case 3: return launch_extrema_nd<T, 3>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
     case 4: return launch_extrema_nd<T, 4>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
