@@ -454,8 +454,8 @@ template <int ND>
 __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const ExsRow<ND>& old, bool emit,
                                          const float* __restrict__ g, size_t plane, int B, int b, int H, int W, int yy,
                                          int x, int strip_c0, float* __restrict__ ring, int& slot, int stage_row, int filter,
-                                         double contrast_th, double ratio_th, uint32_t* __restrict__ extrema, int pitch,
-                                         int lane) {
+                                         double contrast_th, double ratio_th, uint32_t*& out_p, size_t out_kstride, int pitch,
+                                         bool writer, uint32_t colmask, int lane) {
   asm volatile("cp.async.wait_group %0;" ::"n"(kExsRows - 2) : "memory");
   __syncwarp();
   const float* srow = ring + slot * ((ND + 1) * kExsPitch) + 4 * lane;
@@ -500,23 +500,36 @@ __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const 
   }
   if (emit) {
     const int y = yy - 1;  // the row being evaluated
-    const bool row_ok = (y >= 1) && (y <= H - 3);
+    // centres need 1 <= y <= H-3 and 1 <= x <= W-3 (:69-70); colmask holds the lane's valid columns
+    const uint32_t okmask = (y >= 1 && y <= H - 3) ? colmask : 0u;
 #pragma unroll
     for (int k = 1; k <= ND - 2; ++k) {
-      uint32_t nib = 0, slow = 0;
+      uint32_t cand = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float M = max3_t<float>(old.emax[k - 1][j], mid.nmax[k - 1][j], nw.emax[k - 1][j]);
         const float m = min3_t<float>(old.emin[k - 1][j], mid.nmin[k - 1][j], nw.emin[k - 1][j]);
         const float c = mid.c[k - 1][j];
-        const bool ok = row_ok && (x + j >= 1) && (x + j <= W - 3);
-        const bool hit = ok && (c > M || c < m);
-        const bool tie = ok && !hit && (c == M || c == m) && !(c == M && c == m);
-        nib |= hit ? (1u << j) : 0u;
-        slow |= tie ? (1u << j) : 0u;
+        cand |= (c >= M || c <= m) ? (1u << j) : 0u;
       }
-      if (filter == FC_FILTER_SCRIPT) { slow |= nib; nib = 0u; }  // the script variant's contrast / edge tests
-      if (__any_sync(0xffffffffu, slow != 0u)) {
+      cand &= okmask;
+      uint32_t nib = cand;
+      if (__any_sync(0xffffffffu, cand != 0u)) {
+        // rare (1-2 % of the pixels): tell unique extrema from ties; ties and the script variant's hits take the exact path
+        uint32_t slow = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float M = max3_t<float>(old.emax[k - 1][j], mid.nmax[k - 1][j], nw.emax[k - 1][j]);
+          const float m = min3_t<float>(old.emin[k - 1][j], mid.nmin[k - 1][j], nw.emin[k - 1][j]);
+          const float c = mid.c[k - 1][j];
+          const bool strict = c > M || c < m;
+          const bool flat = c == M && c == m;  // all 27 equal: the first one wins, not the centre
+          if (!strict) {
+            nib &= ~(1u << j);
+            if (!flat) slow |= cand & (1u << j);
+          }
+        }
+        if (filter == FC_FILTER_SCRIPT) { slow |= nib; nib = 0u; }  // contrast / edge tests of the script variant
         while (slow) {
           const int j = __ffs(slow) - 1;
           slow &= slow - 1;
@@ -528,8 +541,9 @@ __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const 
       v |= __shfl_xor_sync(0xffffffffu, v, 1);
       v |= __shfl_xor_sync(0xffffffffu, v, 2);
       v |= __shfl_xor_sync(0xffffffffu, v, 4);
-      if ((lane & 7) == 0 && x < W && y < H) extrema[(((size_t)(k - 1) * B + b) * H + y) * pitch + (x >> 5)] = v;
+      if (writer) out_p[(size_t)(k - 1) * out_kstride] = v;
     }
+    out_p += pitch;
   }
   mid = cur;
 }
@@ -556,8 +570,14 @@ extrema_strip_kernel(const float* __restrict__ gauss, int B, int H, int W, int r
   ExsRow<ND> R0, R1, R2;
   ExsMid<ND> mid;
   int yy = y0 - 1;
+  uint32_t colmask = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) colmask |= (x + j >= 1 && x + j <= W - 3) ? (1u << j) : 0u;
+  const bool writer = (lane & 7) == 0 && x < W;
+  const size_t out_kstride = (size_t)B * H * pitch;                      // words between the masks of k and k+1
+  uint32_t* out_p = extrema + ((size_t)b * H + y0) * pitch + (x >> 5);  // mask word of (k = 1, row y0, this lane group)
 #define FC_EXS(NW, OLD) \
-  exs_step<ND>(NW, mid, OLD, yy >= y0 + 1, g, plane, B, b, H, W, yy, x, strip_c0, ring, slot, yy + kExsRows - 1, filter, contrast_th, ratio_th, extrema, pitch, lane)
+  exs_step<ND>(NW, mid, OLD, yy >= y0 + 1, g, plane, B, b, H, W, yy, x, strip_c0, ring, slot, yy + kExsRows - 1, filter, contrast_th, ratio_th, out_p, out_kstride, pitch, writer, colmask, lane)
   // the full-slice maxima of three consecutive rows rotate through R0, R1, R2 without moving a register
   for (;;) {
     FC_EXS(R0, R1); if (++yy > y1) break;
