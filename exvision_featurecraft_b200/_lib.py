@@ -54,7 +54,8 @@ SIGNATURES = {
     "fc_convert_f64": (_i, [_p, _i64, _i, _p, _p]),
     "fc_gradient_field": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "fc_orientation_bins": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p]),
-    "fc_gradient_field_packed": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "fc_gradient_field_packed": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fc_descriptors_interleaved": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
     "fc_orientation_bins_packed": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _p]),
     "fc_orientation_scan": (_i, [_p, _i, _p, _p, _p]),
     "fc_orientation_emit": (_i, [_p, _p, _p, _i, _p, _p]),

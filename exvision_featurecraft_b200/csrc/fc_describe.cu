@@ -43,7 +43,7 @@ __device__ __forceinline__ T py_mod360(T a) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int W, T* __restrict__ mag,
-                      T* __restrict__ dir, uint8_t* __restrict__ obin, uint32_t* __restrict__ packed) {
+                      T* __restrict__ dir, T* __restrict__ mag_dir, uint8_t* __restrict__ obin, uint32_t* __restrict__ packed) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -60,8 +60,13 @@ gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int 
   // |deg| <= 180, so Python's % 360 is the identity for deg >= 0 and one rounded + 360 otherwise
   const T d = deg < T(0) ? Math<T>::add(deg, T(360)) : deg;
   const size_t o = ((size_t)b * H + y) * W + x;
-  mag[o] = m;
-  dir[o] = d;
+  if (mag_dir) {  // interleaved (magnitude, direction) pairs: one 8-byte gather per descriptor sample
+    mag_dir[2 * o] = m;
+    mag_dir[2 * o + 1] = d;
+  } else {
+    mag[o] = m;
+    dir[o] = d;
+  }
   // np.round(direction * 36 / 360): half to even, evaluated in the scale-space type on the stored direction
   if constexpr (sizeof(T) == 4) {
     const int ob = (int)rintf(__fdiv_rn(__fmul_rn(d, 36.0f), 360.0f));
@@ -103,7 +108,8 @@ __device__ __forceinline__ float atan2_degrees_0_360(float y, float x) {
 
 __global__ void __launch_bounds__(256)
 gradient_field4_kernel(const float* __restrict__ gauss, int L, int level, int H, int W, float* __restrict__ mag,
-                       float* __restrict__ dir, uint8_t* __restrict__ obin, uint32_t* __restrict__ packed) {
+                       float* __restrict__ dir, float* __restrict__ mag_dir, uint8_t* __restrict__ obin,
+                       uint32_t* __restrict__ packed) {
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -131,8 +137,13 @@ gradient_field4_kernel(const float* __restrict__ gauss, int L, int level, int H,
     pk[i] = ((__float_as_uint(m[i]) + 32u) & ~63u) | (uint32_t)ob[i];
   }
   const size_t o = ((size_t)b * H + y) * W + x;
-  *reinterpret_cast<float4*>(mag + o) = make_float4(m[0], m[1], m[2], m[3]);
-  *reinterpret_cast<float4*>(dir + o) = make_float4(a[0], a[1], a[2], a[3]);
+  if (mag_dir) {
+    reinterpret_cast<float4*>(mag_dir + 2 * o)[0] = make_float4(m[0], a[0], m[1], a[1]);
+    reinterpret_cast<float4*>(mag_dir + 2 * o)[1] = make_float4(m[2], a[2], m[3], a[3]);
+  } else {
+    *reinterpret_cast<float4*>(mag + o) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(dir + o) = make_float4(a[0], a[1], a[2], a[3]);
+  }
   if (obin) *reinterpret_cast<uchar4*>(obin + o) = make_uchar4((unsigned char)ob[0], (unsigned char)ob[1], (unsigned char)ob[2], (unsigned char)ob[3]);
   if (packed) *reinterpret_cast<uint4*>(packed + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
@@ -305,7 +316,8 @@ static constexpr int kTrigStride = 2 + 32;
 
 // Persistent: every CTA converts the host tables once (Gaussian mask, bin edges, the fixed-point column deltas as
 // int32, cos / sin) into shared memory, then its warps walk the oriented keypoints with stride = warps in the grid.
-template <typename T, typename OUT>
+// IL: `mag` holds interleaved (magnitude, direction) pairs (fc_gradient_field_packed), `dir` is unused
+template <typename T, typename OUT, bool IL>
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, int W, const int32_t* __restrict__ oriented,
                   int n_oriented, const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc) {
@@ -352,8 +364,8 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
 #pragma unroll
     for (int k = 0; k < 9; ++k) myh[k * 32] = ACC(0);
     __syncwarp();
-    const T* m = mag + (size_t)b * H * W;
-    const T* d = dir + (size_t)b * H * W;
+    const T* m = mag + (size_t)b * H * W * (IL ? 2 : 1);
+    const T* d = IL ? nullptr : dir + (size_t)b * H * W;
     const int4 ad4 = *reinterpret_cast<const int4*>(&sAd[bin][cx]);
     const int4 bd4 = *reinterpret_cast<const int4*>(&sBd[bin][cx]);
     const int ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w}, bd[4] = {bd4.x, bd4.y, bd4.z, bd4.w};
@@ -369,13 +381,14 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
       for (int rx = 0; rx < 4; ++rx) {
         const int X = (X0 + ad[rx]) >> 10;
         const int Y = (Y0 + bd[rx]) >> 10;
-        if (interior) {
-          const int o = Y * W + X;  // one image plane has fewer than 2^31 pixels (checked on the host)
-          mv[ry][rx] = m[o];
-          dv[ry][rx] = d[o];
+        const bool in = interior || (((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H));
+        const int o = in ? Y * W + X : 0;  // one image plane has fewer than 2^30 pixels (checked on the host)
+        if constexpr (IL) {
+          static_assert(!IL || sizeof(T) == 4, "interleaved planes are float32");
+          const float2 v = reinterpret_cast<const float2*>(m)[o];
+          mv[ry][rx] = in ? (T)v.x : T(0);
+          dv[ry][rx] = in ? (T)v.y : T(0);
         } else {
-          const bool in = ((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H);
-          const int o = in ? Y * W + X : 0;
           mv[ry][rx] = in ? m[o] : T(0);
           dv[ry][rx] = in ? d[o] : T(0);
         }
@@ -496,23 +509,27 @@ extern "C" int fc_rotated_window(const double* image, int height, int width, dou
 }
 
 static int launch_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
-                                 void* magnitude, void* direction, uint8_t* orientation_bin, uint32_t* packed, void* stream) {
-  if (!gauss || !magnitude || !direction || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+                                 void* magnitude, void* direction, void* mag_dir, uint8_t* orientation_bin, uint32_t* packed,
+                                 void* stream) {
+  if (!gauss || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (!mag_dir && (!magnitude || !direction)) return FC_ERR_BAD_ARG;
   if (level < 0 || level >= n_levels) return FC_ERR_BAD_ARG;
   dim3 grid(div_up(width, 256), height, batch);
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec_ok = (width % 4 == 0) && (((reinterpret_cast<uintptr_t>(gauss) | reinterpret_cast<uintptr_t>(magnitude) |
-                                            reinterpret_cast<uintptr_t>(direction) | reinterpret_cast<uintptr_t>(packed)) & 15) == 0) &&
+                                            reinterpret_cast<uintptr_t>(direction) | reinterpret_cast<uintptr_t>(mag_dir) |
+                                            reinterpret_cast<uintptr_t>(packed)) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(orientation_bin) & 3) == 0);
   if (dtype == FC_F32 && vec_ok)
     gradient_field4_kernel<<<dim3(div_up(width, 1024), height, batch), 256, 0, st>>>(
-        (const float*)gauss, n_levels, level, height, width, (float*)magnitude, (float*)direction, orientation_bin, packed);
+        (const float*)gauss, n_levels, level, height, width, (float*)magnitude, (float*)direction, (float*)mag_dir,
+        orientation_bin, packed);
   else if (dtype == FC_F32)
-    gradient_field_kernel<float><<<grid, 256, 0, st>>>((const float*)gauss, n_levels, level, height, width,
-                                                       (float*)magnitude, (float*)direction, orientation_bin, packed);
-  else if (dtype == FC_F64 && orientation_bin && !packed)
+    gradient_field_kernel<float><<<grid, 256, 0, st>>>((const float*)gauss, n_levels, level, height, width, (float*)magnitude,
+                                                       (float*)direction, (float*)mag_dir, orientation_bin, packed);
+  else if (dtype == FC_F64 && orientation_bin && !packed && !mag_dir)
     gradient_field_kernel<double><<<grid, 256, 0, st>>>((const double*)gauss, n_levels, level, height, width,
-                                                        (double*)magnitude, (double*)direction, orientation_bin, nullptr);
+                                                        (double*)magnitude, (double*)direction, nullptr, orientation_bin, nullptr);
   else
     return FC_ERR_BAD_ARG;
   note_launch();
@@ -523,15 +540,15 @@ static int launch_gradient_field(const void* gauss, int dtype, int batch, int n_
 extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
                                  void* magnitude, void* direction, uint8_t* orientation_bin, void* stream) {
   if (!orientation_bin) return FC_ERR_BAD_ARG;
-  return launch_gradient_field(gauss, dtype, batch, n_levels, level, height, width, magnitude, direction, orientation_bin,
-                               nullptr, stream);
+  return launch_gradient_field(gauss, dtype, batch, n_levels, level, height, width, magnitude, direction, nullptr,
+                               orientation_bin, nullptr, stream);
 }
 
 extern "C" int fc_gradient_field_packed(const void* gauss, int batch, int n_levels, int level, int height, int width,
-                                        void* magnitude, void* direction, uint32_t* magnitude_bin, void* stream) {
-  if (!magnitude_bin) return FC_ERR_BAD_ARG;
-  return launch_gradient_field(gauss, FC_F32, batch, n_levels, level, height, width, magnitude, direction, nullptr,
-                               magnitude_bin, stream);
+                                        void* magnitude_direction, uint32_t* magnitude_bin, void* stream) {
+  if (!magnitude_direction || !magnitude_bin) return FC_ERR_BAD_ARG;
+  return launch_gradient_field(gauss, FC_F32, batch, n_levels, level, height, width, nullptr, nullptr, magnitude_direction,
+                               nullptr, magnitude_bin, stream);
 }
 
 static int launch_orientation(const void* magnitude, const uint8_t* orientation_bin, int dtype, bool packed, int batch,
@@ -604,14 +621,15 @@ extern "C" int fc_orientation_emit(const int32_t* keypoints, const uint64_t* bin
   return FC_OK;
 }
 
-extern "C" int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
-                              const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
+static int launch_descriptors(const void* magnitude, const void* direction, bool interleaved, int dtype, int batch, int height,
+                              int width, const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
                               void* descriptors, int out_dtype, void* stream) {
-  if (!magnitude || !direction || !gmask || !trig || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (!magnitude || (!interleaved && !direction) || !gmask || !trig || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
   if (n_oriented == 0) return FC_OK;
   if (!oriented || !descriptors || n_oriented < 0) return FC_ERR_BAD_ARG;
-  if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
+  if ((int64_t)height * width > 0x3fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
   if (reinterpret_cast<uintptr_t>(oriented) & 15) return FC_ERR_BAD_ARG;
+  if (interleaved && (reinterpret_cast<uintptr_t>(magnitude) & 7)) return FC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   // persistent grid: as many CTAs as are resident at once (occupancy query per instantiation), fewer when there is less work
   static int n_sm = 0;
@@ -620,23 +638,40 @@ extern "C" int fc_descriptors(const void* magnitude, const void* direction, int 
     FC_CUDA_TRY(cudaGetDevice(&dev));
     FC_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-#define FC_LAUNCH(T, OUT)                                                                                         \
+#define FC_LAUNCH(T, OUT, IL)                                                                                     \
   do {                                                                                                            \
     static int per_sm = 0;                                                                                        \
     if (per_sm == 0)                                                                                              \
-      FC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descriptor_kernel<T, OUT>, kDescWarps * 32, 0)); \
+      FC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descriptor_kernel<T, OUT, IL>, kDescWarps * 32, 0)); \
     const int want = div_up(n_oriented, kDescWarps);                                                              \
     const int blocks = want < n_sm * per_sm ? want : n_sm * per_sm;                                               \
-    descriptor_kernel<T, OUT><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
-                                                                 width, oriented, n_oriented, gmask, trig, (OUT*)descriptors); \
+    descriptor_kernel<T, OUT, IL><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
+                                                                     width, oriented, n_oriented, gmask, trig, (OUT*)descriptors); \
   } while (0)
-  if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float);
-  else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double);
-  else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float);
-  else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double);
+  if (interleaved && dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, true);
+  else if (interleaved && dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, true);
+  else if (interleaved) return FC_ERR_BAD_ARG;
+  else if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, false);
+  else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, false);
+  else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float, false);
+  else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double, false);
   else return FC_ERR_BAD_ARG;
 #undef FC_LAUNCH
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
+}
+
+extern "C" int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
+                              const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
+                              void* descriptors, int out_dtype, void* stream) {
+  return launch_descriptors(magnitude, direction, false, dtype, batch, height, width, oriented, n_oriented, gmask, trig,
+                            descriptors, out_dtype, stream);
+}
+
+extern "C" int fc_descriptors_interleaved(const void* magnitude_direction, int batch, int height, int width,
+                                          const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
+                                          void* descriptors, int out_dtype, void* stream) {
+  return launch_descriptors(magnitude_direction, nullptr, true, FC_F32, batch, height, width, oriented, n_oriented, gmask, trig,
+                            descriptors, out_dtype, stream);
 }

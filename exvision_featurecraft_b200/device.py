@@ -25,6 +25,12 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def base_ptr(t):
+    """Device pointer of the first element of a (possibly strided) CUDA tensor view."""
+    assert t.is_cuda
+    return C.c_void_p(t.data_ptr())
+
+
 def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import ptr, read_int, read_last_ints, require_cuda, scan_scratch, stream_ptr, to_device
+from .device import base_ptr, ptr, read_int, read_last_ints, require_cuda, scan_scratch, stream_ptr, to_device
 
 
 @dataclass(frozen=True)
@@ -368,16 +368,19 @@ def keypoints_from_mask(mask: torch.Tensor, width: int) -> torch.Tensor:
 
 
 def gradient_field(octv: Octave, level: int, params: SiftParams):
-    """sift_gradient of one level -> (magnitude, direction, orientation operand).  The orientation operand is the
-    uint8 bin plane in f64 mode and the packed magnitude|bin int32 plane in f32 mode (one gather per sample)."""
+    """sift_gradient of one level -> (magnitude, direction, orientation operand).
+
+    f64 mode: three dense planes (the uint8 bin plane is the orientation operand).  f32 mode: magnitude and direction
+    are the two halves of ONE interleaved [b, h, w, 2] plane (returned as strided views, so that a descriptor sample
+    is a single 8-byte gather) and the orientation operand is the packed magnitude|bin int32 plane."""
     b, L, h, w = octv.gauss.shape
+    if params.fc_dtype == _lib.FC_F32:
+        md = torch.empty((b, h, w, 2), dtype=torch.float32, device=octv.gauss.device)
+        packed = torch.empty((b, h, w), dtype=torch.int32, device=md.device)
+        _lib.call("fc_gradient_field_packed", ptr(octv.gauss), b, L, level, h, w, ptr(md), ptr(packed), stream_ptr())
+        return md[..., 0], md[..., 1], packed
     mag = torch.empty((b, h, w), dtype=octv.gauss.dtype, device=octv.gauss.device)
     direction = torch.empty_like(mag)
-    if params.fc_dtype == _lib.FC_F32:
-        packed = torch.empty((b, h, w), dtype=torch.int32, device=mag.device)
-        _lib.call("fc_gradient_field_packed", ptr(octv.gauss), b, L, level, h, w, ptr(mag), ptr(direction), ptr(packed),
-                  stream_ptr())
-        return mag, direction, packed
     obin = torch.empty((b, h, w), dtype=torch.uint8, device=mag.device)
     _lib.call("fc_gradient_field", ptr(octv.gauss), params.fc_dtype, b, L, level, h, w, ptr(mag), ptr(direction), ptr(obin),
               stream_ptr())
@@ -424,8 +427,14 @@ def describe(mag, direction, oriented, sigma, params: SiftParams, out_dtype=torc
     gmask = _cached(("gmask", float(sigma)), lambda: gaussian_mask16(sigma))
     trig = _cached(("trig",), trig_table)
     b, h, w = mag.shape
-    _lib.call("fc_descriptors", ptr(mag), ptr(direction), params.fc_dtype, b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig),
-              ptr(desc), _lib.FC_F32 if out_dtype == torch.float32 else _lib.FC_F64, stream_ptr())
+    out_fc = _lib.FC_F32 if out_dtype == torch.float32 else _lib.FC_F64
+    if mag.stride(-1) == 2:  # halves of gradient_field's interleaved plane: mag.data_ptr() is the plane itself
+        assert direction.data_ptr() == mag.data_ptr() + mag.element_size()
+        _lib.call("fc_descriptors_interleaved", base_ptr(mag), b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig), ptr(desc), out_fc,
+                  stream_ptr())
+    else:
+        _lib.call("fc_descriptors", ptr(mag), ptr(direction), params.fc_dtype, b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig),
+                  ptr(desc), out_fc, stream_ptr())
     return desc
 
 

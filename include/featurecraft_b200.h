@@ -168,11 +168,12 @@ FC_API int fc_convert_f64(const double* src, int64_t n, int dtype, void* dst, vo
 FC_API int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
                       void* magnitude, void* direction, uint8_t* orientation_bin, void* stream);
 
-/* The same gradient field for the float32 pipeline, with the orientation operand packed for a single gather:
- * magnitude_bin[b][y][x] = (bits of magnitude rounded to 18 mantissa bits) | orientation_bin (low 6 bits).
- * magnitude and direction are written in full float32 as above (the descriptor stage reads those). */
+/* The same gradient field laid out for the float32 pipeline's gathers:
+ * magnitude_direction[b][y][x] = (magnitude, direction) as interleaved float32 pairs (one 8-byte gather per
+ * descriptor sample), magnitude_bin[b][y][x] = (bits of magnitude rounded to 18 mantissa bits) | orientation_bin
+ * in the low 6 bits (one 4-byte gather per orientation sample). */
 FC_API int fc_gradient_field_packed(const void* gauss, int batch, int n_levels, int level, int height, int width,
-                             void* magnitude, void* direction, uint32_t* magnitude_bin, void* stream);
+                             void* magnitude_direction, uint32_t* magnitude_bin, void* stream);
 
 /* dog_keypoints_orientations (:116-172) for one (octave, scale): keypoints are (image, row, col)
  * int32 triples in reference order; `weights` is gaussian_filter_kernel(sigma) as a dense (2r+1)^2 device
@@ -203,6 +204,10 @@ FC_API int fc_orientation_emit(const int32_t* keypoints, const uint64_t* bin_mas
 FC_API int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
                    const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
                    void* descriptors, int out_dtype, void* stream);
+/* float32 pipeline: the same descriptors from fc_gradient_field_packed's interleaved (magnitude, direction) plane. */
+FC_API int fc_descriptors_interleaved(const void* magnitude_direction, int batch, int height, int width,
+                               const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
+                               void* descriptors, int out_dtype, void* stream);
 
 /* rotated_subimage (:175-212) on its own: nearest-neighbour window of out_width x out_height (<= 1024
  * samples) around (center_x, center_y) with cv2.warpAffine's 10-bit fixed-point coordinates; the caller
