@@ -305,6 +305,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
+    from exvision_featurecraft_b200 import sharding
+
+    numa_bound = sharding.bind_to_gpu_numa(local)  # before any pinned staging buffer is allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from exvision_featurecraft_b200 import _lib
@@ -404,11 +407,15 @@ def main():
                 "roofline": {"kernel": kname, "bound": bound, "achieved": ach, "peak": peak, "unit": punit,
                              "frac": (ach / peak) if ach else None, "traffic": traffic,
                              "peak_source": src, "kernel_ms": kms, "algorithmic_per_launch": alg},
-                "clocks": clocks, "pcie": pcie}
+                "clocks": clocks, "pcie": pcie, "numa_bound": bool(numa_bound)}
         extra = getattr(wl, "extra", None)
         if extra:
             line["stages"] = extra() if callable(extra) else extra
         if not args.no_cpu_baseline:
+            try:  # the CPU arm uses every host core again (the GPU arm was pinned next to its GPU)
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))
+            except OSError:
+                pass
             cores = os.cpu_count() or 1
             n_items = getattr(wl, "cpu_sample_items", cores)
             wall, res = cpu_pool_run(wl.cpu_task, wl.cpu_items(n_items), min(cores, n_items))
