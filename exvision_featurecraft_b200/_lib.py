@@ -43,6 +43,10 @@ SIGNATURES = {
     "fc_scan_scratch_elems": (_i64, [_i64]),
     "fc_mask_scan": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "fc_publish_i32": (_i, [_p, _p, _i, _p]),
+    "fc_mask_row_count": (_i, [_p, _i, _i, _i, _p, _p]),
+    "fc_popcount_u64": (_i, [_p, _i64, _p, _p]),
+    "fc_exclusive_scan_i32": (_i, [_p, _i64, _p, _p, _p]),
+    "fc_publish_gather_i32": (_i, [_p, _p, _i, _p, _p]),
     "fc_mask_emit": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "fc_mask_emit_keypoints": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "fc_gauss_octave": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _d, _d, _p, _p, _p]),

@@ -1050,6 +1050,16 @@ extern "C" int fc_mask_scan(const uint32_t* mask, int batch, int height, int wid
   return exclusive_scan_i32(scratch, rows, row_offsets, scratch + rows, st);
 }
 
+// counts[i] = set bits of mask row i (the first half of fc_mask_scan), for callers that scan several masks at once
+extern "C" int fc_mask_row_count(const uint32_t* mask, int batch, int height, int width, int32_t* counts, void* stream) {
+  if (bad_image_args(mask, batch, height, width) || !counts) return FC_ERR_BAD_ARG;
+  const int64_t rows = (int64_t)batch * height;
+  mask_row_count_kernel<<<(unsigned)div_up64(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(mask, rows, div_up(width, 32), counts);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
 extern "C" int fc_mask_emit(const uint32_t* mask, const int32_t* row_offsets, int batch, int height, int width,
                             const double* map, int32_t* coords, double* values, void* stream) {
   if (bad_image_args(mask, batch, height, width) || !row_offsets || !coords) return FC_ERR_BAD_ARG;

@@ -102,6 +102,48 @@ __global__ void publish_i32_kernel(const int32_t* __restrict__ src, volatile int
 }
 }  // namespace fc
 
+namespace fc {
+struct GatherIdx {
+  long long idx[32];
+};
+__global__ void publish_gather_i32_kernel(const int32_t* __restrict__ src, GatherIdx g, volatile int32_t* __restrict__ dst_host, int n) {
+  const int i = threadIdx.x;
+  if (i < n) dst_host[i] = src[g.idx[i]];
+  __threadfence_system();
+}
+__global__ void popcount_u64_kernel(const unsigned long long* __restrict__ m, long long n, int32_t* __restrict__ counts) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) counts[i] = __popcll(m[i]);
+}
+}  // namespace fc
+
+// dst_host_pinned[i] = src[indices_host[i]], i < n <= 32, with ONE launch: the output sizes of all (octave, scale) blocks
+// of a batch are the values of one concatenated scan at the block boundaries.
+extern "C" int fc_publish_gather_i32(const int32_t* src, const int64_t* indices_host, int n, int32_t* dst_host_pinned, void* stream) {
+  if (!src || !indices_host || !dst_host_pinned || n <= 0 || n > 32) return FC_ERR_BAD_ARG;
+  fc::GatherIdx g;
+  for (int i = 0; i < 32; ++i) g.idx[i] = i < n ? (long long)indices_host[i] : 0;
+  fc::publish_gather_i32_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(src, g, dst_host_pinned, n);
+  fc::note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+// out[i] = sum(in[0..i)), i in [0, n]: the scan behind fc_mask_scan / fc_orientation_scan on its own, so that the counts of
+// several masks (or bin-mask arrays) can be concatenated and scanned with one call.
+extern "C" int fc_exclusive_scan_i32(const int32_t* in, int64_t n, int32_t* out, int32_t* scratch, void* stream) {
+  if (!in || !out || n < 0 || (n > 2048 && !scratch)) return FC_ERR_BAD_ARG;
+  return fc::exclusive_scan_i32(in, n, out, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int fc_popcount_u64(const uint64_t* masks, int64_t n, int32_t* counts, void* stream) {
+  if (!masks || !counts || n <= 0) return FC_ERR_BAD_ARG;
+  fc::popcount_u64_kernel<<<(unsigned)fc::div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)masks, n, counts);
+  fc::note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
 extern "C" int fc_publish_i32(const int32_t* src, int32_t* dst_host_pinned, int n, void* stream) {
   if (!src || !dst_host_pinned || n <= 0) return FC_ERR_BAD_ARG;
   fc::publish_i32_kernel<<<fc::div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(src, dst_host_pinned, n);

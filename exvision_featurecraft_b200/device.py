@@ -74,6 +74,23 @@ def read_last_ints(tensors) -> list:
     return [int(v) for v in host[: len(tensors)].tolist()]
 
 
+def read_ints_at(t: torch.Tensor, indices) -> list:
+    """[int(t[i]) for i in indices] (int32 CUDA tensor, at most 32 indices) with ONE kernel launch and ONE host
+    synchronisation: the values are gathered into pinned host memory by a kernel (see read_int)."""
+    assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and 0 < len(indices) <= 32
+    key = (t.device.index, torch.cuda.current_stream().cuda_stream)
+    slot = _PINNED_SLOTS.get(key)
+    if slot is None or slot[0].numel() < 32:
+        slot = (torch.zeros(32, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        _PINNED_SLOTS[key] = slot
+    host, ev = slot
+    idx = (C.c_int64 * len(indices))(*[int(i) for i in indices])
+    _lib.call("fc_publish_gather_i32", C.c_void_p(t.data_ptr()), idx, len(indices), C.c_void_p(host.data_ptr()), stream_ptr())
+    ev.record()
+    ev.synchronize()
+    return [int(v) for v in host[: len(indices)].tolist()]
+
+
 def read_int(t: torch.Tensor, index: int = -1) -> int:
     """int(t[index]) for an int32 CUDA tensor WITHOUT a D2H memcpy: a kernel stores the value into pinned host
     memory and the host waits on an event.  A 4-byte cudaMemcpy would queue behind any bulk device-to-host

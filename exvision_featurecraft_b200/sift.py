@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import base_ptr, ptr, read_int, read_last_ints, require_cuda, scan_scratch, stream_ptr, to_device
+from .device import base_ptr, ptr, read_int, read_ints_at, read_last_ints, require_cuda, scan_scratch, stream_ptr, to_device
 
 
 @dataclass(frozen=True)
@@ -490,48 +490,77 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     work = [(o, k) for o in range(params.n_octaves) for k in scales]
     if not work:
         return res
-    # B: row-major compaction offsets of every extrema mask, then one sync for the counts
+    # B: row-major compaction offsets.  The row counts of every (octave, scale) mask go into ONE concatenated array,
+    # one scan covers them all and one gather launch brings the cumulative keypoint counts at the block boundaries to
+    # the host: keypoints of all blocks then live in one list, block after block, in the reference's order.
+    n_blocks = len(work)
+    if n_blocks > 32:
+        raise ValueError("more than 32 (octave, scale) blocks")
+    rows = [octaves[o].gauss.shape[0] * octaves[o].height for o, _ in work]
+    row_start = [0]
+    for r in rows:
+        row_start.append(row_start[-1] + r)
     with _stage("compact"):
-        row_offs = [_mask_scan(octaves[o].extrema[k - 1], octaves[o].width) for o, k in work]
-        n_kps = read_last_ints(row_offs)
-    # C: keypoints, gradient fields, orientation histograms, scans of the per-keypoint orientation counts
+        counts = torch.empty(row_start[-1], dtype=torch.int32, device=dev)
+        for i, (o, k) in enumerate(work):
+            octv = octaves[o]
+            _lib.call("fc_mask_row_count", ptr(octv.extrema[k - 1]), octv.gauss.shape[0], octv.height, octv.width,
+                      ptr(counts[row_start[i]:]), stream_ptr())
+        row_offs = torch.empty(row_start[-1] + 1, dtype=torch.int32, device=dev)
+        _lib.call("fc_exclusive_scan_i32", ptr(counts), row_start[-1], ptr(row_offs), ptr(scan_scratch(row_start[-1])), stream_ptr())
+        kp_end = read_ints_at(row_offs, row_start[1:])  # cumulative keypoint count after each block
+    kp_start = [0] + kp_end[:-1]
+    total_kp = kp_end[-1]
+    kps_all = torch.empty((total_kp, 3), dtype=torch.int32, device=dev)
+    bin_mask_all = torch.empty(max(total_kp, 1), dtype=torch.int64, device=dev)
+    # C: keypoints, gradient fields, orientation histograms of every block; then ONE scan of all per-keypoint
+    # orientation counts and one gather for the cumulative oriented counts
     state = []
-    for (o, k), ro, n in zip(work, row_offs, n_kps):
+    for i, (o, k) in enumerate(work):
         octv = octaves[o]
         b, h = octv.gauss.shape[0], octv.height
-        kps = torch.empty((n, 3), dtype=torch.int32, device=dev)
+        n = kp_end[i] - kp_start[i]
+        kps = kps_all[kp_start[i]:kp_end[i]]
         blk = ScaleBlock(o, k, kps)
         res.blocks.append(blk)
         if n == 0:
             state.append(None)
             continue
         with _stage("compact"):
-            _lib.call("fc_mask_emit_keypoints", ptr(octv.extrema[k - 1]), ptr(ro), b, h, octv.width, ptr(kps), stream_ptr())
+            # the row offsets are positions in the concatenated list: emit through its base pointer
+            _lib.call("fc_mask_emit_keypoints", ptr(octv.extrema[k - 1]), ptr(row_offs[row_start[i]:]), b, h, octv.width,
+                      ptr(kps_all), stream_ptr())
         sigma = keypoint_sigma(params.sigma_base, o, k, params.s_value)
         with _stage("gradient_field"):
             mag, direction, obin = gradient_field(octv, k, params)
         with _stage("orientation"):
             radius, weights = _orientation_weights(sigma, params)
-            bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
-            orientation_bins(mag, obin, kps, n, weights, radius, bin_mask, params)
-            offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
-            scratch = scan_scratch(n)
-            _lib.call("fc_orientation_scan", ptr(bin_mask), n, ptr(offsets), ptr(scratch), stream_ptr())
-        state.append((mag, direction, bin_mask, offsets, sigma))
-    live = [st for st in state if st is not None]
+            orientation_bins(mag, obin, kps, n, weights, radius, bin_mask_all[kp_start[i]:kp_end[i]], params)
+        state.append((mag, direction, sigma))
+    if total_kp == 0:
+        for blk in res.blocks:
+            blk.oriented = torch.empty((0, 4), dtype=torch.int32, device=dev)
+            blk.descriptors = torch.empty((0, 128), dtype=out_dtype, device=dev)
+        return res
     with _stage("orientation"):
-        totals = iter(read_last_ints([st[3] for st in live]))
-    # D: oriented keypoint lists and descriptors
-    for blk, st in zip(res.blocks, state):
+        ori_counts = torch.empty(total_kp, dtype=torch.int32, device=dev)
+        _lib.call("fc_popcount_u64", ptr(bin_mask_all), total_kp, ptr(ori_counts), stream_ptr())
+        ori_offs = torch.empty(total_kp + 1, dtype=torch.int32, device=dev)
+        _lib.call("fc_exclusive_scan_i32", ptr(ori_counts), total_kp, ptr(ori_offs), ptr(scan_scratch(total_kp)), stream_ptr())
+        ori_end = read_ints_at(ori_offs, kp_end)  # cumulative oriented-keypoint count after each block
+    ori_start = [0] + ori_end[:-1]
+    oriented_all = torch.empty((max(ori_end[-1], 1), 4), dtype=torch.int32, device=dev)
+    # D: oriented keypoint lists (every array is concatenated in block order, so ONE launch expands them all) and
+    # descriptors
+    if ori_end[-1] > 0:
+        with _stage("orientation"):
+            _lib.call("fc_orientation_emit", ptr(kps_all), ptr(bin_mask_all), ptr(ori_offs), total_kp, ptr(oriented_all), stream_ptr())
+    for i, (blk, st) in enumerate(zip(res.blocks, state)):
+        blk.oriented = oriented_all[ori_start[i]:ori_end[i]]
         if st is None:
+            blk.descriptors = torch.empty((0, 128), dtype=out_dtype, device=dev)
             continue
-        mag, direction, bin_mask, offsets, sigma = st
-        total = next(totals)
-        n = blk.keypoints.shape[0]
-        blk.oriented = torch.empty((total, 4), dtype=torch.int32, device=dev)
-        if total:
-            with _stage("orientation"):
-                _lib.call("fc_orientation_emit", ptr(blk.keypoints), ptr(bin_mask), ptr(offsets), n, ptr(blk.oriented), stream_ptr())
+        mag, direction, sigma = st
         with _stage("descriptors"):
             blk.descriptors = describe(mag, direction, blk.oriented, sigma, params, out_dtype)
     return res

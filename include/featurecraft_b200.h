@@ -109,6 +109,16 @@ FC_API int fc_mask_scan(const uint32_t* mask, int batch, int height, int width, 
 /* Copy n int32 from device memory to PINNED host memory by a kernel store (UVA pointer), not by the D2H copy
  * engine: the way the host mirrors read output sizes without queueing behind bulk result transfers. */
 FC_API int fc_publish_i32(const int32_t* src, int32_t* dst_host_pinned, int n, void* stream);
+/* The pieces of fc_mask_scan / fc_orientation_scan on their own, for the batched driver: the per-row (per-keypoint)
+ * counts of several masks are written into ONE concatenated array, scanned with one call, and the totals of all
+ * blocks (the scan values at the block boundaries, indices given by the host) reach pinned host memory with one
+ * launch.  Row offsets taken from such a scan are positions in the concatenated output list, so fc_mask_emit* /
+ * fc_orientation_emit are called with the base pointer of that list.
+ * fc_exclusive_scan_i32: out[i] = sum(in[0..i)), i in [0, n]; scratch: fc_scan_scratch_elems(n) int32. */
+FC_API int fc_mask_row_count(const uint32_t* mask, int batch, int height, int width, int32_t* counts, void* stream);
+FC_API int fc_popcount_u64(const uint64_t* masks, int64_t n, int32_t* counts, void* stream);
+FC_API int fc_exclusive_scan_i32(const int32_t* in, int64_t n, int32_t* out, int32_t* scratch, void* stream);
+FC_API int fc_publish_gather_i32(const int32_t* src, const int64_t* indices_host, int n, int32_t* dst_host_pinned, void* stream);
 
 /* coords: [total][2] int32 (row, col); values (optional): map gathered at those pixels. */
 FC_API int fc_mask_emit(const uint32_t* mask, const int32_t* row_offsets, int batch, int height, int width,
