@@ -85,6 +85,44 @@ def test_scale_space_f32_within_tolerance(S, case):
     assert n_common >= 0.99 * n_ref
 
 
+@pytest.mark.parametrize("kind", ["smooth", "ties"])
+@pytest.mark.parametrize("variant", ["app", "script"])
+def test_extrema_strip_kernel_is_exact(S, kind, variant):
+    """The float32 strip kernel (register max/min of the 26 neighbours, exact path only for ties) must return exactly
+    the reference rule evaluated on the same float32 DoG values -- including inputs that are full of ties."""
+    import torch
+
+    from exvision_featurecraft_b200 import _lib
+    from exvision_featurecraft_b200.device import ptr, stream_ptr
+    from oracle import featurecraft_oracle as O
+
+    rng = np.random.default_rng(5)
+    B, L, H, W = 2, 5, 70, 328  # three 128-column strips (the last one partial), several row bands
+    if kind == "smooth":
+        base = rng.random((B, 1, H, W))
+        g = np.cumsum(base + 0.05 * rng.standard_normal((B, L, H, W)), axis=1)
+    else:
+        g = rng.integers(0, 3, size=(B, L, H, W)).astype(np.float64)  # DoG values in {-2..2}: ties everywhere
+        g[:, :, 20:40, 100:200] = 1.0                                   # and an all-equal region
+    g32 = torch.from_numpy(g.astype(np.float32)).cuda().contiguous()
+    mask = torch.zeros((L - 3, B, H, (W + 31) // 32), dtype=torch.int32, device="cuda")
+    filt = _lib.FC_FILTER_SCRIPT if variant == "script" else _lib.FC_FILTER_APP
+    _lib.call("fc_gauss_octave_extrema", ptr(g32), _lib.FC_F32, B, H, W, L, filt, 0.03, 10.0, ptr(mask), stream_ptr())
+    got = mask.cpu().numpy().view(np.uint32)
+    gh = g32.cpu().numpy()
+    for b in range(B):
+        dogs = [gh[b, l + 1] - gh[b, l] for l in range(L - 1)]  # float32 subtraction, as on the device
+        for k in (1, 2):
+            ref = O.extrema_mask(dogs[k - 1], dogs[k], dogs[k + 1])
+            if variant == "script":
+                ref = O.script_filter_mask(ref, [d.astype(np.float64) for d in dogs], k, 0.03, 10.0)
+            bits = np.unpackbits(got[k - 1, b].view(np.uint8), axis=-1, bitorder="little")[:, :W].astype(bool)
+            assert np.array_equal(bits, ref), (kind, variant, b, k, int((bits != ref).sum()))
+        if kind == "ties":
+            assert ref.sum() >= 0  # exercised; the all-equal block has no extrema
+            assert not bits[22:38, 102:198].any()
+
+
 def test_gradient_field(S):
     g = load_golden("sift_pieces")
     img = g["img"]
