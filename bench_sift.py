@@ -19,7 +19,7 @@ class SiftWorkload:
     cpu_sample_note = "(256x256 crops of the same generator, oracle with separable blurs: the reference's direct 2-D convolution is ~5x slower and a 1024x1024 image takes ~5 min per core)"
 
     def __init__(self, args):
-        self.batch = args.batch or 8
+        self.batch = args.batch or 16
         self.mode = getattr(args, "sift_dtype", None) or "f32"
         self.dtype = self.mode
 
@@ -43,7 +43,10 @@ class SiftWorkload:
         host = np.concatenate([imgs] * ((self.batch + len(imgs) - 1) // len(imgs)))[: self.batch]
         self.host_in = torch.from_numpy(np.ascontiguousarray(host)).pin_memory()
         self.dev_in = self.host_in.cuda(non_blocking=True)
-        self.timer = sift.StageTimer()
+        # inside the timed region only the dominant kernel is bracketed by CUDA events (one pair per step); the full
+        # per-stage breakdown comes from extra untimed steps afterwards (two events per stage and block are ~0.5 ms of
+        # host time per step, which would be charged to `value`)
+        self.timer = sift.StageTimer(only={"pyramid_o0"})
         self.recorded_steps = 0
 
     def _run(self, dev_in):
@@ -98,8 +101,16 @@ class SiftWorkload:
         return tr["gauss_octave_packed_kernel"]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W) * (2 if self.mode == "f64" else 1)
 
     def extra(self):
-        n = max(self.recorded_steps, 1)
-        return {k: round(v / n, 4) for k, v in sorted(self.timer.totals().items())}
+        full = self.sift.StageTimer()
+        n = 3
+        self.sift.TIMER = full
+        try:
+            for _ in range(n):
+                self._run(self.dev_in)
+        finally:
+            self.sift.TIMER = None
+        self.torch.cuda.synchronize()
+        return {k: round(v / n, 4) for k, v in sorted(full.totals().items())}
 
     cpu_task = staticmethod(_cpu_sift_task)
 

@@ -133,8 +133,9 @@ _TABLE_CACHE: dict = {}
 class StageTimer:
     """Optional CUDA-event timing of the pipeline stages (bench.py installs one; None = no overhead)."""
 
-    def __init__(self):
+    def __init__(self, only=None):
         self.events = []
+        self.only = set(only) if only else None  # record just these stages (the others cost no events at all)
 
     class _Ctx:
         def __init__(self, owner, name):
@@ -150,6 +151,8 @@ class StageTimer:
             self.owner.events.append((self.name, self.a, self.b))
 
     def stage(self, name):
+        if self.only is not None and name not in self.only:
+            return _NULL
         return StageTimer._Ctx(self, name)
 
     def totals(self):
