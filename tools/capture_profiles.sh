@@ -13,7 +13,9 @@ run() {  # name, workload flags, kernel regex, capture count
   ncu --set full --clock-control none --import-source on -k "regex:$regex" -c $count -f -o $out/r01_${name}_kernels \
       python bench.py $flags --steps 1 --warmup 1 --no-cpu-baseline > $out/ncu_f_$name.log 2>&1
 }
-run sift "--workload sift" "gauss_octave_packed|extrema_strip|gradient_field4|orientation_kernel|descriptor_kernel|upsample2_block" 24
-run harris "--workload harris" "harris5_f32|lambda5_strip|threshold_mask" 3
-run match "--workload match" "match_tc2|match_rerank|match_prep" 3
+only=${1:-all}
+want() { [ "$only" = all ] || [ "$only" = "$1" ]; }
+want sift && run sift "--workload sift --batch 8" "gauss_octave_packed|extrema_strip|gradient_field4|orientation_kernel|descriptor_kernel|upsample2_block" 40
+want harris && run harris "--workload harris" "harris5_f32|lambda5_strip|threshold_mask" 3
+want match && run match "--workload match" "match_tc2|match_rerank|match_prep" 3
 ls -la $out | tail -20
