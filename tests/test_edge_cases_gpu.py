@@ -172,3 +172,41 @@ def test_rethreshold_and_batch_drivers(M):
         base = M.sift.upsample2(sift_imgs[b], p)[0].cpu().numpy()
         rp, _ = O.compute_keypoints_and_descriptors_from_base(base, 4, 2, 1.6, 0.03, 10, "app", "separable")
         assert r0[b][0].shape[0] == len(rp)
+
+
+def test_batched_compaction_pieces(M, lib):
+    """fc_mask_row_count / fc_popcount_u64 / fc_exclusive_scan_i32 / fc_publish_gather_i32: the pieces the batched SIFT
+    driver concatenates; compared with numpy, large enough for the multi-level scan."""
+    import ctypes as C
+
+    from exvision_featurecraft_b200 import _lib
+    from exvision_featurecraft_b200.device import ptr, read_ints_at, scan_scratch, stream_ptr
+
+    rng = np.random.default_rng(11)
+    B, H, W = 3, 37, 200
+    pitch = (W + 31) // 32
+    words = rng.integers(0, 2 ** 32, size=(B, H, pitch), dtype=np.uint64).astype(np.uint32)
+    mask = torch.from_numpy(words.view(np.int32)).cuda()
+    counts = torch.empty(B * H, dtype=torch.int32, device="cuda")
+    _lib.call("fc_mask_row_count", ptr(mask), B, H, W, ptr(counts), stream_ptr())
+    ref = np.unpackbits(words.view(np.uint8), axis=-1).reshape(B * H, -1).sum(1)
+    assert np.array_equal(counts.cpu().numpy(), ref)
+
+    n = 300_001  # > 2048 * 2048 / 16: three scan levels are not needed, two are
+    m64 = rng.integers(0, 2 ** 36, size=n, dtype=np.int64)
+    masks = torch.from_numpy(m64).cuda()
+    pc = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.call("fc_popcount_u64", ptr(masks), n, ptr(pc), stream_ptr())
+    ref_pc = np.array([bin(int(v)).count("1") for v in m64[:5000]])
+    assert np.array_equal(pc.cpu().numpy()[:5000], ref_pc)
+    offs = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    _lib.call("fc_exclusive_scan_i32", ptr(pc), n, ptr(offs), ptr(scan_scratch(n)), stream_ptr())
+    ref_offs = np.concatenate([[0], np.cumsum(pc.cpu().numpy(), dtype=np.int64)])
+    assert np.array_equal(offs.cpu().numpy().astype(np.int64), ref_offs)
+    idx = [0, 1, 2047, 2048, 2049, 123_456, n]
+    assert read_ints_at(offs, idx) == [int(ref_offs[i]) for i in idx]
+    # bad arguments
+    assert lib.fc_publish_gather_i32(ptr(offs), (C.c_int64 * 1)(0), 33, ptr(offs), stream_ptr()) != 0
+    assert lib.fc_exclusive_scan_i32(None, 10, ptr(offs), None, stream_ptr()) != 0
+    assert lib.fc_popcount_u64(ptr(masks), 0, ptr(pc), stream_ptr()) != 0
+    assert lib.fc_mask_row_count(None, B, H, W, ptr(counts), stream_ptr()) != 0
