@@ -86,6 +86,19 @@ def get_keypoints(DOG_octave, k, contrast_th, ratio_th, DoG_full_array):
     return _extrema_to_list(ext[sel - 1], w, k)
 
 
+def localize_keypoint(D, x, y, s):
+    """implementation_without_ui/SIFT/SIFT.py:225-269: the 2x2 spatial Hessian of DoG level s at (y, x) -> (H, x, y, s).
+
+    Nine array elements and six float64 operations on the host: on the device this arithmetic is fused into the
+    extremum kernels (script filter, fc_dog_extrema with FC_FILTER_SCRIPT); the function exists so that code written
+    against the script's API keeps working.  The operation order is the reference's (:248-259)."""
+    D = np.asarray(D).astype(np.float64)
+    dxx = D[y, x + 1, s] - 2 * D[y, x, s] + D[y, x - 1, s]
+    dxy = ((D[y + 1, x + 1, s] - D[y + 1, x - 1, s]) - (D[y - 1, x + 1, s] - D[y - 1, x - 1, s])) / 4
+    dyy = D[y + 1, x, s] - 2 * D[y, x, s] + D[y - 1, x, s]
+    return np.array([[dxx, dxy], [dxy, dyy]]), x, y, s
+
+
 def generate_gaussian_images_in_octave(image, gaussian_kernels, contrast_th, ratio_th, octave_index):
     """:109-160 -> (gaussian images, DoG images, keypoints [i, j, k])."""
     taps = _taps_from_kernels(gaussian_kernels)

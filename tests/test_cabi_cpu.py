@@ -69,3 +69,32 @@ def test_compute_call_without_gpu_raises():
 
     with pytest.raises(_lib.FeatureCraftError):
         corners.harris(np.zeros((8, 8), np.uint8))
+
+
+def test_localize_keypoint_mirror_follows_the_script():
+    """SIFT.py:225-269 restated literally here (float64, the script's operation order) against the mirror; when the
+    reference tree is mounted (authoring container) the script's own function is used as well."""
+    import os
+
+    import numpy as np
+
+    from exvision_featurecraft_b200.utils.SIFT_scale_space import localize_keypoint
+
+    rng = np.random.default_rng(2)
+    D = rng.standard_normal((9, 11, 4)).astype(np.float32)
+    funcs = []
+    from oracle import ref_loader
+
+    if ref_loader.available():
+        funcs.append(ref_loader.script_namespace()["localize_keypoint"])
+    for y, x, s in [(1, 1, 0), (4, 7, 2), (7, 9, 3)]:
+        H, xo, yo, so = localize_keypoint(D, x, y, s)
+        Dd = D.astype(np.float64)
+        dxx = Dd[y, x + 1, s] - 2 * Dd[y, x, s] + Dd[y, x - 1, s]
+        dyy = Dd[y + 1, x, s] - 2 * Dd[y, x, s] + Dd[y - 1, x, s]
+        dxy = ((Dd[y + 1, x + 1, s] - Dd[y + 1, x - 1, s]) - (Dd[y - 1, x + 1, s] - Dd[y - 1, x - 1, s])) / 4
+        assert (xo, yo, so) == (x, y, s)
+        assert np.array_equal(H, np.array([[dxx, dxy], [dxy, dyy]]))
+        for f in funcs:
+            Hr, xr, yr, sr = f(D, x, y, s)
+            assert np.array_equal(H, Hr) and (xr, yr, sr) == (x, y, s)
