@@ -669,6 +669,122 @@ lambda5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_pe
   }
 }
 
+// Rolled variant (the one fc_lambda_minus_response launches).  The kernel above keeps the five image rows of the
+// vertical K_X taps in registers and unrolls the row loop five times so that their roles rotate statically; with
+// four pixels of float64 divide / square-root sequences per step that is 12 600 instructions (200 KB) of straight
+// code -- every warp misses the instruction cache all the time -- and the newest row is loaded right where it is
+// needed.  Here the rows live in a per-thread shared-memory ring of 8 slots that cp.async fills three rows ahead
+// (no register scoreboard, no exposed load latency) and are read back in logical order, so ONE copy of the step
+// body (2 500 instructions) serves every row; the 5x5 window sums use the same int4 ring as the Harris kernel.
+static constexpr int kLamRowSlots = 8;
+
+__device__ __forceinline__ void lambda_stage_row(const uint8_t* __restrict__ img, int row, int H, int W, int c0,
+                                                 uint4* __restrict__ rows_ring) {
+  uint4* dst = rows_ring + (row & (kLamRowSlots - 1)) * kStripThreads;
+  if (row < 0 || row >= H) {
+    *dst = make_uint4(0u, 0u, 0u, 0u);  // zero padding (padding_matrix)
+  } else {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (size_t)row * W);
+    const int wi = c0 >> 2, nw = W >> 2;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      const int idx = wi - 1 + w;
+      if (idx >= 0 && idx < nw) {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(d + w);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(p + idx) : "memory");
+      } else {
+        d[w] = 0u;
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kStripThreads, 4)
+lambda5_ring_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double* __restrict__ out,
+                    unsigned long long* __restrict__ img_max_bits) {
+  __shared__ int4 sRing[5 * 3 * kStripThreads];            // [slot][xx, xy, yy][thread]: row sums of the last 5 rows
+  __shared__ uint4 sRows[kLamRowSlots * kStripThreads];    // [row & 7][thread]: the thread's 12 bytes of an image row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * kStripWarps + warp;
+  const int strip_c0 = strip * kStripCols;
+  if (strip_c0 >= W) return;  // warp-uniform, no block-wide barrier in this kernel
+  const int c0 = strip_c0 + lane * 4;
+  const bool active = c0 < W;
+  const size_t img_off = (size_t)blockIdx.z * H * W;
+  const uint8_t* img = gray + img_off;
+  double* o = out + img_off;
+  const int y0 = blockIdx.y * rows_per_band;
+  const int y1 = min(y0 + rows_per_band, H);
+  const bool cols_interior = (strip_c0 - 2 >= 0) && (strip_c0 + kStripCols + 1 <= W - 1);
+  int4* ring = sRing + threadIdx.x;
+  uint4* rows_ring = sRows + threadIdx.x;
+  uint32_t Sxx[4], Syy[4];
+  long long Sxy[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { Sxx[j] = 0u; Syy[j] = 0u; Sxy[j] = 0; }
+#pragma unroll
+  for (int i = 0; i < 15; ++i) ring[i * kStripThreads] = make_int4(0, 0, 0, 0);
+  // rows hr-2 .. hr+2 of the first step (hr = y0-2) and two rows ahead
+  for (int r = y0 - 4; r <= y0 + 2; ++r) lambda_stage_row(img, r, H, W, c0, rows_ring);
+  double local_max = -INFINITY;
+  int slot = 0;
+#pragma unroll 1
+  for (int hr = y0 - 2; hr <= y1 + 1; ++hr) {
+    asm volatile("cp.async.wait_group 2;" ::: "memory");  // rows <= hr+2 have landed (each thread reads only its own copies)
+    Row5 R;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const uint4 v = rows_ring[((hr - 2 + q) & (kLamRowSlots - 1)) * kStripThreads];
+      R.r[q].w[0] = v.x; R.r[q].w[1] = v.y; R.r[q].w[2] = v.z;
+    }
+    lambda_stage_row(img, hr + 5, H, W, c0, rows_ring);  // slot of row hr-3, no longer needed
+    int h[12];
+    if (hr < 0 || hr >= H) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) h[i] = 0;
+    } else {
+      lambda_row_sums<4>(R, W, c0, cols_interior, h);  // S = 4: rows hr-2 .. hr+2 are R.r[0] .. R.r[4]
+    }
+    int4* s = ring + slot;
+    const int4 oxx = s[0], oxy = s[kStripThreads], oyy = s[2 * kStripThreads];
+    s[0] = make_int4(h[0], h[1], h[2], h[3]);
+    s[kStripThreads] = make_int4(h[4], h[5], h[6], h[7]);
+    s[2 * kStripThreads] = make_int4(h[8], h[9], h[10], h[11]);
+    slot = (slot == 4 * 3 * kStripThreads) ? 0 : slot + 3 * kStripThreads;
+    const int ox[4] = {oxx.x, oxx.y, oxx.z, oxx.w}, om[4] = {oxy.x, oxy.y, oxy.z, oxy.w}, oy[4] = {oyy.x, oyy.y, oyy.z, oyy.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      Sxx[j] += (uint32_t)(h[j] - ox[j]);
+      Sxy[j] += (long long)(h[4 + j] - om[j]);
+      Syy[j] += (uint32_t)(h[8 + j] - oy[j]);
+    }
+    const int r = hr - 2;  // rows r-2 .. r+2 are now summed
+    if (r >= y0) {
+      double res[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double a = div25_exact(exact_u32_to_f64(Sxx[j]));
+        const double b = div25_exact(exact_i64_to_f64(Sxy[j]));
+        const double c = div25_exact(exact_u32_to_f64(Syy[j]));
+        res[j] = lambda_min_psd(a, b, c);
+        if (active) local_max = fmax(local_max, res[j]);
+      }
+      if (active) {
+        double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
+        __stcs(dst, make_double2(res[0], res[1]));
+        __stcs(dst + 1, make_double2(res[2], res[3]));
+      }
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  if (img_max_bits) {
+    const double m = warp_max(local_max);
+    if (lane == 0 && m > -INFINITY) atomicMax(img_max_bits + blockIdx.z, ordered_bits(m));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // General path: shared-memory tiled, any odd window <= 31, both gradients, both responses
 // ------------------------------------------------------------------------------------------------
@@ -998,7 +1114,11 @@ extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int heig
     int rows = 64;
     while (rows > 8 && (int64_t)strips * div_up(height, rows) * batch < 148 * 16) rows >>= 1;
     dim3 grid(div_up(strips, kStripWarps), div_up(height, rows), batch);
-    lambda5_strip_kernel<<<grid, kStripThreads, 0, st>>>(gray, height, width, rows, eig, bits);
+    static const bool unrolled_variant = getenv("FC_LAMBDA_UNROLLED") != nullptr;  // A/B switch: the register-rotation kernel
+    if (unrolled_variant)
+      lambda5_strip_kernel<<<grid, kStripThreads, 0, st>>>(gray, height, width, rows, eig, bits);
+    else
+      lambda5_ring_kernel<<<grid, kStripThreads, 0, st>>>(gray, height, width, rows, eig, bits);
     note_launch();
     FC_RETURN_IF_LAUNCH_FAILED();
   } else {
