@@ -74,3 +74,75 @@ def match_indices(desc_a, desc_b, tuning_distance: float = 0.3, engine: str = "t
     q = torch.nonzero(good).flatten()
     pairs = torch.stack([q, idx[q, 0].to(torch.int64)], 1)
     return pairs.cpu().numpy(), dist[q, 0].cpu().numpy()
+
+
+class BatchMatcher:
+    """match() for a stream of equally sized (query, train) descriptor-set pairs that live on the HOST.
+
+    Three CUDA streams like the extraction drivers: pinned descriptors -> device (copy-in), the matching kernels
+    (compute = the caller's current stream), results -> pinned host memory (copy-out).  `submit` returns as soon as
+    the work of a pair is queued; `collect` waits for that pair's copy-out only, so the 2 x nq x 512 bytes of the
+    next pair cross PCIe while the current pair is on the tensor cores."""
+
+    def __init__(self, n_query: int, n_train: int, ratio: float = 0.3, depth: int = 2, engine: str = "tensor"):
+        dev = require_cuda()
+        self.nq, self.nt, self.ratio, self.depth, self.engine = int(n_query), int(n_train), float(ratio), depth, engine
+        self.copy_in = torch.cuda.Stream(device=dev)
+        self.copy_out = torch.cuda.Stream(device=dev)
+        self.host_q = [torch.empty((self.nq, 128), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.host_t = [torch.empty((self.nt, 128), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.dev_q = [torch.empty((self.nq, 128), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.dev_t = [torch.empty((self.nt, 128), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.host_good = [torch.empty(self.nq, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.host_idx = [torch.empty(self.nq, dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.host_dist = [torch.empty(self.nq, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.consumed = [None] * depth  # event after the kernels that read dev_q/dev_t[slot]
+        self.done = [None] * depth      # event after the copy-out of a slot
+        self.keep = [None] * depth      # device results kept alive until their copy-out has run
+        self.n_submitted = 0
+
+    def submit(self, query=None, train=None) -> int:
+        """Queue one pair.  query / train: [n,128] float32 arrays or tensors on the host; None = the pinned staging
+        buffers host_q / host_t of this ticket's slot were filled by the caller."""
+        ticket = self.n_submitted
+        slot = ticket % self.depth
+        self.n_submitted += 1
+        if query is not None:
+            self.host_q[slot].copy_(query if isinstance(query, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(query, np.float32)))
+        if train is not None:
+            self.host_t[slot].copy_(train if isinstance(train, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(train, np.float32)))
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_in):
+            if self.consumed[slot] is not None:
+                self.copy_in.wait_event(self.consumed[slot])
+            self.dev_q[slot].copy_(self.host_q[slot], non_blocking=True)
+            self.dev_t[slot].copy_(self.host_t[slot], non_blocking=True)
+            staged = torch.cuda.Event()
+            staged.record()
+        compute.wait_event(staged)
+        idx, dist, good = knn2(self.dev_q[slot], self.dev_t[slot], self.ratio, self.engine)
+        best_idx, best_dist, good_u8 = idx[:, 0].contiguous(), dist[:, 0].contiguous(), good.to(torch.uint8)
+        ready = torch.cuda.Event()
+        ready.record()
+        self.consumed[slot] = ready
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(ready)
+            self.host_good[slot].copy_(good_u8, non_blocking=True)
+            self.host_idx[slot].copy_(best_idx, non_blocking=True)
+            self.host_dist[slot].copy_(best_dist, non_blocking=True)
+            out = torch.cuda.Event()
+            out.record()
+        self.done[slot] = out
+        self.keep[slot] = (best_idx, best_dist, good_u8)
+        return ticket
+
+    def collect(self, ticket: int):
+        """-> (pairs [M,2] int64 (queryIdx, trainIdx), distances [M] float32): the `good` list of match(), query order."""
+        slot = ticket % self.depth
+        self.done[slot].synchronize()
+        q = np.flatnonzero(self.host_good[slot].numpy())
+        pairs = np.stack([q, self.host_idx[slot].numpy()[q].astype(np.int64)], 1)
+        return pairs, self.host_dist[slot].numpy()[q].copy()
+
+    def bytes_per_pair(self):
+        return (self.nq + self.nt) * 512, self.nq * 9

@@ -163,6 +163,35 @@ def test_matching_random_vs_oracle(engine):
             assert np.array_equal(dist, ref_dist)
 
 
+def test_batch_matcher_pipeline_equals_single_calls():
+    """matching.BatchMatcher (host -> device -> host pipeline over a stream of pairs) returns, pair by pair, what
+    match_indices returns for that pair alone -- with pairs in flight overlapping each other."""
+    from exvision_featurecraft_b200 import matching
+
+    rng = np.random.default_rng(9)
+    nq, nt = 700, 900
+    pairs_in = []
+    for s in range(5):
+        b = rng.random((nt, 128)).astype(np.float32)
+        b /= np.linalg.norm(b, axis=1, keepdims=True)
+        a = b[rng.integers(0, nt, nq)] + rng.normal(0, 0.002 * (s + 1), (nq, 128)).astype(np.float32)
+        a[::5] = rng.random((len(a[::5]), 128)).astype(np.float32)
+        pairs_in.append((a, b))
+    bm = matching.BatchMatcher(nq, nt, 0.6, depth=2)
+    tickets, results = [], []
+    for a, b in pairs_in:  # keep two pairs in flight
+        tickets.append(bm.submit(a, b))
+        if len(tickets) >= 2:
+            results.append(bm.collect(tickets[len(results)]))
+    while len(results) < len(tickets):
+        results.append(bm.collect(tickets[len(results)]))
+    for (a, b), (pairs, dist) in zip(pairs_in, results):
+        ref_pairs, ref_dist = matching.match_indices(a, b, 0.6, "exact")
+        assert np.array_equal(pairs, ref_pairs)
+        assert np.array_equal(dist, ref_dist)
+    assert sum(len(p) for p, _ in results) > 500  # the comparison above is not between empty lists
+
+
 def test_tensor_matcher_rarely_needs_the_exact_recheck():
     """The tcgen05 candidates + bounds must decide almost every row on their own (otherwise the test above
     would pass on the exact fallback alone), and agree with the exact engine at a size that spans many tiles,
