@@ -16,6 +16,6 @@ run() {  # name, workload flags, kernel regex, capture count
 only=${1:-all}
 want() { [ "$only" = all ] || [ "$only" = "$1" ]; }
 want sift && run sift "--workload sift --batch 8" "gauss_octave_packed|extrema_strip|gradient_field4|orientation_kernel|descriptor_kernel|upsample2_block" 40
-want harris && run harris "--workload harris" "harris5_f32|lambda5_strip|threshold_mask" 3
+want harris && run harris "--workload harris" "harris5_f32|lambda5_ring|threshold_mask" 3
 want match && run match "--workload match" "match_tc2|match_rerank|match_prep" 3
 ls -la $out | tail -20
