@@ -38,6 +38,7 @@ SIGNATURES = {
     "fc_notebook_harris_response": (_i, [_p, _i, _i, _i, _i, _d, _p, _p]),
     "fc_lambda_minus_response": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "fc_selftest_div25": (_i, [_p, _p]),
+    "fc_selftest_divsqrt": (_i, [_p, _p]),
     "fc_threshold_mask_abs": (_i, [_p, _i, _i, _i, _d, _i, _p, _p]),
     "fc_threshold_mask_rel": (_i, [_p, _i, _i, _i, _d, _p, _p, _p]),
     "fc_scan_scratch_elems": (_i64, [_i64]),

@@ -580,6 +580,40 @@ __global__ void selftest_div25_kernel(unsigned long long* __restrict__ mismatche
   if (bad) atomicAdd(mismatches, bad);
 }
 
+// div_seq / sqrt_seq against the library's correctly rounded operations on pseudo-random operands of the range the
+// lambda-minus kernel feeds them (magnitudes 2^-10 .. 2^30, quotients of any size in between, radicands in [1, 2] and
+// across the range), 2^32 samples per call
+__global__ void selftest_divsqrt_kernel(unsigned long long* __restrict__ mismatches) {
+  unsigned long long n = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (; n < (1ull << 32); n += stride) {
+    // splitmix64
+    unsigned long long z = n * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    unsigned long long w = z * 0xD6E8FEB86659FD93ull;
+    w ^= w >> 32;
+    // mantissas from the hash, exponents in [-10, 30]
+    const int ea = (int)(z % 41) - 10, eb = (int)((z >> 8) % 41) - 10;
+    const double a = __longlong_as_double((long long)((z >> 12) | ((unsigned long long)(1023 + ea) << 52)));
+    const double b = __longlong_as_double((long long)((w >> 12) | ((unsigned long long)(1023 + eb) << 52)));
+    const double sa = (z & 1) ? -a : a;
+    bad += (div_seq(sa, b, rcp_seq(b)) != __ddiv_rn(sa, b));
+    bad += (sqrt_seq(a) != __dsqrt_rn(a));
+    const double x12 = __longlong_as_double((long long)((w >> 12) | (1023ull << 52)));  // [1, 2)
+    bad += (sqrt_seq(x12) != __dsqrt_rn(x12));
+    // multiples of 1/25 like the kernel's operands
+    const double m1 = __ddiv_rn((double)(unsigned)(z >> 33), 25.0), m2 = __ddiv_rn((double)(unsigned)((w >> 33) | 1u), 25.0);
+    bad += (div_seq(m1, m2, rcp_seq(m2)) != __ddiv_rn(m1, m2));
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+// out-of-line copy of the rare LAPACK split path (one body instead of one per pixel)
+static __device__ __noinline__ double dsterf_2x2_min_call(double a, double b, double c) { return dsterf_2x2_min(a, b, c); }
+
 struct LambdaState {
   Row5 R;
   uint32_t Sxx[4], Syy[4];
@@ -619,6 +653,7 @@ __device__ __forceinline__ void lambda_step(LambdaState& st, const uint8_t* __re
       const double b = div25_exact(exact_i64_to_f64(st.Sxy[j]));
       const double c = div25_exact(exact_u32_to_f64(st.Syy[j]));
       res[j] = lambda_min_psd(a, b, c);
+      if (lambda_needs_dsterf(a, b, c)) res[j] = dsterf_2x2_min_call(a, b, c);
       if (active) st.local_max = fmax(st.local_max, res[j]);
     }
     if (active) {
@@ -763,12 +798,24 @@ lambda5_ring_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per
     const int r = hr - 2;  // rows r-2 .. r+2 are now summed
     if (r >= y0) {
       double res[4];
+      double av[4], bv[4], cv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double a = div25_exact(exact_u32_to_f64(Sxx[j]));
-        const double b = div25_exact(exact_i64_to_f64(Sxy[j]));
-        const double c = div25_exact(exact_u32_to_f64(Syy[j]));
-        res[j] = lambda_min_psd(a, b, c);
+        av[j] = div25_exact(exact_u32_to_f64(Sxx[j]));
+        bv[j] = div25_exact(exact_i64_to_f64(Sxy[j]));
+        cv[j] = div25_exact(exact_u32_to_f64(Syy[j]));
+        res[j] = lambda_min_psd(av[j], bv[j], cv[j]);  // straight-line: the four float64 chains interleave
+      }
+      bool rare = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rare |= lambda_needs_dsterf(av[j], bv[j], cv[j]);
+      if (rare) {  // tiny non-zero off-diagonal: LAPACK's split test decides (practically never on image data)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (lambda_needs_dsterf(av[j], bv[j], cv[j])) res[j] = dsterf_2x2_min_call(av[j], bv[j], cv[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         if (active) local_max = fmax(local_max, res[j]);
       }
       if (active) {
@@ -1092,6 +1139,15 @@ extern "C" int fc_selftest_div25(unsigned long long* mismatches, void* stream) {
   if (!mismatches) return FC_ERR_BAD_ARG;
   FC_CUDA_TRY(cudaMemsetAsync(mismatches, 0, sizeof(unsigned long long), (cudaStream_t)stream));
   selftest_div25_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(mismatches);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_selftest_divsqrt(unsigned long long* mismatches, void* stream) {
+  if (!mismatches) return FC_ERR_BAD_ARG;
+  FC_CUDA_TRY(cudaMemsetAsync(mismatches, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  selftest_divsqrt_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(mismatches);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;

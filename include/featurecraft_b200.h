@@ -90,6 +90,10 @@ FC_API int fc_lambda_minus_response(const uint8_t* gray, int batch, int height, 
 /* Device self-test: counts the integers |n| <= 2^33 for which the division-free n/25 used by the lambda-minus
  * kernel differs from IEEE division (must be 0).  mismatches: one device uint64. */
 FC_API int fc_selftest_div25(unsigned long long* mismatches, void* stream);
+/* Device self-test of the straight-line float64 division / square-root sequences the lambda-minus kernel uses instead of
+ * the library calls (so that the pixels of a thread overlap): compares them with __ddiv_rn / __dsqrt_rn on 2^32
+ * pseudo-random operands of the kernel's range and writes the number of mismatches (must be 0). */
+FC_API int fc_selftest_divsqrt(unsigned long long* mismatches, void* stream);
 
 /* np.argwhere(map > thr) as a bit mask (APP/FeatureCraft_Backend.py:358, :268).  Pixels closer than
  * `border` to any image edge are never set. */

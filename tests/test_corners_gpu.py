@@ -182,3 +182,14 @@ def test_div25_identity_is_exhaustively_exact(fc, lib):
     out = torch.zeros(1, dtype=torch.int64, device="cuda")
     assert lib.fc_selftest_div25(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
     assert int(out.item()) == 0
+
+
+def test_division_and_sqrt_sequences_equal_the_ieee_operations(fc, lib):
+    """The lambda-minus kernel evaluates its float64 quotients and square root with the straight-line Newton sequences
+    of fc_common.cuh (so that the pixels of a thread overlap); the device compares them with __ddiv_rn / __dsqrt_rn
+    on 2^32 pseudo-random operands of the kernel's range."""
+    import ctypes
+
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert lib.fc_selftest_divsqrt(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    assert int(out.item()) == 0
