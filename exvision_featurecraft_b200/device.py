@@ -75,20 +75,24 @@ def read_last_ints(tensors) -> list:
 
 
 def read_ints_at(t: torch.Tensor, indices) -> list:
-    """[int(t[i]) for i in indices] (int32 CUDA tensor, at most 32 indices) with ONE kernel launch and ONE host
+    """[int(t[i]) for i in indices] (int32 CUDA tensor) with one kernel launch per 32 indices and ONE host
     synchronisation: the values are gathered into pinned host memory by a kernel (see read_int)."""
-    assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and 0 < len(indices) <= 32
+    assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and len(indices) > 0
+    n = len(indices)
     key = (t.device.index, torch.cuda.current_stream().cuda_stream)
     slot = _PINNED_SLOTS.get(key)
-    if slot is None or slot[0].numel() < 32:
-        slot = (torch.zeros(32, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+    if slot is None or slot[0].numel() < max(32, n):
+        slot = (torch.zeros(max(32, n), dtype=torch.int32).pin_memory(), torch.cuda.Event())
         _PINNED_SLOTS[key] = slot
     host, ev = slot
-    idx = (C.c_int64 * len(indices))(*[int(i) for i in indices])
-    _lib.call("fc_publish_gather_i32", C.c_void_p(t.data_ptr()), idx, len(indices), C.c_void_p(host.data_ptr()), stream_ptr())
+    for lo in range(0, n, 32):
+        part = [int(i) for i in indices[lo:lo + 32]]
+        idx = (C.c_int64 * len(part))(*part)
+        _lib.call("fc_publish_gather_i32", C.c_void_p(t.data_ptr()), idx, len(part), C.c_void_p(host.data_ptr() + 4 * lo),
+                  stream_ptr())
     ev.record()
     ev.synchronize()
-    return [int(v) for v in host[: len(indices)].tolist()]
+    return [int(v) for v in host[:n].tolist()]
 
 
 def read_int(t: torch.Tensor, index: int = -1) -> int:

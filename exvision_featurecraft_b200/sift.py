@@ -496,9 +496,6 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     # B: row-major compaction offsets.  The row counts of every (octave, scale) mask go into ONE concatenated array,
     # one scan covers them all and one gather launch brings the cumulative keypoint counts at the block boundaries to
     # the host: keypoints of all blocks then live in one list, block after block, in the reference's order.
-    n_blocks = len(work)
-    if n_blocks > 32:
-        raise ValueError("more than 32 (octave, scale) blocks")
     rows = [octaves[o].gauss.shape[0] * octaves[o].height for o, _ in work]
     row_start = [0]
     for r in rows:

@@ -203,7 +203,7 @@ def test_batched_compaction_pieces(M, lib):
     _lib.call("fc_exclusive_scan_i32", ptr(pc), n, ptr(offs), ptr(scan_scratch(n)), stream_ptr())
     ref_offs = np.concatenate([[0], np.cumsum(pc.cpu().numpy(), dtype=np.int64)])
     assert np.array_equal(offs.cpu().numpy().astype(np.int64), ref_offs)
-    idx = [0, 1, 2047, 2048, 2049, 123_456, n]
+    idx = [0, 1, 2047, 2048, 2049, 123_456, n] + [int(v) for v in rng.integers(0, n + 1, 40)]  # > 32: two gather launches
     assert read_ints_at(offs, idx) == [int(ref_offs[i]) for i in idx]
     # bad arguments
     assert lib.fc_publish_gather_i32(ptr(offs), (C.c_int64 * 1)(0), 33, ptr(offs), stream_ptr()) != 0
