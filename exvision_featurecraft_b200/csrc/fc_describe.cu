@@ -448,10 +448,14 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
         s2 += v * v;
       }
     } else {
-      const NT nrm = Math<NT>::sqrt_(ss);
+      // exact mode: IEEE square root and divisions as the straight-line sequences of fc_common.cuh (bit-identical to
+      // sqrt / `/` for these operands, one refined reciprocal per divisor); an all-zero window gives NaN like the
+      // reference's 0 / 0
+      const NT nrm = sqrt_seq(ss);
+      const NT rn = rcp_seq(nrm);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        NT v = f[k] / nrm;  // IEEE division; 0 / 0 = NaN for an all-zero window, like the reference
+        NT v = div_seq(f[k], nrm, rn);
         if (v == v) v = v < lo ? lo : (v > hi ? hi : v);
         f[k] = v;
         s2 += v * v;
@@ -469,9 +473,10 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
         for (int k = 0; k < 4; ++k) dst[k] = (OUT)(f[k] * inv2);
       }
     } else {
-      const NT nrm2 = Math<NT>::sqrt_(s2);
+      const NT nrm2 = sqrt_seq(s2);
+      const NT rn2 = rcp_seq(nrm2);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dst[k] = (OUT)(f[k] / nrm2);
+      for (int k = 0; k < 4; ++k) dst[k] = (OUT)div_seq(f[k], nrm2, rn2);
     }
     __syncwarp();  // the next keypoint rewrites sXY and the private bins
   }
