@@ -1,16 +1,15 @@
 // Harris / lambda-minus corner response kernels (sm_100a).
 //
-//   harris5_strip_kernel   app Harris, 5x5 window (the reference default and the benchmarked config):
+//   harris5_f32_kernel     app Harris, 5x5 window (the reference default and the benchmarked config):
 //                          sliding-window kernel, one warp per 128-column strip, 4 pixels per thread,
-//                          exact int32 / int64 arithmetic (bytes unpacked by PRMT, no conversion-unit ops).
+//                          exact packed-float32 sums (bytes unpacked by PRMT, no conversion-unit ops).
+//   lambda5_ring_kernel    lambda-minus, same strip structure, exact integer sums + LAPACK's dlae2 sequence.
 //   corner_tiled_kernel    every other combination (any odd window <= 31, K_X gradient, lambda-minus):
 //                          shared-memory tiled, exact integer sums.
 //
 // Reference arithmetic: APP/FeatureCraft_Backend.py:336-355 (Harris), :402-437 (lambda-minus),
 // implementation_without_ui/Corner Detection/harris.ipynb:150-190 (notebook Harris).
 // HBM traffic per pixel: 1 B gray in + 8 B float64 response out (+ 1 bit mask).
-#include <stdlib.h>
-
 #include "fc_common.cuh"
 
 namespace fc {
@@ -19,19 +18,8 @@ enum { GRAD_CENTRAL = 0, GRAD_KX = 1 };
 enum { RESP_HARRIS = 0, RESP_LAMBDA_MINUS = 1 };
 
 // ------------------------------------------------------------------------------------------------
-// Fast path: Harris, np.gradient, 5x5 window
+// Shared pieces of the two strip kernels: packed image rows and exact integer -> float64 moves
 // ------------------------------------------------------------------------------------------------
-//
-// All quantities are kept in units that make them integers: g2 = 2*gradient (|g2| <= 510), products
-// p = g2*g2 (<= 260100), 5-tap row sums (<= 1.3e6), 5x5 sums A, B, C (<= 6.6e6): int32 arithmetic, exact.
-// With Sxx = A/4, Sxy = B/4, Syy = C/4 the reference's R = (Sxx*Syy - Sxy^2) - k*(Sxx+Syy)^2 equals
-//   R = ( (A*C - B*B) - rn(k * (A+C)^2) ) / 16
-// because A*C, B*B, (A+C)^2 < 2^53 are exact in float64, det and trace^2 are therefore exact in the
-// reference too, scaling by 2^-4 commutes with rounding, and exactly two roundings remain (k*tr^2 and
-// the final subtraction), performed here with __dmul_rn / __dsub_rn.  A*C - B*B and (A+C)^2 are formed in
-// int64 and moved to float64 with the 2^52 exponent trick (no I2F / F2F: the conversion unit runs at a
-// quarter of the ALU rate and was the bottleneck of the float version of this kernel).
-
 struct Row3 {
   uint32_t w[3];  // bytes of columns c0-4 .. c0+7 of one image row
 };
@@ -53,51 +41,6 @@ __device__ __forceinline__ int col_i(const Row3& r, int k) {
   return (int)__byte_perm(r.w[k >> 2], 0u, 0x4440u + (unsigned)(k & 3));
 }
 
-// Horizontal 5-tap sums of the three products for output columns c0..c0+3 of image row `row`.
-// h[0..3] = xx, h[4..7] = xy, h[8..11] = yy.   INTERIOR: no image border within reach.
-template <bool INTERIOR>
-__device__ __forceinline__ void harris_row_sums(const Row3& up, const Row3& mid, const Row3& dn, int row, int H, int W,
-                                                int c0, int (&h)[12]) {
-  int gx[8], gy[8];  // product columns c0-2 .. c0+5  <->  k = 2 .. 9
-  if (INTERIOR) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      gx[i] = col_i(dn, i + 2) - col_i(up, i + 2);
-      gy[i] = col_i(mid, i + 3) - col_i(mid, i + 1);
-    }
-  } else {
-    // rows were clamped when loaded, so dn - up is the one-sided difference on the first / last row
-    const int sy = (row == 0 || row == H - 1) ? 2 : 1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 - 2 + i;
-      const bool inside = (c >= 0) && (c < W);
-      const int vx = sy * (col_i(dn, i + 2) - col_i(up, i + 2));
-      int vy;
-      if (c == 0) vy = 2 * (col_i(mid, i + 3) - col_i(mid, i + 2));
-      else if (c == W - 1) vy = 2 * (col_i(mid, i + 2) - col_i(mid, i + 1));
-      else vy = col_i(mid, i + 3) - col_i(mid, i + 1);
-      gx[i] = inside ? vx : 0;
-      gy[i] = inside ? vy : 0;
-    }
-  }
-  int xx = gx[0] * gx[0], xy = gx[0] * gy[0], yy = gy[0] * gy[0];
-#pragma unroll
-  for (int i = 1; i < 5; ++i) {
-    xx += gx[i] * gx[i];
-    xy += gx[i] * gy[i];
-    yy += gy[i] * gy[i];
-  }
-  h[0] = xx; h[4] = xy; h[8] = yy;
-#pragma unroll
-  for (int j = 1; j < 4; ++j) {
-    xx += gx[j + 4] * gx[j + 4] - gx[j - 1] * gx[j - 1];
-    xy += gx[j + 4] * gy[j + 4] - gx[j - 1] * gy[j - 1];
-    yy += gy[j + 4] * gy[j + 4] - gy[j - 1] * gy[j - 1];
-    h[j] = xx; h[4 + j] = xy; h[8 + j] = yy;
-  }
-}
-
 // exact int64 -> float64 for |n| < 2^51: build 2^52 + (n + 2^51) from bits, subtract 2^52 + 2^51
 __device__ __forceinline__ double exact_i64_to_f64(long long n) {
   const unsigned long long u = (unsigned long long)(n + (1ll << 51));
@@ -105,98 +48,9 @@ __device__ __forceinline__ double exact_i64_to_f64(long long n) {
   return __dsub_rn(biased, 6755399441055744.0);  // 2^52 + 2^51
 }
 
-__device__ __forceinline__ double harris_from_quarter_sums(int a, int b, int c, double k) {
-  const long long det16 = (long long)a * c - (long long)b * b;  // |.| < 2^46
-  const long long tr = (long long)a + c;
-  const double t = __dmul_rn(k, exact_i64_to_f64(tr * tr));     // tr^2 < 2^48
-  return __dmul_rn(__dsub_rn(exact_i64_to_f64(det16), t), 0.0625);
-}
-
 static constexpr int kStripWarps = 4;
 static constexpr int kStripCols = 128;  // per warp
 static constexpr int kStripThreads = kStripWarps * 32;
-
-__global__ void __launch_bounds__(kStripThreads, 5)
-harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double k, double thr,
-                     double* __restrict__ out, uint32_t* __restrict__ mask, int mask_pitch) {
-  // ring of the last 5 rows of horizontal sums, private to each thread: [slot][quantity][thread] (conflict free)
-  __shared__ int sRing[5 * 12 * kStripThreads];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int strip = blockIdx.x * kStripWarps + warp;
-  const int strip_c0 = strip * kStripCols;
-  if (strip_c0 >= W) return;  // warp-uniform, and the kernel has no block-wide barrier
-  const int c0 = strip_c0 + lane * 4;
-  const bool active = c0 < W;
-  const size_t img_off = (size_t)blockIdx.z * H * W;
-  const uint8_t* img = gray + img_off;
-  double* o = out + img_off;
-  uint32_t* m = mask ? mask + (size_t)blockIdx.z * H * mask_pitch : nullptr;
-  const int y0 = blockIdx.y * rows_per_band;
-  const int y1 = min(y0 + rows_per_band, H);
-  // product columns of the whole strip are c in [strip_c0 - 2, strip_c0 + 129]; they all need
-  // 1 <= c <= W-2 for the border-free code path
-  const bool cols_interior = (strip_c0 - 2 >= 1) && (strip_c0 + kStripCols + 1 <= W - 2);
-  int* ring = sRing + threadIdx.x;
-  int S[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    S[i] = 0;
-#pragma unroll
-    for (int s = 0; s < 5; ++s) ring[(s * 12 + i) * kStripThreads] = 0;
-  }
-  Row3 up = load_row3(img, y0 - 3, H, W, c0);
-  Row3 mid = load_row3(img, y0 - 2, H, W, c0);
-  Row3 dn = load_row3(img, y0 - 1, H, W, c0);
-
-  for (int base = y0 - 2; base <= y1 + 1; base += 5) {
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      const int hr = base + s;  // image row whose horizontal sums are produced now
-      if (hr > y1 + 1) break;
-      const Row3 nxt = load_row3(img, hr + 2, H, W, c0);  // prefetch for the next iteration
-      int h[12];
-      if (hr < 0 || hr >= H) {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) h[i] = 0;
-      } else if (cols_interior && hr >= 1 && hr <= H - 2) {
-        harris_row_sums<true>(up, mid, dn, hr, H, W, c0, h);
-      } else {
-        harris_row_sums<false>(up, mid, dn, hr, H, W, c0, h);
-      }
-#pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        int* slot = ring + (s * 12 + i) * kStripThreads;
-        S[i] += h[i] - *slot;
-        *slot = h[i];
-      }
-      const int r = hr - 2;  // rows r-2 .. r+2 are now summed
-      if (r >= y0) {
-        double res[4];
-        uint32_t nib = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          res[j] = harris_from_quarter_sums(S[j], S[4 + j], S[8 + j], k);
-          nib |= (res[j] > thr) ? (1u << j) : 0u;
-        }
-        if (active) {
-          double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
-          __stcs(dst, make_double2(res[0], res[1]));
-          __stcs(dst + 1, make_double2(res[2], res[3]));
-        }
-        if (m) {
-          uint32_t v = active ? (nib << (4 * (lane & 7))) : 0u;
-          v |= __shfl_xor_sync(0xffffffffu, v, 1);
-          v |= __shfl_xor_sync(0xffffffffu, v, 2);
-          v |= __shfl_xor_sync(0xffffffffu, v, 4);
-          if ((lane & 7) == 0 && active) m[(size_t)r * mask_pitch + (c0 >> 5)] = v;
-        }
-      }
-      up = mid;
-      mid = dn;
-      dn = nxt;
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Harris fast path, packed-fp32 variant (the one fc_harris_response launches)
@@ -210,7 +64,7 @@ harris5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_pe
 // of np.gradient costs one subtraction.  Only the response itself (det, trace^2 up to 2^44) needs float64: three
 // exact float->double conversions and six float64 operations per pixel, two of which round -- the same two as in
 // the reference (k * trace^2 and the final subtraction, APP/FeatureCraft_Backend.py:351-355).
-// 56 instructions per pixel instead of the 81 of the integer kernel above (kept for A/B runs: FC_HARRIS_INT=1).
+// 56 instructions per pixel (an exact int32 / int64 predecessor of this kernel needed 81).
 struct RowF {
   float lo;      // column c0 - 3            (k = 1 in Row3 numbering)
   float2 e[4];   // columns c0 - 2 .. c0 + 5 (k = 2 .. 9), register-pair aligned
@@ -494,19 +348,6 @@ struct Row5 {
   Row3 r[5];  // circular: slot (row + 2) % 5 when the band starts at a multiple of 5 of the unrolled loop
 };
 
-__device__ __forceinline__ Row3 load_row3_zero(const uint8_t* __restrict__ img, int row, int H, int W, int c0) {
-  Row3 r;
-  r.w[0] = r.w[1] = r.w[2] = 0u;
-  if (row < 0 || row >= H) return r;
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (size_t)row * W);
-  const int wi = c0 >> 2;
-  const int nw = W >> 2;
-  if (wi - 1 >= 0 && wi - 1 < nw) r.w[0] = __ldg(p + wi - 1);
-  if (wi < nw) r.w[1] = __ldg(p + wi);
-  if (wi + 1 < nw) r.w[2] = __ldg(p + wi + 1);
-  return r;
-}
-
 // S = slot of the NEWEST row (hr+2); rows hr-2 .. hr+2 sit in slots S+1, S+2, S+3, S+4, S (mod 5): with the row
 // loop unrolled by 5 every index is static and no register is ever moved when the window slides.
 template <int S>
@@ -614,103 +455,11 @@ __global__ void selftest_divsqrt_kernel(unsigned long long* __restrict__ mismatc
 // out-of-line copy of the rare LAPACK split path (one body instead of one per pixel)
 static __device__ __noinline__ double dsterf_2x2_min_call(double a, double b, double c) { return dsterf_2x2_min(a, b, c); }
 
-struct LambdaState {
-  Row5 R;
-  uint32_t Sxx[4], Syy[4];
-  long long Sxy[4];
-  double local_max;
-};
-
-// one image row of the band; S = hr mod-5 slot (static), see lambda_row_sums
-template <int S>
-__device__ __forceinline__ void lambda_step(LambdaState& st, const uint8_t* __restrict__ img, int hr, int H, int W, int c0,
-                                            bool cols_interior, bool active, int y0, int* __restrict__ ring,
-                                            double* __restrict__ o) {
-  st.R.r[S] = load_row3_zero(img, hr + 2, H, W, c0);  // replaces row hr-3
-  int h[12];
-  if (hr < 0 || hr >= H) {
-#pragma unroll
-    for (int i = 0; i < 12; ++i) h[i] = 0;
-  } else {
-    lambda_row_sums<S>(st.R, W, c0, cols_interior, h);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int* s0 = ring + (S * 12 + j) * kStripThreads;
-    int* s1 = ring + (S * 12 + 4 + j) * kStripThreads;
-    int* s2 = ring + (S * 12 + 8 + j) * kStripThreads;
-    st.Sxx[j] += (uint32_t)(h[j] - *s0);
-    st.Sxy[j] += (long long)(h[4 + j] - *s1);
-    st.Syy[j] += (uint32_t)(h[8 + j] - *s2);
-    *s0 = h[j]; *s1 = h[4 + j]; *s2 = h[8 + j];
-  }
-  const int r = hr - 2;  // rows r-2 .. r+2 are now summed
-  if (r >= y0) {
-    double res[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double a = div25_exact(exact_u32_to_f64(st.Sxx[j]));
-      const double b = div25_exact(exact_i64_to_f64(st.Sxy[j]));
-      const double c = div25_exact(exact_u32_to_f64(st.Syy[j]));
-      res[j] = lambda_min_psd(a, b, c);
-      if (lambda_needs_dsterf(a, b, c)) res[j] = dsterf_2x2_min_call(a, b, c);
-      if (active) st.local_max = fmax(st.local_max, res[j]);
-    }
-    if (active) {
-      double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
-      __stcs(dst, make_double2(res[0], res[1]));
-      __stcs(dst + 1, make_double2(res[2], res[3]));
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kStripThreads, 4)
-lambda5_strip_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double* __restrict__ out,
-                     unsigned long long* __restrict__ img_max_bits) {
-  __shared__ int sRing[5 * 12 * kStripThreads];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int strip = blockIdx.x * kStripWarps + warp;
-  const int strip_c0 = strip * kStripCols;
-  if (strip_c0 >= W) return;  // warp-uniform, no block-wide barrier in this kernel
-  const int c0 = strip_c0 + lane * 4;
-  const bool active = c0 < W;
-  const size_t img_off = (size_t)blockIdx.z * H * W;
-  const uint8_t* img = gray + img_off;
-  double* o = out + img_off;
-  const int y0 = blockIdx.y * rows_per_band;
-  const int y1 = min(y0 + rows_per_band, H);
-  const bool cols_interior = (strip_c0 - 2 >= 0) && (strip_c0 + kStripCols + 1 <= W - 1);
-  int* ring = sRing + threadIdx.x;
-  LambdaState st;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { st.Sxx[j] = 0u; st.Syy[j] = 0u; st.Sxy[j] = 0; }
-#pragma unroll
-  for (int i = 0; i < 12; ++i)
-#pragma unroll
-    for (int s = 0; s < 5; ++s) ring[(s * 12 + i) * kStripThreads] = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) st.R.r[q + 1] = load_row3_zero(img, y0 - 4 + q, H, W, c0);  // rows hr-2 .. hr+1 of hr = y0-2
-  st.local_max = -INFINITY;
-
-  for (int base = y0 - 2; base <= y1 + 1; base += 5) {
-#define FC_LSTEP(S) \
-  if (base + S <= y1 + 1) lambda_step<S>(st, img, base + S, H, W, c0, cols_interior, active, y0, ring, o);
-    FC_LSTEP(0) FC_LSTEP(1) FC_LSTEP(2) FC_LSTEP(3) FC_LSTEP(4)
-#undef FC_LSTEP
-  }
-  if (img_max_bits) {
-    const double m = warp_max(st.local_max);
-    if (lane == 0 && m > -INFINITY) atomicMax(img_max_bits + blockIdx.z, ordered_bits(m));
-  }
-}
-
-// Rolled variant (the one fc_lambda_minus_response launches).  The kernel above keeps the five image rows of the
-// vertical K_X taps in registers and unrolls the row loop five times so that their roles rotate statically; with
-// four pixels of float64 divide / square-root sequences per step that is 12 600 instructions (200 KB) of straight
-// code -- every warp misses the instruction cache all the time -- and the newest row is loaded right where it is
-// needed.  Here the rows live in a per-thread shared-memory ring of 8 slots that cp.async fills three rows ahead
-// (no register scoreboard, no exposed load latency) and are read back in logical order, so ONE copy of the step
-// body (2 500 instructions) serves every row; the 5x5 window sums use the same int4 ring as the Harris kernel.
+// The five image rows of the vertical K_X taps live in a per-thread shared-memory ring of 8 slots that cp.async
+// fills three rows ahead (no register scoreboard, no exposed load latency) and are read back in logical order, so
+// ONE copy of the step body (2 500 instructions) serves every row -- keeping the rows in registers needs a five-fold
+// unrolled row loop (12 600 instructions of straight code, an instruction-cache miss on every warp: measured 1.6x
+// slower).  The 5x5 window sums use the same int4 ring as the Harris kernel.
 static constexpr int kLamRowSlots = 8;
 
 __device__ __forceinline__ void lambda_stage_row(const uint8_t* __restrict__ img, int row, int H, int W, int c0,
@@ -1110,10 +859,7 @@ extern "C" int fc_harris_response(const uint8_t* gray, int batch, int height, in
     int rows = 64;
     while (rows > 8 && (int64_t)strips * div_up(height, rows) * batch < 148 * 16) rows >>= 1;
     dim3 grid(div_up(strips, kStripWarps), div_up(height, rows), batch);
-    static const bool int_variant = getenv("FC_HARRIS_INT") != nullptr;  // A/B switch: the integer kernel
-    if (int_variant)
-      harris5_strip_kernel<<<grid, kStripWarps * 32, 0, st>>>(gray, height, width, rows, k, threshold, response, mask, pitch);
-    else if (mask)
+    if (mask)
       harris5_f32_kernel<true><<<grid, kStripWarps * 32, 0, st>>>(gray, height, width, rows, k, threshold, response, mask, pitch);
     else
       harris5_f32_kernel<false><<<grid, kStripWarps * 32, 0, st>>>(gray, height, width, rows, k, threshold, response, mask, pitch);
@@ -1170,11 +916,7 @@ extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int heig
     int rows = 64;
     while (rows > 8 && (int64_t)strips * div_up(height, rows) * batch < 148 * 16) rows >>= 1;
     dim3 grid(div_up(strips, kStripWarps), div_up(height, rows), batch);
-    static const bool unrolled_variant = getenv("FC_LAMBDA_UNROLLED") != nullptr;  // A/B switch: the register-rotation kernel
-    if (unrolled_variant)
-      lambda5_strip_kernel<<<grid, kStripThreads, 0, st>>>(gray, height, width, rows, eig, bits);
-    else
-      lambda5_ring_kernel<<<grid, kStripThreads, 0, st>>>(gray, height, width, rows, eig, bits);
+    lambda5_ring_kernel<<<grid, kStripThreads, 0, st>>>(gray, height, width, rows, eig, bits);
     note_launch();
     FC_RETURN_IF_LAUNCH_FAILED();
   } else {

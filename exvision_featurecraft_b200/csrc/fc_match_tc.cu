@@ -11,16 +11,15 @@
 //   match_prep_kernel    fp32 -> fp16 operands written in the UMMA canonical K-major no-swizzle layout
 //                        (8-row x 16-byte core matrices; row-group stride SBO = 18*128 B, K stride LBO = 128 B),
 //                        so a 128-row tile is one contiguous 36 KB block and needs no tensor map.
-//   match_tc_kernel      1 CTA per (256 queries, train split).  warp 0: bulk-copy producer (3-stage ring of
-//                        128-row train tiles), warp 1: MMA issuer (2 x 9 tcgen05.mma 128x128x16 per tile, two
-//                        accumulator stages = all 512 TMEM columns), warps 2-5: epilogue (tcgen05.ld, min-tree
-//                        fast path, sorted top-4 insert on the rare slow path).
+//   match_tc2_kernel     1 CTA pair per (256 queries, train split).  warp 0: bulk-copy producer (4-stage ring of
+//                        256-row train tiles, half per CTA), warp 1: MMA issuer (9 tcgen05.mma.cta_group::2 256x256x16
+//                        per tile, two accumulator stages = all 512 TMEM columns), warps 2-9: epilogue (tcgen05.ld,
+//                        min-tree fast path, sorted top-4 insert on the rare slow path).
 //   match_rerank_kernel  one warp per query: exact float32 distances of the members of the kept groups (same operation order
 //                        as the exact kernel), top-2, ratio test, and the bound test that proves the answer equals
 //                        the brute-force one; undecidable rows are appended to a list ...
 //   match_exact_kernel   ... and re-done exactly (fc_match_exact.cu).
 #include <cuda_fp16.h>
-#include <cstdlib>
 
 #include "fc_common.cuh"
 
@@ -37,14 +36,12 @@ constexpr int KC = KP / 8;                     // core matrices along K
 constexpr int kRowGroupBytes = KC * 128;       // SBO: one 8-row group
 constexpr int kTileRows = 128;
 constexpr int kTileBytes = kTileRows / 8 * kRowGroupBytes;  // 36864
-constexpr int kStages = 3;
 constexpr int kQueriesPerCta = 256;
 constexpr int kCand = 4;   // kept groups per (query row, split)
 constexpr int kGroup = 8;   // train rows per group
 constexpr int kMaxSplits = 4;
 constexpr int kThreads = 320;  // producer warp, MMA warp, 8 epilogue warps
 constexpr float kPadNorm = 60000.0f;
-constexpr size_t kSmemBytes = 2 * kTileBytes + kStages * kTileBytes + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -72,16 +69,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(kRowGroupBytes >> 4) << 32) |
          (1ull << 46);
-}
-// kind::f16: D = f32 (bit 4), A = B = f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -191,131 +178,10 @@ match_prep_kernel(const float* __restrict__ src, int n_rows, int n_rows_padded, 
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
-match_tc_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, int n_query_padded, int n_tiles_total,
-                int tiles_per_split, float* __restrict__ cand_score, int32_t* __restrict__ cand_idx) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sA = smem;                                // 2 tiles
-  unsigned char* sB = smem + 2 * kTileBytes;               // kStages tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kStages) * kTileBytes);
-  uint64_t* full = bars;                // [kStages]
-  uint64_t* empty = bars + kStages;     // [kStages]
-  uint64_t* a_full = bars + 2 * kStages;
-  uint64_t* t_full = a_full + 1;        // [2]
-  uint64_t* t_empty = t_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qtile = blockIdx.x, split = blockIdx.y;
-  const int tile0 = split * tiles_per_split;
-  const int n_tiles = min(tiles_per_split, n_tiles_total - tile0);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    mbar_init(a_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(t_full + s, 1); mbar_init(t_empty + s, 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const char* a_src = reinterpret_cast<const char*>(Ah) + (size_t)qtile * 2 * kTileBytes;
-      mbar_expect_tx(a_full, 2 * kTileBytes);
-      bulk_g2s(sA, a_src, kTileBytes, a_full);
-      bulk_g2s(sA + kTileBytes, a_src + kTileBytes, kTileBytes, a_full);
-      const char* b_src = reinterpret_cast<const char*>(Bh) + (size_t)tile0 * kTileBytes;
-      for (int it = 0; it < n_tiles; ++it) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(empty + st, ph ^ 1);
-        mbar_expect_tx(full + st, kTileBytes);
-        bulk_g2s(sB + (size_t)st * kTileBytes, b_src + (size_t)it * kTileBytes, kTileBytes, full + st);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(a_full, 0);
-      const uint32_t a_addr = smem_u32(sA);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        const int acc = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(t_empty + acc, aph ^ 1);
-        mbar_wait(full + st, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b_addr = smem_u32(sB + (size_t)st * kTileBytes);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t d = tmem_base + acc * 256 + h * 128;
-#pragma unroll
-          for (int kk = 0; kk < KP / 16; ++kk)
-            umma_f16(d, umma_desc(a_addr + h * kTileBytes + kk * 256), umma_desc(b_addr + kk * 256), kk > 0);
-        }
-        umma_commit(empty + st);    // smem stage free once these MMAs have read it
-        umma_commit(t_full + acc);  // accumulators ready
-      }
-    }
-  } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 only; warps 2-5 take the first 128 queries (h = 0),
-    // warps 6-9 the second 128 (h = 1).  Loads are software pipelined: chunk c+1 is in flight while c is scanned.
-    const int lg = warp & 3;
-    const int h = (warp - 2) >> 2;
-    const int row = lg * 32 + lane;
-    TopK best;
-    best.init();
-    for (int it = 0; it < n_tiles; ++it) {
-      const int acc = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      mbar_wait(t_full + acc, aph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int n0 = (tile0 + it) * (kTileRows / kGroup);  // first 8-row group of this tile
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 256 + h * 128;
-      uint32_t ra[32], rb[32];
-      tmem_ld32_issue(taddr, ra);
-      tmem_ld_wait();
-      tmem_ld32_issue(taddr + 32, rb);
-      scan_chunk(ra, n0, best);
-      tmem_ld_wait();
-      tmem_ld32_issue(taddr + 64, ra);
-      scan_chunk(rb, n0 + 4, best);
-      tmem_ld_wait();
-      tmem_ld32_issue(taddr + 96, rb);
-      scan_chunk(ra, n0 + 8, best);
-      tmem_ld_wait();
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + acc);  // TMEM stage is free as soon as the registers hold it
-      scan_chunk(rb, n0 + 12, best);
-    }
-    {
-      const size_t q = (size_t)qtile * kQueriesPerCta + h * 128 + row;
-      const size_t o = ((size_t)split * n_query_padded + q) * kCand;
-      *reinterpret_cast<float4*>(cand_score + o) = make_float4(best.s[0], best.s[1], best.s[2], best.s[3]);
-      *reinterpret_cast<int4*>(cand_idx + o) = make_int4(best.i[0], best.i[1], best.i[2], best.i[3]);
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// 2-SM variant: a cluster of two CTAs issues tcgen05.mma.cta_group::2 (M = 256 = 2 x 128 query rows, N = 256 train
-// rows per instruction).  Each CTA stages its own 128-row query tile and ITS HALF of every 256-row train tile, so per
-// SM and MMA only 4 KB (A) + 4 KB (half of B) are read from shared memory instead of 8 + 8 KB for the same FLOPs:
-// the 1-SM kernel above is bound by the 128 B/clk shared-memory port (ncu: tensor pipe 79 % active), this one is not.
+// A cluster of two CTAs issues tcgen05.mma.cta_group::2 (M = 256 = 2 x 128 query rows, N = 256 train rows per
+// instruction).  Each CTA stages its own 128-row query tile and ITS HALF of every 256-row train tile, so per SM and MMA
+// only 4 KB (A) + 4 KB (half of B) are read from shared memory instead of 8 + 8 KB for the same FLOPs: a 1-SM
+// (cta_group::1) version of this kernel is bound by the 128 B/clk shared-memory port, this one is not.
 //   leader CTA (rank 0): MMA issue; waits for its own and the peer's operand halves, commits with multicast so the
 //                        smem-free and accumulator-ready barriers of BOTH CTAs are signalled;
 //   peer CTA (rank 1):   warp 1 relays "my half has landed" to the leader; epilogue warps arrive remotely on the
@@ -324,6 +190,7 @@ match_tc_kernel(const __half* __restrict__ Ah, const __half* __restrict__ Bh, in
 constexpr int kStages2 = 4;
 constexpr int kTileRows2 = 256;                 // train rows per stage (128 per CTA)
 constexpr size_t kSmemBytes2 = (1 + kStages2) * kTileBytes + 512;
+// kind::f16: D = f32 (bit 4), A = B = f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kIdesc2 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);  // M = 256, N = 256
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -630,25 +497,16 @@ __global__ void zero_u32_kernel(unsigned int* p, int n) {
 }
 
 struct Plan {
-  int nq_pad, nt_pad, n_qtiles, n_tiles, splits, tiles_per_split;  // tiles = kTileRows2-row tiles when two_sm
+  int nq_pad, nt_pad, n_qtiles, n_tiles, splits, tiles_per_split;  // tiles = kTileRows2-row train tiles
   size_t off_a, off_b, off_cs, off_ci, off_stats, off_rows, total;
 };
 
-static bool use_two_sm() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("FC_MATCH_1SM");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-
 static Plan make_plan(int nq, int nt) {
   Plan p;
-  const int tile_rows = use_two_sm() ? kTileRows2 : kTileRows;
+  const int tile_rows = kTileRows2;
   p.nq_pad = div_up(nq, kQueriesPerCta) * kQueriesPerCta;
   p.nt_pad = div_up(nt, tile_rows) * tile_rows;
-  p.n_qtiles = p.nq_pad / kQueriesPerCta;  // 256 queries: one CTA (1-SM kernel) or one CTA pair (2-SM kernel)
+  p.n_qtiles = p.nq_pad / kQueriesPerCta;  // 256 queries per CTA pair
   p.n_tiles = p.nt_pad / tile_rows;
   // number of train splits: fill the 148 SMs (1 CTA each) in whole waves, keep >= 16 tiles per CTA when possible
   int want = 1;
@@ -656,7 +514,7 @@ static Plan make_plan(int nq, int nt) {
   // (every extra split costs a second set of candidates in the re-rank: only split when it buys >= 15 %)
   for (int s = 1; s <= kMaxSplits && s <= p.n_tiles; ++s) {
     if (s > 1 && p.n_tiles / s < 16) break;
-    const int ctas = p.n_qtiles * s * (use_two_sm() ? 2 : 1);
+    const int ctas = p.n_qtiles * s * 2;
     const double eff = (double)ctas / ((double)div_up(ctas, 148) * 148.0);
     if (eff > best_eff + 0.15) { best_eff = eff; want = s; }
   }
@@ -711,14 +569,10 @@ extern "C" int fc_match_knn2(const float* query, int n_query, const float* train
   tc::match_prep_kernel<<<div_up(p.nt_pad * 32, 256), 256, 0, st>>>(train, n_train, p.nt_pad, 0, Bh, stats);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
-  if (tc::use_two_sm()) {
+  {
     FC_CUDA_TRY(cudaFuncSetAttribute(tc::match_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes2));
     dim3 grid(2 * p.n_qtiles, p.splits);
     tc::match_tc2_kernel<<<grid, tc::kThreads, tc::kSmemBytes2, st>>>(Ah, Bh, p.nq_pad, p.n_tiles, p.tiles_per_split, cs, ci);
-  } else {
-    FC_CUDA_TRY(cudaFuncSetAttribute(tc::match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes));
-    dim3 grid(p.n_qtiles, p.splits);
-    tc::match_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(Ah, Bh, p.nq_pad, p.n_tiles, p.tiles_per_split, cs, ci);
   }
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();

@@ -11,8 +11,6 @@
 //
 // HBM traffic per octave pixel (T = float): 4 B base read + 4 B x n_levels written; the extrema kernel
 // re-reads the levels once (+ 4 B x n_levels) -- DESIGN.md states the algorithmic figure (24 B).
-#include <stdlib.h>
-
 #include "fc_common.cuh"
 
 namespace fc {
@@ -609,15 +607,10 @@ __global__ void convert_f64_kernel(const double* __restrict__ src, int64_t n, T*
 // Fused fast path for the reference's default scale space (sigma 1.6, s = 2 -> radii 3, 5, 6, 9, 13; float32)
 // ------------------------------------------------------------------------------------------------
 // Every level blurs the SAME base image, so the vertical pass is done once for all levels: the 34 input values of
-// a column segment are loaded once, the symmetric pair sums v[-k] + v[+k] are formed once (13 FADD) and feed the
-// R_l + 1 FFMA of every level (taps are kernel-parameter constants with compile-time offsets: FFMA operands, no
+// a column segment are loaded once, the symmetric pair sums v[-k] + v[+k] are formed once and feed the R_l + 1
+// multiply-adds of every level (taps are kernel-parameter constants with compile-time offsets: FFMA operands, no
 // registers).  The five intermediate tiles stay in shared memory together, so the five horizontal passes follow
-// without any barrier in between: 2 block-wide barriers per tile instead of 10, 40 % fewer shared-memory loads and
-// 13 % fewer FP instructions than the level-by-level kernel above.
-struct FusedTaps {
-  float t[5][14];  // t[l][k] = tap at distance k of level l (centre first)
-};
-
+// without any barrier in between: 2 block-wide barriers per tile instead of 10.
 template <int L> struct FusedRadius;
 template <> struct FusedRadius<0> { static constexpr int R = 3; };
 template <> struct FusedRadius<1> { static constexpr int R = 5; };
@@ -625,138 +618,14 @@ template <> struct FusedRadius<2> { static constexpr int R = 6; };
 template <> struct FusedRadius<3> { static constexpr int R = 9; };
 template <> struct FusedRadius<4> { static constexpr int R = 13; };
 
-static constexpr int kFTX = 64, kFTY = 32, kFR = 13, kFRP = 16;
-static constexpr int kFIW = kFTX + 2 * kFR;       // 90 input columns
-static constexpr int kFIP = kFIW + 1;             // input pitch
-static constexpr int kFIH = kFTY + 2 * kFR;       // 58 input rows
-static constexpr int kFTP = kFTX + 2 * kFRP + 4;  // tmp pitch (100), multiple of 4
-static constexpr int kFInElems = (kFIH * kFIP + 3) & ~3;
-static constexpr size_t kFusedSmem = sizeof(float) * (kFInElems + 5 * kFTY * kFTP);
-
-template <int L>
-__device__ __forceinline__ void fused_vertical_level(const FusedTaps& taps, float centre, const float (&s)[kFR + 1],
-                                                     float* __restrict__ dst) {
-  constexpr int R = FusedRadius<L>::R;
-  float acc = taps.t[L][0] * centre;
-#pragma unroll
-  for (int k = 1; k <= R; ++k) acc = fmaf(taps.t[L][k], s[k], acc);
-  *dst = acc;
-}
-
-// 8 output columns per thread: TY * TX / 8 = 256 items = exactly one per thread, no loop
-template <int L>
-__device__ __forceinline__ void fused_horizontal_level(const FusedTaps& taps, const float* __restrict__ sTmp,
-                                                       float* __restrict__ out, int x0, int y0, int H, int W, bool vec_ok) {
-  constexpr int R = FusedRadius<L>::R;
-  constexpr int RP = (R + 3) & ~3;
-  constexpr int NV = (8 + 2 * RP) / 4;
-  constexpr int G = kFTX / 8;
-  static_assert(kFTY * G == 256, "one item per thread");
-  const int y = threadIdx.x / G;
-  const int g = threadIdx.x - y * G;
-  const float4* src = reinterpret_cast<const float4*>(sTmp + L * kFTY * kFTP + (kFRP - RP) + y * kFTP + g * 8);
-  float v[4 * NV];
-#pragma unroll
-  for (int q = 0; q < NV; ++q) {
-    const float4 t = src[q];
-    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-  }
-  float r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float acc = taps.t[L][0] * v[j + RP];
-#pragma unroll
-    for (int k = 1; k <= R; ++k) acc = fmaf(taps.t[L][k], v[j + RP - k] + v[j + RP + k], acc);
-    r[j] = acc;
-  }
-  const int yy = y0 + y, xx = x0 + g * 8;
-  if (yy < H && xx < W) {
-    float* dst = out + (size_t)yy * W + xx;
-    if (vec_ok && xx + 7 < W) {
-      reinterpret_cast<float4*>(dst)[0] = make_float4(r[0], r[1], r[2], r[3]);
-      reinterpret_cast<float4*>(dst)[1] = make_float4(r[4], r[5], r[6], r[7]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (xx + j < W) dst[j] = r[j];
-    }
-  }
-}
-
-// IDENT0: level 0 is the base itself (octaves > 0), only levels 1..4 are blurred
-template <bool IDENT0>
-__global__ void __launch_bounds__(256, 2)
-gauss_octave_fused_kernel(const float* __restrict__ base, int H, int W, FusedTaps taps, float* __restrict__ gauss) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sIn = reinterpret_cast<float*>(smem_raw);
-  float* sTmp = sIn + kFInElems;
-  const int x0 = blockIdx.x * kFTX, y0 = blockIdx.y * kFTY;
-  const int b = blockIdx.z;
-  const float* img = base + (size_t)b * H * W;
-  float* gout = gauss + (size_t)b * 5 * H * W;
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool interior_x = (x0 - kFR >= 0) && (x0 - kFR + kFIW <= W);
-    for (int r = warp; r < kFIH; r += 8) {
-      const int y = reflect_symm(y0 - kFR + r, H);
-      const float* row = img + (size_t)y * W;
-      float* dst = sIn + r * kFIP;
-      if (interior_x) {
-        const float* src = row + (x0 - kFR);
-        for (int c = lane; c < kFIW; c += 32) cp_async_elem<float>(dst + c, src + c);
-      } else {
-        for (int c = lane; c < kFIW; c += 32) cp_async_elem<float>(dst + c, row + reflect_symm(x0 - kFR + c, W));
-      }
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-  }
-  __syncthreads();
-  // fused vertical pass: item = (8-row group, input column)
-  for (int item = threadIdx.x; item < (kFTY / 8) * kFIW; item += 256) {
-    const int g = item / kFIW;
-    const int c = item - g * kFIW;
-    const float* src = sIn + (g * 8) * kFIP + c;
-    float v[8 + 2 * kFR];
-#pragma unroll
-    for (int k = 0; k < 8 + 2 * kFR; ++k) v[k] = src[k * kFIP];
-    float* dst = sTmp + (g * 8) * kFTP + (kFRP - kFR) + c;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s[kFR + 1];
-#pragma unroll
-      for (int k = 1; k <= kFR; ++k) s[k] = v[j + kFR - k] + v[j + kFR + k];
-      const float centre = v[j + kFR];
-      float* d = dst + j * kFTP;
-      if (!IDENT0) fused_vertical_level<0>(taps, centre, s, d);
-      fused_vertical_level<1>(taps, centre, s, d + 1 * kFTY * kFTP);
-      fused_vertical_level<2>(taps, centre, s, d + 2 * kFTY * kFTP);
-      fused_vertical_level<3>(taps, centre, s, d + 3 * kFTY * kFTP);
-      fused_vertical_level<4>(taps, centre, s, d + 4 * kFTY * kFTP);
-    }
-  }
-  const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gauss) & 15) == 0);
-  if (IDENT0) {
-    // level 0 of octaves > 0 is the unblurred base (:136-137); reads sIn only, so it can run before the barrier
-    for (int t = threadIdx.x; t < kFTX * kFTY; t += 256) {
-      const int r = t / kFTX, c = t - r * kFTX;
-      if (y0 + r < H && x0 + c < W) gout[(size_t)(y0 + r) * W + x0 + c] = sIn[(r + kFR) * kFIP + c + kFR];
-    }
-  }
-  __syncthreads();
-  const size_t plane = (size_t)H * W;
-  if (!IDENT0) fused_horizontal_level<0>(taps, sTmp, gout, x0, y0, H, W, vec_ok);
-  fused_horizontal_level<1>(taps, sTmp, gout + plane, x0, y0, H, W, vec_ok);
-  fused_horizontal_level<2>(taps, sTmp, gout + 2 * plane, x0, y0, H, W, vec_ok);
-  fused_horizontal_level<3>(taps, sTmp, gout + 3 * plane, x0, y0, H, W, vec_ok);
-  fused_horizontal_level<4>(taps, sTmp, gout + 4 * plane, x0, y0, H, W, vec_ok);
-}
+static constexpr int kFR = 13;  // largest radius of the default levels
 
 // ------------------------------------------------------------------------------------------------
-// Packed (FFMA2) variant of the fused default-radii kernel
+// Packed (FFMA2) arithmetic
 // ------------------------------------------------------------------------------------------------
-// The fused kernel above is issue-bound: 9.4 warp instructions per octave pixel of which only 4.9 are FP32 math.
-// sm_100 has packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2: one issue slot, two lanes of the FP32 pipe), so this
-// version keeps every value as an aligned pair of horizontally adjacent pixels:
+// A scalar version of this kernel is issue-bound: 9.4 warp instructions per octave pixel of which only 4.9 are FP32 math.
+// sm_100 has packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2: one issue slot, two lanes of the FP32 pipe), so every
+// value is kept as an aligned pair of horizontally adjacent pixels:
 //   * vertical pass: a thread owns a column PAIR and 8 output rows; the 34-row window, the 13 pair sums
 //     v[-k] + v[+k] (shared by all five levels) and the taps (t, t) are all float2 -> 13 FADD2 + 41 FFMA2 per output pair.
 //   * horizontal pass: a thread owns 12 consecutive output columns (6 pairs) of one row and walks the ALIGNED input
@@ -1006,28 +875,6 @@ static int launch_octave_packed(const void* base, int B, int H, int W, const dou
   return FC_OK;
 }
 
-static int launch_octave_fused(const void* base, int B, int H, int W, const double* taps_host, const int* tap_len_host,
-                               int first_is_identity, void* gauss, cudaStream_t st) {
-  FusedTaps ft;
-  const double* tp = taps_host;
-  for (int l = 0; l < 5; ++l) {
-    const int n = tap_len_host[l], r = n / 2;
-    for (int k = 0; k < 14; ++k) ft.t[l][k] = (k <= r) ? (float)tp[r + k] : 0.0f;
-    tp += n;
-  }
-  dim3 grid(div_up(W, kFTX), div_up(H, kFTY), B);
-  if (first_is_identity) {
-    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
-    gauss_octave_fused_kernel<true><<<grid, 256, kFusedSmem, st>>>((const float*)base, H, W, ft, (float*)gauss);
-  } else {
-    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
-    gauss_octave_fused_kernel<false><<<grid, 256, kFusedSmem, st>>>((const float*)base, H, W, ft, (float*)gauss);
-  }
-  note_launch();
-  FC_RETURN_IF_LAUNCH_FAILED();
-  return FC_OK;
-}
-
 // does the tap list describe the default radii (3, 5, 6, 9, 13) with symmetric taps?
 static bool fused_applicable(int L, const double* taps_host, const int* tap_len_host) {
   static const int want[5] = {7, 11, 13, 19, 27};
@@ -1131,8 +978,7 @@ static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_
                           uint32_t* extrema, cudaStream_t st) {
   const int nd = is_dog ? L : L - 1;
   if constexpr (sizeof(T) == 4) {
-    static const bool tiled_variant = getenv("FC_EXTREMA_TILED") != nullptr;  // A/B switch for profiling
-    if (!is_dog && !tiled_variant && W % 4 == 0 && H >= 3 && (reinterpret_cast<uintptr_t>(gauss) & 15) == 0) {
+    if (!is_dog && W % 4 == 0 && H >= 3 && (reinterpret_cast<uintptr_t>(gauss) & 15) == 0) {
       if (nd == 4) return launch_extrema_strip<4>(gauss, B, H, W, filter, cth, rth, extrema, st);
       if (nd == 3) return launch_extrema_strip<3>(gauss, B, H, W, filter, cth, rth, extrema, st);
       if (nd == 5) return launch_extrema_strip<5>(gauss, B, H, W, filter, cth, rth, extrema, st);
@@ -1162,10 +1008,7 @@ extern "C" int fc_gauss_octave(const void* base, int dtype, int batch, int heigh
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (dtype == FC_F32 && fused_applicable(n_levels, taps_host, tap_len_host)) {
-    static const bool scalar_variant = getenv("FC_PYRAMID_SCALAR") != nullptr;  // A/B switch for profiling
-    rc = scalar_variant
-             ? launch_octave_fused(base, batch, height, width, taps_host, tap_len_host, first_is_identity, gauss, st)
-             : launch_octave_packed(base, batch, height, width, taps_host, tap_len_host, first_is_identity, gauss, st);
+    rc = launch_octave_packed(base, batch, height, width, taps_host, tap_len_host, first_is_identity, gauss, st);
   } else
     rc = dtype == FC_F32
              ? launch_octave<float>(base, batch, height, width, n_levels, taps_host, tap_len_host, first_is_identity, gauss, st)
