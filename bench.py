@@ -286,7 +286,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="images per step per GPU")
     ap.add_argument("--ref-items-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sift-dtype", default=None, choices=["f32", "f64"])
+    ap.add_argument("--sift-dtype", default=None, choices=["mixed", "f32", "f64"])
     args = ap.parse_args()
     wl_cls = pick_workload(args.workload)
     wl = wl_cls(args)

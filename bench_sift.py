@@ -13,15 +13,15 @@ class SiftWorkload:
     name = "sift"
     metric = "sift_megapixels_per_sec"
     unit = "MP/s"
-    dtype = "f32"
+    dtype = "mixed"
     H = W = 1024
     cpu_sample_items = 16
     cpu_sample_note = "(256x256 crops of the same generator, oracle with separable blurs: the reference's direct 2-D convolution is ~5x slower and a 1024x1024 image takes ~5 min per core)"
 
     def __init__(self, args):
         self.batch = args.batch or 16
-        self.mode = getattr(args, "sift_dtype", None) or "f32"
-        self.dtype = self.mode
+        self.mode = getattr(args, "sift_dtype", None) or "mixed"
+        self.dtype = {"mixed": "f32 arithmetic + f64-certified decisions", "f32": "f32", "f64": "f64"}[self.mode]
 
     def describe(self, world):
         return {"workload": "config[1]: SIFT keypoints + descriptors, %d synthetic 1024x1024 float64 images per step per GPU "
@@ -51,7 +51,7 @@ class SiftWorkload:
 
     def _run(self, dev_in):
         base = self.sift.upsample2(dev_in, self.params)
-        return self.sift.detect_and_describe(base, self.params, out_dtype=self.torch.float32)
+        return self.sift.detect_and_describe(base, self.params, out_dtype=self.torch.float32)  # descriptors stay on the device
 
     def step_device(self, record=False):
         if record:
@@ -61,7 +61,7 @@ class SiftWorkload:
             res = self._run(self.dev_in)
         finally:
             self.sift.TIMER = None
-        self.desc_per_image = sum(b.descriptors.shape[0] for b in res.blocks if b.descriptors is not None) / self.batch
+        self.desc_per_image = res.total / self.batch
         return res
 
     def e2e_begin(self):
@@ -77,15 +77,15 @@ class SiftWorkload:
     def step_e2e(self):
         t = self.extractor.submit(None, prefetch_next=True)  # the pinned staging buffers already hold the images
         if self.pending is not None:
-            out = self.extractor.collect(self.pending)
-            self.io_bytes = self.extractor.bytes_per_batch(out)
+            rec, desc, cnt = self.extractor.collect(self.pending, raw=True)
+            self.io_bytes = self.extractor.bytes_per_batch(rec.shape[0])
         self.pending = t
         return self.io_bytes
 
     def e2e_end(self):
-        out = self.extractor.collect(self.pending)
+        rec, desc, cnt = self.extractor.collect(self.pending, raw=True)
         self.pending = None
-        self.io_bytes = self.extractor.bytes_per_batch(out)
+        self.io_bytes = self.extractor.bytes_per_batch(rec.shape[0])
         return self.io_bytes
 
     def dominant_kernel(self):
@@ -95,7 +95,7 @@ class SiftWorkload:
         alg = 24.0 * self.batch * (2 * self.H) * (2 * self.W)  # 4 B base read + 5 x 4 B levels written per octave pixel
         if self.mode == "f64":
             alg *= 2
-        return "gauss_octave_packed_kernel (octave 0)" if self.mode == "f32" else "gauss_octave_kernel (octave 0)", alg, ms, "hbm"
+        return "gauss_octave_packed_kernel (octave 0)" if self.mode != "f64" else "gauss_octave_kernel (octave 0)", alg, ms, "hbm"
 
     def traffic(self, tr):
         return tr["gauss_octave_packed_kernel"]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W) * (2 if self.mode == "f64" else 1)

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libfeaturecraft_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "featurecraft_b200.h")
 
 FC_OK = 0
-FC_F32, FC_F64 = 0, 1
+FC_F32, FC_F64, FC_F16 = 0, 1, 2
 FC_FILTER_APP, FC_FILTER_SCRIPT = 0, 1
 
 
@@ -58,18 +58,35 @@ SIGNATURES = {
     "fc_downsample2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fc_convert_f64": (_i, [_p, _i64, _i, _p, _p]),
     "fc_gradient_field": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
-    "fc_orientation_bins": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p]),
+    "fc_orientation_bins": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p]),
     "fc_gradient_field_packed": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "fc_descriptors_interleaved": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
-    "fc_orientation_bins_packed": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _p]),
+    "fc_descriptors_interleaved": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _p]),
+    "fc_sift_layout": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "fc_orientation_bins_packed": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p]),
+    "fc_orientation_bins_coded": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _d, _p, _p]),
+    "fc_orientation_recheck": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p]),
+    "fc_gradient_codes": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "fc_descriptors_coded": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _p]),
+    "fc_convert_f64_bound": (_i, [_p, _i64, _p, _p, _p]),
+    "fc_gauss_levels_f64": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "fc_gauss_octave_extrema_certified": (_i, [_p, _i, _i, _i, _i, _i, _d, _d, _p, _d, _p, _p, _i, _p, _p]),
+    "fc_extrema_repair": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _d, _d, _p, _p, _i, _p, _p]),
     "fc_orientation_scan": (_i, [_p, _i, _p, _p, _p]),
     "fc_orientation_emit": (_i, [_p, _p, _p, _i, _p, _p]),
-    "fc_descriptors": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p]),
+    "fc_descriptors": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _p]),
     "fc_match_workspace_bytes": (_i64, [_i, _i]),
     "fc_match_workspace_stats_offset": (_i64, [_i, _i]),
     "fc_match_knn2": (_i, [_p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),
     "fc_match_knn2_exact": (_i, [_p, _i, _p, _i, _d, _p, _p, _p, _p]),
 }
+
+
+
+class DescPlacement(C.Structure):
+    """fc_desc_placement of include/featurecraft_b200.h"""
+
+    _fields_ = [("remap", C.c_void_p), ("points", C.c_void_p), ("list_base", C.c_int), ("octave", C.c_int), ("scale", C.c_int)]
+
 
 _lib = None
 

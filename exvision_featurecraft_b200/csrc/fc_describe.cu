@@ -12,6 +12,8 @@
 //                              OpenCV's 10-bit fixed-point coordinates (:175-212), 4x4 cells x 8 bins with
 //                              float32 cell histograms, normalise / clip [2^-10, 0.2] / normalise (:259-287).
 //                              Two lanes per cell, 8 samples per lane, 8 private bins in registers.
+#include <cuda_fp16.h>
+
 #include "fc_common.cuh"
 
 namespace fc {
@@ -148,6 +150,101 @@ gradient_field4_kernel(const float* __restrict__ gauss, int L, int level, int H,
   if (packed) *reinterpret_cast<uint4*>(packed + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Certified mode: one 32-bit word per pixel = magnitude | exact direction code
+// ------------------------------------------------------------------------------------------------
+// Both consumers of the direction only ever look at which side of a multiple of 5 degrees it lies on: the
+// orientation histogram bins by np.round(direction * 36 / 360) (edges at 5, 15, ..; :140-142) and the descriptor by
+// int(((direction - theta) % 360) * 8 / 360) with theta = 10 b + 5 (edges at theta + 45 j; :263-268).  So the gradient
+// field is reduced to
+//   bits  5..0   o   = the reference's 36-bin orientation index (0..36, half-to-even on exact ties)
+//   bits  7..6   sub = 0: direction in [10 o - 5, 10 o), 1: in [10 o, 10 o + 5), 2: exactly 10 o + 5 (tie rounded down)
+//   bits 31..8   the float32 magnitude without its sign, rounded to 16 mantissa bits (relative error 2^-17)
+// i.e. the 5-degree sector is c = 2 o - 1 + sub.  Gradients are differences of the FLOAT64 level; the sector comes from
+// a float32 arctangent of the octant-reduced angle in [0, 45] degrees (error < 2e-5 degrees) unless that angle lies
+// within 1e-4 degrees of a multiple of 5: then -- and for vanishing gradients -- the reference's own float64
+// expression decides (np.rad2deg(np.arctan2(gy, gx)) % 360), so that the codes are the float64 pipeline's codes.
+__device__ __forceinline__ uint32_t direction_code_exact(double gy, double gx) {
+  const double deg = __dmul_rn(atan2(gy, gx), 57.29577951308232087680);
+  const double d = deg < 0.0 ? __dadd_rn(deg, 360.0) : deg;
+  const int o = (int)rint(__ddiv_rn(__dmul_rn(d, 36.0), 360.0));
+  const double centre = (double)(10 * o);
+  uint32_t sub = d >= centre ? 1u : 0u;
+  if (d == centre + 5.0) sub = 2u;
+  return (sub << 6) | (uint32_t)o;
+}
+
+__device__ __forceinline__ uint32_t gradient_code(double gxd, double gyd) {
+  const float x = (float)gxd, y = (float)gyd;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float m;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(fmaf(x, x, y * y)));
+  const uint32_t mbits = ((__float_as_uint(m) + 64u) >> 7) << 8;
+  float rcp;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(mx));
+  const float a = mn * rcp;
+  const float t = a * a;
+  float p = -2.323167295e-01f;
+  p = fmaf(p, t, 1.252680846e+00f);
+  p = fmaf(p, t, -3.203576766e+00f);
+  p = fmaf(p, t, 5.524598167e+00f);
+  p = fmaf(p, t, -7.969067623e+00f);
+  p = fmaf(p, t, 1.142854225e+01f);
+  p = fmaf(p, t, -1.909660375e+01f);
+  p = fmaf(p, t, 5.729574145e+01f);
+  const float r = p * a;  // octant-reduced angle in [0, 45] degrees
+  const float s = rintf(r * 0.2f);
+  const bool unsure = !(mx >= 1e-30f) || fabsf(fmaf(s, -5.0f, r)) < 1e-4f;
+  if (unsure) return mbits | direction_code_exact(gyd, gxd);
+  int c = __float2int_rd(r * 0.2f);  // sector of the reduced angle, 0..8 (r is at least 1e-4 away from every edge)
+  c = ay > ax ? 17 - c : c;          // reflections map 5-degree sectors onto 5-degree sectors
+  c = x < 0.f ? 35 - c : c;
+  c = y < 0.f ? 71 - c : c;
+  const uint32_t o = (uint32_t)(c + 1) >> 1;
+  return mbits | (((c & 1) ? 0u : 1u) << 6) | o;
+}
+
+// level = one float64 plane [B][n_planes][H][W] (plane index `plane_idx`); true convolution with [-1, 0, 1], 'symm' border
+__global__ void __launch_bounds__(256)
+gradient_codes_kernel(const double* __restrict__ levels, int n_planes, int plane_idx, int H, int W,
+                      uint32_t* __restrict__ codes) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= W) return;
+  const double* g = levels + ((size_t)b * n_planes + plane_idx) * H * W;
+  const int xl = x > 0 ? x - 1 : 0, xr = x < W - 1 ? x + 1 : W - 1;
+  const int yu = y > 0 ? y - 1 : 0, yd = y < H - 1 ? y + 1 : H - 1;
+  const double gx = g[(size_t)y * W + xl] - g[(size_t)y * W + xr];
+  const double gy = g[(size_t)yu * W + x] - g[(size_t)yd * W + x];
+  codes[((size_t)b * H + y) * W + x] = gradient_code(gx, gy);
+}
+
+// four pixels per thread (W % 4 == 0, 16-byte aligned planes): 32-byte loads, one 16-byte store
+__global__ void __launch_bounds__(256)
+gradient_codes4_kernel(const double* __restrict__ levels, int n_planes, int plane_idx, int H, int W,
+                       uint32_t* __restrict__ codes) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= W) return;
+  const double* g = levels + ((size_t)b * n_planes + plane_idx) * H * W;
+  const int yu = y > 0 ? y - 1 : 0, yd = y < H - 1 ? y + 1 : H - 1;
+  const double* row = g + (size_t)y * W;
+  const double2 c0 = *reinterpret_cast<const double2*>(row + x), c1 = *reinterpret_cast<const double2*>(row + x + 2);
+  const double2 u0 = *reinterpret_cast<const double2*>(g + (size_t)yu * W + x), u1 = *reinterpret_cast<const double2*>(g + (size_t)yu * W + x + 2);
+  const double2 d0 = *reinterpret_cast<const double2*>(g + (size_t)yd * W + x), d1 = *reinterpret_cast<const double2*>(g + (size_t)yd * W + x + 2);
+  const double left = row[x > 0 ? x - 1 : 0];
+  const double right = row[x + 4 < W ? x + 4 : W - 1];
+  uint4 out;
+  out.x = gradient_code(left - c0.y, u0.x - d0.x);
+  out.y = gradient_code(c0.x - c1.x, u0.y - d0.y);
+  out.z = gradient_code(c0.y - c1.y, u1.x - d1.x);
+  out.w = gradient_code(c1.x - right, u1.y - d1.y);
+  *reinterpret_cast<uint4*>(codes + ((size_t)b * H + y) * W + x) = out;
+}
+
 // 16-byte shared-memory vectors of the histogram type
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
@@ -170,11 +267,22 @@ static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the fi
 // histograms) is the same for every LPK, so small windows -- most keypoints sit in octave 0 with 15x15 or 21x21
 // windows -- use 8 lanes and amortise it over four keypoints per warp.  Sums are in T: double in exact (f64) mode,
 // float in f32 mode (whose parity bar is a tolerance), always in a fixed order (deterministic).
-template <typename T, int LPK, int NR, bool PACKED>
+// MODE: kOriPlanes = magnitude plane + bin plane (float64 exact mode and the standalone entry point), kOriPacked =
+// float32 mode's magnitude | bin words, kOriCoded = certified mode's magnitude | code words (gradient_codes_kernel).
+// The weight table holds |dy| <= wry, |dx| <= wrx only (the window is clipped to the image, so a table larger than
+// twice the image is never read): weight of offset (dy, dx) = weights[(dy + wry) * (2 wrx + 1) + dx + wrx].
+// kOriCoded also certifies its float32 histogram: `tol` bounds the relative error of a bin against the float64 sum
+// (magnitudes carry 2^-17, the float32 products and the running sums the rest); a keypoint with a bin within tol * max
+// of the 0.8 * max cut is marked (bit 63) for fc_orientation_recheck instead of being decided here.
+enum { kOriPlanes = 0, kOriPacked = 1, kOriCoded = 2 };
+static constexpr unsigned long long kOriRecheckBit = 1ull << 63;
+
+template <typename T, int LPK, int NR, int MODE>
 __global__ void __launch_bounds__(kOriWarps * 32)
 orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, int H, int W,
                    const int32_t* __restrict__ keypoints, int n_keypoints, const T* __restrict__ weights,
-                   int radius, unsigned long long* __restrict__ bin_mask) {
+                   int radius, int wry, int wrx, float tol, unsigned long long* __restrict__ bin_mask) {
+  constexpr bool PACKED = MODE != kOriPlanes;
   constexpr int KPW = 32 / LPK;        // keypoints per warp
   constexpr int PITCH = LPK;           // [bin][lane]: rows of LPK values, so clearing and the final sums move 16 bytes at a time
   constexpr int NB = (kOriBins + LPK - 1) / LPK;  // bins reduced by one lane
@@ -199,7 +307,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const uint8_t* ob = PACKED ? nullptr : obin + (size_t)b * H * W;
   // PACKED (float only): `mag` holds fc_gradient_field_packed's words = magnitude | bin
   const uint32_t* pk = reinterpret_cast<const uint32_t*>(m);
-  const int side = 2 * radius + 1;
+  const int side = 2 * wrx + 1;
   // clip the window to the image (outside is zero padding = no contribution)
   const int r0 = max(ki - radius, 0), r1 = valid ? min(ki + radius, H - 1) : -1;
   const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
@@ -207,7 +315,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   // gathers, one table load and one private shared-memory update -- no index division.  Two rows (2*NR samples
   // per lane) are loaded before the first dependent histogram update.
   // NR = column rounds that cover the window (template parameter, chosen by the launcher from the radius)
-  const int woff = (radius - ki) * side + (radius - kj);  // weight of image pixel (r, c): weights[woff + r*side + c]
+  const int woff = (wry - ki) * side + (wrx - kj);  // weight of image pixel (r, c): weights[woff + r*side + c]
   const int rounds = (c1 - c0 + LPK) / LPK;
   T* hme = h + sub;
   if (rounds <= NR) {
@@ -229,7 +337,8 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
             if constexpr (PACKED) {
               const uint32_t p = pk[ro + c];
               bins[v][u] = (int)(p & 63u);
-              ws[v][u] = (T)__fmul_rn(__uint_as_float(p & ~63u), (float)weights[wo + c]);
+              const float pm = MODE == kOriCoded ? __uint_as_float((p & ~255u) >> 1) : __uint_as_float(p & ~63u);
+              ws[v][u] = (T)__fmul_rn(pm, (float)weights[wo + c]);
             } else {
               bins[v][u] = ob[ro + c];
               ws[v][u] = Math<T>::mul(m[ro + c], weights[wo + c]);
@@ -248,7 +357,8 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
       for (int c = c0 + sub; c <= c1; c += LPK) {
         if constexpr (PACKED) {
           const uint32_t p = pk[rr * W + c];
-          hme[(p & 63u) * PITCH] += (T)__fmul_rn(__uint_as_float(p & ~63u), (float)weights[woff + rr * side + c]);
+          const float pm = MODE == kOriCoded ? __uint_as_float((p & ~255u) >> 1) : __uint_as_float(p & ~63u);
+          hme[(p & 63u) * PITCH] += (T)__fmul_rn(pm, (float)weights[woff + rr * side + c]);
         } else {
           hme[ob[rr * W + c] * PITCH] += Math<T>::mul(m[rr * W + c], weights[woff + rr * side + c]);
         }
@@ -274,7 +384,10 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   }
 #pragma unroll
   for (int o = LPK / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float cut = __fmul_rn(0.8f, mx);  // NEP 50: python float * float32 scalar stays float32
+  // numpy >= 2 (NEP 50, what the golden vectors were produced with): python float * float32 scalar stays float32.
+  // The reference pins numpy 1.26, whose legacy promotion rounds the float64 product 0.8 * max to float32 instead: the
+  // two cuts differ by at most one float32 ulp, i.e. only for a bin that sits exactly on the cut (parity).
+  const float cut = __fmul_rn(0.8f, mx);
   uint32_t lo = 0u, hi = 0u;
 #pragma unroll
   for (int q = 0; q < NB; ++q) {
@@ -282,6 +395,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
     if (bin < kOriBins && f[q] >= cut) {
       if (bin < 32) lo |= 1u << bin; else hi |= 1u << (bin - 32);
     }
+    if (MODE == kOriCoded && bin < kOriBins && fabsf(f[q] - cut) <= tol * mx) hi |= 0x80000000u;
   }
 #pragma unroll
   for (int o = LPK / 2; o > 0; o >>= 1) {
@@ -310,17 +424,151 @@ __global__ void orientation_emit_kernel(const int32_t* __restrict__ keypoints, c
   }
 }
 
+// Certified mode: the keypoints orientation_kernel<.., kOriCoded> marked (bit 63) are decided here the way the float64
+// pipeline decides them -- float64 magnitudes from the float64 level, float64 window weights, the exact bin codes,
+// float64 sums rounded to float32 (:158-163), cut at float32(0.8) * max.  One warp per keypoint (unmarked ones leave
+// at once), per-lane private histograms, fixed summation order.
+static constexpr int kRecheckWarps = 4;
+
+__global__ void __launch_bounds__(kRecheckWarps * 32)
+orientation_recheck_kernel(const double* __restrict__ levels, int n_planes, int plane_idx, const uint32_t* __restrict__ codes,
+                           int H, int W, const int32_t* __restrict__ keypoints, int n_keypoints,
+                           const double* __restrict__ weights, int radius, int wry, int wrx,
+                           unsigned long long* __restrict__ bin_mask) {
+  __shared__ double hist[kRecheckWarps][kOriBins + 1][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kRecheckWarps + warp;
+  if (n >= n_keypoints) return;                    // warp-uniform; no block-wide barrier below
+  if (!(bin_mask[n] & kOriRecheckBit)) return;
+  for (int bn = 0; bn <= kOriBins; ++bn) hist[warp][bn][lane] = 0.0;
+  __syncwarp();
+  const int b = keypoints[3 * n], ki = keypoints[3 * n + 1], kj = keypoints[3 * n + 2];
+  const double* g = levels + ((size_t)b * n_planes + plane_idx) * H * W;
+  const uint32_t* pk = codes + (size_t)b * H * W;
+  const int side = 2 * wrx + 1;
+  const int r0 = max(ki - radius, 0), r1 = min(ki + radius, H - 1);
+  const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
+  const int woff = (wry - ki) * side + (wrx - kj);
+  for (int r = r0; r <= r1; ++r) {
+    const int ru = r > 0 ? r - 1 : 0, rd = r < H - 1 ? r + 1 : H - 1;
+    for (int c = c0 + lane; c <= c1; c += 32) {
+      const int cl = c > 0 ? c - 1 : 0, cr = c < W - 1 ? c + 1 : W - 1;
+      const double gx = g[(size_t)r * W + cl] - g[(size_t)r * W + cr];
+      const double gy = g[(size_t)ru * W + c] - g[(size_t)rd * W + c];
+      const double m = sqrt(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)));
+      hist[warp][pk[(size_t)r * W + c] & 63u][lane] += __dmul_rn(m, weights[woff + r * side + c]);
+    }
+  }
+  __syncwarp();
+  // lane q reduces bin q (and bin q + 32): lanes 0, 1, 2, ... in order
+  float f0 = -1.0f, f1 = -1.0f;
+  {
+    double a = 0.0;
+    for (int l = 0; l < 32; ++l) a += hist[warp][lane][l];
+    f0 = (float)a;
+    if (lane + 32 < kOriBins) {
+      double a1 = 0.0;
+      for (int l = 0; l < 32; ++l) a1 += hist[warp][lane + 32][l];
+      f1 = (float)a1;
+    }
+  }
+  float mx = fmaxf(f0, f1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float cut = __fmul_rn(0.8f, mx);
+  const uint32_t lo = __ballot_sync(0xffffffffu, f0 >= cut);
+  const uint32_t hi = __ballot_sync(0xffffffffu, lane + 32 < kOriBins && f1 >= cut);
+  if (lane == 0) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Final placement of the batched pipeline's outputs
+// ------------------------------------------------------------------------------------------------
+// The pipeline keeps its lists block-major: (octave, scale) blocks one after the other, each sorted by (image, row,
+// col, bin).  The caller wants image-major.  From the two scans the pipeline already has -- row_offs (cumulative
+// keypoints over the concatenated mask rows of all blocks) and ori_offs (cumulative oriented keypoints over all
+// keypoints) -- this single-CTA kernel derives, per block i and image b, the list index OB(i, b) of the first oriented
+// keypoint and its final row, plus the per-image totals.
+struct LayoutBlocks {
+  int n_blocks;
+  int row_start[64];  // first row of block i in the concatenated row array
+  int height[64];     // image rows per image in block i
+};
+
+__global__ void __launch_bounds__(256)
+sift_layout_kernel(const int32_t* __restrict__ row_offs, const int32_t* __restrict__ ori_offs, const LayoutBlocks lb, int batch,
+                   int2* __restrict__ remap, int32_t* __restrict__ image_counts) {
+  extern __shared__ int s_start[];  // [batch + 1] first final row of every image
+  auto first = [&](int i, int b) { return ori_offs[row_offs[lb.row_start[i] + b * lb.height[i]]]; };
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    int total = 0;
+    for (int i = 0; i < lb.n_blocks; ++i) total += first(i, b + 1) - first(i, b);
+    image_counts[b] = total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 0; b < batch; ++b) { s_start[b] = run; run += image_counts[b]; }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    int run = s_start[b];
+    for (int i = 0; i < lb.n_blocks; ++i) {
+      const int ob = first(i, b);
+      remap[i * batch + b] = make_int2(ob, run);
+      run += first(i, b + 1) - ob;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 static constexpr int kDescWarps = 4;
 static constexpr int kTrigStride = 2 + 32;
 
 // Persistent: every CTA converts the host tables once (Gaussian mask, bin edges, the fixed-point column deltas as
 // int32, cos / sin) into shared memory, then its warps walk the oriented keypoints with stride = warps in the grid.
-// IL: `mag` holds interleaved (magnitude, direction) pairs (fc_gradient_field_packed), `dir` is unused
-template <typename T, typename OUT, bool IL>
+// LAYOUT: kDescPlanes = separate magnitude / direction planes, kDescInterleaved = `mag` holds interleaved (magnitude,
+// direction) pairs (fc_gradient_field_packed), kDescCoded = `mag` holds certified mode's magnitude | code words
+// (gradient_codes_kernel): the descriptor bin is then integer arithmetic on the exact 5-degree sector,
+//   sector of (direction - theta) = (2 (o - b) - 2 + sub) mod 72,  bin = sector / 9   (theta = 10 b + 5),
+// so no float rounding can move a sample across a bin edge.
+enum { kDescPlanes = 0, kDescInterleaved = 1, kDescCoded = 2 };
+
+// Output placement: without `remap` descriptor n of this call goes to row n.  With it (the batched pipeline) the rows
+// land directly in the caller's final order -- images one after the other, each image in the reference's emission order
+// (octave, scale, row-major, bin): remap[image] = (index of the image's first oriented keypoint of this (octave, scale)
+// block in the block-major list, its final row), see sift_layout_kernel; `points` then receives the matching keypoint
+// records (int16 row, int16 col, uint8 octave, uint8 scale, uint8 orientation bin, 0) so that no sort or gather pass
+// over the descriptors is needed afterwards.
+struct DescPlacement {
+  const int2* remap;  // [batch] or null
+  uint2* points;      // final-order keypoint records or null
+  int list_base;      // index of this call's first oriented keypoint in the block-major list
+  int octave, scale;
+};
+
+template <typename OUT> struct Store4;
+template <> struct Store4<float> {
+  static __device__ __forceinline__ void put(float* d, float a, float b, float c, float e) { *reinterpret_cast<float4*>(d) = make_float4(a, b, c, e); }
+};
+template <> struct Store4<double> {
+  static __device__ __forceinline__ void put(double* d, double a, double b, double c, double e) {
+    reinterpret_cast<double2*>(d)[0] = make_double2(a, b);
+    reinterpret_cast<double2*>(d)[1] = make_double2(c, e);
+  }
+};
+template <> struct Store4<__half> {
+  static __device__ __forceinline__ void put(__half* d, float a, float b, float c, float e) {
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, e);
+    *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  }
+};
+
+template <typename T, typename OUT, int LAYOUT>
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, int W, const int32_t* __restrict__ oriented,
-                  int n_oriented, const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc) {
+                  int n_oriented, const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc,
+                  const DescPlacement place) {
   using ACC = T;  // per-sample arithmetic: double in exact mode, float in f32 mode (tolerance-based parity)
   __shared__ int sXY[kDescWarps][32];       // x0[0..15], y0[0..15] per warp
   __shared__ ACC sHist[kDescWarps][9][32];  // per-lane private bins 0..8 (8 = dropped), [bin][lane]: conflict free
@@ -364,8 +612,10 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
 #pragma unroll
     for (int k = 0; k < 9; ++k) myh[k * 32] = ACC(0);
     __syncwarp();
+    constexpr bool IL = LAYOUT == kDescInterleaved;
+    constexpr bool CODED = LAYOUT == kDescCoded;
     const T* m = mag + (size_t)b * H * W * (IL ? 2 : 1);
-    const T* d = IL ? nullptr : dir + (size_t)b * H * W;
+    const T* d = LAYOUT == kDescPlanes ? dir + (size_t)b * H * W : nullptr;
     const int4 ad4 = *reinterpret_cast<const int4*>(&sAd[bin][cx]);
     const int4 bd4 = *reinterpret_cast<const int4*>(&sBd[bin][cx]);
     const int ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w}, bd[4] = {bd4.x, bd4.y, bd4.z, bd4.w};
@@ -374,6 +624,7 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     const bool interior = (ki >= 12) && (ki < H - 12) && (kj >= 12) && (kj < W - 12);
     // all 8 gathers of the lane are issued before the first dependent histogram update
     T mv[2][4], dv[2][4];
+    int sect[2][4];  // CODED: 2 o - 1 + sub of the sample
 #pragma unroll
     for (int ry = 0; ry < 2; ++ry) {
       const int X0 = sXY[warp][cy + ry], Y0 = sXY[warp][16 + cy + ry];
@@ -383,7 +634,14 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
         const int Y = (Y0 + bd[rx]) >> 10;
         const bool in = interior || (((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H));
         const int o = in ? Y * W + X : 0;  // one image plane has fewer than 2^30 pixels (checked on the host)
-        if constexpr (IL) {
+        sect[ry][rx] = 0;
+        if constexpr (CODED) {
+          static_assert(!CODED || sizeof(T) == 4, "code words carry a float32 magnitude");
+          const uint32_t p = in ? reinterpret_cast<const uint32_t*>(m)[o] : 0u;
+          mv[ry][rx] = (T)__uint_as_float((p & ~255u) >> 1);
+          dv[ry][rx] = T(0);
+          sect[ry][rx] = 2 * (int)(p & 63u) - 1 + (int)((p >> 6) & 3u);
+        } else if constexpr (IL) {
           static_assert(!IL || sizeof(T) == 4, "interleaved planes are float32");
           const float2 v = reinterpret_cast<const float2*>(m)[o];
           mv[ry][rx] = in ? (T)v.x : T(0);
@@ -404,7 +662,12 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
         ACC rel = Math<ACC>::add((ACC)dv[ry][rx], -theta_a);
         if (rel < ACC(0)) rel = Math<ACC>::add(rel, ACC(360));
         int hb;
-        if constexpr (sizeof(ACC) == 4) {
+        if constexpr (CODED) {
+          int sc = sect[ry][rx] - (2 * bin + 1);  // in [-72, 72]
+          sc += sc < 0 ? 72 : 0;
+          sc -= sc >= 72 ? 72 : 0;
+          hb = (sc * 57) >> 9;                    // sc / 9 for 0 <= sc < 72
+        } else if constexpr (sizeof(ACC) == 4) {
           // f32 mode: truncate rel / 45 and repair the one-off at the bin edges with a single compare
           hb = __float2int_rz(rel * 0.022222222f);
           hb += (rel >= 45.0f * (float)(hb + 1)) ? 1 : 0;
@@ -463,20 +726,22 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    OUT* dst = desc + (size_t)n * 128 + lane * 4;
+    size_t row = (size_t)n;
+    if (place.remap) {
+      const int2 rm = place.remap[b];
+      row = (size_t)(rm.y + (place.list_base + n - rm.x));
+    }
+    if (place.points && lane == 0)
+      place.points[row] = make_uint2(((uint32_t)ki & 0xffffu) | ((uint32_t)kj << 16),
+                                     (uint32_t)place.octave | ((uint32_t)place.scale << 8) | ((uint32_t)bin << 16));
+    OUT* dst = desc + row * 128 + lane * 4;
     if constexpr (sizeof(NT) == 4) {
       const float inv2 = rsqrtf(s2);
-      if (sizeof(OUT) == 4) {
-        *reinterpret_cast<float4*>(dst) = make_float4(f[0] * inv2, f[1] * inv2, f[2] * inv2, f[3] * inv2);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = (OUT)(f[k] * inv2);
-      }
+      Store4<OUT>::put(dst, f[0] * inv2, f[1] * inv2, f[2] * inv2, f[3] * inv2);
     } else {
       const NT nrm2 = sqrt_seq(s2);
       const NT rn2 = rcp_seq(nrm2);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dst[k] = (OUT)div_seq(f[k], nrm2, rn2);
+      Store4<OUT>::put(dst, div_seq(f[0], nrm2, rn2), div_seq(f[1], nrm2, rn2), div_seq(f[2], nrm2, rn2), div_seq(f[3], nrm2, rn2));
     }
     __syncwarp();  // the next keypoint rewrites sXY and the private bins
   }
@@ -556,35 +821,42 @@ extern "C" int fc_gradient_field_packed(const void* gauss, int batch, int n_leve
                                nullptr, magnitude_bin, stream);
 }
 
-static int launch_orientation(const void* magnitude, const uint8_t* orientation_bin, int dtype, bool packed, int batch,
+static int launch_orientation(const void* magnitude, const uint8_t* orientation_bin, int dtype, int mode, int batch,
                               int height, int width, const int32_t* keypoints, int n_keypoints, const void* weights,
-                              int radius, uint64_t* bin_mask, void* stream) {
-  if (!magnitude || (!packed && !orientation_bin) || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0)
+                              int radius, int table_ry, int table_rx, float tol, uint64_t* bin_mask, void* stream) {
+  if (!magnitude || (mode == kOriPlanes && !orientation_bin) || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0)
+    return FC_ERR_BAD_ARG;
+  // the table must cover every offset of the image-clipped window
+  if (table_ry < (radius < height - 1 ? radius : height - 1) || table_rx < (radius < width - 1 ? radius : width - 1))
     return FC_ERR_BAD_ARG;
   if (n_keypoints == 0) return FC_OK;
   if (!keypoints || !bin_mask || n_keypoints < 0) return FC_ERR_BAD_ARG;
   if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
+  if ((int64_t)(2 * table_ry + 1) * (2 * table_rx + 1) > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype != FC_F32 && dtype != FC_F64) return FC_ERR_BAD_ARG;
   // lanes per keypoint by window size: (2r+1)^2 <= 441 samples -> 8, <= 961 -> 16, else a whole warp; the number
   // of column rounds per row is a template parameter so that the row loop is fully unrolled and predicated
   const int lpk = radius <= 10 ? 8 : (radius <= 15 ? 16 : 32);
   const int nr = div_up(2 * radius + 1, lpk);
-#define FC_ORI(T, LPK, NR, PK)                                                                                      \
-  orientation_kernel<T, LPK, NR, PK><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(        \
+#define FC_ORI(T, LPK, NR, MD)                                                                                      \
+  orientation_kernel<T, LPK, NR, MD><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(        \
       (const T*)magnitude, orientation_bin, height, width, keypoints, n_keypoints, (const T*)weights, radius,      \
-      (unsigned long long*)bin_mask)
-#define FC_ORI_T(T, PK)                                              \
+      table_ry, table_rx, tol, (unsigned long long*)bin_mask)
+#define FC_ORI_T(T, MD)                                              \
   do {                                                               \
     if (lpk == 8) {                                                  \
-      if (nr <= 1) FC_ORI(T, 8, 1, PK); else if (nr == 2) FC_ORI(T, 8, 2, PK); else FC_ORI(T, 8, 3, PK); \
+      if (nr <= 1) FC_ORI(T, 8, 1, MD); else if (nr == 2) FC_ORI(T, 8, 2, MD); else FC_ORI(T, 8, 3, MD); \
     } else if (lpk == 16) {                                          \
-      FC_ORI(T, 16, 2, PK);                                          \
+      FC_ORI(T, 16, 2, MD);                                          \
     } else {                                                         \
-      if (nr <= 2) FC_ORI(T, 32, 2, PK); else if (nr == 3) FC_ORI(T, 32, 3, PK); else if (nr == 4) FC_ORI(T, 32, 4, PK); else FC_ORI(T, 32, 5, PK); \
+      if (nr <= 2) FC_ORI(T, 32, 2, MD); else if (nr == 3) FC_ORI(T, 32, 3, MD); else if (nr == 4) FC_ORI(T, 32, 4, MD); else FC_ORI(T, 32, 5, MD); \
     }                                                                \
   } while (0)
-  if (packed) FC_ORI_T(float, true); else if (dtype == FC_F32) FC_ORI_T(float, false); else FC_ORI_T(double, false);
+  if (mode == kOriCoded) FC_ORI_T(float, kOriCoded);
+  else if (mode == kOriPacked) FC_ORI_T(float, kOriPacked);
+  else if (dtype == FC_F32) FC_ORI_T(float, kOriPlanes);
+  else FC_ORI_T(double, kOriPlanes);
 #undef FC_ORI_T
 #undef FC_ORI
   note_launch();
@@ -594,16 +866,56 @@ static int launch_orientation(const void* magnitude, const uint8_t* orientation_
 
 extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
                                    int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
-                                   uint64_t* bin_mask, void* stream) {
-  return launch_orientation(magnitude, orientation_bin, dtype, false, batch, height, width, keypoints, n_keypoints, weights,
-                            radius, bin_mask, stream);
+                                   int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
+  return launch_orientation(magnitude, orientation_bin, dtype, kOriPlanes, batch, height, width, keypoints, n_keypoints,
+                            weights, radius, table_ry, table_rx, 0.f, bin_mask, stream);
 }
 
 extern "C" int fc_orientation_bins_packed(const uint32_t* magnitude_bin, int batch, int height, int width,
                                           const int32_t* keypoints, int n_keypoints, const float* weights, int radius,
-                                          uint64_t* bin_mask, void* stream) {
-  return launch_orientation(magnitude_bin, nullptr, FC_F32, true, batch, height, width, keypoints, n_keypoints, weights,
-                            radius, bin_mask, stream);
+                                          int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
+  return launch_orientation(magnitude_bin, nullptr, FC_F32, kOriPacked, batch, height, width, keypoints, n_keypoints, weights,
+                            radius, table_ry, table_rx, 0.f, bin_mask, stream);
+}
+
+extern "C" int fc_orientation_bins_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* keypoints,
+                                         int n_keypoints, const float* weights, int radius, int table_ry, int table_rx,
+                                         double tolerance, uint64_t* bin_mask, void* stream) {
+  if (!(tolerance >= 0.0)) return FC_ERR_BAD_ARG;
+  return launch_orientation(codes, nullptr, FC_F32, kOriCoded, batch, height, width, keypoints, n_keypoints, weights, radius,
+                            table_ry, table_rx, (float)tolerance, bin_mask, stream);
+}
+
+extern "C" int fc_orientation_recheck(const double* levels, int n_planes, int plane, const uint32_t* codes, int batch,
+                                      int height, int width, const int32_t* keypoints, int n_keypoints, const double* weights,
+                                      int radius, int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
+  if (!levels || !codes || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0 || plane < 0 || plane >= n_planes)
+    return FC_ERR_BAD_ARG;
+  if (table_ry < (radius < height - 1 ? radius : height - 1) || table_rx < (radius < width - 1 ? radius : width - 1))
+    return FC_ERR_BAD_ARG;
+  if (n_keypoints == 0) return FC_OK;
+  if (!keypoints || !bin_mask || n_keypoints < 0) return FC_ERR_BAD_ARG;
+  if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;
+  orientation_recheck_kernel<<<div_up(n_keypoints, kRecheckWarps), kRecheckWarps * 32, 0, (cudaStream_t)stream>>>(
+      levels, n_planes, plane, codes, height, width, keypoints, n_keypoints, weights, radius, table_ry, table_rx,
+      (unsigned long long*)bin_mask);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_gradient_codes(const double* levels, int batch, int n_planes, int plane, int height, int width,
+                                 uint32_t* codes, void* stream) {
+  if (!levels || !codes || batch <= 0 || height <= 0 || width <= 0 || plane < 0 || plane >= n_planes) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec_ok = (width % 4 == 0) && (((reinterpret_cast<uintptr_t>(levels) | reinterpret_cast<uintptr_t>(codes)) & 15) == 0);
+  if (vec_ok)
+    gradient_codes4_kernel<<<dim3(div_up(width, 1024), height, batch), 256, 0, st>>>(levels, n_planes, plane, height, width, codes);
+  else
+    gradient_codes_kernel<<<dim3(div_up(width, 256), height, batch), 256, 0, st>>>(levels, n_planes, plane, height, width, codes);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
 }
 
 extern "C" int fc_orientation_scan(const uint64_t* bin_mask, int n_keypoints, int32_t* offsets, int32_t* scratch, void* stream) {
@@ -626,10 +938,19 @@ extern "C" int fc_orientation_emit(const int32_t* keypoints, const uint64_t* bin
   return FC_OK;
 }
 
-static int launch_descriptors(const void* magnitude, const void* direction, bool interleaved, int dtype, int batch, int height,
+static int launch_descriptors(const void* magnitude, const void* direction, int layout, int dtype, int batch, int height,
                               int width, const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
-                              void* descriptors, int out_dtype, void* stream) {
-  if (!magnitude || (!interleaved && !direction) || !gmask || !trig || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+                              void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream) {
+  DescPlacement place;
+  place.remap = placement ? reinterpret_cast<const int2*>(placement->remap) : nullptr;
+  place.points = placement ? reinterpret_cast<uint2*>(placement->points) : nullptr;
+  place.list_base = placement ? placement->list_base : 0;
+  place.octave = placement ? placement->octave : 0;
+  place.scale = placement ? placement->scale : 0;
+  if (placement && ((reinterpret_cast<uintptr_t>(placement->remap) | reinterpret_cast<uintptr_t>(placement->points)) & 7))
+    return FC_ERR_BAD_ARG;
+  const bool interleaved = layout == kDescInterleaved, coded = layout == kDescCoded;
+  if (!magnitude || (layout == kDescPlanes && !direction) || !gmask || !trig || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
   if (n_oriented == 0) return FC_OK;
   if (!oriented || !descriptors || n_oriented < 0) return FC_ERR_BAD_ARG;
   if ((int64_t)height * width > 0x3fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
@@ -643,7 +964,7 @@ static int launch_descriptors(const void* magnitude, const void* direction, bool
     FC_CUDA_TRY(cudaGetDevice(&dev));
     FC_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-#define FC_LAUNCH(T, OUT, IL)                                                                                     \
+#define FC_LAUNCH(T, OUT, IL)                                                                                   \
   do {                                                                                                            \
     static int per_sm = 0;                                                                                        \
     if (per_sm == 0)                                                                                              \
@@ -651,15 +972,19 @@ static int launch_descriptors(const void* magnitude, const void* direction, bool
     const int want = div_up(n_oriented, kDescWarps);                                                              \
     const int blocks = want < n_sm * per_sm ? want : n_sm * per_sm;                                               \
     descriptor_kernel<T, OUT, IL><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
-                                                                     width, oriented, n_oriented, gmask, trig, (OUT*)descriptors); \
+                                                                     width, oriented, n_oriented, gmask, trig, (OUT*)descriptors, place); \
   } while (0)
-  if (interleaved && dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, true);
-  else if (interleaved && dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, true);
+  if (coded && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescCoded);
+  else if (coded && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescCoded);
+  else if (coded && out_dtype == FC_F16) FC_LAUNCH(float, __half, kDescCoded);
+  else if (coded) return FC_ERR_BAD_ARG;
+  else if (interleaved && dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescInterleaved);
+  else if (interleaved && dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescInterleaved);
   else if (interleaved) return FC_ERR_BAD_ARG;
-  else if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, false);
-  else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, false);
-  else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float, false);
-  else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double, false);
+  else if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescPlanes);
+  else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescPlanes);
+  else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float, kDescPlanes);
+  else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double, kDescPlanes);
   else return FC_ERR_BAD_ARG;
 #undef FC_LAUNCH
   note_launch();
@@ -669,14 +994,41 @@ static int launch_descriptors(const void* magnitude, const void* direction, bool
 
 extern "C" int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
                               const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
-                              void* descriptors, int out_dtype, void* stream) {
-  return launch_descriptors(magnitude, direction, false, dtype, batch, height, width, oriented, n_oriented, gmask, trig,
-                            descriptors, out_dtype, stream);
+                              void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream) {
+  return launch_descriptors(magnitude, direction, kDescPlanes, dtype, batch, height, width, oriented, n_oriented, gmask, trig,
+                            descriptors, out_dtype, placement, stream);
 }
 
 extern "C" int fc_descriptors_interleaved(const void* magnitude_direction, int batch, int height, int width,
                                           const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
-                                          void* descriptors, int out_dtype, void* stream) {
-  return launch_descriptors(magnitude_direction, nullptr, true, FC_F32, batch, height, width, oriented, n_oriented, gmask, trig,
-                            descriptors, out_dtype, stream);
+                                          void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream) {
+  return launch_descriptors(magnitude_direction, nullptr, kDescInterleaved, FC_F32, batch, height, width, oriented, n_oriented,
+                            gmask, trig, descriptors, out_dtype, placement, stream);
+}
+
+extern "C" int fc_descriptors_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* oriented,
+                                    int n_oriented, const double* gmask, const double* trig, void* descriptors, int out_dtype,
+                                    const fc_desc_placement* placement, void* stream) {
+  return launch_descriptors(codes, nullptr, kDescCoded, FC_F32, batch, height, width, oriented, n_oriented, gmask, trig,
+                            descriptors, out_dtype, placement, stream);
+}
+
+extern "C" int fc_sift_layout(const int32_t* row_offsets, const int32_t* oriented_offsets, const int* block_row_start_host,
+                              const int* block_height_host, int n_blocks, int batch, int32_t* remap, int32_t* image_counts,
+                              void* stream) {
+  if (!row_offsets || !oriented_offsets || !block_row_start_host || !block_height_host || !remap || !image_counts)
+    return FC_ERR_BAD_ARG;
+  if (n_blocks < 1 || n_blocks > 64 || batch < 1 || batch > 8192) return FC_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(remap) & 7) return FC_ERR_BAD_ARG;
+  LayoutBlocks lb;
+  lb.n_blocks = n_blocks;
+  for (int i = 0; i < 64; ++i) {
+    lb.row_start[i] = i < n_blocks ? block_row_start_host[i] : 0;
+    lb.height[i] = i < n_blocks ? block_height_host[i] : 0;
+  }
+  sift_layout_kernel<<<1, 256, (batch + 1) * sizeof(int), (cudaStream_t)stream>>>(
+      row_offsets, oriented_offsets, lb, batch, reinterpret_cast<int2*>(remap), image_counts);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
 }

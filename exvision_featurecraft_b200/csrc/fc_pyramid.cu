@@ -214,6 +214,19 @@ gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, i
 // blocks; only those (~1 %) run the exact 26-neighbour test with the reference's strict / non-strict tie rule.
 static constexpr int kExTX = 32, kExTY = 64, kExPitch = 36;
 
+// CERT (the float32 stack is the rounded image of a float64 scale space, certified mode): `eps` bounds the error of
+// a difference of two float32 DoG values against the float64 one.  c > M + eps is an extremum of the float64 DoG as
+// well, c < M - eps (and c > m + eps) is none; everything in between -- including every tie, and with the script
+// filter every hit, whose contrast / edge tests are float64 decisions too -- is appended to `amb` as (image, k, row,
+// col) with its mask bit CLEAR: fc_extrema_repair evaluates those entries on float64 values and sets the bits.
+struct ExsCert {
+  float eps;
+  int4* amb;
+  int amb_cap;
+  int* amb_count;
+};
+
+
 template <typename T> __device__ __forceinline__ T max3_t(T a, T b, T c) { return fmax(fmax(a, b), c); }
 template <typename T> __device__ __forceinline__ T min3_t(T a, T b, T c) { return fmin(fmin(a, b), c); }
 template <> __device__ __forceinline__ float max3_t<float>(float a, float b, float c) {
@@ -249,10 +262,13 @@ __device__ __forceinline__ bool exact_extremum(const T* d0, const T* d1, const T
   return is_max || is_min;
 }
 
-template <typename T, int ND>
+template <typename T, int ND, bool CERT>
 __global__ void __launch_bounds__(256)
 extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int is_dog, int filter, double contrast_th,
-               double ratio_th, uint32_t* __restrict__ extrema, int pitch) {
+               double ratio_th, uint32_t* __restrict__ extrema, int pitch, const float* __restrict__ value_bound,
+               float eps_rel, int4* __restrict__ amb, int amb_cap, int* __restrict__ amb_count) {
+  static_assert(!CERT || sizeof(T) == 4, "the certified variant works on the float32 stack");
+  const T eps = CERT ? (T)(eps_rel * fmaxf(*value_bound, 1e-30f)) : T(0);
   extern __shared__ __align__(16) unsigned char ex_smem[];
   T* sD = reinterpret_cast<T*>(ex_smem);  // [ND][TH][kExPitch]
   constexpr int TW = kExPitch, TH = kExTY + 2;
@@ -314,7 +330,28 @@ extrema_kernel(const T* __restrict__ gauss, int B, int H, int W, int is_dog, int
     for (int k = 1; k <= ND - 2; ++k) {
       bool hit = false;
       const T c = col[(k * TH + t) * TW + 1];
-      if (center_ok && (c >= max3_t<T>(M[k - 1], M[k], M[k + 1]) || c <= min3_t<T>(m[k - 1], m[k], m[k + 1]))) {
+      if (CERT && center_ok && (c >= max3_t<T>(M[k - 1], M[k], M[k + 1]) - eps || c <= min3_t<T>(m[k - 1], m[k], m[k + 1]) + eps)) {
+        // certified mode (see ExsCert): sure extrema are those beyond eps of the 26 NEIGHBOURS' max / min
+        const T* d1 = col + (k * TH + t - 1) * TW;
+        T M26 = -INFINITY, m26 = INFINITY;
+#pragma unroll
+        for (int dl = -1; dl <= 1; ++dl)
+#pragma unroll
+          for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 3; ++dj)
+              if (!(dl == 0 && di == 1 && dj == 1)) {
+                const T a = d1[dl * TH * TW + di * TW + dj];
+                M26 = fmax(M26, a);
+                m26 = fmin(m26, a);
+              }
+        hit = c > M26 + eps || c < m26 - eps;
+        if (!hit || filter == FC_FILTER_SCRIPT) {
+          hit = false;
+          const int pos = atomicAdd(amb_count, 1);
+          if (pos < amb_cap) amb[pos] = make_int4(b, k, y, x);
+        }
+      } else if (!CERT && center_ok && (c >= max3_t<T>(M[k - 1], M[k], M[k + 1]) || c <= min3_t<T>(m[k - 1], m[k], m[k + 1]))) {
         const T* d1 = col + (k * TH + t - 1) * TW;
         hit = exact_extremum<T>(d1 - TH * TW, d1, d1 + TH * TW, TW);
         if (hit && filter == FC_FILTER_SCRIPT) {
@@ -448,12 +485,12 @@ __device__ __noinline__ bool exs_exact(const float* __restrict__ g, size_t plane
 // (`old`, `nw`).  M = max over the 26 neighbours: c > M is a unique maximum (argmax == 13), c < M is no maximum,
 // c == M is a tie whose outcome depends on the position of the equal neighbour -> exact path (rare; an all-equal
 // neighbourhood, c == M == m, is decided here: the first of 27 equal values wins, not the centre).
-template <int ND>
+template <int ND, bool CERT>
 __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const ExsRow<ND>& old, bool emit,
                                          const float* __restrict__ g, size_t plane, int B, int b, int H, int W, int yy,
                                          int x, int strip_c0, float* __restrict__ ring, int& slot, int stage_row, int filter,
                                          double contrast_th, double ratio_th, uint32_t*& out_p, size_t out_kstride, int pitch,
-                                         bool writer, uint32_t colmask, int lane) {
+                                         bool writer, uint32_t colmask, int lane, const ExsCert& cert) {
   asm volatile("cp.async.wait_group %0;" ::"n"(kExsRows - 2) : "memory");
   __syncwarp();
   const float* srow = ring + slot * ((ND + 1) * kExsPitch) + 4 * lane;
@@ -508,11 +545,32 @@ __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const 
         const float M = max3_t<float>(old.emax[k - 1][j], mid.nmax[k - 1][j], nw.emax[k - 1][j]);
         const float m = min3_t<float>(old.emin[k - 1][j], mid.nmin[k - 1][j], nw.emin[k - 1][j]);
         const float c = mid.c[k - 1][j];
-        cand |= (c >= M || c <= m) ? (1u << j) : 0u;
+        if constexpr (CERT) cand |= (c >= M - cert.eps || c <= m + cert.eps) ? (1u << j) : 0u;
+        else cand |= (c >= M || c <= m) ? (1u << j) : 0u;
       }
       cand &= okmask;
       uint32_t nib = cand;
-      if (__any_sync(0xffffffffu, cand != 0u)) {
+      if constexpr (CERT) {
+        if (__any_sync(0xffffffffu, cand != 0u)) {
+          uint32_t amb = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float M = max3_t<float>(old.emax[k - 1][j], mid.nmax[k - 1][j], nw.emax[k - 1][j]);
+            const float m = min3_t<float>(old.emin[k - 1][j], mid.nmin[k - 1][j], nw.emin[k - 1][j]);
+            const float c = mid.c[k - 1][j];
+            const bool sure = c > M + cert.eps || c < m - cert.eps;
+            if (!sure || filter == FC_FILTER_SCRIPT) amb |= cand & (1u << j);
+          }
+          nib &= ~amb;
+          while (amb) {
+            const int j = __ffs(amb) - 1;
+            amb &= amb - 1;
+            const int pos = atomicAdd(cert.amb_count, 1);
+            if (pos < cert.amb_cap) cert.amb[pos] = make_int4(b, k, y, x + j);
+          }
+          __syncwarp();
+        }
+      } else if (__any_sync(0xffffffffu, cand != 0u)) {
         // rare (1-2 % of the pixels): tell unique extrema from ties; ties and the script variant's hits take the exact path
         uint32_t slow = 0;
 #pragma unroll
@@ -546,10 +604,17 @@ __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const 
   mid = cur;
 }
 
-template <int ND>
+template <int ND, bool CERT>
 __global__ void __launch_bounds__(kExsWarps * 32, 3)
 extrema_strip_kernel(const float* __restrict__ gauss, int B, int H, int W, int rows_per_band, int filter,
-                     double contrast_th, double ratio_th, uint32_t* __restrict__ extrema, int pitch) {
+                     double contrast_th, double ratio_th, uint32_t* __restrict__ extrema, int pitch,
+                     const float* __restrict__ value_bound, float eps_rel, int4* __restrict__ amb, int amb_cap,
+                     int* __restrict__ amb_count) {
+  ExsCert cert;
+  cert.eps = CERT ? eps_rel * fmaxf(*value_bound, 1e-30f) : 0.f;
+  cert.amb = amb;
+  cert.amb_cap = amb_cap;
+  cert.amb_count = amb_count;
   extern __shared__ __align__(16) float exs_ring[];  // [warp][kExsRows][ND + 1][kExsPitch]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip_c0 = (blockIdx.x * kExsWarps + warp) * 128;
@@ -575,7 +640,7 @@ extrema_strip_kernel(const float* __restrict__ gauss, int B, int H, int W, int r
   const size_t out_kstride = (size_t)B * H * pitch;                      // words between the masks of k and k+1
   uint32_t* out_p = extrema + ((size_t)b * H + y0) * pitch + (x >> 5);  // mask word of (k = 1, row y0, this lane group)
 #define FC_EXS(NW, OLD) \
-  exs_step<ND>(NW, mid, OLD, yy >= y0 + 1, g, plane, B, b, H, W, yy, x, strip_c0, ring, slot, yy + kExsRows - 1, filter, contrast_th, ratio_th, out_p, out_kstride, pitch, writer, colmask, lane)
+  exs_step<ND, CERT>(NW, mid, OLD, yy >= y0 + 1, g, plane, B, b, H, W, yy, x, strip_c0, ring, slot, yy + kExsRows - 1, filter, contrast_th, ratio_th, out_p, out_kstride, pitch, writer, colmask, lane, cert)
   // the full-slice maxima of three consecutive rows rotate through R0, R1, R2 without moving a register
   for (;;) {
     FC_EXS(R0, R1); if (++yy > y1) break;
@@ -601,6 +666,22 @@ __global__ void convert_f64_kernel(const double* __restrict__ src, int64_t n, T*
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] = (T)src[i];
+}
+
+__global__ void convert_f64_bound_kernel(const double* __restrict__ src, int64_t n, float* __restrict__ dst,
+                                         unsigned int* __restrict__ bound_bits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float m = 0.f;
+  for (; i < n; i += stride) {
+    const double v = src[i];
+    dst[i] = (float)v;
+    m = fmaxf(m, (float)fabs(v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // non-negative floats order like their bit patterns; round the bound up by one ulp (the cast above rounds to nearest)
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bound_bits, __float_as_uint(m) + 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -835,6 +916,114 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// float64 levels of the certified mode
+// ------------------------------------------------------------------------------------------------
+// Certified ("mixed") mode keeps the float32 stack above for the bulk comparisons and adds the levels 1 .. s of each
+// octave in float64: they are the ones the gradient fields are taken from (APP/utils/keypoint_descriptor.py:126,
+// :241) and level s is the next octave's base (APP/utils/SIFT_scale_space.py:209), so that neither the orientation /
+// descriptor bins nor the deeper octaves inherit float32 rounding.  For the default s = 2 both levels (radii 5, 6)
+// come out of one pass over a shared-memory tile with the pair sums v[-k] + v[+k] shared between them:
+// tile = 116 x 32 outputs, 128 x 44 inputs, 2 x 19 + 2 x 24 float64 operations per pixel on the FP64 pipe.
+struct MidTaps {
+  double t[2][8];  // t[l][k] = tap at distance k (centre first), zero beyond the radius
+};
+static constexpr int kMTX = 116, kMTY = 32, kMP = 128, kMR = 6;
+static constexpr int kMIH = kMTY + 2 * kMR;  // 44 input rows
+static constexpr size_t kMidSmem = sizeof(double) * (size_t)(kMIH * kMP + 2 * kMTY * kMP);
+
+template <int RA, int RB>
+__global__ void __launch_bounds__(256, 2)
+gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid_constant__ MidTaps taps,
+                     double* __restrict__ out, int n_planes, int plane0) {
+  static_assert(RA <= kMR && RB <= kMR, "radius class");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sIn = reinterpret_cast<double*>(smem_raw);
+  double* sTmp = sIn + kMIH * kMP;
+  const int x0 = blockIdx.x * kMTX, y0 = blockIdx.y * kMTY;
+  const int b = blockIdx.z;
+  const size_t plane = (size_t)H * W;
+  const double* img = base + (size_t)b * plane;
+  // smem column c <-> image column x0 - 6 + c, smem row r <-> image row y0 - 6 + r
+  const bool interior = (x0 - kMR >= 0) && (x0 - kMR + kMP <= W) && (y0 - kMR >= 0) && (y0 - kMR + kMIH <= H) &&
+                        (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  if (interior) {
+    for (int i = threadIdx.x; i < kMIH * (kMP / 2); i += 256) {
+      const int r = i >> 6, c2 = i & 63;
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(sIn + r * kMP + 2 * c2);
+      const double* src = img + (size_t)(y0 - kMR + r) * W + (x0 - kMR) + 2 * c2;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    }
+  } else {
+    for (int i = threadIdx.x; i < kMIH * kMP; i += 256) {
+      const int r = i >> 7, c = i & 127;
+      cp_async_elem<double>(sIn + r * kMP + c, img + (size_t)reflect_symm(y0 - kMR + r, H) * W + reflect_symm(x0 - kMR + c, W));
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // vertical pass: (8-row group, column) items, 4 x 128 = two per thread
+#pragma unroll 1
+  for (int item = threadIdx.x; item < (kMTY / 8) * kMP; item += 256) {
+    const int g = item >> 7, c = item & 127;
+    const double* src = sIn + (g * 8) * kMP + c;
+    double v[8 + 2 * kMR];
+#pragma unroll
+    for (int k = 0; k < 8 + 2 * kMR; ++k) v[k] = src[k * kMP];
+    double* dst = sTmp + (g * 8) * kMP + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double sp[kMR + 1];
+#pragma unroll
+      for (int k = 1; k <= kMR; ++k) sp[k] = v[j + kMR - k] + v[j + kMR + k];
+      double a = taps.t[0][0] * v[j + kMR], bb = taps.t[1][0] * v[j + kMR];
+#pragma unroll
+      for (int k = 1; k <= RA; ++k) a = fma(taps.t[0][k], sp[k], a);
+#pragma unroll
+      for (int k = 1; k <= RB; ++k) bb = fma(taps.t[1][k], sp[k], bb);
+      dst[j * kMP] = a;
+      dst[kMTY * kMP + j * kMP] = bb;
+    }
+  }
+  __syncthreads();
+  // horizontal pass: 4 outputs per item; tmp column 6 + o <-> output column x0 + o
+  const bool vec_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  double* o0 = out + ((size_t)b * n_planes + plane0) * plane;
+#pragma unroll 1
+  for (int item = threadIdx.x; item < kMTY * (kMTX / 4); item += 256) {
+    const int y = item / (kMTX / 4), g = item - y * (kMTX / 4);
+    const int yy = y0 + y, xx = x0 + 4 * g;
+    if (yy >= H || xx >= W) continue;
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      const double2* src = reinterpret_cast<const double2*>(sTmp + l * kMTY * kMP + y * kMP + 4 * g);
+      double v[4 + 2 * kMR];
+#pragma unroll
+      for (int q = 0; q < (4 + 2 * kMR) / 2; ++q) {
+        const double2 t = src[q];
+        v[2 * q] = t.x; v[2 * q + 1] = t.y;
+      }
+      double r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double acc = taps.t[l][0] * v[j + kMR];
+#pragma unroll
+        for (int k = 1; k <= (l == 0 ? RA : RB); ++k) acc = fma(taps.t[l][k], v[j + kMR - k] + v[j + kMR + k], acc);
+        r[j] = acc;
+      }
+      double* dst = o0 + (size_t)l * plane + (size_t)yy * W + xx;
+      if (vec_ok && xx + 3 < W) {
+        reinterpret_cast<double2*>(dst)[0] = make_double2(r[0], r[1]);
+        reinterpret_cast<double2*>(dst)[1] = make_double2(r[2], r[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (xx + j < W) dst[j] = r[j];
+      }
+    }
+  }
+}
+
 static int launch_octave_packed(const void* base, int B, int H, int W, const double* taps_host, const int* tap_len_host,
                                 int first_is_identity, void* gauss, cudaStream_t st) {
   static const int radius[5] = {3, 5, 6, 9, 13};
@@ -942,32 +1131,42 @@ static int launch_octave(const void* base, int B, int H, int W, int L, const dou
   }
 }
 
-template <typename T, int ND>
+struct CertArgs {  // certified mode of the strip kernel (all null / zero otherwise)
+  const float* value_bound = nullptr;
+  float eps_rel = 0.f;
+  int4* amb = nullptr;
+  int amb_cap = 0;
+  int* amb_count = nullptr;
+};
+
+template <typename T, int ND, bool CERT = false>
 static int launch_extrema_nd(const void* gauss, int B, int H, int W, int is_dog, int filter, double cth, double rth,
-                             uint32_t* extrema, cudaStream_t st) {
+                             uint32_t* extrema, cudaStream_t st, const CertArgs& ca = CertArgs()) {
   const int pitch = div_up(W, 32);
   const size_t smem = sizeof(T) * (size_t)ND * (kExTY + 2) * kExPitch;
-  auto kern = extrema_kernel<T, ND>;
+  auto kern = extrema_kernel<T, ND, CERT>;
   FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(pitch, div_up(H, kExTY), B);
-  kern<<<grid, 256, smem, st>>>((const T*)gauss, B, H, W, is_dog, filter, cth, rth, extrema, pitch);
+  kern<<<grid, 256, smem, st>>>((const T*)gauss, B, H, W, is_dog, filter, cth, rth, extrema, pitch, ca.value_bound,
+                                ca.eps_rel, ca.amb, ca.amb_cap, ca.amb_count);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
 }
 
-template <int ND>
+template <int ND, bool CERT>
 static int launch_extrema_strip(const void* gauss, int B, int H, int W, int filter, double cth, double rth, uint32_t* extrema,
-                                cudaStream_t st) {
+                                cudaStream_t st, const CertArgs& ca = CertArgs()) {
   const int pitch = div_up(W, 32);
   const size_t smem = sizeof(float) * kExsWarps * kExsRows * (ND + 1) * kExsPitch;
-  auto kern = extrema_strip_kernel<ND>;
+  auto kern = extrema_strip_kernel<ND, CERT>;
   FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int strips = div_up(W, 128);
   int rows = 64;  // band height: amortise the two halo rows, but keep enough warps in flight on small inputs
   while (rows > 8 && (int64_t)strips * div_up(H, rows) * B < 148 * 12) rows >>= 1;
   dim3 grid(div_up(strips, kExsWarps), div_up(H, rows), B);
-  kern<<<grid, kExsWarps * 32, smem, st>>>((const float*)gauss, B, H, W, rows, filter, cth, rth, extrema, pitch);
+  kern<<<grid, kExsWarps * 32, smem, st>>>((const float*)gauss, B, H, W, rows, filter, cth, rth, extrema, pitch,
+                                           ca.value_bound, ca.eps_rel, ca.amb, ca.amb_cap, ca.amb_count);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
@@ -979,9 +1178,9 @@ static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_
   const int nd = is_dog ? L : L - 1;
   if constexpr (sizeof(T) == 4) {
     if (!is_dog && W % 4 == 0 && H >= 3 && (reinterpret_cast<uintptr_t>(gauss) & 15) == 0) {
-      if (nd == 4) return launch_extrema_strip<4>(gauss, B, H, W, filter, cth, rth, extrema, st);
-      if (nd == 3) return launch_extrema_strip<3>(gauss, B, H, W, filter, cth, rth, extrema, st);
-      if (nd == 5) return launch_extrema_strip<5>(gauss, B, H, W, filter, cth, rth, extrema, st);
+      if (nd == 4) return launch_extrema_strip<4, false>(gauss, B, H, W, filter, cth, rth, extrema, st);
+      if (nd == 3) return launch_extrema_strip<3, false>(gauss, B, H, W, filter, cth, rth, extrema, st);
+      if (nd == 5) return launch_extrema_strip<5, false>(gauss, B, H, W, filter, cth, rth, extrema, st);
     }
   }
   switch (nd) {
@@ -990,6 +1189,124 @@ static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_
     case 5: return launch_extrema_nd<T, 5>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
     case 6: return launch_extrema_nd<T, 6>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
     case 7: return launch_extrema_nd<T, 7>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
+    default: return FC_ERR_UNSUPPORTED;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// float64 decision of the entries the certified extremum search could not decide in float32
+// ------------------------------------------------------------------------------------------------
+// One warp per entry (image, k, row, col): the 3x3 neighbourhoods of the Gaussian levels k-1 .. k+2 are taken from the
+// stored float64 levels where they exist (`mid`: levels mid_first .. mid_first + mid_count - 1) and are otherwise
+// blurred on demand from the octave's float64 base (warp_blur3x3).  The reference rule (APP/utils/SIFT_scale_space.py:
+// 78-88, first maximum / minimum of the flattened 3x3x3 block wins) and, for the script variant, the contrast and
+// edge tests (implementation_without_ui/SIFT/SIFT.py:202-215) are then evaluated on float64 DoG values, exactly as
+// the float64 kernels above do.
+static constexpr int kRepairCols = 2 * 24 + 3;  // columns x-1-R .. x+1+R of the vertical pass for the largest radius
+
+// 3x3 block of one blurred level around (y, x), with the operation order of the float64 octave kernels (vertical pass
+// with symmetric pair sums, then the horizontal one), so that the values -- and every tie between them -- are bit for
+// bit those of gauss_octave_kernel<double> / gauss_mid_f64_kernel.  lane = one column of the vertical pass; `tmp` is
+// this warp's [3][kRepairCols] staging area in shared memory.
+__device__ __forceinline__ void warp_blur3x3(const double* __restrict__ img, int H, int W, int y, int x,
+                                             const double* __restrict__ taps, int R, int lane, double* __restrict__ tmp,
+                                             double* __restrict__ out9) {
+  const int ncol = 2 * R + 3;
+  for (int c = lane; c < ncol; c += 32) {
+    const int xc = reflect_symm(x - 1 - R + c, W);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yc = y - 1 + dy;
+      double acc = taps[R] * img[(size_t)reflect_symm(yc, H) * W + xc];
+      for (int k = 1; k <= R; ++k)
+        acc = fma(taps[R + k], img[(size_t)reflect_symm(yc - k, H) * W + xc] + img[(size_t)reflect_symm(yc + k, H) * W + xc], acc);
+      tmp[dy * kRepairCols + c] = acc;
+    }
+  }
+  __syncwarp();
+  if (lane < 9) {
+    const int dy = lane / 3, dx = lane - 3 * dy;
+    const double* row = tmp + dy * kRepairCols + (R + dx);  // tmp column of image column x - 1 + dx
+    double acc = taps[R] * row[0];
+    for (int k = 1; k <= R; ++k) acc = fma(taps[R + k], row[-k] + row[k], acc);
+    out9[lane] = acc;
+  }
+  __syncwarp();
+}
+
+static constexpr int kRepairWarps = 4;
+
+__global__ void __launch_bounds__(kRepairWarps * 32)
+extrema_repair_kernel(const double* __restrict__ base, int first_is_identity, const double* __restrict__ mid, int mid_first,
+                      int mid_count, int B, int H, int W, int L, const __grid_constant__ TapTable<double> tab, int filter,
+                      double contrast_th, double ratio_th, const int4* __restrict__ amb, const int* __restrict__ amb_count,
+                      int amb_cap, uint32_t* __restrict__ extrema, int pitch) {
+  __shared__ double sG[kRepairWarps][4][9];  // levels k-1 .. k+2, 3x3 each (row-major)
+  __shared__ double sTmp[kRepairWarps][3 * kRepairCols];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = min(*amb_count, amb_cap);
+  const size_t plane = (size_t)H * W;
+  for (int e = blockIdx.x * kRepairWarps + warp; e < n; e += gridDim.x * kRepairWarps) {
+    const int4 ent = amb[e];
+    const int b = ent.x, k = ent.y, y = ent.z, x = ent.w;
+    for (int q = 0; q < 4; ++q) {
+      const int l = k - 1 + q;
+      const double* src = nullptr;
+      if (l >= mid_first && l < mid_first + mid_count) src = mid + ((size_t)b * mid_count + (l - mid_first)) * plane;
+      else if (l == 0 && first_is_identity) src = base + (size_t)b * plane;
+      if (src) {
+        // centres satisfy 1 <= y <= H-3, 1 <= x <= W-3: the 3x3 block is inside the image
+        if (lane < 9) sG[warp][q][lane] = src[(size_t)(y - 1 + lane / 3) * W + (x - 1 + lane % 3)];
+      } else {
+        warp_blur3x3(base + (size_t)b * plane, H, W, y, x, tab.taps + tab.offset[l], tab.radius[l], lane, sTmp[warp], sG[warp][q]);
+      }
+    }
+    __syncwarp();
+    // lane = flat index of the (3,3,3) block with the scale axis fastest: di * 9 + dj * 3 + dk
+    const int fl = lane < 27 ? lane : 13;
+    const int pos = fl / 3, dk = fl - 3 * pos;
+    const double d = sG[warp][dk + 1][pos] - sG[warp][dk][pos];
+    const double c = __shfl_sync(0xffffffffu, d, 13);
+    const bool mx = lane >= 27 || lane == 13 || (lane < 13 ? c > d : c >= d);
+    const bool mn = lane >= 27 || lane == 13 || (lane < 13 ? c < d : c <= d);
+    bool hit = __all_sync(0xffffffffu, mx) || __all_sync(0xffffffffu, mn);
+    if (hit && filter == FC_FILTER_SCRIPT && lane == 0) {
+      const int ci = 2 * k - 1;  // SIFT.py:206 indexes the local 3-stack with the global k
+      double contrast = 0.0;
+      if (ci < L - 1 && ci >= k - 1 && ci + 1 <= k + 2) contrast = sG[warp][ci + 1 - (k - 1)][4] - sG[warp][ci - (k - 1)][4];
+      double dd[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) dd[i] = sG[warp][2][i] - sG[warp][1][i];  // DoG_k
+      const double c0 = dd[4];
+      const double dxx = __dadd_rn(__dsub_rn(dd[5], __dmul_rn(2.0, c0)), dd[3]);
+      const double dyy = __dadd_rn(__dsub_rn(dd[7], __dmul_rn(2.0, c0)), dd[1]);
+      const double dxy = __ddiv_rn(__dsub_rn(__dsub_rn(dd[8], dd[6]), __dsub_rn(dd[2], dd[0])), 4.0);
+      const double tr = __dadd_rn(dxx, dyy);
+      const double det = __dsub_rn(__dmul_rn(dxx, dyy), __dmul_rn(dxy, dxy));
+      const double r = __ddiv_rn(__dmul_rn(tr, tr), det);
+      if (fabs(contrast) < contrast_th) hit = false;
+      if (r > ratio_th) hit = false;
+    }
+    if (lane == 0 && hit) atomicOr(extrema + (((size_t)(k - 1) * B + b) * H + y) * pitch + (x >> 5), 1u << (x & 31));
+    __syncwarp();
+  }
+}
+
+// certified float32 extremum search: the strip kernel where it applies, else the tiled one (any width, up to 7 DoG levels)
+static int launch_extrema_certified(const void* gauss, int B, int H, int W, int L, int filter, double cth, double rth,
+                                    uint32_t* extrema, cudaStream_t st, const CertArgs& ca) {
+  const int nd = L - 1;
+  if (W % 4 == 0 && H >= 3 && (reinterpret_cast<uintptr_t>(gauss) & 15) == 0) {
+    if (nd == 4) return launch_extrema_strip<4, true>(gauss, B, H, W, filter, cth, rth, extrema, st, ca);
+    if (nd == 3) return launch_extrema_strip<3, true>(gauss, B, H, W, filter, cth, rth, extrema, st, ca);
+    if (nd == 5) return launch_extrema_strip<5, true>(gauss, B, H, W, filter, cth, rth, extrema, st, ca);
+  }
+  switch (nd) {
+    case 3: return launch_extrema_nd<float, 3, true>(gauss, B, H, W, 0, filter, cth, rth, extrema, st, ca);
+    case 4: return launch_extrema_nd<float, 4, true>(gauss, B, H, W, 0, filter, cth, rth, extrema, st, ca);
+    case 5: return launch_extrema_nd<float, 5, true>(gauss, B, H, W, 0, filter, cth, rth, extrema, st, ca);
+    case 6: return launch_extrema_nd<float, 6, true>(gauss, B, H, W, 0, filter, cth, rth, extrema, st, ca);
+    case 7: return launch_extrema_nd<float, 7, true>(gauss, B, H, W, 0, filter, cth, rth, extrema, st, ca);
     default: return FC_ERR_UNSUPPORTED;
   }
 }
@@ -1019,6 +1336,113 @@ extern "C" int fc_gauss_octave(const void* base, int dtype, int batch, int heigh
                          : launch_extrema<double>(gauss, batch, height, width, n_levels, 0, filter, contrast_th, ratio_th, extrema, st);
   }
   return rc;
+}
+
+// levels [first_level, first_level + level_count) of the scale space in float64 (certified mode), out = [batch][level_count][h][w]
+extern "C" int fc_gauss_levels_f64(const double* base, int batch, int height, int width, int n_levels, const double* taps_host,
+                                   const int* tap_len_host, int first_level, int level_count, double* out, void* stream) {
+  if (!base || !out || !taps_host || !tap_len_host || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (n_levels < 1 || n_levels > kMaxLevels || first_level < 0 || level_count < 1 || first_level + level_count > n_levels)
+    return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const double* tp = taps_host;
+  for (int l = 0; l < first_level; ++l) tp += tap_len_host[l];
+  const int* lens = tap_len_host + first_level;
+  bool symmetric = true;
+  {
+    const double* q = tp;
+    for (int l = 0; l < level_count; ++l) {
+      if (lens[l] < 1 || (lens[l] & 1) == 0) return FC_ERR_BAD_ARG;
+      for (int k = 0; k < lens[l]; ++k) symmetric &= q[k] == q[lens[l] - 1 - k];
+      q += lens[l];
+    }
+  }
+  if (!symmetric) return FC_ERR_UNSUPPORTED;
+  if (level_count == 2 && lens[0] == 11 && lens[1] == 13) {  // the default s = 2 levels: radii 5 and 6
+    MidTaps mt;
+    for (int k = 0; k < 8; ++k) {
+      mt.t[0][k] = k <= 5 ? tp[5 + k] : 0.0;
+      mt.t[1][k] = k <= 6 ? tp[11 + 6 + k] : 0.0;
+    }
+    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_mid_f64_kernel<5, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMidSmem));
+    dim3 grid(div_up(width, kMTX), div_up(height, kMTY), batch);
+    gauss_mid_f64_kernel<5, 6><<<grid, 256, kMidSmem, st>>>(base, height, width, mt, out, 2, 0);
+    note_launch();
+    FC_RETURN_IF_LAUNCH_FAILED();
+    return FC_OK;
+  }
+  return launch_octave<double>(base, batch, height, width, level_count, tp, lens, 0, out, st);
+}
+
+// float32 copy of a float64 array + the largest magnitude seen (value_bound[0], a float; zeroed here first): the scale
+// against which the certified kernels measure their float32 error bounds
+extern "C" int fc_convert_f64_bound(const double* src, int64_t n, float* dst, float* value_bound, void* stream) {
+  if (!src || !dst || !value_bound || n <= 0) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  FC_CUDA_TRY(cudaMemsetAsync(value_bound, 0, sizeof(float), st));
+  const unsigned blocks = (unsigned)(div_up64(n, 256) < 148 * 32 ? div_up64(n, 256) : 148 * 32);
+  convert_f64_bound_kernel<<<blocks, 256, 0, st>>>(src, n, dst, reinterpret_cast<unsigned int*>(value_bound));
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+// certified extremum search on the float32 stack (see ExsCert): decided pixels go to `extrema`, undecided ones to
+// `amb` (int32 quadruples image, k, row, col; amb_count is zeroed here and may exceed amb_cap: the caller checks)
+extern "C" int fc_gauss_octave_extrema_certified(const float* gauss, int batch, int height, int width, int n_levels, int filter,
+                                                 double contrast_th, double ratio_th, const float* value_bound,
+                                                 double eps_rel, uint32_t* extrema, int32_t* amb, int amb_cap,
+                                                 int32_t* amb_count, void* stream) {
+  if (!gauss || !extrema || !value_bound || !amb || !amb_count || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if (n_levels < 4 || n_levels > kMaxLevels || amb_cap < 0 || !(eps_rel >= 0.0)) return FC_ERR_BAD_ARG;
+  if (filter != FC_FILTER_APP && filter != FC_FILTER_SCRIPT) return FC_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(amb) & 15) return FC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  FC_CUDA_TRY(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+  CertArgs ca;
+  ca.value_bound = value_bound;
+  ca.eps_rel = (float)eps_rel;
+  ca.amb = reinterpret_cast<int4*>(amb);
+  ca.amb_cap = amb_cap;
+  ca.amb_count = amb_count;
+  return launch_extrema_certified(gauss, batch, height, width, n_levels, filter, contrast_th, ratio_th, extrema, st, ca);
+}
+
+extern "C" int fc_extrema_repair(const double* base, int first_is_identity, const double* mid, int mid_first, int mid_count,
+                                 int batch, int height, int width, int n_levels, const double* taps_host,
+                                 const int* tap_len_host, int filter, double contrast_th, double ratio_th, const int32_t* amb,
+                                 const int32_t* amb_count, int amb_cap, uint32_t* extrema, void* stream) {
+  if (!base || !taps_host || !tap_len_host || !amb || !amb_count || !extrema || batch <= 0 || height <= 0 || width <= 0)
+    return FC_ERR_BAD_ARG;
+  if (n_levels < 4 || n_levels > kMaxLevels || mid_count < 0 || (mid_count > 0 && !mid)) return FC_ERR_BAD_ARG;
+  if (filter != FC_FILTER_APP && filter != FC_FILTER_SCRIPT) return FC_ERR_BAD_ARG;
+  if (amb_cap == 0) return FC_OK;
+  TapTable<double> tab;
+  tab.n_levels = n_levels;
+  tab.first_is_identity = first_is_identity;
+  int off = 0;
+  const double* tp = taps_host;
+  for (int l = 0; l < n_levels; ++l) {
+    const int n = tap_len_host[l];
+    if (n < 1 || (n & 1) == 0 || off + n > kMaxTapsTotal) return FC_ERR_UNSUPPORTED;
+    tab.radius[l] = n / 2;
+    tab.offset[l] = off;
+    for (int k = 0; k < n; ++k) {
+      if (tp[k] != tp[n - 1 - k]) return FC_ERR_UNSUPPORTED;
+      tab.taps[off + k] = tp[k];
+    }
+    off += n;
+    tp += n;
+  }
+  for (int l = n_levels; l < kMaxLevels; ++l) tab.radius[l] = tab.offset[l] = 0;
+  const int want = div_up(amb_cap, kRepairWarps);
+  const int blocks = want < 148 * 8 ? want : 148 * 8;
+  extrema_repair_kernel<<<blocks, kRepairWarps * 32, 0, (cudaStream_t)stream>>>(
+      base, first_is_identity, mid, mid_first, mid_count, batch, height, width, n_levels, tab, filter, contrast_th, ratio_th,
+      reinterpret_cast<const int4*>(amb), amb_count, amb_cap, extrema, div_up(width, 32));
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
 }
 
 extern "C" int fc_gauss_octave_extrema(const void* gauss, int dtype, int batch, int height, int width, int n_levels,

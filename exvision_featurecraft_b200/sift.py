@@ -15,7 +15,8 @@ Reference structure followed (APP = FeatureCraft-PyQt-App):
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from collections import OrderedDict
+from dataclasses import dataclass, field, replace
 from math import cos, sin
 
 import numpy as np
@@ -35,10 +36,21 @@ class SiftParams:
     contrast_th: float = 0.03
     ratio_th: float = 10
     variant: str = "app"  # "app": keep every extremum; "script": SIFT.py contrast + edge tests
-    dtype: str = "f32"  # storage / arithmetic type of the scale space: "f32" (production) or "f64" (exact mode)
+    # arithmetic of the scale space:
+    #   "mixed" (production): float32 bulk arithmetic with every discrete decision certified -- an extremum, an
+    #           orientation bin or a descriptor bin is taken from float32 values only when their error bound cannot
+    #           change it, and is otherwise re-evaluated on float64 values: the keypoint lists are the float64 path's;
+    #   "f64":  everything in float64 (the reference's arithmetic);
+    #   "f32":  plain float32, no certification (tolerance-level parity only).
+    dtype: str = "mixed"
+
+    def __post_init__(self):
+        if self.dtype not in ("mixed", "f64", "f32"):
+            raise ValueError("dtype must be 'mixed', 'f64' or 'f32'")
 
     @property
     def torch_dtype(self):
+        """element type of the octave base images"""
         return torch.float32 if self.dtype == "f32" else torch.float64
 
     @property
@@ -77,11 +89,15 @@ def separable_taps(sigma):
     return np.exp(-(x ** 2) / (2 * sigma ** 2)) / np.sqrt(2 * np.pi * (sigma ** 2))
 
 
-def gaussian_window_table(sigma):
-    """gaussian_filter_kernel(sigma) as the dense 2-D table the orientation stage multiplies by (SS:22-28)."""
+def gaussian_window_table(sigma, ry=None, rx=None):
+    """gaussian_filter_kernel(sigma) as the dense 2-D table the orientation stage multiplies by (SS:22-28).
+    ry / rx restrict it to the offsets |dy| <= ry, |dx| <= rx (same element-wise expression, so the same values):
+    a window clipped to a small high-octave image never reads the rest of a (2r+1)^2 table."""
     r = kernel_radius(sigma)
-    x = np.arange(-r, r + 1)[:, np.newaxis]
-    y = np.arange(-r, r + 1)
+    ry = r if ry is None else min(r, ry)
+    rx = r if rx is None else min(r, rx)
+    x = np.arange(-ry, ry + 1)[:, np.newaxis]
+    y = np.arange(-rx, rx + 1)
     k = np.exp(-(x ** 2 + y ** 2) / (2 * sigma ** 2))
     k /= 2 * np.pi * (sigma ** 2)
     return k
@@ -127,7 +143,8 @@ def trig_table():
     return t
 
 
-_TABLE_CACHE: dict = {}
+_TABLE_CACHE: "OrderedDict" = OrderedDict()
+_TABLE_CACHE_LIMIT = 256 << 20  # bytes of device tables kept (least recently used go first)
 
 
 class StageTimer:
@@ -184,11 +201,17 @@ def _stage(name):
 
 def _cached(key, builder, dtype=torch.float64):
     dev = torch.cuda.current_device()
-    k = (dev,) + key
+    k = (dev,) + key + (dtype,)
     t = _TABLE_CACHE.get(k)
     if t is None:
         t = to_device(np.ascontiguousarray(builder(), dtype=np.float64)).to(dtype).contiguous()
         _TABLE_CACHE[k] = t
+        total = sum(v.numel() * v.element_size() for v in _TABLE_CACHE.values())
+        while total > _TABLE_CACHE_LIMIT and len(_TABLE_CACHE) > 1:
+            _, old = _TABLE_CACHE.popitem(last=False)
+            total -= old.numel() * old.element_size()
+    else:
+        _TABLE_CACHE.move_to_end(k)
     return t
 
 
@@ -203,85 +226,61 @@ class Octave:
 
 @dataclass
 class ScaleBlock:
-    """Everything for one (octave, scale): keypoints (image,row,col), oriented (image,row,col,bin), descriptors."""
+    """The block-major lists of one (octave, scale): keypoints (image,row,col), oriented (image,row,col,bin)."""
 
     octave: int
     scale: int
     keypoints: torch.Tensor
     oriented: torch.Tensor | None = None
-    descriptors: torch.Tensor | None = None
 
 
 @dataclass
 class SiftResult:
+    """Outputs of detect_and_describe, all on the device and already in the reference's order: images one after the
+    other, each image's keypoints in emission order (octave, scale, row-major, orientation bin)."""
+
     params: SiftParams
     octaves: list
     blocks: list = field(default_factory=list)
+    descriptors: torch.Tensor | None = None  # [M, 128]
+    records: torch.Tensor | None = None      # [M, 2] int32: packed (row, col) | (octave, scale, bin), see unpack_records
+    counts: torch.Tensor | None = None       # [B] int32 descriptors per image
+
+    @property
+    def total(self) -> int:
+        return 0 if self.descriptors is None else int(self.descriptors.shape[0])
 
     def assemble_device(self, batch: int):
-        """Device tensors (points [M,5] float64, descriptors [M,128], per-image counts [B] int64), images
-        concatenated, each image in the reference's emission order (octave, scale, row-major, bin)."""
-        pts, desc = [], []
-        for blk in self.blocks:
-            if blk.oriented is None or blk.oriented.shape[0] == 0:
-                continue
-            o = blk.oriented
-            p = torch.empty((o.shape[0], 6), dtype=torch.float64, device=o.device)
-            p[:, :3] = o[:, :3]
-            p[:, 3] = blk.octave
-            p[:, 4] = blk.scale
-            p[:, 5] = o[:, 3].to(torch.float64) * 10.0 + 5.0
-            pts.append(p)
-            desc.append(blk.descriptors)
-        if not pts:
-            dev = require_cuda()
-            return (torch.zeros((0, 5), dtype=torch.float64, device=dev), torch.zeros((0, 128), dtype=torch.float32, device=dev),
-                    torch.zeros(batch, dtype=torch.int64, device=dev))
-        p = torch.cat(pts)
-        d = torch.cat(desc)
-        img = p[:, 0].to(torch.int64)
-        if batch > 1:
-            img, order = torch.sort(img, stable=True)
-            p = p[order]
-            d = d[order]
-        # per-image counts without torch.bincount (which reads the maximum back to the host)
-        edges = torch.searchsorted(img, torch.arange(batch + 1, device=img.device, dtype=torch.int64))
-        counts = edges[1:] - edges[:-1]
-        return p[:, 1:].contiguous(), d, counts
+        """(records [M,2] int32, descriptors [M,128], per-image counts [B] int32) -- device tensors, no copies."""
+        return self.records, self.descriptors, self.counts
 
     def assemble(self, batch: int):
-        """Per-image (points [m,5] float64 = (i, j, octave, scale, angle), descriptors [m,128]) in the
+        """Per-image (points [m,5] float64 = (i, j, octave, scale, angle), descriptors [m,128]) on the host, in the
         reference's emission order (octave, scale, row-major, bin)."""
-        pts, desc = [], []
-        for blk in self.blocks:
-            if blk.oriented is None or blk.oriented.shape[0] == 0:
-                continue
-            o = blk.oriented
-            p = torch.empty((o.shape[0], 6), dtype=torch.float64, device=o.device)
-            p[:, 0] = o[:, 0]
-            p[:, 1] = o[:, 1]
-            p[:, 2] = o[:, 2]
-            p[:, 3] = blk.octave
-            p[:, 4] = blk.scale
-            p[:, 5] = o[:, 3].to(torch.float64) * 10.0 + 5.0
-            pts.append(p)
-            desc.append(blk.descriptors)
-        if not pts:
+        if self.descriptors is None or self.total == 0:
             e = np.zeros((0, 5))
             return [(e, np.zeros((0, 128), dtype=np.float32)) for _ in range(batch)]
-        p = torch.cat(pts)
-        d = torch.cat(desc)
-        order = torch.sort(p[:, 0], stable=True).indices
-        p = p[order]
-        d = d[order]
-        counts = torch.bincount(p[:, 0].to(torch.int64), minlength=batch).cpu().numpy()
-        p = p[:, 1:].cpu().numpy()
-        d = d.cpu().numpy()
+        counts = self.counts.cpu().numpy()
+        pts = unpack_records(self.records.cpu().numpy())
+        d = self.descriptors.cpu().numpy()
         out, lo = [], 0
         for b in range(batch):
-            out.append((p[lo:lo + counts[b]], d[lo:lo + counts[b]]))
+            out.append((pts[lo:lo + counts[b]], d[lo:lo + counts[b]]))
             lo += counts[b]
         return out
+
+
+def unpack_records(rec: np.ndarray) -> np.ndarray:
+    """[M,2] int32 keypoint records (uint16 row | uint16 col << 16, uint8 octave | scale << 8 | bin << 16) -> the
+    reference's 5-tuples as [M,5] float64: (i, j, octave, scale, (bin + 0.5) * 10) (KD:167-170)."""
+    r = np.ascontiguousarray(rec).view(np.uint32).reshape(-1, 2)
+    out = np.empty((r.shape[0], 5), dtype=np.float64)
+    out[:, 0] = r[:, 0] & 0xFFFF
+    out[:, 1] = r[:, 0] >> 16
+    out[:, 2] = r[:, 1] & 0xFF
+    out[:, 3] = (r[:, 1] >> 8) & 0xFF
+    out[:, 4] = ((r[:, 1] >> 16) & 0xFF) * 10.0 + 5.0
+    return out
 
 
 def _as_base_batch(base, params: SiftParams) -> torch.Tensor:
@@ -308,23 +307,34 @@ def upsample2(gray, params: SiftParams) -> torch.Tensor:
     return out
 
 
+def _level_taps(params: SiftParams, taps=None):
+    if taps is None:
+        taps = [separable_taps(s) for s in sigma_levels(params.sigma_base, params.s_value)]
+    lens = (C.c_int * len(taps))(*[len(t) for t in taps])
+    flat = np.ascontiguousarray(np.concatenate(taps))
+    return flat, lens
+
+
+def _filter_code(params: SiftParams) -> int:
+    if params.variant == "script" and params.n_levels - 3 >= 3:
+        # SIFT.py:206 indexes a 3-deep stack with the global k: k >= 3 raises in the reference
+        raise IndexError("index 3 is out of bounds for axis 2 with size 3")
+    return _lib.FC_FILTER_SCRIPT if params.variant == "script" else _lib.FC_FILTER_APP
+
+
 def gauss_octave(base: torch.Tensor, params: SiftParams, octave_index: int, with_extrema: bool = True, taps=None) -> Octave:
     """generate_gaussian_images_in_octave for a [B,h,w] batch (SS:109-160).  `taps` overrides the separable
     taps derived from (sigma_base, s_value) -- used when the caller hands in its own kernel list."""
+    if params.dtype == "mixed":
+        return gauss_octave_mixed(base, params, octave_index, with_extrema, taps)[0]
     b, h, w = base.shape
     L = params.n_levels
-    if taps is None:
-        taps = [separable_taps(s) for s in sigma_levels(params.sigma_base, params.s_value)]
-    lens = (C.c_int * L)(*[len(t) for t in taps])
-    flat = np.ascontiguousarray(np.concatenate(taps))
+    flat, lens = _level_taps(params, taps)
     gauss = torch.empty((b, L, h, w), dtype=params.torch_dtype, device=base.device)
     extrema = None
     if with_extrema and L >= 4:
         extrema = torch.empty((L - 3, b, h, (w + 31) // 32), dtype=torch.int32, device=base.device)
-    filt = _lib.FC_FILTER_SCRIPT if params.variant == "script" else _lib.FC_FILTER_APP
-    if params.variant == "script" and L - 3 >= 3:
-        # SIFT.py:206 indexes a 3-deep stack with the global k: k >= 3 raises in the reference
-        raise IndexError("index 3 is out of bounds for axis 2 with size 3")
+    filt = _filter_code(params)
     with _stage("pyramid_o%d" % octave_index):
         _lib.call("fc_gauss_octave", ptr(base), params.fc_dtype, b, h, w, L, flat.ctypes.data_as(C.c_void_p),
                   C.cast(lens, C.c_void_p), 1 if octave_index > 0 else 0, filt, float(params.contrast_th),
@@ -336,23 +346,111 @@ def gauss_octave(base: torch.Tensor, params: SiftParams, octave_index: int, with
     return Octave(gauss, extrema, h, w)
 
 
-def downsample(octv: Octave, params: SiftParams) -> torch.Tensor:
-    """next base = G[-3][::2, ::2] (SS:209)."""
+# --- certified ("mixed") mode -----------------------------------------------------------------------------------
+#: |DoG32 - DoG64| stays below 4e-7 * max|image| (13-tap .. 27-tap float32 blurs of values in [0, 1]: measured 3.4e-7
+#: on 8M pixels, rms 4e-8); a comparison of two DoG values is trusted when they differ by more than EXTREMA_EPS * max|image|
+EXTREMA_EPS = 2.0 ** -19
+#: entries of the undecided-pixel list per octave: this fraction of the octave's (pixel, k) pairs (app filter decides
+#: ~2e-4 of them in float64; the script filter sends every extremum, ~1e-2).  More than that -> float64 fallback.
+AMB_FRACTION = {"app": 1.0 / 256, "script": 1.0 / 16}
+
+
+@dataclass
+class MixedOctave:
+    """float64 companions of a certified octave: base image, levels 1..s, and the undecided-pixel counter."""
+
+    base: torch.Tensor        # [B, h, w] float64
+    mid: torch.Tensor         # [B, s, h, w] float64: levels 1 .. s
+    amb_count: torch.Tensor   # [1] int32, entries the float32 search left to float64 (may exceed amb_cap)
+    amb_cap: int
+
+
+def gauss_octave_mixed(base64: torch.Tensor, params: SiftParams, octave_index: int, with_extrema: bool = True, taps=None,
+                       value_bound: torch.Tensor | None = None):
+    """One octave in certified mode -> (Octave with the float32 stack and the certified extremum masks, MixedOctave).
+
+    base64 is the octave's float64 base.  value_bound: device float with max |image| (computed here for octave 0 while
+    the float32 copy is made; deeper octaves are blurs of it and inherit the bound)."""
+    b, h, w = base64.shape
+    dev = base64.device
+    L, s = params.n_levels, params.s_value
+    flat, lens = _level_taps(params, taps)
+    tp, lp = flat.ctypes.data_as(C.c_void_p), C.cast(lens, C.c_void_p)
+    filt = _filter_code(params)
+    ident = 1 if octave_index > 0 else 0
+    base32 = torch.empty((b, h, w), dtype=torch.float32, device=dev)
+    with _stage("pyramid_f64"):
+        if value_bound is None:
+            value_bound = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.call("fc_convert_f64_bound", ptr(base64), C.c_int64(base64.numel()), ptr(base32), ptr(value_bound), stream_ptr())
+        else:
+            _lib.call("fc_convert_f64", ptr(base64), C.c_int64(base64.numel()), _lib.FC_F32, ptr(base32), stream_ptr())
+    gauss = torch.empty((b, L, h, w), dtype=torch.float32, device=dev)
+    with _stage("pyramid_o%d" % octave_index):
+        _lib.call("fc_gauss_octave", ptr(base32), _lib.FC_F32, b, h, w, L, tp, lp, ident, filt, float(params.contrast_th),
+                  float(params.ratio_th), ptr(gauss), None, stream_ptr())
+    n_mid = min(s, L - 1)
+    mid = torch.empty((b, n_mid, h, w), dtype=torch.float64, device=dev)
+    with _stage("pyramid_f64"):
+        _lib.call("fc_gauss_levels_f64", ptr(base64), b, h, w, L, tp, lp, 1, n_mid, ptr(mid), stream_ptr())
+    extrema, amb_count, cap = None, torch.zeros(1, dtype=torch.int32, device=dev), 0
+    if with_extrema and L >= 4:
+        extrema = torch.empty((L - 3, b, h, (w + 31) // 32), dtype=torch.int32, device=dev)
+        cap = int(b * h * w * (L - 3) * AMB_FRACTION[params.variant]) + 4096
+        amb = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+        with _stage("extrema"):
+            _lib.call("fc_gauss_octave_extrema_certified", ptr(gauss), b, h, w, L, filt, float(params.contrast_th),
+                      float(params.ratio_th), ptr(value_bound), float(EXTREMA_EPS), ptr(extrema), ptr(amb), cap, ptr(amb_count),
+                      stream_ptr())
+        with _stage("extrema_f64"):
+            _lib.call("fc_extrema_repair", ptr(base64), ident, ptr(mid), 1, n_mid, b, h, w, L, tp, lp, filt,
+                      float(params.contrast_th), float(params.ratio_th), ptr(amb), ptr(amb_count), cap, ptr(extrema), stream_ptr())
+    octv = Octave(gauss, extrema, h, w)
+    octv.value_bound = value_bound
+    return octv, MixedOctave(base64, mid, amb_count, cap)
+
+
+def downsample(octv: Octave, params: SiftParams, mixed: MixedOctave | None = None) -> torch.Tensor:
+    """next base = G[-3][::2, ::2] (SS:209); certified mode takes it from the float64 level s."""
     b, L, h, w = octv.gauss.shape
+    if mixed is not None:
+        n_mid = mixed.mid.shape[1]
+        if L - 3 < 1 or L - 3 > n_mid:
+            raise _lib.FeatureCraftError("certified mode keeps levels 1..s; the next base is level s")
+        out = torch.empty((b, (h + 1) // 2, (w + 1) // 2), dtype=torch.float64, device=mixed.mid.device)
+        _lib.call("fc_downsample2", ptr(mixed.mid), _lib.FC_F64, b, n_mid, L - 4, h, w, ptr(out), stream_ptr())
+        return out
     out = torch.empty((b, (h + 1) // 2, (w + 1) // 2), dtype=octv.gauss.dtype, device=octv.gauss.device)
     _lib.call("fc_downsample2", ptr(octv.gauss), params.fc_dtype, b, L, L - 3, h, w, ptr(out), stream_ptr())
     return out
 
 
+def _build_octaves(img, params: SiftParams, with_extrema: bool = True):
+    """-> (octaves, mixed companions or None per octave).  Certified mode that overflows its undecided-pixel list is
+    detected by the callers (they read the counters with the keypoint counts)."""
+    octaves, companions = [], []
+    bound = None
+    for o in range(params.n_octaves):
+        if params.dtype == "mixed":
+            octv, mx = gauss_octave_mixed(img, params, o, with_extrema, value_bound=bound)
+            bound = octv.value_bound
+        else:
+            octv, mx = gauss_octave(img, params, o, with_extrema), None
+        octaves.append(octv)
+        companions.append(mx)
+        if o + 1 < params.n_octaves:
+            img = downsample(octv, params, mx)
+    return octaves, companions
+
+
 def scale_space(base, params: SiftParams, with_extrema: bool = True) -> list:
     """generate_octaves_pyramid (SS:163-210) for a batch of base images."""
     img = _as_base_batch(base, params)
-    octaves = []
-    for o in range(params.n_octaves):
-        octv = gauss_octave(img, params, o, with_extrema)
-        octaves.append(octv)
-        if o + 1 < params.n_octaves:
-            img = downsample(octv, params)
+    octaves, companions = _build_octaves(img, params, with_extrema)
+    if params.dtype == "mixed" and with_extrema:
+        counts = [int(m.amb_count.item()) for m in companions]
+        if any(c > m.amb_cap for c, m in zip(counts, companions)):
+            return scale_space(base, replace(params, dtype="f64"), with_extrema)
     return octaves
 
 
@@ -375,9 +473,10 @@ def gradient_field(octv: Octave, level: int, params: SiftParams):
 
     f64 mode: three dense planes (the uint8 bin plane is the orientation operand).  f32 mode: magnitude and direction
     are the two halves of ONE interleaved [b, h, w, 2] plane (returned as strided views, so that a descriptor sample
-    is a single 8-byte gather) and the orientation operand is the packed magnitude|bin int32 plane."""
+    is a single 8-byte gather) and the orientation operand is the packed magnitude|bin int32 plane.  (Certified mode
+    uses gradient_codes instead.)"""
     b, L, h, w = octv.gauss.shape
-    if params.fc_dtype == _lib.FC_F32:
+    if octv.gauss.dtype == torch.float32:
         md = torch.empty((b, h, w, 2), dtype=torch.float32, device=octv.gauss.device)
         packed = torch.empty((b, h, w), dtype=torch.int32, device=md.device)
         _lib.call("fc_gradient_field_packed", ptr(octv.gauss), b, L, level, h, w, ptr(md), ptr(packed), stream_ptr())
@@ -385,20 +484,65 @@ def gradient_field(octv: Octave, level: int, params: SiftParams):
     mag = torch.empty((b, h, w), dtype=octv.gauss.dtype, device=octv.gauss.device)
     direction = torch.empty_like(mag)
     obin = torch.empty((b, h, w), dtype=torch.uint8, device=mag.device)
-    _lib.call("fc_gradient_field", ptr(octv.gauss), params.fc_dtype, b, L, level, h, w, ptr(mag), ptr(direction), ptr(obin),
+    _lib.call("fc_gradient_field", ptr(octv.gauss), _lib.FC_F64, b, L, level, h, w, ptr(mag), ptr(direction), ptr(obin),
               stream_ptr())
     return mag, direction, obin
 
 
-def orientation_bins(mag, obin, keypoints, n, weights, radius, bin_mask, params: SiftParams):
+def gradient_codes(levels64: torch.Tensor, plane: int) -> torch.Tensor:
+    """Certified mode's gradient field of one float64 level: [B,h,w] int32 words = magnitude | exact direction code."""
+    b, n, h, w = levels64.shape
+    codes = torch.empty((b, h, w), dtype=torch.int32, device=levels64.device)
+    _lib.call("fc_gradient_codes", ptr(levels64), b, n, plane, h, w, ptr(codes), stream_ptr())
+    return codes
+
+
+def _orientation_weights(sigma, h, w, dtype):
+    """(radius, table_ry, table_rx, device table): gaussian_filter_kernel(sigma) (KD:136) restricted to the offsets a
+    window clipped to an h x w image can reach."""
+    radius = int(round(sigma * 2))
+    if 2 * kernel_radius(sigma) + 1 != 2 * radius + 1:
+        # the reference multiplies a (2r+1)^2 window by the kernel: shapes must agree or numpy raises
+        raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,%d)"
+                         % (2 * radius + 1, 2 * radius + 1, 2 * kernel_radius(sigma) + 1, 2 * kernel_radius(sigma) + 1))
+    ry, rx = min(radius, max(h - 1, 0)), min(radius, max(w - 1, 0))
+    return radius, ry, rx, _cached(("ori", float(sigma), ry, rx), lambda: gaussian_window_table(sigma, ry, rx), dtype)
+
+
+def orientation_tolerance(radius: int) -> float:
+    """Relative error bound of a float32 orientation bin of certified mode against the float64 sum, doubled (the bin
+    and the 0.8 * max cut both carry it): magnitudes are rounded to 16 mantissa bits (2^-17), weights and products to
+    float32 (2 x 2^-24), and a lane adds at most ceil((2r+1)/lanes) * (2r+1) terms before the lanes are combined."""
+    lanes = 8 if radius <= 10 else (16 if radius <= 15 else 32)
+    side = 2 * radius + 1
+    per_lane = -(-side // lanes) * side
+    return 2.0 * (2.0 ** -17 + (per_lane + lanes + 4) * 2.0 ** -24)
+
+
+def orientation_bins(mag, obin, keypoints, n, sigma, bin_mask):
     """Launch the 36-bin histogram kernel on whichever orientation operand gradient_field produced."""
     b, h, w = mag.shape
     if obin.dtype == torch.int32:
-        _lib.call("fc_orientation_bins_packed", ptr(obin), b, h, w, ptr(keypoints), n, ptr(weights), radius, ptr(bin_mask),
+        radius, ry, rx, weights = _orientation_weights(sigma, h, w, torch.float32)
+        _lib.call("fc_orientation_bins_packed", ptr(obin), b, h, w, ptr(keypoints), n, ptr(weights), radius, ry, rx, ptr(bin_mask),
                   stream_ptr())
     else:
-        _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), params.fc_dtype, b, h, w, ptr(keypoints), n, ptr(weights),
-                  radius, ptr(bin_mask), stream_ptr())
+        fc = _lib.FC_F32 if mag.dtype == torch.float32 else _lib.FC_F64
+        radius, ry, rx, weights = _orientation_weights(sigma, h, w, mag.dtype)
+        _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), fc, b, h, w, ptr(keypoints), n, ptr(weights), radius, ry, rx,
+                  ptr(bin_mask), stream_ptr())
+
+
+def orientation_bins_certified(levels64, plane, codes, keypoints, n, sigma, bin_mask):
+    """Certified mode: float32 histograms from the code words, then the float64 decision of the keypoints whose
+    0.8 * max comparison the float32 error bound cannot guarantee."""
+    b, h, w = codes.shape
+    radius, ry, rx, w32 = _orientation_weights(sigma, h, w, torch.float32)
+    _, _, _, w64 = _orientation_weights(sigma, h, w, torch.float64)
+    _lib.call("fc_orientation_bins_coded", ptr(codes), b, h, w, ptr(keypoints), n, ptr(w32), radius, ry, rx,
+              float(orientation_tolerance(radius)), ptr(bin_mask), stream_ptr())
+    _lib.call("fc_orientation_recheck", ptr(levels64), levels64.shape[1], plane, ptr(codes), b, h, w, ptr(keypoints), n,
+              ptr(w64), radius, ry, rx, ptr(bin_mask), stream_ptr())
 
 
 def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
@@ -407,10 +551,8 @@ def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
     dev = mag.device
     if n == 0:
         return torch.empty((0, 4), dtype=torch.int32, device=dev)
-    radius, weights = _orientation_weights(sigma, params)
-    b, h, w = mag.shape
     bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
-    orientation_bins(mag, obin, keypoints, n, weights, radius, bin_mask, params)
+    orientation_bins(mag, obin, keypoints, n, sigma, bin_mask)
     offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
     scratch = scan_scratch(n)
     _lib.call("fc_orientation_scan", ptr(bin_mask), n, ptr(offsets), ptr(scratch), stream_ptr())
@@ -421,23 +563,35 @@ def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
     return oriented
 
 
-def describe(mag, direction, oriented, sigma, params: SiftParams, out_dtype=torch.float32) -> torch.Tensor:
-    """extract_sift_descriptors for one (octave, scale): -> [m,128]."""
+_FC_OUT = {torch.float32: _lib.FC_F32, torch.float64: _lib.FC_F64, torch.float16: _lib.FC_F16}
+
+
+def describe(mag, direction, oriented, sigma, params: SiftParams, out_dtype=torch.float32, out=None, placement=None) -> torch.Tensor:
+    """extract_sift_descriptors for one (octave, scale): -> [m,128].  mag = certified mode's code plane (int32),
+    the interleaved float32 plane's magnitude half, or a dense magnitude plane (with `direction`).
+    out / placement: write into the rows of `out` that the fc_desc_placement (an _lib.DescPlacement) selects."""
     m = oriented.shape[0]
-    desc = torch.empty((m, 128), dtype=out_dtype, device=mag.device)
+    desc = out if out is not None else torch.empty((m, 128), dtype=out_dtype, device=mag.device)
     if m == 0:
         return desc
     gmask = _cached(("gmask", float(sigma)), lambda: gaussian_mask16(sigma))
     trig = _cached(("trig",), trig_table)
     b, h, w = mag.shape
-    out_fc = _lib.FC_F32 if out_dtype == torch.float32 else _lib.FC_F64
-    if mag.stride(-1) == 2:  # halves of gradient_field's interleaved plane: mag.data_ptr() is the plane itself
+    out_fc = _FC_OUT[desc.dtype]
+    pl = C.byref(placement) if placement is not None else None
+    if mag.dtype == torch.int32:
+        _lib.call("fc_descriptors_coded", ptr(mag), b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig), ptr(desc), out_fc, pl,
+                  stream_ptr())
+    elif desc.dtype == torch.float16:
+        raise _lib.FeatureCraftError("float16 descriptor export is implemented for the certified (mixed) pipeline")
+    elif mag.stride(-1) == 2:  # halves of gradient_field's interleaved plane: mag.data_ptr() is the plane itself
         assert direction.data_ptr() == mag.data_ptr() + mag.element_size()
         _lib.call("fc_descriptors_interleaved", base_ptr(mag), b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig), ptr(desc), out_fc,
-                  stream_ptr())
+                  pl, stream_ptr())
     else:
-        _lib.call("fc_descriptors", ptr(mag), ptr(direction), params.fc_dtype, b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig),
-                  ptr(desc), out_fc, stream_ptr())
+        fc = _lib.FC_F32 if mag.dtype == torch.float32 else _lib.FC_F64
+        _lib.call("fc_descriptors", ptr(mag), ptr(direction), fc, b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig),
+                  ptr(desc), out_fc, pl, stream_ptr())
     return desc
 
 
@@ -449,23 +603,6 @@ def active_scales(params: SiftParams):
     if ks and ks[-1] >= params.n_levels:
         raise IndexError("list index out of range")
     return [k for k in ks if k <= params.s_value]
-
-
-def _mask_scan(mask: torch.Tensor, width: int):
-    b, h, _ = mask.shape
-    row_offsets = torch.empty(b * h + 1, dtype=torch.int32, device=mask.device)
-    scratch = scan_scratch(b * h)
-    _lib.call("fc_mask_scan", ptr(mask), b, h, width, ptr(row_offsets), ptr(scratch), stream_ptr())
-    return row_offsets
-
-
-def _orientation_weights(sigma, params: SiftParams):
-    radius = int(round(sigma * 2))
-    if 2 * kernel_radius(sigma) + 1 != 2 * radius + 1:
-        # the reference multiplies a (2r+1)^2 window by the kernel: shapes must agree or numpy raises
-        raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,%d)"
-                         % (2 * radius + 1, 2 * radius + 1, 2 * kernel_radius(sigma) + 1, 2 * kernel_radius(sigma) + 1))
-    return radius, _cached(("ori", float(sigma), params.dtype), lambda: gaussian_window_table(sigma), params.torch_dtype)
 
 
 def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch.float32, keep_octaves: bool = False) -> SiftResult:
@@ -481,13 +618,9 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     img = _as_base_batch(base, params)
     dev = img.device
     res = SiftResult(params, [])
+    certified = params.dtype == "mixed"
     # A: scale space
-    octaves = []
-    for o in range(params.n_octaves):
-        octv = gauss_octave(img, params, o, True)
-        octaves.append(octv)
-        if o + 1 < params.n_octaves:
-            img = downsample(octv, params)
+    octaves, companions = _build_octaves(img, params, True)
     if keep_octaves:
         res.octaves = octaves
     work = [(o, k) for o in range(params.n_octaves) for k in scales]
@@ -496,19 +629,27 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     # B: row-major compaction offsets.  The row counts of every (octave, scale) mask go into ONE concatenated array,
     # one scan covers them all and one gather launch brings the cumulative keypoint counts at the block boundaries to
     # the host: keypoints of all blocks then live in one list, block after block, in the reference's order.
+    # (Certified mode appends its per-octave undecided-pixel counters to the same array and reads them with the counts.)
     rows = [octaves[o].gauss.shape[0] * octaves[o].height for o, _ in work]
     row_start = [0]
     for r in rows:
         row_start.append(row_start[-1] + r)
+    n_extra = params.n_octaves if certified else 0
     with _stage("compact"):
         counts = torch.empty(row_start[-1], dtype=torch.int32, device=dev)
         for i, (o, k) in enumerate(work):
             octv = octaves[o]
             _lib.call("fc_mask_row_count", ptr(octv.extrema[k - 1]), octv.gauss.shape[0], octv.height, octv.width,
                       ptr(counts[row_start[i]:]), stream_ptr())
-        row_offs = torch.empty(row_start[-1] + 1, dtype=torch.int32, device=dev)
+        row_offs = torch.empty(row_start[-1] + 1 + n_extra, dtype=torch.int32, device=dev)
         _lib.call("fc_exclusive_scan_i32", ptr(counts), row_start[-1], ptr(row_offs), ptr(scan_scratch(row_start[-1])), stream_ptr())
-        kp_end = read_ints_at(row_offs, row_start[1:])  # cumulative keypoint count after each block
+        if certified:
+            row_offs[row_start[-1] + 1:] = torch.cat([m.amb_count for m in companions])
+        got = read_ints_at(row_offs, row_start[1:] + [row_start[-1] + 1 + o for o in range(n_extra)])
+    kp_end = got[:len(work)]  # cumulative keypoint count after each block
+    if certified and any(c > m.amb_cap for c, m in zip(got[len(work):], companions)):
+        # more undecided pixels than the list holds (large exactly-flat regions): the float64 kernels decide everything
+        return detect_and_describe(base, replace(params, dtype="f64"), out_dtype, keep_octaves)
     kp_start = [0] + kp_end[:-1]
     total_kp = kp_end[-1]
     kps_all = torch.empty((total_kp, 3), dtype=torch.int32, device=dev)
@@ -531,16 +672,26 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
             _lib.call("fc_mask_emit_keypoints", ptr(octv.extrema[k - 1]), ptr(row_offs[row_start[i]:]), b, h, octv.width,
                       ptr(kps_all), stream_ptr())
         sigma = keypoint_sigma(params.sigma_base, o, k, params.s_value)
+        if certified:
+            mid = companions[o].mid
+            with _stage("gradient_field"):
+                codes = gradient_codes(mid, k - 1)
+            with _stage("orientation"):
+                orientation_bins_certified(mid, k - 1, codes, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]])
+            state.append((codes, None, sigma))
+            continue
         with _stage("gradient_field"):
             mag, direction, obin = gradient_field(octv, k, params)
         with _stage("orientation"):
-            radius, weights = _orientation_weights(sigma, params)
-            orientation_bins(mag, obin, kps, n, weights, radius, bin_mask_all[kp_start[i]:kp_end[i]], params)
+            orientation_bins(mag, obin, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]])
         state.append((mag, direction, sigma))
+    batch = octaves[0].gauss.shape[0]
     if total_kp == 0:
         for blk in res.blocks:
             blk.oriented = torch.empty((0, 4), dtype=torch.int32, device=dev)
-            blk.descriptors = torch.empty((0, 128), dtype=out_dtype, device=dev)
+        res.descriptors = torch.empty((0, 128), dtype=out_dtype, device=dev)
+        res.records = torch.empty((0, 2), dtype=torch.int32, device=dev)
+        res.counts = torch.zeros(batch, dtype=torch.int32, device=dev)
         return res
     with _stage("orientation"):
         ori_counts = torch.empty(total_kp, dtype=torch.int32, device=dev)
@@ -549,20 +700,30 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
         _lib.call("fc_exclusive_scan_i32", ptr(ori_counts), total_kp, ptr(ori_offs), ptr(scan_scratch(total_kp)), stream_ptr())
         ori_end = read_ints_at(ori_offs, kp_end)  # cumulative oriented-keypoint count after each block
     ori_start = [0] + ori_end[:-1]
-    oriented_all = torch.empty((max(ori_end[-1], 1), 4), dtype=torch.int32, device=dev)
-    # D: oriented keypoint lists (every array is concatenated in block order, so ONE launch expands them all) and
-    # descriptors
-    if ori_end[-1] > 0:
-        with _stage("orientation"):
+    total = ori_end[-1]
+    oriented_all = torch.empty((max(total, 1), 4), dtype=torch.int32, device=dev)
+    # D: oriented keypoint lists (every array is concatenated in block order, so ONE launch expands them all), the
+    # final row of every (block, image) run, and the descriptors -- written straight to their final image-major rows
+    # together with the keypoint records, so nothing is sorted or gathered afterwards
+    res.descriptors = torch.empty((total, 128), dtype=out_dtype, device=dev)
+    res.records = torch.empty((total, 2), dtype=torch.int32, device=dev)
+    res.counts = torch.empty(batch, dtype=torch.int32, device=dev)
+    remap = torch.empty((len(work), batch, 2), dtype=torch.int32, device=dev)
+    with _stage("orientation"):
+        if total > 0:
             _lib.call("fc_orientation_emit", ptr(kps_all), ptr(bin_mask_all), ptr(ori_offs), total_kp, ptr(oriented_all), stream_ptr())
+        starts = (C.c_int * len(work))(*row_start[:-1])
+        heights = (C.c_int * len(work))(*[octaves[o].height for o, _ in work])
+        _lib.call("fc_sift_layout", ptr(row_offs), ptr(ori_offs), starts, heights, len(work), batch, ptr(remap), ptr(res.counts),
+                  stream_ptr())
     for i, (blk, st) in enumerate(zip(res.blocks, state)):
         blk.oriented = oriented_all[ori_start[i]:ori_end[i]]
-        if st is None:
-            blk.descriptors = torch.empty((0, 128), dtype=out_dtype, device=dev)
+        if st is None or ori_end[i] == ori_start[i]:
             continue
         mag, direction, sigma = st
+        place = _lib.DescPlacement(remap[i].data_ptr(), res.records.data_ptr(), ori_start[i], blk.octave, blk.scale)
         with _stage("descriptors"):
-            blk.descriptors = describe(mag, direction, blk.oriented, sigma, params, out_dtype)
+            describe(mag, direction, blk.oriented, sigma, params, out=res.descriptors, placement=place)
     return res
 
 
@@ -574,21 +735,26 @@ class BatchExtractor:
 
     Three CUDA streams: pinned input -> device (copy-in), the kernels (compute, = the caller's current stream),
     results -> pinned output (copy-out).  `submit` returns as soon as the work of a batch is queued; `collect`
-    waits for its copy-out only, so the D2H of batch i overlaps the kernels of batch i+1 (descriptors are
-    ~80 MB per 1024x1024 image: PCIe, not the kernels, bounds the end-to-end rate)."""
+    waits for its copy-out only, so the D2H of batch i overlaps the kernels of batch i+1.  A 1024x1024 image yields
+    ~156 000 descriptors, so PCIe, not the kernels, bounds the end-to-end rate; the export is therefore compact:
+    8-byte keypoint records (see unpack_records) and float16 descriptors by default (`descriptor_dtype`; the values
+    lie in [0, 0.7], so the float16 rounding moves a unit descriptor by < 5e-4 in L2 -- float32 is available)."""
 
     def __init__(self, params: SiftParams, batch: int, height: int, width: int, max_descriptors: int, depth: int = 2,
-                 upsample: bool = True):
+                 upsample: bool = True, descriptor_dtype=torch.float16):
         dev = require_cuda()
         self.params, self.batch, self.h, self.w, self.depth, self.upsample = params, batch, height, width, depth, upsample
+        if descriptor_dtype == torch.float16 and params.dtype != "mixed":
+            descriptor_dtype = torch.float32
+        self.desc_dtype = descriptor_dtype
         self.cap = int(max_descriptors)
         self.copy_in = torch.cuda.Stream(device=dev)
         self.copy_out = torch.cuda.Stream(device=dev)
         self.host_in = [torch.empty((batch, height, width), dtype=torch.float64).pin_memory() for _ in range(depth)]
         self.dev_in = [torch.empty((batch, height, width), dtype=torch.float64, device=dev) for _ in range(depth)]
-        self.host_desc = [torch.empty((self.cap, 128), dtype=torch.float32).pin_memory() for _ in range(depth)]
-        self.host_pts = [torch.empty((self.cap, 5), dtype=torch.float64).pin_memory() for _ in range(depth)]
-        self.host_cnt = [torch.empty(batch, dtype=torch.int64).pin_memory() for _ in range(depth)]
+        self.host_desc = [torch.empty((self.cap, 128), dtype=descriptor_dtype).pin_memory() for _ in range(depth)]
+        self.host_rec = [torch.empty((self.cap, 2), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.host_cnt = [torch.empty(batch, dtype=torch.int32).pin_memory() for _ in range(depth)]
         self.slots = [None] * depth
         self.staged = [None] * depth   # H2D-done event of an input already on its way to the device
         self.consumed = [None] * depth  # event after the last kernel that read dev_in[slot]
@@ -614,7 +780,8 @@ class BatchExtractor:
         """images: [B,H,W] float64 numpy array / CPU tensor (copied into the pinned staging buffer) or None to
         reuse what the staging buffer of this slot already holds (or what stage() already sent).  prefetch_next:
         also start the H2D of the following ticket from ITS staging buffer before this batch's kernels are queued.
-        Returns a ticket for collect()."""
+        Returns a ticket for collect().  Raises FeatureCraftError (FC_ERR_CAPACITY semantics) when the batch yields more
+        descriptors than max_descriptors -- before anything is copied."""
         ticket = self.n_submitted
         slot = ticket % self.depth
         if self.slots[slot] is not None:
@@ -629,40 +796,46 @@ class BatchExtractor:
         base = upsample2(self.dev_in[slot], self.params) if self.upsample else _as_base_batch(self.dev_in[slot], self.params)
         self.consumed[slot] = torch.cuda.Event()
         self.consumed[slot].record(compute)
-        res = detect_and_describe(base, self.params, out_dtype=torch.float32)
-        pts, desc, counts = res.assemble_device(self.batch)
-        m = int(pts.shape[0])
+        res = detect_and_describe(base, self.params, out_dtype=self.desc_dtype)
+        m = res.total
         if m > self.cap:
-            raise _lib.FeatureCraftError("batch produced %d descriptors, more than max_descriptors=%d" % (m, self.cap))
+            raise _lib.FeatureCraftError("%s: batch produced %d descriptors, max_descriptors=%d"
+                                         % (_lib.load().fc_status_string(-2).decode(), m, self.cap))
         ev_done = torch.cuda.Event()
         ev_done.record(compute)
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(ev_done)
-            self.host_desc[slot][:m].copy_(desc, non_blocking=True)
-            self.host_pts[slot][:m].copy_(pts, non_blocking=True)
-            self.host_cnt[slot].copy_(counts, non_blocking=True)
+            if m:
+                self.host_desc[slot][:m].copy_(res.descriptors, non_blocking=True)
+                self.host_rec[slot][:m].copy_(res.records, non_blocking=True)
+            self.host_cnt[slot].copy_(res.counts, non_blocking=True)
             ev_out = torch.cuda.Event()
             ev_out.record(self.copy_out)
-        self.slots[slot] = (ev_out, m, (pts, desc, counts))  # keep the device tensors alive until the copy is done
+        self.slots[slot] = (ev_out, m, res)  # keep the device tensors alive until the copy is done
         self.n_submitted += 1
         return ticket
 
-    def collect(self, ticket: int, copy: bool = False):
-        """-> list of (points [m,5] float64, descriptors [m,128] float32) per image; views into the pinned
-        buffers (valid until the slot is reused) unless copy=True."""
+    def collect(self, ticket: int, copy: bool = False, raw: bool = False):
+        """raw=False -> list of (points [m,5] float64, descriptors [m,128]) per image, like the reference returns them;
+        raw=True -> (records [M,2] int32, descriptors [M,128], counts [B] int32) exactly as they arrived (views into the
+        pinned buffers, valid until the slot is reused, unless copy=True): unpack_records() turns records into 5-tuples."""
         slot = ticket % self.depth
         ev_out, m, _keep = self.slots[slot]
         ev_out.synchronize()
         self.slots[slot] = None
         cnt = self.host_cnt[slot].numpy()
-        pts = self.host_pts[slot][:m].numpy()
+        rec = self.host_rec[slot][:m].numpy()
         desc = self.host_desc[slot][:m].numpy()
+        if raw:
+            return (rec.copy(), desc.copy(), cnt.copy()) if copy else (rec, desc, cnt)
+        pts = unpack_records(rec)
         out, lo = [], 0
         for b in range(self.batch):
             hi = lo + int(cnt[b])
-            out.append((pts[lo:hi].copy(), desc[lo:hi].copy()) if copy else (pts[lo:hi], desc[lo:hi]))
+            out.append((pts[lo:hi], desc[lo:hi].copy() if copy else desc[lo:hi]))
             lo = hi
         return out
 
-    def bytes_per_batch(self, ticket_result):
-        return self.batch * self.h * self.w * 8, sum(p.nbytes + d.nbytes for p, d in ticket_result) + self.batch * 8
+    def bytes_per_batch(self, m: int):
+        """(host->device, device->host) bytes of a batch with m descriptors"""
+        return self.batch * self.h * self.w * 8, m * (128 * self.host_desc[0].element_size() + 8) + self.batch * 4

@@ -48,7 +48,7 @@ def represent_keypoints(keypoints, DoG):
 
 
 def _params(s, sigma_base=1.6, n_octaves=4):
-    return sift.SiftParams(n_octaves=n_octaves, s_value=s, sigma_base=sigma_base, dtype=_ss.DTYPE, variant=_ss.VARIANT)
+    return sift.SiftParams(n_octaves=n_octaves, s_value=s, sigma_base=sigma_base, dtype=_ss.stage_dtype(), variant=_ss.VARIANT)
 
 
 def _level_as_octave(img, p):

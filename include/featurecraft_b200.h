@@ -40,7 +40,7 @@ typedef enum fc_status {
 } fc_status;
 
 /* element type of the SIFT scale space (FC_F32 = production layout, FC_F64 = exact-parity mode) */
-typedef enum fc_dtype { FC_F32 = 0, FC_F64 = 1 } fc_dtype;
+typedef enum fc_dtype { FC_F32 = 0, FC_F64 = 1, FC_F16 = 2 /* descriptor export only */ } fc_dtype;
 
 /* keypoint filter: FC_FILTER_APP keeps every extremum (APP/utils/SIFT_scale_space.py:89-105),
  * FC_FILTER_SCRIPT applies the contrast + edge-ratio tests of
@@ -173,6 +173,43 @@ FC_API int fc_downsample2(const void* gauss, int dtype, int batch, int n_levels,
 FC_API int fc_convert_f64(const double* src, int64_t n, int dtype, void* dst, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Certified mode of the scale space: float32 bulk arithmetic, float64 decisions.
+ * The float32 stack of fc_gauss_octave is kept for the 3x3x3 comparisons; every comparison whose outcome the
+ * float32 error bound cannot guarantee is re-evaluated on float64 values, so the keypoint lists are the ones the
+ * float64 path (and the reference, APP/utils/SIFT_scale_space.py:78-88) produces.
+ * ------------------------------------------------------------------------------------------- */
+
+/* float32 copy of a float64 array; value_bound[0] (float) receives an upper bound of max |src| -- the scale the
+ * error bounds below are relative to. */
+FC_API int fc_convert_f64_bound(const double* src, int64_t n, float* dst, float* value_bound, void* stream);
+
+/* Levels first_level .. first_level + level_count - 1 of the octave in float64 (same operator as fc_gauss_octave,
+ * SIFT_scale_space.py:132,144): out [batch][level_count][h][w].  Certified mode keeps levels 1 .. s: the gradient
+ * fields are taken from them (APP/utils/keypoint_descriptor.py:126, :241) and level s is the next octave's base
+ * (SIFT_scale_space.py:209). */
+FC_API int fc_gauss_levels_f64(const double* base, int batch, int height, int width, int n_levels, const double* taps_host,
+                        const int* tap_len_host, int first_level, int level_count, double* out, void* stream);
+
+/* get_keypoints on the float32 stack with an error margin: a centre that beats its 26 neighbours by more than
+ * eps = eps_rel * value_bound[0] is an extremum of the float64 DoG too and is written to `extrema`; one that loses by
+ * more than eps is not; anything closer (every tie included; with FC_FILTER_SCRIPT every hit, whose contrast / edge
+ * tests are float64 decisions as well) is appended to amb as int32 (image, k, row, col) with its mask bit clear.
+ * amb_count[0] is zeroed first and counts ALL such entries: if it exceeds amb_cap the list is incomplete and the
+ * caller must fall back to the float64 kernels for this octave. */
+FC_API int fc_gauss_octave_extrema_certified(const float* gauss, int batch, int height, int width, int n_levels, int filter,
+                                      double contrast_th, double ratio_th, const float* value_bound, double eps_rel,
+                                      uint32_t* extrema, int32_t* amb, int amb_cap, int32_t* amb_count, void* stream);
+
+/* Decides the amb entries on float64 DoG values and sets their bits in `extrema`: levels mid_first ..
+ * mid_first + mid_count - 1 are read from `mid` ([batch][mid_count][h][w], fc_gauss_levels_f64), level 0 of an
+ * octave > 0 (first_is_identity) from `base`, every other level is blurred on demand from `base` (float64) around the
+ * entry.  taps_host / tap_len_host as for fc_gauss_octave. */
+FC_API int fc_extrema_repair(const double* base, int first_is_identity, const double* mid, int mid_first, int mid_count,
+                      int batch, int height, int width, int n_levels, const double* taps_host, const int* tap_len_host,
+                      int filter, double contrast_th, double ratio_th, const int32_t* amb, const int32_t* amb_count,
+                      int amb_cap, uint32_t* extrema, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * SIFT orientation + descriptor (APP/utils/keypoint_descriptor.py)
  * ------------------------------------------------------------------------------------------- */
 
@@ -189,17 +226,39 @@ FC_API int fc_gradient_field(const void* gauss, int dtype, int batch, int n_leve
 FC_API int fc_gradient_field_packed(const void* gauss, int batch, int n_levels, int level, int height, int width,
                              void* magnitude_direction, uint32_t* magnitude_bin, void* stream);
 
+/* Certified mode's gradient field of plane `plane` of a float64 [batch][n_planes][h][w] stack: one word per pixel,
+ *   bits 5..0  the reference's orientation bin np.round(direction * 36 / 360) (:140-142; 0..36),
+ *   bits 7..6  which side of the bin centre the direction lies on (0 below, 1 at / above, 2 exactly on the upper
+ *              edge of a tie rounded down), so that 2 * bin - 1 + side is the exact 5-degree sector of the direction,
+ *   bits 31..8 the float32 magnitude (sign dropped) rounded to 16 mantissa bits.
+ * Sectors are decided in float32 unless the direction lies within 1e-4 degrees of a multiple of 5: those pixels
+ * evaluate the reference's float64 expression, so the codes are the float64 pipeline's. */
+FC_API int fc_gradient_codes(const double* levels, int batch, int n_planes, int plane, int height, int width,
+                      uint32_t* codes, void* stream);
+
 /* dog_keypoints_orientations (:116-172) for one (octave, scale): keypoints are (image, row, col)
- * int32 triples in reference order; `weights` is gaussian_filter_kernel(sigma) as a dense (2r+1)^2 device
- * table of element type `dtype`.  For keypoint n the 36-bin float32 histogram is built (sums in `dtype`)
- * and bin_mask[n] receives bit b for every bin with hist[b] >= float32(0.8) * max (:165-167). */
+ * int32 triples in reference order; `weights` is gaussian_filter_kernel(sigma) restricted to the offsets a window
+ * clipped to the image can reach: a dense (2 table_ry + 1) x (2 table_rx + 1) device table of element type `dtype`,
+ * entry [dy + table_ry][dx + table_rx], table_ry >= min(radius, h - 1), table_rx >= min(radius, w - 1).
+ * For keypoint n the 36-bin float32 histogram is built (sums in `dtype`) and bin_mask[n] receives bit b for every
+ * bin with hist[b] >= float32(0.8) * max (:165-167). */
 FC_API int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
                         int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
-                        uint64_t* bin_mask, void* stream);
+                        int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
 /* float32 pipeline: the same histograms from fc_gradient_field_packed's words (weights float32). */
 FC_API int fc_orientation_bins_packed(const uint32_t* magnitude_bin, int batch, int height, int width,
                                const int32_t* keypoints, int n_keypoints, const float* weights, int radius,
-                               uint64_t* bin_mask, void* stream);
+                               int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
+/* certified mode: float32 histograms from fc_gradient_codes' words; a keypoint with a bin within
+ * tolerance * max of the cut gets bit 63 of its mask set instead of a decision ... */
+FC_API int fc_orientation_bins_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* keypoints,
+                              int n_keypoints, const float* weights, int radius, int table_ry, int table_rx,
+                              double tolerance, uint64_t* bin_mask, void* stream);
+/* ... and this call decides exactly those keypoints with float64 magnitudes (from the float64 level), float64
+ * weights and float64 sums, clearing bit 63: bin_mask then equals the float64 path's. */
+FC_API int fc_orientation_recheck(const double* levels, int n_planes, int plane, const uint32_t* codes, int batch,
+                           int height, int width, const int32_t* keypoints, int n_keypoints, const double* weights,
+                           int radius, int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
 
 /* Expand bin masks into oriented keypoints in reference order: offsets[n] = popcount prefix
  * (exclusive, offsets[n_keypoints] = total; scratch as for fc_mask_scan), then
@@ -213,15 +272,43 @@ FC_API int fc_orientation_emit(const int32_t* keypoints, const uint64_t* bin_mas
  * from get_gaussian_mask :215-227), 4x4x8 float32 cell histograms, normalise / clip / normalise.
  * trig: device table [37][2 + 32] float64; rows 0..35 per orientation bin: cos, sin of theta*3.14159/180 and
  * the rint(cos*x*1024), rint(sin*x*1024) columns for x = 0..15 (computed on the host with the
- * reference's own libm calls); row 36, entries 0..7: smallest float64 rel with int(rel*8/360.0) >= j+1.  descriptors: [n_oriented][128] float32 (out_dtype FC_F32) or
- * float64. */
+ * reference's own libm calls); row 36, entries 0..7: smallest float64 rel with int(rel*8/360.0) >= j+1.
+ * descriptors: [n_oriented][128] float32 (out_dtype FC_F32) or float64; fc_descriptors_coded also writes FC_F16
+ * (host export at half the bytes: element error <= 2^-11 relative, i.e. <= 5e-4 L2 on a unit vector). */
+/* Optional output placement of the descriptor calls (NULL = descriptor n of the call goes to row n).  The batched
+ * pipeline keeps its keypoint lists block-major -- (octave, scale) blocks, each sorted by (image, row, col, bin) --
+ * while the reference's output is image-major (per image: octave, scale, row-major, bin).  With a placement the rows
+ * land in that final order directly: remap[image] = (list index of the image's first oriented keypoint of this block,
+ * its final row) from fc_sift_layout, list_base = list index of the call's first keypoint; `points` (optional)
+ * receives the keypoint record of every row: int16 row, int16 col, uint8 octave, uint8 scale, uint8 orientation bin,
+ * uint8 0 (the reference's 5-tuple (i, j, octave, scale, (bin + 0.5) * 10), APP/utils/keypoint_descriptor.py:167-170). */
+typedef struct fc_desc_placement {
+  const int32_t* remap; /* device, [batch][2] */
+  void* points;         /* device, [total oriented][8 bytes], or NULL */
+  int list_base;
+  int octave, scale;
+} fc_desc_placement;
+
 FC_API int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
                    const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
-                   void* descriptors, int out_dtype, void* stream);
+                   void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream);
 /* float32 pipeline: the same descriptors from fc_gradient_field_packed's interleaved (magnitude, direction) plane. */
 FC_API int fc_descriptors_interleaved(const void* magnitude_direction, int batch, int height, int width,
                                const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
-                               void* descriptors, int out_dtype, void* stream);
+                               void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream);
+
+/* remap tables ([n_blocks][batch][2] int32) and per-image totals ([batch] int32) for fc_desc_placement, from the
+ * pipeline's two scans: row_offsets = cumulative keypoints over the concatenated mask rows of all blocks (block i
+ * starts at row block_row_start_host[i] and has block_height_host[i] rows per image), oriented_offsets = cumulative
+ * oriented keypoints over all keypoints (fc_orientation_scan / fc_exclusive_scan_i32). */
+FC_API int fc_sift_layout(const int32_t* row_offsets, const int32_t* oriented_offsets, const int* block_row_start_host,
+                   const int* block_height_host, int n_blocks, int batch, int32_t* remap, int32_t* image_counts, void* stream);
+
+/* certified mode: the same descriptors from fc_gradient_codes' words; the bin of a sample is integer arithmetic on
+ * the exact direction sector (no float rounding near a bin edge). */
+FC_API int fc_descriptors_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* oriented,
+                         int n_oriented, const double* gmask, const double* trig, void* descriptors, int out_dtype,
+                         const fc_desc_placement* placement, void* stream);
 
 /* rotated_subimage (:175-212) on its own: nearest-neighbour window of out_width x out_height (<= 1024
  * samples) around (center_x, center_y) with cv2.warpAffine's 10-bit fixed-point coordinates; the caller
