@@ -63,11 +63,13 @@ SIGNATURES = {
     "fc_descriptors_interleaved": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _p]),
     "fc_sift_layout": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "fc_orientation_bins_packed": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p]),
-    "fc_orientation_bins_coded": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _d, _p, _p]),
-    "fc_orientation_recheck": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p]),
+    "fc_orientation_bins_coded": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _d, _p, _p, _p, _p]),
+    "fc_orientation_recheck": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _p]),
     "fc_gradient_codes": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fc_descriptors_coded": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _p]),
     "fc_convert_f64_bound": (_i, [_p, _i64, _p, _p, _p]),
+    "fc_upsample2_dual": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
+    "fc_downsample2_dual": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fc_gauss_levels_f64": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
     "fc_gauss_octave_extrema_certified": (_i, [_p, _i, _i, _i, _i, _i, _d, _d, _p, _d, _p, _p, _i, _p, _p]),
     "fc_extrema_repair": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _d, _d, _p, _p, _i, _p, _p]),

@@ -273,7 +273,8 @@ static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the fi
 // twice the image is never read): weight of offset (dy, dx) = weights[(dy + wry) * (2 wrx + 1) + dx + wrx].
 // kOriCoded also certifies its float32 histogram: `tol` bounds the relative error of a bin against the float64 sum
 // (magnitudes carry 2^-17, the float32 products and the running sums the rest); a keypoint with a bin within tol * max
-// of the 0.8 * max cut is marked (bit 63) for fc_orientation_recheck instead of being decided here.
+// of the 0.8 * max cut is marked (bit 63) and appended to `recheck_list` for fc_orientation_recheck instead of being
+// decided here (the list holds up to n_keypoints entries; recheck_count is zeroed by the launcher).
 enum { kOriPlanes = 0, kOriPacked = 1, kOriCoded = 2 };
 static constexpr unsigned long long kOriRecheckBit = 1ull << 63;
 
@@ -281,7 +282,8 @@ template <typename T, int LPK, int NR, int MODE>
 __global__ void __launch_bounds__(kOriWarps * 32)
 orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, int H, int W,
                    const int32_t* __restrict__ keypoints, int n_keypoints, const T* __restrict__ weights,
-                   int radius, int wry, int wrx, float tol, unsigned long long* __restrict__ bin_mask) {
+                   int radius, int wry, int wrx, float tol, unsigned long long* __restrict__ bin_mask,
+                   int32_t* __restrict__ recheck_list, int32_t* __restrict__ recheck_count) {
   constexpr bool PACKED = MODE != kOriPlanes;
   constexpr int KPW = 32 / LPK;        // keypoints per warp
   constexpr int PITCH = LPK;           // [bin][lane]: rows of LPK values, so clearing and the final sums move 16 bytes at a time
@@ -402,7 +404,10 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
     lo |= __shfl_xor_sync(0xffffffffu, lo, o);
     hi |= __shfl_xor_sync(0xffffffffu, hi, o);
   }
-  if (sub == 0 && valid) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+  if (sub == 0 && valid) {
+    bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    if (MODE == kOriCoded && (hi & 0x80000000u)) recheck_list[atomicAdd(recheck_count, 1)] = n;
+  }
 }
 
 __global__ void popcount64_kernel(const unsigned long long* __restrict__ m, int n, int32_t* __restrict__ counts) {
@@ -426,20 +431,21 @@ __global__ void orientation_emit_kernel(const int32_t* __restrict__ keypoints, c
 
 // Certified mode: the keypoints orientation_kernel<.., kOriCoded> marked (bit 63) are decided here the way the float64
 // pipeline decides them -- float64 magnitudes from the float64 level, float64 window weights, the exact bin codes,
-// float64 sums rounded to float32 (:158-163), cut at float32(0.8) * max.  One warp per keypoint (unmarked ones leave
-// at once), per-lane private histograms, fixed summation order.
+// float64 sums rounded to float32 (:158-163), cut at float32(0.8) * max.  The warps of a small persistent grid walk the
+// list the histogram kernel appended to; per-lane private histograms, fixed summation order.
 static constexpr int kRecheckWarps = 4;
 
 __global__ void __launch_bounds__(kRecheckWarps * 32)
 orientation_recheck_kernel(const double* __restrict__ levels, int n_planes, int plane_idx, const uint32_t* __restrict__ codes,
                            int H, int W, const int32_t* __restrict__ keypoints, int n_keypoints,
                            const double* __restrict__ weights, int radius, int wry, int wrx,
-                           unsigned long long* __restrict__ bin_mask) {
+                           unsigned long long* __restrict__ bin_mask, const int32_t* __restrict__ recheck_list,
+                           const int32_t* __restrict__ recheck_count) {
   __shared__ double hist[kRecheckWarps][kOriBins + 1][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * kRecheckWarps + warp;
-  if (n >= n_keypoints) return;                    // warp-uniform; no block-wide barrier below
-  if (!(bin_mask[n] & kOriRecheckBit)) return;
+  const int n_list = min(*recheck_count, n_keypoints);
+  for (int e = blockIdx.x * kRecheckWarps + warp; e < n_list; e += gridDim.x * kRecheckWarps) {  // warp-uniform
+  const int n = recheck_list[e];
   for (int bn = 0; bn <= kOriBins; ++bn) hist[warp][bn][lane] = 0.0;
   __syncwarp();
   const int b = keypoints[3 * n], ki = keypoints[3 * n + 1], kj = keypoints[3 * n + 2];
@@ -479,6 +485,8 @@ orientation_recheck_kernel(const double* __restrict__ levels, int n_planes, int 
   const uint32_t lo = __ballot_sync(0xffffffffu, f0 >= cut);
   const uint32_t hi = __ballot_sync(0xffffffffu, lane + 32 < kOriBins && f1 >= cut);
   if (lane == 0) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+  __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -823,7 +831,10 @@ extern "C" int fc_gradient_field_packed(const void* gauss, int batch, int n_leve
 
 static int launch_orientation(const void* magnitude, const uint8_t* orientation_bin, int dtype, int mode, int batch,
                               int height, int width, const int32_t* keypoints, int n_keypoints, const void* weights,
-                              int radius, int table_ry, int table_rx, float tol, uint64_t* bin_mask, void* stream) {
+                              int radius, int table_ry, int table_rx, float tol, uint64_t* bin_mask, int32_t* recheck_list,
+                              int32_t* recheck_count, void* stream) {
+  if (mode == kOriCoded && (!recheck_list || !recheck_count)) return FC_ERR_BAD_ARG;
+  if (mode == kOriCoded) FC_CUDA_TRY(cudaMemsetAsync(recheck_count, 0, sizeof(int32_t), (cudaStream_t)stream));
   if (!magnitude || (mode == kOriPlanes && !orientation_bin) || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0)
     return FC_ERR_BAD_ARG;
   // the table must cover every offset of the image-clipped window
@@ -842,7 +853,7 @@ static int launch_orientation(const void* magnitude, const uint8_t* orientation_
 #define FC_ORI(T, LPK, NR, MD)                                                                                      \
   orientation_kernel<T, LPK, NR, MD><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(        \
       (const T*)magnitude, orientation_bin, height, width, keypoints, n_keypoints, (const T*)weights, radius,      \
-      table_ry, table_rx, tol, (unsigned long long*)bin_mask)
+      table_ry, table_rx, tol, (unsigned long long*)bin_mask, recheck_list, recheck_count)
 #define FC_ORI_T(T, MD)                                              \
   do {                                                               \
     if (lpk == 8) {                                                  \
@@ -868,27 +879,30 @@ extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orienta
                                    int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
                                    int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
   return launch_orientation(magnitude, orientation_bin, dtype, kOriPlanes, batch, height, width, keypoints, n_keypoints,
-                            weights, radius, table_ry, table_rx, 0.f, bin_mask, stream);
+                            weights, radius, table_ry, table_rx, 0.f, bin_mask, nullptr, nullptr, stream);
 }
 
 extern "C" int fc_orientation_bins_packed(const uint32_t* magnitude_bin, int batch, int height, int width,
                                           const int32_t* keypoints, int n_keypoints, const float* weights, int radius,
                                           int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
   return launch_orientation(magnitude_bin, nullptr, FC_F32, kOriPacked, batch, height, width, keypoints, n_keypoints, weights,
-                            radius, table_ry, table_rx, 0.f, bin_mask, stream);
+                            radius, table_ry, table_rx, 0.f, bin_mask, nullptr, nullptr, stream);
 }
 
 extern "C" int fc_orientation_bins_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* keypoints,
                                          int n_keypoints, const float* weights, int radius, int table_ry, int table_rx,
-                                         double tolerance, uint64_t* bin_mask, void* stream) {
+                                         double tolerance, uint64_t* bin_mask, int32_t* recheck_list, int32_t* recheck_count,
+                                         void* stream) {
   if (!(tolerance >= 0.0)) return FC_ERR_BAD_ARG;
   return launch_orientation(codes, nullptr, FC_F32, kOriCoded, batch, height, width, keypoints, n_keypoints, weights, radius,
-                            table_ry, table_rx, (float)tolerance, bin_mask, stream);
+                            table_ry, table_rx, (float)tolerance, bin_mask, recheck_list, recheck_count, stream);
 }
 
 extern "C" int fc_orientation_recheck(const double* levels, int n_planes, int plane, const uint32_t* codes, int batch,
                                       int height, int width, const int32_t* keypoints, int n_keypoints, const double* weights,
-                                      int radius, int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
+                                      int radius, int table_ry, int table_rx, uint64_t* bin_mask, const int32_t* recheck_list,
+                                      const int32_t* recheck_count, void* stream) {
+  if (!recheck_list || !recheck_count) return FC_ERR_BAD_ARG;
   if (!levels || !codes || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0 || plane < 0 || plane >= n_planes)
     return FC_ERR_BAD_ARG;
   if (table_ry < (radius < height - 1 ? radius : height - 1) || table_rx < (radius < width - 1 ? radius : width - 1))
@@ -896,9 +910,10 @@ extern "C" int fc_orientation_recheck(const double* levels, int n_planes, int pl
   if (n_keypoints == 0) return FC_OK;
   if (!keypoints || !bin_mask || n_keypoints < 0) return FC_ERR_BAD_ARG;
   if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;
-  orientation_recheck_kernel<<<div_up(n_keypoints, kRecheckWarps), kRecheckWarps * 32, 0, (cudaStream_t)stream>>>(
+  const int want = div_up(n_keypoints, kRecheckWarps);
+  orientation_recheck_kernel<<<want < 148 * 4 ? want : 148 * 4, kRecheckWarps * 32, 0, (cudaStream_t)stream>>>(
       levels, n_planes, plane, codes, height, width, keypoints, n_keypoints, weights, radius, table_ry, table_rx,
-      (unsigned long long*)bin_mask);
+      (unsigned long long*)bin_mask, recheck_list, recheck_count);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;

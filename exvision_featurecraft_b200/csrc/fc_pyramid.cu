@@ -1203,24 +1203,25 @@ static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_
 // edge tests (implementation_without_ui/SIFT/SIFT.py:202-215) are then evaluated on float64 DoG values, exactly as
 // the float64 kernels above do.
 static constexpr int kRepairCols = 2 * 24 + 3;  // columns x-1-R .. x+1+R of the vertical pass for the largest radius
+static constexpr int kPatchR = 13;               // radii up to this one work from a shared-memory copy of the support
+static constexpr int kPatchSide = 2 * kPatchR + 3;
 
 // 3x3 block of one blurred level around (y, x), with the operation order of the float64 octave kernels (vertical pass
 // with symmetric pair sums, then the horizontal one), so that the values -- and every tie between them -- are bit for
 // bit those of gauss_octave_kernel<double> / gauss_mid_f64_kernel.  lane = one column of the vertical pass; `tmp` is
-// this warp's [3][kRepairCols] staging area in shared memory.
-__device__ __forceinline__ void warp_blur3x3(const double* __restrict__ img, int H, int W, int y, int x,
-                                             const double* __restrict__ taps, int R, int lane, double* __restrict__ tmp,
-                                             double* __restrict__ out9) {
+// this warp's [3][kRepairCols] staging area in shared memory; at(dy, dx) = base value at (y + dy, x + dx), 'symm'
+// reflected (from global memory, or from the warp's shared-memory patch when the support fits).
+template <typename At>
+__device__ __forceinline__ void warp_blur3x3(const At& at, const double* __restrict__ taps, int R, int lane,
+                                             double* __restrict__ tmp, double* __restrict__ out9) {
   const int ncol = 2 * R + 3;
   for (int c = lane; c < ncol; c += 32) {
-    const int xc = reflect_symm(x - 1 - R + c, W);
+    const int dx = c - 1 - R;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int yc = y - 1 + dy;
-      double acc = taps[R] * img[(size_t)reflect_symm(yc, H) * W + xc];
-      for (int k = 1; k <= R; ++k)
-        acc = fma(taps[R + k], img[(size_t)reflect_symm(yc - k, H) * W + xc] + img[(size_t)reflect_symm(yc + k, H) * W + xc], acc);
-      tmp[dy * kRepairCols + c] = acc;
+    for (int dy = -1; dy <= 1; ++dy) {
+      double acc = taps[R] * at(dy, dx);
+      for (int k = 1; k <= R; ++k) acc = fma(taps[R + k], at(dy - k, dx) + at(dy + k, dx), acc);
+      tmp[(dy + 1) * kRepairCols + c] = acc;
     }
   }
   __syncwarp();
@@ -1243,12 +1244,32 @@ extrema_repair_kernel(const double* __restrict__ base, int first_is_identity, co
                       int amb_cap, uint32_t* __restrict__ extrema, int pitch) {
   __shared__ double sG[kRepairWarps][4][9];  // levels k-1 .. k+2, 3x3 each (row-major)
   __shared__ double sTmp[kRepairWarps][3 * kRepairCols];
+  __shared__ double sPatch[kRepairWarps][kPatchSide * kPatchSide];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = min(*amb_count, amb_cap);
   const size_t plane = (size_t)H * W;
   for (int e = blockIdx.x * kRepairWarps + warp; e < n; e += gridDim.x * kRepairWarps) {
     const int4 ent = amb[e];
     const int b = ent.x, k = ent.y, y = ent.z, x = ent.w;
+    const double* img = base + (size_t)b * plane;
+    // largest radius among the levels that have to be blurred on demand: if its support fits, copy it to shared
+    // memory once (every load independent: one memory latency instead of one per tap)
+    int rm = 0;
+    for (int q = 0; q < 4; ++q) {
+      const int l = k - 1 + q;
+      const bool stored = (l >= mid_first && l < mid_first + mid_count) || (l == 0 && first_is_identity);
+      if (!stored) rm = max(rm, tab.radius[l]);
+    }
+    const bool patched = rm > 0 && rm <= kPatchR;
+    if (patched) {
+      const int side = 2 * rm + 3;
+      for (int i = lane; i < side * side; i += 32) {
+        const int r = i / side, c = i - r * side;
+        sPatch[warp][r * kPatchSide + c] = img[(size_t)reflect_symm(y - 1 - rm + r, H) * W + reflect_symm(x - 1 - rm + c, W)];
+      }
+      __syncwarp();
+    }
+    const double* patch = sPatch[warp] + (rm + 1) * kPatchSide + (rm + 1);  // element (y, x)
     for (int q = 0; q < 4; ++q) {
       const int l = k - 1 + q;
       const double* src = nullptr;
@@ -1257,8 +1278,12 @@ extrema_repair_kernel(const double* __restrict__ base, int first_is_identity, co
       if (src) {
         // centres satisfy 1 <= y <= H-3, 1 <= x <= W-3: the 3x3 block is inside the image
         if (lane < 9) sG[warp][q][lane] = src[(size_t)(y - 1 + lane / 3) * W + (x - 1 + lane % 3)];
+      } else if (patched) {
+        warp_blur3x3([&](int dy, int dx) { return patch[dy * kPatchSide + dx]; }, tab.taps + tab.offset[l], tab.radius[l], lane,
+                     sTmp[warp], sG[warp][q]);
       } else {
-        warp_blur3x3(base + (size_t)b * plane, H, W, y, x, tab.taps + tab.offset[l], tab.radius[l], lane, sTmp[warp], sG[warp][q]);
+        warp_blur3x3([&](int dy, int dx) { return img[(size_t)reflect_symm(y + dy, H) * W + reflect_symm(x + dx, W)]; },
+                     tab.taps + tab.offset[l], tab.radius[l], lane, sTmp[warp], sG[warp][q]);
       }
     }
     __syncwarp();
@@ -1530,6 +1555,81 @@ upsample2_block_kernel(const double* __restrict__ in, int H, int W, T* __restric
   }
 }
 }  // namespace fc
+
+// Certified mode wants the base twice -- float64 for the exact levels and the repair, float32 for the bulk kernels -- plus
+// the magnitude bound the float32 error margins scale with: one pass writes all three.
+namespace fc {
+__global__ void __launch_bounds__(256)
+upsample2_dual_kernel(const double* __restrict__ in, int H, int W, double* __restrict__ out64, float* __restrict__ out32,
+                      unsigned int* __restrict__ bound_bits) {
+  const int kx = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int ky = blockIdx.y;
+  const int b = blockIdx.z;
+  float m = 0.f;
+  if (kx < W) {
+    const double* a = in + (size_t)b * H * W;
+    const int yu = mirror_idx(ky - 1, H), yd = mirror_idx(ky + 1, H);
+    const int xc[4] = {mirror_idx(kx - 1, W), kx, kx + 1, mirror_idx(kx + 2, W)};
+    double ve[4], vo[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double mid = a[(size_t)ky * W + xc[c]];
+      ve[c] = lerp_075_025(mid, a[(size_t)yu * W + xc[c]]);
+      vo[c] = lerp_075_025(mid, a[(size_t)yd * W + xc[c]]);
+    }
+    const double e[4] = {lerp_075_025(ve[1], ve[0]), lerp_075_025(ve[1], ve[2]), lerp_075_025(ve[2], ve[1]), lerp_075_025(ve[2], ve[3])};
+    const double o[4] = {lerp_075_025(vo[1], vo[0]), lerp_075_025(vo[1], vo[2]), lerp_075_025(vo[2], vo[1]), lerp_075_025(vo[2], vo[3])};
+    const size_t off = ((size_t)b * 2 * H + 2 * ky) * 2 * W + 2 * kx;
+    double2* d0 = reinterpret_cast<double2*>(out64 + off);
+    double2* d1 = reinterpret_cast<double2*>(out64 + off + 2 * W);
+    d0[0] = make_double2(e[0], e[1]); d0[1] = make_double2(e[2], e[3]);
+    d1[0] = make_double2(o[0], o[1]); d1[1] = make_double2(o[2], o[3]);
+    *reinterpret_cast<float4*>(out32 + off) = make_float4((float)e[0], (float)e[1], (float)e[2], (float)e[3]);
+    *reinterpret_cast<float4*>(out32 + off + 2 * W) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) m = fmaxf(m, fmaxf((float)fabs(e[c]), (float)fabs(o[c])));
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bound_bits, __float_as_uint(m) + 1u);
+}
+
+// next octave's base in both precisions: level `level` of the float64 stack at the even pixels (SIFT_scale_space.py:209)
+__global__ void downsample2_dual_kernel(const double* __restrict__ gauss, int L, int level, int H, int W,
+                                        double* __restrict__ out64, float* __restrict__ out32, int H2, int W2) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= W2) return;
+  const double v = gauss[(((size_t)b * L + level) * H + 2 * y) * W + 2 * x];
+  out64[((size_t)b * H2 + y) * W2 + x] = v;
+  out32[((size_t)b * H2 + y) * W2 + x] = (float)v;
+}
+}  // namespace fc
+
+extern "C" int fc_upsample2_dual(const double* image, int batch, int height, int width, double* out64, float* out32,
+                                 float* value_bound, void* stream) {
+  if (!image || !out64 || !out32 || !value_bound || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
+  if ((width & 1) || ((reinterpret_cast<uintptr_t>(out64) | reinterpret_cast<uintptr_t>(out32)) & 15)) return FC_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  FC_CUDA_TRY(cudaMemsetAsync(value_bound, 0, sizeof(float), st));
+  upsample2_dual_kernel<<<dim3(div_up(width / 2, 256), height, batch), 256, 0, st>>>(
+      image, height, width, out64, out32, reinterpret_cast<unsigned int*>(value_bound));
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+extern "C" int fc_downsample2_dual(const double* gauss, int batch, int n_levels, int level, int height, int width,
+                                   double* out64, float* out32, void* stream) {
+  if (!gauss || !out64 || !out32 || batch <= 0 || height <= 0 || width <= 0 || level < 0 || level >= n_levels) return FC_ERR_BAD_ARG;
+  const int H2 = (height + 1) / 2, W2 = (width + 1) / 2;
+  downsample2_dual_kernel<<<dim3(div_up(W2, 256), H2, batch), 256, 0, (cudaStream_t)stream>>>(gauss, n_levels, level, height,
+                                                                                             width, out64, out32, H2, W2);
+  note_launch();
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
 
 extern "C" int fc_upsample2(const double* image, int batch, int height, int width, int dtype, void* out, void* stream) {
   if (!image || !out || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;

@@ -74,22 +74,29 @@ def read_last_ints(tensors) -> list:
     return [int(v) for v in host[: len(tensors)].tolist()]
 
 
-def read_ints_at(t: torch.Tensor, indices) -> list:
+def read_ints_at(t: torch.Tensor, indices, *more) -> list:
     """[int(t[i]) for i in indices] (int32 CUDA tensor) with one kernel launch per 32 indices and ONE host
-    synchronisation: the values are gathered into pinned host memory by a kernel (see read_int)."""
-    assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous() and len(indices) > 0
-    n = len(indices)
+    synchronisation: the values are gathered into pinned host memory by a kernel (see read_int).  Further
+    (tensor, indices) pairs may follow; their values are appended, still under the single synchronisation."""
+    jobs = [(t, list(indices))] + [(a, list(b)) for a, b in zip(more[0::2], more[1::2])]
+    n = sum(len(ix) for _, ix in jobs)
+    assert n > 0
+    for a, _ in jobs:
+        assert a.is_cuda and a.dtype == torch.int32 and a.is_contiguous()
     key = (t.device.index, torch.cuda.current_stream().cuda_stream)
     slot = _PINNED_SLOTS.get(key)
     if slot is None or slot[0].numel() < max(32, n):
         slot = (torch.zeros(max(32, n), dtype=torch.int32).pin_memory(), torch.cuda.Event())
         _PINNED_SLOTS[key] = slot
     host, ev = slot
-    for lo in range(0, n, 32):
-        part = [int(i) for i in indices[lo:lo + 32]]
-        idx = (C.c_int64 * len(part))(*part)
-        _lib.call("fc_publish_gather_i32", C.c_void_p(t.data_ptr()), idx, len(part), C.c_void_p(host.data_ptr() + 4 * lo),
-                  stream_ptr())
+    at = 0
+    for a, ix in jobs:
+        for lo in range(0, len(ix), 32):
+            part = [int(i) for i in ix[lo:lo + 32]]
+            idx = (C.c_int64 * len(part))(*part)
+            _lib.call("fc_publish_gather_i32", C.c_void_p(a.data_ptr()), idx, len(part), C.c_void_p(host.data_ptr() + 4 * at),
+                      stream_ptr())
+            at += len(part)
     ev.record()
     ev.synchronize()
     return [int(v) for v in host[:n].tolist()]

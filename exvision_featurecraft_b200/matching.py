@@ -99,6 +99,7 @@ class BatchMatcher:
         self.consumed = [None] * depth  # event after the kernels that read dev_q/dev_t[slot]
         self.done = [None] * depth      # event after the copy-out of a slot
         self.keep = [None] * depth      # device results kept alive until their copy-out has run
+        self.slots = [None] * depth     # ticket that occupies a slot until collect() releases it
         self.n_submitted = 0
 
     def submit(self, query=None, train=None) -> int:
@@ -106,6 +107,11 @@ class BatchMatcher:
         buffers host_q / host_t of this ticket's slot were filled by the caller."""
         ticket = self.n_submitted
         slot = ticket % self.depth
+        if self.slots[slot] is not None:
+            # the staging buffers and result buffers of this slot still belong to an uncollected pair: overwriting
+            # them would corrupt its pending H2D copy and make collect(old ticket) return this pair's matches
+            raise RuntimeError("collect() ticket %d (submitted %d calls ago) before reusing its buffers" % (self.slots[slot], self.depth))
+        self.slots[slot] = ticket
         self.n_submitted += 1
         if query is not None:
             self.host_q[slot].copy_(query if isinstance(query, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(query, np.float32)))
@@ -139,10 +145,15 @@ class BatchMatcher:
     def collect(self, ticket: int):
         """-> (pairs [M,2] int64 (queryIdx, trainIdx), distances [M] float32): the `good` list of match(), query order."""
         slot = ticket % self.depth
+        if self.slots[slot] != ticket:
+            raise RuntimeError("ticket %d is not pending (already collected, or never submitted)" % ticket)
         self.done[slot].synchronize()
         q = np.flatnonzero(self.host_good[slot].numpy())
         pairs = np.stack([q, self.host_idx[slot].numpy()[q].astype(np.int64)], 1)
-        return pairs, self.host_dist[slot].numpy()[q].copy()
+        dist = self.host_dist[slot].numpy()[q].copy()
+        self.slots[slot] = None
+        self.keep[slot] = None
+        return pairs, dist
 
     def bytes_per_pair(self):
         return (self.nq + self.nt) * 512, self.nq * 9

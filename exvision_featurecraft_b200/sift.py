@@ -303,6 +303,13 @@ def upsample2(gray, params: SiftParams) -> torch.Tensor:
         t = t.unsqueeze(0)
     b, h, w = t.shape
     out = torch.empty((b, 2 * h, 2 * w), dtype=params.torch_dtype, device=t.device)
+    if params.dtype == "mixed" and w % 2 == 0:
+        # certified mode wants the base in both precisions and its magnitude bound: one pass writes all three; the
+        # float32 companions ride along on the tensor (gauss_octave_mixed picks them up)
+        out._fc_base32 = torch.empty((b, 2 * h, 2 * w), dtype=torch.float32, device=t.device)
+        out._fc_bound = torch.empty(1, dtype=torch.float32, device=t.device)
+        _lib.call("fc_upsample2_dual", ptr(t), b, h, w, ptr(out), ptr(out._fc_base32), ptr(out._fc_bound), stream_ptr())
+        return out
     _lib.call("fc_upsample2", ptr(t), b, h, w, params.fc_dtype, ptr(out), stream_ptr())
     return out
 
@@ -366,7 +373,7 @@ class MixedOctave:
 
 
 def gauss_octave_mixed(base64: torch.Tensor, params: SiftParams, octave_index: int, with_extrema: bool = True, taps=None,
-                       value_bound: torch.Tensor | None = None):
+                       value_bound: torch.Tensor | None = None, amb_count: torch.Tensor | None = None):
     """One octave in certified mode -> (Octave with the float32 stack and the certified extremum masks, MixedOctave).
 
     base64 is the octave's float64 base.  value_bound: device float with max |image| (computed here for octave 0 while
@@ -378,13 +385,17 @@ def gauss_octave_mixed(base64: torch.Tensor, params: SiftParams, octave_index: i
     tp, lp = flat.ctypes.data_as(C.c_void_p), C.cast(lens, C.c_void_p)
     filt = _filter_code(params)
     ident = 1 if octave_index > 0 else 0
-    base32 = torch.empty((b, h, w), dtype=torch.float32, device=dev)
-    with _stage("pyramid_f64"):
-        if value_bound is None:
-            value_bound = torch.empty(1, dtype=torch.float32, device=dev)
-            _lib.call("fc_convert_f64_bound", ptr(base64), C.c_int64(base64.numel()), ptr(base32), ptr(value_bound), stream_ptr())
-        else:
-            _lib.call("fc_convert_f64", ptr(base64), C.c_int64(base64.numel()), _lib.FC_F32, ptr(base32), stream_ptr())
+    base32 = getattr(base64, "_fc_base32", None)
+    if base32 is not None and value_bound is None:
+        value_bound = getattr(base64, "_fc_bound", None)
+    if base32 is None or value_bound is None:
+        base32 = torch.empty((b, h, w), dtype=torch.float32, device=dev)
+        with _stage("pyramid_f64"):
+            if value_bound is None:
+                value_bound = torch.empty(1, dtype=torch.float32, device=dev)
+                _lib.call("fc_convert_f64_bound", ptr(base64), C.c_int64(base64.numel()), ptr(base32), ptr(value_bound), stream_ptr())
+            else:
+                _lib.call("fc_convert_f64", ptr(base64), C.c_int64(base64.numel()), _lib.FC_F32, ptr(base32), stream_ptr())
     gauss = torch.empty((b, L, h, w), dtype=torch.float32, device=dev)
     with _stage("pyramid_o%d" % octave_index):
         _lib.call("fc_gauss_octave", ptr(base32), _lib.FC_F32, b, h, w, L, tp, lp, ident, filt, float(params.contrast_th),
@@ -393,7 +404,9 @@ def gauss_octave_mixed(base64: torch.Tensor, params: SiftParams, octave_index: i
     mid = torch.empty((b, n_mid, h, w), dtype=torch.float64, device=dev)
     with _stage("pyramid_f64"):
         _lib.call("fc_gauss_levels_f64", ptr(base64), b, h, w, L, tp, lp, 1, n_mid, ptr(mid), stream_ptr())
-    extrema, amb_count, cap = None, torch.zeros(1, dtype=torch.int32, device=dev), 0
+    extrema, cap = None, 0
+    if amb_count is None:
+        amb_count = torch.zeros(1, dtype=torch.int32, device=dev)
     if with_extrema and L >= 4:
         extrema = torch.empty((L - 3, b, h, (w + 31) // 32), dtype=torch.int32, device=dev)
         cap = int(b * h * w * (L - 3) * AMB_FRACTION[params.variant]) + 4096
@@ -418,7 +431,8 @@ def downsample(octv: Octave, params: SiftParams, mixed: MixedOctave | None = Non
         if L - 3 < 1 or L - 3 > n_mid:
             raise _lib.FeatureCraftError("certified mode keeps levels 1..s; the next base is level s")
         out = torch.empty((b, (h + 1) // 2, (w + 1) // 2), dtype=torch.float64, device=mixed.mid.device)
-        _lib.call("fc_downsample2", ptr(mixed.mid), _lib.FC_F64, b, n_mid, L - 4, h, w, ptr(out), stream_ptr())
+        out._fc_base32 = torch.empty(out.shape, dtype=torch.float32, device=out.device)
+        _lib.call("fc_downsample2_dual", ptr(mixed.mid), b, n_mid, L - 4, h, w, ptr(out), ptr(out._fc_base32), stream_ptr())
         return out
     out = torch.empty((b, (h + 1) // 2, (w + 1) // 2), dtype=octv.gauss.dtype, device=octv.gauss.device)
     _lib.call("fc_downsample2", ptr(octv.gauss), params.fc_dtype, b, L, L - 3, h, w, ptr(out), stream_ptr())
@@ -426,13 +440,16 @@ def downsample(octv: Octave, params: SiftParams, mixed: MixedOctave | None = Non
 
 
 def _build_octaves(img, params: SiftParams, with_extrema: bool = True):
-    """-> (octaves, mixed companions or None per octave).  Certified mode that overflows its undecided-pixel list is
-    detected by the callers (they read the counters with the keypoint counts)."""
+    """-> (octaves, mixed companions or None per octave, per-octave undecided-pixel counters or None).  Certified mode
+    that overflows its undecided-pixel list is detected by the callers (they read the counters with the keypoint counts)."""
     octaves, companions = [], []
     bound = None
+    amb_counts = None
+    if params.dtype == "mixed":
+        amb_counts = torch.empty(params.n_octaves, dtype=torch.int32, device=img.device)  # zeroed by the search kernels' launcher
     for o in range(params.n_octaves):
         if params.dtype == "mixed":
-            octv, mx = gauss_octave_mixed(img, params, o, with_extrema, value_bound=bound)
+            octv, mx = gauss_octave_mixed(img, params, o, with_extrema, value_bound=bound, amb_count=amb_counts[o:o + 1])
             bound = octv.value_bound
         else:
             octv, mx = gauss_octave(img, params, o, with_extrema), None
@@ -440,15 +457,15 @@ def _build_octaves(img, params: SiftParams, with_extrema: bool = True):
         companions.append(mx)
         if o + 1 < params.n_octaves:
             img = downsample(octv, params, mx)
-    return octaves, companions
+    return octaves, companions, amb_counts
 
 
 def scale_space(base, params: SiftParams, with_extrema: bool = True) -> list:
     """generate_octaves_pyramid (SS:163-210) for a batch of base images."""
     img = _as_base_batch(base, params)
-    octaves, companions = _build_octaves(img, params, with_extrema)
+    octaves, companions, amb_counts = _build_octaves(img, params, with_extrema)
     if params.dtype == "mixed" and with_extrema:
-        counts = [int(m.amb_count.item()) for m in companions]
+        counts = amb_counts.tolist()
         if any(c > m.amb_cap for c, m in zip(counts, companions)):
             return scale_space(base, replace(params, dtype="f64"), with_extrema)
     return octaves
@@ -533,16 +550,16 @@ def orientation_bins(mag, obin, keypoints, n, sigma, bin_mask):
                   ptr(bin_mask), stream_ptr())
 
 
-def orientation_bins_certified(levels64, plane, codes, keypoints, n, sigma, bin_mask):
+def orientation_bins_certified(levels64, plane, codes, keypoints, n, sigma, bin_mask, recheck_list, recheck_count):
     """Certified mode: float32 histograms from the code words, then the float64 decision of the keypoints whose
-    0.8 * max comparison the float32 error bound cannot guarantee."""
+    0.8 * max comparison the float32 error bound cannot guarantee (recheck_list: int32 [n] scratch, recheck_count: [1])."""
     b, h, w = codes.shape
     radius, ry, rx, w32 = _orientation_weights(sigma, h, w, torch.float32)
     _, _, _, w64 = _orientation_weights(sigma, h, w, torch.float64)
     _lib.call("fc_orientation_bins_coded", ptr(codes), b, h, w, ptr(keypoints), n, ptr(w32), radius, ry, rx,
-              float(orientation_tolerance(radius)), ptr(bin_mask), stream_ptr())
+              float(orientation_tolerance(radius)), ptr(bin_mask), ptr(recheck_list), ptr(recheck_count), stream_ptr())
     _lib.call("fc_orientation_recheck", ptr(levels64), levels64.shape[1], plane, ptr(codes), b, h, w, ptr(keypoints), n,
-              ptr(w64), radius, ry, rx, ptr(bin_mask), stream_ptr())
+              ptr(w64), radius, ry, rx, ptr(bin_mask), ptr(recheck_list), ptr(recheck_count), stream_ptr())
 
 
 def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
@@ -620,7 +637,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     res = SiftResult(params, [])
     certified = params.dtype == "mixed"
     # A: scale space
-    octaves, companions = _build_octaves(img, params, True)
+    octaves, companions, amb_dev = _build_octaves(img, params, True)
     if keep_octaves:
         res.octaves = octaves
     work = [(o, k) for o in range(params.n_octaves) for k in scales]
@@ -629,7 +646,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     # B: row-major compaction offsets.  The row counts of every (octave, scale) mask go into ONE concatenated array,
     # one scan covers them all and one gather launch brings the cumulative keypoint counts at the block boundaries to
     # the host: keypoints of all blocks then live in one list, block after block, in the reference's order.
-    # (Certified mode appends its per-octave undecided-pixel counters to the same array and reads them with the counts.)
+    # (Certified mode reads its per-octave undecided-pixel counters in the same synchronisation.)
     rows = [octaves[o].gauss.shape[0] * octaves[o].height for o, _ in work]
     row_start = [0]
     for r in rows:
@@ -641,19 +658,23 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
             octv = octaves[o]
             _lib.call("fc_mask_row_count", ptr(octv.extrema[k - 1]), octv.gauss.shape[0], octv.height, octv.width,
                       ptr(counts[row_start[i]:]), stream_ptr())
-        row_offs = torch.empty(row_start[-1] + 1 + n_extra, dtype=torch.int32, device=dev)
+        row_offs = torch.empty(row_start[-1] + 1, dtype=torch.int32, device=dev)
         _lib.call("fc_exclusive_scan_i32", ptr(counts), row_start[-1], ptr(row_offs), ptr(scan_scratch(row_start[-1])), stream_ptr())
         if certified:
-            row_offs[row_start[-1] + 1:] = torch.cat([m.amb_count for m in companions])
-        got = read_ints_at(row_offs, row_start[1:] + [row_start[-1] + 1 + o for o in range(n_extra)])
-    kp_end = got[:len(work)]  # cumulative keypoint count after each block
-    if certified and any(c > m.amb_cap for c, m in zip(got[len(work):], companions)):
+            got = read_ints_at(row_offs, row_start[1:], amb_dev, range(n_extra))
+        else:
+            got = read_ints_at(row_offs, row_start[1:])
+    kp_end, amb_counts = got[:len(work)], got[len(work):]  # cumulative keypoint count after each block
+    if certified and any(c > m.amb_cap for c, m in zip(amb_counts, companions)):
         # more undecided pixels than the list holds (large exactly-flat regions): the float64 kernels decide everything
         return detect_and_describe(base, replace(params, dtype="f64"), out_dtype, keep_octaves)
     kp_start = [0] + kp_end[:-1]
     total_kp = kp_end[-1]
     kps_all = torch.empty((total_kp, 3), dtype=torch.int32, device=dev)
     bin_mask_all = torch.empty(max(total_kp, 1), dtype=torch.int64, device=dev)
+    if certified:
+        recheck_all = torch.empty(max(total_kp, 1), dtype=torch.int32, device=dev)
+        recheck_counts = torch.empty(len(work), dtype=torch.int32, device=dev)
     # C: keypoints, gradient fields, orientation histograms of every block; then ONE scan of all per-keypoint
     # orientation counts and one gather for the cumulative oriented counts
     state = []
@@ -677,7 +698,8 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
             with _stage("gradient_field"):
                 codes = gradient_codes(mid, k - 1)
             with _stage("orientation"):
-                orientation_bins_certified(mid, k - 1, codes, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]])
+                orientation_bins_certified(mid, k - 1, codes, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]],
+                                           recheck_all[kp_start[i]:kp_end[i]], recheck_counts[i:i + 1])
             state.append((codes, None, sigma))
             continue
         with _stage("gradient_field"):
@@ -705,7 +727,9 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     # D: oriented keypoint lists (every array is concatenated in block order, so ONE launch expands them all), the
     # final row of every (block, image) run, and the descriptors -- written straight to their final image-major rows
     # together with the keypoint records, so nothing is sorted or gathered afterwards
-    res.descriptors = torch.empty((total, 128), dtype=out_dtype, device=dev)
+    # (float16 export is a store format of the certified kernels; the other modes convert afterwards)
+    desc_dtype = out_dtype if (certified or out_dtype != torch.float16) else torch.float32
+    res.descriptors = torch.empty((total, 128), dtype=desc_dtype, device=dev)
     res.records = torch.empty((total, 2), dtype=torch.int32, device=dev)
     res.counts = torch.empty(batch, dtype=torch.int32, device=dev)
     remap = torch.empty((len(work), batch, 2), dtype=torch.int32, device=dev)
@@ -724,6 +748,8 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
         place = _lib.DescPlacement(remap[i].data_ptr(), res.records.data_ptr(), ori_start[i], blk.octave, blk.scale)
         with _stage("descriptors"):
             describe(mag, direction, blk.oriented, sigma, params, out=res.descriptors, placement=place)
+    if desc_dtype != out_dtype:
+        res.descriptors = res.descriptors.to(out_dtype)
     return res
 
 

@@ -183,6 +183,13 @@ FC_API int fc_convert_f64(const double* src, int64_t n, int dtype, void* dst, vo
  * error bounds below are relative to. */
 FC_API int fc_convert_f64_bound(const double* src, int64_t n, float* dst, float* value_bound, void* stream);
 
+/* The two base-image producers of certified mode, each writing the float64 and the float32 copy in one pass:
+ * fc_upsample2 (even width; also value_bound as fc_convert_f64_bound) and fc_downsample2 of a float64 stack. */
+FC_API int fc_upsample2_dual(const double* image, int batch, int height, int width, double* out64, float* out32,
+                      float* value_bound, void* stream);
+FC_API int fc_downsample2_dual(const double* gauss, int batch, int n_levels, int level, int height, int width,
+                        double* out64, float* out32, void* stream);
+
 /* Levels first_level .. first_level + level_count - 1 of the octave in float64 (same operator as fc_gauss_octave,
  * SIFT_scale_space.py:132,144): out [batch][level_count][h][w].  Certified mode keeps levels 1 .. s: the gradient
  * fields are taken from them (APP/utils/keypoint_descriptor.py:126, :241) and level s is the next octave's base
@@ -250,15 +257,18 @@ FC_API int fc_orientation_bins_packed(const uint32_t* magnitude_bin, int batch, 
                                const int32_t* keypoints, int n_keypoints, const float* weights, int radius,
                                int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
 /* certified mode: float32 histograms from fc_gradient_codes' words; a keypoint with a bin within
- * tolerance * max of the cut gets bit 63 of its mask set instead of a decision ... */
+ * tolerance * max of the cut gets bit 63 of its mask set instead of a decision and its index appended to
+ * recheck_list (int32 [n_keypoints]; recheck_count[0] is zeroed first) ... */
 FC_API int fc_orientation_bins_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* keypoints,
                               int n_keypoints, const float* weights, int radius, int table_ry, int table_rx,
-                              double tolerance, uint64_t* bin_mask, void* stream);
+                              double tolerance, uint64_t* bin_mask, int32_t* recheck_list, int32_t* recheck_count,
+                              void* stream);
 /* ... and this call decides exactly those keypoints with float64 magnitudes (from the float64 level), float64
  * weights and float64 sums, clearing bit 63: bin_mask then equals the float64 path's. */
 FC_API int fc_orientation_recheck(const double* levels, int n_planes, int plane, const uint32_t* codes, int batch,
                            int height, int width, const int32_t* keypoints, int n_keypoints, const double* weights,
-                           int radius, int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
+                           int radius, int table_ry, int table_rx, uint64_t* bin_mask, const int32_t* recheck_list,
+                           const int32_t* recheck_count, void* stream);
 
 /* Expand bin masks into oriented keypoints in reference order: offsets[n] = popcount prefix
  * (exclusive, offsets[n_keypoints] = total; scratch as for fc_mask_scan), then

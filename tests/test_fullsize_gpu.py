@@ -161,9 +161,10 @@ def test_full_size_keypoints_and_descriptors_equal_reference(mods, large, name):
     ok = ~np.isnan(sample).any(1)
     # descriptors: every 32nd one in full (north_star: 1e-3 L2; float32 rounding gives ~1e-6) ...
     assert np.linalg.norm(d[::SAMPLE_STRIDE][ok] - sample[ok], axis=1).max() < 2e-5
-    # ... and ALL of them through two fixed projections (a single sample in a wrong bin moves these by ~1e-2)
+    # ... and ALL of them through two fixed projections: |projection error| <= |P column| (~11) x L2 error, so this
+    # bounds nothing above north_star's 1e-3 L2 away, while a sample of typical weight in a wrong bin moves it by ~1e-2
     proj = np.nan_to_num(d) @ projection_matrix()
-    assert np.abs(proj - g[name + "/desc_proj"]).max() < 2e-4
+    assert np.abs(proj - g[name + "/desc_proj"]).max() < 1e-3
 
 
 @pytest.mark.parametrize("ratio", [0.3, 0.6, 0.8])
