@@ -76,6 +76,11 @@ SIGNATURES = {
     "fc_orientation_scan": (_i, [_p, _i, _p, _p, _p]),
     "fc_orientation_emit": (_i, [_p, _p, _p, _i, _p, _p]),
     "fc_descriptors": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _p]),
+    "fc_bgr_to_rgb_u8": (_i, [_p, _i, _i, _i, _p, _p]),
+    "fc_rgb_to_gray_f64": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "fc_u8_to_unit_f64": (_i, [_p, _i64, _p, _p]),
+    "fc_blur_axis_f64": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
+    "fc_zoom_linear_f64": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fc_match_workspace_bytes": (_i64, [_i, _i]),
     "fc_match_workspace_stats_offset": (_i64, [_i, _i]),
     "fc_match_knn2": (_i, [_p, _i, _p, _i, _d, _p, _p, _p, _p, _p]),

@@ -87,21 +87,51 @@ def harris_detection(img, window_size, k, threshold):
     return [[int(x), int(y), r] for (y, x), r in zip(rc.tolist(), vals.tolist())], out
 
 
-def apply_sift(main_image, template, n_octaves=4, s_value=2, sigma_base=1.6, contrast_th=0.03, r_ratio=10,
-               tuning_factor=0.3, resize=None):
-    """BackendClass.apply_sift (FeatureCraft_Backend.py:480-523) / SIFT.py:683-707 without the Qt calls:
-    keypoints + descriptors of both images, 2-NN ratio-test matching.
+def apply_sift_matches(main_image, template, n_octaves=4, s_value=2, sigma_base=1.6, contrast_th=0.03, r_ratio=10,
+                       tuning_factor=0.3, resize=True, return_keypoints=True):
+    """The arithmetic of apply_sift, device resident from the first resize to the ratio test: both images are resized
+    (sift_resize), described (computeKeypointsAndDescriptors) and matched without their descriptors ever leaving HBM
+    -- what crosses PCIe is the two input images and the `good` list.
 
-    `resize` is the reference's ``sift_resize`` (scikit-image, the step before the hot path): pass it to get the
-    reference's ~1 MP working size, or None to use the images as given.  Returns
-    (good [(queryIdx, trainIdx, distance)], (points_main, desc_main), (points_template, desc_template));
-    the reference draws `good` with cv2.drawMatches (utils/keypoint_descriptor.py:351-364)."""
+    Returns (good [(queryIdx, trainIdx, distance)], points_main, points_template); the point lists are the reference's
+    5-tuples (None with return_keypoints=False)."""
+    import torch
+
+    from . import matching, sift
     from .utils import keypoint_descriptor as KD
 
-    if resize is not None:
-        main_image, ratio = resize(main_image)
-        template, _ = resize(template, ratio)
-    kp_a, des_a = KD.computeKeypointsAndDescriptors(main_image, n_octaves, s_value, sigma_base, contrast_th, r_ratio)
-    kp_b, des_b = KD.computeKeypointsAndDescriptors(template, n_octaves, s_value, sigma_base, contrast_th, r_ratio)
-    good = KD.match(main_image, kp_a, des_a, template, kp_b, des_b, tuning_factor)
-    return good, (kp_a, des_a), (kp_b, des_b)
+    if resize:
+        shape = np.shape(main_image)
+        ratio = np.sqrt((1024 * 1024) / np.prod(shape[:2]))
+        images = []
+        for img in (main_image, template):
+            t = KD._as_float_image(img)
+            newshape = [int(round(d * ratio)) for d in t.shape[:2]]
+            images.append(KD.resize_device(t, newshape, anti_aliasing=True))
+    else:
+        images = [KD._as_float_image(main_image), KD._as_float_image(template)]
+    ra, rb = (KD.extract_device(img, n_octaves, s_value, sigma_base, contrast_th, r_ratio, out_dtype=torch.float32) for img in images)
+    if rb.total < 2:
+        raise ValueError("not enough values to unpack (expected 2, got %d)" % rb.total)  # `for m, n in matches`, KD:345
+    idx, dist, good = matching.knn2(ra.descriptors, rb.descriptors, tuning_factor, "tensor")
+    q = torch.nonzero(good).flatten()
+    triples = torch.stack([q.to(torch.float64), idx[q, 0].to(torch.float64), dist[q, 0].to(torch.float64)], 1).cpu().numpy()
+    out = [(int(a), int(b), float(c)) for a, b, c in triples.tolist()]
+    if not return_keypoints:
+        return out, None, None
+    pa = [tuple(r) for r in sift.unpack_records(ra.records.cpu().numpy()).tolist()]
+    pb = [tuple(r) for r in sift.unpack_records(rb.records.cpu().numpy()).tolist()]
+    return out, pa, pb
+
+
+def apply_sift(main_image, template, n_octaves, s_value, sigma_base, contrast_th, r_ratio, tuning_factor):
+    """BackendClass.apply_sift (FeatureCraft_Backend.py:480-523) / SIFT.py:683-707 without the Qt calls, same arguments
+    and return value: sift_resize of both images (ratio from the main image), keypoints + descriptors of both, match()
+    -> the match canvas (cv2.drawMatches on the host, utils/keypoint_descriptor.py:351-364)."""
+    from .utils import keypoint_descriptor as KD
+
+    main_image, ratio = KD.sift_resize(main_image)
+    template, _ = KD.sift_resize(template, ratio)
+    img_kp, img_des = KD.computeKeypointsAndDescriptors(main_image, n_octaves, s_value, sigma_base, contrast_th, r_ratio)
+    template_kp, template_des = KD.computeKeypointsAndDescriptors(template, n_octaves, s_value, sigma_base, contrast_th, r_ratio)
+    return KD.match(main_image, img_kp, img_des, template, template_kp, template_des, tuning_factor)

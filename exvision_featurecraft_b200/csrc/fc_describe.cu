@@ -431,9 +431,11 @@ __global__ void orientation_emit_kernel(const int32_t* __restrict__ keypoints, c
 
 // Certified mode: the keypoints orientation_kernel<.., kOriCoded> marked (bit 63) are decided here the way the float64
 // pipeline decides them -- float64 magnitudes from the float64 level, float64 window weights, the exact bin codes,
-// float64 sums rounded to float32 (:158-163), cut at float32(0.8) * max.  The warps of a small persistent grid walk the
-// list the histogram kernel appended to; per-lane private histograms, fixed summation order.
-static constexpr int kRecheckWarps = 4;
+// float64 sums rounded to float32 (:158-163), cut at float32(0.8) * max.  A small persistent grid walks the list the
+// histogram kernel appended to, one CTA of 8 warps per keypoint (windows reach 155 x 155 samples: a single warp would
+// need a millisecond for one of those); every lane owns a private histogram, sums are combined in a fixed order.
+static constexpr int kRecheckWarps = 8;
+static constexpr size_t kRecheckSmem = sizeof(double) * kRecheckWarps * (kOriBins + 1) * 33;
 
 __global__ void __launch_bounds__(kRecheckWarps * 32)
 orientation_recheck_kernel(const double* __restrict__ levels, int n_planes, int plane_idx, const uint32_t* __restrict__ codes,
@@ -441,51 +443,54 @@ orientation_recheck_kernel(const double* __restrict__ levels, int n_planes, int 
                            const double* __restrict__ weights, int radius, int wry, int wrx,
                            unsigned long long* __restrict__ bin_mask, const int32_t* __restrict__ recheck_list,
                            const int32_t* __restrict__ recheck_count) {
-  __shared__ double hist[kRecheckWarps][kOriBins + 1][33];
+  extern __shared__ __align__(16) double rc_hist[];  // [warp][bin 0..36][33]
+  __shared__ float s_f[kOriBins];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* myh = rc_hist + (size_t)warp * (kOriBins + 1) * 33 + lane;
   const int n_list = min(*recheck_count, n_keypoints);
-  for (int e = blockIdx.x * kRecheckWarps + warp; e < n_list; e += gridDim.x * kRecheckWarps) {  // warp-uniform
-  const int n = recheck_list[e];
-  for (int bn = 0; bn <= kOriBins; ++bn) hist[warp][bn][lane] = 0.0;
-  __syncwarp();
-  const int b = keypoints[3 * n], ki = keypoints[3 * n + 1], kj = keypoints[3 * n + 2];
-  const double* g = levels + ((size_t)b * n_planes + plane_idx) * H * W;
-  const uint32_t* pk = codes + (size_t)b * H * W;
-  const int side = 2 * wrx + 1;
-  const int r0 = max(ki - radius, 0), r1 = min(ki + radius, H - 1);
-  const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
-  const int woff = (wry - ki) * side + (wrx - kj);
-  for (int r = r0; r <= r1; ++r) {
-    const int ru = r > 0 ? r - 1 : 0, rd = r < H - 1 ? r + 1 : H - 1;
-    for (int c = c0 + lane; c <= c1; c += 32) {
+  for (int e = blockIdx.x; e < n_list; e += gridDim.x) {  // block-uniform
+    const int n = recheck_list[e];
+    for (int bn = 0; bn <= kOriBins; ++bn) myh[bn * 33] = 0.0;
+    const int b = keypoints[3 * n], ki = keypoints[3 * n + 1], kj = keypoints[3 * n + 2];
+    const double* g = levels + ((size_t)b * n_planes + plane_idx) * H * W;
+    const uint32_t* pk = codes + (size_t)b * H * W;
+    const int side = 2 * wrx + 1;
+    const int r0 = max(ki - radius, 0), r1 = min(ki + radius, H - 1);
+    const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
+    const int ncol = c1 - c0 + 1, total = ncol * (r1 - r0 + 1);
+    const int woff = (wry - ki) * side + (wrx - kj);
+    for (int i = threadIdx.x; i < total; i += kRecheckWarps * 32) {
+      const int rr = i / ncol;
+      const int r = r0 + rr, c = c0 + (i - rr * ncol);
+      const int ru = r > 0 ? r - 1 : 0, rd = r < H - 1 ? r + 1 : H - 1;
       const int cl = c > 0 ? c - 1 : 0, cr = c < W - 1 ? c + 1 : W - 1;
       const double gx = g[(size_t)r * W + cl] - g[(size_t)r * W + cr];
       const double gy = g[(size_t)ru * W + c] - g[(size_t)rd * W + c];
       const double m = sqrt(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)));
-      hist[warp][pk[(size_t)r * W + c] & 63u][lane] += __dmul_rn(m, weights[woff + r * side + c]);
+      myh[(pk[(size_t)r * W + c] & 63u) * 33] += __dmul_rn(m, weights[woff + r * side + c]);
     }
-  }
-  __syncwarp();
-  // lane q reduces bin q (and bin q + 32): lanes 0, 1, 2, ... in order
-  float f0 = -1.0f, f1 = -1.0f;
-  {
-    double a = 0.0;
-    for (int l = 0; l < 32; ++l) a += hist[warp][lane][l];
-    f0 = (float)a;
-    if (lane + 32 < kOriBins) {
-      double a1 = 0.0;
-      for (int l = 0; l < 32; ++l) a1 += hist[warp][lane + 32][l];
-      f1 = (float)a1;
+    __syncthreads();
+    // thread q < 36 sums bin q: warps 0, 1, .. and within a warp lanes 0, 1, .. in order
+    if (threadIdx.x < kOriBins) {
+      double a = 0.0;
+      for (int w = 0; w < kRecheckWarps; ++w) {
+        const double* row = rc_hist + ((size_t)w * (kOriBins + 1) + threadIdx.x) * 33;
+        for (int l = 0; l < 32; ++l) a += row[l];
+      }
+      s_f[threadIdx.x] = (float)a;
     }
-  }
-  float mx = fmaxf(f0, f1);
+    __syncthreads();
+    if (warp == 0) {
+      const float f0 = s_f[lane], f1 = lane + 32 < kOriBins ? s_f[lane + 32] : -1.0f;
+      float mx = fmaxf(f0, f1);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float cut = __fmul_rn(0.8f, mx);
-  const uint32_t lo = __ballot_sync(0xffffffffu, f0 >= cut);
-  const uint32_t hi = __ballot_sync(0xffffffffu, lane + 32 < kOriBins && f1 >= cut);
-  if (lane == 0) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
-  __syncwarp();
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float cut = __fmul_rn(0.8f, mx);
+      const uint32_t lo = __ballot_sync(0xffffffffu, f0 >= cut);
+      const uint32_t hi = __ballot_sync(0xffffffffu, lane + 32 < kOriBins && f1 >= cut);
+      if (lane == 0) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    }
+    __syncthreads();
   }
 }
 
@@ -910,8 +915,8 @@ extern "C" int fc_orientation_recheck(const double* levels, int n_planes, int pl
   if (n_keypoints == 0) return FC_OK;
   if (!keypoints || !bin_mask || n_keypoints < 0) return FC_ERR_BAD_ARG;
   if ((int64_t)height * width > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;
-  const int want = div_up(n_keypoints, kRecheckWarps);
-  orientation_recheck_kernel<<<want < 148 * 4 ? want : 148 * 4, kRecheckWarps * 32, 0, (cudaStream_t)stream>>>(
+  FC_CUDA_TRY(cudaFuncSetAttribute(orientation_recheck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecheckSmem));
+  orientation_recheck_kernel<<<n_keypoints < 148 * 2 ? n_keypoints : 148 * 2, kRecheckWarps * 32, kRecheckSmem, (cudaStream_t)stream>>>(
       levels, n_planes, plane, codes, height, width, keypoints, n_keypoints, weights, radius, table_ry, table_rx,
       (unsigned long long*)bin_mask, recheck_list, recheck_count);
   note_launch();

@@ -924,16 +924,17 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
 // :241) and level s is the next octave's base (APP/utils/SIFT_scale_space.py:209), so that neither the orientation /
 // descriptor bins nor the deeper octaves inherit float32 rounding.  For the default s = 2 both levels (radii 5, 6)
 // come out of one pass over a shared-memory tile with the pair sums v[-k] + v[+k] shared between them:
-// tile = 116 x 32 outputs, 128 x 44 inputs, 2 x 19 + 2 x 24 float64 operations per pixel on the FP64 pipe.
+// tile = 116 x 16 outputs, 128 x 28 inputs (61 KB of shared memory: three CTAs per SM -- with 32-row tiles and two
+// CTAs the FP64 pipe was 31 % busy, the kernel waited on its own loads), 19 + 24 float64 operations per pixel.
 struct MidTaps {
   double t[2][8];  // t[l][k] = tap at distance k (centre first), zero beyond the radius
 };
-static constexpr int kMTX = 116, kMTY = 32, kMP = 128, kMR = 6;
-static constexpr int kMIH = kMTY + 2 * kMR;  // 44 input rows
+static constexpr int kMTX = 116, kMTY = 16, kMP = 128, kMR = 6;
+static constexpr int kMIH = kMTY + 2 * kMR;  // 28 input rows
 static constexpr size_t kMidSmem = sizeof(double) * (size_t)(kMIH * kMP + 2 * kMTY * kMP);
 
 template <int RA, int RB>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid_constant__ MidTaps taps,
                      double* __restrict__ out, int n_planes, int plane0) {
   static_assert(RA <= kMR && RB <= kMR, "radius class");
@@ -962,7 +963,7 @@ gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  // vertical pass: (8-row group, column) items, 4 x 128 = two per thread
+  // vertical pass: (8-row group, column) items, 2 x 128 = one per thread
 #pragma unroll 1
   for (int item = threadIdx.x; item < (kMTY / 8) * kMP; item += 256) {
     const int g = item >> 7, c = item & 127;
@@ -1237,6 +1238,34 @@ __device__ __forceinline__ void warp_blur3x3(const At& at, const double* __restr
 
 static constexpr int kRepairWarps = 4;
 
+static constexpr size_t kRepairPatchSmem = sizeof(double) * kRepairWarps * 2 * kPatchSide * kPatchSide;
+
+// largest radius among the levels of entry k that have to be blurred on demand (0: every level is stored)
+__device__ __forceinline__ int repair_radius(const TapTable<double>& tab, int k, int mid_first, int mid_count,
+                                             int first_is_identity) {
+  int rm = 0;
+  for (int q = 0; q < 4; ++q) {
+    const int l = k - 1 + q;
+    const bool stored = (l >= mid_first && l < mid_first + mid_count) || (l == 0 && first_is_identity);
+    if (!stored) rm = max(rm, tab.radius[l]);
+  }
+  return rm;
+}
+
+// copy the (2 rm + 3)^2 support of an entry into the warp's patch buffer ('symm' reflected), asynchronously
+__device__ __forceinline__ void repair_stage_patch(const double* __restrict__ img, int H, int W, int y, int x, int rm,
+                                                   double* __restrict__ patch, int lane) {
+  if (rm > 0 && rm <= kPatchR) {
+    const int side = 2 * rm + 3;
+    for (int i = lane; i < side * side; i += 32) {
+      const int r = i / side, c = i - r * side;
+      cp_async_elem<double>(patch + r * kPatchSide + c,
+                            img + (size_t)reflect_symm(y - 1 - rm + r, H) * W + reflect_symm(x - 1 - rm + c, W));
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kRepairWarps * 32)
 extrema_repair_kernel(const double* __restrict__ base, int first_is_identity, const double* __restrict__ mid, int mid_first,
                       int mid_count, int B, int H, int W, int L, const __grid_constant__ TapTable<double> tab, int filter,
@@ -1244,37 +1273,44 @@ extrema_repair_kernel(const double* __restrict__ base, int first_is_identity, co
                       int amb_cap, uint32_t* __restrict__ extrema, int pitch) {
   __shared__ double sG[kRepairWarps][4][9];  // levels k-1 .. k+2, 3x3 each (row-major)
   __shared__ double sTmp[kRepairWarps][3 * kRepairCols];
-  __shared__ double sPatch[kRepairWarps][kPatchSide * kPatchSide];
+  extern __shared__ __align__(16) double sPatchAll[];  // [warp][2][kPatchSide^2]: the entry being evaluated and the next one
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = min(*amb_count, amb_cap);
   const size_t plane = (size_t)H * W;
-  for (int e = blockIdx.x * kRepairWarps + warp; e < n; e += gridDim.x * kRepairWarps) {
+  const int stride = gridDim.x * kRepairWarps;
+  double* bufs = sPatchAll + (size_t)warp * 2 * kPatchSide * kPatchSide;
+  int e = blockIdx.x * kRepairWarps + warp;
+  int cur = 0;
+  if (e < n) {
+    const int4 ent = amb[e];
+    repair_stage_patch(base + (size_t)ent.x * plane, H, W, ent.z, ent.w,
+                       repair_radius(tab, ent.y, mid_first, mid_count, first_is_identity), bufs, lane);
+  }
+  for (; e < n; e += stride) {
     const int4 ent = amb[e];
     const int b = ent.x, k = ent.y, y = ent.z, x = ent.w;
     const double* img = base + (size_t)b * plane;
-    // largest radius among the levels that have to be blurred on demand: if its support fits, copy it to shared
-    // memory once (every load independent: one memory latency instead of one per tap)
-    int rm = 0;
-    for (int q = 0; q < 4; ++q) {
-      const int l = k - 1 + q;
-      const bool stored = (l >= mid_first && l < mid_first + mid_count) || (l == 0 && first_is_identity);
-      if (!stored) rm = max(rm, tab.radius[l]);
-    }
+    const int rm = repair_radius(tab, k, mid_first, mid_count, first_is_identity);
     const bool patched = rm > 0 && rm <= kPatchR;
-    if (patched) {
-      const int side = 2 * rm + 3;
-      for (int i = lane; i < side * side; i += 32) {
-        const int r = i / side, c = i - r * side;
-        sPatch[warp][r * kPatchSide + c] = img[(size_t)reflect_symm(y - 1 - rm + r, H) * W + reflect_symm(x - 1 - rm + c, W)];
-      }
-      __syncwarp();
+    // the support of the NEXT entry is requested before this one is evaluated: its memory latency hides behind the
+    // ~800 warp instructions of the three on-demand blurs
+    if (e + stride < n) {
+      const int4 nx = amb[e + stride];
+      repair_stage_patch(base + (size_t)nx.x * plane, H, W, nx.z, nx.w,
+                         repair_radius(tab, nx.y, mid_first, mid_count, first_is_identity),
+                         bufs + (cur ^ 1) * kPatchSide * kPatchSide, lane);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    const double* patch = sPatch[warp] + (rm + 1) * kPatchSide + (rm + 1);  // element (y, x)
+    __syncwarp();
+    const double* patch = bufs + cur * kPatchSide * kPatchSide + (rm + 1) * kPatchSide + (rm + 1);  // element (y, x)
+    cur ^= 1;
     for (int q = 0; q < 4; ++q) {
       const int l = k - 1 + q;
       const double* src = nullptr;
       if (l >= mid_first && l < mid_first + mid_count) src = mid + ((size_t)b * mid_count + (l - mid_first)) * plane;
-      else if (l == 0 && first_is_identity) src = base + (size_t)b * plane;
+      else if (l == 0 && first_is_identity) src = img;
       if (src) {
         // centres satisfy 1 <= y <= H-3, 1 <= x <= W-3: the 3x3 block is inside the image
         if (lane < 9) sG[warp][q][lane] = src[(size_t)(y - 1 + lane / 3) * W + (x - 1 + lane % 3)];
@@ -1461,8 +1497,9 @@ extern "C" int fc_extrema_repair(const double* base, int first_is_identity, cons
   }
   for (int l = n_levels; l < kMaxLevels; ++l) tab.radius[l] = tab.offset[l] = 0;
   const int want = div_up(amb_cap, kRepairWarps);
-  const int blocks = want < 148 * 8 ? want : 148 * 8;
-  extrema_repair_kernel<<<blocks, kRepairWarps * 32, 0, (cudaStream_t)stream>>>(
+  const int blocks = want < 148 * 3 ? want : 148 * 3;  // 3 CTAs of 60 KB per SM; the warps stride over the list
+  FC_CUDA_TRY(cudaFuncSetAttribute(extrema_repair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRepairPatchSmem));
+  extrema_repair_kernel<<<blocks, kRepairWarps * 32, kRepairPatchSmem, (cudaStream_t)stream>>>(
       base, first_is_identity, mid, mid_first, mid_count, batch, height, width, n_levels, tab, filter, contrast_th, ratio_th,
       reinterpret_cast<const int4*>(amb), amb_count, amb_cap, extrema, div_up(width, 32));
   note_launch();

@@ -6,6 +6,7 @@ tables.  Drawing (cv2.drawMatches, :351-364) is not part of the hot path: ``matc
 """
 from __future__ import annotations
 
+import ctypes
 from math import cos, sin
 
 import numpy as np
@@ -17,18 +18,77 @@ from . import SIFT_scale_space as _ss
 from .SIFT_scale_space import gaussian_filter_kernel, generate_octaves_pyramid  # noqa: F401  (KD:8 star-imports them)
 
 
+def _gaussian_taps(sigma, truncate=4.0):
+    """scipy.ndimage's Gaussian weights: radius int(truncate * sigma + 0.5), exp(-x^2 / 2 sigma^2) normalised to sum 1."""
+    r = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-r, r + 1)
+    w = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return w / w.sum(), r
+
+
+def resize_device(img: torch.Tensor, newshape, anti_aliasing=True) -> torch.Tensor:
+    """skimage.transform.resize(img, newshape, anti_aliasing=...) for a float64 [H,W] or [H,W,C] device tensor, as the
+    scipy.ndimage calls scikit-image 0.24 makes: gaussian_filter(sigma = max(0, (in/out - 1)/2) per axis, 'mirror')
+    then zoom(order=1, mode='mirror', grid_mode=True)."""
+    t = img if img.dim() == 3 else img.unsqueeze(-1)
+    t = t.contiguous()
+    h, w, c = t.shape
+    h2, w2 = int(newshape[0]), int(newshape[1])
+    if anti_aliasing:
+        for axis, (n_in, n_out) in enumerate(((h, h2), (w, w2))):
+            sigma = max(0.0, (n_in / n_out - 1.0) / 2.0)
+            if sigma > 1e-15:  # gaussian_filter skips axes with a vanishing sigma
+                taps, r = _gaussian_taps(sigma)
+                d_taps = to_device(taps)
+                out = torch.empty_like(t)
+                _lib.call("fc_blur_axis_f64", ptr(t), 1, h, w, c, axis, ptr(d_taps), r, ptr(out), stream_ptr())
+                t = out
+    out = torch.empty((h2, w2, c), dtype=torch.float64, device=t.device)
+    _lib.call("fc_zoom_linear_f64", ptr(t), 1, h, w, c, h2, w2, ptr(out), stream_ptr())
+    return out if img.dim() == 3 else out[..., 0]
+
+
+def _as_float_image(img) -> torch.Tensor:
+    """skimage.util.img_as_float (what resize applies first): uint8 -> value / 255, floats unchanged."""
+    a = np.asarray(img) if not isinstance(img, torch.Tensor) else img
+    if a.dtype in (np.uint8, torch.uint8):
+        t8 = to_device(a, torch.uint8)
+        out = torch.empty(t8.shape, dtype=torch.float64, device=t8.device)
+        _lib.call("fc_u8_to_unit_f64", ptr(t8), ctypes.c_int64(t8.numel()), ptr(out), stream_ptr())
+        return out
+    return to_device(a, torch.float64)
+
+
 def sift_resize(img, ratio=None):
-    """:11-33 needs skimage.transform.resize (anti-aliased), which is the step BEFORE the hot path and
-    cannot be pinned in this image (no scikit-image): SURVEY 8(f) item 1."""
-    raise NotImplementedError("sift_resize (skimage.transform.resize) is outside the B200 hot path; resize on the host")
+    """:11-33 -- resize to ~1 MP (or by `ratio`) with skimage.transform.resize(anti_aliasing=True); returns
+    (resized image, ratio).  The resize runs on the device as the scipy.ndimage calls scikit-image makes (the library
+    itself is not in this image: pinned against scipy)."""
+    shape = np.shape(img) if not isinstance(img, torch.Tensor) else tuple(img.shape)
+    ratio = ratio if ratio is not None else np.sqrt((1024 * 1024) / np.prod(shape[:2]))
+    newshape = list(map(lambda d: int(round(d * ratio)), shape[:2]))
+    out = resize_device(_as_float_image(img), newshape, anti_aliasing=True)
+    return out.cpu().numpy(), ratio
 
 
 def convert_to_grayscale(image):
     """:36-39 -- float weighted sum, no cast (three multiply-adds per pixel, done where the image lives)."""
+    if isinstance(image, torch.Tensor):
+        return grayscale_device(image)
     image = np.asarray(image)
     if image.ndim == 3:
         return np.dot(image[..., :3], [0.2989, 0.5870, 0.1140])
     return image
+
+
+def grayscale_device(image: torch.Tensor) -> torch.Tensor:
+    """convert_to_grayscale for a device tensor [H,W] / [H,W,C>=3] (float64 in, float64 out)."""
+    if image.dim() != 3:
+        return image
+    t = image.to(torch.float64).contiguous()
+    h, w, c = t.shape
+    out = torch.empty((h, w), dtype=torch.float64, device=t.device)
+    _lib.call("fc_rgb_to_gray_f64", ptr(t), 1, h, w, c, ptr(out), stream_ptr())
+    return out
 
 
 def represent_keypoints(keypoints, DoG):
@@ -147,24 +207,51 @@ def extract_sift_descriptors(img_gaussians, keypoints, base_sigma, num_bins=8, s
     return [tuple(k) for k in keypoints], descriptors
 
 
+def extract_device(image, n_octaves, s_value, sigma_base, constract_th, r_ratio, out_dtype=torch.float32) -> "sift.SiftResult":
+    """computeKeypointsAndDescriptors with everything left on the device (records + descriptors of one image)."""
+    gray = convert_to_grayscale(image)
+    p = sift.SiftParams(n_octaves, s_value, sigma_base, constract_th, r_ratio, _ss.VARIANT, _ss.DTYPE)
+    base = sift.upsample2(gray if isinstance(gray, torch.Tensor) else np.asarray(gray, dtype=np.float64), p)
+    return sift.detect_and_describe(base, p, out_dtype=out_dtype)
+
+
 def computeKeypointsAndDescriptors(image, n_octaves, s_value, sigma_base, constract_th, r_ratio):
     """:292-311 -- gray, x2 up-sample, pyramid, orientations, descriptors; one device-resident pass."""
-    gray = np.asarray(convert_to_grayscale(image), dtype=np.float64)
-    p = sift.SiftParams(n_octaves, s_value, sigma_base, constract_th, r_ratio, _ss.VARIANT, _ss.DTYPE)
-    base = sift.upsample2(gray, p)
-    res = sift.detect_and_describe(base, p, out_dtype=torch.float64)
+    res = extract_device(image, n_octaves, s_value, sigma_base, constract_th, r_ratio, out_dtype=torch.float64)
     pts, desc = res.assemble(1)[0]
     points = [(int(a), int(b), int(c), int(d), float(e)) for a, b, c, d, e in pts.tolist()]
     return points, [row for row in desc]
 
 
-def kp_list_2_opencv_kp_list(kp_list):
-    """:314-327 without the cv2 dependency: (x, y, size, angle) tuples in cv2.KeyPoint's argument order."""
+def kp_list_2_xy(kp_list):
+    """The constructor arguments of :314-327 as plain tuples (x, y, size, angle)."""
     return [(kp[1] * (2 ** (kp[2] - 1)), kp[0] * (2 ** (kp[2] - 1)), kp[3], kp[4]) for kp in kp_list]
 
 
-def match(img_a, pts_a, desc_a, img_b, pts_b, desc_b, tuning_distance=0.3):
-    """:330-349 -- knnMatch(k=2) + ratio test.  Returns the `good` list as (queryIdx, trainIdx, distance)
-    tuples; the reference then draws them (cv2.drawMatches, :351-364), which is left to the caller."""
+def kp_list_2_opencv_kp_list(kp_list):
+    """:314-327 -- cv2.KeyPoint(x = j * 2^(octave-1), y = i * 2^(octave-1), size = scale, angle) per keypoint.
+    (Host bookkeeping like in the reference; cv2 is only needed by this export and by the match canvas.)"""
+    import cv2
+
+    return [cv2.KeyPoint(x=float(x), y=float(y), size=float(s), angle=float(a)) for x, y, s, a in kp_list_2_xy(kp_list)]
+
+
+def match_good(desc_a, desc_b, tuning_distance=0.3):
+    """:333-349 -- the `good` list of match(): knnMatch(k=2) + ratio test as (queryIdx, trainIdx, distance) tuples.
+    desc_a / desc_b: lists / arrays like the reference's, or device tensors (then nothing crosses PCIe but the list)."""
     pairs, dist = matching.match_indices(desc_a, desc_b, tuning_distance)
     return [(int(q), int(t), float(d)) for (q, t), d in zip(pairs.tolist(), dist.tolist())]
+
+
+def match(img_a, pts_a, desc_a, img_b, pts_b, desc_b, tuning_distance=0.3):
+    """:330-366 -- knnMatch(k=2) + ratio test on the device, then the reference's canvas: both images side by side with
+    the good matches drawn by cv2.drawMatches (host; drawing is not part of the hot path).  Returns img_match."""
+    import cv2
+
+    good = match_good(desc_a, desc_b, tuning_distance)
+    img_a, img_b = tuple(map(lambda i: np.uint8(np.asarray(i) * 255), [img_a, img_b]))
+    kp_a, kp_b = kp_list_2_opencv_kp_list(pts_a), kp_list_2_opencv_kp_list(pts_b)
+    dm = [cv2.DMatch(_queryIdx=q, _trainIdx=t, _distance=d) for q, t, d in good]
+    img_match = np.empty((max(img_a.shape[0], img_b.shape[0]), img_a.shape[1] + img_b.shape[1], 3), dtype=np.uint8)
+    cv2.drawMatches(img_a, kp_a, img_b, kp_b, dm, outImg=img_match, flags=cv2.DrawMatchesFlags_NOT_DRAW_SINGLE_POINTS)
+    return img_match

@@ -327,6 +327,31 @@ FC_API int fc_rotated_window(const double* image, int height, int width, double 
                       double cos_theta, double sin_theta, int out_width, int out_height, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * In front of the hot path: channel handling at load time and sift_resize
+ * ------------------------------------------------------------------------------------------- */
+
+/* convert_BGR_to_RGB (APP/utils/helper_functions.py:12-14), applied to the cv2.imread result in load_image
+ * (APP/FeatureCraft_Backend.py:105-106): [batch][h][w][3] uint8, channel order reversed (out of place). */
+FC_API int fc_bgr_to_rgb_u8(const uint8_t* bgr, int batch, int height, int width, uint8_t* rgb, void* stream);
+
+/* convert_to_grayscale (APP/utils/keypoint_descriptor.py:36-39): np.dot(image[..., :3], [0.2989, 0.5870, 0.1140]) on
+ * float64 pixels with `channels` >= 3 interleaved channels; no cast. */
+FC_API int fc_rgb_to_gray_f64(const double* rgb, int batch, int height, int width, int channels, double* gray, void* stream);
+
+/* skimage.util.img_as_float of uint8 data (value / 255), the first thing skimage.transform.resize does */
+FC_API int fc_u8_to_unit_f64(const uint8_t* src, int64_t n, double* dst, void* stream);
+
+/* The two halves of sift_resize (APP/utils/keypoint_descriptor.py:11-33 = skimage.transform.resize(img, newshape,
+ * anti_aliasing=True)) as the scipy.ndimage calls scikit-image 0.24 makes, on [batch][h][w][channels] float64:
+ * fc_blur_axis_f64 = gaussian_filter's 1-D correlation with `taps` (2 radius + 1 device doubles) along axis 0 (rows) or
+ * 1 (columns), 'mirror' border; fc_zoom_linear_f64 = zoom(order=1, mode='mirror', grid_mode=True) to out_height x
+ * out_width. */
+FC_API int fc_blur_axis_f64(const double* in, int batch, int height, int width, int channels, int axis, const double* taps,
+                     int radius, double* out, void* stream);
+FC_API int fc_zoom_linear_f64(const double* in, int batch, int height, int width, int channels, int out_height, int out_width,
+                       double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Matching (APP/utils/keypoint_descriptor.py:330-349)
  * ------------------------------------------------------------------------------------------- */
 

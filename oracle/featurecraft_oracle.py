@@ -15,8 +15,9 @@ this image and are restated from their published algorithm instead:
 
 * ``cv2.warpAffine(INTER_NEAREST|WARP_INVERSE_MAP)`` (opencv-python==4.10.0.84): AB_BITS=10
   fixed-point coordinate rounding, see ``nn_rotated_window``.
-* ``skimage.transform.rescale/resize`` (scikit-image==0.24.0): NOT restated; the parity boundary
-  starts at the up-sampled base image ("parity unpinned" for that one call).
+* ``skimage.transform.rescale/resize`` (scikit-image==0.24.0): restated as the scipy.ndimage calls
+  scikit-image makes (``sift_resize``, ``rescale2``) but PARITY UNPINNED -- no scikit-image here to run
+  them against; the pinned parity boundary starts at the up-sampled base image.
 
 Third-party arithmetic that IS available here and that the oracle calls exactly as the reference
 does: ``scipy.signal.convolve2d`` (reference pins scipy==1.14.0), numpy ufuncs.  ``np.gradient`` and
@@ -564,6 +565,53 @@ def compute_keypoints_and_descriptors_from_base(base_image, n_octaves, s_value, 
     masks = represent_keypoints(kps, dog)
     oriented = dog_keypoints_orientations(pyramid, masks, sigma_base, 36, s_value)
     return extract_sift_descriptors(pyramid, oriented, sigma_base, 8, s_value)
+
+
+def sift_resize(img, ratio=None):
+    """APP/utils/keypoint_descriptor.py:11-33 with skimage.transform.resize(img, newshape, anti_aliasing=True)
+    (scikit-image==0.24.0, absent here) restated as the scipy.ndimage calls it makes: img_as_float (uint8 -> /255),
+    gaussian_filter(sigma = max(0, (in/out - 1)/2) per spatial axis, mode='mirror'), zoom(order=1, mode='mirror',
+    grid_mode=True).  UNPINNED against skimage itself (see the module docstring)."""
+    from scipy import ndimage
+
+    img = np.asarray(img)
+    ratio = ratio if ratio is not None else np.sqrt((1024 * 1024) / np.prod(img.shape[:2]))
+    newshape = list(map(lambda d: int(round(d * ratio)), img.shape[:2]))
+    image = img.astype(np.float64) / 255.0 if img.dtype == np.uint8 else img.astype(np.float64)
+    factors = [image.shape[a] / newshape[a] for a in range(2)]
+    sig = [max(0.0, (f - 1.0) / 2.0) for f in factors] + [0.0] * (image.ndim - 2)
+    if any(s > 0 for s in sig):
+        image = ndimage.gaussian_filter(image, sig, mode="mirror")
+    zoom = [newshape[a] / image.shape[a] for a in range(2)] + [1.0] * (image.ndim - 2)
+    return ndimage.zoom(image, zoom, order=1, mode="mirror", grid_mode=True), ratio
+
+
+def rescale2(gray):
+    """skimage.transform.rescale(gray, 2, anti_aliasing=False) (APP/utils/keypoint_descriptor.py:296) as the
+    scipy.ndimage call it makes; UNPINNED against skimage itself."""
+    from scipy import ndimage
+
+    return ndimage.zoom(np.asarray(gray, dtype=np.float64), 2, order=1, mode="mirror", grid_mode=True)
+
+
+def apply_sift_good(main_image, template, n_octaves, s_value, sigma_base, contrast_th, r_ratio, tuning_factor,
+                    blur_mode="direct"):
+    """apply_sift (APP/FeatureCraft_Backend.py:480-523 / SIFT.py:683-707) up to the `good` list that match() draws:
+    sift_resize both (ratio from the main image), gray, x2, keypoints + descriptors, knn + ratio test.
+    Returns (good (M, 2) int array, points_main, points_template)."""
+    main_image, ratio = sift_resize(main_image)
+    template, _ = sift_resize(template, ratio)
+    out = []
+    for img in (main_image, template):
+        base = rescale2(convert_to_grayscale(img))
+        out.append(compute_keypoints_and_descriptors_from_base(base, n_octaves, s_value, sigma_base, contrast_th, r_ratio,
+                                                               "app", blur_mode))
+    (pa, da), (pb, db) = out
+    da, db = np.array(da, dtype=np.float32).reshape(-1, 128), np.array(db, dtype=np.float32).reshape(-1, 128)
+    ok = ~np.isnan(da).any(1)  # a NaN query row makes BFMatcher undefined; defined here as "no match" (SURVEY A.8)
+    pairs, _ = match_indices(da[ok], db, tuning_factor)
+    pairs[:, 0] = np.nonzero(ok)[0][pairs[:, 0]]
+    return pairs, pa, pb
 
 
 def kp_list_2_xy(kp_list):

@@ -182,6 +182,16 @@ def sift():
         assert np.array_equal(w, O.nn_rotated_window(img, (j, i), th))
         wins.append(w)
     assert np.array_equal(kd.get_gaussian_mask(3.39, 16), O.get_gaussian_mask(3.39, 16))
+    # kp_list_2_opencv_kp_list (:314-327): the cv2.KeyPoint fields against the oracle's tuple twin
+    kl = [(3, 7, 0, 1, 45.0), (10, 2, 3, 2, 355.0), (0, 0, 1, 1, 5.0)]
+    for kp, (x, y, size, angle) in zip(kd.kp_list_2_opencv_kp_list(kl), O.kp_list_2_xy(kl)):
+        assert (kp.pt[0], kp.pt[1], kp.size, kp.angle) == (np.float32(x), np.float32(y), np.float32(size), np.float32(angle))
+    # sift_resize / rescale: the reference functions run through the scipy stub (ref_loader) -- this pins the ORACLE's
+    # restatement to that stub, not to scikit-image (absent): documented as unpinned
+    rgb = np.random.default_rng(4).random((50, 70, 3))
+    a, ra = kd.sift_resize(rgb)
+    b, rb = O.sift_resize(rgb)
+    assert ra == rb and np.array_equal(a, b)
     _save("sift_pieces", img=img, mag=ref[2], direction=ref[3], windows=np.stack(wins))
 
 

@@ -1,8 +1,9 @@
 """Loads the UNMODIFIED reference from /root/reference, in place, for pinning the oracle.
 
-TEST INFRASTRUCTURE ONLY.  This module is imported by ``oracle/make_golden.py`` and by the
-``tests/test_oracle_vs_reference.py`` cases that are skipped when /root/reference is absent
-(it does not exist on the GPU box).  Nothing here is shipped or timed.
+TEST INFRASTRUCTURE ONLY.  This module is imported by ``oracle/make_golden.py`` /
+``oracle/make_golden_large.py`` (authoring container) and by the one case of ``tests/test_cabi_cpu.py`` that uses
+the script's own ``localize_keypoint`` when /root/reference is mounted (it is absent on the GPU box).  Nothing here
+is shipped or timed.
 
 No reference source is copied into this repository: function definitions are read from the
 reference files at run time (``importlib`` for the modules that import cleanly, ``ast`` extraction

@@ -26,7 +26,7 @@ def test_template_matching_is_geometrically_consistent(mods):
     main = synthetic.sift_image(360, 480, seed=21)
     y0, x0, size = 96, 160, 128
     tmpl = np.ascontiguousarray(main[y0:y0 + size, x0:x0 + size])
-    good, (kp_a, des_a), (kp_b, des_b) = backend.apply_sift(main, tmpl, 4, 2, 1.6, 0.03, 10, 0.5)
+    good, kp_a, kp_b = backend.apply_sift_matches(main, tmpl, 4, 2, 1.6, 0.03, 10, 0.5, resize=False)
     assert len(good) > 200
     ok = 0
     for q, t, dist in good:

@@ -100,7 +100,9 @@ def test_small_pieces(KD):
     sl = [-3, 9, 45, 60]
     assert np.array_equal(KD.padded_slice(g["img"], sl), O.padded_slice(g["img"], sl))
     kl = [(3, 4, 0, 1, 15.0), (10, 2, 3, 2, 355.0)]
-    assert KD.kp_list_2_opencv_kp_list(kl) == O.kp_list_2_xy(kl)
+    assert KD.kp_list_2_xy(kl) == O.kp_list_2_xy(kl)
+    assert [(k.pt[0], k.pt[1], k.size, k.angle) for k in KD.kp_list_2_opencv_kp_list(kl)] == \
+        [tuple(np.float32(v) for v in t) for t in O.kp_list_2_xy(kl)]
     rgb = np.random.default_rng(0).random((9, 11, 3))
     assert np.array_equal(KD.convert_to_grayscale(rgb), O.convert_to_grayscale(rgb))
 
@@ -136,7 +138,7 @@ def test_matching_golden(KD, engine):
         assert np.array_equal(pairs, g["good_%g" % t])
     with pytest.raises(ValueError):
         matching.knn2(g["desc_a"], g["desc_b"][:1], 0.3, engine)
-    m = KD.match(None, None, g["desc_a"], None, None, g["desc_b"], 0.8)
+    m = KD.match_good(g["desc_a"], g["desc_b"], 0.8)
     assert [x[:2] for x in m] == [tuple(r) for r in g["good_0.8"].tolist()]
 
 
