@@ -1,4 +1,4 @@
-"""SIFT and matching workloads for bench.py (kept in a separate module so bench.py stays readable)."""
+"""SIFT, matching and pipeline workloads for bench.py (kept in a separate module so bench.py stays readable)."""
 from __future__ import annotations
 
 import numpy as np
@@ -13,23 +13,20 @@ class SiftWorkload:
     name = "sift"
     metric = "sift_megapixels_per_sec"
     unit = "MP/s"
-    dtype = "mixed"
     H = W = 1024
-    cpu_sample_items = 16
-    cpu_sample_note = "(256x256 crops of the same generator, oracle with separable blurs: the reference's direct 2-D convolution is ~5x slower and a 1024x1024 image takes ~5 min per core)"
+    CROP = 192  # CPU arms: crops of the same images (a whole 1024x1024 image costs the reference ~5 min per core)
 
     def __init__(self, args):
         self.batch = args.batch or 16
         self.mode = getattr(args, "sift_dtype", None) or "mixed"
-        self.dtype = {"mixed": "f32 arithmetic + f64-certified decisions", "f32": "f32", "f64": "f64"}[self.mode]
+        self.dtype = {"mixed": "f32 arithmetic, f64-certified decisions", "f32": "f32", "f64": "f64"}[self.mode]
+        self.desc_per_image = None
 
     def describe(self, world):
         return {"workload": "config[1]: SIFT keypoints + descriptors, %d synthetic 1024x1024 float64 images per step per GPU "
-                            "(x2 up-sample -> 2048^2 base, 4 octaves, 5 Gaussian levels, app filter variant, %s scale space)"
-                            % (self.batch, self.mode),
+                            "(x2 up-sample -> 2048^2 base, 4 octaves, 5 Gaussian levels, sigma 1.6, app filter variant)" % self.batch,
                 "images_per_step_per_gpu": self.batch, "image": [self.H, self.W], "sharding": "images, no collective",
-                "descriptors_per_image": getattr(self, "desc_per_image", None),
-                "l2": "per-step working set (%.1f GB) exceeds the 126 MB L2; no flush needed" % (self.batch * 0.35)}
+                "l2": "per-step working set (%.1f GB) exceeds the 126 MB L2; no flush needed" % (self.batch * 0.5)}
 
     def units_per_step(self):
         return self.batch * self.H * self.W / 1e6
@@ -66,7 +63,8 @@ class SiftWorkload:
 
     def e2e_begin(self):
         """Pipelined end-to-end driver: pinned input -> H2D -> kernels -> D2H into pinned output, the D2H of batch
-        i overlapping the kernels of batch i+1 (sift.BatchExtractor, the public batch API)."""
+        i overlapping the kernels of batch i+1 (sift.BatchExtractor, the public batch API; compact export: 8-byte
+        keypoint records + float16 descriptors in certified mode)."""
         cap = int(self.desc_per_image * self.batch * 1.25) + 4096
         self.extractor = self.sift.BatchExtractor(self.params, self.batch, self.H, self.W, cap, depth=2)
         for s in range(2):
@@ -88,17 +86,21 @@ class SiftWorkload:
         self.io_bytes = self.extractor.bytes_per_batch(rec.shape[0])
         return self.io_bytes
 
-    def dominant_kernel(self):
+    def kernels(self):
         tot = self.timer.totals()
         n = max(self.recorded_steps, 1)
         ms = tot.get("pyramid_o0", 0.0) / n
         alg = 24.0 * self.batch * (2 * self.H) * (2 * self.W)  # 4 B base read + 5 x 4 B levels written per octave pixel
         if self.mode == "f64":
             alg *= 2
-        return "gauss_octave_packed_kernel (octave 0)" if self.mode != "f64" else "gauss_octave_kernel (octave 0)", alg, ms, "hbm"
+        name = "gauss_octave_packed_kernel (octave 0)" if self.mode != "f64" else "gauss_octave_kernel<double> (octave 0)"
+        return [(name, alg, ms, "hbm")]
 
     def traffic(self, tr):
         return tr["gauss_octave_packed_kernel"]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W) * (2 if self.mode == "f64" else 1)
+
+    def stats(self):
+        return {"descriptors_per_image": self.desc_per_image, "scale_space": self.mode}
 
     def extra(self):
         full = self.sift.StageTimer()
@@ -113,13 +115,24 @@ class SiftWorkload:
         return {k: round(v / n, 4) for k, v in sorted(full.totals().items())}
 
     cpu_task = staticmethod(_cpu_sift_task)
+    cpu_sample_items = None  # one crop per core
 
-    def cpu_items(self, n):
-        # the oracle needs ~5 min per 1024^2 image per core: the CPU arm uses 256^2 crops of the same generator
-        return [(256, 256, s) for s in range(n)]
+    def cpu_items(self, n, step=0):
+        # crop k = tile k % 25 of image seed (k // 25) % 4: non-overlapping 192x192 crops of the images the GPU arm uses
+        out = []
+        for i in range(n):
+            k = step * n + i
+            tile = k % 25
+            out.append((self.H, self.W, (k // 25) % 4, (tile // 5) * self.CROP, (tile % 5) * self.CROP, self.CROP, self.CROP))
+        return out
 
     def cpu_units(self, n):
-        return n * 256 * 256 / 1e6
+        return n * self.CROP * self.CROP / 1e6
+
+    def cpu_sample(self, n):
+        return ("%d crops of %dx%d pixels of the config[1] images per step, one per process, through the oracle with the "
+                "reference's direct 2-D convolutions (a whole 1024x1024 image takes the reference ~5 min on one core)"
+                % (n, self.CROP, self.CROP))
 
 
 def _cpu_match_task(args):
@@ -155,7 +168,6 @@ class MatchWorkload:
     unit = "Gpairs/s"
     dtype = "fp16 tcgen05 candidates, fp32 exact re-rank"
     cpu_sample_items = 16
-    cpu_sample_note = "(2048 x 8192 descriptor sets per task: float32 brute force of the oracle)"
 
     def __init__(self, args):
         self.nq = self.nt = (args.batch or 128) * 1024
@@ -182,15 +194,18 @@ class MatchWorkload:
         self.ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(64)]
         self.ev_i = 0
 
+    def _call(self):
+        return self.matching.knn2(self.a, self.b, 0.3, "tensor")
+
     def step_device(self, record=False):
         if record and self.ev_i < len(self.ev):
             e0, e1 = self.ev[self.ev_i]
             self.ev_i += 1
             e0.record()
-            out = self.matching.knn2(self.a, self.b, 0.3, "tensor")
+            out = self._call()
             e1.record()
             return out
-        return self.matching.knn2(self.a, self.b, 0.3, "tensor")
+        return self._call()
 
     def e2e_begin(self):
         """Pipelined end-to-end driver (matching.BatchMatcher, the public batch API): the H2D of pair i+1 runs while
@@ -216,10 +231,11 @@ class MatchWorkload:
         self.n_good = len(pairs)
         return self.matcher.bytes_per_pair()
 
-    def dominant_kernel(self):
+    def kernels(self):
         ms = [a.elapsed_time(b) for a, b in self.ev[: self.ev_i]]
         # whole knn2 call (prep + GEMM + re-rank + re-check); algorithmic FLOPs = 2 * nq * nt * 128
-        return "match_tc_kernel (+prep, re-rank, re-check)", 2.0 * self.nq * self.nt * 128, float(np.mean(ms)) if ms else None, "tensor"
+        return [("match_tc2_kernel (+prep, re-rank, re-check: the whole fc_match_knn2 call)", 2.0 * self.nq * self.nt * 128,
+                 float(np.mean(ms)) if ms else None, "tensor")]
 
     def traffic(self, tr):
         t = tr["match_tc_kernel"]
@@ -230,11 +246,14 @@ class MatchWorkload:
 
     cpu_task = staticmethod(_cpu_match_task)
 
-    def cpu_items(self, n):
-        return [(2048, 8192, s) for s in range(n)]
+    def cpu_items(self, n, step=0):
+        return [(2048, 8192, step * n + s) for s in range(n)]
 
     def cpu_units(self, n):
         return n * 2048 * 8192 / 1e9
+
+    def cpu_sample(self, n):
+        return "%d tasks of 2048 x 8192 descriptors: float32 brute force + ratio test of the oracle (cv2.BFMatcher's arithmetic)" % n
 
 
 class AllPairsWorkload(MatchWorkload):
@@ -264,19 +283,27 @@ class AllPairsWorkload(MatchWorkload):
 
         self.sharding = sharding
         self.world = sharding.world_info()[1]
+        # before anything is timed: the ring's answer for the LAST block to arrive (it crossed world-1 hops) must be the
+        # exact engine's answer for that pair of blocks
+        res = self._run()
+        train_rank, (idx, dist, good) = res[-1]
+        a_t, _ = match_sets(self.nq, self.nt, train_rank)
+        ei, ed, eg = self.matching.knn2(self.a, torch.from_numpy(a_t).cuda(), 0.3, "exact")
+        g = eg.nonzero().flatten()
+        assert torch.equal(good, eg) and torch.equal(idx[g, 0], ei[g, 0]), "ring all-pairs result differs from the exact engine"
+        self.verified = {"train_rank": int(train_rank), "good": int(g.numel()), "equal_to_exact_engine": True}
+
+    def stats(self):
+        return {"ring_check": self.verified}
 
     def _run(self):
         return self.sharding.all_pairs_match(self.a, lambda q, t: self.matching.knn2(q, t, 0.3, "tensor"), max_rows=self.nq)
 
-    def step_device(self, record=False):
-        if record and self.ev_i < len(self.ev):
-            e0, e1 = self.ev[self.ev_i]
-            self.ev_i += 1
-            e0.record()
-            out = self._run()
-            e1.record()
-            return out
+    def _call(self):
         return self._run()
+
+    def e2e_begin(self):
+        self.pending = None
 
     def step_e2e(self):
         a = self.host_a.cuda(non_blocking=True)
@@ -290,7 +317,106 @@ class AllPairsWorkload(MatchWorkload):
             d2h += sum(t.numel() * t.element_size() for t in out)
         return self.nq * 512, d2h
 
-    def dominant_kernel(self):
+    def e2e_end(self):
+        return self.nq * 512, 0
+
+    def kernels(self):
         ms = [a.elapsed_time(b) for a, b in self.ev[: self.ev_i]]
-        return ("match_tc_kernel (+prep, re-rank, ring exchange)", 2.0 * self.nq * self.nt * self.world * 128,
-                float(np.mean(ms)) if ms else None, "tensor")
+        return [("match_tc2_kernel (+prep, re-rank, ring exchange)", 2.0 * self.nq * self.nt * self.world * 128,
+                 float(np.mean(ms)) if ms else None, "tensor")]
+
+
+class Pipeline4kWorkload:
+    """BASELINE configs[4] as a pipeline, one step of it per GPU: SIFT keypoints + descriptors of one 3840x2160 image
+    (certified mode, descriptors stay in HBM) and 2-NN ratio-test matching of that image against the images of ALL ranks
+    -- the descriptor blocks visit around the NCCL ring (sharding.all_pairs_match).  The images are overlapping crops of
+    one synthetic scene, so true matches exist between every pair.  value = input megapixels per second through the
+    whole pipeline; the matching grows with the number of ranks (every image meets every image), which `stats` breaks out."""
+
+    name = "pipeline4k"
+    metric = "sift4k_extract_and_allpairs_match_megapixels_per_sec"
+    unit = "MP/s"
+    dtype = "f32 arithmetic, f64-certified decisions; fp16 tcgen05 matching"
+    H, W = 2160, 3840
+
+    def __init__(self, args):
+        self.world = 1
+        self.n_desc = None
+        self.n_good = None
+
+    def describe(self, world):
+        return {"workload": "config[4] pipeline: per step and GPU one synthetic 3840x2160 image -> SIFT (x2 up-sample, 4 octaves) "
+                            "-> its descriptors matched against the images of all %d GPUs (ratio 0.3), ring of NCCL send/recv" % world,
+                "image": [self.H, self.W], "sharding": "one image per rank and step; descriptor blocks travel the ring",
+                "l2": "one image's scale space is 2.7 GB: far beyond the 126 MB L2"}
+
+    def units_per_step(self):
+        return self.H * self.W / 1e6
+
+    def setup(self, rank, torch):
+        from exvision_featurecraft_b200 import matching, sharding, sift, synthetic
+
+        self.torch, self.sift, self.matching, self.sharding = torch, sift, matching, sharding
+        self.world = sharding.world_info()[1]
+        scene = synthetic.sift_image(self.H + 64 * 8, self.W + 64 * 8, seed=77, max_blobs=3000)
+        off = 64 * (rank % 8)
+        img = np.ascontiguousarray(scene[off:off + self.H, off:off + self.W])
+        self.host_in = torch.from_numpy(img[None]).pin_memory()
+        self.dev_in = self.host_in.cuda()
+        self.params = sift.SiftParams(dtype="mixed")
+        self.ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(16)]
+        self.ev_i = 0
+
+    def _run(self, dev_in, ev=None):
+        if ev:
+            ev[0].record()
+        res = self.sift.detect_and_describe(self.sift.upsample2(dev_in, self.params), self.params, out_dtype=self.torch.float32)
+        if ev:
+            ev[1].record()
+        cap = int(res.total * 1.2) + 4096  # ring buffers: the other ranks' images yield about as many descriptors
+        if self.world > 1:
+            t = self.torch.tensor([cap], dtype=self.torch.int64, device="cuda")
+            self.torch.distributed.all_reduce(t, op=self.torch.distributed.ReduceOp.MAX)
+            cap = int(t.item())
+        out = self.sharding.all_pairs_match(res.descriptors, lambda q, t: self.matching.knn2(q, t, 0.3, "tensor"), max_rows=cap)
+        if ev:
+            ev[2].record()
+        self.n_desc = res.total
+        return res, out
+
+    def step_device(self, record=False):
+        ev = None
+        if record and self.ev_i < len(self.ev):
+            ev = self.ev[self.ev_i]
+            self.ev_i += 1
+        return self._run(self.dev_in, ev)
+
+    def step_e2e(self):
+        dev = self.host_in.cuda(non_blocking=True)
+        res, out = self._run(dev)
+        d2h = 0
+        self.n_good = []
+        for _, (idx, dist, good) in out:
+            q = self.torch.nonzero(good).flatten()
+            host = (q.cpu(), idx[q, 0].cpu(), dist[q, 0].cpu())
+            self.n_good.append(int(q.numel()))
+            d2h += sum(t.numel() * t.element_size() for t in host)
+        return self.host_in.numel() * 8, d2h
+
+    def kernels(self):
+        n = self.ev_i
+        if not n:
+            return []
+        ms = float(np.mean([e[1].elapsed_time(e[2]) for e in self.ev[:n]]))
+        return [("match_tc2_kernel (+prep, re-rank, ring exchange): %d image pairs per GPU and step" % self.world,
+                 2.0 * float(self.n_desc) ** 2 * self.world * 128, ms, "tensor")]
+
+    def traffic(self, tr):
+        return None
+
+    def stats(self):
+        n = max(self.ev_i, 1)
+        return {"descriptors_per_image": self.n_desc, "good_matches_per_pair": self.n_good,
+                "extract_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in self.ev[:n]])) if self.ev_i else None,
+                "match_ms": float(np.mean([e[1].elapsed_time(e[2]) for e in self.ev[:n]])) if self.ev_i else None,
+                "image_pairs_per_step": self.world * self.world}

@@ -15,10 +15,23 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "featurecraft_b200
 FC_OK = 0
 FC_F32, FC_F64, FC_F16 = 0, 1, 2
 FC_FILTER_APP, FC_FILTER_SCRIPT = 0, 1
+FC_GRAD_CENTRAL, FC_GRAD_KX, FC_GRAD_SOBEL = 0, 1, 2
+FC_WINDOW_BOX, FC_WINDOW_GAUSS = 0, 1
+FC_RESP_HARRIS, FC_RESP_LAMBDA_MINUS = 0, 1
 
 
 class FeatureCraftError(RuntimeError):
     pass
+
+
+class CapacityError(FeatureCraftError):
+    """FC_ERR_CAPACITY: a caller-provided output buffer is too small; `required` is the count that would fit."""
+
+    status = -2
+
+    def __init__(self, what: str, required: int, capacity: int):
+        super().__init__("%s: output capacity too small (%d needed, %d available)" % (what, required, capacity))
+        self.required, self.capacity = int(required), int(capacity)
 
 
 _p = C.c_void_p
@@ -37,6 +50,8 @@ SIGNATURES = {
     "fc_harris_response": (_i, [_p, _i, _i, _i, _i, _d, _d, _p, _p, _p]),
     "fc_notebook_harris_response": (_i, [_p, _i, _i, _i, _i, _d, _p, _p]),
     "fc_lambda_minus_response": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "fc_corner_response_ex": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _d, _i, _d, _p, _p, _p]),
+    "fc_nms3x3_mask": (_i, [_p, _i, _i, _i, _d, _p, _p]),
     "fc_selftest_div25": (_i, [_p, _p]),
     "fc_selftest_divsqrt": (_i, [_p, _p]),
     "fc_threshold_mask_abs": (_i, [_p, _i, _i, _i, _d, _i, _p, _p]),
@@ -54,6 +69,7 @@ SIGNATURES = {
     "fc_gauss_octave_extrema": (_i, [_p, _i, _i, _i, _i, _i, _i, _d, _d, _p, _p]),
     "fc_dog_extrema": (_i, [_p, _i, _i, _i, _i, _i, _i, _d, _d, _p, _p]),
     "fc_upsample2": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "fc_refine_keypoints": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _d, _d, _p, _p, _p, _p, _p]),
     "fc_rotated_window": (_i, [_p, _i, _i, _d, _d, _d, _d, _i, _i, _p, _p]),
     "fc_downsample2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fc_convert_f64": (_i, [_p, _i64, _i, _p, _p]),

@@ -129,6 +129,60 @@ def lambda_minus(gray, threshold_percentage: float | None = 0.01, compact: bool 
     return res
 
 
+_GRADIENTS = {"central": _lib.FC_GRAD_CENTRAL, "kx": _lib.FC_GRAD_KX, "sobel": _lib.FC_GRAD_SOBEL}
+_WINDOWS = {"box": _lib.FC_WINDOW_BOX, "gaussian": _lib.FC_WINDOW_GAUSS}
+_RESPONSES = {"harris": _lib.FC_RESP_HARRIS, "lambda_minus": _lib.FC_RESP_LAMBDA_MINUS}
+
+
+def gaussian_window_taps(n: int, sigma: float):
+    """cv2.getGaussianKernel(n, sigma) for sigma > 0: exp(-(i - (n-1)/2)^2 / (2 sigma^2)), normalised to sum 1."""
+    import numpy as np
+
+    if not sigma > 0:
+        raise ValueError("the Gaussian window needs sigma > 0")
+    x = np.arange(n, dtype=np.float64) - (n - 1) * 0.5
+    w = np.exp(-(x * x) / (2.0 * sigma * sigma))
+    return w / w.sum()
+
+
+def corner_response(gray, gradient: str = "central", window: str = "box", window_size: int = 5, sigma: float | None = None,
+                    response: str = "harris", k: float = 0.04, threshold: float | None = None, nms: bool = False,
+                    compact: bool = True) -> CornerResult:
+    """The corner response with its OPT-IN components (BASELINE north_star; the reference uses none of them, so the
+    defaults are the app's Harris): gradient "central" (np.gradient) | "kx" (5x5 K_X) | "sobel" (cv2.Sobel ksize 3),
+    window "box" (zero padded ones window) | "gaussian" (cv2.GaussianBlur with `sigma`), response "harris" |
+    "lambda_minus", and with a threshold optionally 3x3 non-maximum suppression."""
+    import ctypes as C
+
+    g = _as_gray_batch(gray)
+    b, h, w = g.shape
+    if window_size % 2 == 0:
+        raise ValueError("window_size must be odd")
+    taps = None
+    if window == "gaussian":
+        t = gaussian_window_taps(window_size, sigma)
+        taps = (C.c_double * window_size)(*t.tolist())
+    resp = torch.empty((b, h, w), dtype=torch.float64, device=g.device)
+    mask = _new_mask(b, h, w, g.device) if threshold is not None else None
+    _lib.call("fc_corner_response_ex", ptr(g), b, h, w, _GRADIENTS[gradient], _WINDOWS[window], int(window_size), taps,
+              _RESPONSES[response], float(k), 1 if (nms and mask is not None) else 0,
+              float(threshold if threshold is not None else 0.0), ptr(resp), ptr(mask), stream_ptr())
+    res = CornerResult(resp, mask)
+    if mask is not None and compact:
+        res.coords, res.values, res.image_offsets = compact_mask(mask, w, resp)
+    return res
+
+
+def nms_threshold(response: torch.Tensor, threshold: float):
+    """Opt-in 3x3 non-maximum suppression of a resident response map (the reference only thresholds): corners where
+    R > threshold and R >= its neighbours -> (coords, values, image_offsets) like rethreshold()."""
+    r = response if response.dim() == 3 else response.unsqueeze(0)
+    b, h, w = r.shape
+    mask = _new_mask(b, h, w, r.device)
+    _lib.call("fc_nms3x3_mask", ptr(r), b, h, w, float(threshold), ptr(mask), stream_ptr())
+    return compact_mask(mask, w, r)
+
+
 def rethreshold(response: torch.Tensor, threshold: float, border: int = 0):
     """on_changing_threshold (APP/FeatureCraft_Backend.py:261-292): re-threshold a resident map with
     an ABSOLUTE value (the reference compares eigenvalues to slider/10000, not to a percentage)."""
@@ -202,7 +256,7 @@ class BatchCornerDetector:
         self.consumed[slot].record(compute)
         n1, n2 = int(hr.coords.shape[0]), int(lm.coords.shape[0])
         if max(n1, n2) > self.cap:
-            raise _lib.FeatureCraftError("batch produced %d corners, more than max_corners=%d" % (max(n1, n2), self.cap))
+            raise _lib.CapacityError("BatchCornerDetector.submit (corners of the batch)", max(n1, n2), self.cap)
         offs = torch.stack([hr.image_offsets, lm.image_offsets])
         ev_done = torch.cuda.Event()
         ev_done.record(compute)

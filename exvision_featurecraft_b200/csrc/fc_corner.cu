@@ -876,7 +876,9 @@ extern "C" int fc_harris_response(const uint8_t* gray, int batch, int height, in
 extern "C" int fc_notebook_harris_response(const uint8_t* gray, int batch, int height, int width, int window_size,
                                            double k, double* response, void* stream) {
   if (bad_image_args(gray, batch, height, width) || !response) return FC_ERR_BAD_ARG;
-  if (window_size < 1 || window_size > 31 || (window_size & 1) == 0) return FC_ERR_BAD_ARG;
+  // the notebook takes any size: offset = int(window_size / 2), window = 2 * offset + 1 (harris.ipynb:170-176); only the
+  // app's convolve2d_optimized path fails on even sizes
+  if (window_size < 1 || window_size > 31) return FC_ERR_BAD_ARG;
   return launch_tiled<GRAD_KX>(gray, batch, height, width, window_size / 2, RESP_HARRIS, k, response, nullptr,
                                (cudaStream_t)stream);
 }

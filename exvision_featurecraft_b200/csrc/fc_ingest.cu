@@ -45,7 +45,8 @@ __device__ __forceinline__ int mirror_index(int i, int n) {
 }
 
 // out[.., i, ..] = sum_k w[k] * in[.., mirror(i + k - r), ..] along `axis` of a [planes][H][W][C] array (C interleaved
-// channels); taps summed in ascending k like ndimage.correlate1d's inner loop
+// channels), evaluated like ndimage's correlate1d evaluates a symmetric filter (ni_filters.c): centre tap first, then
+// the pairs (in[i - d] + in[i + d]) * w[d] from the outermost distance inwards; explicit roundings, no contraction
 __global__ void __launch_bounds__(256)
 blur_axis_kernel(const double* __restrict__ in, int H, int W, int C, int axis, const double* __restrict__ taps, int radius,
                  double* __restrict__ out) {
@@ -56,12 +57,11 @@ blur_axis_kernel(const double* __restrict__ in, int H, int W, int C, int axis, c
   const int c = (int)(i % C);
   const int x = (int)((i / C) % W);
   const int y = (int)(i / ((int64_t)C * W));
-  double acc = 0.0;
-  if (axis == 0) {
-    for (int k = -radius; k <= radius; ++k) acc += taps[k + radius] * src[((size_t)mirror_index(y + k, H) * W + x) * C + c];
-  } else {
-    for (int k = -radius; k <= radius; ++k) acc += taps[k + radius] * src[((size_t)y * W + mirror_index(x + k, W)) * C + c];
-  }
+  auto at = [&](int d) {
+    return axis == 0 ? src[((size_t)mirror_index(y + d, H) * W + x) * C + c] : src[((size_t)y * W + mirror_index(x + d, W)) * C + c];
+  };
+  double acc = __dmul_rn(at(0), taps[radius]);
+  for (int d = radius; d >= 1; --d) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(at(-d), at(d)), taps[radius - d]));
   out[(size_t)blockIdx.y * per_plane + i] = acc;
 }
 
@@ -76,18 +76,19 @@ zoom_linear_kernel(const double* __restrict__ in, int H, int W, int C, int H2, i
   const int c = (int)(i % C);
   const int x = (int)((i / C) % W2);
   const int y = (int)(i / ((int64_t)C * W2));
-  const double sy = ((double)y + 0.5) * ((double)H / (double)H2) - 0.5;
-  const double sx = ((double)x + 0.5) * ((double)W / (double)W2) - 0.5;
+  // (explicit roundings: a fused multiply-add here moves the sample position by an ulp of ~1000, i.e. 1e-13)
+  const double sy = __dsub_rn(__dmul_rn(__dadd_rn((double)y, 0.5), __ddiv_rn((double)H, (double)H2)), 0.5);
+  const double sx = __dsub_rn(__dmul_rn(__dadd_rn((double)x, 0.5), __ddiv_rn((double)W, (double)W2)), 0.5);
   const double fy = floor(sy), fx = floor(sx);
-  const double ty = sy - fy, tx = sx - fx;
+  const double ty = __dsub_rn(sy, fy), tx = __dsub_rn(sx, fx);
   const int y0 = mirror_index((int)fy, H), y1 = mirror_index((int)fy + 1, H);
   const int x0 = mirror_index((int)fx, W), x1 = mirror_index((int)fx + 1, W);
   const double v00 = src[((size_t)y0 * W + x0) * C + c], v01 = src[((size_t)y0 * W + x1) * C + c];
   const double v10 = src[((size_t)y1 * W + x0) * C + c], v11 = src[((size_t)y1 * W + x1) * C + c];
   // separable evaluation, rows first then columns (the spline filter's axis order)
-  const double a = (1.0 - ty) * v00 + ty * v10;
-  const double b = (1.0 - ty) * v01 + ty * v11;
-  out[(size_t)blockIdx.y * per_out + i] = (1.0 - tx) * a + tx * b;
+  const double a = __dadd_rn(__dmul_rn(__dsub_rn(1.0, ty), v00), __dmul_rn(ty, v10));
+  const double b = __dadd_rn(__dmul_rn(__dsub_rn(1.0, ty), v01), __dmul_rn(ty, v11));
+  out[(size_t)blockIdx.y * per_out + i] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, tx), a), __dmul_rn(tx, b));
 }
 
 __global__ void u8_to_unit_f64_kernel(const uint8_t* __restrict__ src, int64_t n, double* __restrict__ dst) {

@@ -612,6 +612,24 @@ def describe(mag, direction, oriented, sigma, params: SiftParams, out_dtype=torc
     return desc
 
 
+def refine_keypoints(octv: Octave, k: int, keypoints: torch.Tensor, contrast_th: float = 0.03, ratio_th: float = 10.0):
+    """OPT-IN sub-pixel refinement (the reference keeps it commented out, SS:89-103): localize_keypoint (SS:213-261) for
+    the (image, row, col) keypoints of DoG level k of a float64 octave.  -> dict of device tensors: offsets [n,3] in
+    (x, y, s) order, contrast [n], ratio [n], keep [n] bool (the commented-out acceptance tests)."""
+    if octv.gauss.dtype != torch.float64:
+        raise _lib.FeatureCraftError("refine_keypoints works on the float64 scale space (SiftParams(dtype='f64'))")
+    b, L, h, w = octv.gauss.shape
+    n = int(keypoints.shape[0])
+    dev = octv.gauss.device
+    out = {"offsets": torch.empty((n, 3), dtype=torch.float64, device=dev), "contrast": torch.empty(n, dtype=torch.float64, device=dev),
+           "ratio": torch.empty(n, dtype=torch.float64, device=dev)}
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    _lib.call("fc_refine_keypoints", ptr(octv.gauss), b, L, h, w, ptr(keypoints.contiguous()), n, int(k), float(contrast_th),
+              float(ratio_th), ptr(out["offsets"]), ptr(out["contrast"]), ptr(out["ratio"]), ptr(keep), stream_ptr())
+    out["keep"] = keep.bool()
+    return out
+
+
 def active_scales(params: SiftParams):
     """represent_keypoints builds masks for dog_idx in range(1, n_octaves-1) (KD:60: len(DoG) is the
     number of OCTAVES); get_keypoints only ever emits k in 1..s.  dog_keypoints_orientations then reads
@@ -806,8 +824,8 @@ class BatchExtractor:
         """images: [B,H,W] float64 numpy array / CPU tensor (copied into the pinned staging buffer) or None to
         reuse what the staging buffer of this slot already holds (or what stage() already sent).  prefetch_next:
         also start the H2D of the following ticket from ITS staging buffer before this batch's kernels are queued.
-        Returns a ticket for collect().  Raises FeatureCraftError (FC_ERR_CAPACITY semantics) when the batch yields more
-        descriptors than max_descriptors -- before anything is copied."""
+        Returns a ticket for collect().  Raises _lib.CapacityError (FC_ERR_CAPACITY, with the required count) when the
+        batch yields more descriptors than max_descriptors -- before anything is copied."""
         ticket = self.n_submitted
         slot = ticket % self.depth
         if self.slots[slot] is not None:
@@ -825,8 +843,7 @@ class BatchExtractor:
         res = detect_and_describe(base, self.params, out_dtype=self.desc_dtype)
         m = res.total
         if m > self.cap:
-            raise _lib.FeatureCraftError("%s: batch produced %d descriptors, max_descriptors=%d"
-                                         % (_lib.load().fc_status_string(-2).decode(), m, self.cap))
+            raise _lib.CapacityError("BatchExtractor.submit (descriptors of the batch)", m, self.cap)
         ev_done = torch.cuda.Event()
         ev_done.record(compute)
         with torch.cuda.stream(self.copy_out):

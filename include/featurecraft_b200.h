@@ -34,7 +34,10 @@ extern "C" {
 typedef enum fc_status {
   FC_OK = 0,
   FC_ERR_BAD_ARG = -1,   /* null pointer, non-positive size, unsupported parameter            */
-  FC_ERR_CAPACITY = -2,  /* an output buffer is too small; the required count is written back */
+  FC_ERR_CAPACITY = -2,  /* an output buffer is too small.  Output sizes of this path are data dependent and known
+                            only after the device counted them, so it is the host-side drivers (BatchExtractor,
+                            BatchCornerDetector) that report it -- with the required count -- after their one
+                            synchronisation and BEFORE anything is written to the caller's buffers */
   FC_ERR_CUDA = -3,      /* a CUDA runtime call or launch failed                              */
   FC_ERR_UNSUPPORTED = -4
 } fc_status;
@@ -46,6 +49,12 @@ typedef enum fc_dtype { FC_F32 = 0, FC_F64 = 1, FC_F16 = 2 /* descriptor export 
  * FC_FILTER_SCRIPT applies the contrast + edge-ratio tests of
  * implementation_without_ui/SIFT/SIFT.py:202-215. */
 typedef enum fc_filter { FC_FILTER_APP = 0, FC_FILTER_SCRIPT = 1 } fc_filter;
+
+/* Opt-in variants of the corner response.  The reference uses none of them (SURVEY.md trap 1), so every host-side
+ * default is the first enumerator: np.gradient / K_X gradients, box window, no non-maximum suppression. */
+typedef enum fc_gradient { FC_GRAD_CENTRAL = 0, FC_GRAD_KX = 1, FC_GRAD_SOBEL = 2 } fc_gradient;
+typedef enum fc_window { FC_WINDOW_BOX = 0, FC_WINDOW_GAUSS = 1 } fc_window;
+typedef enum fc_response { FC_RESP_HARRIS = 0, FC_RESP_LAMBDA_MINUS = 1 } fc_response;
 
 FC_API int fc_version(void);
 FC_API const char* fc_status_string(int status);
@@ -75,10 +84,27 @@ FC_API int fc_harris_response(const uint8_t* gray, int batch, int height, int wi
                        double threshold, double* response, uint32_t* mask, void* stream);
 
 /* harris_detection, implementation_without_ui/Corner Detection/harris.ipynb:150-201: same response
- * with the 5x5 K_X gradient (zero padded).  The notebook only visits window_size/2 <= y < H - ...;
+ * with the 5x5 K_X gradient (zero padded).  The window is 2 * int(window_size / 2) + 1 wide, so even sizes are
+ * accepted like in the notebook (:170-176).  The notebook only visits window_size/2 <= y < H - ...;
  * pass that as `border` to fc_threshold_mask_abs. */
 FC_API int fc_notebook_harris_response(const uint8_t* gray, int batch, int height, int width, int window_size, double k,
                                 double* response, void* stream);
+
+/* The corner response with its opt-in components (north_star: Sobel gradients, Gaussian window, 3x3 NMS), one
+ * shared-memory-tiled kernel: gradient (fc_gradient) -> structure-tensor products -> window (fc_window: ones window of
+ * window_size^2 with zero padding like the reference, or the separable Gaussian window_taps_host[window_size] with
+ * BORDER_REFLECT_101 like cv2.GaussianBlur) -> response (Harris det - k tr^2, or the smallest eigenvalue of the window
+ * MEAN) -> optional mask: R > threshold, with nms != 0 also R >= its 8 neighbours.  FC_GRAD_CENTRAL + FC_WINDOW_BOX +
+ * FC_RESP_HARRIS equals fc_harris_response and FC_GRAD_KX + FC_WINDOW_BOX(5) + FC_RESP_LAMBDA_MINUS equals
+ * fc_lambda_minus_response bit for bit; the other combinations are checked against cv2.Sobel / cv2.GaussianBlur. */
+FC_API int fc_corner_response_ex(const uint8_t* gray, int batch, int height, int width, int gradient, int window,
+                          int window_size, const double* window_taps_host, int response, double k, int nms, double threshold,
+                          double* out, uint32_t* mask, void* stream);
+
+/* 3x3 non-maximum suppression + threshold of a resident response map: bit set iff R > threshold and R >= every
+ * neighbour inside the image.  Opt-in: the reference thresholds only (APP/FeatureCraft_Backend.py:358, :441). */
+FC_API int fc_nms3x3_mask(const double* response, int batch, int height, int width, double threshold, uint32_t* mask,
+                   void* stream);
 
 /* apply_lambda_minus_vectorized, APP/FeatureCraft_Backend.py:402-437: K_X gradients, 5x5 ones
  * window / 25, smallest eigenvalue with LAPACK's dsterf/dlae2 rounding sequence, bit-exact.
@@ -157,6 +183,15 @@ FC_API int fc_gauss_octave_extrema(const void* gauss, int dtype, int batch, int 
  * n_dog >= 3 DoG images [batch][n_dog][h][w]: extrema [n_dog-2][batch][h][(w+31)/32], plane k-1 for DoG k. */
 FC_API int fc_dog_extrema(const void* dog, int dtype, int batch, int height, int width, int n_dog, int filter,
                    double contrast_th, double ratio_th, uint32_t* extrema, void* stream);
+
+/* Opt-in sub-pixel refinement (north_star; the reference leaves it commented out, APP/utils/SIFT_scale_space.py:
+ * 89-103): localize_keypoint (:213-261) for n keypoints (image, row, col) of DoG level k of a float64 Gaussian stack
+ * [batch][n_levels][h][w] (interior keypoints, as get_keypoints emits them).  offsets[i] = -inv(H) J in (x, y, s)
+ * order, contrast[i] = D + J.offset / 2, ratio[i] = tr^2 / det of the spatial Hessian, keep[i] = the commented-out
+ * acceptance: max(offset) <= 0.5 and |contrast| >= contrast_th and not ratio > ratio_th. */
+FC_API int fc_refine_keypoints(const double* gauss, int batch, int n_levels, int height, int width, const int32_t* keypoints,
+                        int n_keypoints, int k, double contrast_th, double ratio_th, double* offsets, double* contrast,
+                        double* ratio, uint8_t* keep, void* stream);
 
 /* rescale(gray, 2, anti_aliasing=False) in front of the pyramid (APP/utils/keypoint_descriptor.py:296):
  * bilinear, pixel-centre aligned, mirror border (== scipy.ndimage.zoom(order=1, mode='mirror',

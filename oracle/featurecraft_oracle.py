@@ -355,6 +355,39 @@ def script_filter_mask(mask, dogs, k, contrast_th, ratio_th):
     return keep
 
 
+def localize_keypoint_full(D, x, y, s):
+    """APP/utils/SIFT_scale_space.py:213-261 (the app's 3-D quadratic fit; its only call site is commented out,
+    :89-103): first and second differences of the DoG stack D[y, x, s], offset = -inv(H) J.  Returns
+    (offset, J, H[:2, :2], x, y, s) like the reference."""
+    D = np.asarray(D).astype(np.float64)
+    dx = (D[y, x + 1, s] - D[y, x - 1, s]) / 2.0
+    dy = (D[y + 1, x, s] - D[y - 1, x, s]) / 2.0
+    ds = (D[y, x, s + 1] - D[y, x, s - 1]) / 2.0
+    dxx = D[y, x + 1, s] - 2 * D[y, x, s] + D[y, x - 1, s]
+    dxy = ((D[y + 1, x + 1, s] - D[y + 1, x - 1, s]) - (D[y - 1, x + 1, s] - D[y - 1, x - 1, s])) / 4
+    dxs = ((D[y, x + 1, s + 1] - D[y, x - 1, s + 1]) - (D[y, x + 1, s - 1] - D[y, x - 1, s - 1])) / 4
+    dyy = D[y + 1, x, s] - 2 * D[y, x, s] + D[y - 1, x, s]
+    dys = ((D[y + 1, x, s + 1] - D[y - 1, x, s + 1]) - (D[y + 1, x, s - 1] - D[y - 1, x, s - 1])) / 4
+    dss = D[y, x, s + 1] - 2 * D[y, x, s] + D[y, x, s - 1]
+    J = np.array([dx, dy, ds])
+    H = np.array([[dxx, dxy, dxs], [dxy, dyy, dys], [dxs, dys, dss]])
+    offset = -np.linalg.inv(H).dot(J)
+    return offset, J, H[:2, :2], x, y, s
+
+
+def refine_keypoint(D, x, y, s, contrast_th, ratio_th):
+    """The acceptance tests get_keypoints keeps commented out around localize_keypoint
+    (APP/utils/SIFT_scale_space.py:89-101), evaluated as written: -> (offset, contrast, ratio, keep)."""
+    offset, J, H, x, y, s = localize_keypoint_full(D, x, y, s)
+    contrast = np.asarray(D, dtype=np.float64)[y, x, s] + 0.5 * J.dot(offset)
+    tr = H[0][0] + H[1][1]
+    det = H[0][0] * H[1][1] - H[0][1] ** 2
+    with np.errstate(all="ignore"):
+        r = (tr ** 2) / det
+    keep = not (np.max(offset) > 0.5) and not (abs(contrast) < contrast_th) and not (r > ratio_th)
+    return offset, contrast, r, keep
+
+
 def get_keypoints(DOG_octave, k, contrast_th, ratio_th, DoG_full_array, variant="app"):
     """APP/utils/SIFT_scale_space.py:60-106 (variant='app': every extremum is kept) or
     implementation_without_ui/SIFT/SIFT.py:172-222 (variant='script').  DoG_full_array may be the

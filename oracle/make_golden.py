@@ -186,6 +186,13 @@ def sift():
     kl = [(3, 7, 0, 1, 45.0), (10, 2, 3, 2, 355.0), (0, 0, 1, 1, 5.0)]
     for kp, (x, y, size, angle) in zip(kd.kp_list_2_opencv_kp_list(kl), O.kp_list_2_xy(kl)):
         assert (kp.pt[0], kp.pt[1], kp.size, kp.angle) == (np.float32(x), np.float32(y), np.float32(size), np.float32(angle))
+    # localize_keypoint (:213-261, dead code in the app): the oracle twin against the reference's own function
+    rngl = np.random.default_rng(21)
+    Dl = rngl.standard_normal((9, 11, 4))
+    for (yy, xx, sl) in ((1, 1, 1), (4, 7, 2), (7, 9, 1)):
+        a = ss.localize_keypoint(Dl, xx, yy, sl)
+        b = O.localize_keypoint_full(Dl, xx, yy, sl)
+        assert all(np.array_equal(u, v) for u, v in zip(a[:3], b[:3])) and a[3:] == b[3:]
     # sift_resize / rescale: the reference functions run through the scipy stub (ref_loader) -- this pins the ORACLE's
     # restatement to that stub, not to scikit-image (absent): documented as unpinned
     rgb = np.random.default_rng(4).random((50, 70, 3))

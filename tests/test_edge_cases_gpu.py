@@ -210,3 +210,38 @@ def test_batched_compaction_pieces(M, lib):
     assert lib.fc_exclusive_scan_i32(None, 10, ptr(offs), None, stream_ptr()) != 0
     assert lib.fc_popcount_u64(ptr(masks), 0, ptr(pc), stream_ptr()) != 0
     assert lib.fc_mask_row_count(None, B, H, W, ptr(counts), stream_ptr()) != 0
+
+
+def test_capacity_errors_carry_the_required_count(M, lib):
+    """FC_ERR_CAPACITY: the batch drivers know the output size after their one synchronisation and refuse BEFORE
+    anything is copied into the caller's (too small) buffers."""
+    from exvision_featurecraft_b200 import _lib, synthetic
+
+    imgs = np.stack([synthetic.sift_image(48, 64, seed=s) for s in range(2)])
+    ex = M.sift.BatchExtractor(M.sift.SiftParams(), 2, 48, 64, max_descriptors=10, depth=2)
+    with pytest.raises(_lib.CapacityError) as ei:
+        ex.submit(imgs)
+    assert ei.value.status == -2 and ei.value.required > 10 and ei.value.capacity == 10
+    big = M.sift.BatchExtractor(M.sift.SiftParams(), 2, 48, 64, max_descriptors=ei.value.required, depth=2)
+    out = big.collect(big.submit(imgs))
+    assert sum(len(p) for p, _ in out) == ei.value.required
+    gray = np.stack([synthetic.corner_image(64, 128, seed=s) for s in range(2)])
+    det = M.corners.BatchCornerDetector(2, 64, 128, max_corners=3)
+    with pytest.raises(_lib.CapacityError) as ec:
+        det.submit(gray)
+    assert ec.value.required > 3
+
+
+def test_notebook_harris_accepts_even_windows(M):
+    """harris.ipynb:170-176: offset = int(window_size / 2), window = 2 * offset + 1 -- any size works in the notebook;
+    only the app's convolve2d_optimized path fails on even sizes."""
+    from exvision_featurecraft_b200 import synthetic
+
+    gray = synthetic.corner_image(60, 72, seed=8)
+    for ws in (4, 6):
+        got = M.corners.notebook_harris(gray, ws, 0.04, 1e8)
+        corners_ref, r_ref = O.harris_detection(gray, ws, 0.04, 1e8)
+        assert np.abs(got.response[0].cpu().numpy() - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
+        assert got.coords.cpu().numpy().tolist() == [[y, x] for x, y, _ in corners_ref]
+    with pytest.raises(ValueError):
+        M.corners.harris(gray, 4, 0.04, 10000)
