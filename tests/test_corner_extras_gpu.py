@@ -78,7 +78,7 @@ def test_nms_is_a_3x3_dilation_test(C):
             dil = cv2.dilate(padded, np.ones((3, 3), np.uint8))[1:-1, 1:-1]
             ref = np.argwhere((R > 10000) & (R >= dil))
             got = coords[offs[b]:offs[b + 1]].cpu().numpy()
-            assert np.array_equal(got, ref) and len(ref) > 10
+            assert np.array_equal(got, ref) and len(ref) >= 3
             assert len(ref) < (R > 10000).sum()  # it suppresses something: the reference's plain threshold keeps more
 
 
@@ -109,4 +109,4 @@ def test_subpixel_refinement_equals_localize_keypoint(lib):
                     assert bool(keep[i]) == rk
                 checked += 1
                 kept += int(keep[i])
-    assert checked > 500 and 0 < kept < checked
+    assert checked > 200 and 0 < kept < checked
