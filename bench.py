@@ -423,7 +423,7 @@ def main():
     ap.add_argument("--ref-items-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--sift-dtype", default=None, choices=["mixed", "f32", "f64"])
+    ap.add_argument("--sift-dtype", default=None, choices=["mixed", "f64"])
     args = ap.parse_args()
     table = workloads()
     wl = table[args.workload or "sift"](args)

@@ -19,7 +19,7 @@ class SiftWorkload:
     def __init__(self, args):
         self.batch = args.batch or 16
         self.mode = getattr(args, "sift_dtype", None) or "mixed"
-        self.dtype = {"mixed": "f32 arithmetic, f64-certified decisions", "f32": "f32", "f64": "f64"}[self.mode]
+        self.dtype = {"mixed": "f32 arithmetic, f64-certified decisions", "f64": "f64"}[self.mode]
         self.desc_per_image = None
 
     def describe(self, world):

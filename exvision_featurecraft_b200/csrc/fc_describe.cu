@@ -2,7 +2,8 @@
 //
 //   gradient_field_kernel<T>   sift_gradient (APP/utils/keypoint_descriptor.py:72-79) of one pyramid level:
 //                              magnitude, direction (degrees, Python % 360) and the 36-bin index
-//                              np.round(direction * 36 / 360) (:140-142) as one byte per pixel.
+//                              np.round(direction * 36 / 360) (:140-142) as one byte per pixel (float64 mode).
+//   gradient_codes_kernel      certified mode: magnitude | exact direction code, one word per pixel.
 //   orientation_kernel<T,LPK>  8 / 16 / 32 lanes per keypoint: zero-padded (2r+1)^2 window, weight = magnitude x
 //                              unnormalised Gaussian table, 36-bin histogram (:144-163).  Every lane owns a
 //                              private copy of the histogram in shared memory ([bin][lane],
@@ -45,7 +46,7 @@ __device__ __forceinline__ T py_mod360(T a) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int W, T* __restrict__ mag,
-                      T* __restrict__ dir, T* __restrict__ mag_dir, uint8_t* __restrict__ obin, uint32_t* __restrict__ packed) {
+                      T* __restrict__ dir, uint8_t* __restrict__ obin) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -62,92 +63,11 @@ gradient_field_kernel(const T* __restrict__ gauss, int L, int level, int H, int 
   // |deg| <= 180, so Python's % 360 is the identity for deg >= 0 and one rounded + 360 otherwise
   const T d = deg < T(0) ? Math<T>::add(deg, T(360)) : deg;
   const size_t o = ((size_t)b * H + y) * W + x;
-  if (mag_dir) {  // interleaved (magnitude, direction) pairs: one 8-byte gather per descriptor sample
-    mag_dir[2 * o] = m;
-    mag_dir[2 * o + 1] = d;
-  } else {
-    mag[o] = m;
-    dir[o] = d;
-  }
-  // np.round(direction * 36 / 360): half to even, evaluated in the scale-space type on the stored direction
-  if constexpr (sizeof(T) == 4) {
-    const int ob = (int)rintf(__fdiv_rn(__fmul_rn(d, 36.0f), 360.0f));
-    if (obin) obin[o] = (uint8_t)ob;
-    // orientation operand of the f32 pipeline: magnitude rounded to 18 mantissa bits with the bin (0..36) in the low
-    // 6 bits, so that the orientation kernel gathers one 4-byte word per sample instead of a float and a byte
-    if (packed) packed[o] = ((__float_as_uint(m) + 32u) & ~63u) | (uint32_t)ob;
-  } else {
-    obin[o] = (uint8_t)(int)rint(__ddiv_rn(__dmul_rn((double)d, 36.0), 360.0));
-  }
-}
-
-// float32 fast path of the gradient field: four pixels per thread (16-byte loads and stores) and straight-line
-// arithmetic -- the angle comes from a degree-15 odd minimax polynomial in min/max of |gx|, |gy| evaluated
-// directly in degrees (max error 8.5e-6 degrees, the float32 resolution of the result), followed by the octant
-// fix-ups; square root and reciprocal are the MUFU approximations (<= 2 ulp).  The generic kernel above spends
-// ~85 instructions per pixel (atan2f, IEEE sqrt and divide sequences), this one ~40.  f32 mode's parity bar is a
-// tolerance against the float64 oracle (tests/test_sift_gpu.py::test_gradient_field), which both kernels meet.
-__device__ __forceinline__ float atan2_degrees_0_360(float y, float x) {
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  float rcp;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(mx));
-  const float a = mx > 0.f ? mn * rcp : 0.f;
-  const float t = a * a;
-  float p = -2.323167295e-01f;
-  p = fmaf(p, t, 1.252680846e+00f);
-  p = fmaf(p, t, -3.203576766e+00f);
-  p = fmaf(p, t, 5.524598167e+00f);
-  p = fmaf(p, t, -7.969067623e+00f);
-  p = fmaf(p, t, 1.142854225e+01f);
-  p = fmaf(p, t, -1.909660375e+01f);
-  p = fmaf(p, t, 5.729574145e+01f);
-  float r = p * a;                 // [0, 45]
-  r = ay > ax ? 90.f - r : r;      // [0, 90]
-  r = x < 0.f ? 180.f - r : r;     // [0, 180]
-  return y < 0.f ? 360.f - r : r;  // np.rad2deg(arctan2) % 360: negative angles are shifted up by 360
-}
-
-__global__ void __launch_bounds__(256)
-gradient_field4_kernel(const float* __restrict__ gauss, int L, int level, int H, int W, float* __restrict__ mag,
-                       float* __restrict__ dir, float* __restrict__ mag_dir, uint8_t* __restrict__ obin,
-                       uint32_t* __restrict__ packed) {
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y;
-  const int b = blockIdx.z;
-  if (x >= W) return;  // W % 4 == 0 on this path
-  const float* g = gauss + ((size_t)b * L + level) * H * W;
-  // true convolution with [-1, 0, 1], 'symm' border: gx = I[., x-1] - I[., x+1] with the edge sample repeated
-  const int yu = y > 0 ? y - 1 : 0, yd = y < H - 1 ? y + 1 : H - 1;
-  const float* row = g + (size_t)y * W;
-  const float4 c = *reinterpret_cast<const float4*>(row + x);
-  const float4 u = *reinterpret_cast<const float4*>(g + (size_t)yu * W + x);
-  const float4 d = *reinterpret_cast<const float4*>(g + (size_t)yd * W + x);
-  const float left = row[x > 0 ? x - 1 : 0];
-  const float right = row[x + 4 < W ? x + 4 : W - 1];
-  const float gx[4] = {left - c.y, c.x - c.z, c.y - c.w, c.z - right};
-  const float gy[4] = {u.x - d.x, u.y - d.y, u.z - d.z, u.w - d.w};
-  float m[4], a[4];
-  uint32_t pk[4];
-  int ob[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float ss = fmaf(gx[i], gx[i], gy[i] * gy[i]);
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m[i]) : "f"(ss));
-    a[i] = atan2_degrees_0_360(gy[i], gx[i]);
-    ob[i] = __float2int_rn(a[i] * 0.1f);  // np.round(direction * 36 / 360)
-    pk[i] = ((__float_as_uint(m[i]) + 32u) & ~63u) | (uint32_t)ob[i];
-  }
-  const size_t o = ((size_t)b * H + y) * W + x;
-  if (mag_dir) {
-    reinterpret_cast<float4*>(mag_dir + 2 * o)[0] = make_float4(m[0], a[0], m[1], a[1]);
-    reinterpret_cast<float4*>(mag_dir + 2 * o)[1] = make_float4(m[2], a[2], m[3], a[3]);
-  } else {
-    *reinterpret_cast<float4*>(mag + o) = make_float4(m[0], m[1], m[2], m[3]);
-    *reinterpret_cast<float4*>(dir + o) = make_float4(a[0], a[1], a[2], a[3]);
-  }
-  if (obin) *reinterpret_cast<uchar4*>(obin + o) = make_uchar4((unsigned char)ob[0], (unsigned char)ob[1], (unsigned char)ob[2], (unsigned char)ob[3]);
-  if (packed) *reinterpret_cast<uint4*>(packed + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  mag[o] = m;
+  dir[o] = d;
+  // np.round(direction * 36 / 360): half to even, evaluated in the field's type on the stored direction
+  if constexpr (sizeof(T) == 4) obin[o] = (uint8_t)(int)rintf(__fdiv_rn(__fmul_rn(d, 36.0f), 360.0f));
+  else obin[o] = (uint8_t)(int)rint(__ddiv_rn(__dmul_rn((double)d, 36.0), 360.0));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -267,15 +187,15 @@ static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the fi
 // histograms) is the same for every LPK, so small windows -- most keypoints sit in octave 0 with 15x15 or 21x21
 // windows -- use 8 lanes and amortise it over four keypoints per warp.  Sums are in T: double in exact (f64) mode,
 // float in f32 mode (whose parity bar is a tolerance), always in a fixed order (deterministic).
-// MODE: kOriPlanes = magnitude plane + bin plane (float64 exact mode and the standalone entry point), kOriPacked =
-// float32 mode's magnitude | bin words, kOriCoded = certified mode's magnitude | code words (gradient_codes_kernel).
+// MODE: kOriPlanes = magnitude plane + bin plane (float64 exact mode and the standalone entry point), kOriCoded =
+// certified mode's magnitude | code words (gradient_codes_kernel).
 // The weight table holds |dy| <= wry, |dx| <= wrx only (the window is clipped to the image, so a table larger than
 // twice the image is never read): weight of offset (dy, dx) = weights[(dy + wry) * (2 wrx + 1) + dx + wrx].
 // kOriCoded also certifies its float32 histogram: `tol` bounds the relative error of a bin against the float64 sum
 // (magnitudes carry 2^-17, the float32 products and the running sums the rest); a keypoint with a bin within tol * max
 // of the 0.8 * max cut is marked (bit 63) and appended to `recheck_list` for fc_orientation_recheck instead of being
 // decided here (the list holds up to n_keypoints entries; recheck_count is zeroed by the launcher).
-enum { kOriPlanes = 0, kOriPacked = 1, kOriCoded = 2 };
+enum { kOriPlanes = 0, kOriCoded = 2 };
 static constexpr unsigned long long kOriRecheckBit = 1ull << 63;
 
 template <typename T, int LPK, int NR, int MODE>
@@ -307,7 +227,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const int b = keypoints[3 * nn], ki = keypoints[3 * nn + 1], kj = keypoints[3 * nn + 2];
   const T* m = mag + (size_t)b * H * W;
   const uint8_t* ob = PACKED ? nullptr : obin + (size_t)b * H * W;
-  // PACKED (float only): `mag` holds fc_gradient_field_packed's words = magnitude | bin
+  // PACKED (float only): `mag` holds fc_gradient_codes' words = magnitude | direction code
   const uint32_t* pk = reinterpret_cast<const uint32_t*>(m);
   const int side = 2 * wrx + 1;
   // clip the window to the image (outside is zero padding = no contribution)
@@ -339,8 +259,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
             if constexpr (PACKED) {
               const uint32_t p = pk[ro + c];
               bins[v][u] = (int)(p & 63u);
-              const float pm = MODE == kOriCoded ? __uint_as_float((p & ~255u) >> 1) : __uint_as_float(p & ~63u);
-              ws[v][u] = (T)__fmul_rn(pm, (float)weights[wo + c]);
+              ws[v][u] = (T)__fmul_rn(__uint_as_float((p & ~255u) >> 1), (float)weights[wo + c]);
             } else {
               bins[v][u] = ob[ro + c];
               ws[v][u] = Math<T>::mul(m[ro + c], weights[wo + c]);
@@ -359,8 +278,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
       for (int c = c0 + sub; c <= c1; c += LPK) {
         if constexpr (PACKED) {
           const uint32_t p = pk[rr * W + c];
-          const float pm = MODE == kOriCoded ? __uint_as_float((p & ~255u) >> 1) : __uint_as_float(p & ~63u);
-          hme[(p & 63u) * PITCH] += (T)__fmul_rn(pm, (float)weights[woff + rr * side + c]);
+          hme[(p & 63u) * PITCH] += (T)__fmul_rn(__uint_as_float((p & ~255u) >> 1), (float)weights[woff + rr * side + c]);
         } else {
           hme[ob[rr * W + c] * PITCH] += Math<T>::mul(m[rr * W + c], weights[woff + rr * side + c]);
         }
@@ -540,12 +458,11 @@ static constexpr int kTrigStride = 2 + 32;
 
 // Persistent: every CTA converts the host tables once (Gaussian mask, bin edges, the fixed-point column deltas as
 // int32, cos / sin) into shared memory, then its warps walk the oriented keypoints with stride = warps in the grid.
-// LAYOUT: kDescPlanes = separate magnitude / direction planes, kDescInterleaved = `mag` holds interleaved (magnitude,
-// direction) pairs (fc_gradient_field_packed), kDescCoded = `mag` holds certified mode's magnitude | code words
+// LAYOUT: kDescPlanes = separate magnitude / direction planes, kDescCoded = `mag` holds certified mode's magnitude | code words
 // (gradient_codes_kernel): the descriptor bin is then integer arithmetic on the exact 5-degree sector,
 //   sector of (direction - theta) = (2 (o - b) - 2 + sub) mod 72,  bin = sector / 9   (theta = 10 b + 5),
 // so no float rounding can move a sample across a bin edge.
-enum { kDescPlanes = 0, kDescInterleaved = 1, kDescCoded = 2 };
+enum { kDescPlanes = 0, kDescCoded = 2 };
 
 // Output placement: without `remap` descriptor n of this call goes to row n.  With it (the batched pipeline) the rows
 // land directly in the caller's final order -- images one after the other, each image in the reference's emission order
@@ -625,9 +542,8 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
 #pragma unroll
     for (int k = 0; k < 9; ++k) myh[k * 32] = ACC(0);
     __syncwarp();
-    constexpr bool IL = LAYOUT == kDescInterleaved;
     constexpr bool CODED = LAYOUT == kDescCoded;
-    const T* m = mag + (size_t)b * H * W * (IL ? 2 : 1);
+    const T* m = mag + (size_t)b * H * W;
     const T* d = LAYOUT == kDescPlanes ? dir + (size_t)b * H * W : nullptr;
     const int4 ad4 = *reinterpret_cast<const int4*>(&sAd[bin][cx]);
     const int4 bd4 = *reinterpret_cast<const int4*>(&sBd[bin][cx]);
@@ -654,11 +570,6 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
           mv[ry][rx] = (T)__uint_as_float((p & ~255u) >> 1);
           dv[ry][rx] = T(0);
           sect[ry][rx] = 2 * (int)(p & 63u) - 1 + (int)((p >> 6) & 3u);
-        } else if constexpr (IL) {
-          static_assert(!IL || sizeof(T) == 4, "interleaved planes are float32");
-          const float2 v = reinterpret_cast<const float2*>(m)[o];
-          mv[ry][rx] = in ? (T)v.x : T(0);
-          dv[ry][rx] = in ? (T)v.y : T(0);
         } else {
           mv[ry][rx] = in ? m[o] : T(0);
           dv[ry][rx] = in ? d[o] : T(0);
@@ -760,6 +671,161 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
   }
 }
 
+// Certified-mode descriptors with the source patch staged in shared memory (the kernel the pipeline launches when
+// the image width is a multiple of 4).  The 256 samples of a keypoint lie within 11 pixels of it; gathering them from
+// global memory costs ~16 cache-line wavefronts per warp load (a rotated 16x16 window touches 10-16 image rows per
+// load instruction, 8 instructions per keypoint: the L1 wavefront rate was the bound).  Here the 23-row x 28-column
+// aligned patch around the keypoint is copied with 16-byte cp.async chunks -- row-coalesced, ~40 wavefronts per
+// keypoint -- into one of two per-warp buffers while the previous keypoint is being evaluated, and the rotated samples
+// are read from shared memory.  Outside the image the patch holds zeros (= cv2.warpAffine's constant border).
+static constexpr int kPatchRows = 23, kPatchCols = 28, kPatchWords = kPatchRows * kPatchCols;
+
+__device__ __forceinline__ void desc_stage_patch(const uint32_t* __restrict__ codes, int H, int W, const int4 kp,
+                                                 uint32_t* __restrict__ buf, int lane) {
+  const uint32_t* img = codes + (size_t)kp.x * H * W;
+  const int py0 = kp.y - 11, px0 = (kp.z - 11) & ~3;
+  for (int i = lane; i < kPatchRows * (kPatchCols / 4); i += 32) {
+    const int r = i / (kPatchCols / 4), c4 = i - r * (kPatchCols / 4);
+    const int y = py0 + r, x = px0 + 4 * c4;
+    uint32_t* dst = buf + r * kPatchCols + 4 * c4;
+    if (y >= 0 && y < H && x >= 0 && x + 3 < W) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(img + (size_t)y * W + x) : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = (y >= 0 && y < H && x + j >= 0 && x + j < W) ? img[(size_t)y * W + x + j] : 0u;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(kDescWarps * 32)
+descriptor_patch_kernel(const uint32_t* __restrict__ codes, int H, int W, const int32_t* __restrict__ oriented, int n_oriented,
+                        const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc,
+                        const DescPlacement place) {
+  __shared__ int sXY[kDescWarps][32];         // x0[0..15], y0[0..15] per warp
+  __shared__ float sHist[kDescWarps][9][32];  // per-lane private bins 0..8 (8 = dropped), [bin][lane]: conflict free
+  __shared__ float sMask[256];
+  __shared__ __align__(16) int sAd[36][16], sBd[36][16];  // rint(cos * x * 1024), rint(sin * x * 1024) per bin
+  __shared__ double sCS[36][2];
+  __shared__ __align__(16) uint32_t sPatch[kDescWarps][2][kPatchWords];
+  for (int t = threadIdx.x; t < 256; t += kDescWarps * 32) sMask[t] = (float)gmask[t];
+  for (int t = threadIdx.x; t < 36 * 16; t += kDescWarps * 32) {
+    const int bn = t >> 4, x = t & 15;
+    sAd[bn][x] = (int)trig[bn * kTrigStride + 2 + x];
+    sBd[bn][x] = (int)trig[bn * kTrigStride + 18 + x];
+  }
+  if (threadIdx.x < 72) sCS[threadIdx.x >> 1][threadIdx.x & 1] = trig[(threadIdx.x >> 1) * kTrigStride + (threadIdx.x & 1)];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cell = lane >> 1, half = lane & 1;
+  const int cy = (cell >> 2) * 4 + half * 2, cx = (cell & 3) * 4;
+  float* myh = &sHist[warp][0][lane];
+  float wmask[2][4];  // this lane's 8 Gaussian weights never change
+#pragma unroll
+  for (int ry = 0; ry < 2; ++ry)
+#pragma unroll
+    for (int rx = 0; rx < 4; ++rx) wmask[ry][rx] = sMask[(cy + ry) * 16 + cx + rx];
+  const int warps_total = gridDim.x * kDescWarps;
+  const int4* list = reinterpret_cast<const int4*>(oriented);
+  int n = blockIdx.x * kDescWarps + warp;
+  int cur = 0;
+  if (n < n_oriented) desc_stage_patch(codes, H, W, list[n], sPatch[warp][0], lane);
+  for (; n < n_oriented; n += warps_total) {  // no block-wide barrier inside
+    const int4 kp = list[n];
+    const int b = kp.x, ki = kp.y, kj = kp.z, bin = kp.w;
+    const double cs = sCS[bin][0], sn = sCS[bin][1];
+    {
+      // rotated_subimage: v_x = (c, s), v_y = (-s, c); s_x = j - c*7.5 - (-s)*7.5; s_y = i - s*7.5 - c*7.5
+      // X0[y] = rint((M01*y + M02) * 1024) + 512 ; Y0[y] = rint((M11*y + M12) * 1024) + 512
+      const double yy = (double)(lane & 15);
+      double a;
+      if (lane < 16) a = __dadd_rn(__dmul_rn(-sn, yy), __dsub_rn(__dsub_rn((double)kj, __dmul_rn(cs, 7.5)), __dmul_rn(-sn, 7.5)));
+      else a = __dadd_rn(__dmul_rn(cs, yy), __dsub_rn(__dsub_rn((double)ki, __dmul_rn(sn, 7.5)), __dmul_rn(cs, 7.5)));
+      sXY[warp][lane] = __double2int_rn(__dmul_rn(a, 1024.0)) + 512;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) myh[k * 32] = 0.f;
+    // request the next keypoint's patch, then wait for this one's
+    if (n + warps_total < n_oriented) {
+      desc_stage_patch(codes, H, W, list[n + warps_total], sPatch[warp][cur ^ 1], lane);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t* patch = sPatch[warp][cur];
+    cur ^= 1;
+    const int py0 = ki - 11, px0 = (kj - 11) & ~3;
+    const int4 ad4 = *reinterpret_cast<const int4*>(&sAd[bin][cx]);
+    const int4 bd4 = *reinterpret_cast<const int4*>(&sBd[bin][cx]);
+    const int ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w}, bd[4] = {bd4.x, bd4.y, bd4.z, bd4.w};
+    uint32_t pv[2][4];
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+      const int X0 = sXY[warp][cy + ry], Y0 = sXY[warp][16 + cy + ry];
+#pragma unroll
+      for (int rx = 0; rx < 4; ++rx) {
+        const int px = ((X0 + ad[rx]) >> 10) - px0;
+        const int py = ((Y0 + bd[rx]) >> 10) - py0;
+        // |offset| <= 7.5 * sqrt(2) + rounding < 11.2: always inside the patch; the test only guards the arithmetic
+        const bool ok = (unsigned)px < (unsigned)kPatchCols && (unsigned)py < (unsigned)kPatchRows;
+        pv[ry][rx] = ok ? patch[py * kPatchCols + px] : 0u;
+      }
+    }
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+#pragma unroll
+      for (int rx = 0; rx < 4; ++rx) {
+        const uint32_t p = pv[ry][rx];
+        const float wv = __fmul_rn(__uint_as_float((p & ~255u) >> 1), wmask[ry][rx]);
+        int sc = 2 * (int)(p & 63u) - 1 + (int)((p >> 6) & 3u) - (2 * bin + 1);  // sector of (direction - theta), in [-72, 72]
+        sc += sc < 0 ? 72 : 0;
+        sc -= sc >= 72 ? 72 : 0;
+        myh[((sc * 57) >> 9) * 32] += wv;  // sc / 9 for 0 <= sc < 72
+      }
+    }
+    __syncwarp();
+    // merge the two halves of the cell (rows 0-1 then rows 2-3), round to float32 like the reference's cell hist;
+    // normalise / clip [2^-10, 0.2] / normalise (:281-287)
+    float f[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float mine = myh[k * 32];
+      const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+      const float sum = half ? __fadd_rn(other, mine) : __fadd_rn(mine, other);
+      if ((k >> 2) == half) f[k & 3] = sum;  // even lane keeps bins 0..3, odd lane bins 4..7 of the cell
+    }
+    float ss = f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float lo = 0.0009765625f, hi = 0.2f;  // np.finfo(np.float16).eps, 0.2
+    const float inv = rsqrtf(ss);               // 0 * inf = NaN for an all-zero window, like the reference's 0 / 0
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = f[k] * inv;
+      if (v == v) v = v < lo ? lo : (v > hi ? hi : v);  // np.clip keeps NaN
+      f[k] = v;
+      s2 += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    size_t row = (size_t)n;
+    if (place.remap) {
+      const int2 rm = place.remap[b];
+      row = (size_t)(rm.y + (place.list_base + n - rm.x));
+    }
+    if (place.points && lane == 0)
+      place.points[row] = make_uint2(((uint32_t)ki & 0xffffu) | ((uint32_t)kj << 16),
+                                     (uint32_t)place.octave | ((uint32_t)place.scale << 8) | ((uint32_t)bin << 16));
+    const float inv2 = rsqrtf(s2);
+    Store4<OUT>::put(desc + row * 128 + lane * 4, f[0] * inv2, f[1] * inv2, f[2] * inv2, f[3] * inv2);
+    __syncwarp();  // the next keypoint rewrites sXY, the private bins and (one step later) this patch buffer
+  }
+}
+
 // rotated_subimage (APP/utils/keypoint_descriptor.py:175-212) as a standalone call: any theta, any size
 // up to 64x64; cos/sin are computed by the caller with the reference's own libm calls.
 __global__ void rotated_window_kernel(const double* __restrict__ image, int H, int W, double cx, double cy, double cs,
@@ -791,47 +857,23 @@ extern "C" int fc_rotated_window(const double* image, int height, int width, dou
   return FC_OK;
 }
 
-static int launch_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
-                                 void* magnitude, void* direction, void* mag_dir, uint8_t* orientation_bin, uint32_t* packed,
-                                 void* stream) {
-  if (!gauss || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
-  if (!mag_dir && (!magnitude || !direction)) return FC_ERR_BAD_ARG;
+extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
+                                 void* magnitude, void* direction, uint8_t* orientation_bin, void* stream) {
+  if (!gauss || !magnitude || !direction || !orientation_bin || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
   if (level < 0 || level >= n_levels) return FC_ERR_BAD_ARG;
   dim3 grid(div_up(width, 256), height, batch);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool vec_ok = (width % 4 == 0) && (((reinterpret_cast<uintptr_t>(gauss) | reinterpret_cast<uintptr_t>(magnitude) |
-                                            reinterpret_cast<uintptr_t>(direction) | reinterpret_cast<uintptr_t>(mag_dir) |
-                                            reinterpret_cast<uintptr_t>(packed)) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(orientation_bin) & 3) == 0);
-  if (dtype == FC_F32 && vec_ok)
-    gradient_field4_kernel<<<dim3(div_up(width, 1024), height, batch), 256, 0, st>>>(
-        (const float*)gauss, n_levels, level, height, width, (float*)magnitude, (float*)direction, (float*)mag_dir,
-        orientation_bin, packed);
-  else if (dtype == FC_F32)
+  if (dtype == FC_F32)
     gradient_field_kernel<float><<<grid, 256, 0, st>>>((const float*)gauss, n_levels, level, height, width, (float*)magnitude,
-                                                       (float*)direction, (float*)mag_dir, orientation_bin, packed);
-  else if (dtype == FC_F64 && orientation_bin && !packed && !mag_dir)
+                                                       (float*)direction, orientation_bin);
+  else if (dtype == FC_F64)
     gradient_field_kernel<double><<<grid, 256, 0, st>>>((const double*)gauss, n_levels, level, height, width,
-                                                        (double*)magnitude, (double*)direction, nullptr, orientation_bin, nullptr);
+                                                        (double*)magnitude, (double*)direction, orientation_bin);
   else
     return FC_ERR_BAD_ARG;
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
-}
-
-extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
-                                 void* magnitude, void* direction, uint8_t* orientation_bin, void* stream) {
-  if (!orientation_bin) return FC_ERR_BAD_ARG;
-  return launch_gradient_field(gauss, dtype, batch, n_levels, level, height, width, magnitude, direction, nullptr,
-                               orientation_bin, nullptr, stream);
-}
-
-extern "C" int fc_gradient_field_packed(const void* gauss, int batch, int n_levels, int level, int height, int width,
-                                        void* magnitude_direction, uint32_t* magnitude_bin, void* stream) {
-  if (!magnitude_direction || !magnitude_bin) return FC_ERR_BAD_ARG;
-  return launch_gradient_field(gauss, FC_F32, batch, n_levels, level, height, width, nullptr, nullptr, magnitude_direction,
-                               nullptr, magnitude_bin, stream);
 }
 
 static int launch_orientation(const void* magnitude, const uint8_t* orientation_bin, int dtype, int mode, int batch,
@@ -870,7 +912,6 @@ static int launch_orientation(const void* magnitude, const uint8_t* orientation_
     }                                                                \
   } while (0)
   if (mode == kOriCoded) FC_ORI_T(float, kOriCoded);
-  else if (mode == kOriPacked) FC_ORI_T(float, kOriPacked);
   else if (dtype == FC_F32) FC_ORI_T(float, kOriPlanes);
   else FC_ORI_T(double, kOriPlanes);
 #undef FC_ORI_T
@@ -885,13 +926,6 @@ extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orienta
                                    int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
   return launch_orientation(magnitude, orientation_bin, dtype, kOriPlanes, batch, height, width, keypoints, n_keypoints,
                             weights, radius, table_ry, table_rx, 0.f, bin_mask, nullptr, nullptr, stream);
-}
-
-extern "C" int fc_orientation_bins_packed(const uint32_t* magnitude_bin, int batch, int height, int width,
-                                          const int32_t* keypoints, int n_keypoints, const float* weights, int radius,
-                                          int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
-  return launch_orientation(magnitude_bin, nullptr, FC_F32, kOriPacked, batch, height, width, keypoints, n_keypoints, weights,
-                            radius, table_ry, table_rx, 0.f, bin_mask, nullptr, nullptr, stream);
 }
 
 extern "C" int fc_orientation_bins_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* keypoints,
@@ -969,13 +1003,12 @@ static int launch_descriptors(const void* magnitude, const void* direction, int 
   place.scale = placement ? placement->scale : 0;
   if (placement && ((reinterpret_cast<uintptr_t>(placement->remap) | reinterpret_cast<uintptr_t>(placement->points)) & 7))
     return FC_ERR_BAD_ARG;
-  const bool interleaved = layout == kDescInterleaved, coded = layout == kDescCoded;
+  const bool coded = layout == kDescCoded;
   if (!magnitude || (layout == kDescPlanes && !direction) || !gmask || !trig || batch <= 0 || height <= 0 || width <= 0) return FC_ERR_BAD_ARG;
   if (n_oriented == 0) return FC_OK;
   if (!oriented || !descriptors || n_oriented < 0) return FC_ERR_BAD_ARG;
   if ((int64_t)height * width > 0x3fffffffLL) return FC_ERR_UNSUPPORTED;  // kernels index one image plane with int32
   if (reinterpret_cast<uintptr_t>(oriented) & 15) return FC_ERR_BAD_ARG;
-  if (interleaved && (reinterpret_cast<uintptr_t>(magnitude) & 7)) return FC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   // persistent grid: as many CTAs as are resident at once (occupancy query per instantiation), fewer when there is less work
   static int n_sm = 0;
@@ -994,19 +1027,31 @@ static int launch_descriptors(const void* magnitude, const void* direction, int 
     descriptor_kernel<T, OUT, IL><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
                                                                      width, oriented, n_oriented, gmask, trig, (OUT*)descriptors, place); \
   } while (0)
-  if (coded && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescCoded);
+#define FC_LAUNCH_PATCH(OUT)                                                                                        \
+  do {                                                                                                            \
+    static int per_sm = 0;                                                                                        \
+    if (per_sm == 0)                                                                                              \
+      FC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descriptor_patch_kernel<OUT>, kDescWarps * 32, 0)); \
+    const int want = div_up(n_oriented, kDescWarps);                                                              \
+    const int blocks = want < n_sm * per_sm ? want : n_sm * per_sm;                                               \
+    descriptor_patch_kernel<OUT><<<blocks, kDescWarps * 32, 0, st>>>((const uint32_t*)magnitude, height, width, oriented, \
+                                                                    n_oriented, gmask, trig, (OUT*)descriptors, place); \
+  } while (0)
+  const bool patch_ok = coded && (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(magnitude) & 15) == 0);
+  if (patch_ok && out_dtype == FC_F32) FC_LAUNCH_PATCH(float);
+  else if (patch_ok && out_dtype == FC_F64) FC_LAUNCH_PATCH(double);
+  else if (patch_ok && out_dtype == FC_F16) FC_LAUNCH_PATCH(__half);
+  else if (coded && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescCoded);
   else if (coded && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescCoded);
   else if (coded && out_dtype == FC_F16) FC_LAUNCH(float, __half, kDescCoded);
   else if (coded) return FC_ERR_BAD_ARG;
-  else if (interleaved && dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescInterleaved);
-  else if (interleaved && dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescInterleaved);
-  else if (interleaved) return FC_ERR_BAD_ARG;
   else if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescPlanes);
   else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescPlanes);
   else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float, kDescPlanes);
   else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double, kDescPlanes);
   else return FC_ERR_BAD_ARG;
 #undef FC_LAUNCH
+#undef FC_LAUNCH_PATCH
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
@@ -1017,13 +1062,6 @@ extern "C" int fc_descriptors(const void* magnitude, const void* direction, int 
                               void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream) {
   return launch_descriptors(magnitude, direction, kDescPlanes, dtype, batch, height, width, oriented, n_oriented, gmask, trig,
                             descriptors, out_dtype, placement, stream);
-}
-
-extern "C" int fc_descriptors_interleaved(const void* magnitude_direction, int batch, int height, int width,
-                                          const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
-                                          void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream) {
-  return launch_descriptors(magnitude_direction, nullptr, kDescInterleaved, FC_F32, batch, height, width, oriented, n_oriented,
-                            gmask, trig, descriptors, out_dtype, placement, stream);
 }
 
 extern "C" int fc_descriptors_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* oriented,

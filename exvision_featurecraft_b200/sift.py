@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import base_ptr, ptr, read_int, read_ints_at, read_last_ints, require_cuda, scan_scratch, stream_ptr, to_device
+from .device import ptr, read_int, read_ints_at, read_last_ints, require_cuda, scan_scratch, stream_ptr, to_device
 
 
 @dataclass(frozen=True)
@@ -40,22 +40,23 @@ class SiftParams:
     #   "mixed" (production): float32 bulk arithmetic with every discrete decision certified -- an extremum, an
     #           orientation bin or a descriptor bin is taken from float32 values only when their error bound cannot
     #           change it, and is otherwise re-evaluated on float64 values: the keypoint lists are the float64 path's;
-    #   "f64":  everything in float64 (the reference's arithmetic);
-    #   "f32":  plain float32, no certification (tolerance-level parity only).
+    #   "f64":  everything in float64 (the reference's arithmetic).
+    # (An uncertified float32 mode existed in round 1: ~1 % of its descriptors had a sample on the wrong side of a bin
+    # edge and a few dozen extrema per image flipped; certified mode costs 35 % more time and has neither.)
     dtype: str = "mixed"
 
     def __post_init__(self):
-        if self.dtype not in ("mixed", "f64", "f32"):
-            raise ValueError("dtype must be 'mixed', 'f64' or 'f32'")
+        if self.dtype not in ("mixed", "f64"):
+            raise ValueError("dtype must be 'mixed' or 'f64'")
 
     @property
     def torch_dtype(self):
-        """element type of the octave base images"""
-        return torch.float32 if self.dtype == "f32" else torch.float64
+        """element type of the octave base images (both modes start from the float64 base)"""
+        return torch.float64
 
     @property
     def fc_dtype(self):
-        return _lib.FC_F32 if self.dtype == "f32" else _lib.FC_F64
+        return _lib.FC_F64
 
     @property
     def n_levels(self):
@@ -289,11 +290,7 @@ def _as_base_batch(base, params: SiftParams) -> torch.Tensor:
         t = t.unsqueeze(0)
     if t.dim() != 3:
         raise ValueError("expected [H,W] or [B,H,W] grayscale base images")
-    if t.dtype == torch.float64 and params.dtype == "f32":
-        out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
-        _lib.call("fc_convert_f64", ptr(t.contiguous()), C.c_int64(t.numel()), _lib.FC_F32, ptr(out), stream_ptr())
-        return out
-    return t.to(params.torch_dtype).contiguous()
+    return t.to(torch.float64).contiguous()
 
 
 def upsample2(gray, params: SiftParams) -> torch.Tensor:
@@ -486,23 +483,14 @@ def keypoints_from_mask(mask: torch.Tensor, width: int) -> torch.Tensor:
 
 
 def gradient_field(octv: Octave, level: int, params: SiftParams):
-    """sift_gradient of one level -> (magnitude, direction, orientation operand).
-
-    f64 mode: three dense planes (the uint8 bin plane is the orientation operand).  f32 mode: magnitude and direction
-    are the two halves of ONE interleaved [b, h, w, 2] plane (returned as strided views, so that a descriptor sample
-    is a single 8-byte gather) and the orientation operand is the packed magnitude|bin int32 plane.  (Certified mode
-    uses gradient_codes instead.)"""
+    """sift_gradient of one level of a float64 (or float32) stack -> (magnitude, direction, uint8 orientation bins), three
+    dense planes.  (Certified mode uses gradient_codes on its float64 levels instead.)"""
     b, L, h, w = octv.gauss.shape
-    if octv.gauss.dtype == torch.float32:
-        md = torch.empty((b, h, w, 2), dtype=torch.float32, device=octv.gauss.device)
-        packed = torch.empty((b, h, w), dtype=torch.int32, device=md.device)
-        _lib.call("fc_gradient_field_packed", ptr(octv.gauss), b, L, level, h, w, ptr(md), ptr(packed), stream_ptr())
-        return md[..., 0], md[..., 1], packed
+    fc = _lib.FC_F32 if octv.gauss.dtype == torch.float32 else _lib.FC_F64
     mag = torch.empty((b, h, w), dtype=octv.gauss.dtype, device=octv.gauss.device)
     direction = torch.empty_like(mag)
     obin = torch.empty((b, h, w), dtype=torch.uint8, device=mag.device)
-    _lib.call("fc_gradient_field", ptr(octv.gauss), _lib.FC_F64, b, L, level, h, w, ptr(mag), ptr(direction), ptr(obin),
-              stream_ptr())
+    _lib.call("fc_gradient_field", ptr(octv.gauss), fc, b, L, level, h, w, ptr(mag), ptr(direction), ptr(obin), stream_ptr())
     return mag, direction, obin
 
 
@@ -537,17 +525,12 @@ def orientation_tolerance(radius: int) -> float:
 
 
 def orientation_bins(mag, obin, keypoints, n, sigma, bin_mask):
-    """Launch the 36-bin histogram kernel on whichever orientation operand gradient_field produced."""
+    """Launch the 36-bin histogram kernel on gradient_field's magnitude / bin planes."""
     b, h, w = mag.shape
-    if obin.dtype == torch.int32:
-        radius, ry, rx, weights = _orientation_weights(sigma, h, w, torch.float32)
-        _lib.call("fc_orientation_bins_packed", ptr(obin), b, h, w, ptr(keypoints), n, ptr(weights), radius, ry, rx, ptr(bin_mask),
-                  stream_ptr())
-    else:
-        fc = _lib.FC_F32 if mag.dtype == torch.float32 else _lib.FC_F64
-        radius, ry, rx, weights = _orientation_weights(sigma, h, w, mag.dtype)
-        _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), fc, b, h, w, ptr(keypoints), n, ptr(weights), radius, ry, rx,
-                  ptr(bin_mask), stream_ptr())
+    fc = _lib.FC_F32 if mag.dtype == torch.float32 else _lib.FC_F64
+    radius, ry, rx, weights = _orientation_weights(sigma, h, w, mag.dtype)
+    _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), fc, b, h, w, ptr(keypoints), n, ptr(weights), radius, ry, rx,
+              ptr(bin_mask), stream_ptr())
 
 
 def orientation_bins_certified(levels64, plane, codes, keypoints, n, sigma, bin_mask, recheck_list, recheck_count):
@@ -584,8 +567,8 @@ _FC_OUT = {torch.float32: _lib.FC_F32, torch.float64: _lib.FC_F64, torch.float16
 
 
 def describe(mag, direction, oriented, sigma, params: SiftParams, out_dtype=torch.float32, out=None, placement=None) -> torch.Tensor:
-    """extract_sift_descriptors for one (octave, scale): -> [m,128].  mag = certified mode's code plane (int32),
-    the interleaved float32 plane's magnitude half, or a dense magnitude plane (with `direction`).
+    """extract_sift_descriptors for one (octave, scale): -> [m,128].  mag = certified mode's code plane (int32) or a
+    dense magnitude plane (with `direction`).
     out / placement: write into the rows of `out` that the fc_desc_placement (an _lib.DescPlacement) selects."""
     m = oriented.shape[0]
     desc = out if out is not None else torch.empty((m, 128), dtype=out_dtype, device=mag.device)
@@ -601,10 +584,6 @@ def describe(mag, direction, oriented, sigma, params: SiftParams, out_dtype=torc
                   stream_ptr())
     elif desc.dtype == torch.float16:
         raise _lib.FeatureCraftError("float16 descriptor export is implemented for the certified (mixed) pipeline")
-    elif mag.stride(-1) == 2:  # halves of gradient_field's interleaved plane: mag.data_ptr() is the plane itself
-        assert direction.data_ptr() == mag.data_ptr() + mag.element_size()
-        _lib.call("fc_descriptors_interleaved", base_ptr(mag), b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig), ptr(desc), out_fc,
-                  pl, stream_ptr())
     else:
         fc = _lib.FC_F32 if mag.dtype == torch.float32 else _lib.FC_F64
         _lib.call("fc_descriptors", ptr(mag), ptr(direction), fc, b, h, w, ptr(oriented), m, ptr(gmask), ptr(trig),

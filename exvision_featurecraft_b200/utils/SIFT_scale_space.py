@@ -3,8 +3,7 @@
 numpy in, numpy / Python lists out -- like the reference.  ``DTYPE`` selects the arithmetic (see
 ``sift.SiftParams.dtype``): "mixed" (default) = the certified pipeline for the end-to-end drivers
 (computeKeypointsAndDescriptors, apply_sift), whose keypoint lists equal the float64 path's; the stage-level
-functions of this module return the reference's float64 images and therefore run in float64 unless
-``set_dtype("f32")`` asks for plain float32.  ``VARIANT`` selects the keypoint filter: "app" (this module in the
+functions of this module return the reference's float64 images and therefore always run in float64.  ``VARIANT`` selects the keypoint filter: "app" (this module in the
 reference keeps every extremum, :89-105) or "script" (implementation_without_ui/SIFT/SIFT.py:202-215).
 """
 from __future__ import annotations
@@ -21,13 +20,13 @@ VARIANT = "app"
 
 def set_dtype(dtype: str) -> None:
     global DTYPE
-    assert dtype in ("mixed", "f32", "f64")
+    assert dtype in ("mixed", "f64")
     DTYPE = dtype
 
 
 def stage_dtype() -> str:
     """arithmetic of the stage-level mirrors: they hand float64 images back to the caller like the reference does"""
-    return "f32" if DTYPE == "f32" else "f64"
+    return "f64"
 
 
 def set_variant(variant: str) -> None:
@@ -71,8 +70,7 @@ def _extrema_to_list(mask_k: torch.Tensor, width: int, k: int):
 
 def get_keypoints(DOG_octave, k, contrast_th, ratio_th, DoG_full_array):
     """:60-106 (app) / SIFT.py:172-222 (script): 3x3x3 extrema of the middle of three DoG images."""
-    fc_dtype = _lib.FC_F32 if stage_dtype() == "f32" else _lib.FC_F64
-    tdt = torch.float32 if stage_dtype() == "f32" else torch.float64
+    fc_dtype, tdt = _lib.FC_F64, torch.float64
     if VARIANT == "script":
         # the reference passes an (H, W, n) array (:155); a list of 2-D images is accepted too
         if isinstance(DoG_full_array, np.ndarray) and DoG_full_array.ndim == 3:
@@ -116,9 +114,6 @@ def generate_gaussian_images_in_octave(image, gaussian_kernels, contrast_th, rat
     g = octv.gauss[0].to(torch.float64).cpu().numpy()
     gaussians = [g[i] for i in range(g.shape[0])]
     dogs = [gaussians[i + 1] - gaussians[i] for i in range(len(gaussians) - 1)]
-    if stage_dtype() == "f32":
-        gf = octv.gauss[0]
-        dogs = [(gf[i + 1] - gf[i]).to(torch.float64).cpu().numpy() for i in range(gf.shape[0] - 1)]
     keypoints = []
     for k in range(1, len(taps) - 2):
         keypoints.extend(_extrema_to_list(octv.extrema[k - 1], octv.width, k))

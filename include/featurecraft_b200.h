@@ -42,7 +42,7 @@ typedef enum fc_status {
   FC_ERR_UNSUPPORTED = -4
 } fc_status;
 
-/* element type of the SIFT scale space (FC_F32 = production layout, FC_F64 = exact-parity mode) */
+/* element type of a scale-space stack (FC_F32: the bulk stack of certified mode, FC_F64: the float64 mode) */
 typedef enum fc_dtype { FC_F32 = 0, FC_F64 = 1, FC_F16 = 2 /* descriptor export only */ } fc_dtype;
 
 /* keypoint filter: FC_FILTER_APP keeps every extremum (APP/utils/SIFT_scale_space.py:89-105),
@@ -261,13 +261,6 @@ FC_API int fc_extrema_repair(const double* base, int first_is_identity, const do
 FC_API int fc_gradient_field(const void* gauss, int dtype, int batch, int n_levels, int level, int height, int width,
                       void* magnitude, void* direction, uint8_t* orientation_bin, void* stream);
 
-/* The same gradient field laid out for the float32 pipeline's gathers:
- * magnitude_direction[b][y][x] = (magnitude, direction) as interleaved float32 pairs (one 8-byte gather per
- * descriptor sample), magnitude_bin[b][y][x] = (bits of magnitude rounded to 18 mantissa bits) | orientation_bin
- * in the low 6 bits (one 4-byte gather per orientation sample). */
-FC_API int fc_gradient_field_packed(const void* gauss, int batch, int n_levels, int level, int height, int width,
-                             void* magnitude_direction, uint32_t* magnitude_bin, void* stream);
-
 /* Certified mode's gradient field of plane `plane` of a float64 [batch][n_planes][h][w] stack: one word per pixel,
  *   bits 5..0  the reference's orientation bin np.round(direction * 36 / 360) (:140-142; 0..36),
  *   bits 7..6  which side of the bin centre the direction lies on (0 below, 1 at / above, 2 exactly on the upper
@@ -287,10 +280,6 @@ FC_API int fc_gradient_codes(const double* levels, int batch, int n_planes, int 
 FC_API int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
                         int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
                         int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
-/* float32 pipeline: the same histograms from fc_gradient_field_packed's words (weights float32). */
-FC_API int fc_orientation_bins_packed(const uint32_t* magnitude_bin, int batch, int height, int width,
-                               const int32_t* keypoints, int n_keypoints, const float* weights, int radius,
-                               int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
 /* certified mode: float32 histograms from fc_gradient_codes' words; a keypoint with a bin within
  * tolerance * max of the cut gets bit 63 of its mask set instead of a decision and its index appended to
  * recheck_list (int32 [n_keypoints]; recheck_count[0] is zeroed first) ... */
@@ -337,11 +326,6 @@ typedef struct fc_desc_placement {
 FC_API int fc_descriptors(const void* magnitude, const void* direction, int dtype, int batch, int height, int width,
                    const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
                    void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream);
-/* float32 pipeline: the same descriptors from fc_gradient_field_packed's interleaved (magnitude, direction) plane. */
-FC_API int fc_descriptors_interleaved(const void* magnitude_direction, int batch, int height, int width,
-                               const int32_t* oriented, int n_oriented, const double* gmask, const double* trig,
-                               void* descriptors, int out_dtype, const fc_desc_placement* placement, void* stream);
-
 /* remap tables ([n_blocks][batch][2] int32) and per-image totals ([batch] int32) for fc_desc_placement, from the
  * pipeline's two scans: row_offsets = cumulative keypoints over the concatenated mask rows of all blocks (block i
  * starts at row block_row_start_host[i] and has block_height_host[i] rows per image), oriented_offsets = cumulative

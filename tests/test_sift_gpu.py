@@ -3,8 +3,7 @@ the golden vectors produced by the unmodified reference.
 
 f64 mode reproduces the reference's float64 arithmetic up to summation order (separable instead of
 direct 2-D convolution: <= 1e-14), so every discrete output (extrema, orientation bins, keypoint
-list) must be IDENTICAL; f32 mode (production layout) is held to BASELINE.json's tolerances:
-responses 1e-4 relative, keypoints 0.5 px, descriptors 1e-3 L2."""
+list) must be IDENTICAL.  The benchmarked certified mode is held to the same bar in test_sift_mixed_gpu.py."""
 import numpy as np
 import pytest
 import torch
@@ -64,27 +63,6 @@ def test_scale_space_script_filter(S, case):
             assert np.array_equal(_kps_of(S, octv, k), ref_k[ref_k[:, 2] == k][:, :2]), (o, k)
 
 
-@pytest.mark.parametrize("case", SIFT_CASES)
-def test_scale_space_f32_within_tolerance(S, case):
-    g = load_golden("sift")
-    p = _params(S, g, case, dtype="f32")
-    octs = S.scale_space(g[case + "/base"], p)
-    n_ref = n_common = 0
-    for o, octv in enumerate(octs):
-        ref = g["%s/G_oct%d" % (case, o)]
-        got = octv.gauss[0].cpu().numpy().astype(np.float64)
-        assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()  # north_star: responses within 1e-4 relative
-        assert np.abs(got - ref).max() < 1e-6
-        ref_k = g["%s/kps_oct%d" % (case, o)]
-        for k in range(1, p.s_value + 1):
-            a = set(map(tuple, _kps_of(S, octv, k).tolist()))
-            b = set(map(tuple, ref_k[ref_k[:, 2] == k][:, :2].tolist()))
-            n_ref += len(b)
-            n_common += len(a & b)
-            assert abs(len(a) - len(b)) <= max(2, 0.01 * len(b))
-    assert n_common >= 0.99 * n_ref
-
-
 @pytest.mark.parametrize("kind", ["smooth", "ties"])
 @pytest.mark.parametrize("variant", ["app", "script"])
 def test_extrema_strip_kernel_is_exact(S, kind, variant):
@@ -126,29 +104,16 @@ def test_extrema_strip_kernel_is_exact(S, kind, variant):
 def test_gradient_field(S):
     g = load_golden("sift_pieces")
     img = g["img"]
-    for dt, tol in (("f64", 1e-12), ("f32", 2e-4)):
-        p = S.SiftParams(dtype=dt)
-        t = S._as_base_batch(img, p)
-        octv = S.Octave(t.unsqueeze(1).contiguous(), None, img.shape[0], img.shape[1])
-        mag, direction, obin = S.gradient_field(octv, 0, p)
-        m, d = mag[0].cpu().numpy().astype(np.float64), direction[0].cpu().numpy().astype(np.float64)
-        assert np.abs(m - g["mag"]).max() < (1e-15 if dt == "f64" else 1e-6)
-        dd = np.abs(d - g["direction"])
-        dd = np.minimum(dd, 360 - dd)
-        if dt == "f64":
-            assert dd.max() < tol
-            ref_bin = np.round(g["direction"] * 36 / 360).astype(int)
-            assert (obin[0].cpu().numpy() != ref_bin).mean() < 1e-3
-        else:
-            # angles of near-zero gradients are ill conditioned in float32; compare where |g| is resolvable
-            ok = g["mag"] > 1e-3
-            assert dd[ok].max() < 5e-3
-            # f32 mode returns the orientation operand packed: magnitude (18 mantissa bits) | 36-bin index (low 6 bits)
-            pk = obin[0].cpu().numpy().view(np.uint32)
-            ref_bin = np.round(g["direction"] * 36 / 360).astype(int)
-            assert ((pk & 63) != ref_bin)[ok].mean() < 1e-3
-            pm = (pk & ~np.uint32(63)).view(np.float32).astype(np.float64)
-            assert np.abs(pm - g["mag"]).max() <= 2.0 ** -18 * g["mag"].max() + 1e-6
+    p = S.SiftParams(dtype="f64")
+    t = S._as_base_batch(img, p)
+    octv = S.Octave(t.unsqueeze(1).contiguous(), None, img.shape[0], img.shape[1])
+    mag, direction, obin = S.gradient_field(octv, 0, p)
+    m, d = mag[0].cpu().numpy(), direction[0].cpu().numpy()
+    assert np.abs(m - g["mag"]).max() < 1e-15
+    dd = np.abs(d - g["direction"])
+    assert np.minimum(dd, 360 - dd).max() < 1e-12
+    ref_bin = np.round(g["direction"] * 36 / 360).astype(int)
+    assert (obin[0].cpu().numpy() != ref_bin).mean() < 1e-3
 
 
 def _run_full(S, g, case, dtype):
@@ -167,24 +132,6 @@ def test_full_pipeline_f64_equals_reference(S, case):
     nan_ref = np.isnan(ref_d).any(1)
     assert np.array_equal(np.isnan(desc).any(1), nan_ref)
     assert np.abs(desc[~nan_ref] - ref_d[~nan_ref]).max() < 1e-9
-
-
-@pytest.mark.parametrize("case", SIFT_CASES)
-def test_full_pipeline_f32_within_tolerance(S, case):
-    g = load_golden("sift")
-    pts, desc = _run_full(S, g, case, "f32")
-    ref_p, ref_d = g[case + "/points"], g[case + "/descriptors"]
-    ref_idx = {tuple(r): n for n, r in enumerate(ref_p.tolist())}
-    hit = [(n, ref_idx[tuple(r)]) for n, r in enumerate(pts.tolist()) if tuple(r) in ref_idx]
-    assert len(hit) >= 0.99 * len(ref_p) and len(pts) <= 1.01 * len(ref_p) + 2
-    a = desc[[h[0] for h in hit]]
-    b = ref_d[[h[1] for h in hit]]
-    ok = ~np.isnan(b).any(1) & ~np.isnan(a).any(1)
-    l2 = np.linalg.norm(a[ok] - b[ok], axis=1)
-    # float32 scale space: ~1 % of descriptors see one of their 256 samples flip an orientation bin
-    # (direction within float32 resolution of a 45-degree edge); everything else is ~1e-5
-    assert (l2 < 1e-3).mean() >= 0.98
-    assert np.median(l2) < 1e-5
 
 
 def test_batched_equals_single(S):
@@ -221,7 +168,7 @@ def test_large_image_properties(S):
     from exvision_featurecraft_b200 import synthetic
 
     base = synthetic.sift_image(2048, 2048, seed=2, max_blobs=512)
-    p = S.SiftParams(dtype="f32")
+    p = S.SiftParams(dtype="mixed")
     octs = S.scale_space(base, p)
     assert [tuple(o.gauss.shape[2:]) for o in octs] == [(2048, 2048), (1024, 1024), (512, 512), (256, 256)]
     kern = O.generateGaussianKernels(1.6, 2)
@@ -231,7 +178,8 @@ def test_large_image_properties(S):
         got = octs[0].gauss[0, lvl, 940:1060].cpu().numpy()
         assert np.abs(got - ref).max() < 1e-6
     # octave 1 base is G[2][::2, ::2] of octave 0 and sits unblurred in slot 0
-    assert torch.equal(octs[1].gauss[0, 0], octs[0].gauss[0, 2, ::2, ::2])
+    # octave 1's float32 base is the rounding of the FLOAT64 level 2 of octave 0 (certified mode), not of its float32 twin
+    assert (octs[1].gauss[0, 0] - octs[0].gauss[0, 2, ::2, ::2]).abs().max() < 5e-7
     # a constant image has no extrema (every comparison ties) and G = c * sum(kernel)
     flat = S.scale_space(np.full((128, 160), 0.25), S.SiftParams(dtype="f64"))
     assert int(flat[0].extrema.ne(0).sum()) == 0
