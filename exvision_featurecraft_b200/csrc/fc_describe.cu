@@ -671,45 +671,23 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
   }
 }
 
-// Certified-mode descriptors with the source patch staged in shared memory (the kernel the pipeline launches when
-// the image width is a multiple of 4).  The 256 samples of a keypoint lie within 11 pixels of it; gathering them from
-// global memory costs ~16 cache-line wavefronts per warp load (a rotated 16x16 window touches 10-16 image rows per
-// load instruction, 8 instructions per keypoint: the L1 wavefront rate was the bound).  Here the 23-row x 28-column
-// aligned patch around the keypoint is copied with 16-byte cp.async chunks -- row-coalesced, ~40 wavefronts per
-// keypoint -- into one of two per-warp buffers while the previous keypoint is being evaluated, and the rotated samples
-// are read from shared memory.  Outside the image the patch holds zeros (= cv2.warpAffine's constant border).
-static constexpr int kPatchRows = 23, kPatchCols = 28, kPatchWords = kPatchRows * kPatchCols;
-
-__device__ __forceinline__ void desc_stage_patch(const uint32_t* __restrict__ codes, int H, int W, const int4 kp,
-                                                 uint32_t* __restrict__ buf, int lane) {
-  const uint32_t* img = codes + (size_t)kp.x * H * W;
-  const int py0 = kp.y - 11, px0 = (kp.z - 11) & ~3;
-  for (int i = lane; i < kPatchRows * (kPatchCols / 4); i += 32) {
-    const int r = i / (kPatchCols / 4), c4 = i - r * (kPatchCols / 4);
-    const int y = py0 + r, x = px0 + 4 * c4;
-    uint32_t* dst = buf + r * kPatchCols + 4 * c4;
-    if (y >= 0 && y < H && x >= 0 && x + 3 < W) {
-      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(img + (size_t)y * W + x) : "memory");
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = (y >= 0 && y < H && x + j >= 0 && x + j < W) ? img[(size_t)y * W + x + j] : 0u;
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
+// Certified-mode descriptors, the kernel the pipeline launches.  ncu showed the generic kernel above to be bound by
+// instruction issue (68 % issue-active, ALU pipe 58 %, ~500 warp instructions per keypoint), not by its gathers: with
+// two lanes per 4x4 cell every keypoint pays the per-warp fixed work (window origin, clearing and merging the private
+// bins of two half cells, two 32-lane reductions) for only 8 samples per lane.  Here HALF a warp owns a keypoint and
+// a lane owns a whole cell: 16 samples per lane, no merge step, 16-lane reductions, and the fixed work is shared by
+// two keypoints per warp -- ~300 warp instructions per keypoint.  Arithmetic and summation order per cell (row-major
+// over its 4x4 samples, float32) are otherwise those of descriptor_kernel<float, ., kDescCoded>.
 template <typename OUT>
 __global__ void __launch_bounds__(kDescWarps * 32)
-descriptor_patch_kernel(const uint32_t* __restrict__ codes, int H, int W, const int32_t* __restrict__ oriented, int n_oriented,
+descriptor_coded_kernel(const uint32_t* __restrict__ codes, int H, int W, const int32_t* __restrict__ oriented, int n_oriented,
                         const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc,
                         const DescPlacement place) {
-  __shared__ int sXY[kDescWarps][32];         // x0[0..15], y0[0..15] per warp
+  __shared__ int sXY[kDescWarps][2][32];      // per half warp: x0[0..15], y0[0..15]
   __shared__ float sHist[kDescWarps][9][32];  // per-lane private bins 0..8 (8 = dropped), [bin][lane]: conflict free
   __shared__ float sMask[256];
   __shared__ __align__(16) int sAd[36][16], sBd[36][16];  // rint(cos * x * 1024), rint(sin * x * 1024) per bin
   __shared__ double sCS[36][2];
-  __shared__ __align__(16) uint32_t sPatch[kDescWarps][2][kPatchWords];
   for (int t = threadIdx.x; t < 256; t += kDescWarps * 32) sMask[t] = (float)gmask[t];
   for (int t = threadIdx.x; t < 36 * 16; t += kDescWarps * 32) {
     const int bn = t >> 4, x = t & 15;
@@ -719,110 +697,102 @@ descriptor_patch_kernel(const uint32_t* __restrict__ codes, int H, int W, const 
   if (threadIdx.x < 72) sCS[threadIdx.x >> 1][threadIdx.x & 1] = trig[(threadIdx.x >> 1) * kTrigStride + (threadIdx.x & 1)];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cell = lane >> 1, half = lane & 1;
-  const int cy = (cell >> 2) * 4 + half * 2, cx = (cell & 3) * 4;
+  const int hw = lane >> 4, cell = lane & 15;  // half warp = keypoint slot, lane of it = cell (row-major 4x4)
+  const int cy = (cell >> 2) * 4, cx = (cell & 3) * 4;
   float* myh = &sHist[warp][0][lane];
-  float wmask[2][4];  // this lane's 8 Gaussian weights never change
+  float wmask[4][4];  // this lane's 16 Gaussian weights never change
 #pragma unroll
-  for (int ry = 0; ry < 2; ++ry)
+  for (int ry = 0; ry < 4; ++ry)
 #pragma unroll
     for (int rx = 0; rx < 4; ++rx) wmask[ry][rx] = sMask[(cy + ry) * 16 + cx + rx];
-  const int warps_total = gridDim.x * kDescWarps;
-  const int4* list = reinterpret_cast<const int4*>(oriented);
-  int n = blockIdx.x * kDescWarps + warp;
-  int cur = 0;
-  if (n < n_oriented) desc_stage_patch(codes, H, W, list[n], sPatch[warp][0], lane);
-  for (; n < n_oriented; n += warps_total) {  // no block-wide barrier inside
-    const int4 kp = list[n];
+  const int* xy = sXY[warp][hw];
+  const int pairs_total = gridDim.x * kDescWarps;
+  for (int pair = blockIdx.x * kDescWarps + warp; 2 * pair < n_oriented; pair += pairs_total) {  // no block-wide barrier inside
+    const int n = 2 * pair + hw;
+    const bool valid = n < n_oriented;
+    const int4 kp = reinterpret_cast<const int4*>(oriented)[valid ? n : 2 * pair];
     const int b = kp.x, ki = kp.y, kj = kp.z, bin = kp.w;
     const double cs = sCS[bin][0], sn = sCS[bin][1];
     {
       // rotated_subimage: v_x = (c, s), v_y = (-s, c); s_x = j - c*7.5 - (-s)*7.5; s_y = i - s*7.5 - c*7.5
-      // X0[y] = rint((M01*y + M02) * 1024) + 512 ; Y0[y] = rint((M11*y + M12) * 1024) + 512
-      const double yy = (double)(lane & 15);
-      double a;
-      if (lane < 16) a = __dadd_rn(__dmul_rn(-sn, yy), __dsub_rn(__dsub_rn((double)kj, __dmul_rn(cs, 7.5)), __dmul_rn(-sn, 7.5)));
-      else a = __dadd_rn(__dmul_rn(cs, yy), __dsub_rn(__dsub_rn((double)ki, __dmul_rn(sn, 7.5)), __dmul_rn(cs, 7.5)));
-      sXY[warp][lane] = __double2int_rn(__dmul_rn(a, 1024.0)) + 512;
+      // X0[y] = rint((M01*y + M02) * 1024) + 512 ; Y0[y] = rint((M11*y + M12) * 1024) + 512   (lane `cell` does row y = cell)
+      const double yy = (double)cell;
+      const double ax = __dadd_rn(__dmul_rn(-sn, yy), __dsub_rn(__dsub_rn((double)kj, __dmul_rn(cs, 7.5)), __dmul_rn(-sn, 7.5)));
+      const double ay = __dadd_rn(__dmul_rn(cs, yy), __dsub_rn(__dsub_rn((double)ki, __dmul_rn(sn, 7.5)), __dmul_rn(cs, 7.5)));
+      sXY[warp][hw][cell] = __double2int_rn(__dmul_rn(ax, 1024.0)) + 512;
+      sXY[warp][hw][16 + cell] = __double2int_rn(__dmul_rn(ay, 1024.0)) + 512;
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) myh[k * 32] = 0.f;
-    // request the next keypoint's patch, then wait for this one's
-    if (n + warps_total < n_oriented) {
-      desc_stage_patch(codes, H, W, list[n + warps_total], sPatch[warp][cur ^ 1], lane);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
     __syncwarp();
-    const uint32_t* patch = sPatch[warp][cur];
-    cur ^= 1;
-    const int py0 = ki - 11, px0 = (kj - 11) & ~3;
+    const uint32_t* m = codes + (size_t)b * H * W;
     const int4 ad4 = *reinterpret_cast<const int4*>(&sAd[bin][cx]);
     const int4 bd4 = *reinterpret_cast<const int4*>(&sBd[bin][cx]);
     const int ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w}, bd[4] = {bd4.x, bd4.y, bd4.z, bd4.w};
-    uint32_t pv[2][4];
+    const int cb = 2 * bin + 2;
+    // the rotated 16x16 window reaches at most 7.5 * sqrt(2) + 1 < 12 pixels from the keypoint
+    const bool interior = (ki >= 12) && (ki < H - 12) && (kj >= 12) && (kj < W - 12);
+    uint32_t pv[4][4];  // all 16 gathers of the lane are issued before the first dependent histogram update
 #pragma unroll
-    for (int ry = 0; ry < 2; ++ry) {
-      const int X0 = sXY[warp][cy + ry], Y0 = sXY[warp][16 + cy + ry];
+    for (int ry = 0; ry < 4; ++ry) {
+      const int X0 = xy[cy + ry], Y0 = xy[16 + cy + ry];
 #pragma unroll
       for (int rx = 0; rx < 4; ++rx) {
-        const int px = ((X0 + ad[rx]) >> 10) - px0;
-        const int py = ((Y0 + bd[rx]) >> 10) - py0;
-        // |offset| <= 7.5 * sqrt(2) + rounding < 11.2: always inside the patch; the test only guards the arithmetic
-        const bool ok = (unsigned)px < (unsigned)kPatchCols && (unsigned)py < (unsigned)kPatchRows;
-        pv[ry][rx] = ok ? patch[py * kPatchCols + px] : 0u;
+        const int X = (X0 + ad[rx]) >> 10;
+        const int Y = (Y0 + bd[rx]) >> 10;
+        const bool in = interior || (((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H));
+        pv[ry][rx] = in ? m[Y * W + X] : 0u;  // one image plane has fewer than 2^30 pixels (checked on the host)
       }
     }
 #pragma unroll
-    for (int ry = 0; ry < 2; ++ry) {
+    for (int ry = 0; ry < 4; ++ry) {
 #pragma unroll
       for (int rx = 0; rx < 4; ++rx) {
         const uint32_t p = pv[ry][rx];
         const float wv = __fmul_rn(__uint_as_float((p & ~255u) >> 1), wmask[ry][rx]);
-        int sc = 2 * (int)(p & 63u) - 1 + (int)((p >> 6) & 3u) - (2 * bin + 1);  // sector of (direction - theta), in [-72, 72]
+        int sc = 2 * (int)(p & 63u) + (int)((p >> 6) & 3u) - cb;  // sector of (direction - theta), in [-72, 72]
         sc += sc < 0 ? 72 : 0;
         sc -= sc >= 72 ? 72 : 0;
         myh[((sc * 57) >> 9) * 32] += wv;  // sc / 9 for 0 <= sc < 72
       }
     }
-    __syncwarp();
-    // merge the two halves of the cell (rows 0-1 then rows 2-3), round to float32 like the reference's cell hist;
-    // normalise / clip [2^-10, 0.2] / normalise (:281-287)
-    float f[4];
+    // normalise / clip [2^-10, 0.2] / normalise (:281-287); sums over the 16 lanes of the half warp
+    float f[8];
+    float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float mine = myh[k * 32];
-      const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-      const float sum = half ? __fadd_rn(other, mine) : __fadd_rn(mine, other);
-      if ((k >> 2) == half) f[k & 3] = sum;  // even lane keeps bins 0..3, odd lane bins 4..7 of the cell
+      f[k] = myh[k * 32];
+      ss = fmaf(f[k], f[k], ss);
     }
-    float ss = f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float lo = 0.0009765625f, hi = 0.2f;  // np.finfo(np.float16).eps, 0.2
     const float inv = rsqrtf(ss);               // 0 * inf = NaN for an all-zero window, like the reference's 0 / 0
     float s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       float v = f[k] * inv;
       if (v == v) v = v < lo ? lo : (v > hi ? hi : v);  // np.clip keeps NaN
       f[k] = v;
-      s2 += v * v;
+      s2 = fmaf(v, v, s2);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    size_t row = (size_t)n;
-    if (place.remap) {
-      const int2 rm = place.remap[b];
-      row = (size_t)(rm.y + (place.list_base + n - rm.x));
+    for (int o = 8; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (valid) {
+      size_t row = (size_t)n;
+      if (place.remap) {
+        const int2 rm = place.remap[b];
+        row = (size_t)(rm.y + (place.list_base + n - rm.x));
+      }
+      if (place.points && cell == 0)
+        place.points[row] = make_uint2(((uint32_t)ki & 0xffffu) | ((uint32_t)kj << 16),
+                                       (uint32_t)place.octave | ((uint32_t)place.scale << 8) | ((uint32_t)bin << 16));
+      const float inv2 = rsqrtf(s2);
+      OUT* dst = desc + row * 128 + cell * 8;
+      Store4<OUT>::put(dst, f[0] * inv2, f[1] * inv2, f[2] * inv2, f[3] * inv2);
+      Store4<OUT>::put(dst + 4, f[4] * inv2, f[5] * inv2, f[6] * inv2, f[7] * inv2);
     }
-    if (place.points && lane == 0)
-      place.points[row] = make_uint2(((uint32_t)ki & 0xffffu) | ((uint32_t)kj << 16),
-                                     (uint32_t)place.octave | ((uint32_t)place.scale << 8) | ((uint32_t)bin << 16));
-    const float inv2 = rsqrtf(s2);
-    Store4<OUT>::put(desc + row * 128 + lane * 4, f[0] * inv2, f[1] * inv2, f[2] * inv2, f[3] * inv2);
-    __syncwarp();  // the next keypoint rewrites sXY, the private bins and (one step later) this patch buffer
+    __syncwarp();  // the next pair rewrites sXY and the private bins
   }
 }
 
@@ -1027,23 +997,19 @@ static int launch_descriptors(const void* magnitude, const void* direction, int 
     descriptor_kernel<T, OUT, IL><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
                                                                      width, oriented, n_oriented, gmask, trig, (OUT*)descriptors, place); \
   } while (0)
-#define FC_LAUNCH_PATCH(OUT)                                                                                        \
+#define FC_LAUNCH_CODED(OUT)                                                                                        \
   do {                                                                                                            \
     static int per_sm = 0;                                                                                        \
     if (per_sm == 0)                                                                                              \
-      FC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descriptor_patch_kernel<OUT>, kDescWarps * 32, 0)); \
-    const int want = div_up(n_oriented, kDescWarps);                                                              \
+      FC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descriptor_coded_kernel<OUT>, kDescWarps * 32, 0)); \
+    const int want = div_up(div_up(n_oriented, 2), kDescWarps);                                                   \
     const int blocks = want < n_sm * per_sm ? want : n_sm * per_sm;                                               \
-    descriptor_patch_kernel<OUT><<<blocks, kDescWarps * 32, 0, st>>>((const uint32_t*)magnitude, height, width, oriented, \
+    descriptor_coded_kernel<OUT><<<blocks, kDescWarps * 32, 0, st>>>((const uint32_t*)magnitude, height, width, oriented, \
                                                                     n_oriented, gmask, trig, (OUT*)descriptors, place); \
   } while (0)
-  const bool patch_ok = coded && (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(magnitude) & 15) == 0);
-  if (patch_ok && out_dtype == FC_F32) FC_LAUNCH_PATCH(float);
-  else if (patch_ok && out_dtype == FC_F64) FC_LAUNCH_PATCH(double);
-  else if (patch_ok && out_dtype == FC_F16) FC_LAUNCH_PATCH(__half);
-  else if (coded && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescCoded);
-  else if (coded && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescCoded);
-  else if (coded && out_dtype == FC_F16) FC_LAUNCH(float, __half, kDescCoded);
+  if (coded && out_dtype == FC_F32) FC_LAUNCH_CODED(float);
+  else if (coded && out_dtype == FC_F64) FC_LAUNCH_CODED(double);
+  else if (coded && out_dtype == FC_F16) FC_LAUNCH_CODED(__half);
   else if (coded) return FC_ERR_BAD_ARG;
   else if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescPlanes);
   else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescPlanes);
@@ -1051,7 +1017,7 @@ static int launch_descriptors(const void* magnitude, const void* direction, int 
   else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double, kDescPlanes);
   else return FC_ERR_BAD_ARG;
 #undef FC_LAUNCH
-#undef FC_LAUNCH_PATCH
+#undef FC_LAUNCH_CODED
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
