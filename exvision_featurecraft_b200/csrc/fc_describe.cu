@@ -241,36 +241,65 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   const int rounds = (c1 - c0 + LPK) / LPK;
   T* hme = h + sub;
   if (rounds <= NR) {
+    // Per-lane base pointers advance by whole rows, so that every sample of the unrolled (NROWS x NR) block is a load
+    // with an immediate offset under a predicate: ncu counted 33 instructions per sample when the addresses were formed
+    // as r * W + c per sample (8 IMAD + 4 LEA of them), most of them 64-bit address arithmetic.
+    const int cb = c0 + sub;
+    bool cok[NR];
+#pragma unroll
+    for (int u = 0; u < NR; ++u) cok[u] = cb + u * LPK <= c1;
+    const ptrdiff_t first = (ptrdiff_t)r0 * W + cb;
+    const uint32_t* prow = pk + first;
+    const T* mrow = m + first;
+    const uint8_t* orow = PACKED ? nullptr : ob + first;
+    const T* wrow = weights + (woff + r0 * side + cb);
     for (int rr = r0; rr <= r1; rr += NROWS) {
       int bins[NROWS][NR];
       T ws[NROWS][NR];
 #pragma unroll
       for (int v = 0; v < NROWS; ++v) {
-        const int r = rr + v;
-        const bool row_ok = r <= r1;
-        const int ro = r * W;
-        const int wo = woff + r * side;
+        const bool row_ok = rr + v <= r1;
+        const T* wv = wrow + v * side;
 #pragma unroll
         for (int u = 0; u < NR; ++u) {
-          const int c = c0 + sub + u * LPK;
           bins[v][u] = kOriBins;  // the dropped bin
           ws[v][u] = T(0);
-          if (row_ok && c <= c1) {
+          if (row_ok && cok[u]) {
             if constexpr (PACKED) {
-              const uint32_t p = pk[ro + c];
+              const uint32_t p = (prow + (ptrdiff_t)v * W)[u * LPK];
               bins[v][u] = (int)(p & 63u);
-              ws[v][u] = (T)__fmul_rn(__uint_as_float((p & ~255u) >> 1), (float)weights[wo + c]);
+              ws[v][u] = (T)__fmul_rn(__uint_as_float((p & ~255u) >> 1), (float)wv[u * LPK]);
             } else {
-              bins[v][u] = ob[ro + c];
-              ws[v][u] = Math<T>::mul(m[ro + c], weights[wo + c]);
+              bins[v][u] = (orow + (ptrdiff_t)v * W)[u * LPK];
+              ws[v][u] = Math<T>::mul((mrow + (ptrdiff_t)v * W)[u * LPK], wv[u * LPK]);
             }
           }
         }
       }
+      prow += (ptrdiff_t)NROWS * W;
+      mrow += (ptrdiff_t)NROWS * W;
+      if (!PACKED) orow += (ptrdiff_t)NROWS * W;
+      wrow += NROWS * side;
+      if constexpr (PACKED && sizeof(T) == 4) {
+        // private bin of this lane: one shift-add on the 32-bit shared address (the compiler otherwise rebuilds
+        // (sub + bin * PITCH) * 4 + base for every sample); bin 36 is accumulated but never read
+        const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(hme);
 #pragma unroll
-      for (int v = 0; v < NROWS; ++v)
+        for (int v = 0; v < NROWS; ++v)
 #pragma unroll
-        for (int u = 0; u < NR; ++u) hme[bins[v][u] * PITCH] += ws[v][u];  // bin 36 is accumulated but never read
+          for (int u = 0; u < NR; ++u) {
+            const uint32_t a = hbase + ((uint32_t)bins[v][u] << (2 + (LPK == 8 ? 3 : (LPK == 16 ? 4 : 5))));
+            float cur;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur) : "r"(a));
+            cur = __fadd_rn(cur, (float)ws[v][u]);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(cur) : "memory");
+          }
+      } else {
+#pragma unroll
+        for (int v = 0; v < NROWS; ++v)
+#pragma unroll
+          for (int u = 0; u < NR; ++u) hme[bins[v][u] * PITCH] += ws[v][u];  // bin 36 is accumulated but never read
+      }
     }
   } else {
     // window wider than the class was sized for (only reachable through the C ABI with a hand-picked radius)
