@@ -256,6 +256,19 @@ class MatchWorkload:
         return "%d tasks of 2048 x 8192 descriptors: float32 brute force + ratio test of the oracle (cv2.BFMatcher's arithmetic)" % n
 
 
+def ring_block(n, rank):
+    """Descriptor block of one rank for the all-pairs workload: noisy copies of rows of ONE base set every rank
+    generates identically, so that true matches exist between any two ranks' blocks (unrelated random blocks would
+    make every ratio test fail and the ring check vacuous)."""
+    base = np.abs(np.random.default_rng(1234).standard_normal((n, 128), dtype=np.float32))
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    rng = np.random.default_rng(500 + rank)
+    rows = rng.permutation(n)
+    a = base[rows] + rng.normal(0, 0.01, (n, 128)).astype(np.float32)
+    a[::3] = np.abs(rng.standard_normal((len(a[::3]), 128), dtype=np.float32)) / 11.3  # a third without a partner
+    return np.ascontiguousarray(a)
+
+
 class AllPairsWorkload(MatchWorkload):
     """BASELINE configs[4] matching leg, scaled: every rank keeps its block of descriptors resident and matches it
     against the block of every rank; the blocks travel around a ring of NCCL send/recv (sharding.all_pairs_match).
@@ -278,17 +291,19 @@ class AllPairsWorkload(MatchWorkload):
         return self.nq * self.nt * self.world / 1e9
 
     def setup(self, rank, torch):
-        super().setup(rank, torch)
-        from exvision_featurecraft_b200 import sharding
+        from exvision_featurecraft_b200 import matching, sharding
 
-        self.sharding = sharding
+        self.torch, self.matching, self.sharding = torch, matching, sharding
         self.world = sharding.world_info()[1]
+        self.host_a = torch.from_numpy(ring_block(self.nq, rank)).pin_memory()
+        self.a = self.host_a.cuda()
+        self.ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(64)]
+        self.ev_i = 0
         # before anything is timed: the ring's answer for the LAST block to arrive (it crossed world-1 hops) must be the
         # exact engine's answer for that pair of blocks
         res = self._run()
         train_rank, (idx, dist, good) = res[-1]
-        a_t, _ = match_sets(self.nq, self.nt, train_rank)
-        ei, ed, eg = self.matching.knn2(self.a, torch.from_numpy(a_t).cuda(), 0.3, "exact")
+        ei, ed, eg = self.matching.knn2(self.a, torch.from_numpy(ring_block(self.nq, train_rank)).cuda(), 0.3, "exact")
         g = eg.nonzero().flatten()
         assert torch.equal(good, eg) and torch.equal(idx[g, 0], ei[g, 0]), "ring all-pairs result differs from the exact engine"
         self.verified = {"train_rank": int(train_rank), "good": int(g.numel()), "equal_to_exact_engine": True}

@@ -11,6 +11,10 @@
 //
 // HBM traffic per octave pixel (T = float): 4 B base read + 4 B x n_levels written; the extrema kernel
 // re-reads the levels once (+ 4 B x n_levels) -- DESIGN.md states the algorithmic figure (24 B).
+#include <string.h>
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "fc_common.cuh"
 
 namespace fc {
@@ -791,28 +795,68 @@ __device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, 
   }
 }
 
+// -- TMA (cp.async.bulk.tensor) staging of an interior input tile ---------------------------------------------------
+// The 128 x 58 float box around a tile is one tensor-map copy issued by one thread; completion is counted in bytes on
+// an mbarrier the whole CTA waits on.  Tiles that touch the image border need the 'symm' reflection, which a tensor map
+// cannot express (out-of-bounds elements are filled with zeros), and keep the per-element cp.async path.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_addr(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy accesses of the tile are ordered before the copy
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar)) : "memory");
+}
+
 // Persistent: 2 CTAs per SM walk the tile list with stride gridDim.x.  The input tile is dead once the vertical pass
 // is done, so the NEXT tile's cp.async copies are issued right after the middle barrier and land while the horizontal
 // pass (55 % of the arithmetic, reads only the intermediate tiles) runs.
 template <bool IDENT0>
 __global__ void __launch_bounds__(256, 2)
 gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int tiles_x, int tiles_y, int n_tiles,
-                           const __grid_constant__ PackedTaps taps, float* __restrict__ gauss) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                           const __grid_constant__ PackedTaps taps, float* __restrict__ gauss,
+                           const __grid_constant__ CUtensorMap in_map, int use_tma) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t tile_bar;
   float* sIn = reinterpret_cast<float*>(smem_raw);
+  if (threadIdx.x == 0) mbar_init(&tile_bar, 1);
+  __syncthreads();
+  uint32_t tma_phase = 0;
   float* sTmp = sIn + kPIH * kPP;
   const bool vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(gauss) & 15) == 0);
   const bool in_vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
   const size_t plane = (size_t)H * W;
 
-  auto issue_load = [&](int tile) {
+  // -> true when the tile is fetched by TMA (then the mbarrier, not cp.async.wait_all, tells when it has landed)
+  auto issue_load = [&](int tile) -> bool {
     const int tx = tile % tiles_x;
     const int rest = tile / tiles_x;
     const int ty = rest % tiles_y;
     const int b = rest / tiles_y;
     const int x0 = tx * kPTX, y0 = ty * kPTY;
     const float* img = base + (size_t)b * plane;
-    // smem column c <-> image column x0 - 16 + c; interior tiles copy 16 bytes per cp.async
+    // smem column c <-> image column x0 - 16 + c
+    if (use_tma && x0 - 16 >= 0 && x0 - 16 + kPP <= W && y0 - kFR >= 0 && y0 - kFR + kPIH <= H) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&tile_bar, kPIH * kPP * sizeof(float));
+        tma_load_3d(sIn, &in_map, x0 - 16, y0 - kFR, b, &tile_bar);
+      }
+      return true;
+    }
+    // interior columns without TMA (or rows that need reflection): 16 bytes per cp.async
     if (in_vec_ok && x0 - 16 >= 0 && x0 - 16 + kPP <= W) {
       // thread -> (row r0 + 8i, 16-byte column c4): one pointer increment per copy when no row is reflected
       const int r0 = threadIdx.x >> 5, c4 = threadIdx.x & 31;
@@ -845,10 +889,12 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
         for (int k = 0; k < 4; ++k) cp_async_elem<float>(dst + 32 * k, row + xr[k]);
       }
     }
+    return false;
   };
 
   int tile = blockIdx.x;
-  if (tile < n_tiles) issue_load(tile);
+  bool by_tma = false;
+  if (tile < n_tiles) by_tma = issue_load(tile);
   for (; tile < n_tiles; tile += gridDim.x) {
     const int tx = tile % tiles_x;
     const int rest = tile / tiles_x;
@@ -856,7 +902,12 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
     const int b = rest / tiles_y;
     const int x0 = tx * kPTX, y0 = ty * kPTY;
     float* gout = gauss + (size_t)b * 5 * plane;
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (by_tma) {
+      mbar_wait(&tile_bar, tma_phase);
+      tma_phase ^= 1;
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
     __syncthreads();  // input tile complete; every thread has left the previous tile's horizontal pass
     if (threadIdx.x < 4 * kPPairs) {
       const int rg = threadIdx.x / kPPairs;
@@ -899,7 +950,7 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
       }
     }
     __syncthreads();  // intermediates complete, input tile free
-    if (tile + (int)gridDim.x < n_tiles) issue_load(tile + gridDim.x);
+    by_tma = (tile + (int)gridDim.x < n_tiles) ? issue_load(tile + gridDim.x) : false;
     {
       const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
       const int yy = y0 + y, xx = x0 + 12 * g;
@@ -1025,6 +1076,33 @@ gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid
   }
 }
 
+// tensor map of a [B][H][W] float32 batch with a 128 x 58 x 1 box (the packed kernel's input tile); false when the
+// driver entry point is missing or the layout does not qualify (row pitch and base must be multiples of 16 bytes)
+static bool make_input_map(const void* base, int B, int H, int W, CUtensorMap* map) {
+  typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode encode = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<Encode>(fn);
+    else
+      (void)cudaGetLastError();
+  }
+  if (!encode || W % 4 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || W < kPP || H < kPIH) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kPP, (cuuint32_t)kPIH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_octave_packed(const void* base, int B, int H, int W, const double* taps_host, const int* tap_len_host,
                                 int first_is_identity, void* gauss, cudaStream_t st) {
   static const int radius[5] = {3, 5, 6, 9, 13};
@@ -1053,12 +1131,17 @@ static int launch_octave_packed(const void* base, int B, int H, int W, const dou
     FC_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
+  CUtensorMap in_map;
+  memset(&in_map, 0, sizeof(in_map));
+  const int use_tma = make_input_map(base, B, H, W, &in_map) ? 1 : 0;
   if (first_is_identity) {
     FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmem));
-    gauss_octave_packed_kernel<true><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, pt, (float*)gauss);
+    gauss_octave_packed_kernel<true><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, pt,
+                                                                    (float*)gauss, in_map, use_tma);
   } else {
     FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmem));
-    gauss_octave_packed_kernel<false><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, pt, (float*)gauss);
+    gauss_octave_packed_kernel<false><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, pt,
+                                                                     (float*)gauss, in_map, use_tma);
   }
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
