@@ -975,53 +975,44 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
 // :241) and level s is the next octave's base (APP/utils/SIFT_scale_space.py:209), so that neither the orientation /
 // descriptor bins nor the deeper octaves inherit float32 rounding.  For the default s = 2 both levels (radii 5, 6)
 // come out of one pass over a shared-memory tile with the pair sums v[-k] + v[+k] shared between them:
-// tile = 116 x 16 outputs, 128 x 28 inputs (61 KB of shared memory: three CTAs per SM -- with 32-row tiles and two
-// CTAs the FP64 pipe was 31 % busy, the kernel waited on its own loads), 19 + 24 float64 operations per pixel.
+// tile = 116 x 32 outputs from 128 x 44 inputs, 19 + 24 float64 operations per pixel.
 struct MidTaps {
   double t[2][8];  // t[l][k] = tap at distance k (centre first), zero beyond the radius
 };
-static constexpr int kMTX = 116, kMTY = 16, kMP = 128, kMR = 6;
-static constexpr int kMIH = kMTY + 2 * kMR;  // 28 input rows
-static constexpr size_t kMidSmem = sizeof(double) * (size_t)(kMIH * kMP + 2 * kMTY * kMP);
+static constexpr int kMTX = 116, kMTY = 32, kMP = 128, kMR = 6;
+static constexpr size_t kMidSmem = sizeof(double) * (size_t)(2 * kMTY * kMP);
 
+// The vertical pass reads its 20-row column segments straight from global memory (coalesced along the row, all 20
+// loads of a thread in flight at once, no staging tile and no barrier before the arithmetic starts); only the two
+// intermediate tiles live in shared memory (64 KB: three CTAs per SM).  A first version staged the input tile with
+// cp.async like the float32 kernel: 110 KB, two CTAs per SM, FP64 pipe 31 % busy -- it mostly waited for its own loads
+// and for the shared-memory port (20 + 16 eight-byte accesses per 8 outputs in the vertical pass alone).
 template <int RA, int RB>
 __global__ void __launch_bounds__(256, 3)
 gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid_constant__ MidTaps taps,
                      double* __restrict__ out, int n_planes, int plane0) {
   static_assert(RA <= kMR && RB <= kMR, "radius class");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sIn = reinterpret_cast<double*>(smem_raw);
-  double* sTmp = sIn + kMIH * kMP;
+  double* sTmp = reinterpret_cast<double*>(smem_raw);  // [2][kMTY][kMP]
   const int x0 = blockIdx.x * kMTX, y0 = blockIdx.y * kMTY;
   const int b = blockIdx.z;
   const size_t plane = (size_t)H * W;
   const double* img = base + (size_t)b * plane;
-  // smem column c <-> image column x0 - 6 + c, smem row r <-> image row y0 - 6 + r
-  const bool interior = (x0 - kMR >= 0) && (x0 - kMR + kMP <= W) && (y0 - kMR >= 0) && (y0 - kMR + kMIH <= H) &&
-                        (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
-  if (interior) {
-    for (int i = threadIdx.x; i < kMIH * (kMP / 2); i += 256) {
-      const int r = i >> 6, c2 = i & 63;
-      const uint32_t d = (uint32_t)__cvta_generic_to_shared(sIn + r * kMP + 2 * c2);
-      const double* src = img + (size_t)(y0 - kMR + r) * W + (x0 - kMR) + 2 * c2;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-    }
-  } else {
-    for (int i = threadIdx.x; i < kMIH * kMP; i += 256) {
-      const int r = i >> 7, c = i & 127;
-      cp_async_elem<double>(sIn + r * kMP + c, img + (size_t)reflect_symm(y0 - kMR + r, H) * W + reflect_symm(x0 - kMR + c, W));
-    }
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
-  // vertical pass: (8-row group, column) items, 2 x 128 = one per thread
+  // tmp column c <-> image column x0 - 6 + c; the vertical item (g, c) produces tmp rows 8g .. 8g+7 of column c
+  const bool interior = (x0 - kMR >= 0) && (x0 - kMR + kMP <= W) && (y0 - kMR >= 0) && (y0 + kMTY + kMR <= H);
 #pragma unroll 1
   for (int item = threadIdx.x; item < (kMTY / 8) * kMP; item += 256) {
     const int g = item >> 7, c = item & 127;
-    const double* src = sIn + (g * 8) * kMP + c;
     double v[8 + 2 * kMR];
+    if (interior) {
+      const double* src = img + (size_t)(y0 - kMR + g * 8) * W + (x0 - kMR + c);
 #pragma unroll
-    for (int k = 0; k < 8 + 2 * kMR; ++k) v[k] = src[k * kMP];
+      for (int k = 0; k < 8 + 2 * kMR; ++k) v[k] = src[(size_t)k * W];
+    } else {
+      const double* col = img + reflect_symm(x0 - kMR + c, W);
+#pragma unroll
+      for (int k = 0; k < 8 + 2 * kMR; ++k) v[k] = col[(size_t)reflect_symm(y0 - kMR + g * 8 + k, H) * W];
+    }
     double* dst = sTmp + (g * 8) * kMP + c;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1679,35 +1670,55 @@ upsample2_block_kernel(const double* __restrict__ in, int H, int W, T* __restric
 // Certified mode wants the base twice -- float64 for the exact levels and the repair, float32 for the bulk kernels -- plus
 // the magnitude bound the float32 error margins scale with: one pass writes all three.
 namespace fc {
-__global__ void __launch_bounds__(256)
+// A thread owns two input columns and walks kUpRows input rows, keeping the three input rows a pair of output rows
+// needs in registers (4 columns each): every input value is loaded once per thread instead of three times, and the
+// twelve scattered 8-byte loads per 8 outputs of the one-row version (ncu: issue slots 17 % used, the memory
+// instruction queue full) become four.
+static constexpr int kUpRows = 8;
+
+__global__ void __launch_bounds__(128)
 upsample2_dual_kernel(const double* __restrict__ in, int H, int W, double* __restrict__ out64, float* __restrict__ out32,
                       unsigned int* __restrict__ bound_bits) {
   const int kx = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  const int ky = blockIdx.y;
+  const int ky0 = blockIdx.y * kUpRows;
   const int b = blockIdx.z;
   float m = 0.f;
   if (kx < W) {
     const double* a = in + (size_t)b * H * W;
-    const int yu = mirror_idx(ky - 1, H), yd = mirror_idx(ky + 1, H);
     const int xc[4] = {mirror_idx(kx - 1, W), kx, kx + 1, mirror_idx(kx + 2, W)};
-    double ve[4], vo[4];
+    double up[4], mid[4], dn[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const double mid = a[(size_t)ky * W + xc[c]];
-      ve[c] = lerp_075_025(mid, a[(size_t)yu * W + xc[c]]);
-      vo[c] = lerp_075_025(mid, a[(size_t)yd * W + xc[c]]);
+      up[c] = a[(size_t)mirror_idx(ky0 - 1, H) * W + xc[c]];
+      mid[c] = a[(size_t)ky0 * W + xc[c]];
     }
-    const double e[4] = {lerp_075_025(ve[1], ve[0]), lerp_075_025(ve[1], ve[2]), lerp_075_025(ve[2], ve[1]), lerp_075_025(ve[2], ve[3])};
-    const double o[4] = {lerp_075_025(vo[1], vo[0]), lerp_075_025(vo[1], vo[2]), lerp_075_025(vo[2], vo[1]), lerp_075_025(vo[2], vo[3])};
-    const size_t off = ((size_t)b * 2 * H + 2 * ky) * 2 * W + 2 * kx;
-    double2* d0 = reinterpret_cast<double2*>(out64 + off);
-    double2* d1 = reinterpret_cast<double2*>(out64 + off + 2 * W);
-    d0[0] = make_double2(e[0], e[1]); d0[1] = make_double2(e[2], e[3]);
-    d1[0] = make_double2(o[0], o[1]); d1[1] = make_double2(o[2], o[3]);
-    *reinterpret_cast<float4*>(out32 + off) = make_float4((float)e[0], (float)e[1], (float)e[2], (float)e[3]);
-    *reinterpret_cast<float4*>(out32 + off + 2 * W) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+    const int ky1 = min(ky0 + kUpRows, H);
+    for (int ky = ky0; ky < ky1; ++ky) {
+      const int yd = mirror_idx(ky + 1, H);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) m = fmaxf(m, fmaxf((float)fabs(e[c]), (float)fabs(o[c])));
+      for (int c = 0; c < 4; ++c) dn[c] = a[(size_t)yd * W + xc[c]];
+      double ve[4], vo[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ve[c] = lerp_075_025(mid[c], up[c]);
+        vo[c] = lerp_075_025(mid[c], dn[c]);
+      }
+      const double e[4] = {lerp_075_025(ve[1], ve[0]), lerp_075_025(ve[1], ve[2]), lerp_075_025(ve[2], ve[1]), lerp_075_025(ve[2], ve[3])};
+      const double o[4] = {lerp_075_025(vo[1], vo[0]), lerp_075_025(vo[1], vo[2]), lerp_075_025(vo[2], vo[1]), lerp_075_025(vo[2], vo[3])};
+      const size_t off = ((size_t)b * 2 * H + 2 * ky) * 2 * W + 2 * kx;
+      double2* d0 = reinterpret_cast<double2*>(out64 + off);
+      double2* d1 = reinterpret_cast<double2*>(out64 + off + 2 * W);
+      d0[0] = make_double2(e[0], e[1]); d0[1] = make_double2(e[2], e[3]);
+      d1[0] = make_double2(o[0], o[1]); d1[1] = make_double2(o[2], o[3]);
+      *reinterpret_cast<float4*>(out32 + off) = make_float4((float)e[0], (float)e[1], (float)e[2], (float)e[3]);
+      *reinterpret_cast<float4*>(out32 + off + 2 * W) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        m = fmaxf(m, fmaxf((float)fabs(e[c]), (float)fabs(o[c])));
+        up[c] = mid[c];
+        mid[c] = dn[c];
+      }
+    }
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
@@ -1733,7 +1744,7 @@ extern "C" int fc_upsample2_dual(const double* image, int batch, int height, int
   if ((width & 1) || ((reinterpret_cast<uintptr_t>(out64) | reinterpret_cast<uintptr_t>(out32)) & 15)) return FC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   FC_CUDA_TRY(cudaMemsetAsync(value_bound, 0, sizeof(float), st));
-  upsample2_dual_kernel<<<dim3(div_up(width / 2, 256), height, batch), 256, 0, st>>>(
+  upsample2_dual_kernel<<<dim3(div_up(width / 2, 128), div_up(height, kUpRows), batch), 128, 0, st>>>(
       image, height, width, out64, out32, reinterpret_cast<unsigned int*>(value_bound));
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
