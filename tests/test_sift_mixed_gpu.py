@@ -206,3 +206,63 @@ def _tiny_cap(fn):
         mx.amb_cap = 8  # pretend the list was this small: the counters say "overflow"
         return octv, mx
     return wrapped
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (64, 33), (19, 90), (101, 77)])
+def test_odd_and_tiny_sizes_equal_float64(S, shape):
+    """Widths that are not multiples of 4 take the tiled certified extremum kernel, the scalar code kernel and the
+    generic float64 level kernel: the lists must still be the float64 path's."""
+    from exvision_featurecraft_b200 import synthetic
+
+    base = synthetic.sift_image(*shape, seed=shape[0] + shape[1])
+    a = S.detect_and_describe(base, S.SiftParams(dtype="mixed"), out_dtype=torch.float32).assemble(1)[0]
+    b = S.detect_and_describe(base, S.SiftParams(dtype="f64"), out_dtype=torch.float64).assemble(1)[0]
+    assert np.array_equal(a[0], b[0])
+    ok = ~np.isnan(b[1]).any(1)
+    assert np.array_equal(np.isnan(a[1]).any(1), ~ok)
+    if ok.any():
+        assert np.linalg.norm(a[1][ok] - b[1][ok], axis=1).max() < 2e-5
+
+
+@pytest.mark.parametrize("params", [dict(n_octaves=5, s_value=3, sigma_base=2.5), dict(n_octaves=4, s_value=2, sigma_base=3.0),
+                                    dict(n_octaves=6, s_value=4, sigma_base=1.6), dict(n_octaves=4, s_value=2, sigma_base=1.6, variant="script"),
+                                    dict(n_octaves=4, s_value=2, sigma_base=2.0, variant="script", contrast_th=0.01, ratio_th=6.0)])
+def test_ui_parameter_ranges_equal_float64(S, params):
+    """Points of the app's parameter ranges (FeatureCraft_UI.py:197-273: octaves 4-8, s 2-5, sigma 1.6-3, r 6-12) and the
+    script filter: non-default radii take the generic float32 / float64 blur kernels, more DoG levels the tiled
+    certified search; both filters go through the float64 repair.  Certified mode must equal float64 mode everywhere."""
+    from exvision_featurecraft_b200 import synthetic
+
+    base = synthetic.sift_image(160, 192, seed=41)
+    a = S.detect_and_describe(base, S.SiftParams(dtype="mixed", **params), out_dtype=torch.float32)
+    b = S.detect_and_describe(base, S.SiftParams(dtype="f64", **params), out_dtype=torch.float64)
+    pa, da = a.assemble(1)[0]
+    pb, db = b.assemble(1)[0]
+    assert pb.shape[0] > 50
+    assert np.array_equal(pa, pb)
+    ok = ~np.isnan(db).any(1)
+    assert np.array_equal(np.isnan(da).any(1), ~ok)
+    assert np.linalg.norm(da[ok] - db[ok], axis=1).max() < 2e-5
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_images_certified_equals_float64(S, seed):
+    """Different image statistics (blob fields, pure noise, smooth ramps with saturated plateaus, quantised values):
+    whatever the data, every decision of certified mode must be the float64 decision."""
+    rng = np.random.default_rng(100 + seed)
+    h, w = int(rng.integers(48, 140)), int(rng.integers(12, 36)) * 4
+    kind = seed % 3
+    if kind == 0:
+        base = rng.random((h, w))
+    elif kind == 1:
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = np.clip(0.5 + 0.8 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + rng.normal(0, 0.01, (h, w)), 0.0, 1.0)  # clipped plateaus
+    else:
+        base = np.round(rng.random((h, w)) * 8) / 8  # nine grey levels: ties everywhere
+    a = S.detect_and_describe(base, S.SiftParams(dtype="mixed"), out_dtype=torch.float32).assemble(1)[0]
+    b = S.detect_and_describe(base, S.SiftParams(dtype="f64"), out_dtype=torch.float64).assemble(1)[0]
+    assert np.array_equal(a[0], b[0])
+    ok = ~np.isnan(b[1]).any(1)
+    assert np.array_equal(np.isnan(a[1]).any(1), ~ok)
+    if ok.any():
+        assert np.linalg.norm(a[1][ok] - b[1][ok], axis=1).max() < 2e-5
