@@ -758,21 +758,31 @@ descriptor_coded_kernel(const uint32_t* __restrict__ codes, int H, int W, const 
     const int4 ad4 = *reinterpret_cast<const int4*>(&sAd[bin][cx]);
     const int4 bd4 = *reinterpret_cast<const int4*>(&sBd[bin][cx]);
     const int ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w}, bd[4] = {bd4.x, bd4.y, bd4.z, bd4.w};
-    const int cb = 2 * bin + 2;
-    // the rotated 16x16 window reaches at most 7.5 * sqrt(2) + 1 < 12 pixels from the keypoint
+    // the rotated 16x16 window reaches at most 7.5 * sqrt(2) + 1 < 12 pixels from the keypoint: when both keypoints of
+    // the warp are that far inside the image (nearly always) no sample needs a bounds test
     const bool interior = (ki >= 12) && (ki < H - 12) && (kj >= 12) && (kj < W - 12);
     uint32_t pv[4][4];  // all 16 gathers of the lane are issued before the first dependent histogram update
+    if (__all_sync(0xffffffffu, interior)) {
 #pragma unroll
-    for (int ry = 0; ry < 4; ++ry) {
-      const int X0 = xy[cy + ry], Y0 = xy[16 + cy + ry];
+      for (int ry = 0; ry < 4; ++ry) {
+        const int X0 = xy[cy + ry], Y0 = xy[16 + cy + ry];
 #pragma unroll
-      for (int rx = 0; rx < 4; ++rx) {
-        const int X = (X0 + ad[rx]) >> 10;
-        const int Y = (Y0 + bd[rx]) >> 10;
-        const bool in = interior || (((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H));
-        pv[ry][rx] = in ? m[Y * W + X] : 0u;  // one image plane has fewer than 2^30 pixels (checked on the host)
+        for (int rx = 0; rx < 4; ++rx) pv[ry][rx] = m[((Y0 + bd[rx]) >> 10) * W + ((X0 + ad[rx]) >> 10)];
+      }
+    } else {
+#pragma unroll
+      for (int ry = 0; ry < 4; ++ry) {
+        const int X0 = xy[cy + ry], Y0 = xy[16 + cy + ry];
+#pragma unroll
+        for (int rx = 0; rx < 4; ++rx) {
+          const int X = (X0 + ad[rx]) >> 10;
+          const int Y = (Y0 + bd[rx]) >> 10;
+          const bool in = ((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H);
+          pv[ry][rx] = in ? m[Y * W + X] : 0u;  // one image plane has fewer than 2^30 pixels (checked on the host)
+        }
       }
     }
+    const int cb = 2 * bin + 2;
 #pragma unroll
     for (int ry = 0; ry < 4; ++ry) {
 #pragma unroll
