@@ -85,6 +85,7 @@ SIGNATURES = {
     "fc_downsample2_dual": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fc_gauss_levels_f64": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
     "fc_gauss_octave_extrema_certified": (_i, [_p, _i, _i, _i, _i, _i, _d, _d, _p, _d, _p, _p, _i, _p, _p]),
+    "fc_gauss_octave_search": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _d, _p, _p, _i, _p, _p]),
     "fc_extrema_repair": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _d, _d, _p, _p, _i, _p, _p]),
     "fc_orientation_scan": (_i, [_p, _i, _p, _p, _p]),
     "fc_orientation_emit": (_i, [_p, _p, _p, _i, _p, _p]),

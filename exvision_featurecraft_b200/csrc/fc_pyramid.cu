@@ -743,8 +743,7 @@ __device__ __forceinline__ void packed_vertical_level(const PackedTaps& taps, fl
 }
 
 template <int L>
-__device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, const float* __restrict__ sRow,
-                                                        float* __restrict__ dst, bool in_img, bool full, int n_valid) {
+__device__ __forceinline__ void packed_horizontal_compute(const PackedTaps& taps, const float* __restrict__ sRow, float (&r)[12]) {
   constexpr int R = FusedRadius<L>::R;
   constexpr int E = (R & 1) ? R + 1 : R;    // input pairs at even offsets -E .. E of each output pair
   constexpr int E4 = (E + 3) & ~3;
@@ -758,7 +757,6 @@ __device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, 
     p[2 * q] = make_float2(t.x, t.y);
     p[2 * q + 1] = make_float2(t.z, t.w);
   }
-  float r[12];
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
     float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
@@ -784,6 +782,13 @@ __device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, 
     r[2 * q] = a.x + b.y;
     r[2 * q + 1] = a.y + b.x;
   }
+}
+
+template <int L>
+__device__ __forceinline__ void packed_horizontal_level(const PackedTaps& taps, const float* __restrict__ sRow,
+                                                        float* __restrict__ dst, bool in_img, bool full, int n_valid) {
+  float r[12];
+  packed_horizontal_compute<L>(taps, sRow, r);
   if (full) {
     reinterpret_cast<float4*>(dst)[0] = make_float4(r[0], r[1], r[2], r[3]);
     reinterpret_cast<float4*>(dst)[1] = make_float4(r[4], r[5], r[6], r[7]);
@@ -824,11 +829,30 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 // Persistent: 2 CTAs per SM walk the tile list with stride gridDim.x.  The input tile is dead once the vertical pass
 // is done, so the NEXT tile's cp.async copies are issued right after the middle barrier and land while the horizontal
 // pass (55 % of the arithmetic, reads only the intermediate tiles) runs.
-template <bool IDENT0>
+//
+// SEARCH: the certified pipeline never reads the float32 stack again once the extrema are found -- gradients, next base
+// and every float64 decision come from the float64 levels -- so this variant does not write it at all.  The horizontal
+// pass leaves DoG_d = G_{d+1} - G_d of its 96 x 32 region in shared memory (over the intermediate tiles it has just
+// consumed) and the certified 3x3x3 search (see ExsCert) runs on the inner 92 x 30 pixels right there: tiles overlap
+// by the search halo (stride 92 x 30), decided extrema are OR-ed into the (zeroed) masks, undecided ones go to the
+// list for fc_extrema_repair.  The search costs about a third of the instructions of the stand-alone strip kernel (no
+// staging, no DoG re-computation from five global levels) and the stage writes ~0 instead of 20 bytes per pixel.
+struct SearchArgs {
+  int B, filter, pitch, amb_cap;
+  float eps_rel;
+  const float* value_bound;
+  uint32_t* extrema;  // [2][B][H][pitch]
+  int4* amb;
+  int* amb_count;
+};
+static constexpr int kSTX = 92, kSTY = 30;  // centres per tile in SEARCH mode
+
+template <bool IDENT0, bool SEARCH>
 __global__ void __launch_bounds__(256, 2)
 gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int tiles_x, int tiles_y, int n_tiles,
                            const __grid_constant__ PackedTaps taps, float* __restrict__ gauss,
-                           const __grid_constant__ CUtensorMap in_map, int use_tma) {
+                           const __grid_constant__ CUtensorMap in_map, int use_tma, const SearchArgs sa) {
+  constexpr int kStepX = SEARCH ? kSTX : kPTX, kStepY = SEARCH ? kSTY : kPTY;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t tile_bar;
   float* sIn = reinterpret_cast<float*>(smem_raw);
@@ -846,7 +870,7 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
     const int rest = tile / tiles_x;
     const int ty = rest % tiles_y;
     const int b = rest / tiles_y;
-    const int x0 = tx * kPTX, y0 = ty * kPTY;
+    const int x0 = tx * kStepX, y0 = ty * kStepY;
     const float* img = base + (size_t)b * plane;
     // smem column c <-> image column x0 - 16 + c
     if (use_tma && x0 - 16 >= 0 && x0 - 16 + kPP <= W && y0 - kFR >= 0 && y0 - kFR + kPIH <= H) {
@@ -900,8 +924,8 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
     const int rest = tile / tiles_x;
     const int ty = rest % tiles_y;
     const int b = rest / tiles_y;
-    const int x0 = tx * kPTX, y0 = ty * kPTY;
-    float* gout = gauss + (size_t)b * 5 * plane;
+    const int x0 = tx * kStepX, y0 = ty * kStepY;
+    float* gout = SEARCH ? nullptr : gauss + (size_t)b * 5 * plane;
     if (by_tma) {
       mbar_wait(&tile_bar, tma_phase);
       tma_phase ^= 1;
@@ -931,7 +955,16 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
         packed_vertical_level<4>(taps, centre, s, d + 4 * kPTY * (kPP / 2));
       }
     }
-    if (IDENT0) {
+    float ident[12];  // SEARCH && IDENT0: level 0 = the base itself, taken from the input tile before it is recycled
+    if (SEARCH && IDENT0) {
+      const float4* s4 = reinterpret_cast<const float4*>(sIn + ((threadIdx.x >> 3) + kFR) * kPP + 16 + 12 * (threadIdx.x & 7));
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 t = s4[q];
+        ident[4 * q] = t.x; ident[4 * q + 1] = t.y; ident[4 * q + 2] = t.z; ident[4 * q + 3] = t.w;
+      }
+    }
+    if (IDENT0 && !SEARCH) {
       // level 0 of octaves > 0 is the unblurred base (:136-137); reads the input tile, so it goes before the barrier
       const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
       const int yy = y0 + y, xx = x0 + 12 * g;
@@ -951,7 +984,7 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
     }
     __syncthreads();  // intermediates complete, input tile free
     by_tma = (tile + (int)gridDim.x < n_tiles) ? issue_load(tile + gridDim.x) : false;
-    {
+    if constexpr (!SEARCH) {
       const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
       const int yy = y0 + y, xx = x0 + 12 * g;
       const bool in_img = yy < H && xx < W;
@@ -963,6 +996,138 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
       packed_horizontal_level<2>(taps, sRow, dst + 2 * plane, in_img, full, W - xx);
       packed_horizontal_level<3>(taps, sRow, dst + 3 * plane, in_img, full, W - xx);
       packed_horizontal_level<4>(taps, sRow, dst + 4 * plane, in_img, full, W - xx);
+    } else {
+      // ---- horizontal pass into DoG planes: D_{l-1} = G_l - G_{l-1} overwrites row y of intermediate tile l-1, which
+      // only the eight threads of this row (same warp) have read, all of them before their level-l loads
+      {
+        const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
+        float* sRow = sTmp + y * kPP + 16 + 12 * g;
+        float prev[12], cur[12];
+        if (IDENT0) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) prev[j] = ident[j];
+        } else {
+          packed_horizontal_compute<0>(taps, sRow, prev);
+        }
+#define FC_DOG_LEVEL(LV)                                                                                         \
+  packed_horizontal_compute<LV>(taps, sRow, cur);                                                                \
+  __syncwarp();                                                                                                  \
+  {                                                                                                              \
+    float4* d4 = reinterpret_cast<float4*>(sRow + (LV - 1) * kPTY * kPP);                                        \
+    d4[0] = make_float4(cur[0] - prev[0], cur[1] - prev[1], cur[2] - prev[2], cur[3] - prev[3]);                 \
+    d4[1] = make_float4(cur[4] - prev[4], cur[5] - prev[5], cur[6] - prev[6], cur[7] - prev[7]);                 \
+    d4[2] = make_float4(cur[8] - prev[8], cur[9] - prev[9], cur[10] - prev[10], cur[11] - prev[11]);             \
+  }                                                                                                              \
+  _Pragma("unroll") for (int j = 0; j < 12; ++j) prev[j] = cur[j];
+        FC_DOG_LEVEL(1)
+        FC_DOG_LEVEL(2)
+        FC_DOG_LEVEL(3)
+        FC_DOG_LEVEL(4)
+#undef FC_DOG_LEVEL
+      }
+      // ---- certified 3x3x3 search on the inner 92 x 30 pixels, in three steps that never re-derive a value:
+      //  (1) each thread re-reads the four DoG values of its own 12 columns (+ one neighbour column each side) of its row;
+      //  (2) in registers: per pixel the level-max / -min over k-1, k, k+1, then the 3-max / 3-min along x = the row's
+      //      contribution H to the rows above and below it, and the same reduction WITHOUT the centre = the row's own
+      //      contribution N; H overwrites the (now dead) DoG row in shared memory;
+      //  (3) after a barrier M = max3(H above, N own, H below) is the maximum of the 26 neighbours: c > M + eps is a
+      //      float64 extremum too, c < M - eps is none, in between the pixel goes to the undecided list (see ExsCert).
+      // region column j <-> smem column 16 + j <-> image column x0 + j; region row <-> image row y0 + row.
+      {
+        __syncwarp();  // the DoG row written by this row's eight threads is complete
+        const int yr = threadIdx.x >> 3, g = threadIdx.x & 7;
+        float* rowp = sTmp + yr * kPP + 16 + 12 * g;
+        float nmax[2][12], nmin[2][12], ctr[2][12];
+        {
+          float d[4][14];  // columns 12g-1 .. 12g+12 of the four DoG planes
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            const float* pl = rowp + l * kPTY * kPP;
+            d[l][0] = pl[-1];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const float4 t = reinterpret_cast<const float4*>(pl)[q];
+              d[l][1 + 4 * q] = t.x; d[l][2 + 4 * q] = t.y; d[l][3 + 4 * q] = t.z; d[l][4 + 4 * q] = t.w;
+            }
+            d[l][13] = pl[12];
+          }
+          __syncwarp();  // the row's eight threads (same warp) have their DoG values: the row may be overwritten
+#pragma unroll
+          for (int k = 1; k <= 2; ++k) {
+            float bx[14], bn[14], ax[14], an[14];  // levels k-1, k+1 only / all three
+#pragma unroll
+            for (int i = 0; i < 14; ++i) {
+              bx[i] = fmaxf(d[k - 1][i], d[k + 1][i]);
+              bn[i] = fminf(d[k - 1][i], d[k + 1][i]);
+              ax[i] = fmaxf(bx[i], d[k][i]);
+              an[i] = fminf(bn[i], d[k][i]);
+            }
+            float hx[12], hn[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+              hx[j] = max3_t<float>(ax[j], ax[j + 1], ax[j + 2]);
+              hn[j] = min3_t<float>(an[j], an[j + 1], an[j + 2]);
+              nmax[k - 1][j] = fmaxf(max3_t<float>(bx[j], bx[j + 1], bx[j + 2]), fmaxf(d[k][j], d[k][j + 2]));
+              nmin[k - 1][j] = fminf(min3_t<float>(bn[j], bn[j + 1], bn[j + 2]), fminf(d[k][j], d[k][j + 2]));
+              ctr[k - 1][j] = d[k][j + 1];
+            }
+            float4* hxp = reinterpret_cast<float4*>(rowp + (2 * (k - 1)) * kPTY * kPP);
+            float4* hnp = reinterpret_cast<float4*>(rowp + (2 * (k - 1) + 1) * kPTY * kPP);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              hxp[q] = make_float4(hx[4 * q], hx[4 * q + 1], hx[4 * q + 2], hx[4 * q + 3]);
+              hnp[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+            }
+          }
+        }
+        __syncthreads();  // planes 0..3 now hold H: (k=1 max, k=1 min, k=2 max, k=2 min)
+        const int y = y0 + yr;
+        if (yr >= 1 && yr <= kSTY && y >= 1 && y <= H - 3) {
+          const float eps = sa.eps_rel * fmaxf(*sa.value_bound, 1e-30f);
+#pragma unroll
+          for (int k = 1; k <= 2; ++k) {
+            float up[2][12], dn[2][12];  // [max / min] of the rows above and below
+#pragma unroll
+            for (int mm = 0; mm < 2; ++mm) {
+              const float4* pu = reinterpret_cast<const float4*>(rowp + (2 * (k - 1) + mm) * kPTY * kPP - kPP);
+              const float4* pd = reinterpret_cast<const float4*>(rowp + (2 * (k - 1) + mm) * kPTY * kPP + kPP);
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const float4 a = pu[q], c4 = pd[q];
+                up[mm][4 * q] = a.x; up[mm][4 * q + 1] = a.y; up[mm][4 * q + 2] = a.z; up[mm][4 * q + 3] = a.w;
+                dn[mm][4 * q] = c4.x; dn[mm][4 * q + 1] = c4.y; dn[mm][4 * q + 2] = c4.z; dn[mm][4 * q + 3] = c4.w;
+              }
+            }
+            uint32_t bits = 0, amb = 0;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+              const float M = max3_t<float>(up[0][j], nmax[k - 1][j], dn[0][j]);
+              const float m = min3_t<float>(up[1][j], nmin[k - 1][j], dn[1][j]);
+              const float c = ctr[k - 1][j];
+              const int rj = 12 * g + j;  // region column of the centre
+              const int x = x0 + rj;
+              const bool ok = rj >= 1 && rj <= kSTX && x >= 1 && x <= W - 3;
+              const bool cand = ok && (c >= M - eps || c <= m + eps);
+              const bool sure = c > M + eps || c < m - eps;
+              if (cand && sure && sa.filter != FC_FILTER_SCRIPT) bits |= 1u << j;
+              else if (cand) amb |= 1u << j;
+            }
+            while (amb) {  // rare: the float64 repair decides these
+              const int j = __ffs(amb) - 1;
+              amb &= amb - 1;
+              const int pos = atomicAdd(sa.amb_count, 1);
+              if (pos < sa.amb_cap) sa.amb[pos] = make_int4(b, k, y, x0 + 12 * g + j);
+            }
+            if (bits) {
+              uint32_t* mrow = sa.extrema + (((size_t)(k - 1) * sa.B + b) * H + y) * sa.pitch;
+              const int xb = x0 + 12 * g;  // bit j of `bits` is image column xb + j
+              const unsigned long long wide = (unsigned long long)bits << (xb & 31);
+              atomicOr(mrow + (xb >> 5), (uint32_t)wide);
+              if (wide >> 32) atomicOr(mrow + (xb >> 5) + 1, (uint32_t)(wide >> 32));
+            }
+          }
+        }
+      }
     }
   }
 }
@@ -1095,7 +1260,7 @@ static bool make_input_map(const void* base, int B, int H, int W, CUtensorMap* m
 }
 
 static int launch_octave_packed(const void* base, int B, int H, int W, const double* taps_host, const int* tap_len_host,
-                                int first_is_identity, void* gauss, cudaStream_t st) {
+                                int first_is_identity, void* gauss, cudaStream_t st, const SearchArgs* search = nullptr) {
   static const int radius[5] = {3, 5, 6, 9, 13};
   PackedTaps pt;
   const double* tp = taps_host;
@@ -1111,7 +1276,10 @@ static int launch_octave_packed(const void* base, int B, int H, int W, const dou
     }
     tp += tap_len_host[l];
   }
-  const int tiles_x = div_up(W, kPTX), tiles_y = div_up(H, kPTY);
+  // search mode: tile (tx, ty) evaluates the centres x0+1 .. x0+92, y0+1 .. y0+30 (x0 = 92 tx, y0 = 30 ty); centres
+  // range over 1 .. W-3 and 1 .. H-3
+  const int tiles_x = search ? div_up(W - 3, kSTX) : div_up(W, kPTX), tiles_y = search ? div_up(H - 3, kSTY) : div_up(H, kPTY);
+  if (tiles_x < 1 || tiles_y < 1) return FC_ERR_UNSUPPORTED;
   const long long n_tiles_ll = (long long)tiles_x * tiles_y * B;
   if (n_tiles_ll > 0x7fffffffLL) return FC_ERR_UNSUPPORTED;
   const int n_tiles = (int)n_tiles_ll;
@@ -1125,15 +1293,22 @@ static int launch_octave_packed(const void* base, int B, int H, int W, const dou
   CUtensorMap in_map;
   memset(&in_map, 0, sizeof(in_map));
   const int use_tma = make_input_map(base, B, H, W, &in_map) ? 1 : 0;
-  if (first_is_identity) {
-    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmem));
-    gauss_octave_packed_kernel<true><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, pt,
-                                                                    (float*)gauss, in_map, use_tma);
+  SearchArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  if (search) sa = *search;
+#define FC_PACKED(ID, SE)                                                                                            \
+  do {                                                                                                              \
+    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<ID, SE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)kPackedSmem));                                                            \
+    gauss_octave_packed_kernel<ID, SE><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, \
+                                                                      pt, (float*)gauss, in_map, use_tma, sa);     \
+  } while (0)
+  if (search) {
+    if (first_is_identity) FC_PACKED(true, true); else FC_PACKED(false, true);
   } else {
-    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_octave_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmem));
-    gauss_octave_packed_kernel<false><<<grid, 256, kPackedSmem, st>>>((const float*)base, H, W, tiles_x, tiles_y, n_tiles, pt,
-                                                                     (float*)gauss, in_map, use_tma);
+    if (first_is_identity) FC_PACKED(true, false); else FC_PACKED(false, false);
   }
+#undef FC_PACKED
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
@@ -1541,6 +1716,34 @@ extern "C" int fc_gauss_octave_extrema_certified(const float* gauss, int batch, 
   ca.amb_cap = amb_cap;
   ca.amb_count = amb_count;
   return launch_extrema_certified(gauss, batch, height, width, n_levels, filter, contrast_th, ratio_th, extrema, st, ca);
+}
+
+// fused form of fc_gauss_octave + fc_gauss_octave_extrema_certified for the pipeline that does not need the float32
+// stack itself: default radii only (FC_ERR_UNSUPPORTED otherwise -- the caller then uses the two calls above)
+extern "C" int fc_gauss_octave_search(const float* base, int batch, int height, int width, int n_levels, const double* taps_host,
+                                      const int* tap_len_host, int first_is_identity, int filter, const float* value_bound,
+                                      double eps_rel, uint32_t* extrema, int32_t* amb, int amb_cap, int32_t* amb_count,
+                                      void* stream) {
+  if (!base || !taps_host || !tap_len_host || !value_bound || !extrema || !amb || !amb_count) return FC_ERR_BAD_ARG;
+  if (batch <= 0 || height <= 0 || width <= 0 || amb_cap < 0 || !(eps_rel >= 0.0)) return FC_ERR_BAD_ARG;
+  if (filter != FC_FILTER_APP && filter != FC_FILTER_SCRIPT) return FC_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(amb) & 15) return FC_ERR_BAD_ARG;
+  if (n_levels != 5 || !fused_applicable(n_levels, taps_host, tap_len_host) || height < 4 || width < 4) return FC_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pitch = div_up(width, 32);
+  FC_CUDA_TRY(cudaMemsetAsync(amb_count, 0, sizeof(int32_t), st));
+  FC_CUDA_TRY(cudaMemsetAsync(extrema, 0, sizeof(uint32_t) * 2 * (size_t)batch * height * pitch, st));
+  SearchArgs sa;
+  sa.B = batch;
+  sa.filter = filter;
+  sa.pitch = pitch;
+  sa.amb_cap = amb_cap;
+  sa.eps_rel = (float)eps_rel;
+  sa.value_bound = value_bound;
+  sa.extrema = extrema;
+  sa.amb = reinterpret_cast<int4*>(amb);
+  sa.amb_count = amb_count;
+  return launch_octave_packed(base, batch, height, width, taps_host, tap_len_host, first_is_identity, nullptr, st, &sa);
 }
 
 extern "C" int fc_extrema_repair(const double* base, int first_is_identity, const double* mid, int mid_first, int mid_count,

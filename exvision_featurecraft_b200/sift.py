@@ -219,10 +219,11 @@ def _cached(key, builder, dtype=torch.float64):
 # ---------------------------------------------------------------------------------------------
 @dataclass
 class Octave:
-    gauss: torch.Tensor  # [B, L, h, w]
+    gauss: torch.Tensor | None  # [B, L, h, w]; None when the certified pipeline fused the search into the blur kernel
     extrema: torch.Tensor | None  # [L-3, B, h, ceil(w/32)] int32 bit masks, index k-1
     height: int
     width: int
+    batch: int = 0
 
 
 @dataclass
@@ -347,7 +348,7 @@ def gauss_octave(base: torch.Tensor, params: SiftParams, octave_index: int, with
         with _stage("extrema"):
             _lib.call("fc_gauss_octave_extrema", ptr(gauss), params.fc_dtype, b, h, w, L, filt, float(params.contrast_th),
                       float(params.ratio_th), ptr(extrema), stream_ptr())
-    return Octave(gauss, extrema, h, w)
+    return Octave(gauss, extrema, h, w, b)
 
 
 # --- certified ("mixed") mode -----------------------------------------------------------------------------------
@@ -370,11 +371,13 @@ class MixedOctave:
 
 
 def gauss_octave_mixed(base64: torch.Tensor, params: SiftParams, octave_index: int, with_extrema: bool = True, taps=None,
-                       value_bound: torch.Tensor | None = None, amb_count: torch.Tensor | None = None):
+                       value_bound: torch.Tensor | None = None, amb_count: torch.Tensor | None = None, need_stack: bool = True):
     """One octave in certified mode -> (Octave with the float32 stack and the certified extremum masks, MixedOctave).
 
     base64 is the octave's float64 base.  value_bound: device float with max |image| (computed here for octave 0 while
-    the float32 copy is made; deeper octaves are blurs of it and inherit the bound)."""
+    the float32 copy is made; deeper octaves are blurs of it and inherit the bound).  need_stack=False (the pipeline:
+    nothing reads the float32 levels after the search) lets the blur kernel run the search on its own tiles and skip
+    writing the stack (fc_gauss_octave_search; default radii only, otherwise the two-kernel form is used)."""
     b, h, w = base64.shape
     dev = base64.device
     L, s = params.n_levels, params.s_value
@@ -393,37 +396,49 @@ def gauss_octave_mixed(base64: torch.Tensor, params: SiftParams, octave_index: i
                 _lib.call("fc_convert_f64_bound", ptr(base64), C.c_int64(base64.numel()), ptr(base32), ptr(value_bound), stream_ptr())
             else:
                 _lib.call("fc_convert_f64", ptr(base64), C.c_int64(base64.numel()), _lib.FC_F32, ptr(base32), stream_ptr())
-    gauss = torch.empty((b, L, h, w), dtype=torch.float32, device=dev)
-    with _stage("pyramid_o%d" % octave_index):
-        _lib.call("fc_gauss_octave", ptr(base32), _lib.FC_F32, b, h, w, L, tp, lp, ident, filt, float(params.contrast_th),
-                  float(params.ratio_th), ptr(gauss), None, stream_ptr())
-    n_mid = min(s, L - 1)
-    mid = torch.empty((b, n_mid, h, w), dtype=torch.float64, device=dev)
-    with _stage("pyramid_f64"):
-        _lib.call("fc_gauss_levels_f64", ptr(base64), b, h, w, L, tp, lp, 1, n_mid, ptr(mid), stream_ptr())
-    extrema, cap = None, 0
     if amb_count is None:
         amb_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    extrema, cap, amb, gauss = None, 0, None, None
     if with_extrema and L >= 4:
         extrema = torch.empty((L - 3, b, h, (w + 31) // 32), dtype=torch.int32, device=dev)
         cap = int(b * h * w * (L - 3) * AMB_FRACTION[params.variant]) + 4096
         amb = torch.empty((cap, 4), dtype=torch.int32, device=dev)
-        with _stage("extrema"):
-            _lib.call("fc_gauss_octave_extrema_certified", ptr(gauss), b, h, w, L, filt, float(params.contrast_th),
-                      float(params.ratio_th), ptr(value_bound), float(EXTREMA_EPS), ptr(extrema), ptr(amb), cap, ptr(amb_count),
-                      stream_ptr())
+    fused = False
+    if extrema is not None and not need_stack and L == 5 and w % 4 == 0:
+        with _stage("pyramid_o%d" % octave_index):
+            rc = _lib.load().fc_gauss_octave_search(ptr(base32), b, h, w, L, tp, lp, ident, filt, ptr(value_bound), float(EXTREMA_EPS),
+                                                    ptr(extrema), ptr(amb), cap, ptr(amb_count), stream_ptr())
+        if rc == _lib.FC_OK:
+            fused = True
+        elif rc != -4:  # FC_ERR_UNSUPPORTED: other radii -> the two-kernel form below
+            _lib.check(rc, "fc_gauss_octave_search")
+    if not fused:
+        gauss = torch.empty((b, L, h, w), dtype=torch.float32, device=dev)
+        with _stage("pyramid_o%d" % octave_index):
+            _lib.call("fc_gauss_octave", ptr(base32), _lib.FC_F32, b, h, w, L, tp, lp, ident, filt, float(params.contrast_th),
+                      float(params.ratio_th), ptr(gauss), None, stream_ptr())
+    n_mid = min(s, L - 1)
+    mid = torch.empty((b, n_mid, h, w), dtype=torch.float64, device=dev)
+    with _stage("pyramid_f64"):
+        _lib.call("fc_gauss_levels_f64", ptr(base64), b, h, w, L, tp, lp, 1, n_mid, ptr(mid), stream_ptr())
+    if extrema is not None:
+        if not fused:
+            with _stage("extrema"):
+                _lib.call("fc_gauss_octave_extrema_certified", ptr(gauss), b, h, w, L, filt, float(params.contrast_th),
+                          float(params.ratio_th), ptr(value_bound), float(EXTREMA_EPS), ptr(extrema), ptr(amb), cap, ptr(amb_count),
+                          stream_ptr())
         with _stage("extrema_f64"):
             _lib.call("fc_extrema_repair", ptr(base64), ident, ptr(mid), 1, n_mid, b, h, w, L, tp, lp, filt,
                       float(params.contrast_th), float(params.ratio_th), ptr(amb), ptr(amb_count), cap, ptr(extrema), stream_ptr())
-    octv = Octave(gauss, extrema, h, w)
+    octv = Octave(gauss, extrema, h, w, b)
     octv.value_bound = value_bound
     return octv, MixedOctave(base64, mid, amb_count, cap)
 
 
 def downsample(octv: Octave, params: SiftParams, mixed: MixedOctave | None = None) -> torch.Tensor:
     """next base = G[-3][::2, ::2] (SS:209); certified mode takes it from the float64 level s."""
-    b, L, h, w = octv.gauss.shape
     if mixed is not None:
+        b, h, w, L = octv.batch, octv.height, octv.width, params.n_levels
         n_mid = mixed.mid.shape[1]
         if L - 3 < 1 or L - 3 > n_mid:
             raise _lib.FeatureCraftError("certified mode keeps levels 1..s; the next base is level s")
@@ -431,12 +446,13 @@ def downsample(octv: Octave, params: SiftParams, mixed: MixedOctave | None = Non
         out._fc_base32 = torch.empty(out.shape, dtype=torch.float32, device=out.device)
         _lib.call("fc_downsample2_dual", ptr(mixed.mid), b, n_mid, L - 4, h, w, ptr(out), ptr(out._fc_base32), stream_ptr())
         return out
+    b, L, h, w = octv.gauss.shape
     out = torch.empty((b, (h + 1) // 2, (w + 1) // 2), dtype=octv.gauss.dtype, device=octv.gauss.device)
     _lib.call("fc_downsample2", ptr(octv.gauss), params.fc_dtype, b, L, L - 3, h, w, ptr(out), stream_ptr())
     return out
 
 
-def _build_octaves(img, params: SiftParams, with_extrema: bool = True):
+def _build_octaves(img, params: SiftParams, with_extrema: bool = True, need_stack: bool = True):
     """-> (octaves, mixed companions or None per octave, per-octave undecided-pixel counters or None).  Certified mode
     that overflows its undecided-pixel list is detected by the callers (they read the counters with the keypoint counts)."""
     octaves, companions = [], []
@@ -446,7 +462,8 @@ def _build_octaves(img, params: SiftParams, with_extrema: bool = True):
         amb_counts = torch.empty(params.n_octaves, dtype=torch.int32, device=img.device)  # zeroed by the search kernels' launcher
     for o in range(params.n_octaves):
         if params.dtype == "mixed":
-            octv, mx = gauss_octave_mixed(img, params, o, with_extrema, value_bound=bound, amb_count=amb_counts[o:o + 1])
+            octv, mx = gauss_octave_mixed(img, params, o, with_extrema, value_bound=bound, amb_count=amb_counts[o:o + 1],
+                                          need_stack=need_stack)
             bound = octv.value_bound
         else:
             octv, mx = gauss_octave(img, params, o, with_extrema), None
@@ -634,7 +651,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     res = SiftResult(params, [])
     certified = params.dtype == "mixed"
     # A: scale space
-    octaves, companions, amb_dev = _build_octaves(img, params, True)
+    octaves, companions, amb_dev = _build_octaves(img, params, True, need_stack=keep_octaves)
     if keep_octaves:
         res.octaves = octaves
     work = [(o, k) for o in range(params.n_octaves) for k in scales]
@@ -644,7 +661,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     # one scan covers them all and one gather launch brings the cumulative keypoint counts at the block boundaries to
     # the host: keypoints of all blocks then live in one list, block after block, in the reference's order.
     # (Certified mode reads its per-octave undecided-pixel counters in the same synchronisation.)
-    rows = [octaves[o].gauss.shape[0] * octaves[o].height for o, _ in work]
+    rows = [octaves[o].batch * octaves[o].height for o, _ in work]
     row_start = [0]
     for r in rows:
         row_start.append(row_start[-1] + r)
@@ -653,7 +670,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
         counts = torch.empty(row_start[-1], dtype=torch.int32, device=dev)
         for i, (o, k) in enumerate(work):
             octv = octaves[o]
-            _lib.call("fc_mask_row_count", ptr(octv.extrema[k - 1]), octv.gauss.shape[0], octv.height, octv.width,
+            _lib.call("fc_mask_row_count", ptr(octv.extrema[k - 1]), octv.batch, octv.height, octv.width,
                       ptr(counts[row_start[i]:]), stream_ptr())
         row_offs = torch.empty(row_start[-1] + 1, dtype=torch.int32, device=dev)
         _lib.call("fc_exclusive_scan_i32", ptr(counts), row_start[-1], ptr(row_offs), ptr(scan_scratch(row_start[-1])), stream_ptr())
@@ -677,7 +694,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     state = []
     for i, (o, k) in enumerate(work):
         octv = octaves[o]
-        b, h = octv.gauss.shape[0], octv.height
+        b, h = octv.batch, octv.height
         n = kp_end[i] - kp_start[i]
         kps = kps_all[kp_start[i]:kp_end[i]]
         blk = ScaleBlock(o, k, kps)
@@ -704,7 +721,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
         with _stage("orientation"):
             orientation_bins(mag, obin, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]])
         state.append((mag, direction, sigma))
-    batch = octaves[0].gauss.shape[0]
+    batch = octaves[0].batch
     if total_kp == 0:
         for blk in res.blocks:
             blk.oriented = torch.empty((0, 4), dtype=torch.int32, device=dev)

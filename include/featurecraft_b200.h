@@ -242,6 +242,14 @@ FC_API int fc_gauss_octave_extrema_certified(const float* gauss, int batch, int 
                                       double contrast_th, double ratio_th, const float* value_bound, double eps_rel,
                                       uint32_t* extrema, int32_t* amb, int amb_cap, int32_t* amb_count, void* stream);
 
+/* fc_gauss_octave (float32, default radii 3/5/6/9/13 only) and fc_gauss_octave_extrema_certified fused: the float32
+ * levels never leave shared memory -- nothing but the search reads them in certified mode -- and the search runs on the
+ * DoG tiles in place.  Same outputs as the two calls (extrema [2][batch][h][(w+31)/32] is zeroed here, amb / amb_count
+ * as above); FC_ERR_UNSUPPORTED for other tap sets or images below 4 x 4: use the two calls then. */
+FC_API int fc_gauss_octave_search(const float* base, int batch, int height, int width, int n_levels, const double* taps_host,
+                           const int* tap_len_host, int first_is_identity, int filter, const float* value_bound,
+                           double eps_rel, uint32_t* extrema, int32_t* amb, int amb_cap, int32_t* amb_count, void* stream);
+
 /* Decides the amb entries on float64 DoG values and sets their bits in `extrema`: levels mid_first ..
  * mid_first + mid_count - 1 are read from `mid` ([batch][mid_count][h][w], fc_gauss_levels_f64), level 0 of an
  * octave > 0 (first_is_identity) from `base`, every other level is blurred on demand from `base` (float64) around the

@@ -266,3 +266,21 @@ def test_random_images_certified_equals_float64(S, seed):
     assert np.array_equal(np.isnan(a[1]).any(1), ~ok)
     if ok.any():
         assert np.linalg.norm(a[1][ok] - b[1][ok], axis=1).max() < 2e-5
+
+
+def test_fused_search_equals_two_kernel_form(S):
+    """fc_gauss_octave_search (blur + certified search in one kernel, no float32 stack written; what the pipeline runs)
+    against the two-kernel form (keep_octaves=True keeps the stack): same masks, same undecided decisions, same result;
+    sizes that exercise partial tiles (92 x 30 centre stride), several images, both filters."""
+    from exvision_featurecraft_b200 import synthetic
+
+    for shape, variant in (((2 * 60, 2 * 100), "app"), ((188, 376), "app"), ((96, 112), "script"), ((300, 96), "app")):
+        imgs = np.stack([synthetic.sift_image(*shape, seed=s) for s in (3, 4)])
+        p = S.SiftParams(dtype="mixed", variant=variant)
+        a = S.detect_and_describe(imgs, p, out_dtype=torch.float32)
+        b = S.detect_and_describe(imgs, p, out_dtype=torch.float32, keep_octaves=True)
+        assert b.octaves[0].gauss is not None
+        assert torch.equal(a.records, b.records) and torch.equal(a.counts, b.counts)
+        assert torch.equal(a.descriptors.nan_to_num(), b.descriptors.nan_to_num())
+        for blk_a, blk_b in zip(a.blocks, b.blocks):
+            assert torch.equal(blk_a.keypoints, blk_b.keypoints)
