@@ -59,6 +59,7 @@ class SiftWorkload:
         finally:
             self.sift.TIMER = None
         self.desc_per_image = res.total / self.batch
+        self.last = res
         return res
 
     def e2e_begin(self):
@@ -90,17 +91,52 @@ class SiftWorkload:
         tot = self.timer.totals()
         n = max(self.recorded_steps, 1)
         ms = tot.get("pyramid_o0", 0.0) / n
-        alg = 24.0 * self.batch * (2 * self.H) * (2 * self.W)  # 4 B base read + 5 x 4 B levels written per octave pixel
+        # SURVEY 8(d), pyramid + DoG + extrema row: 4 B base read + 5 x 4 B levels per octave pixel
+        alg = 24.0 * self.batch * (2 * self.H) * (2 * self.W)
         if self.mode == "f64":
-            alg *= 2
-        name = "gauss_octave_packed_kernel (octave 0)" if self.mode != "f64" else "gauss_octave_kernel<double> (octave 0)"
-        return [(name, alg, ms, "hbm")]
+            return [("gauss_octave_kernel<double> (octave 0, blur only)", 2 * alg, ms, "hbm")]
+        out = [("gauss_octave_packed_kernel<SEARCH> (octave 0: five blurs + DoG + certified 3x3x3 search fused; the float32 "
+                "levels stay in shared memory)", alg, ms, "hbm")]
+        blur = self._blur_only_ms()
+        if blur:
+            out.append(("gauss_octave_packed_kernel (octave 0, blur only, levels written: the stand-alone fc_gauss_octave)", alg, blur, "hbm"))
+        return out
+
+    def _blur_only_ms(self):
+        """the same octave through the stand-alone blur kernel (TMA-staged tiles, writes the five levels), CUDA events"""
+        import ctypes as C
+
+        from exvision_featurecraft_b200 import _lib
+        from exvision_featurecraft_b200.device import ptr, stream_ptr
+
+        torch, sift = self.torch, self.sift
+        b, h, w = self.batch, 2 * self.H, 2 * self.W
+        base = torch.rand((b, h, w), dtype=torch.float32, device="cuda")
+        out = torch.empty((b, 5, h, w), dtype=torch.float32, device="cuda")
+        flat, lens = sift._level_taps(self.params)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(4):
+            if i == 1:
+                ev[0].record()
+            _lib.call("fc_gauss_octave", ptr(base), _lib.FC_F32, b, h, w, 5, flat.ctypes.data_as(C.c_void_p), C.cast(lens, C.c_void_p),
+                      0, 0, 0.03, 10.0, ptr(out), None, stream_ptr())
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / 3
 
     def traffic(self, tr):
-        return tr["gauss_octave_packed_kernel"]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W) * (2 if self.mode == "f64" else 1)
+        key = "gauss_octave_search_kernel" if self.mode == "mixed" else "gauss_octave_kernel_f64"
+        return tr[key]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W)
 
     def stats(self):
-        return {"descriptors_per_image": self.desc_per_image, "scale_space": self.mode}
+        out = {"descriptors_per_image": self.desc_per_image, "scale_space": self.mode}
+        if self.mode == "mixed" and getattr(self, "last", None) is not None:
+            kp = sum(int(blk.keypoints.shape[0]) for blk in self.last.blocks)
+            out["keypoints_per_image"] = kp / self.batch
+            out["float64_decided_extrema_per_image"] = self.last.undecided_extrema / self.batch
+            if self.last.recheck_counts is not None:
+                out["float64_decided_orientations_per_image"] = int(self.last.recheck_counts.sum().item()) / self.batch
+        return out
 
     def extra(self):
         full = self.sift.StageTimer()

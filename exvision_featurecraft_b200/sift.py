@@ -247,6 +247,8 @@ class SiftResult:
     descriptors: torch.Tensor | None = None  # [M, 128]
     records: torch.Tensor | None = None      # [M, 2] int32: packed (row, col) | (octave, scale, bin), see unpack_records
     counts: torch.Tensor | None = None       # [B] int32 descriptors per image
+    undecided_extrema: int = 0               # certified mode: pixels the float64 repair kernel decided
+    recheck_counts: torch.Tensor | None = None  # certified mode: per (octave, scale) block, keypoints decided in float64
 
     @property
     def total(self) -> int:
@@ -682,13 +684,15 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
     if certified and any(c > m.amb_cap for c, m in zip(amb_counts, companions)):
         # more undecided pixels than the list holds (large exactly-flat regions): the float64 kernels decide everything
         return detect_and_describe(base, replace(params, dtype="f64"), out_dtype, keep_octaves)
+    res.undecided_extrema = int(sum(amb_counts))
     kp_start = [0] + kp_end[:-1]
     total_kp = kp_end[-1]
     kps_all = torch.empty((total_kp, 3), dtype=torch.int32, device=dev)
     bin_mask_all = torch.empty(max(total_kp, 1), dtype=torch.int64, device=dev)
     if certified:
         recheck_all = torch.empty(max(total_kp, 1), dtype=torch.int32, device=dev)
-        recheck_counts = torch.empty(len(work), dtype=torch.int32, device=dev)
+        recheck_counts = torch.zeros(len(work), dtype=torch.int32, device=dev)
+        res.recheck_counts = recheck_counts
     # C: keypoints, gradient fields, orientation histograms of every block; then ONE scan of all per-keypoint
     # orientation counts and one gather for the cumulative oriented counts
     state = []
