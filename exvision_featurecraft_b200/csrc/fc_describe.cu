@@ -379,9 +379,9 @@ __global__ void orientation_emit_kernel(const int32_t* __restrict__ keypoints, c
 // Certified mode: the keypoints orientation_kernel<.., kOriCoded> marked (bit 63) are decided here the way the float64
 // pipeline decides them -- float64 magnitudes from the float64 level, float64 window weights, the exact bin codes,
 // float64 sums rounded to float32 (:158-163), cut at float32(0.8) * max.  A small persistent grid walks the list the
-// histogram kernel appended to, one CTA of 8 warps per keypoint (windows reach 155 x 155 samples: a single warp would
+// histogram kernel appended to, one CTA of 16 warps per keypoint (windows reach 155 x 155 samples: a single warp would
 // need a millisecond for one of those); every lane owns a private histogram, sums are combined in a fixed order.
-static constexpr int kRecheckWarps = 8;
+static constexpr int kRecheckWarps = 16;
 static constexpr size_t kRecheckSmem = sizeof(double) * kRecheckWarps * (kOriBins + 1) * 33;
 
 __global__ void __launch_bounds__(kRecheckWarps * 32)
@@ -404,27 +404,46 @@ orientation_recheck_kernel(const double* __restrict__ levels, int n_planes, int 
     const int side = 2 * wrx + 1;
     const int r0 = max(ki - radius, 0), r1 = min(ki + radius, H - 1);
     const int c0 = max(kj - radius, 0), c1 = min(kj + radius, W - 1);
-    const int ncol = c1 - c0 + 1, total = ncol * (r1 - r0 + 1);
+    const int ncol = c1 - c0 + 1, chunks = (ncol + 31) >> 5, items = chunks * (r1 - r0 + 1);
     const int woff = (wry - ki) * side + (wrx - kj);
-    for (int i = threadIdx.x; i < total; i += kRecheckWarps * 32) {
-      const int rr = i / ncol;
-      const int r = r0 + rr, c = c0 + (i - rr * ncol);
-      const int ru = r > 0 ? r - 1 : 0, rd = r < H - 1 ? r + 1 : H - 1;
-      const int cl = c > 0 ? c - 1 : 0, cr = c < W - 1 ? c + 1 : W - 1;
-      const double gx = g[(size_t)r * W + cl] - g[(size_t)r * W + cr];
-      const double gy = g[(size_t)ru * W + c] - g[(size_t)rd * W + c];
-      const double m = sqrt(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)));
-      myh[(pk[(size_t)r * W + c] & 63u) * 33] += __dmul_rn(m, weights[woff + r * side + c]);
+    // a warp takes (row, 32-column chunk) items; the loads of four items are in flight before the first square root
+    // (with one item at a time a 155 x 155 window is a chain of ~100 dependent global round trips per thread)
+    constexpr int kUnroll = 4;
+    for (int it0 = warp; it0 < items; it0 += kRecheckWarps * kUnroll) {
+      double gx[kUnroll], gy[kUnroll], wv[kUnroll];
+      uint32_t bn[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int it = it0 + u * kRecheckWarps;
+        const int rr = it / chunks;
+        const int r = r0 + rr, c = c0 + ((it - rr * chunks) << 5) + lane;
+        gx[u] = gy[u] = wv[u] = 0.0;
+        bn[u] = kOriBins;
+        if (it < items && c <= c1) {
+          const int ru = r > 0 ? r - 1 : 0, rd = r < H - 1 ? r + 1 : H - 1;
+          const int cl = c > 0 ? c - 1 : 0, cr = c < W - 1 ? c + 1 : W - 1;
+          gx[u] = g[(size_t)r * W + cl] - g[(size_t)r * W + cr];
+          gy[u] = g[(size_t)ru * W + c] - g[(size_t)rd * W + c];
+          wv[u] = weights[woff + r * side + c];
+          bn[u] = pk[(size_t)r * W + c] & 63u;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const double m = sqrt(__dadd_rn(__dmul_rn(gx[u], gx[u]), __dmul_rn(gy[u], gy[u])));
+        myh[bn[u] * 33] += __dmul_rn(m, wv[u]);  // bin 36 collects the masked lanes and is never read
+      }
     }
     __syncthreads();
-    // thread q < 36 sums bin q: warps 0, 1, .. and within a warp lanes 0, 1, .. in order
-    if (threadIdx.x < kOriBins) {
+    // warp w sums bins w, w + 16, ..: lane l adds column l of the 16 private copies in warp order, then a fixed
+    // shuffle tree over the lanes (deterministic)
+    for (int bn = warp; bn < kOriBins; bn += kRecheckWarps) {
       double a = 0.0;
-      for (int w = 0; w < kRecheckWarps; ++w) {
-        const double* row = rc_hist + ((size_t)w * (kOriBins + 1) + threadIdx.x) * 33;
-        for (int l = 0; l < 32; ++l) a += row[l];
-      }
-      s_f[threadIdx.x] = (float)a;
+#pragma unroll
+      for (int w = 0; w < kRecheckWarps; ++w) a += rc_hist[((size_t)w * (kOriBins + 1) + bn) * 33 + lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) s_f[bn] = (float)a;
     }
     __syncthreads();
     if (warp == 0) {
@@ -487,10 +506,8 @@ static constexpr int kTrigStride = 2 + 32;
 
 // Persistent: every CTA converts the host tables once (Gaussian mask, bin edges, the fixed-point column deltas as
 // int32, cos / sin) into shared memory, then its warps walk the oriented keypoints with stride = warps in the grid.
-// LAYOUT: kDescPlanes = separate magnitude / direction planes, kDescCoded = `mag` holds certified mode's magnitude | code words
-// (gradient_codes_kernel): the descriptor bin is then integer arithmetic on the exact 5-degree sector,
-//   sector of (direction - theta) = (2 (o - b) - 2 + sub) mod 72,  bin = sector / 9   (theta = 10 b + 5),
-// so no float rounding can move a sample across a bin edge.
+// Input: separate magnitude / direction planes (float64 mode, and float32 planes of a caller's own stack).  The certified
+// mode's code-word planes go through descriptor_coded_kernel below.
 enum { kDescPlanes = 0, kDescCoded = 2 };
 
 // Output placement: without `remap` descriptor n of this call goes to row n.  With it (the batched pipeline) the rows
@@ -523,7 +540,7 @@ template <> struct Store4<__half> {
   }
 };
 
-template <typename T, typename OUT, int LAYOUT>
+template <typename T, typename OUT>
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, int W, const int32_t* __restrict__ oriented,
                   int n_oriented, const double* __restrict__ gmask, const double* __restrict__ trig, OUT* __restrict__ desc,
@@ -571,9 +588,8 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
 #pragma unroll
     for (int k = 0; k < 9; ++k) myh[k * 32] = ACC(0);
     __syncwarp();
-    constexpr bool CODED = LAYOUT == kDescCoded;
     const T* m = mag + (size_t)b * H * W;
-    const T* d = LAYOUT == kDescPlanes ? dir + (size_t)b * H * W : nullptr;
+    const T* d = dir + (size_t)b * H * W;
     const int4 ad4 = *reinterpret_cast<const int4*>(&sAd[bin][cx]);
     const int4 bd4 = *reinterpret_cast<const int4*>(&sBd[bin][cx]);
     const int ad[4] = {ad4.x, ad4.y, ad4.z, ad4.w}, bd[4] = {bd4.x, bd4.y, bd4.z, bd4.w};
@@ -582,7 +598,6 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
     const bool interior = (ki >= 12) && (ki < H - 12) && (kj >= 12) && (kj < W - 12);
     // all 8 gathers of the lane are issued before the first dependent histogram update
     T mv[2][4], dv[2][4];
-    int sect[2][4];  // CODED: 2 o - 1 + sub of the sample
 #pragma unroll
     for (int ry = 0; ry < 2; ++ry) {
       const int X0 = sXY[warp][cy + ry], Y0 = sXY[warp][16 + cy + ry];
@@ -592,17 +607,8 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
         const int Y = (Y0 + bd[rx]) >> 10;
         const bool in = interior || (((unsigned)X < (unsigned)W) && ((unsigned)Y < (unsigned)H));
         const int o = in ? Y * W + X : 0;  // one image plane has fewer than 2^30 pixels (checked on the host)
-        sect[ry][rx] = 0;
-        if constexpr (CODED) {
-          static_assert(!CODED || sizeof(T) == 4, "code words carry a float32 magnitude");
-          const uint32_t p = in ? reinterpret_cast<const uint32_t*>(m)[o] : 0u;
-          mv[ry][rx] = (T)__uint_as_float((p & ~255u) >> 1);
-          dv[ry][rx] = T(0);
-          sect[ry][rx] = 2 * (int)(p & 63u) - 1 + (int)((p >> 6) & 3u);
-        } else {
-          mv[ry][rx] = in ? m[o] : T(0);
-          dv[ry][rx] = in ? d[o] : T(0);
-        }
+        mv[ry][rx] = in ? m[o] : T(0);
+        dv[ry][rx] = in ? d[o] : T(0);
       }
     }
 #pragma unroll
@@ -615,12 +621,7 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
         ACC rel = Math<ACC>::add((ACC)dv[ry][rx], -theta_a);
         if (rel < ACC(0)) rel = Math<ACC>::add(rel, ACC(360));
         int hb;
-        if constexpr (CODED) {
-          int sc = sect[ry][rx] - (2 * bin + 1);  // in [-72, 72]
-          sc += sc < 0 ? 72 : 0;
-          sc -= sc >= 72 ? 72 : 0;
-          hb = (sc * 57) >> 9;                    // sc / 9 for 0 <= sc < 72
-        } else if constexpr (sizeof(ACC) == 4) {
+        if constexpr (sizeof(ACC) == 4) {
           // f32 mode: truncate rel / 45 and repair the one-off at the bin edges with a single compare
           hb = __float2int_rz(rel * 0.022222222f);
           hb += (rel >= 45.0f * (float)(hb + 1)) ? 1 : 0;
@@ -706,7 +707,7 @@ descriptor_kernel(const T* __restrict__ mag, const T* __restrict__ dir, int H, i
 // bins of two half cells, two 32-lane reductions) for only 8 samples per lane.  Here HALF a warp owns a keypoint and
 // a lane owns a whole cell: 16 samples per lane, no merge step, 16-lane reductions, and the fixed work is shared by
 // two keypoints per warp -- ~300 warp instructions per keypoint.  Arithmetic and summation order per cell (row-major
-// over its 4x4 samples, float32) are otherwise those of descriptor_kernel<float, ., kDescCoded>.
+// over its 4x4 samples, float32) are otherwise those of descriptor_kernel<float, .>.
 template <typename OUT>
 __global__ void __launch_bounds__(kDescWarps * 32)
 descriptor_coded_kernel(const uint32_t* __restrict__ codes, int H, int W, const int32_t* __restrict__ oriented, int n_oriented,
@@ -1026,14 +1027,14 @@ static int launch_descriptors(const void* magnitude, const void* direction, int 
     FC_CUDA_TRY(cudaGetDevice(&dev));
     FC_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-#define FC_LAUNCH(T, OUT, IL)                                                                                   \
+#define FC_LAUNCH(T, OUT)                                                                                       \
   do {                                                                                                            \
     static int per_sm = 0;                                                                                        \
     if (per_sm == 0)                                                                                              \
-      FC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descriptor_kernel<T, OUT, IL>, kDescWarps * 32, 0)); \
+      FC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descriptor_kernel<T, OUT>, kDescWarps * 32, 0)); \
     const int want = div_up(n_oriented, kDescWarps);                                                              \
     const int blocks = want < n_sm * per_sm ? want : n_sm * per_sm;                                               \
-    descriptor_kernel<T, OUT, IL><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
+    descriptor_kernel<T, OUT><<<blocks, kDescWarps * 32, 0, st>>>((const T*)magnitude, (const T*)direction, height, \
                                                                      width, oriented, n_oriented, gmask, trig, (OUT*)descriptors, place); \
   } while (0)
 #define FC_LAUNCH_CODED(OUT)                                                                                        \
@@ -1050,10 +1051,10 @@ static int launch_descriptors(const void* magnitude, const void* direction, int 
   else if (coded && out_dtype == FC_F64) FC_LAUNCH_CODED(double);
   else if (coded && out_dtype == FC_F16) FC_LAUNCH_CODED(__half);
   else if (coded) return FC_ERR_BAD_ARG;
-  else if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float, kDescPlanes);
-  else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double, kDescPlanes);
-  else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float, kDescPlanes);
-  else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double, kDescPlanes);
+  else if (dtype == FC_F32 && out_dtype == FC_F32) FC_LAUNCH(float, float);
+  else if (dtype == FC_F32 && out_dtype == FC_F64) FC_LAUNCH(float, double);
+  else if (dtype == FC_F64 && out_dtype == FC_F32) FC_LAUNCH(double, float);
+  else if (dtype == FC_F64 && out_dtype == FC_F64) FC_LAUNCH(double, double);
   else return FC_ERR_BAD_ARG;
 #undef FC_LAUNCH
 #undef FC_LAUNCH_CODED

@@ -1,10 +1,12 @@
 // Exact float32 brute-force 2-NN matcher on CUDA cores: the verification twin of the tcgen05 path and
 // the re-check kernel for the rows that path flags as ambiguous.
 //
-// cv2.BFMatcher().knnMatch(query, train, k=2) (APP/utils/keypoint_descriptor.py:338-342): L2 distance
+// The definition it implements is the oracle's (oracle/featurecraft_oracle.py, knn_match): L2 distance
 // accumulated in float32 as sum((a-b)^2) over the 128 components in order, sqrt, two smallest per query
-// row, ties -> lower train index; then the ratio test m.distance < t * n.distance (:345-349, evaluated
-// in double on the float32 distances, strict).
+// row, ties -> lower train index; then the ratio test m.distance < t * n.distance evaluated in double on
+// the float32 distances, strict (APP/utils/keypoint_descriptor.py:338-349).  That is exact against the
+// oracle; cv2.BFMatcher's own kernel sums with SIMD partial accumulators, so its distances can differ from
+// these in the last float32 ulp (<= 5e-6 in the golden case) and a ratio test that close can fall either way.
 #include "fc_common.cuh"
 
 namespace fc {

@@ -2,7 +2,9 @@
 
 ``knn2`` is cv2.BFMatcher().knnMatch(query, train, k=2) + ``m.distance < t * n.distance``:
 the tcgen05 path (``engine="tensor"``: fp16 GEMM candidate search, exact float32 re-rank, exact re-check
-of ambiguous rows) and its CUDA-core twin (``engine="exact"``) return the same arrays.
+of ambiguous rows) and its CUDA-core twin (``engine="exact"``) return the same arrays.  "Exact" is meant against the
+oracle's definition (sequential float32 sum of squares); OpenCV sums with SIMD partial accumulators, so its distances
+agree to the last float32 ulp only and a ratio test decided inside that ulp can differ.
 """
 from __future__ import annotations
 
