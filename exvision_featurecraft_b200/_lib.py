@@ -45,6 +45,7 @@ SIGNATURES = {
     "fc_status_string": (C.c_char_p, [_i]),
     "fc_last_cuda_error": (_i, []),
     "fc_launch_count": (C.c_ulonglong, []),
+    "fc_path_count": (C.c_ulonglong, [_i]),
     "fc_rgb_to_gray_u8": (_i, [_p, _i, _i, _i, _p, _p]),
     "fc_correlate_zero_pad_f64": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
     "fc_harris_response": (_i, [_p, _i, _i, _i, _i, _d, _d, _p, _p, _p]),
@@ -148,3 +149,12 @@ def call(name: str, *args) -> None:
 
 def launch_count() -> int:
     return int(load().fc_launch_count())
+
+
+PATHS = ("packed_blur", "fused_search", "mid_f64", "generic_octave", "repair_patch")  # fc_path enumerators
+
+
+def path_counts() -> dict:
+    """How often each scale-space kernel family has been launched in this process (fc_path_count)."""
+    lib = load()
+    return {name: int(lib.fc_path_count(i)) for i, name in enumerate(PATHS)}

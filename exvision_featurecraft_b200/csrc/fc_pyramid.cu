@@ -730,7 +730,7 @@ struct PackedTaps {
 static constexpr int kPTX = 96, kPTY = 32, kPP = 128;  // tile and shared pitch (floats)
 static constexpr int kPIH = kPTY + 2 * kFR;            // 58 input rows
 static constexpr int kPPairs = (kPTX + 28) / 2;        // 62 column pairs: smem columns 2 .. 125
-static constexpr size_t kPackedSmem = sizeof(float) * (size_t)(kPIH * kPP + 5 * kPTY * kPP);
+static constexpr size_t kPackedSmem = sizeof(float) * (size_t)(kPIH * kPP + 5 * kPTY * kPP) + 128;  // + alignment slack
 
 template <int L>
 __device__ __forceinline__ void packed_vertical_level(const PackedTaps& taps, float2 centre, const float2 (&s)[kFR + 1],
@@ -853,9 +853,12 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
                            const __grid_constant__ PackedTaps taps, float* __restrict__ gauss,
                            const __grid_constant__ CUtensorMap in_map, int use_tma, const SearchArgs sa) {
   constexpr int kStepX = SEARCH ? kSTX : kPTX, kStepY = SEARCH ? kSTY : kPTY;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // the TMA destination must be 128-byte aligned.  Every kernel's `extern __shared__` array is the same dynamic
+  // allocation and the alignment the toolchain gives it depends on the other declarations of the translation unit, so
+  // the base is rounded up here (the launcher allocates 128 bytes of slack) instead of trusting __align__.
+  extern __shared__ __align__(128) unsigned char packed_smem[];
   __shared__ __align__(8) uint64_t tile_bar;
-  float* sIn = reinterpret_cast<float*>(smem_raw);
+  float* sIn = reinterpret_cast<float*>(packed_smem + ((128u - (smem_addr(packed_smem) & 127u)) & 127u));
   if (threadIdx.x == 0) mbar_init(&tile_bar, 1);
   __syncthreads();
   uint32_t tma_phase = 0;
@@ -1142,81 +1145,91 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
 // come out of one pass over a shared-memory tile with the pair sums v[-k] + v[+k] shared between them:
 // tile = 116 x 32 outputs from 128 x 44 inputs, 19 + 24 float64 operations per pixel.
 struct MidTaps {
-  double t[2][8];  // t[l][k] = tap at distance k (centre first), zero beyond the radius
+  double t[2][13];  // t[l][k] = tap at distance k (centre first), zero beyond the radius
 };
-static constexpr int kMTX = 116, kMTY = 32, kMP = 128, kMR = 6;
+static constexpr int kMTY = 32, kMP = 128;
 static constexpr size_t kMidSmem = sizeof(double) * (size_t)(2 * kMTY * kMP);
 
-// The vertical pass reads its 20-row column segments straight from global memory (coalesced along the row, all 20
-// loads of a thread in flight at once, no staging tile and no barrier before the arithmetic starts); only the two
-// intermediate tiles live in shared memory (64 KB: three CTAs per SM).  A first version staged the input tile with
-// cp.async like the float32 kernel: 110 KB, two CTAs per SM, FP64 pipe 31 % busy -- it mostly waited for its own loads
-// and for the shared-memory port (20 + 16 eight-byte accesses per 8 outputs in the vertical pass alone).
-template <int RA, int RB>
-__global__ void __launch_bounds__(256, 3)
+// The vertical pass reads its column segments straight from global memory (coalesced along the row, all loads of a
+// thread in flight at once, no staging tile and no barrier before the arithmetic starts); only the two intermediate
+// tiles live in shared memory (64 KB: three CTAs per SM).  A first version staged the input tile with cp.async like the
+// float32 kernel: 110 KB, two CTAs per SM, FP64 pipe 31 % busy -- it mostly waited for its own loads and for the
+// shared-memory port (20 + 16 eight-byte accesses per 8 outputs in the vertical pass alone).
+// MR = radius class (halo of the tile: 128 - 2 MR output columns), RA / RB = radii the two levels are evaluated with
+// (<= MR; the tap table is zero beyond a level's true radius, and a zero tap adds an exact zero, so the values are those
+// of the level's own radius); RB = 0: one level only.  ROWS = output rows per vertical item (column segment of
+// ROWS + 2 MR values in registers).  The default levels are <6, 5, 6>; the other points of the UI ranges (sigma 1.6 .. 3,
+// s 2 .. 5: radii of the levels 1 .. s between 5 and 12) run in the classes MR = 6, 8, 10, 12, two levels per launch.
+template <int MR, int RA, int RB, int ROWS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid_constant__ MidTaps taps,
                      double* __restrict__ out, int n_planes, int plane0) {
-  static_assert(RA <= kMR && RB <= kMR, "radius class");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sTmp = reinterpret_cast<double*>(smem_raw);  // [2][kMTY][kMP]
-  const int x0 = blockIdx.x * kMTX, y0 = blockIdx.y * kMTY;
+  static_assert(RA <= MR && RB <= MR && MR <= 12 && MR % 2 == 0 && kMTY % ROWS == 0, "radius class");
+  constexpr int NL = RB > 0 ? 2 : 1;
+  constexpr int TX = kMP - 2 * MR;
+  extern __shared__ __align__(16) unsigned char mid_smem[];
+  double* sTmp = reinterpret_cast<double*>(mid_smem);  // [2][kMTY][kMP]
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * kMTY;
   const int b = blockIdx.z;
   const size_t plane = (size_t)H * W;
   const double* img = base + (size_t)b * plane;
-  // tmp column c <-> image column x0 - 6 + c; the vertical item (g, c) produces tmp rows 8g .. 8g+7 of column c
-  const bool interior = (x0 - kMR >= 0) && (x0 - kMR + kMP <= W) && (y0 - kMR >= 0) && (y0 + kMTY + kMR <= H);
+  // tmp column c <-> image column x0 - MR + c; the vertical item (g, c) produces tmp rows ROWS g .. ROWS g + ROWS - 1 of column c
+  const bool interior = (x0 - MR >= 0) && (x0 - MR + kMP <= W) && (y0 - MR >= 0) && (y0 + kMTY + MR <= H);
 #pragma unroll 1
-  for (int item = threadIdx.x; item < (kMTY / 8) * kMP; item += 256) {
+  for (int item = threadIdx.x; item < (kMTY / ROWS) * kMP; item += 256) {
     const int g = item >> 7, c = item & 127;
-    double v[8 + 2 * kMR];
+    double v[ROWS + 2 * MR];
     if (interior) {
-      const double* src = img + (size_t)(y0 - kMR + g * 8) * W + (x0 - kMR + c);
+      const double* src = img + (size_t)(y0 - MR + g * ROWS) * W + (x0 - MR + c);
 #pragma unroll
-      for (int k = 0; k < 8 + 2 * kMR; ++k) v[k] = src[(size_t)k * W];
+      for (int k = 0; k < ROWS + 2 * MR; ++k) v[k] = src[(size_t)k * W];
     } else {
-      const double* col = img + reflect_symm(x0 - kMR + c, W);
+      const double* col = img + reflect_symm(x0 - MR + c, W);
 #pragma unroll
-      for (int k = 0; k < 8 + 2 * kMR; ++k) v[k] = col[(size_t)reflect_symm(y0 - kMR + g * 8 + k, H) * W];
+      for (int k = 0; k < ROWS + 2 * MR; ++k) v[k] = col[(size_t)reflect_symm(y0 - MR + g * ROWS + k, H) * W];
     }
-    double* dst = sTmp + (g * 8) * kMP + c;
+    double* dst = sTmp + (g * ROWS) * kMP + c;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      double sp[kMR + 1];
+    for (int j = 0; j < ROWS; ++j) {
+      double sp[MR + 1];
 #pragma unroll
-      for (int k = 1; k <= kMR; ++k) sp[k] = v[j + kMR - k] + v[j + kMR + k];
-      double a = taps.t[0][0] * v[j + kMR], bb = taps.t[1][0] * v[j + kMR];
+      for (int k = 1; k <= MR; ++k) sp[k] = v[j + MR - k] + v[j + MR + k];
+      double a = taps.t[0][0] * v[j + MR];
 #pragma unroll
       for (int k = 1; k <= RA; ++k) a = fma(taps.t[0][k], sp[k], a);
-#pragma unroll
-      for (int k = 1; k <= RB; ++k) bb = fma(taps.t[1][k], sp[k], bb);
       dst[j * kMP] = a;
-      dst[kMTY * kMP + j * kMP] = bb;
+      if (NL == 2) {
+        double bb = taps.t[1][0] * v[j + MR];
+#pragma unroll
+        for (int k = 1; k <= RB; ++k) bb = fma(taps.t[1][k], sp[k], bb);
+        dst[kMTY * kMP + j * kMP] = bb;
+      }
     }
   }
   __syncthreads();
-  // horizontal pass: 4 outputs per item; tmp column 6 + o <-> output column x0 + o
+  // horizontal pass: 4 outputs per item; tmp column MR + o <-> output column x0 + o
   const bool vec_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   double* o0 = out + ((size_t)b * n_planes + plane0) * plane;
 #pragma unroll 1
-  for (int item = threadIdx.x; item < kMTY * (kMTX / 4); item += 256) {
-    const int y = item / (kMTX / 4), g = item - y * (kMTX / 4);
+  for (int item = threadIdx.x; item < kMTY * (TX / 4); item += 256) {
+    const int y = item / (TX / 4), g = item - y * (TX / 4);
     const int yy = y0 + y, xx = x0 + 4 * g;
     if (yy >= H || xx >= W) continue;
 #pragma unroll
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < NL; ++l) {
       const double2* src = reinterpret_cast<const double2*>(sTmp + l * kMTY * kMP + y * kMP + 4 * g);
-      double v[4 + 2 * kMR];
+      double v[4 + 2 * MR];
 #pragma unroll
-      for (int q = 0; q < (4 + 2 * kMR) / 2; ++q) {
+      for (int q = 0; q < (4 + 2 * MR) / 2; ++q) {
         const double2 t = src[q];
         v[2 * q] = t.x; v[2 * q + 1] = t.y;
       }
       double r[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        double acc = taps.t[l][0] * v[j + kMR];
+        double acc = taps.t[l][0] * v[j + MR];
 #pragma unroll
-        for (int k = 1; k <= (l == 0 ? RA : RB); ++k) acc = fma(taps.t[l][k], v[j + kMR - k] + v[j + kMR + k], acc);
+        for (int k = 1; k <= (l == 0 ? RA : RB); ++k) acc = fma(taps.t[l][k], v[j + MR - k] + v[j + MR + k], acc);
         r[j] = acc;
       }
       double* dst = o0 + (size_t)l * plane + (size_t)yy * W + xx;
@@ -1230,6 +1243,37 @@ gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid
       }
     }
   }
+}
+
+template <int MR, int RA, int RB, int ROWS, int MINB>
+static int launch_mid_f64(const double* base, int B, int H, int W, const MidTaps& mt, double* out, int n_planes, int plane0,
+                          cudaStream_t st) {
+  auto kern = gauss_mid_f64_kernel<MR, RA, RB, ROWS, MINB>;
+  FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMidSmem));
+  dim3 grid(div_up(W, kMP - 2 * MR), div_up(H, kMTY), B);
+  kern<<<grid, 256, kMidSmem, st>>>(base, H, W, mt, out, n_planes, plane0);
+  note_launch();
+  note_path(FC_PATH_MID_F64);
+  FC_RETURN_IF_LAUNCH_FAILED();
+  return FC_OK;
+}
+
+// one or two consecutive float64 levels (radii ra, rb <= 12; rb = 0: one level) into planes plane0, plane0 + 1 of `out`
+static int launch_mid_levels(const double* base, int B, int H, int W, const double* taps_a, int ra, const double* taps_b, int rb,
+                             double* out, int n_planes, int plane0, cudaStream_t st) {
+  MidTaps mt;
+  for (int k = 0; k < 13; ++k) {
+    mt.t[0][k] = k <= ra ? taps_a[ra + k] : 0.0;
+    mt.t[1][k] = (rb > 0 && k <= rb) ? taps_b[rb + k] : 0.0;
+  }
+  const int rm = ra > rb ? ra : rb;
+  if (ra == 5 && rb == 6) return launch_mid_f64<6, 5, 6, 8, 3>(base, B, H, W, mt, out, n_planes, plane0, st);
+#define FC_MID(MRC, ROWS, MINB)                                                                                     return rb > 0 ? launch_mid_f64<MRC, MRC, MRC, ROWS, MINB>(base, B, H, W, mt, out, n_planes, plane0, st)                          : launch_mid_f64<MRC, MRC, 0, ROWS, MINB>(base, B, H, W, mt, out, n_planes, plane0, st)
+  if (rm <= 6) FC_MID(6, 8, 3);
+  if (rm <= 8) FC_MID(8, 8, 2);
+  if (rm <= 10) FC_MID(10, 4, 2);
+  FC_MID(12, 4, 2);
+#undef FC_MID
 }
 
 // tensor map of a [B][H][W] float32 batch with a 128 x 58 x 1 box (the packed kernel's input tile); false when the
@@ -1310,6 +1354,7 @@ static int launch_octave_packed(const void* base, int B, int H, int W, const dou
   }
 #undef FC_PACKED
   note_launch();
+  note_path(search ? FC_PATH_FUSED_SEARCH : FC_PATH_PACKED_BLUR);
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
 }
@@ -1342,6 +1387,7 @@ static int launch_octave_cfg(const void* base, int B, int H, int W, const TapTab
   dim3 grid(div_up(W, TX), div_up(H, TY), B);
   kern<<<grid, 256, smem, st>>>((const T*)base, H, W, tab, rmax, (T*)gauss);
   note_launch();
+  note_path(FC_PATH_GENERIC_OCTAVE);
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
 }
@@ -1453,8 +1499,7 @@ static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_
 // edge tests (implementation_without_ui/SIFT/SIFT.py:202-215) are then evaluated on float64 DoG values, exactly as
 // the float64 kernels above do.
 static constexpr int kRepairCols = 2 * 24 + 3;  // columns x-1-R .. x+1+R of the vertical pass for the largest radius
-static constexpr int kPatchR = 13;               // radii up to this one work from a shared-memory copy of the support
-static constexpr int kPatchSide = 2 * kPatchR + 3;
+static constexpr int kPatchRMax = 16;            // radii up to this one work from a shared-memory copy of the support
 
 // 3x3 block of one blurred level around (y, x), with the operation order of the float64 octave kernels (vertical pass
 // with symmetric pair sums, then the horizontal one), so that the values -- and every tie between them -- are bit for
@@ -1487,7 +1532,6 @@ __device__ __forceinline__ void warp_blur3x3(const At& at, const double* __restr
 
 static constexpr int kRepairWarps = 4;
 
-static constexpr size_t kRepairPatchSmem = sizeof(double) * kRepairWarps * 2 * kPatchSide * kPatchSide;
 
 // largest radius among the levels of entry k that have to be blurred on demand (0: every level is stored)
 __device__ __forceinline__ int repair_radius(const TapTable<double>& tab, int k, int mid_first, int mid_count,
@@ -1503,12 +1547,12 @@ __device__ __forceinline__ int repair_radius(const TapTable<double>& tab, int k,
 
 // copy the (2 rm + 3)^2 support of an entry into the warp's patch buffer ('symm' reflected), asynchronously
 __device__ __forceinline__ void repair_stage_patch(const double* __restrict__ img, int H, int W, int y, int x, int rm,
-                                                   double* __restrict__ patch, int lane) {
-  if (rm > 0 && rm <= kPatchR) {
+                                                   double* __restrict__ patch, int patch_side, int lane) {
+  if (rm > 0 && 2 * rm + 3 <= patch_side) {
     const int side = 2 * rm + 3;
     for (int i = lane; i < side * side; i += 32) {
       const int r = i / side, c = i - r * side;
-      cp_async_elem<double>(patch + r * kPatchSide + c,
+      cp_async_elem<double>(patch + r * patch_side + c,
                             img + (size_t)reflect_symm(y - 1 - rm + r, H) * W + reflect_symm(x - 1 - rm + c, W));
     }
   }
@@ -1519,41 +1563,43 @@ __global__ void __launch_bounds__(kRepairWarps * 32)
 extrema_repair_kernel(const double* __restrict__ base, int first_is_identity, const double* __restrict__ mid, int mid_first,
                       int mid_count, int B, int H, int W, int L, const __grid_constant__ TapTable<double> tab, int filter,
                       double contrast_th, double ratio_th, const int4* __restrict__ amb, const int* __restrict__ amb_count,
-                      int amb_cap, uint32_t* __restrict__ extrema, int pitch) {
+                      int amb_cap, uint32_t* __restrict__ extrema, int pitch, int patch_side) {
   __shared__ double sG[kRepairWarps][4][9];  // levels k-1 .. k+2, 3x3 each (row-major)
   __shared__ double sTmp[kRepairWarps][3 * kRepairCols];
-  extern __shared__ __align__(16) double sPatchAll[];  // [warp][2][kPatchSide^2]: the entry being evaluated and the next one
+  extern __shared__ __align__(16) double sPatchAll[];  // [warp][2][patch_side^2]: the entry being evaluated and the next one
+  // (patch_side = 2 R + 3 for the largest on-demand radius R of this launch, 0 = no patch: support read from global memory)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = min(*amb_count, amb_cap);
   const size_t plane = (size_t)H * W;
   const int stride = gridDim.x * kRepairWarps;
-  double* bufs = sPatchAll + (size_t)warp * 2 * kPatchSide * kPatchSide;
+  const int patch_elems = patch_side * patch_side;
+  double* bufs = sPatchAll + (size_t)warp * 2 * patch_elems;
   int e = blockIdx.x * kRepairWarps + warp;
   int cur = 0;
   if (e < n) {
     const int4 ent = amb[e];
     repair_stage_patch(base + (size_t)ent.x * plane, H, W, ent.z, ent.w,
-                       repair_radius(tab, ent.y, mid_first, mid_count, first_is_identity), bufs, lane);
+                       repair_radius(tab, ent.y, mid_first, mid_count, first_is_identity), bufs, patch_side, lane);
   }
   for (; e < n; e += stride) {
     const int4 ent = amb[e];
     const int b = ent.x, k = ent.y, y = ent.z, x = ent.w;
     const double* img = base + (size_t)b * plane;
     const int rm = repair_radius(tab, k, mid_first, mid_count, first_is_identity);
-    const bool patched = rm > 0 && rm <= kPatchR;
+    const bool patched = rm > 0 && 2 * rm + 3 <= patch_side;
     // the support of the NEXT entry is requested before this one is evaluated: its memory latency hides behind the
     // ~800 warp instructions of the three on-demand blurs
     if (e + stride < n) {
       const int4 nx = amb[e + stride];
       repair_stage_patch(base + (size_t)nx.x * plane, H, W, nx.z, nx.w,
                          repair_radius(tab, nx.y, mid_first, mid_count, first_is_identity),
-                         bufs + (cur ^ 1) * kPatchSide * kPatchSide, lane);
+                         bufs + (cur ^ 1) * patch_elems, patch_side, lane);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncwarp();
-    const double* patch = bufs + cur * kPatchSide * kPatchSide + (rm + 1) * kPatchSide + (rm + 1);  // element (y, x)
+    const double* patch = bufs + cur * patch_elems + (rm + 1) * patch_side + (rm + 1);  // element (y, x)
     cur ^= 1;
     for (int q = 0; q < 4; ++q) {
       const int l = k - 1 + q;
@@ -1564,7 +1610,7 @@ extrema_repair_kernel(const double* __restrict__ base, int first_is_identity, co
         // centres satisfy 1 <= y <= H-3, 1 <= x <= W-3: the 3x3 block is inside the image
         if (lane < 9) sG[warp][q][lane] = src[(size_t)(y - 1 + lane / 3) * W + (x - 1 + lane % 3)];
       } else if (patched) {
-        warp_blur3x3([&](int dy, int dx) { return patch[dy * kPatchSide + dx]; }, tab.taps + tab.offset[l], tab.radius[l], lane,
+        warp_blur3x3([&](int dy, int dx) { return patch[dy * patch_side + dx]; }, tab.taps + tab.offset[l], tab.radius[l], lane,
                      sTmp[warp], sG[warp][q]);
       } else {
         warp_blur3x3([&](int dy, int dx) { return img[(size_t)reflect_symm(y + dy, H) * W + reflect_symm(x + dx, W)]; },
@@ -1668,17 +1714,20 @@ extern "C" int fc_gauss_levels_f64(const double* base, int batch, int height, in
     }
   }
   if (!symmetric) return FC_ERR_UNSUPPORTED;
-  if (level_count == 2 && lens[0] == 11 && lens[1] == 13) {  // the default s = 2 levels: radii 5 and 6
-    MidTaps mt;
-    for (int k = 0; k < 8; ++k) {
-      mt.t[0][k] = k <= 5 ? tp[5 + k] : 0.0;
-      mt.t[1][k] = k <= 6 ? tp[11 + 6 + k] : 0.0;
+  int rmax = 0, rmin = 1 << 30;
+  for (int l = 0; l < level_count; ++l) {
+    rmax = lens[l] / 2 > rmax ? lens[l] / 2 : rmax;
+    rmin = lens[l] / 2 < rmin ? lens[l] / 2 : rmin;
+  }
+  if (rmax <= 12 && rmin >= 1) {
+    // two levels per launch share the column pair sums (the default s = 2: radii 5 and 6 in one launch)
+    const double* q = tp;
+    for (int l = 0; l < level_count; l += 2) {
+      const int ra = lens[l] / 2, rb = l + 1 < level_count ? lens[l + 1] / 2 : 0;
+      const int rc = launch_mid_levels(base, batch, height, width, q, ra, q + lens[l], rb, out, level_count, l, st);
+      if (rc != FC_OK) return rc;
+      q += lens[l] + (l + 1 < level_count ? lens[l + 1] : 0);
     }
-    FC_CUDA_TRY(cudaFuncSetAttribute(gauss_mid_f64_kernel<5, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMidSmem));
-    dim3 grid(div_up(width, kMTX), div_up(height, kMTY), batch);
-    gauss_mid_f64_kernel<5, 6><<<grid, 256, kMidSmem, st>>>(base, height, width, mt, out, 2, 0);
-    note_launch();
-    FC_RETURN_IF_LAUNCH_FAILED();
     return FC_OK;
   }
   return launch_octave<double>(base, batch, height, width, level_count, tp, lens, 0, out, st);
@@ -1773,13 +1822,23 @@ extern "C" int fc_extrema_repair(const double* base, int first_is_identity, cons
     tp += n;
   }
   for (int l = n_levels; l < kMaxLevels; ++l) tab.radius[l] = tab.offset[l] = 0;
+  // shared-memory patch sized for the largest radius that is blurred on demand (levels that are not stored)
+  int r_demand = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const bool stored = (mid && l >= mid_first && l < mid_first + mid_count) || (l == 0 && first_is_identity);
+    if (!stored && tab.radius[l] > r_demand) r_demand = tab.radius[l];
+  }
+  const int patch_side = (r_demand > 0 && r_demand <= kPatchRMax) ? 2 * r_demand + 3 : 0;
+  const size_t smem = sizeof(double) * kRepairWarps * 2 * (size_t)patch_side * patch_side;
   const int want = div_up(amb_cap, kRepairWarps);
-  const int blocks = want < 148 * 3 ? want : 148 * 3;  // 3 CTAs of 60 KB per SM; the warps stride over the list
-  FC_CUDA_TRY(cudaFuncSetAttribute(extrema_repair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRepairPatchSmem));
-  extrema_repair_kernel<<<blocks, kRepairWarps * 32, kRepairPatchSmem, (cudaStream_t)stream>>>(
+  const int blocks = want < 148 * 3 ? want : 148 * 3;  // default radii: 3 CTAs of 54 KB per SM; the warps stride over the list
+  FC_CUDA_TRY(cudaFuncSetAttribute(extrema_repair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(sizeof(double) * kRepairWarps * 2 * (2 * kPatchRMax + 3) * (2 * kPatchRMax + 3))));
+  extrema_repair_kernel<<<blocks, kRepairWarps * 32, smem, (cudaStream_t)stream>>>(
       base, first_is_identity, mid, mid_first, mid_count, batch, height, width, n_levels, tab, filter, contrast_th, ratio_th,
-      reinterpret_cast<const int4*>(amb), amb_count, amb_cap, extrema, div_up(width, 32));
+      reinterpret_cast<const int4*>(amb), amb_count, amb_cap, extrema, div_up(width, 32), patch_side);
   note_launch();
+  if (patch_side > 0 || r_demand == 0) note_path(FC_PATH_REPAIR_PATCH);
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
 }

@@ -61,6 +61,14 @@ FC_API const char* fc_status_string(int status);
 FC_API int fc_last_cuda_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 FC_API unsigned long long fc_launch_count(void);
+/* which kernel family the scale-space calls of this process took (introspection for tests and bench.py): launches of
+ * the packed float32 blur kernel, of its fused blur + DoG + search form, of the two-level float64 kernel, of the
+ * generic level-by-level kernel, and fc_extrema_repair calls that worked from shared-memory patches */
+typedef enum fc_path {
+  FC_PATH_PACKED_BLUR = 0, FC_PATH_FUSED_SEARCH = 1, FC_PATH_MID_F64 = 2, FC_PATH_GENERIC_OCTAVE = 3, FC_PATH_REPAIR_PATCH = 4,
+  FC_PATH_COUNT = 5
+} fc_path;
+FC_API unsigned long long fc_path_count(int path);
 
 /* ---------------------------------------------------------------------------------------------
  * Corner detectors

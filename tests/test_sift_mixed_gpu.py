@@ -225,16 +225,33 @@ def test_odd_and_tiny_sizes_equal_float64(S, shape):
 
 
 @pytest.mark.parametrize("params", [dict(n_octaves=5, s_value=3, sigma_base=2.5), dict(n_octaves=4, s_value=2, sigma_base=3.0),
-                                    dict(n_octaves=6, s_value=4, sigma_base=1.6), dict(n_octaves=4, s_value=2, sigma_base=1.6, variant="script"),
+                                    dict(n_octaves=6, s_value=4, sigma_base=1.6), dict(n_octaves=4, s_value=5, sigma_base=3.0),
+                                    dict(n_octaves=4, s_value=5, sigma_base=1.6), dict(n_octaves=4, s_value=3, sigma_base=1.9),
+                                    dict(n_octaves=8, s_value=4, sigma_base=2.2),
+                                    dict(n_octaves=4, s_value=2, sigma_base=1.6, variant="script"),
                                     dict(n_octaves=4, s_value=2, sigma_base=2.0, variant="script", contrast_th=0.01, ratio_th=6.0)])
 def test_ui_parameter_ranges_equal_float64(S, params):
     """Points of the app's parameter ranges (FeatureCraft_UI.py:197-273: octaves 4-8, s 2-5, sigma 1.6-3, r 6-12) and the
-    script filter: non-default radii take the generic float32 / float64 blur kernels, more DoG levels the tiled
-    certified search; both filters go through the float64 repair.  Certified mode must equal float64 mode everywhere."""
-    from exvision_featurecraft_b200 import synthetic
+    script filter.  Certified mode must equal float64 mode everywhere, and it must get there on the fast kernels: the
+    float64 levels 1 .. s (radii 5 .. 12 over the whole range) through the two-level kernel in its radius classes, never
+    through the generic level-by-level one, and the float64 repair from shared-memory patches whenever the largest
+    on-demand radius is <= 16."""
+    from exvision_featurecraft_b200 import _lib, synthetic
 
     base = synthetic.sift_image(160, 192, seed=41)
+    before = _lib.path_counts()
     a = S.detect_and_describe(base, S.SiftParams(dtype="mixed", **params), out_dtype=torch.float32)
+    after = _lib.path_counts()
+    took = {k: after[k] - before[k] for k in after}
+    p = S.SiftParams(dtype="mixed", **params)
+    radii = [S.kernel_radius(x) for x in S.sigma_levels(p.sigma_base, p.s_value)]
+    assert took["mid_f64"] == p.n_octaves * ((p.s_value + 1) // 2), took
+    # the only generic launches are the float32 stacks of non-default radii (one per octave)
+    assert took["generic_octave"] == (0 if radii == [3, 5, 6, 9, 13] else p.n_octaves), took
+    if radii == [3, 5, 6, 9, 13]:
+        assert took["fused_search"] == p.n_octaves, took
+    if max(radii) <= 16:
+        assert took["repair_patch"] == p.n_octaves, took
     b = S.detect_and_describe(base, S.SiftParams(dtype="f64", **params), out_dtype=torch.float64)
     pa, da = a.assemble(1)[0]
     pb, db = b.assemble(1)[0]
