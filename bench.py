@@ -409,7 +409,7 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
-SECONDARY = (("harris", 5), ("match", 5), ("pipeline4k", 2), ("sift_f64", 3))
+SECONDARY = (("harris", 5), ("match", 5), ("pipeline4k", 2), ("sift_f64", 3), ("sift_ui", 3))
 
 
 def main():
@@ -482,15 +482,17 @@ def main():
             sub_args = argparse.Namespace(**vars(args))
             sub_args.batch = None
             sub_args.sift_dtype = "f64" if name == "sift_f64" else None
-            cls = table["sift" if name == "sift_f64" else name]
-            if name == "sift_f64":
+            cls = table["sift" if name in ("sift_f64", "sift_ui") else name]
+            if name in ("sift_f64", "sift_ui"):
                 sub_args.batch = 8
+            # another point of the app's parameter ranges (FeatureCraft_UI.py:197-229): 6 levels, radii 5 .. 16
+            sub_args.sift_params = {"sigma_base": 2.5, "s_value": 3} if name == "sift_ui" else None
             w2 = cls(sub_args)
             try:
                 sub = measure(w2, env, k, 3, sample_clocks=False)
                 for drop in ("higher_is_better", "scaling", "vs_baseline", "data", "n_gpus", "clocks"):
                     sub.pop(drop, None)
-                if rank == 0 and not args.no_cpu_baseline and name not in ("sift_f64", "pipeline4k", "allpairs"):
+                if rank == 0 and not args.no_cpu_baseline and name not in ("sift_f64", "sift_ui", "pipeline4k", "allpairs"):
                     sub["cpu_baseline"] = cpu_baseline(w2)
                 line["secondary"][name] = sub
             except Exception as exc:  # a secondary workload must not take the headline down with it

@@ -19,12 +19,18 @@ class SiftWorkload:
     def __init__(self, args):
         self.batch = args.batch or 16
         self.mode = getattr(args, "sift_dtype", None) or "mixed"
+        self.overrides = dict(getattr(args, "sift_params", None) or {})  # non-default point of the UI parameter ranges
         self.dtype = {"mixed": "f32 arithmetic, f64-certified decisions", "f64": "f64"}[self.mode]
         self.desc_per_image = None
 
     def describe(self, world):
-        return {"workload": "config[1]: SIFT keypoints + descriptors, %d synthetic 1024x1024 float64 images per step per GPU "
-                            "(x2 up-sample -> 2048^2 base, 4 octaves, 5 Gaussian levels, sigma 1.6, app filter variant)" % self.batch,
+        if self.overrides:
+            what = "SIFT keypoints + descriptors at another point of the app's parameter ranges %s, %d synthetic 1024x1024 float64 images per step per GPU" % (
+                self.overrides, self.batch)
+        else:
+            what = ("config[1]: SIFT keypoints + descriptors, %d synthetic 1024x1024 float64 images per step per GPU "
+                    "(x2 up-sample -> 2048^2 base, 4 octaves, 5 Gaussian levels, sigma 1.6, app filter variant)" % self.batch)
+        return {"workload": what,
                 "images_per_step_per_gpu": self.batch, "image": [self.H, self.W], "sharding": "images, no collective",
                 "l2": "per-step working set (%.1f GB) exceeds the 126 MB L2; no flush needed" % (self.batch * 0.5)}
 
@@ -35,7 +41,7 @@ class SiftWorkload:
         from exvision_featurecraft_b200 import sift, synthetic
 
         self.torch, self.sift = torch, sift
-        self.params = sift.SiftParams(dtype=self.mode)
+        self.params = sift.SiftParams(dtype=self.mode, **self.overrides)
         imgs = np.stack([synthetic.sift_image(self.H, self.W, seed=rank * 4 + i, max_blobs=1024) for i in range(min(4, self.batch))])
         host = np.concatenate([imgs] * ((self.batch + len(imgs) - 1) // len(imgs)))[: self.batch]
         self.host_in = torch.from_numpy(np.ascontiguousarray(host)).pin_memory()
@@ -95,6 +101,10 @@ class SiftWorkload:
         alg = 24.0 * self.batch * (2 * self.H) * (2 * self.W)
         if self.mode == "f64":
             return [("gauss_octave_kernel<double> (octave 0, blur only)", 2 * alg, ms, "hbm")]
+        if self.overrides:
+            nl = self.params.n_levels
+            return [("gauss_octave_kernel<float> (octave 0, %d levels, blur only: non-default radii)" % nl,
+                     (4.0 + 4.0 * nl) * self.batch * (2 * self.H) * (2 * self.W), ms, "hbm")]
         out = [("gauss_octave_packed_kernel<SEARCH> (octave 0: five blurs + DoG + certified 3x3x3 search fused; the float32 "
                 "levels stay in shared memory)", alg, ms, "hbm")]
         blur = self._blur_only_ms()
@@ -125,6 +135,8 @@ class SiftWorkload:
         return ev[0].elapsed_time(ev[1]) / 3
 
     def traffic(self, tr):
+        if self.overrides:
+            return None
         key = "gauss_octave_search_kernel" if self.mode == "mixed" else "gauss_octave_kernel_f64"
         return tr[key]["bytes_per_octave_pixel"] * self.batch * (2 * self.H) * (2 * self.W)
 

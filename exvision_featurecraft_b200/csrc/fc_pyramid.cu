@@ -1656,6 +1656,8 @@ static int launch_extrema_certified(const void* gauss, int B, int H, int W, int 
     if (nd == 4) return launch_extrema_strip<4, true>(gauss, B, H, W, filter, cth, rth, extrema, st, ca);
     if (nd == 3) return launch_extrema_strip<3, true>(gauss, B, H, W, filter, cth, rth, extrema, st, ca);
     if (nd == 5) return launch_extrema_strip<5, true>(gauss, B, H, W, filter, cth, rth, extrema, st, ca);
+    if (nd == 6) return launch_extrema_strip<6, true>(gauss, B, H, W, filter, cth, rth, extrema, st, ca);
+    if (nd == 7) return launch_extrema_strip<7, true>(gauss, B, H, W, filter, cth, rth, extrema, st, ca);
   }
   switch (nd) {
     case 3: return launch_extrema_nd<float, 3, true>(gauss, B, H, W, 0, filter, cth, rth, extrema, st, ca);
