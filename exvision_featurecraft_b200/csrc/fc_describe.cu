@@ -783,17 +783,23 @@ descriptor_coded_kernel(const uint32_t* __restrict__ codes, int H, int W, const 
         }
       }
     }
-    const int cb = 2 * bin + 2;
+    // sector of (direction - theta) = (2 o + sub) - (2 bin + 2) mod 72 and bin = sector / 9.  72 = 8 * 9, so with the
+    // offset +72 folded into the constant (sc in [0, 144]) the wrap-around is the `& 7` of the quotient:
+    // ((sc * 57) >> 9) & 7 == (sc mod 72) / 9 for every sc < 200; shifted by 7 it is the byte offset of the lane's bin.
+    const int cb = 70 - 2 * bin;
+    const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(myh);
 #pragma unroll
     for (int ry = 0; ry < 4; ++ry) {
 #pragma unroll
       for (int rx = 0; rx < 4; ++rx) {
         const uint32_t p = pv[ry][rx];
         const float wv = __fmul_rn(__uint_as_float((p & ~255u) >> 1), wmask[ry][rx]);
-        int sc = 2 * (int)(p & 63u) + (int)((p >> 6) & 3u) - cb;  // sector of (direction - theta), in [-72, 72]
-        sc += sc < 0 ? 72 : 0;
-        sc -= sc >= 72 ? 72 : 0;
-        myh[((sc * 57) >> 9) * 32] += wv;  // sc / 9 for 0 <= sc < 72
+        const uint32_t sc = 2u * (p & 63u) + ((p >> 6) & 3u) + (uint32_t)cb;
+        const uint32_t a = hbase + (((sc * 57u) >> 2) & 0x380u);
+        float cur;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur) : "r"(a));
+        cur = __fadd_rn(cur, wv);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(cur) : "memory");
       }
     }
     // normalise / clip [2^-10, 0.2] / normalise (:281-287); sums over the 16 lanes of the half warp
