@@ -253,6 +253,14 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
     const T* mrow = m + first;
     const uint8_t* orow = PACKED ? nullptr : ob + first;
     const T* wrow = weights + (woff + r0 * side + cb);
+    // kOriCoded: separable float32 weights, table = [wy: 2 wry + 1 | wx: 2 wrx + 1] with w(dy, dx) = wy[dy] * wx[dx]
+    // (exp(-dy^2 / 2 sigma^2) / (2 pi sigma^2) and exp(-dx^2 / 2 sigma^2): two more float32 roundings per sample, covered
+    // by `tol`).  The lane's column factors never change and a row needs one factor: one gather per sample instead of two.
+    const float* wy_tab = reinterpret_cast<const float*>(weights) + (wry - ki);             // wy_tab[image row]
+    const float* wx_tab = reinterpret_cast<const float*>(weights) + (2 * wry + 1) + (wrx - kj);  // wx_tab[image column]
+    float cw[NR];
+#pragma unroll
+    for (int u = 0; u < NR; ++u) cw[u] = (PACKED && cok[u]) ? wx_tab[cb + u * LPK] : 0.f;
     for (int rr = r0; rr <= r1; rr += NROWS) {
       int bins[NROWS][NR];
       T ws[NROWS][NR];
@@ -260,6 +268,8 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
       for (int v = 0; v < NROWS; ++v) {
         const bool row_ok = rr + v <= r1;
         const T* wv = wrow + v * side;
+        float rw = 0.f;
+        if (PACKED && row_ok) rw = wy_tab[rr + v];
 #pragma unroll
         for (int u = 0; u < NR; ++u) {
           bins[v][u] = kOriBins;  // the dropped bin
@@ -268,7 +278,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
             if constexpr (PACKED) {
               const uint32_t p = (prow + (ptrdiff_t)v * W)[u * LPK];
               bins[v][u] = (int)(p & 63u);
-              ws[v][u] = (T)__fmul_rn(__uint_as_float((p & ~255u) >> 1), (float)wv[u * LPK]);
+              ws[v][u] = (T)__fmul_rn(__uint_as_float((p & ~255u) >> 1), __fmul_rn(rw, cw[u]));
             } else {
               bins[v][u] = (orow + (ptrdiff_t)v * W)[u * LPK];
               ws[v][u] = Math<T>::mul((mrow + (ptrdiff_t)v * W)[u * LPK], wv[u * LPK]);
@@ -307,7 +317,9 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
       for (int c = c0 + sub; c <= c1; c += LPK) {
         if constexpr (PACKED) {
           const uint32_t p = pk[rr * W + c];
-          hme[(p & 63u) * PITCH] += (T)__fmul_rn(__uint_as_float((p & ~255u) >> 1), (float)weights[woff + rr * side + c]);
+          const float* wt = reinterpret_cast<const float*>(weights);
+          hme[(p & 63u) * PITCH] += (T)__fmul_rn(__uint_as_float((p & ~255u) >> 1),
+                                                 __fmul_rn(wt[wry - ki + rr], wt[2 * wry + 1 + wrx - kj + c]));
         } else {
           hme[ob[rr * W + c] * PITCH] += Math<T>::mul(m[rr * W + c], weights[woff + rr * side + c]);
         }

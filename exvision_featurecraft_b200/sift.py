@@ -533,14 +533,26 @@ def _orientation_weights(sigma, h, w, dtype):
     return radius, ry, rx, _cached(("ori", float(sigma), ry, rx), lambda: gaussian_window_table(sigma, ry, rx), dtype)
 
 
+def separable_window_table(sigma, ry, rx):
+    """Certified mode's float32 orientation weights: gaussian_filter_kernel(sigma)[dy, dx] = wy[dy] * wx[dx] with
+    wy = exp(-dy^2 / 2 sigma^2) / (2 pi sigma^2), wx = exp(-dx^2 / 2 sigma^2); table = [wy (2 ry + 1) | wx (2 rx + 1)].
+    The factorisation is exact in real arithmetic; its float32 roundings are part of orientation_tolerance."""
+    dy = np.arange(-ry, ry + 1, dtype=np.float64)
+    dx = np.arange(-rx, rx + 1, dtype=np.float64)
+    wy = np.exp(-(dy ** 2) / (2 * sigma ** 2)) / (2 * np.pi * (sigma ** 2))
+    wx = np.exp(-(dx ** 2) / (2 * sigma ** 2))
+    return np.concatenate([wy, wx])
+
+
 def orientation_tolerance(radius: int) -> float:
     """Relative error bound of a float32 orientation bin of certified mode against the float64 sum, doubled (the bin
-    and the 0.8 * max cut both carry it): magnitudes are rounded to 16 mantissa bits (2^-17), weights and products to
-    float32 (2 x 2^-24), and a lane adds at most ceil((2r+1)/lanes) * (2r+1) terms before the lanes are combined."""
+    and the 0.8 * max cut both carry it): magnitudes are rounded to 16 mantissa bits (2^-17), the two weight factors,
+    their product and the sample product to float32 (4 x 2^-24), and a lane adds at most ceil((2r+1)/lanes) * (2r+1)
+    terms before the lanes are combined."""
     lanes = 8 if radius <= 10 else (16 if radius <= 15 else 32)
     side = 2 * radius + 1
     per_lane = -(-side // lanes) * side
-    return 2.0 * (2.0 ** -17 + (per_lane + lanes + 4) * 2.0 ** -24)
+    return 2.0 * (2.0 ** -17 + (per_lane + lanes + 6) * 2.0 ** -24)
 
 
 def orientation_bins(mag, obin, keypoints, n, sigma, bin_mask):
@@ -556,8 +568,8 @@ def orientation_bins_certified(levels64, plane, codes, keypoints, n, sigma, bin_
     """Certified mode: float32 histograms from the code words, then the float64 decision of the keypoints whose
     0.8 * max comparison the float32 error bound cannot guarantee (recheck_list: int32 [n] scratch, recheck_count: [1])."""
     b, h, w = codes.shape
-    radius, ry, rx, w32 = _orientation_weights(sigma, h, w, torch.float32)
-    _, _, _, w64 = _orientation_weights(sigma, h, w, torch.float64)
+    radius, ry, rx, w64 = _orientation_weights(sigma, h, w, torch.float64)
+    w32 = _cached(("ori_sep", float(sigma), ry, rx), lambda: separable_window_table(sigma, ry, rx), torch.float32)
     _lib.call("fc_orientation_bins_coded", ptr(codes), b, h, w, ptr(keypoints), n, ptr(w32), radius, ry, rx,
               float(orientation_tolerance(radius)), ptr(bin_mask), ptr(recheck_list), ptr(recheck_count), stream_ptr())
     _lib.call("fc_orientation_recheck", ptr(levels64), levels64.shape[1], plane, ptr(codes), b, h, w, ptr(keypoints), n,

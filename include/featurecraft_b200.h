@@ -298,7 +298,10 @@ FC_API int fc_orientation_bins(const void* magnitude, const uint8_t* orientation
                         int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
 /* certified mode: float32 histograms from fc_gradient_codes' words; a keypoint with a bin within
  * tolerance * max of the cut gets bit 63 of its mask set instead of a decision and its index appended to
- * recheck_list (int32 [n_keypoints]; recheck_count[0] is zeroed first) ... */
+ * recheck_list (int32 [n_keypoints]; recheck_count[0] is zeroed first) ...
+ * `weights` here is the SEPARABLE float32 form of the same window: (2 table_ry + 1) row factors
+ * exp(-dy^2 / 2 sigma^2) / (2 pi sigma^2) followed by (2 table_rx + 1) column factors exp(-dx^2 / 2 sigma^2); the
+ * tolerance has to cover the extra float32 roundings (see sift.orientation_tolerance). */
 FC_API int fc_orientation_bins_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* keypoints,
                               int n_keypoints, const float* weights, int radius, int table_ry, int table_rx,
                               double tolerance, uint64_t* bin_mask, int32_t* recheck_list, int32_t* recheck_count,
