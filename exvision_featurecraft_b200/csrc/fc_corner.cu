@@ -582,6 +582,229 @@ lambda5_ring_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per
 }
 
 // ------------------------------------------------------------------------------------------------
+// lambda-minus, packed form: the integer half of the kernel in 16-bit lanes
+// ------------------------------------------------------------------------------------------------
+// ncu on lambda5_ring_kernel: 945 instructions per thread and row (4 pixels), 240 of them float64 (the LAPACK
+// sequence, irreducible) and ~420 the K_X gradients: per row every one of the 12 columns was unpacked from 5 rows and
+// pushed through both 5-tap kernels, every gradient through a 5x2-tap sum.  Here
+//   * values live as PAIRS of 16-bit lanes in one register (every intermediate fits: |.| <= 12240), encoded as
+//     hi * 65536 + lo with lo signed, so plain 32-bit adds / subtracts are exact lane-wise arithmetic and one IADD3
+//     adds three pairs.  Pairs at even columns are E[j] = (v[2j], v[2j+1]); the odd-aligned O[j] = (v[2j+1], v[2j+2])
+//     come from one PRMT -- built from unsigned quantities only, where the encoding has no borrow;
+//   * both 5-tap kernels are two box filters: (1,2,3,2,1) = box3 * box3 and (2,3,5,3,2) = 2 * (1,2,3,2,1) - box3;
+//   * K_X is separable in the other direction too (K_Y = K_X^T), so  gy = A'(r+2) - A'(r-2) + B'(r+1) - B'(r-1)  with
+//     A', B' the HORIZONTAL kernels of single rows: each row is filtered once, when it enters, and kept in a
+//     per-thread shared-memory ring (5 rows x 32 bytes); the vertical kernels of gx keep running box sums in registers.
+// A row costs ~125 integer instructions instead of ~420; sums, quotients and the eigenvalue sequence are unchanged.
+struct LamPairs {
+  uint32_t e[6];
+};
+
+__device__ __forceinline__ LamPairs lam_unpack(const uint32_t (&w)[3]) {
+  LamPairs v;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    v.e[2 * q] = __byte_perm(w[q], 0u, 0x4140u);      // (byte 0, byte 1) as 16-bit lanes
+    v.e[2 * q + 1] = __byte_perm(w[q], 0u, 0x4342u);  // (byte 2, byte 3)
+  }
+  return v;
+}
+
+// odd-aligned pair (x[2j+1], x[2j+2]) of two even-aligned pairs with non-negative lanes
+__device__ __forceinline__ uint32_t lam_odd(uint32_t ej, uint32_t ej1) { return __byte_perm(ej, ej1, 0x5432u); }
+
+// sign-extended low lane: PTX prmt replicates the sign of a byte when bit 3 of its selector nibble is set
+// (__byte_perm only honours the low three bits)
+__device__ __forceinline__ int lam_lo(uint32_t p) {
+  int r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(p), "r"(0u), "r"(0x9910u));
+  return r;
+}
+__device__ __forceinline__ int lam_hi(uint32_t p) { return (int)(p + 0x8000u) >> 16; }         // high lane incl. the borrow
+
+__global__ void __launch_bounds__(kStripThreads, 4)
+lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double* __restrict__ out,
+                      unsigned long long* __restrict__ img_max_bits) {
+  __shared__ int4 sRing[5 * 3 * kStripThreads];   // [slot][xx, xy, yy][thread]: row sums of the last 5 rows
+  extern __shared__ __align__(16) uint4 sHor[];   // [row % 5][A', B'][thread]: horizontal kernels of the last 5 rows (dynamic: 20 KB)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * kStripWarps + warp;
+  const int strip_c0 = strip * kStripCols;
+  if (strip_c0 >= W) return;  // warp-uniform, no block-wide barrier in this kernel
+  const int c0 = strip_c0 + lane * 4;
+  const bool active = c0 < W;
+  const size_t img_off = (size_t)blockIdx.z * H * W;
+  const uint8_t* img = gray + img_off;
+  double* o = out + img_off;
+  const int y0 = blockIdx.y * rows_per_band;
+  const int y1 = min(y0 + rows_per_band, H);
+  const bool cols_interior = (strip_c0 - 2 >= 0) && (strip_c0 + kStripCols + 1 <= W - 1);
+  int4* ring = sRing + threadIdx.x;
+  uint4* hor = sHor + threadIdx.x;
+  uint32_t Sxx[4], Syy[4];
+  long long Sxy[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { Sxx[j] = 0u; Syy[j] = 0u; Sxy[j] = 0; }
+#pragma unroll
+  for (int i = 0; i < 15; ++i) ring[i * kStripThreads] = make_int4(0, 0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) hor[i * kStripThreads] = make_uint4(0u, 0u, 0u, 0u);
+  // the thread's three words of a row (columns c0-4 .. c0+7), zero outside the image (padding_matrix)
+  const int wi = c0 >> 2, nw = W >> 2;
+  const bool ok0 = wi - 1 >= 0 && wi - 1 < nw, ok1 = wi < nw, ok2 = wi + 1 < nw;
+  auto load_row = [&](int row, uint32_t (&w)[3]) {
+    w[0] = w[1] = w[2] = 0u;
+    if (row >= 0 && row < H) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (size_t)row * W) + wi;
+      if (ok0) w[0] = __ldg(p - 1);
+      if (ok1) w[1] = __ldg(p);
+      if (ok2) w[2] = __ldg(p + 1);
+    }
+  };
+  // vertical state of the gx kernels: raw pairs of rows q-2, q-1 and box sums s(q-3), s(q-2) when row q enters
+  LamPairs vA, vB, sP, sC;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) vA.e[j] = vB.e[j] = sP.e[j] = sC.e[j] = 0u;
+  uint32_t nxt[3];
+  load_row(y0 - 4, nxt);
+  double local_max = -INFINITY;
+  int slot = 0;   // row-sum ring
+  int hslot = 0;  // slot of the entering row in the horizontal ring (rows older by 4, 3, 1 sit at +1, +2, +4 mod 5)
+#pragma unroll 1
+  for (int q = y0 - 4; q <= y1 + 3; ++q) {  // row q enters; hr = q - 2 is the gradient row, r = q - 4 the output row
+    uint32_t w[3] = {nxt[0], nxt[1], nxt[2]};
+    load_row(q + 1, nxt);  // consumed one iteration later
+    const LamPairs vN = lam_unpack(w);
+    // horizontal kernels of row q at the even pairs j = 1..4 (columns c0-2 .. c0+5)
+    uint32_t od[5], se[5], so[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) od[j] = lam_odd(vN.e[j], vN.e[j + 1]);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) so[j] = vN.e[j] + od[j] + vN.e[j + 1];
+#pragma unroll
+    for (int j = 1; j < 5; ++j) se[j] = od[j - 1] + vN.e[j] + od[j];
+    uint32_t An[4], Bn[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      An[p] = so[p] + se[p + 1] + so[p + 1];
+      Bn[p] = 2u * An[p] - se[p + 1];
+    }
+    const int s1 = hslot + 1 >= 5 ? hslot - 4 : hslot + 1;  // row q-4
+    const int s2 = hslot + 2 >= 5 ? hslot - 3 : hslot + 2;  // row q-3
+    const int s4 = hslot + 4 >= 5 ? hslot - 1 : hslot + 4;  // row q-1
+    const uint4 Aold = hor[(2 * s1) * kStripThreads];
+    const uint4 Bup = hor[(2 * s2 + 1) * kStripThreads];
+    const uint4 Bdn = hor[(2 * s4 + 1) * kStripThreads];
+    hor[(2 * hslot) * kStripThreads] = make_uint4(An[0], An[1], An[2], An[3]);
+    hor[(2 * hslot + 1) * kStripThreads] = make_uint4(Bn[0], Bn[1], Bn[2], Bn[3]);
+    hslot = hslot == 4 ? 0 : hslot + 1;
+    // vertical kernels at row hr = q-2: s(hr+1) = v(hr) + v(hr+1) + v(hr+2), A = s(hr-1) + s(hr) + s(hr+1), B = 2A - s(hr)
+    LamPairs sN, A, B;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      sN.e[j] = vA.e[j] + vB.e[j] + vN.e[j];
+      A.e[j] = sP.e[j] + sC.e[j] + sN.e[j];
+      B.e[j] = 2u * A.e[j] - sC.e[j];
+    }
+    const int hr = q - 2;
+    int h[12];
+    if (hr < 0 || hr >= H || hr < y0 - 2) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) h[i] = 0;
+    } else {
+      uint32_t bo[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) bo[j] = lam_odd(B.e[j], B.e[j + 1]);
+      const uint32_t ao[4] = {Aold.x, Aold.y, Aold.z, Aold.w}, bu[4] = {Bup.x, Bup.y, Bup.z, Bup.w},
+                     bd[4] = {Bdn.x, Bdn.y, Bdn.z, Bdn.w};
+      int gx[8], gy[8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const uint32_t GX = (A.e[p + 2] - A.e[p]) + (bo[p + 1] - bo[p]);
+        const uint32_t GY = (An[p] - ao[p]) + (bd[p] - bu[p]);
+        gx[2 * p] = lam_lo(GX); gx[2 * p + 1] = lam_hi(GX);
+        gy[2 * p] = lam_lo(GY); gy[2 * p + 1] = lam_hi(GY);
+      }
+      if (!cols_interior) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = c0 - 2 + i;
+          if (c < 0 || c >= W) { gx[i] = 0; gy[i] = 0; }  // the window sum is zero padded
+        }
+      }
+      int xx = gx[0] * gx[0], xy = gx[0] * gy[0], yy = gy[0] * gy[0];
+#pragma unroll
+      for (int i = 1; i < 5; ++i) {
+        xx += gx[i] * gx[i];
+        xy += gx[i] * gy[i];
+        yy += gy[i] * gy[i];
+      }
+      h[0] = xx; h[4] = xy; h[8] = yy;
+#pragma unroll
+      for (int j = 1; j < 4; ++j) {
+        xx += gx[j + 4] * gx[j + 4] - gx[j - 1] * gx[j - 1];
+        xy += gx[j + 4] * gy[j + 4] - gx[j - 1] * gy[j - 1];
+        yy += gy[j + 4] * gy[j + 4] - gy[j - 1] * gy[j - 1];
+        h[j] = xx; h[4 + j] = xy; h[8 + j] = yy;
+      }
+    }
+    // slide the vertical state
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      vA.e[j] = vB.e[j]; vB.e[j] = vN.e[j];
+      sP.e[j] = sC.e[j]; sC.e[j] = sN.e[j];
+    }
+    if (hr < y0 - 2) continue;  // the four rows above the band only prime the state
+    int4* s = ring + slot;
+    const int4 oxx = s[0], oxy = s[kStripThreads], oyy = s[2 * kStripThreads];
+    s[0] = make_int4(h[0], h[1], h[2], h[3]);
+    s[kStripThreads] = make_int4(h[4], h[5], h[6], h[7]);
+    s[2 * kStripThreads] = make_int4(h[8], h[9], h[10], h[11]);
+    slot = (slot == 4 * 3 * kStripThreads) ? 0 : slot + 3 * kStripThreads;
+    const int ox[4] = {oxx.x, oxx.y, oxx.z, oxx.w}, om[4] = {oxy.x, oxy.y, oxy.z, oxy.w}, oy[4] = {oyy.x, oyy.y, oyy.z, oyy.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      Sxx[j] += (uint32_t)(h[j] - ox[j]);
+      Sxy[j] += (long long)(h[4 + j] - om[j]);
+      Syy[j] += (uint32_t)(h[8 + j] - oy[j]);
+    }
+    const int r = hr - 2;  // rows r-2 .. r+2 are now summed
+    if (r >= y0) {
+      double res[4];
+      double av[4], bv[4], cv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        av[j] = div25_exact(exact_u32_to_f64(Sxx[j]));
+        bv[j] = div25_exact(exact_i64_to_f64(Sxy[j]));
+        cv[j] = div25_exact(exact_u32_to_f64(Syy[j]));
+        res[j] = lambda_min_psd(av[j], bv[j], cv[j]);  // straight-line: the four float64 chains interleave
+      }
+      bool rare = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rare |= lambda_needs_dsterf(av[j], bv[j], cv[j]);
+      if (rare) {  // tiny non-zero off-diagonal: LAPACK's split test decides (practically never on image data)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (lambda_needs_dsterf(av[j], bv[j], cv[j])) res[j] = dsterf_2x2_min_call(av[j], bv[j], cv[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (active) local_max = fmax(local_max, res[j]);
+      }
+      if (active) {
+        double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
+        __stcs(dst, make_double2(res[0], res[1]));
+        __stcs(dst + 1, make_double2(res[2], res[3]));
+      }
+    }
+  }
+  if (img_max_bits) {
+    const double m = warp_max(local_max);
+    if (lane == 0 && m > -INFINITY) atomicMax(img_max_bits + blockIdx.z, ordered_bits(m));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // General path: shared-memory tiled, any odd window <= 31, both gradients, both responses
 // ------------------------------------------------------------------------------------------------
 static constexpr int kTileX = 32;
@@ -918,7 +1141,9 @@ extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int heig
     int rows = 64;
     while (rows > 8 && (int64_t)strips * div_up(height, rows) * batch < 148 * 16) rows >>= 1;
     dim3 grid(div_up(strips, kStripWarps), div_up(height, rows), batch);
-    lambda5_ring_kernel<<<grid, kStripThreads, 0, st>>>(gray, height, width, rows, eig, bits);
+    const int hor_bytes = (int)(sizeof(uint4) * 10 * kStripThreads);
+    FC_CUDA_TRY(cudaFuncSetAttribute(lambda5_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hor_bytes));
+    lambda5_packed_kernel<<<grid, kStripThreads, hor_bytes, st>>>(gray, height, width, rows, eig, bits);
     note_launch();
     FC_RETURN_IF_LAUNCH_FAILED();
   } else {
