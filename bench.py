@@ -235,7 +235,7 @@ class HarrisWorkload:
             return []
         h = float(np.mean([e[0].elapsed_time(e[1]) for e in self.ev[:n]]))
         lm = float(np.mean([e[1].elapsed_time(e[2]) for e in self.ev[:n]]))
-        return [("harris5_f32_kernel", alg, h, "hbm"), ("lambda5_ring_kernel (+ per-image max)", alg, lm, "hbm")]
+        return [("harris5_f32_kernel", alg, h, "hbm"), ("lambda5_packed_kernel (+ per-image max)", alg, lm, "hbm")]
 
     def traffic(self, tr):
         """dram bytes per launch of the dominant kernel, from the committed ncu capture scaled to this launch"""

@@ -3,7 +3,7 @@
 //   harris5_f32_kernel     app Harris, 5x5 window (the reference default and the benchmarked config):
 //                          sliding-window kernel, one warp per 128-column strip, 4 pixels per thread,
 //                          exact packed-float32 sums (bytes unpacked by PRMT, no conversion-unit ops).
-//   lambda5_ring_kernel    lambda-minus, same strip structure, exact integer sums + LAPACK's dlae2 sequence.
+//   lambda5_packed_kernel  lambda-minus, same strip structure, exact integer sums in 16-bit lanes + LAPACK's dlae2 sequence.
 //   corner_tiled_kernel    every other combination (any odd window <= 31, K_X gradient, lambda-minus):
 //                          shared-memory tiled, exact integer sums.
 //
@@ -341,58 +341,12 @@ harris5_f32_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_
 // Fast path: lambda-minus (K_X gradients, 5x5 window / 25, smallest eigenvalue), same strip structure
 // ------------------------------------------------------------------------------------------------
 // K_X = a (x) [-1 0 0 0 1] + b (x) [0 -1 0 1 0] with a = (1,2,3,2,1), b = (2,3,5,3,2) down the rows
-// (APP/FeatureCraft_Backend.py:405-413), applied as zero-padded correlation.  |g| <= 12240, products <= 1.5e8,
-// 5-tap row sums <= 7.5e8 (int32); 5x5 sums <= 3.75e9: Sxx, Syy in uint32 (modular updates are exact below 2^32),
-// Sxy in int64.  One IEEE division by 25 per sum and LAPACK's dlae2 sequence give numpy's eigvalsh bit for bit.
-struct Row5 {
-  Row3 r[5];  // circular: slot (row + 2) % 5 when the band starts at a multiple of 5 of the unrolled loop
-};
-
-// S = slot of the NEWEST row (hr+2); rows hr-2 .. hr+2 sit in slots S+1, S+2, S+3, S+4, S (mod 5): with the row
-// loop unrolled by 5 every index is static and no register is ever moved when the window slides.
-template <int S>
-__device__ __forceinline__ void lambda_row_sums(const Row5& R, int W, int c0, bool cols_interior, int (&h)[12]) {
-  int A[12], B[12], D1[12], D2[12];
-#pragma unroll
-  for (int k = 0; k < 12; ++k) {
-    const int v0 = col_i(R.r[(S + 1) % 5], k), v1 = col_i(R.r[(S + 2) % 5], k), v2 = col_i(R.r[(S + 3) % 5], k),
-              v3 = col_i(R.r[(S + 4) % 5], k), v4 = col_i(R.r[S], k);
-    const int s04 = v0 + v4, s13 = v1 + v3;
-    A[k] = s04 + 2 * s13 + 3 * v2;
-    B[k] = 2 * s04 + 3 * s13 + 5 * v2;
-    D2[k] = v4 - v0;
-    D1[k] = v3 - v1;
-  }
-  int gx[8], gy[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = i + 2;
-    gx[i] = (A[k + 2] - A[k - 2]) + (B[k + 1] - B[k - 1]);
-    gy[i] = (D2[k - 2] + D2[k + 2]) + 2 * (D2[k - 1] + D2[k + 1]) + 3 * D2[k] + 2 * (D1[k - 2] + D1[k + 2]) +
-            3 * (D1[k - 1] + D1[k + 1]) + 5 * D1[k];
-  }
-  if (!cols_interior) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 - 2 + i;
-      if (c < 0 || c >= W) { gx[i] = 0; gy[i] = 0; }  // the window sum is zero padded
-    }
-  }
-  int xx = gx[0] * gx[0], xy = gx[0] * gy[0], yy = gy[0] * gy[0];
-#pragma unroll
-  for (int i = 1; i < 5; ++i) {
-    xx += gx[i] * gx[i];
-    xy += gx[i] * gy[i];
-    yy += gy[i] * gy[i];
-  }
-  h[0] = xx; h[4] = xy; h[8] = yy;
-#pragma unroll
-  for (int j = 1; j < 4; ++j) {
-    xx += gx[j + 4] * gx[j + 4] - gx[j - 1] * gx[j - 1];
-    xy += gx[j + 4] * gy[j + 4] - gx[j - 1] * gy[j - 1];
-    yy += gy[j + 4] * gy[j + 4] - gy[j - 1] * gy[j - 1];
-    h[j] = xx; h[4 + j] = xy; h[8 + j] = yy;
-  }
+// (APP/FeatureCraft_Backend.py:405-413), applied as zero-padded correlation.  Pixels are >= 0, so |g| <= 255 x (sum of
+// the positive weights = 24) = 6120, products <= 3.75e7, 5-tap row sums <= 1.9e8, 5x5 sums <= 9.4e8: everything is int32.
+// One IEEE division by 25 per sum and LAPACK's dlae2 sequence give numpy's eigvalsh bit for bit.
+// exact int32 -> float64: bits of 2^52 + (n + 2^31), minus 2^52 + 2^31
+__device__ __forceinline__ double exact_i32_to_f64(int n) {
+  return __dsub_rn(__hiloint2double(0x43300000, n ^ (int)0x80000000), 4503601774854144.0);
 }
 
 // exact uint32 -> float64: bits of 2^52 + n, minus 2^52
@@ -455,136 +409,10 @@ __global__ void selftest_divsqrt_kernel(unsigned long long* __restrict__ mismatc
 // out-of-line copy of the rare LAPACK split path (one body instead of one per pixel)
 static __device__ __noinline__ double dsterf_2x2_min_call(double a, double b, double c) { return dsterf_2x2_min(a, b, c); }
 
-// The five image rows of the vertical K_X taps live in a per-thread shared-memory ring of 8 slots that cp.async
-// fills three rows ahead (no register scoreboard, no exposed load latency) and are read back in logical order, so
-// ONE copy of the step body (2 500 instructions) serves every row -- keeping the rows in registers needs a five-fold
-// unrolled row loop (12 600 instructions of straight code, an instruction-cache miss on every warp: measured 1.6x
-// slower).  The 5x5 window sums use the same int4 ring as the Harris kernel.
-static constexpr int kLamRowSlots = 8;
-
-__device__ __forceinline__ void lambda_stage_row(const uint8_t* __restrict__ img, int row, int H, int W, int c0,
-                                                 uint4* __restrict__ rows_ring) {
-  uint4* dst = rows_ring + (row & (kLamRowSlots - 1)) * kStripThreads;
-  if (row < 0 || row >= H) {
-    *dst = make_uint4(0u, 0u, 0u, 0u);  // zero padding (padding_matrix)
-  } else {
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (size_t)row * W);
-    const int wi = c0 >> 2, nw = W >> 2;
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-#pragma unroll
-    for (int w = 0; w < 3; ++w) {
-      const int idx = wi - 1 + w;
-      if (idx >= 0 && idx < nw) {
-        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(d + w);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(p + idx) : "memory");
-      } else {
-        d[w] = 0u;
-      }
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(kStripThreads, 4)
-lambda5_ring_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double* __restrict__ out,
-                    unsigned long long* __restrict__ img_max_bits) {
-  __shared__ int4 sRing[5 * 3 * kStripThreads];            // [slot][xx, xy, yy][thread]: row sums of the last 5 rows
-  __shared__ uint4 sRows[kLamRowSlots * kStripThreads];    // [row & 7][thread]: the thread's 12 bytes of an image row
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int strip = blockIdx.x * kStripWarps + warp;
-  const int strip_c0 = strip * kStripCols;
-  if (strip_c0 >= W) return;  // warp-uniform, no block-wide barrier in this kernel
-  const int c0 = strip_c0 + lane * 4;
-  const bool active = c0 < W;
-  const size_t img_off = (size_t)blockIdx.z * H * W;
-  const uint8_t* img = gray + img_off;
-  double* o = out + img_off;
-  const int y0 = blockIdx.y * rows_per_band;
-  const int y1 = min(y0 + rows_per_band, H);
-  const bool cols_interior = (strip_c0 - 2 >= 0) && (strip_c0 + kStripCols + 1 <= W - 1);
-  int4* ring = sRing + threadIdx.x;
-  uint4* rows_ring = sRows + threadIdx.x;
-  uint32_t Sxx[4], Syy[4];
-  long long Sxy[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { Sxx[j] = 0u; Syy[j] = 0u; Sxy[j] = 0; }
-#pragma unroll
-  for (int i = 0; i < 15; ++i) ring[i * kStripThreads] = make_int4(0, 0, 0, 0);
-  // rows hr-2 .. hr+2 of the first step (hr = y0-2) and two rows ahead
-  for (int r = y0 - 4; r <= y0 + 2; ++r) lambda_stage_row(img, r, H, W, c0, rows_ring);
-  double local_max = -INFINITY;
-  int slot = 0;
-#pragma unroll 1
-  for (int hr = y0 - 2; hr <= y1 + 1; ++hr) {
-    asm volatile("cp.async.wait_group 2;" ::: "memory");  // rows <= hr+2 have landed (each thread reads only its own copies)
-    Row5 R;
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      const uint4 v = rows_ring[((hr - 2 + q) & (kLamRowSlots - 1)) * kStripThreads];
-      R.r[q].w[0] = v.x; R.r[q].w[1] = v.y; R.r[q].w[2] = v.z;
-    }
-    lambda_stage_row(img, hr + 5, H, W, c0, rows_ring);  // slot of row hr-3, no longer needed
-    int h[12];
-    if (hr < 0 || hr >= H) {
-#pragma unroll
-      for (int i = 0; i < 12; ++i) h[i] = 0;
-    } else {
-      lambda_row_sums<4>(R, W, c0, cols_interior, h);  // S = 4: rows hr-2 .. hr+2 are R.r[0] .. R.r[4]
-    }
-    int4* s = ring + slot;
-    const int4 oxx = s[0], oxy = s[kStripThreads], oyy = s[2 * kStripThreads];
-    s[0] = make_int4(h[0], h[1], h[2], h[3]);
-    s[kStripThreads] = make_int4(h[4], h[5], h[6], h[7]);
-    s[2 * kStripThreads] = make_int4(h[8], h[9], h[10], h[11]);
-    slot = (slot == 4 * 3 * kStripThreads) ? 0 : slot + 3 * kStripThreads;
-    const int ox[4] = {oxx.x, oxx.y, oxx.z, oxx.w}, om[4] = {oxy.x, oxy.y, oxy.z, oxy.w}, oy[4] = {oyy.x, oyy.y, oyy.z, oyy.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      Sxx[j] += (uint32_t)(h[j] - ox[j]);
-      Sxy[j] += (long long)(h[4 + j] - om[j]);
-      Syy[j] += (uint32_t)(h[8 + j] - oy[j]);
-    }
-    const int r = hr - 2;  // rows r-2 .. r+2 are now summed
-    if (r >= y0) {
-      double res[4];
-      double av[4], bv[4], cv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        av[j] = div25_exact(exact_u32_to_f64(Sxx[j]));
-        bv[j] = div25_exact(exact_i64_to_f64(Sxy[j]));
-        cv[j] = div25_exact(exact_u32_to_f64(Syy[j]));
-        res[j] = lambda_min_psd(av[j], bv[j], cv[j]);  // straight-line: the four float64 chains interleave
-      }
-      bool rare = false;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rare |= lambda_needs_dsterf(av[j], bv[j], cv[j]);
-      if (rare) {  // tiny non-zero off-diagonal: LAPACK's split test decides (practically never on image data)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (lambda_needs_dsterf(av[j], bv[j], cv[j])) res[j] = dsterf_2x2_min_call(av[j], bv[j], cv[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (active) local_max = fmax(local_max, res[j]);
-      }
-      if (active) {
-        double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
-        __stcs(dst, make_double2(res[0], res[1]));
-        __stcs(dst + 1, make_double2(res[2], res[3]));
-      }
-    }
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  if (img_max_bits) {
-    const double m = warp_max(local_max);
-    if (lane == 0 && m > -INFINITY) atomicMax(img_max_bits + blockIdx.z, ordered_bits(m));
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // lambda-minus, packed form: the integer half of the kernel in 16-bit lanes
 // ------------------------------------------------------------------------------------------------
-// ncu on lambda5_ring_kernel: 945 instructions per thread and row (4 pixels), 240 of them float64 (the LAPACK
+// ncu on the first version (every row unpacked to int32 columns): 945 instructions per thread and row (4 pixels), 240 of them float64 (the LAPACK
 // sequence, irreducible) and ~420 the K_X gradients: per row every one of the 12 columns was unpacked from 5 rows and
 // pushed through both 5-tap kernels, every gradient through a 5x2-tap sum.  Here
 //   * values live as PAIRS of 16-bit lanes in one register (every intermediate fits: |.| <= 12240), encoded as
@@ -642,7 +470,7 @@ lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_p
   int4* ring = sRing + threadIdx.x;
   uint4* hor = sHor + threadIdx.x;
   uint32_t Sxx[4], Syy[4];
-  long long Sxy[4];
+  int Sxy[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) { Sxx[j] = 0u; Syy[j] = 0u; Sxy[j] = 0; }
 #pragma unroll
@@ -652,14 +480,13 @@ lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_p
   // the thread's three words of a row (columns c0-4 .. c0+7), zero outside the image (padding_matrix)
   const int wi = c0 >> 2, nw = W >> 2;
   const bool ok0 = wi - 1 >= 0 && wi - 1 < nw, ok1 = wi < nw, ok2 = wi + 1 < nw;
+  const uint32_t* img32 = reinterpret_cast<const uint32_t*>(img) + wi;
   auto load_row = [&](int row, uint32_t (&w)[3]) {
-    w[0] = w[1] = w[2] = 0u;
-    if (row >= 0 && row < H) {
-      const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (size_t)row * W) + wi;
-      if (ok0) w[0] = __ldg(p - 1);
-      if (ok1) w[1] = __ldg(p);
-      if (ok2) w[2] = __ldg(p + 1);
-    }
+    const bool in = (unsigned)row < (unsigned)H;  // warp-uniform
+    const uint32_t* p = img32 + (size_t)(in ? row : 0) * nw;
+    w[0] = (in && ok0) ? __ldg(p - 1) : 0u;
+    w[1] = (in && ok1) ? __ldg(p) : 0u;
+    w[2] = (in && ok2) ? __ldg(p + 1) : 0u;
   };
   // vertical state of the gx kernels: raw pairs of rows q-2, q-1 and box sums s(q-3), s(q-2) when row q enters
   LamPairs vA, vB, sP, sC;
@@ -765,7 +592,7 @@ lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_p
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       Sxx[j] += (uint32_t)(h[j] - ox[j]);
-      Sxy[j] += (long long)(h[4 + j] - om[j]);
+      Sxy[j] += h[4 + j] - om[j];
       Syy[j] += (uint32_t)(h[8 + j] - oy[j]);
     }
     const int r = hr - 2;  // rows r-2 .. r+2 are now summed
@@ -775,7 +602,7 @@ lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_p
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         av[j] = div25_exact(exact_u32_to_f64(Sxx[j]));
-        bv[j] = div25_exact(exact_i64_to_f64(Sxy[j]));
+        bv[j] = div25_exact(exact_i32_to_f64(Sxy[j]));
         cv[j] = div25_exact(exact_u32_to_f64(Syy[j]));
         res[j] = lambda_min_psd(av[j], bv[j], cv[j]);  // straight-line: the four float64 chains interleave
       }
@@ -789,7 +616,7 @@ lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_p
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (active) local_max = fmax(local_max, res[j]);
+        if (active) local_max = res[j] > local_max ? res[j] : local_max;  // res is never NaN
       }
       if (active) {
         double2* dst = reinterpret_cast<double2*>(o + (size_t)r * W + c0);
