@@ -1087,6 +1087,13 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
         const int y = y0 + yr;
         if (yr >= 1 && yr <= kSTY && y >= 1 && y <= H - 3) {
           const float eps = sa.eps_rel * fmaxf(*sa.value_bound, 1e-30f);
+          // centres of this thread: region columns 12g + j with 1 <= 12g + j <= kSTX and image column 1 <= x <= W - 3
+          uint32_t okmask = 0;
+          {
+            const int xb0 = x0 + 12 * g;
+            const int jlo = max(max(1 - 12 * g, 1 - xb0), 0), jhi = min(min(kSTX - 12 * g, W - 3 - xb0), 11);
+            if (jhi >= jlo) okmask = ((2u << jhi) - 1u) & ~((1u << jlo) - 1u);
+          }
 #pragma unroll
           for (int k = 1; k <= 2; ++k) {
             float up[2][12], dn[2][12];  // [max / min] of the rows above and below
@@ -1101,20 +1108,21 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
                 dn[mm][4 * q] = c4.x; dn[mm][4 * q + 1] = c4.y; dn[mm][4 * q + 2] = c4.z; dn[mm][4 * q + 3] = c4.w;
               }
             }
-            uint32_t bits = 0, amb = 0;
+            // t = max(c - M, m - c): > eps -> extremum for certain, < -eps -> certainly none (float32 subtraction is
+            // monotonic and eps is a float, so fl(c - M) > eps iff c - M > eps: no rounding slack is needed here)
+            uint32_t cand_bits = 0, sure_bits = 0;
 #pragma unroll
             for (int j = 0; j < 12; ++j) {
               const float M = max3_t<float>(up[0][j], nmax[k - 1][j], dn[0][j]);
               const float m = min3_t<float>(up[1][j], nmin[k - 1][j], dn[1][j]);
               const float c = ctr[k - 1][j];
-              const int rj = 12 * g + j;  // region column of the centre
-              const int x = x0 + rj;
-              const bool ok = rj >= 1 && rj <= kSTX && x >= 1 && x <= W - 3;
-              const bool cand = ok && (c >= M - eps || c <= m + eps);
-              const bool sure = c > M + eps || c < m - eps;
-              if (cand && sure && sa.filter != FC_FILTER_SCRIPT) bits |= 1u << j;
-              else if (cand) amb |= 1u << j;
+              const float t = fmaxf(c - M, m - c);
+              cand_bits |= (t >= -eps) ? (1u << j) : 0u;
+              sure_bits |= (t > eps) ? (1u << j) : 0u;
             }
+            cand_bits &= okmask;
+            const uint32_t bits = sa.filter != FC_FILTER_SCRIPT ? (cand_bits & sure_bits) : 0u;
+            uint32_t amb = cand_bits & ~bits;
             while (amb) {  // rare: the float64 repair decides these
               const int j = __ffs(amb) - 1;
               amb &= amb - 1;
