@@ -868,11 +868,7 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
   const size_t plane = (size_t)H * W;
 
   // -> true when the tile is fetched by TMA (then the mbarrier, not cp.async.wait_all, tells when it has landed)
-  auto issue_load = [&](int tile) -> bool {
-    const int tx = tile % tiles_x;
-    const int rest = tile / tiles_x;
-    const int ty = rest % tiles_y;
-    const int b = rest / tiles_y;
+  auto issue_load = [&](int tx, int ty, int b) -> bool {
     const int x0 = tx * kStepX, y0 = ty * kStepY;
     const float* img = base + (size_t)b * plane;
     // smem column c <-> image column x0 - 16 + c
@@ -919,14 +915,26 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
     return false;
   };
 
+  // tile -> (tx, ty, image): decoded once, then advanced by the grid stride with carries (the four integer divisions
+  // per tile and thread were 5 % of the kernel's instructions)
   int tile = blockIdx.x;
+  int ntx = tile % tiles_x, nty = (tile / tiles_x) % tiles_y, nb = tile / (tiles_x * tiles_y);  // the NEXT tile to load
+  const int step_x = (int)gridDim.x % tiles_x, step_y = ((int)gridDim.x / tiles_x) % tiles_y,
+            step_b = (int)gridDim.x / (tiles_x * tiles_y);
+  auto advance = [&]() {
+    ntx += step_x;
+    int carry = ntx >= tiles_x ? 1 : 0;
+    ntx -= carry ? tiles_x : 0;
+    nty += step_y + carry;
+    carry = nty >= tiles_y ? 1 : 0;
+    nty -= carry ? tiles_y : 0;
+    nb += step_b + carry;
+  };
   bool by_tma = false;
-  if (tile < n_tiles) by_tma = issue_load(tile);
+  if (tile < n_tiles) by_tma = issue_load(ntx, nty, nb);
   for (; tile < n_tiles; tile += gridDim.x) {
-    const int tx = tile % tiles_x;
-    const int rest = tile / tiles_x;
-    const int ty = rest % tiles_y;
-    const int b = rest / tiles_y;
+    const int tx = ntx, ty = nty, b = nb;
+    advance();
     const int x0 = tx * kStepX, y0 = ty * kStepY;
     float* gout = SEARCH ? nullptr : gauss + (size_t)b * 5 * plane;
     if (by_tma) {
@@ -986,7 +994,7 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
       }
     }
     __syncthreads();  // intermediates complete, input tile free
-    by_tma = (tile + (int)gridDim.x < n_tiles) ? issue_load(tile + gridDim.x) : false;
+    by_tma = (tile + (int)gridDim.x < n_tiles) ? issue_load(ntx, nty, nb) : false;
     if constexpr (!SEARCH) {
       const int y = threadIdx.x >> 3, g = threadIdx.x & 7;
       const int yy = y0 + y, xx = x0 + 12 * g;
