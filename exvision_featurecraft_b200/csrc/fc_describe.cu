@@ -206,21 +206,26 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
                    int32_t* __restrict__ recheck_list, int32_t* __restrict__ recheck_count) {
   constexpr bool PACKED = MODE != kOriPlanes;
   constexpr int KPW = 32 / LPK;        // keypoints per warp
-  constexpr int PITCH = LPK;           // [bin][lane]: rows of LPK values, so clearing and the final sums move 16 bytes at a time
+  // kOriPlanes: [keypoint][bin][lane of the keypoint], rows of LPK values (clearing and the final sums move 16 bytes at a time).
+  // kOriCoded: [bin][lane of the warp] -- a lane's private bins always sit in the lane's own bank.  ncu had the kernel
+  // at 96 % of the L1 data-pipe wavefront limit with 71 % of the wavefronts from shared memory, half of those bank
+  // conflicts between the keypoints of a warp (their rows start 8 banks apart and the bin picks the rest).
+  constexpr bool WIDE = PACKED && sizeof(T) == 4;
+  constexpr int PITCH = WIDE ? 32 : LPK;
   constexpr int NB = (kOriBins + LPK - 1) / LPK;  // bins reduced by one lane
   constexpr int VEC = 16 / sizeof(T);  // values per 16-byte shared access
   constexpr int NROWS = (NR <= 2) ? 4 : 2;  // image rows whose samples are loaded before the first histogram update
-  __shared__ __align__(16) T hist[kOriWarps][KPW][(kOriBins + 1) * PITCH];
+  __shared__ __align__(16) T hist[kOriWarps][(kOriBins + 1) * 32];  // KPW * LPK = 32 values per bin either way
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPK, slot = lane / LPK;
   const int n = (blockIdx.x * kOriWarps + warp) * KPW + slot;
   const bool valid = n < n_keypoints;
   if ((blockIdx.x * kOriWarps + warp) * KPW >= n_keypoints) return;  // warp-uniform; no block-wide barriers below
-  T* h = hist[warp][slot];
+  T* h = hist[warp] + (WIDE ? slot * LPK : slot * (kOriBins + 1) * LPK);  // bin b of lane `sub`: h[b * PITCH + sub]
   {
     using V = typename Vec16<T>::type;
-    V* hv = reinterpret_cast<V*>(h);
-    for (int t = sub; t < (kOriBins + 1) * PITCH / VEC; t += LPK) hv[t] = Vec16<T>::zero();
+    V* hv = reinterpret_cast<V*>(hist[warp]);  // the whole warp clears the warp's table
+    for (int t = lane; t < (kOriBins + 1) * 32 / VEC; t += 32) hv[t] = Vec16<T>::zero();
   }
   __syncwarp();
   const int nn = valid ? n : 0;
@@ -298,7 +303,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
         for (int v = 0; v < NROWS; ++v)
 #pragma unroll
           for (int u = 0; u < NR; ++u) {
-            const uint32_t a = hbase + ((uint32_t)bins[v][u] << (2 + (LPK == 8 ? 3 : (LPK == 16 ? 4 : 5))));
+            const uint32_t a = hbase + ((uint32_t)bins[v][u] << 7);  // WIDE layout: 32 floats per bin row
             float cur;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur) : "r"(a));
             cur = __fadd_rn(cur, (float)ws[v][u]);
@@ -326,6 +331,48 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
       }
   }
   __syncwarp();
+  if constexpr (WIDE) {
+    // Sums without a bank conflict: the eight lanes of a quarter warp read the eight 16-byte chunks of ONE bin row
+    // (chunk c belongs to keypoint c / (LPK / 4)), lane group g = lane / 8 takes bins g, g + 4, ...; the chunks of a
+    // keypoint are combined by shuffles, the maximum and the bin masks over the four lane groups.
+    constexpr int CPS = LPK / 4;  // chunks per keypoint
+    const int chunk = lane & 7, grp = lane >> 3;
+    const int rslot = chunk / CPS;
+    float f[9];
+    float mx = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      const int bin = grp + 4 * q;  // < 36 for every q
+      const float4 t = *reinterpret_cast<const float4*>(hist[warp] + bin * 32 + chunk * 4);
+      float sacc = ((t.x + t.y) + t.z) + t.w;
+#pragma unroll
+      for (int o = 1; o < CPS; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      f[q] = sacc;
+      mx = fmaxf(mx, sacc);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    const float cut = __fmul_rn(0.8f, mx);  // see the note on numpy's promotion rules below
+    uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      const int bin = grp + 4 * q;
+      if (f[q] >= cut) {
+        if (bin < 32) lo |= 1u << bin; else hi |= 1u << (bin - 32);
+      }
+      if (fabsf(f[q] - cut) <= tol * mx) hi |= 0x80000000u;
+    }
+    lo |= __shfl_xor_sync(0xffffffffu, lo, 8);
+    hi |= __shfl_xor_sync(0xffffffffu, hi, 8);
+    lo |= __shfl_xor_sync(0xffffffffu, lo, 16);
+    hi |= __shfl_xor_sync(0xffffffffu, hi, 16);
+    const int nr = (blockIdx.x * kOriWarps + warp) * KPW + rslot;
+    if (grp == 0 && (chunk % CPS) == 0 && nr < n_keypoints) {
+      bin_mask[nr] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+      if (hi & 0x80000000u) recheck_list[atomicAdd(recheck_count, 1)] = nr;
+    }
+    return;
+  }
   // column sums: lane `sub` reduces bins sub, sub + LPK, ...; histogram entries are float32 in the reference (:158)
   float f[NB];
   float mx = 0.0f;

@@ -1182,7 +1182,7 @@ gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid
                      double* __restrict__ out, int n_planes, int plane0) {
   static_assert(RA <= MR && RB <= MR && MR <= 12 && MR % 2 == 0 && kMTY % ROWS == 0, "radius class");
   constexpr int NL = RB > 0 ? 2 : 1;
-  constexpr int TX = kMP - 2 * MR;
+  constexpr int TX = (kMP - 2 * MR) / 6 * 6;  // output columns per tile: 114, 108, 108, 102 for MR = 6, 8, 10, 12
   extern __shared__ __align__(16) unsigned char mid_smem[];
   double* sTmp = reinterpret_cast<double*>(mid_smem);  // [2][kMTY][kMP]
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * kMTY;
@@ -1223,38 +1223,45 @@ gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid
     }
   }
   __syncthreads();
-  // horizontal pass: 4 outputs per item; tmp column MR + o <-> output column x0 + o
+  // horizontal pass: 6 outputs per item; tmp column MR + o <-> output column x0 + o.  ncu showed the kernel at 93 % of the
+  // L1 data-pipe wavefront limit, not at the FP64 limit: with 4 outputs per lane consecutive lanes read 16-byte chunks
+  // 32 bytes apart, which uses half of the bank groups per quarter warp (2-way conflict on every LDS.128).  A stride of
+  // 48 bytes (6 doubles) hits all eight bank groups, and a lane reuses more of what it loads: 1.5 instead of 2 x 2
+  // wavefront-loads per output.
+  constexpr int OPL = 6;              // outputs per lane
+  constexpr int ITEMS_X = TX / OPL;   // TX is a multiple of 6 in every radius class (see launch_mid_f64)
+  static_assert(TX % OPL == 0, "tile width");
   const bool vec_ok = (W % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   double* o0 = out + ((size_t)b * n_planes + plane0) * plane;
 #pragma unroll 1
-  for (int item = threadIdx.x; item < kMTY * (TX / 4); item += 256) {
-    const int y = item / (TX / 4), g = item - y * (TX / 4);
-    const int yy = y0 + y, xx = x0 + 4 * g;
+  for (int item = threadIdx.x; item < kMTY * ITEMS_X; item += 256) {
+    const int y = item / ITEMS_X, g = item - y * ITEMS_X;
+    const int yy = y0 + y, xx = x0 + OPL * g;
     if (yy >= H || xx >= W) continue;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-      const double2* src = reinterpret_cast<const double2*>(sTmp + l * kMTY * kMP + y * kMP + 4 * g);
-      double v[4 + 2 * MR];
+      const double2* src = reinterpret_cast<const double2*>(sTmp + l * kMTY * kMP + y * kMP + OPL * g);
+      double v[OPL + 2 * MR];
 #pragma unroll
-      for (int q = 0; q < (4 + 2 * MR) / 2; ++q) {
+      for (int q = 0; q < (OPL + 2 * MR) / 2; ++q) {
         const double2 t = src[q];
         v[2 * q] = t.x; v[2 * q + 1] = t.y;
       }
-      double r[4];
+      double r[OPL];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < OPL; ++j) {
         double acc = taps.t[l][0] * v[j + MR];
 #pragma unroll
         for (int k = 1; k <= (l == 0 ? RA : RB); ++k) acc = fma(taps.t[l][k], v[j + MR - k] + v[j + MR + k], acc);
         r[j] = acc;
       }
       double* dst = o0 + (size_t)l * plane + (size_t)yy * W + xx;
-      if (vec_ok && xx + 3 < W) {
-        reinterpret_cast<double2*>(dst)[0] = make_double2(r[0], r[1]);
-        reinterpret_cast<double2*>(dst)[1] = make_double2(r[2], r[3]);
+      if (vec_ok && xx + OPL - 1 < W) {
+#pragma unroll
+        for (int j = 0; j < OPL; j += 2) reinterpret_cast<double2*>(dst)[j / 2] = make_double2(r[j], r[j + 1]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < OPL; ++j)
           if (xx + j < W) dst[j] = r[j];
       }
     }
@@ -1266,7 +1273,7 @@ static int launch_mid_f64(const double* base, int B, int H, int W, const MidTaps
                           cudaStream_t st) {
   auto kern = gauss_mid_f64_kernel<MR, RA, RB, ROWS, MINB>;
   FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMidSmem));
-  dim3 grid(div_up(W, kMP - 2 * MR), div_up(H, kMTY), B);
+  dim3 grid(div_up(W, (kMP - 2 * MR) / 6 * 6), div_up(H, kMTY), B);
   kern<<<grid, 256, kMidSmem, st>>>(base, H, W, mt, out, n_planes, plane0);
   note_launch();
   note_path(FC_PATH_MID_F64);
