@@ -234,8 +234,8 @@ def test_ui_parameter_ranges_equal_float64(S, params):
     """Points of the app's parameter ranges (FeatureCraft_UI.py:197-273: octaves 4-8, s 2-5, sigma 1.6-3, r 6-12) and the
     script filter.  Certified mode must equal float64 mode everywhere, and it must get there on the fast kernels: the
     float64 levels 1 .. s (radii 5 .. 12 over the whole range) through the two-level kernel in its radius classes, never
-    through the generic level-by-level one, and the float64 repair from shared-memory patches whenever the largest
-    on-demand radius is <= 16."""
+    through the generic level-by-level one, and the float64 repair from shared-memory patches (radii up to 24 = the
+    whole range)."""
     from exvision_featurecraft_b200 import _lib, synthetic
 
     base = synthetic.sift_image(160, 192, seed=41)
@@ -250,8 +250,7 @@ def test_ui_parameter_ranges_equal_float64(S, params):
     assert took["generic_octave"] == (0 if radii == [3, 5, 6, 9, 13] else p.n_octaves), took
     if radii == [3, 5, 6, 9, 13]:
         assert took["fused_search"] == p.n_octaves, took
-    if max(radii) <= 16:
-        assert took["repair_patch"] == p.n_octaves, took
+    assert max(radii) <= 24 and took["repair_patch"] == p.n_octaves, took
     b = S.detect_and_describe(base, S.SiftParams(dtype="f64", **params), out_dtype=torch.float64)
     pa, da = a.assemble(1)[0]
     pb, db = b.assemble(1)[0]
