@@ -27,7 +27,9 @@ namespace fc {
 
 int launch_match_exact(const float* query, int n_query, const float* train, int n_train, const int32_t* rows,
                        const int32_t* n_rows_ptr, int max_rows, double ratio, int32_t* knn_idx, float* knn_dist,
-                       uint8_t* good, cudaStream_t st);
+                       uint8_t* good, void* part, unsigned int* done, cudaStream_t st);
+size_t match_exact_part_bytes();
+size_t match_exact_done_words();
 
 namespace tc {
 constexpr int kDim = 128;
@@ -498,7 +500,7 @@ __global__ void zero_u32_kernel(unsigned int* p, int n) {
 
 struct Plan {
   int nq_pad, nt_pad, n_qtiles, n_tiles, splits, tiles_per_split;  // tiles = kTileRows2-row train tiles
-  size_t off_a, off_b, off_cs, off_ci, off_stats, off_rows, total;
+  size_t off_a, off_b, off_cs, off_ci, off_stats, off_rows, off_part, total;
 };
 
 static Plan make_plan(int nq, int nt) {
@@ -526,8 +528,9 @@ static Plan make_plan(int nq, int nt) {
   p.off_b = o; o = align(o + (size_t)p.nt_pad * KP * 2);
   p.off_cs = o; o = align(o + (size_t)p.splits * p.nq_pad * kCand * 4);
   p.off_ci = o; o = align(o + (size_t)p.splits * p.nq_pad * kCand * 4);
-  p.off_stats = o; o = align(o + 16);
+  p.off_stats = o; o = align(o + 16 + 4 * match_exact_done_words());  // [0..3] stats, then the re-check's arrival counters
   p.off_rows = o; o = align(o + (size_t)nq * 4);
+  p.off_part = o; o = align(o + match_exact_part_bytes());
   p.total = o;
   return p;
 }
@@ -562,7 +565,8 @@ extern "C" int fc_match_knn2(const float* query, int n_query, const float* train
   unsigned int* stats = reinterpret_cast<unsigned int*>(ws + p.off_stats);  // [0] max|t|^2, [1] overflow, [2] amb count
   int32_t* rows = reinterpret_cast<int32_t*>(ws + p.off_rows);
 
-  tc::zero_u32_kernel<<<1, 32, 0, st>>>(stats, 4);
+  const int n_zero = 4 + (int)match_exact_done_words();
+  tc::zero_u32_kernel<<<div_up(n_zero, 256), 256, 0, st>>>(stats, n_zero);
   note_launch();
   tc::match_prep_kernel<<<div_up(p.nq_pad * 32, 256), 256, 0, st>>>(query, n_query, p.nq_pad, 1, Ah, stats);
   note_launch();
@@ -582,5 +586,5 @@ extern "C" int fc_match_knn2(const float* query, int n_query, const float* train
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return launch_match_exact(query, n_query, train, n_train, rows, reinterpret_cast<const int32_t*>(stats + 2), n_query, ratio,
-                            knn_idx, knn_dist, good, st);
+                            knn_idx, knn_dist, good, ws + p.off_part, stats + 4, st);
 }

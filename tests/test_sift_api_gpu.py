@@ -194,6 +194,41 @@ def test_batch_matcher_pipeline_equals_single_calls():
     assert sum(len(p) for p, _ in results) > 500  # the comparison above is not between empty lists
 
 
+@pytest.mark.parametrize("n_dup", [3, 400])
+def test_exact_recheck_with_split_train_range(n_dup):
+    """Rows the tensor path cannot prove go to the exact kernel, which cuts the train range into pieces when only a few
+    query blocks are flagged (one CTA walking 20 000 train rows alone is a millisecond-long latency chain).  Near-duplicate
+    train rows 1e-5 apart are below what the fp16 candidates can separate: those queries must be re-checked, and the
+    merged pieces must give the exact engine's answer (the fp16-overflow case of the next test sends every row through the
+    same path: many query blocks, fewer pieces)."""
+    import torch
+
+    from exvision_featurecraft_b200 import matching
+
+    rng = np.random.default_rng(21)
+    nq, nt = 3000, 20000
+    b = np.abs(rng.normal(0, 1, (nt, 128))).astype(np.float32)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    dup = rng.choice(nt // 2, n_dup, replace=False)
+    b[nt // 2 + np.arange(n_dup)] = b[dup] + rng.normal(0, 1e-5, (n_dup, 128)).astype(np.float32)  # twins far apart in the range
+    a = np.abs(rng.normal(0, 1, (nq, 128))).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    a[:n_dup] = b[dup] + rng.normal(0, 0.01, (n_dup, 128)).astype(np.float32)  # queries whose two best neighbours are twins
+    for ratio in (0.3, 0.999):
+        ei, ed, eg = matching.knn2(a, b, ratio, "exact")
+        ti, td, tg = matching.knn2(a, b, ratio, "tensor")
+        st = matching.last_stats()
+        assert st["overflow"] == 0
+        assert torch.equal(eg, tg)
+        g = eg.nonzero().flatten()
+        assert torch.equal(ei[g, 0], ti[g, 0]) and torch.equal(ed[g, 0], td[g, 0])
+        if ratio > 0.9:
+            assert st["rechecked_rows"] >= 1, st  # some rows near the ratio cut cannot be proven from the candidates
+        # a second call on the same workspace sizes: the arrival counters were left at zero
+        ti2, td2, tg2 = matching.knn2(a, b, ratio, "tensor")
+        assert torch.equal(tg2, tg) and torch.equal(ti2[g, 0], ti[g, 0])
+
+
 def test_tensor_matcher_rarely_needs_the_exact_recheck():
     """The tcgen05 candidates + bounds must decide almost every row on their own (otherwise the test above
     would pass on the exact fallback alone), and agree with the exact engine at a size that spans many tiles,
