@@ -1,18 +1,22 @@
 // SIFT orientation assignment and descriptors (sm_100a).
 //
-//   gradient_field_kernel<T>   sift_gradient (APP/utils/keypoint_descriptor.py:72-79) of one pyramid level:
-//                              magnitude, direction (degrees, Python % 360) and the 36-bin index
-//                              np.round(direction * 36 / 360) (:140-142) as one byte per pixel (float64 mode).
-//   gradient_codes_kernel      certified mode: magnitude | exact direction code, one word per pixel.
-//   orientation_kernel<T,LPK>  8 / 16 / 32 lanes per keypoint: zero-padded (2r+1)^2 window, weight = magnitude x
-//                              unnormalised Gaussian table, 36-bin histogram (:144-163).  Every lane owns a
-//                              private copy of the histogram in shared memory ([bin][lane],
-//                              no atomics, deterministic float64 sums); bins are reduced by shuffles, rounded
-//                              to float32 and compared with float32(0.8) * max (:165-167).
-//   descriptor_kernel<T>       one warp per oriented keypoint: 16x16 nearest-neighbour rotated window with
-//                              OpenCV's 10-bit fixed-point coordinates (:175-212), 4x4 cells x 8 bins with
-//                              float32 cell histograms, normalise / clip [2^-10, 0.2] / normalise (:259-287).
-//                              Two lanes per cell, 8 samples per lane, 8 private bins in registers.
+//   gradient_field_kernel<T>    sift_gradient (APP/utils/keypoint_descriptor.py:72-79) of one pyramid level:
+//                               magnitude, direction (degrees, Python % 360) and the 36-bin index
+//                               np.round(direction * 36 / 360) (:140-142) as one byte per pixel (float64 mode).
+//   gradient_codes(4)_kernel    certified mode: float32 magnitude | exact 5-degree direction code, one word per pixel.
+//   orientation_kernel<T,LPK,NR,MODE>
+//                               8 / 16 / 32 lanes per keypoint: zero-padded (2r+1)^2 window, weight = magnitude x
+//                               unnormalised Gaussian table, 36-bin histogram (:144-163).  Every lane owns a private
+//                               copy of the histogram in shared memory (no atomics, fixed summation order); bins are
+//                               rounded to float32 and compared with float32(0.8) * max (:165-167).  kOriCoded: the
+//                               certified float32 form (separable weights, bank-per-lane table, error-bound flag).
+//   orientation_recheck_kernel  the flagged keypoints of certified mode in float64, one CTA each.
+//   descriptor_kernel<T,OUT>    one warp per oriented keypoint: 16x16 nearest-neighbour rotated window with
+//                               OpenCV's 10-bit fixed-point coordinates (:175-212), 4x4 cells x 8 bins with
+//                               float32 cell histograms, normalise / clip [2^-10, 0.2] / normalise (:259-287).
+//                               Two lanes per cell, 8 samples per lane (float64 mode and caller-supplied planes).
+//   descriptor_coded_kernel<OUT>  the pipeline's kernel: half a warp per keypoint, a lane per cell, integer bins.
+//   sift_layout_kernel          final image-major placement of descriptors and keypoint records.
 #include <cuda_fp16.h>
 
 #include "fc_common.cuh"

@@ -1,16 +1,20 @@
-// SIFT scale space (sm_100a): one fused kernel per octave builds every Gaussian level from the octave
-// base (the reference blurs the BASE with each kernel, APP/utils/SIFT_scale_space.py:132,144 -- not
-// incrementally), a second kernel evaluates the 3x3x3 extremum rule on DoG values formed on the fly.
+// SIFT scale space (sm_100a).  The reference blurs the octave BASE with each kernel (APP/utils/SIFT_scale_space.py:132,
+// 144 -- not incrementally) and evaluates the 3x3x3 extremum rule on the DoG stack (:78-88).
 //
-//   gauss_octave_kernel<T, TX, TY>  base tile + halo -> shared memory ('symm' reflection), then per level:
-//                                   vertical pass (8 rows per thread, taps and the sliding window in
-//                                   registers) -> shared -> horizontal pass (4 columns per thread,
-//                                   float4 shared loads) -> coalesced vector stores.
-//   extrema_kernel<T>               DoG_k = G_{k+1} - G_k in shared memory, argmax==13 || argmin==13 rule
-//                                   (:78-88), optional script filter (SIFT.py:202-215), ballot -> bit mask.
+//   gauss_octave_kernel<T, TX, TY>  any radii <= 24, float32 / float64: base tile + halo -> shared memory ('symm'
+//                                   reflection), then per level vertical pass -> shared -> horizontal pass -> stores.
+//   gauss_octave_packed_kernel<IDENT0, SEARCH>
+//                                   the default radii (3, 5, 6, 9, 13) in packed fp32x2 arithmetic, TMA-staged tiles;
+//                                   SEARCH: DoG + certified extremum search on the tile, no level leaves the SM.
+//   gauss_mid_f64_kernel<MR, ...>   the float64 levels 1 .. s of certified mode, two per launch, radius classes.
+//   extrema_kernel / extrema_strip_kernel<ND, CERT>
+//                                   stand-alone search: exact (argmax == 13 || argmin == 13 rule, optional script
+//                                   filter SIFT.py:202-215) or certified (error margin + undecided list).
+//   extrema_repair_kernel           float64 decision of the undecided pixels.
+//   upsample2 / downsample2 (+ _dual: float64 and float32 outputs and the value bound in one pass), convert kernels.
 //
-// HBM traffic per octave pixel (T = float): 4 B base read + 4 B x n_levels written; the extrema kernel
-// re-reads the levels once (+ 4 B x n_levels) -- DESIGN.md states the algorithmic figure (24 B).
+// HBM traffic per octave pixel: DESIGN.md states the algorithmic figure (4 B base + 4 B x 5 levels = 24 B) and what the
+// kernels actually move (fused search form: 4.9 B).
 #include <string.h>
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
