@@ -217,6 +217,8 @@ static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the fi
 // decided here (the list holds up to n_keypoints entries; recheck_count is zeroed by the launcher).
 enum { kOriPlanes = 0, kOriCoded = 2 };
 static constexpr unsigned long long kOriRecheckBit = 1ull << 63;
+struct FalseTag { static constexpr bool value = false; };
+struct TrueTag { static constexpr bool value = true; };
 
 template <typename T, int LPK, int NR, int MODE>
 __global__ void __launch_bounds__(kOriWarps * 32)
@@ -286,6 +288,40 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
     float cw[NR];
 #pragma unroll
     for (int u = 0; u < NR; ++u) cw[u] = (PACKED && cok[u]) ? wx_tab[cb + u * LPK] : 0.f;
+    if constexpr (WIDE) {
+      // Certified float32 form.  A sample outside the window needs no dropped bin: its column factor is 0 and a masked
+      // load returns the word 0 (magnitude 0), so it adds +0 to bin 0.  Whole groups of NROWS rows run without any row
+      // test (ncu: predicates, default values and loop bookkeeping were 8 of 20 instructions per sample); one tail
+      // group checks its rows.
+      const uint32_t hbase = (uint32_t)__cvta_generic_to_shared(hme);
+      auto group = [&](auto check_rows, int rr) {
+        constexpr bool CHECK = decltype(check_rows)::value;
+        uint32_t p[NROWS][NR];
+        float rw[NROWS];
+#pragma unroll
+        for (int v = 0; v < NROWS; ++v) {
+          const bool row_ok = !CHECK || rr + v <= r1;
+          rw[v] = row_ok ? wy_tab[rr + v] : 0.f;
+#pragma unroll
+          for (int u = 0; u < NR; ++u) p[v][u] = (row_ok && cok[u]) ? (prow + (ptrdiff_t)v * W)[u * LPK] : 0u;
+        }
+        prow += (ptrdiff_t)NROWS * W;
+#pragma unroll
+        for (int v = 0; v < NROWS; ++v)
+#pragma unroll
+          for (int u = 0; u < NR; ++u) {
+            const uint32_t a = hbase + ((p[v][u] & 63u) << 7);  // 32 floats per bin row
+            const float wv = __fmul_rn(__uint_as_float((p[v][u] & ~255u) >> 1), __fmul_rn(rw[v], cw[u]));
+            float cur;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur) : "r"(a));
+            cur = __fadd_rn(cur, wv);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(cur) : "memory");
+          }
+      };
+      int rr = r0;
+      for (; rr + NROWS - 1 <= r1; rr += NROWS) group(FalseTag(), rr);
+      if (rr <= r1) group(TrueTag(), rr);
+    } else
     for (int rr = r0; rr <= r1; rr += NROWS) {
       int bins[NROWS][NR];
       T ws[NROWS][NR];
