@@ -177,3 +177,27 @@ def test_full_size_match_set_overlaps_reference(mods, large, ratio):
     b = set(map(tuple, ref.tolist()))
     assert len(b) > 1000
     assert len(a & b) >= 0.99 * len(a | b), (len(a), len(b), len(a & b))  # north_star: match sets overlap >= 99 %
+
+
+@pytest.mark.parametrize("params", [dict(), dict(sigma_base=2.5, s_value=3), dict(sigma_base=3.0, s_value=2), dict(n_octaves=6, s_value=5, sigma_base=2.0),
+                                    dict(variant="script", contrast_th=0.01, ratio_th=8.0)])
+def test_fullsize_certified_equals_float64_across_the_ui_ranges(mods, params):
+    """BASELINE config[1] size (1024x1024 -> 2048^2 base): at the default point, at other points of the app's parameter
+    ranges (radius classes of the float64 level kernel, repair patches up to radius 24, 6 .. 8 levels) and with the
+    script filter, certified mode must return the float64 mode's oriented keypoint list -- ~10^5 entries, every one a
+    chain of discrete decisions -- and descriptors within float32 rounding of it."""
+    backend, matching, sift, synthetic = mods
+    img = synthetic.sift_image(1024, 1024, seed=2, max_blobs=1024)
+    pm, pf = sift.SiftParams(dtype="mixed", **params), sift.SiftParams(dtype="f64", **params)
+    a = sift.detect_and_describe(sift.upsample2(img, pm), pm, out_dtype=torch.float32)
+    assert a.undecided_extrema > 0  # the float64 repair had work to do
+    pa, da = a.assemble(1)[0]
+    del a
+    b = sift.detect_and_describe(sift.upsample2(img, pf), pf, out_dtype=torch.float64)
+    pb, db = b.assemble(1)[0]
+    del b
+    assert pb.shape[0] > 5000
+    assert np.array_equal(pa, pb)
+    ok = ~np.isnan(db).any(1)
+    assert np.array_equal(np.isnan(da).any(1), ~ok)
+    assert np.linalg.norm(da[ok] - db[ok], axis=1).max() < 2e-5
