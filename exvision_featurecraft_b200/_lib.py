@@ -75,10 +75,10 @@ SIGNATURES = {
     "fc_downsample2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "fc_convert_f64": (_i, [_p, _i64, _i, _p, _p]),
     "fc_gradient_field": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
-    "fc_orientation_bins": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p]),
+    "fc_orientation_bins": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _i, _p]),
     "fc_sift_layout": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "fc_orientation_bins_coded": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _d, _p, _p, _p, _p]),
-    "fc_orientation_recheck": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "fc_orientation_recheck": (_i, [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _i, _i, _p, _p, _p, _i, _p]),
     "fc_gradient_codes": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fc_descriptors_coded": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _p, _p]),
     "fc_convert_f64_bound": (_i, [_p, _i64, _p, _p, _p]),

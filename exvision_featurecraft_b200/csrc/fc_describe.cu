@@ -217,6 +217,16 @@ static constexpr int kOriPitch = 33;  // [bin][lane] with one pad column: the fi
 // decided here (the list holds up to n_keypoints entries; recheck_count is zeroed by the launcher).
 enum { kOriPlanes = 0, kOriCoded = 2 };
 static constexpr unsigned long long kOriRecheckBit = 1ull << 63;
+
+// `hist >= 0.8 * hist.max()` (APP/utils/keypoint_descriptor.py:165-167) with a float32 histogram.  numpy >= 2 (NEP 50, what
+// this image has and the golden vectors were produced with): the Python float is weak, the product is float32(0.8) * max in
+// float32.  numpy 1.26, which the reference's requirements.txt pins: the scalar product is float64 and is rounded to
+// float32 for the comparison.  The two cuts differ by at most one float32 ulp (in ~20 % of the cases), i.e. only for a bin
+// that sits on the cut; `legacy` selects the second form.  The certified float32 kernel needs no switch: whatever lies
+// within its tolerance of the cut is decided by the float64 re-check, which has one.
+__device__ __forceinline__ float orientation_cut(float mx, int legacy) {
+  return legacy ? __double2float_rn(__dmul_rn(0.8, (double)mx)) : __fmul_rn(0.8f, mx);
+}
 struct FalseTag { static constexpr bool value = false; };
 struct TrueTag { static constexpr bool value = true; };
 
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(kOriWarps * 32)
 orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, int H, int W,
                    const int32_t* __restrict__ keypoints, int n_keypoints, const T* __restrict__ weights,
                    int radius, int wry, int wrx, float tol, unsigned long long* __restrict__ bin_mask,
-                   int32_t* __restrict__ recheck_list, int32_t* __restrict__ recheck_count) {
+                   int32_t* __restrict__ recheck_list, int32_t* __restrict__ recheck_count, int legacy_cut) {
   constexpr bool PACKED = MODE != kOriPlanes;
   constexpr int KPW = 32 / LPK;        // keypoints per warp
   // kOriPlanes: [keypoint][bin][lane of the keypoint], rows of LPK values (clearing and the final sums move 16 bytes at a time).
@@ -448,10 +458,7 @@ orientation_kernel(const T* __restrict__ mag, const uint8_t* __restrict__ obin, 
   }
 #pragma unroll
   for (int o = LPK / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  // numpy >= 2 (NEP 50, what the golden vectors were produced with): python float * float32 scalar stays float32.
-  // The reference pins numpy 1.26, whose legacy promotion rounds the float64 product 0.8 * max to float32 instead: the
-  // two cuts differ by at most one float32 ulp, i.e. only for a bin that sits exactly on the cut (parity).
-  const float cut = __fmul_rn(0.8f, mx);
+  const float cut = orientation_cut(mx, legacy_cut);
   uint32_t lo = 0u, hi = 0u;
 #pragma unroll
   for (int q = 0; q < NB; ++q) {
@@ -504,7 +511,7 @@ orientation_recheck_kernel(const double* __restrict__ levels, int n_planes, int 
                            int H, int W, const int32_t* __restrict__ keypoints, int n_keypoints,
                            const double* __restrict__ weights, int radius, int wry, int wrx,
                            unsigned long long* __restrict__ bin_mask, const int32_t* __restrict__ recheck_list,
-                           const int32_t* __restrict__ recheck_count) {
+                           const int32_t* __restrict__ recheck_count, int legacy_cut) {
   extern __shared__ __align__(16) double rc_hist[];  // [warp][bin 0..36][33]
   __shared__ float s_f[kOriBins];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -566,7 +573,7 @@ orientation_recheck_kernel(const double* __restrict__ levels, int n_planes, int 
       float mx = fmaxf(f0, f1);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float cut = __fmul_rn(0.8f, mx);
+      const float cut = orientation_cut(mx, legacy_cut);
       const uint32_t lo = __ballot_sync(0xffffffffu, f0 >= cut);
       const uint32_t hi = __ballot_sync(0xffffffffu, lane + 32 < kOriBins && f1 >= cut);
       if (lane == 0) bin_mask[n] = (unsigned long long)lo | ((unsigned long long)hi << 32);
@@ -1010,7 +1017,7 @@ extern "C" int fc_gradient_field(const void* gauss, int dtype, int batch, int n_
 static int launch_orientation(const void* magnitude, const uint8_t* orientation_bin, int dtype, int mode, int batch,
                               int height, int width, const int32_t* keypoints, int n_keypoints, const void* weights,
                               int radius, int table_ry, int table_rx, float tol, uint64_t* bin_mask, int32_t* recheck_list,
-                              int32_t* recheck_count, void* stream) {
+                              int32_t* recheck_count, int legacy_cut, void* stream) {
   if (mode == kOriCoded && (!recheck_list || !recheck_count)) return FC_ERR_BAD_ARG;
   if (mode == kOriCoded) FC_CUDA_TRY(cudaMemsetAsync(recheck_count, 0, sizeof(int32_t), (cudaStream_t)stream));
   if (!magnitude || (mode == kOriPlanes && !orientation_bin) || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0)
@@ -1031,7 +1038,7 @@ static int launch_orientation(const void* magnitude, const uint8_t* orientation_
 #define FC_ORI(T, LPK, NR, MD)                                                                                      \
   orientation_kernel<T, LPK, NR, MD><<<div_up(n_keypoints, kOriWarps * (32 / LPK)), kOriWarps * 32, 0, st>>>(        \
       (const T*)magnitude, orientation_bin, height, width, keypoints, n_keypoints, (const T*)weights, radius,      \
-      table_ry, table_rx, tol, (unsigned long long*)bin_mask, recheck_list, recheck_count)
+      table_ry, table_rx, tol, (unsigned long long*)bin_mask, recheck_list, recheck_count, legacy_cut)
 #define FC_ORI_T(T, MD)                                              \
   do {                                                               \
     if (lpk == 8) {                                                  \
@@ -1054,9 +1061,10 @@ static int launch_orientation(const void* magnitude, const uint8_t* orientation_
 
 extern "C" int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
                                    int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
-                                   int table_ry, int table_rx, uint64_t* bin_mask, void* stream) {
+                                   int table_ry, int table_rx, uint64_t* bin_mask, int numpy_legacy_promotion, void* stream) {
   return launch_orientation(magnitude, orientation_bin, dtype, kOriPlanes, batch, height, width, keypoints, n_keypoints,
-                            weights, radius, table_ry, table_rx, 0.f, bin_mask, nullptr, nullptr, stream);
+                            weights, radius, table_ry, table_rx, 0.f, bin_mask, nullptr, nullptr, numpy_legacy_promotion != 0,
+                            stream);
 }
 
 extern "C" int fc_orientation_bins_coded(const uint32_t* codes, int batch, int height, int width, const int32_t* keypoints,
@@ -1065,13 +1073,13 @@ extern "C" int fc_orientation_bins_coded(const uint32_t* codes, int batch, int h
                                          void* stream) {
   if (!(tolerance >= 0.0)) return FC_ERR_BAD_ARG;
   return launch_orientation(codes, nullptr, FC_F32, kOriCoded, batch, height, width, keypoints, n_keypoints, weights, radius,
-                            table_ry, table_rx, (float)tolerance, bin_mask, recheck_list, recheck_count, stream);
+                            table_ry, table_rx, (float)tolerance, bin_mask, recheck_list, recheck_count, 0, stream);
 }
 
 extern "C" int fc_orientation_recheck(const double* levels, int n_planes, int plane, const uint32_t* codes, int batch,
                                       int height, int width, const int32_t* keypoints, int n_keypoints, const double* weights,
                                       int radius, int table_ry, int table_rx, uint64_t* bin_mask, const int32_t* recheck_list,
-                                      const int32_t* recheck_count, void* stream) {
+                                      const int32_t* recheck_count, int numpy_legacy_promotion, void* stream) {
   if (!recheck_list || !recheck_count) return FC_ERR_BAD_ARG;
   if (!levels || !codes || !weights || batch <= 0 || height <= 0 || width <= 0 || radius < 0 || plane < 0 || plane >= n_planes)
     return FC_ERR_BAD_ARG;
@@ -1083,7 +1091,7 @@ extern "C" int fc_orientation_recheck(const double* levels, int n_planes, int pl
   FC_CUDA_TRY(cudaFuncSetAttribute(orientation_recheck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecheckSmem));
   orientation_recheck_kernel<<<n_keypoints < 148 * 2 ? n_keypoints : 148 * 2, kRecheckWarps * 32, kRecheckSmem, (cudaStream_t)stream>>>(
       levels, n_planes, plane, codes, height, width, keypoints, n_keypoints, weights, radius, table_ry, table_rx,
-      (unsigned long long*)bin_mask, recheck_list, recheck_count);
+      (unsigned long long*)bin_mask, recheck_list, recheck_count, numpy_legacy_promotion != 0);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;

@@ -44,6 +44,10 @@ class SiftParams:
     # (An uncertified float32 mode existed in round 1: ~1 % of its descriptors had a sample on the wrong side of a bin
     # edge and a few dozen extrema per image flipped; certified mode costs 35 % more time and has neither.)
     dtype: str = "mixed"
+    # `hist >= 0.8 * hist.max()` on the float32 orientation histogram: numpy >= 2 multiplies in float32 (default; what this
+    # image's numpy does and what the golden vectors were produced with), numpy 1.26 -- the version the reference's
+    # requirements.txt pins -- rounds the float64 product to float32.  The cuts differ by at most one float32 ulp.
+    numpy_legacy_promotion: bool = False
 
     def __post_init__(self):
         if self.dtype not in ("mixed", "f64"):
@@ -555,16 +559,16 @@ def orientation_tolerance(radius: int) -> float:
     return 2.0 * (2.0 ** -17 + (per_lane + lanes + 6) * 2.0 ** -24)
 
 
-def orientation_bins(mag, obin, keypoints, n, sigma, bin_mask):
+def orientation_bins(mag, obin, keypoints, n, sigma, bin_mask, legacy=False):
     """Launch the 36-bin histogram kernel on gradient_field's magnitude / bin planes."""
     b, h, w = mag.shape
     fc = _lib.FC_F32 if mag.dtype == torch.float32 else _lib.FC_F64
     radius, ry, rx, weights = _orientation_weights(sigma, h, w, mag.dtype)
     _lib.call("fc_orientation_bins", ptr(mag), ptr(obin), fc, b, h, w, ptr(keypoints), n, ptr(weights), radius, ry, rx,
-              ptr(bin_mask), stream_ptr())
+              ptr(bin_mask), int(bool(legacy)), stream_ptr())
 
 
-def orientation_bins_certified(levels64, plane, codes, keypoints, n, sigma, bin_mask, recheck_list, recheck_count):
+def orientation_bins_certified(levels64, plane, codes, keypoints, n, sigma, bin_mask, recheck_list, recheck_count, legacy=False):
     """Certified mode: float32 histograms from the code words, then the float64 decision of the keypoints whose
     0.8 * max comparison the float32 error bound cannot guarantee (recheck_list: int32 [n] scratch, recheck_count: [1])."""
     b, h, w = codes.shape
@@ -573,7 +577,7 @@ def orientation_bins_certified(levels64, plane, codes, keypoints, n, sigma, bin_
     _lib.call("fc_orientation_bins_coded", ptr(codes), b, h, w, ptr(keypoints), n, ptr(w32), radius, ry, rx,
               float(orientation_tolerance(radius)), ptr(bin_mask), ptr(recheck_list), ptr(recheck_count), stream_ptr())
     _lib.call("fc_orientation_recheck", ptr(levels64), levels64.shape[1], plane, ptr(codes), b, h, w, ptr(keypoints), n,
-              ptr(w64), radius, ry, rx, ptr(bin_mask), ptr(recheck_list), ptr(recheck_count), stream_ptr())
+              ptr(w64), radius, ry, rx, ptr(bin_mask), ptr(recheck_list), ptr(recheck_count), int(bool(legacy)), stream_ptr())
 
 
 def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
@@ -583,7 +587,7 @@ def orient(mag, obin, keypoints, sigma, params: SiftParams) -> torch.Tensor:
     if n == 0:
         return torch.empty((0, 4), dtype=torch.int32, device=dev)
     bin_mask = torch.empty(n, dtype=torch.int64, device=dev)
-    orientation_bins(mag, obin, keypoints, n, sigma, bin_mask)
+    orientation_bins(mag, obin, keypoints, n, sigma, bin_mask, params.numpy_legacy_promotion)
     offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
     scratch = scan_scratch(n)
     _lib.call("fc_orientation_scan", ptr(bin_mask), n, ptr(offsets), ptr(scratch), stream_ptr())
@@ -729,13 +733,14 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
                 codes = gradient_codes(mid, k - 1)
             with _stage("orientation"):
                 orientation_bins_certified(mid, k - 1, codes, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]],
-                                           recheck_all[kp_start[i]:kp_end[i]], recheck_counts[i:i + 1])
+                                           recheck_all[kp_start[i]:kp_end[i]], recheck_counts[i:i + 1],
+                                           params.numpy_legacy_promotion)
             state.append((codes, None, sigma))
             continue
         with _stage("gradient_field"):
             mag, direction, obin = gradient_field(octv, k, params)
         with _stage("orientation"):
-            orientation_bins(mag, obin, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]])
+            orientation_bins(mag, obin, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]], params.numpy_legacy_promotion)
         state.append((mag, direction, sigma))
     batch = octaves[0].batch
     if total_kp == 0:

@@ -292,10 +292,12 @@ FC_API int fc_gradient_codes(const double* levels, int batch, int n_planes, int 
  * clipped to the image can reach: a dense (2 table_ry + 1) x (2 table_rx + 1) device table of element type `dtype`,
  * entry [dy + table_ry][dx + table_rx], table_ry >= min(radius, h - 1), table_rx >= min(radius, w - 1).
  * For keypoint n the 36-bin float32 histogram is built (sums in `dtype`) and bin_mask[n] receives bit b for every
- * bin with hist[b] >= float32(0.8) * max (:165-167). */
+ * bin with hist[b] >= cut (:165-167); cut = float32(0.8) * max in float32 (numpy >= 2, NEP 50: the default and what the
+ * golden vectors were produced with) or, with numpy_legacy_promotion != 0, float32(0.8 * float64(max)) (numpy 1.26, the
+ * version the reference pins): the two differ by at most one float32 ulp. */
 FC_API int fc_orientation_bins(const void* magnitude, const uint8_t* orientation_bin, int dtype, int batch, int height,
                         int width, const int32_t* keypoints, int n_keypoints, const void* weights, int radius,
-                        int table_ry, int table_rx, uint64_t* bin_mask, void* stream);
+                        int table_ry, int table_rx, uint64_t* bin_mask, int numpy_legacy_promotion, void* stream);
 /* certified mode: float32 histograms from fc_gradient_codes' words; a keypoint with a bin within
  * tolerance * max of the cut gets bit 63 of its mask set instead of a decision and its index appended to
  * recheck_list (int32 [n_keypoints]; recheck_count[0] is zeroed first) ...
@@ -311,7 +313,7 @@ FC_API int fc_orientation_bins_coded(const uint32_t* codes, int batch, int heigh
 FC_API int fc_orientation_recheck(const double* levels, int n_planes, int plane, const uint32_t* codes, int batch,
                            int height, int width, const int32_t* keypoints, int n_keypoints, const double* weights,
                            int radius, int table_ry, int table_rx, uint64_t* bin_mask, const int32_t* recheck_list,
-                           const int32_t* recheck_count, void* stream);
+                           const int32_t* recheck_count, int numpy_legacy_promotion, void* stream);
 
 /* Expand bin masks into oriented keypoints in reference order: offsets[n] = popcount prefix
  * (exclusive, offsets[n_keypoints] = total; scratch as for fc_mask_scan), then

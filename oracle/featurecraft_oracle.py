@@ -493,9 +493,12 @@ def keypoint_sigma(sigma_base, octave_idx, scale_idx, s):
     return 1.5 * sigma_base * (2 ** octave_idx) * ((2 ** (1 / s)) ** (scale_idx))
 
 
-def dog_keypoints_orientations(img_gaussians, keypoints, sigma_base, num_bins=36, s=2):
+def dog_keypoints_orientations(img_gaussians, keypoints, sigma_base, num_bins=36, s=2, numpy_legacy_promotion=False):
     """APP/utils/keypoint_descriptor.py:116-172.  Bin index by np.round (half to even) so bin
-    `num_bins` exists and is dropped; float32 histogram; EVERY bin >= 0.8*max emits a keypoint."""
+    `num_bins` exists and is dropped; float32 histogram; EVERY bin >= 0.8*max emits a keypoint.
+    numpy_legacy_promotion: evaluate `hist >= 0.8 * hist.max()` the way numpy 1.26 (the reference's pinned version) does --
+    float64 scalar product, rounded to float32 for the comparison with the float32 array -- instead of this image's
+    numpy >= 2 rule (float32 product); an emulation, the reference itself can only be run under the numpy installed here."""
     kps = []
     for o in range(len(img_gaussians)):
         for idx, mask in enumerate(keypoints[o]):
@@ -513,7 +516,8 @@ def dog_keypoints_orientations(img_gaussians, keypoints, sigma_base, num_bins=36
                 hist = np.zeros(num_bins, dtype=np.float32)
                 for b in range(num_bins):
                     hist[b] = np.sum(weight[dwin == b])
-                for b in np.argwhere(hist >= 0.8 * hist.max()).tolist():
+                cut = np.float32(0.8 * float(hist.max())) if numpy_legacy_promotion else 0.8 * hist.max()
+                for b in np.argwhere(hist >= cut).tolist():
                     kps.append((i, j, o, scale_idx, (b[0] + 0.5) * (360.0 / num_bins) % 360))
     return kps
 
@@ -590,13 +594,13 @@ def extract_sift_descriptors(img_gaussians, keypoints, base_sigma, num_bins=8, s
 
 
 def compute_keypoints_and_descriptors_from_base(base_image, n_octaves, s_value, sigma_base, contrast_th, r_ratio,
-                                                variant="app", blur_mode="direct"):
+                                                variant="app", blur_mode="direct", numpy_legacy_promotion=False):
     """computeKeypointsAndDescriptors (APP/utils/keypoint_descriptor.py:292-311) from the point
     AFTER rescale(x2): pyramid -> masks -> orientations -> descriptors."""
     pyramid, dog, kps = generate_octaves_pyramid(base_image, n_octaves, s_value, sigma_base, contrast_th, r_ratio,
                                                  variant, blur_mode)
     masks = represent_keypoints(kps, dog)
-    oriented = dog_keypoints_orientations(pyramid, masks, sigma_base, 36, s_value)
+    oriented = dog_keypoints_orientations(pyramid, masks, sigma_base, 36, s_value, numpy_legacy_promotion)
     return extract_sift_descriptors(pyramid, oriented, sigma_base, 8, s_value)
 
 

@@ -184,3 +184,65 @@ def test_large_image_properties(S):
     flat = S.scale_space(np.full((128, 160), 0.25), S.SiftParams(dtype="f64"))
     assert int(flat[0].extrema.ne(0).sum()) == 0
     assert abs(flat[0].gauss[0, 0, 64, 80].item() - 0.25 * kern[0].sum()) < 1e-15
+
+
+def test_orientation_cut_follows_the_selected_numpy_promotion_rule(lib):
+    """`hist >= 0.8 * hist.max()` on a float32 histogram: numpy >= 2 multiplies in float32, numpy 1.26 (pinned by the
+    reference) rounds the float64 product -- the cuts differ by one float32 ulp for ~20 % of the maxima.  A histogram
+    with one bin exactly on the smaller of the two cuts must pass under one rule and fail under the other, in the
+    float64 kernel and in the certified pipeline's re-check alike (same code path: orientation_cut)."""
+    import torch
+
+    from exvision_featurecraft_b200 import sift
+
+    sigma = 2.0
+    radius = int(round(sigma * 2))
+    table = sift.gaussian_window_table(sigma)
+    w0, w1 = float(table[radius, radius]), float(table[radius, radius + 1])
+    rng = np.random.default_rng(5)
+    found = 0
+    for _ in range(200):
+        mx = np.float32(rng.uniform(0.01, 0.5))
+        cut_new, cut_old = np.float32(0.8) * mx, np.float32(0.8 * float(mx))
+        if cut_new == cut_old:
+            continue
+        lo_cut = min(cut_new, cut_old)
+        m0, m1 = float(mx) / w0, float(lo_cut) / w1
+        if np.float32(m0 * w0) != mx or np.float32(m1 * w1) != lo_cut:
+            continue  # the double product does not round back to the float32 target: try another maximum
+        h = w = 4 * radius + 1
+        mag = np.zeros((1, h, w)); obin = np.zeros((1, h, w), np.uint8)
+        c = 2 * radius
+        mag[0, c, c], obin[0, c, c] = m0, 0
+        mag[0, c, c + 1], obin[0, c, c + 1] = m1, 5
+        kp = torch.tensor([[0, c, c]], dtype=torch.int32, device="cuda")
+        got = {}
+        for legacy in (False, True):
+            mask = torch.zeros(1, dtype=torch.int64, device="cuda")
+            sift.orientation_bins(torch.from_numpy(mag).cuda(), torch.from_numpy(obin).cuda(), kp, 1, sigma, mask, legacy)
+            got[legacy] = int(mask.item())
+        assert got[False] & 1 and got[True] & 1  # the maximum itself always passes
+        assert bool(got[False] & (1 << 5)) == bool(lo_cut >= cut_new)
+        assert bool(got[True] & (1 << 5)) == bool(lo_cut >= cut_old)
+        assert got[False] != got[True]
+        found += 1
+        if found >= 5:
+            break
+    assert found >= 3
+
+
+@pytest.mark.parametrize("dtype", ["f64", "mixed"])
+def test_full_pipeline_with_numpy_legacy_promotion_equals_the_oracle(S, dtype):
+    """SiftParams(numpy_legacy_promotion=True) against the oracle evaluating the orientation cut the numpy-1.26 way (an
+    emulation: the reference itself only runs under this image's numpy >= 2, whose rule is the default everywhere else)."""
+    from exvision_featurecraft_b200 import synthetic
+
+    base = synthetic.sift_image(72, 100, seed=2)
+    rp, rd = O.compute_keypoints_and_descriptors_from_base(base, 4, 2, 1.6, 0.03, 10, numpy_legacy_promotion=True)
+    p = S.SiftParams(dtype=dtype, numpy_legacy_promotion=True)
+    pts, desc = S.detect_and_describe(base, p, out_dtype=torch.float64).assemble(1)[0]
+    assert np.array_equal(pts, np.array(rp, dtype=np.float64).reshape(-1, 5))
+    rd = np.asarray(rd, dtype=np.float64)
+    ok = ~np.isnan(rd).any(1)
+    assert np.array_equal(np.isnan(desc).any(1), ~ok)
+    assert np.abs(desc[ok] - rd[ok]).max() < (1e-9 if dtype == "f64" else 2e-5)
