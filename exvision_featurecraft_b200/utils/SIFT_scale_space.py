@@ -16,6 +16,7 @@ from ..device import ptr, stream_ptr, to_device
 
 DTYPE = "mixed"
 VARIANT = "app"
+NUMPY_LEGACY_PROMOTION = False  # orientation cut the numpy-1.26 way (the reference's pinned numpy); see sift.SiftParams
 
 
 def set_dtype(dtype: str) -> None:
@@ -27,6 +28,11 @@ def set_dtype(dtype: str) -> None:
 def stage_dtype() -> str:
     """arithmetic of the stage-level mirrors: they hand float64 images back to the caller like the reference does"""
     return "f64"
+
+
+def set_numpy_legacy_promotion(on: bool) -> None:
+    global NUMPY_LEGACY_PROMOTION
+    NUMPY_LEGACY_PROMOTION = bool(on)
 
 
 def set_variant(variant: str) -> None:

@@ -108,7 +108,8 @@ def represent_keypoints(keypoints, DoG):
 
 
 def _params(s, sigma_base=1.6, n_octaves=4):
-    return sift.SiftParams(n_octaves=n_octaves, s_value=s, sigma_base=sigma_base, dtype=_ss.stage_dtype(), variant=_ss.VARIANT)
+    return sift.SiftParams(n_octaves=n_octaves, s_value=s, sigma_base=sigma_base, dtype=_ss.stage_dtype(), variant=_ss.VARIANT,
+                           numpy_legacy_promotion=_ss.NUMPY_LEGACY_PROMOTION)
 
 
 def _level_as_octave(img, p):
@@ -210,7 +211,8 @@ def extract_sift_descriptors(img_gaussians, keypoints, base_sigma, num_bins=8, s
 def extract_device(image, n_octaves, s_value, sigma_base, constract_th, r_ratio, out_dtype=torch.float32) -> "sift.SiftResult":
     """computeKeypointsAndDescriptors with everything left on the device (records + descriptors of one image)."""
     gray = convert_to_grayscale(image)
-    p = sift.SiftParams(n_octaves, s_value, sigma_base, constract_th, r_ratio, _ss.VARIANT, _ss.DTYPE)
+    p = sift.SiftParams(n_octaves, s_value, sigma_base, constract_th, r_ratio, _ss.VARIANT, _ss.DTYPE,
+                        _ss.NUMPY_LEGACY_PROMOTION)
     base = sift.upsample2(gray if isinstance(gray, torch.Tensor) else np.asarray(gray, dtype=np.float64), p)
     return sift.detect_and_describe(base, p, out_dtype=out_dtype)
 
