@@ -100,7 +100,7 @@ class SiftWorkload:
         # SURVEY 8(d), pyramid + DoG + extrema row: 4 B base read + 5 x 4 B levels per octave pixel
         alg = 24.0 * self.batch * (2 * self.H) * (2 * self.W)
         if self.mode == "f64":
-            return [("gauss_octave_kernel<double> (octave 0, blur only)", 2 * alg, ms, "hbm")]
+            return [("gauss_mid_f64_kernel x 3 (octave 0, float64 blur only: levels in pairs through the radius-class kernel)", 2 * alg, ms, "hbm")]
         if self.overrides:
             nl = self.params.n_levels
             return [("gauss_octave_kernel<float> (octave 0, %d levels, blur only: non-default radii)" % nl,

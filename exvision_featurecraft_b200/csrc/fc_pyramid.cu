@@ -151,7 +151,8 @@ __device__ __forceinline__ void blur_level(const T* sIn, int rmax, T* sTmp, cons
 // RCLASS = largest radius this instantiation can run (registers are sized by the largest unrolled case)
 template <typename T, int TX, int TY, int RCLASS, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, int rmax, T* __restrict__ gauss) {
+gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, int rmax, T* __restrict__ gauss,
+                    int n_planes, int plane0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // pitches are compile-time (sized for RCLASS) so that every shared-memory offset is an immediate
   constexpr int ip = TX + 2 * RCLASS + 1;                   // input tile pitch
@@ -165,7 +166,7 @@ gauss_octave_kernel(const T* __restrict__ base, int H, int W, TapTable<T> tab, i
   const int b = blockIdx.z;
   const T* img = base + (size_t)b * H * W;
   const int L = tab.n_levels;
-  T* gout = gauss + (size_t)b * L * H * W;
+  T* gout = gauss + ((size_t)b * n_planes + plane0) * H * W;  // the table's levels go to planes plane0 .. of an n_planes stack
   {
     // one warp per tile row, lanes along the row (coalesced); reflection only where the tile leaves the image.
     // Every element goes global -> shared with its own cp.async (LDGSTS): all ~32 copies of a thread are in flight
@@ -1165,9 +1166,9 @@ gauss_octave_packed_kernel(const float* __restrict__ base, int H, int W, int til
 // come out of one pass over a shared-memory tile with the pair sums v[-k] + v[+k] shared between them:
 // tile = 116 x 32 outputs from 128 x 44 inputs, 19 + 24 float64 operations per pixel.
 struct MidTaps {
-  double t[2][13];  // t[l][k] = tap at distance k (centre first), zero beyond the radius
+  double t[2][15];  // t[l][k] = tap at distance k (centre first), zero beyond the radius
 };
-static constexpr int kMTY = 32, kMP = 128;
+static constexpr int kMTY = 32, kMP = 128, kMidMaxRadius = 14;
 static constexpr size_t kMidSmem = sizeof(double) * (size_t)(2 * kMTY * kMP);
 
 // The vertical pass reads its column segments straight from global memory (coalesced along the row, all loads of a
@@ -1184,9 +1185,9 @@ template <int MR, int RA, int RB, int ROWS, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 gauss_mid_f64_kernel(const double* __restrict__ base, int H, int W, const __grid_constant__ MidTaps taps,
                      double* __restrict__ out, int n_planes, int plane0) {
-  static_assert(RA <= MR && RB <= MR && MR <= 12 && MR % 2 == 0 && kMTY % ROWS == 0, "radius class");
+  static_assert(RA <= MR && RB <= MR && MR <= 14 && MR % 2 == 0 && kMTY % ROWS == 0, "radius class");
   constexpr int NL = RB > 0 ? 2 : 1;
-  constexpr int TX = (kMP - 2 * MR) / 6 * 6;  // output columns per tile: 114, 108, 108, 102 for MR = 6, 8, 10, 12
+  constexpr int TX = (kMP - 2 * MR) / 6 * 6;  // output columns per tile: 114, 108, 108, 102, 96 for MR = 6, 8, 10, 12, 14
   extern __shared__ __align__(16) unsigned char mid_smem[];
   double* sTmp = reinterpret_cast<double*>(mid_smem);  // [2][kMTY][kMP]
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * kMTY;
@@ -1285,11 +1286,11 @@ static int launch_mid_f64(const double* base, int B, int H, int W, const MidTaps
   return FC_OK;
 }
 
-// one or two consecutive float64 levels (radii ra, rb <= 12; rb = 0: one level) into planes plane0, plane0 + 1 of `out`
+// one or two consecutive float64 levels (radii ra, rb <= 14 = kMidMaxRadius; rb = 0: one level) into planes plane0, plane0 + 1 of `out`
 static int launch_mid_levels(const double* base, int B, int H, int W, const double* taps_a, int ra, const double* taps_b, int rb,
                              double* out, int n_planes, int plane0, cudaStream_t st) {
   MidTaps mt;
-  for (int k = 0; k < 13; ++k) {
+  for (int k = 0; k < 15; ++k) {
     mt.t[0][k] = k <= ra ? taps_a[ra + k] : 0.0;
     mt.t[1][k] = (rb > 0 && k <= rb) ? taps_b[rb + k] : 0.0;
   }
@@ -1299,7 +1300,8 @@ static int launch_mid_levels(const double* base, int B, int H, int W, const doub
   if (rm <= 6) FC_MID(6, 8, 3);
   if (rm <= 8) FC_MID(8, 8, 2);
   if (rm <= 10) FC_MID(10, 4, 2);
-  FC_MID(12, 4, 2);
+  if (rm <= 12) FC_MID(12, 4, 2);
+  FC_MID(14, 4, 2);
 #undef FC_MID
 }
 
@@ -1402,7 +1404,7 @@ static bool fused_applicable(int L, const double* taps_host, const int* tap_len_
 
 template <typename T, int TX, int TY, int RCLASS, int MINB>
 static int launch_octave_cfg(const void* base, int B, int H, int W, const TapTable<T>& tab, int rmax, void* gauss,
-                             cudaStream_t st) {
+                             cudaStream_t st, int n_planes = 0, int plane0 = 0) {
   constexpr int ip = TX + 2 * RCLASS + 1;
   constexpr int tpitch = TX + 2 * ((RCLASS + 3) & ~3) + 4;
   const int ih = TY + 2 * rmax;
@@ -1412,16 +1414,18 @@ static int launch_octave_cfg(const void* base, int B, int H, int W, const TapTab
   auto kern = gauss_octave_kernel<T, TX, TY, RCLASS, MINB>;
   FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(div_up(W, TX), div_up(H, TY), B);
-  kern<<<grid, 256, smem, st>>>((const T*)base, H, W, tab, rmax, (T*)gauss);
+  kern<<<grid, 256, smem, st>>>((const T*)base, H, W, tab, rmax, (T*)gauss, n_planes > 0 ? n_planes : tab.n_levels, plane0);
   note_launch();
   note_path(FC_PATH_GENERIC_OCTAVE);
   FC_RETURN_IF_LAUNCH_FAILED();
   return FC_OK;
 }
 
+// n_planes = 0: `gauss` is the octave's own [B][L][H][W] stack.  n_planes > 0: the L levels of this call go to planes
+// plane0 .. plane0 + L - 1 of a [B][n_planes][H][W] stack (one level of a stack the float64 class kernel fills otherwise).
 template <typename T>
 static int launch_octave(const void* base, int B, int H, int W, int L, const double* taps_host, const int* tap_len_host,
-                         int first_is_identity, void* gauss, cudaStream_t st) {
+                         int first_is_identity, void* gauss, cudaStream_t st, int n_planes = 0, int plane0 = 0) {
   TapTable<T> tab;
   tab.n_levels = L;
   tab.first_is_identity = first_is_identity;
@@ -1446,11 +1450,40 @@ static int launch_octave(const void* base, int B, int H, int W, int L, const dou
   }
   for (int l = L; l < kMaxLevels; ++l) tab.radius[l] = tab.offset[l] = 0;
   if constexpr (sizeof(T) == 4) {
-    if (rmax <= 16) return launch_octave_cfg<T, 64, 64, 16, 3>(base, B, H, W, tab, rmax, gauss, st);
-    return launch_octave_cfg<T, 64, 64, 24, 1>(base, B, H, W, tab, rmax, gauss, st);
+    if (rmax <= 16) return launch_octave_cfg<T, 64, 64, 16, 3>(base, B, H, W, tab, rmax, gauss, st, n_planes, plane0);
+    return launch_octave_cfg<T, 64, 64, 24, 1>(base, B, H, W, tab, rmax, gauss, st, n_planes, plane0);
   } else {
-    if (rmax <= 16) return launch_octave_cfg<T, 32, 32, 16, 1>(base, B, H, W, tab, rmax, gauss, st);
-    return launch_octave_cfg<T, 32, 32, 24, 1>(base, B, H, W, tab, rmax, gauss, st);
+    if (n_planes == 0) {
+      // float64: levels with radii up to kMidMaxRadius go through the two-level class kernel (same operation order, so
+      // the same bits -- the certified mode's tests compare the two), in consecutive pairs; a larger radius takes the
+      // generic kernel for that level alone.  The default stack (3, 5, 6, 9, 13) is three class launches.
+      bool any_small = false;
+      for (int l = first_is_identity ? 1 : 0; l < L; ++l) any_small |= tab.radius[l] <= kMidMaxRadius;
+      if (any_small) {
+        const size_t plane = (size_t)H * W;
+        if (first_is_identity)  // level 0 of octaves > 0 is the base itself (:136-137)
+          FC_CUDA_TRY(cudaMemcpy2DAsync(gauss, (size_t)L * plane * sizeof(double), base, plane * sizeof(double),
+                                        plane * sizeof(double), (size_t)B, cudaMemcpyDeviceToDevice, st));
+        int l = first_is_identity ? 1 : 0;
+        while (l < L) {
+          const int r = tab.radius[l];
+          int rc;
+          if (r <= kMidMaxRadius) {
+            const int rb = (l + 1 < L && tab.radius[l + 1] <= kMidMaxRadius) ? tab.radius[l + 1] : 0;
+            rc = launch_mid_levels((const double*)base, B, H, W, taps_host + tab.offset[l], r,
+                                   taps_host + (rb ? tab.offset[l + 1] : 0), rb, (double*)gauss, L, l, st);
+            l += rb ? 2 : 1;
+          } else {
+            rc = launch_octave<T>(base, B, H, W, 1, taps_host + tab.offset[l], tap_len_host + l, 0, gauss, st, L, l);
+            l += 1;
+          }
+          if (rc != FC_OK) return rc;
+        }
+        return FC_OK;
+      }
+    }
+    if (rmax <= 16) return launch_octave_cfg<T, 32, 32, 16, 1>(base, B, H, W, tab, rmax, gauss, st, n_planes, plane0);
+    return launch_octave_cfg<T, 32, 32, 24, 1>(base, B, H, W, tab, rmax, gauss, st, n_planes, plane0);
   }
 }
 
@@ -1729,22 +1762,6 @@ extern "C" int fc_gauss_levels_f64(const double* base, int batch, int height, in
     }
   }
   if (!symmetric) return FC_ERR_UNSUPPORTED;
-  int rmax = 0, rmin = 1 << 30;
-  for (int l = 0; l < level_count; ++l) {
-    rmax = lens[l] / 2 > rmax ? lens[l] / 2 : rmax;
-    rmin = lens[l] / 2 < rmin ? lens[l] / 2 : rmin;
-  }
-  if (rmax <= 12 && rmin >= 1) {
-    // two levels per launch share the column pair sums (the default s = 2: radii 5 and 6 in one launch)
-    const double* q = tp;
-    for (int l = 0; l < level_count; l += 2) {
-      const int ra = lens[l] / 2, rb = l + 1 < level_count ? lens[l + 1] / 2 : 0;
-      const int rc = launch_mid_levels(base, batch, height, width, q, ra, q + lens[l], rb, out, level_count, l, st);
-      if (rc != FC_OK) return rc;
-      q += lens[l] + (l + 1 < level_count ? lens[l + 1] : 0);
-    }
-    return FC_OK;
-  }
   return launch_octave<double>(base, batch, height, width, level_count, tp, lens, 0, out, st);
 }
 
