@@ -235,7 +235,24 @@ class HarrisWorkload:
             return []
         h = float(np.mean([e[0].elapsed_time(e[1]) for e in self.ev[:n]]))
         lm = float(np.mean([e[1].elapsed_time(e[2]) for e in self.ev[:n]]))
-        return [("harris5_f32_kernel", alg, h, "hbm"), ("lambda5_packed_kernel (+ per-image max)", alg, lm, "hbm")]
+        out = [("harris5_f32_kernel", alg, h, "hbm"), ("lambda5_packed_kernel (+ per-image max)", alg, lm, "hbm")]
+        fast = self._lambda_fast_ms()
+        if fast:
+            out.append(("lambda5_packed_kernel<fast> (opt-in response mode, NOT part of `value`: exact integer determinant / "
+                        "larger eigenvalue, ~1e-15 relative to the default map)", alg, fast, "hbm"))
+        return out
+
+    def _lambda_fast_ms(self):
+        """the opt-in fast lambda-minus mode on the same batch, timed separately after the measured steps (CUDA events)"""
+        torch, c = self.torch, self.corners
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(4):
+            if i == 1:
+                ev[0].record()
+            c.lambda_minus(self.dev_in, None, compact=False, out=self.eig, fast=True)
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / 3
 
     def traffic(self, tr):
         """dram bytes per launch of the dominant kernel, from the committed ncu capture scaled to this launch"""

@@ -51,6 +51,7 @@ SIGNATURES = {
     "fc_harris_response": (_i, [_p, _i, _i, _i, _i, _d, _d, _p, _p, _p]),
     "fc_notebook_harris_response": (_i, [_p, _i, _i, _i, _i, _d, _p, _p]),
     "fc_lambda_minus_response": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "fc_lambda_minus_response_fast": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "fc_corner_response_ex": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _d, _i, _d, _p, _p, _p]),
     "fc_nms3x3_mask": (_i, [_p, _i, _i, _i, _d, _p, _p]),
     "fc_selftest_div25": (_i, [_p, _p]),

@@ -112,13 +112,16 @@ def notebook_harris(gray, window_size: int, k: float, threshold: float, compact:
 
 
 def lambda_minus(gray, threshold_percentage: float | None = 0.01, compact: bool = True,
-                 out: torch.Tensor | None = None) -> CornerResult:
-    """lambda-minus (min eigenvalue) map, per-image max, and map > pct * max."""
+                 out: torch.Tensor | None = None, fast: bool = False) -> CornerResult:
+    """lambda-minus (min eigenvalue) map, per-image max, and map > pct * max.
+    fast=True (opt-in): det / larger eigenvalue from exact 64-bit integer determinants instead of LAPACK's operation
+    sequence -- a few float64 ulps from the default map, not bit-identical (fc_lambda_minus_response_fast)."""
     g = _as_gray_batch(gray)
     b, h, w = g.shape
     eig = out if out is not None else torch.empty((b, h, w), dtype=torch.float64, device=g.device)
     image_max = torch.empty(b, dtype=torch.float64, device=g.device)
-    _lib.call("fc_lambda_minus_response", ptr(g), b, h, w, ptr(eig), ptr(image_max), stream_ptr())
+    _lib.call("fc_lambda_minus_response_fast" if fast else "fc_lambda_minus_response", ptr(g), b, h, w, ptr(eig), ptr(image_max),
+              stream_ptr())
     res = CornerResult(eig, image_max=image_max)
     if threshold_percentage is not None:
         res.mask = _new_mask(b, h, w, g.device)

@@ -349,9 +349,16 @@ __device__ __forceinline__ double exact_i32_to_f64(int n) {
   return __dsub_rn(__hiloint2double(0x43300000, n ^ (int)0x80000000), 4503601774854144.0);
 }
 
+// uint64 -> float64 with one rounding: exact halves, hi * 2^32 + lo in one fused operation
+__device__ __forceinline__ double u64_to_f64(unsigned long long n);
+
 // exact uint32 -> float64: bits of 2^52 + n, minus 2^52
 __device__ __forceinline__ double exact_u32_to_f64(uint32_t n) {
   return __dsub_rn(__hiloint2double(0x43300000, (int)n), 4503599627370496.0);
+}
+
+__device__ __forceinline__ double u64_to_f64(unsigned long long n) {
+  return __fma_rn(exact_u32_to_f64((uint32_t)(n >> 32)), 4294967296.0, exact_u32_to_f64((uint32_t)n));
 }
 
 // n / 25 correctly rounded for every integer |n| < 2^33 (what `sum / 25` gives in numpy): reciprocal multiply +
@@ -450,6 +457,8 @@ __device__ __forceinline__ int lam_lo(uint32_t p) {
 }
 __device__ __forceinline__ int lam_hi(uint32_t p) { return (int)(p + 0x8000u) >> 16; }         // high lane incl. the borrow
 
+// FAST: the opt-in response mode of fc_lambda_minus_response_fast (see there); false = LAPACK's arithmetic, bit for bit.
+template <bool FAST>
 __global__ void __launch_bounds__(kStripThreads, 4)
 lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_per_band, double* __restrict__ out,
                       unsigned long long* __restrict__ img_max_bits) {
@@ -598,6 +607,23 @@ lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_p
     const int r = hr - 2;  // rows r-2 .. r+2 are now summed
     if (r >= y0) {
       double res[4];
+      if constexpr (FAST) {
+        // smaller eigenvalue = det / larger eigenvalue with the determinant and the radicand of the larger one formed
+        // EXACTLY in 64-bit integers (Sxx Syy - Sxy^2 < 2^60, (Sxx - Syy)^2 + 4 Sxy^2 < 2^63), so the cancellation that
+        // makes the textbook formula lose digits on edges never happens: three roundings (two conversions, one square
+        // root) and one division separate the result from the exact value
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long sxy2 = (long long)Sxy[j] * (long long)Sxy[j];
+          const long long det = (long long)((unsigned long long)Sxx[j] * (unsigned long long)Syy[j]) - sxy2;
+          const long long d = (long long)Sxx[j] - (long long)Syy[j];
+          const unsigned long long rad = (unsigned long long)(d * d) + 4ull * (unsigned long long)sxy2;
+          const double R = rad ? sqrt_seq(u64_to_f64(rad)) : 0.0;  // isotropic window: both eigenvalues are Sxx / 25
+          const double den = __dadd_rn(exact_u32_to_f64(Sxx[j] + Syy[j]), R);  // 50 x the larger eigenvalue
+          const double num = __dmul_rn(u64_to_f64((unsigned long long)det), 0.08);  // 2 det / 25
+          res[j] = det > 0 ? div_seq(num, den, rcp_seq(den)) : 0.0;           // det > 0 implies den > 0
+        }
+      } else {
       double av[4], bv[4], cv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -613,6 +639,7 @@ lambda5_packed_kernel(const uint8_t* __restrict__ gray, int H, int W, int rows_p
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (lambda_needs_dsterf(av[j], bv[j], cv[j])) res[j] = dsterf_2x2_min_call(av[j], bv[j], cv[j]);
+      }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -951,8 +978,8 @@ extern "C" int fc_selftest_divsqrt(unsigned long long* mismatches, void* stream)
   return FC_OK;
 }
 
-extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int height, int width, double* eig,
-                                        double* image_max, void* stream) {
+static int launch_lambda_minus(const uint8_t* gray, int batch, int height, int width, double* eig, double* image_max,
+                               bool fast, void* stream) {
   if (bad_image_args(gray, batch, height, width) || !eig) return FC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* bits = reinterpret_cast<unsigned long long*>(image_max);
@@ -963,14 +990,20 @@ extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int heig
   }
   const bool aligned = (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(gray) & 3) == 0) &&
                        ((reinterpret_cast<uintptr_t>(eig) & 15) == 0);
+  if (fast && !aligned) return FC_ERR_UNSUPPORTED;
   if (aligned) {
     const int strips = div_up(width, kStripCols);
     int rows = 64;
     while (rows > 8 && (int64_t)strips * div_up(height, rows) * batch < 148 * 16) rows >>= 1;
     dim3 grid(div_up(strips, kStripWarps), div_up(height, rows), batch);
     const int hor_bytes = (int)(sizeof(uint4) * 10 * kStripThreads);
-    FC_CUDA_TRY(cudaFuncSetAttribute(lambda5_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hor_bytes));
-    lambda5_packed_kernel<<<grid, kStripThreads, hor_bytes, st>>>(gray, height, width, rows, eig, bits);
+    if (fast) {
+      FC_CUDA_TRY(cudaFuncSetAttribute(lambda5_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hor_bytes));
+      lambda5_packed_kernel<true><<<grid, kStripThreads, hor_bytes, st>>>(gray, height, width, rows, eig, bits);
+    } else {
+      FC_CUDA_TRY(cudaFuncSetAttribute(lambda5_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hor_bytes));
+      lambda5_packed_kernel<false><<<grid, kStripThreads, hor_bytes, st>>>(gray, height, width, rows, eig, bits);
+    }
     note_launch();
     FC_RETURN_IF_LAUNCH_FAILED();
   } else {
@@ -983,6 +1016,16 @@ extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int heig
     FC_RETURN_IF_LAUNCH_FAILED();
   }
   return FC_OK;
+}
+
+extern "C" int fc_lambda_minus_response(const uint8_t* gray, int batch, int height, int width, double* eig,
+                                        double* image_max, void* stream) {
+  return launch_lambda_minus(gray, batch, height, width, eig, image_max, false, stream);
+}
+
+extern "C" int fc_lambda_minus_response_fast(const uint8_t* gray, int batch, int height, int width, double* eig,
+                                             double* image_max, void* stream) {
+  return launch_lambda_minus(gray, batch, height, width, eig, image_max, true, stream);
 }
 
 static int launch_threshold(const double* map, int B, int H, int W, double thr, double frac, const double* image_max,

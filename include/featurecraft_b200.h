@@ -120,6 +120,13 @@ FC_API int fc_nms3x3_mask(const double* response, int batch, int height, int wid
  * threshold = pct * max, :440). */
 FC_API int fc_lambda_minus_response(const uint8_t* gray, int batch, int height, int width, double* eig,
                              double* image_max, void* stream);
+/* Opt-in fast form of the same map (default OFF everywhere; north_star's bar for responses is 1e-4 relative): the smaller
+ * eigenvalue as det / larger eigenvalue, with the determinant Sxx Syy - Sxy^2 and the radicand (Sxx - Syy)^2 + 4 Sxy^2 of
+ * the integer window sums formed exactly in 64-bit integers, so no cancellation occurs: agrees with
+ * fc_lambda_minus_response to a few float64 ulps (tests: <= 1e-13 relative) but not bit for bit, at about half the
+ * float64 work.  Needs width % 4 == 0 and the alignments of the fast path (FC_ERR_UNSUPPORTED otherwise). */
+FC_API int fc_lambda_minus_response_fast(const uint8_t* gray, int batch, int height, int width, double* eig,
+                                         double* image_max, void* stream);
 
 /* Device self-test: counts the integers |n| <= 2^33 for which the division-free n/25 used by the lambda-minus
  * kernel differs from IEEE division (must be 0).  mismatches: one device uint64. */

@@ -105,6 +105,38 @@ def test_lambda_minus_vs_oracle(fc, shape):
     assert np.array_equal(res.coords.cpu().numpy(), np.stack([rows, cols], 1))
 
 
+@pytest.mark.parametrize("kind", ["corners", "noise", "edges", "flat"])
+def test_lambda_minus_fast_mode_is_within_ulps_of_the_exact_map(fc, kind):
+    """The opt-in fast response (exact 64-bit integer determinant / larger eigenvalue) against the default LAPACK-exact
+    map: north_star asks 1e-4 relative on responses; the fast map is within a few float64 ulps -- also on pure edges,
+    where the textbook formula loses every digit, and exactly 0 where the exact map is 0.  Default stays the exact kernel."""
+    rng = np.random.default_rng(7)
+    h, w = 192, 256
+    if kind == "corners":
+        gray = fc.synthetic.corner_image(h, w, seed=4)
+    elif kind == "noise":
+        gray = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    elif kind == "edges":
+        gray = np.zeros((h, w), np.uint8)
+        gray[:, w // 2:] = 255       # one vertical step edge: rank-1 structure tensors, lambda_min = 0 exactly
+        gray[h // 3, :] = 90         # and a horizontal line crossing it
+    else:
+        gray = np.full((h, w), 37, np.uint8)
+    exact = fc.corners.lambda_minus(gray, None).response[0].cpu().numpy()
+    fast = fc.corners.lambda_minus(gray, None, fast=True).response[0].cpu().numpy()
+    assert np.array_equal(exact, O.lambda_minus_response(gray))  # the default did not change
+    assert np.isfinite(fast).all() and (fast >= 0).all()
+    scale = np.maximum(np.abs(exact), 1e-300)
+    big = np.abs(exact) > 1e-9 * max(exact.max(), 1e-300)
+    if big.any():
+        assert (np.abs(fast - exact)[big] / scale[big]).max() < 1e-13
+    # where the exact map is (numerically) zero the fast one is zero or as tiny: never a spurious corner
+    assert np.abs(fast - exact)[~big].max(initial=0.0) <= 1e-9 * max(exact.max(), 1.0)
+    # the thresholded corner sets agree
+    if exact.max() > 0:
+        assert np.array_equal(fast > 0.01 * fast.max(), exact > 0.01 * exact.max())
+
+
 def test_eig2x2_device_matches_lapack_golden(fc):
     """dsterf/dlae2 restatement on the adversarial golden set, through lambda-minus-free entry: the
     same device function is exercised via structured images above; here the map-level invariant:
