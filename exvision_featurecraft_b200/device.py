@@ -74,10 +74,12 @@ def read_last_ints(tensors) -> list:
     return [int(v) for v in host[: len(tensors)].tolist()]
 
 
-def read_ints_at(t: torch.Tensor, indices, *more) -> list:
+def read_ints_at(t: torch.Tensor, indices, *more, between=None) -> list:
     """[int(t[i]) for i in indices] (int32 CUDA tensor) with one kernel launch per 32 indices and ONE host
     synchronisation: the values are gathered into pinned host memory by a kernel (see read_int).  Further
-    (tensor, indices) pairs may follow; their values are appended, still under the single synchronisation."""
+    (tensor, indices) pairs may follow; their values are appended, still under the single synchronisation.
+    between: called after the event is recorded and before the host waits for it -- work queued there (kernels that do
+    not need the values) keeps the device busy across the host round trip."""
     jobs = [(t, list(indices))] + [(a, list(b)) for a, b in zip(more[0::2], more[1::2])]
     n = sum(len(ix) for _, ix in jobs)
     assert n > 0
@@ -98,6 +100,8 @@ def read_ints_at(t: torch.Tensor, indices, *more) -> list:
                       stream_ptr())
             at += len(part)
     ev.record()
+    if between is not None:
+        between()
     ev.synchronize()
     return [int(v) for v in host[:n].tolist()]
 

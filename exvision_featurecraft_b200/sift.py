@@ -692,10 +692,18 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
                       ptr(counts[row_start[i]:]), stream_ptr())
         row_offs = torch.empty(row_start[-1] + 1, dtype=torch.int32, device=dev)
         _lib.call("fc_exclusive_scan_i32", ptr(counts), row_start[-1], ptr(row_offs), ptr(scan_scratch(row_start[-1])), stream_ptr())
-        if certified:
-            got = read_ints_at(row_offs, row_start[1:], amb_dev, range(n_extra))
-        else:
-            got = read_ints_at(row_offs, row_start[1:])
+    # the gradient code planes need no counts: queued behind the scan, they run while the host waits for the counts
+    codes_of = {}
+
+    def queue_codes():
+        with _stage("gradient_field"):
+            for i, (o, k) in enumerate(work):
+                codes_of[i] = gradient_codes(companions[o].mid, k - 1)
+
+    if certified:
+        got = read_ints_at(row_offs, row_start[1:], amb_dev, range(n_extra), between=queue_codes)
+    else:
+        got = read_ints_at(row_offs, row_start[1:])
     kp_end, amb_counts = got[:len(work)], got[len(work):]  # cumulative keypoint count after each block
     if certified and any(c > m.amb_cap for c, m in zip(amb_counts, companions)):
         # more undecided pixels than the list holds (large exactly-flat regions): the float64 kernels decide everything
@@ -729,8 +737,7 @@ def detect_and_describe(base, params: SiftParams = SiftParams(), out_dtype=torch
         sigma = keypoint_sigma(params.sigma_base, o, k, params.s_value)
         if certified:
             mid = companions[o].mid
-            with _stage("gradient_field"):
-                codes = gradient_codes(mid, k - 1)
+            codes = codes_of[i]
             with _stage("orientation"):
                 orientation_bins_certified(mid, k - 1, codes, kps, n, sigma, bin_mask_all[kp_start[i]:kp_end[i]],
                                            recheck_all[kp_start[i]:kp_end[i]], recheck_counts[i:i + 1],
