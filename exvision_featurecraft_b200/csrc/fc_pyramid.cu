@@ -1179,7 +1179,8 @@ static constexpr size_t kMidSmem = sizeof(double) * (size_t)(2 * kMTY * kMP);
 // MR = radius class (halo of the tile: 128 - 2 MR output columns), RA / RB = radii the two levels are evaluated with
 // (<= MR; the tap table is zero beyond a level's true radius, and a zero tap adds an exact zero, so the values are those
 // of the level's own radius); RB = 0: one level only.  ROWS = output rows per vertical item (column segment of
-// ROWS + 2 MR values in registers).  The default levels are <6, 5, 6>; the other points of the UI ranges (sigma 1.6 .. 3,
+// ROWS + 2 MR values in registers: 16 rows for the smallest class -- 28 loads per 16 outputs instead of 20 per 8 --, 8 or
+// 4 where the halo would not fit the register file).  The default levels are <6, 5, 6>; the other points of the UI ranges (sigma 1.6 .. 3,
 // s 2 .. 5: radii of the levels 1 .. s between 5 and 12) run in the classes MR = 6, 8, 10, 12, two levels per launch.
 template <int MR, int RA, int RB, int ROWS, int MINB>
 __global__ void __launch_bounds__(256, MINB)
@@ -1295,9 +1296,9 @@ static int launch_mid_levels(const double* base, int B, int H, int W, const doub
     mt.t[1][k] = (rb > 0 && k <= rb) ? taps_b[rb + k] : 0.0;
   }
   const int rm = ra > rb ? ra : rb;
-  if (ra == 5 && rb == 6) return launch_mid_f64<6, 5, 6, 8, 3>(base, B, H, W, mt, out, n_planes, plane0, st);
+  if (ra == 5 && rb == 6) return launch_mid_f64<6, 5, 6, 16, 2>(base, B, H, W, mt, out, n_planes, plane0, st);
 #define FC_MID(MRC, ROWS, MINB)                                                                                     return rb > 0 ? launch_mid_f64<MRC, MRC, MRC, ROWS, MINB>(base, B, H, W, mt, out, n_planes, plane0, st)                          : launch_mid_f64<MRC, MRC, 0, ROWS, MINB>(base, B, H, W, mt, out, n_planes, plane0, st)
-  if (rm <= 6) FC_MID(6, 8, 3);
+  if (rm <= 6) FC_MID(6, 16, 2);
   if (rm <= 8) FC_MID(8, 8, 2);
   if (rm <= 10) FC_MID(10, 4, 2);
   if (rm <= 12) FC_MID(12, 4, 2);
