@@ -47,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    # the link step gets the same target: without it nvcc adds an (empty) device image for its default architecture
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 
