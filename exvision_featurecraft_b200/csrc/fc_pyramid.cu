@@ -414,16 +414,23 @@ struct ExsMid {  // what a row needs when it is the centre row
   float c[ND - 2][4];                      // DoG_k at the lane's 4 pixels
 };
 
-template <int ND>
-__device__ __forceinline__ void exs_stage_row(const float* __restrict__ g, size_t plane, int H, int W, int yy, int x,
-                                              int strip_c0, float* __restrict__ slot, int lane) {
+// G = float or double: element type of the Gaussian stack (and of the ring).  float64 stacks (the float64 mode) take the
+// same kernel: the cheap 26-neighbour rejection runs on the float32 ROUNDINGS of the float64 DoG values -- rounding is
+// monotonic, so a centre that is strictly above (below) all rounded neighbours is strictly above (below) them in float64
+// too, and one that is not above (below) them in float32 cannot be in float64 -- and whatever is left (rounded ties
+// included) takes the exact float64 test.
+template <int ND, typename G>
+__device__ __forceinline__ void exs_stage_row(const G* __restrict__ g, size_t plane, int H, int W, int yy, int x,
+                                              int strip_c0, G* __restrict__ slot, int lane) {
   const int row = min(max(yy, 0), H - 1);
-  const float* src = g + (size_t)row * W;
+  const G* src = g + (size_t)row * W;
   if (x < W) {
 #pragma unroll
     for (int l = 0; l <= ND; ++l) {
       const uint32_t d = (uint32_t)__cvta_generic_to_shared(slot + l * kExsPitch + 4 + 4 * lane);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + l * plane + x) : "memory");
+      if constexpr (sizeof(G) == 8)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(src + l * plane + x + 2) : "memory");
     }
   }
   if (lane == 0 || lane == 31) {
@@ -431,28 +438,25 @@ __device__ __forceinline__ void exs_stage_row(const float* __restrict__ g, size_
     const int hc = lane == 0 ? max(strip_c0 - 1, 0) : min(strip_c0 + 128, W - 1);
     const int di = lane == 0 ? 3 : 132;
 #pragma unroll
-    for (int l = 0; l <= ND; ++l) {
-      const uint32_t d = (uint32_t)__cvta_generic_to_shared(slot + l * kExsPitch + di);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + l * plane + hc) : "memory");
-    }
+    for (int l = 0; l <= ND; ++l) cp_async_elem<G>(slot + l * kExsPitch + di, src + l * plane + hc);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // exact rule on the 3x3x3 block around (y, x, k), read from the Gaussian stack in global memory
-template <int ND>
-__device__ __noinline__ bool exs_exact(const float* __restrict__ g, size_t plane, int W, int y, int x, int k, int filter,
+template <int ND, typename G>
+__device__ __noinline__ bool exs_exact(const G* __restrict__ g, size_t plane, int W, int y, int x, int k, int filter,
                                        double contrast_th, double ratio_th) {
-  float dv[3][3][3];  // [di][dj][level k-1..k+1]
+  G dv[3][3][3];  // [di][dj][level k-1..k+1]
 #pragma unroll
   for (int di = 0; di < 3; ++di)
 #pragma unroll
     for (int dj = 0; dj < 3; ++dj) {
-      const float* p = g + (size_t)(k - 1) * plane + (size_t)(y - 1 + di) * W + (x - 1 + dj);
-      const float g0 = p[0], g1 = p[plane], g2 = p[2 * plane], g3 = p[3 * plane];
+      const G* p = g + (size_t)(k - 1) * plane + (size_t)(y - 1 + di) * W + (x - 1 + dj);
+      const G g0 = p[0], g1 = p[plane], g2 = p[2 * plane], g3 = p[3 * plane];
       dv[di][dj][0] = g1 - g0; dv[di][dj][1] = g2 - g1; dv[di][dj][2] = g3 - g2;
     }
-  const float c = dv[1][1][1];
+  const G c = dv[1][1][1];
   bool is_max = true, is_min = true;
 #pragma unroll
   for (int di = 0; di < 3; ++di)
@@ -461,7 +465,7 @@ __device__ __noinline__ bool exs_exact(const float* __restrict__ g, size_t plane
 #pragma unroll
       for (int dk = 0; dk < 3; ++dk) {
         const int flat = di * 9 + dj * 3 + dk;
-        const float a = dv[di][dj][dk];
+        const G a = dv[di][dj][dk];
         // entries before the centre (flat index < 13): strict; after: non-strict (the first extremum wins)
         if (flat < 13) { is_max &= c > a; is_min &= c < a; }
         else if (flat > 13) { is_max &= c >= a; is_min &= c <= a; }
@@ -472,7 +476,7 @@ __device__ __noinline__ bool exs_exact(const float* __restrict__ g, size_t plane
     const int ci = 2 * k - 1;
     double contrast = 0.0;
     if (ci < ND) {
-      const float* p = g + (size_t)ci * plane + (size_t)y * W + x;
+      const G* p = g + (size_t)ci * plane + (size_t)y * W + x;
       contrast = (double)(p[plane] - p[0]);
     }
     const double c0 = (double)c;
@@ -494,32 +498,41 @@ __device__ __noinline__ bool exs_exact(const float* __restrict__ g, size_t plane
 // (`old`, `nw`).  M = max over the 26 neighbours: c > M is a unique maximum (argmax == 13), c < M is no maximum,
 // c == M is a tie whose outcome depends on the position of the equal neighbour -> exact path (rare; an all-equal
 // neighbourhood, c == M == m, is decided here: the first of 27 equal values wins, not the centre).
-template <int ND, bool CERT>
+template <int ND, bool CERT, typename G>
 __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const ExsRow<ND>& old, bool emit,
-                                         const float* __restrict__ g, size_t plane, int B, int b, int H, int W, int yy,
-                                         int x, int strip_c0, float* __restrict__ ring, int& slot, int stage_row, int filter,
+                                         const G* __restrict__ g, size_t plane, int B, int b, int H, int W, int yy,
+                                         int x, int strip_c0, G* __restrict__ ring, int& slot, int stage_row, int filter,
                                          double contrast_th, double ratio_th, uint32_t*& out_p, size_t out_kstride, int pitch,
                                          bool writer, uint32_t colmask, int lane, const ExsCert& cert) {
   asm volatile("cp.async.wait_group %0;" ::"n"(kExsRows - 2) : "memory");
   __syncwarp();
-  const float* srow = ring + slot * ((ND + 1) * kExsPitch) + 4 * lane;
-  float D[ND][6];
+  const G* srow = ring + slot * ((ND + 1) * kExsPitch) + 4 * lane;
+  float D[ND][6];  // float64 stacks: the DoG value is formed in float64 and rounded once (monotonic)
   {
-    float prev[6];
+    G prev[6];
 #pragma unroll
     for (int l = 0; l <= ND; ++l) {
-      const float4 v = *reinterpret_cast<const float4*>(srow + l * kExsPitch + 4);
-      const float cur[6] = {srow[l * kExsPitch + 3], v.x, v.y, v.z, v.w, srow[l * kExsPitch + 8]};
+      G cur[6];
+      cur[0] = srow[l * kExsPitch + 3];
+      if constexpr (sizeof(G) == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(srow + l * kExsPitch + 4);
+        cur[1] = v.x; cur[2] = v.y; cur[3] = v.z; cur[4] = v.w;
+      } else {
+        const double2 v0 = *reinterpret_cast<const double2*>(srow + l * kExsPitch + 4);
+        const double2 v1 = *reinterpret_cast<const double2*>(srow + l * kExsPitch + 6);
+        cur[1] = v0.x; cur[2] = v0.y; cur[3] = v1.x; cur[4] = v1.y;
+      }
+      cur[5] = srow[l * kExsPitch + 8];
       if (l > 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) D[l - 1][i] = cur[i] - prev[i];
+        for (int i = 0; i < 6; ++i) D[l - 1][i] = (float)(cur[i] - prev[i]);
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) prev[i] = cur[i];
     }
   }
   // refill the slot that held row yy-1 (every lane passed the barrier above after reading it) with row yy+3
-  exs_stage_row<ND>(g, plane, H, W, stage_row, x, strip_c0, ring + ((slot + kExsRows - 1) & (kExsRows - 1)) * ((ND + 1) * kExsPitch), lane);
+  exs_stage_row<ND, G>(g, plane, H, W, stage_row, x, strip_c0, ring + ((slot + kExsRows - 1) & (kExsRows - 1)) * ((ND + 1) * kExsPitch), lane);
   slot = (slot + 1) & (kExsRows - 1);
   ExsMid<ND> cur;  // the newest row's centre-row quantities, needed one step from now
 #pragma unroll
@@ -588,7 +601,9 @@ __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const 
           const float m = min3_t<float>(old.emin[k - 1][j], mid.nmin[k - 1][j], nw.emin[k - 1][j]);
           const float c = mid.c[k - 1][j];
           const bool strict = c > M || c < m;
-          const bool flat = c == M && c == m;  // all 27 equal: the first one wins, not the centre
+          // all 27 equal: the first one wins, not the centre -- decided here for float32 stacks; equal ROUNDINGS of a
+          // float64 stack say nothing about the float64 values, so those go to the exact test like any other tie
+          const bool flat = sizeof(G) == 4 && c == M && c == m;
           if (!strict) {
             nib &= ~(1u << j);
             if (!flat) slow |= cand & (1u << j);
@@ -598,7 +613,7 @@ __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const 
         while (slow) {
           const int j = __ffs(slow) - 1;
           slow &= slow - 1;
-          if (exs_exact<ND>(g, plane, W, y, x + j, k, filter, contrast_th, ratio_th)) nib |= 1u << j;
+          if (exs_exact<ND, G>(g, plane, W, y, x + j, k, filter, contrast_th, ratio_th)) nib |= 1u << j;
         }
         __syncwarp();
       }
@@ -613,9 +628,9 @@ __device__ __forceinline__ void exs_step(ExsRow<ND>& nw, ExsMid<ND>& mid, const 
   mid = cur;
 }
 
-template <int ND, bool CERT>
-__global__ void __launch_bounds__(kExsWarps * 32, 3)
-extrema_strip_kernel(const float* __restrict__ gauss, int B, int H, int W, int rows_per_band, int filter,
+template <int ND, bool CERT, typename G>
+__global__ void __launch_bounds__(kExsWarps * 32, sizeof(G) == 4 ? 3 : 2)
+extrema_strip_kernel(const G* __restrict__ gauss, int B, int H, int W, int rows_per_band, int filter,
                      double contrast_th, double ratio_th, uint32_t* __restrict__ extrema, int pitch,
                      const float* __restrict__ value_bound, float eps_rel, int4* __restrict__ amb, int amb_cap,
                      int* __restrict__ amb_count) {
@@ -624,20 +639,22 @@ extrema_strip_kernel(const float* __restrict__ gauss, int B, int H, int W, int r
   cert.amb = amb;
   cert.amb_cap = amb_cap;
   cert.amb_count = amb_count;
-  extern __shared__ __align__(16) float exs_ring[];  // [warp][kExsRows][ND + 1][kExsPitch]
+  static_assert(!CERT || sizeof(G) == 4, "the certified search runs on float32 stacks");
+  extern __shared__ __align__(16) unsigned char exs_ring_raw[];  // [warp][kExsRows][ND + 1][kExsPitch] of G
+  G* exs_ring = reinterpret_cast<G*>(exs_ring_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip_c0 = (blockIdx.x * kExsWarps + warp) * 128;
   if (strip_c0 >= W) return;  // warp-uniform; the kernel has no block-wide barrier
   const int x = strip_c0 + 4 * lane;
   const int b = blockIdx.z;
   const size_t plane = (size_t)H * W;
-  const float* g = gauss + (size_t)b * (ND + 1) * plane;
+  const G* g = gauss + (size_t)b * (ND + 1) * plane;
   const int y0 = blockIdx.y * rows_per_band;
   const int y1 = min(y0 + rows_per_band, H);
-  float* ring = exs_ring + warp * (kExsRows * (ND + 1) * kExsPitch);
+  G* ring = exs_ring + warp * (kExsRows * (ND + 1) * kExsPitch);
   // rows y0-1 .. y1 are walked; row yy is staged three steps before it is consumed
 #pragma unroll
-  for (int i = 0; i < kExsRows - 1; ++i) exs_stage_row<ND>(g, plane, H, W, y0 - 1 + i, x, strip_c0, ring + i * ((ND + 1) * kExsPitch), lane);
+  for (int i = 0; i < kExsRows - 1; ++i) exs_stage_row<ND, G>(g, plane, H, W, y0 - 1 + i, x, strip_c0, ring + i * ((ND + 1) * kExsPitch), lane);
   int slot = 0;
   ExsRow<ND> R0, R1, R2;
   ExsMid<ND> mid;
@@ -649,7 +666,7 @@ extrema_strip_kernel(const float* __restrict__ gauss, int B, int H, int W, int r
   const size_t out_kstride = (size_t)B * H * pitch;                      // words between the masks of k and k+1
   uint32_t* out_p = extrema + ((size_t)b * H + y0) * pitch + (x >> 5);  // mask word of (k = 1, row y0, this lane group)
 #define FC_EXS(NW, OLD) \
-  exs_step<ND, CERT>(NW, mid, OLD, yy >= y0 + 1, g, plane, B, b, H, W, yy, x, strip_c0, ring, slot, yy + kExsRows - 1, filter, contrast_th, ratio_th, out_p, out_kstride, pitch, writer, colmask, lane, cert)
+  exs_step<ND, CERT, G>(NW, mid, OLD, yy >= y0 + 1, g, plane, B, b, H, W, yy, x, strip_c0, ring, slot, yy + kExsRows - 1, filter, contrast_th, ratio_th, out_p, out_kstride, pitch, writer, colmask, lane, cert)
   // the full-slice maxima of three consecutive rows rotate through R0, R1, R2 without moving a register
   for (;;) {
     FC_EXS(R0, R1); if (++yy > y1) break;
@@ -1511,18 +1528,18 @@ static int launch_extrema_nd(const void* gauss, int B, int H, int W, int is_dog,
   return FC_OK;
 }
 
-template <int ND, bool CERT>
+template <int ND, bool CERT, typename G = float>
 static int launch_extrema_strip(const void* gauss, int B, int H, int W, int filter, double cth, double rth, uint32_t* extrema,
                                 cudaStream_t st, const CertArgs& ca = CertArgs()) {
   const int pitch = div_up(W, 32);
-  const size_t smem = sizeof(float) * kExsWarps * kExsRows * (ND + 1) * kExsPitch;
-  auto kern = extrema_strip_kernel<ND, CERT>;
+  const size_t smem = sizeof(G) * kExsWarps * kExsRows * (ND + 1) * kExsPitch;
+  auto kern = extrema_strip_kernel<ND, CERT, G>;
   FC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int strips = div_up(W, 128);
   int rows = 64;  // band height: amortise the two halo rows, but keep enough warps in flight on small inputs
   while (rows > 8 && (int64_t)strips * div_up(H, rows) * B < 148 * 12) rows >>= 1;
   dim3 grid(div_up(strips, kExsWarps), div_up(H, rows), B);
-  kern<<<grid, kExsWarps * 32, smem, st>>>((const float*)gauss, B, H, W, rows, filter, cth, rth, extrema, pitch,
+  kern<<<grid, kExsWarps * 32, smem, st>>>((const G*)gauss, B, H, W, rows, filter, cth, rth, extrema, pitch,
                                            ca.value_bound, ca.eps_rel, ca.amb, ca.amb_cap, ca.amb_count);
   note_launch();
   FC_RETURN_IF_LAUNCH_FAILED();
@@ -1533,12 +1550,10 @@ template <typename T>
 static int launch_extrema(const void* gauss, int B, int H, int W, int L, int is_dog, int filter, double cth, double rth,
                           uint32_t* extrema, cudaStream_t st) {
   const int nd = is_dog ? L : L - 1;
-  if constexpr (sizeof(T) == 4) {
-    if (!is_dog && W % 4 == 0 && H >= 3 && (reinterpret_cast<uintptr_t>(gauss) & 15) == 0) {
-      if (nd == 4) return launch_extrema_strip<4, false>(gauss, B, H, W, filter, cth, rth, extrema, st);
-      if (nd == 3) return launch_extrema_strip<3, false>(gauss, B, H, W, filter, cth, rth, extrema, st);
-      if (nd == 5) return launch_extrema_strip<5, false>(gauss, B, H, W, filter, cth, rth, extrema, st);
-    }
+  if (!is_dog && W % 4 == 0 && H >= 3 && (reinterpret_cast<uintptr_t>(gauss) & 15) == 0) {
+    if (nd == 4) return launch_extrema_strip<4, false, T>(gauss, B, H, W, filter, cth, rth, extrema, st);
+    if (nd == 3) return launch_extrema_strip<3, false, T>(gauss, B, H, W, filter, cth, rth, extrema, st);
+    if (nd == 5) return launch_extrema_strip<5, false, T>(gauss, B, H, W, filter, cth, rth, extrema, st);
   }
   switch (nd) {
     case 3: return launch_extrema_nd<T, 3>(gauss, B, H, W, is_dog, filter, cth, rth, extrema, st);
